@@ -1,0 +1,201 @@
+"""Flat structure-of-arrays buffers that cross the C-ABI (include/smc_b200.h: smc_reads_soa, smc_loci).
+
+One entry per BAM record, in BAM (coordinate) order -- the index of a read IS its pileup order, which the
+reference's fragment merge depends on (smCounter.py:467-479).  Per-read identity fields replace the
+qname parsing at smCounter.py:319-325: ``umi`` is an injective 64-bit code of the barcode string and
+``frag_id`` the dictionary id of (barcode, readid), assigned in order of first appearance in the BAM.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# BAM 4-bit base codes ("=ACMGRSVTWYHKDBN")
+NT16 = "=ACMGRSVTWYHKDBN"
+_NT16_LUT = np.full(256, 15, dtype=np.uint8)
+for _i, _c in enumerate(NT16):
+    _NT16_LUT[ord(_c)] = _i
+    _NT16_LUT[ord(_c.lower())] = _i
+_NT16_CHARS = np.frombuffer(NT16.encode(), dtype=np.uint8)
+
+CIGAR_OPS = "MIDNSHP=X"
+
+
+@dataclass
+class ReadsSoA:
+    ref_id: np.ndarray      # int32   contig index into ``chroms``
+    pos: np.ndarray         # int32   0-based leftmost reference position
+    flag: np.ndarray        # uint16  BAM flag (0x10 reverse, 0x40 read1, 0x80 read2, 0x4 unmapped)
+    mapq: np.ndarray        # uint8
+    nm: np.ndarray          # int32   NM tag, 0 if absent (smCounter.py:329-334)
+    l_seq: np.ndarray       # int32   query length incl. soft clips
+    seq_off: np.ndarray     # int64   byte offset of the read's packed bases in ``seq``
+    qual_off: np.ndarray    # int64   byte offset of the read's qualities in ``qual``
+    cigar_off: np.ndarray   # int64   index of the read's first CIGAR word in ``cigar``
+    n_cigar: np.ndarray     # uint16
+    umi: np.ndarray         # uint64  injective barcode code
+    frag_id: np.ndarray     # uint32  (barcode, readid) id, first-appearance order
+    seq: np.ndarray         # uint8   4-bit BAM nibbles, high nibble first, each read byte-aligned
+    qual: np.ndarray        # uint8   phred
+    cigar: np.ndarray       # uint32  len<<4 | op
+    chroms: list = field(default_factory=list)
+    umi_names: dict | None = None   # optional code -> barcode string (host side only)
+
+    @property
+    def n(self) -> int:
+        return int(self.ref_id.shape[0])
+
+    def nbytes(self) -> int:
+        return sum(getattr(self, f).nbytes for f in
+                   ("ref_id", "pos", "flag", "mapq", "nm", "l_seq", "seq_off", "qual_off", "cigar_off", "n_cigar",
+                    "umi", "frag_id", "seq", "qual", "cigar"))
+
+    def select(self, idx: np.ndarray) -> "ReadsSoA":
+        """Sub-batch with the reads ``idx`` (ascending), variable-length payloads re-packed."""
+        idx = np.asarray(idx, dtype=np.int64)
+        l_seq = self.l_seq[idx].astype(np.int64)
+        sb = (l_seq + 1) // 2
+        nc = self.n_cigar[idx].astype(np.int64)
+        new_seq_off = np.concatenate(([0], np.cumsum(sb)))[:-1]
+        new_qual_off = np.concatenate(([0], np.cumsum(l_seq)))[:-1]
+        new_cig_off = np.concatenate(([0], np.cumsum(nc)))[:-1]
+
+        def gather(src, offs, lens):
+            tot = int(lens.sum())
+            if tot == 0:
+                return np.zeros(0, dtype=src.dtype)
+            starts = np.repeat(offs - np.concatenate(([0], np.cumsum(lens)))[:-1], lens)
+            return src[starts + np.arange(tot, dtype=np.int64)]
+
+        return ReadsSoA(
+            ref_id=self.ref_id[idx], pos=self.pos[idx], flag=self.flag[idx], mapq=self.mapq[idx], nm=self.nm[idx],
+            l_seq=self.l_seq[idx], seq_off=new_seq_off, qual_off=new_qual_off, cigar_off=new_cig_off,
+            n_cigar=self.n_cigar[idx], umi=self.umi[idx], frag_id=self.frag_id[idx],
+            seq=gather(self.seq, self.seq_off[idx], sb), qual=gather(self.qual, self.qual_off[idx], l_seq),
+            cigar=gather(self.cigar, self.cigar_off[idx], nc), chroms=self.chroms, umi_names=self.umi_names)
+
+    def ref_end(self) -> np.ndarray:
+        """0-based exclusive reference end of every read (host-side helper for sharding)."""
+        ops = self.cigar & 0xF
+        lens = (self.cigar >> 4).astype(np.int64)
+        consumes = np.isin(ops, (0, 2, 3, 7, 8))
+        w = np.where(consumes, lens, 0)
+        cs = np.concatenate(([0], np.cumsum(w)))
+        a = self.cigar_off
+        b = self.cigar_off + self.n_cigar.astype(np.int64)
+        return (self.pos.astype(np.int64) + cs[b] - cs[a]).astype(np.int64)
+
+
+@dataclass
+class Loci:
+    """Unique target positions, sorted by (ref_id, pos0) -- include/smc_b200.h: smc_loci."""
+    ref_id: np.ndarray      # int32
+    pos0: np.ndarray        # int32  0-based
+    ref_base: np.ndarray    # uint8  ASCII upper-case reference base (smCounter.py:311-313)
+
+    @property
+    def n(self) -> int:
+        return int(self.ref_id.shape[0])
+
+
+def umi_code(bc: str, table: dict) -> int:
+    """Injective 64-bit code for a barcode string: 2-bit pack with a length sentinel when the barcode is
+    <= 31 nt of ACGT, else a dictionary id with the top bit set."""
+    if len(bc) <= 31:
+        v = 1
+        for ch in bc:
+            k = "ACGT".find(ch)
+            if k < 0:
+                break
+            v = (v << 2) | k
+        else:
+            return v
+    key = ("#", bc)
+    if key not in table:
+        table[key] = (1 << 63) | len(table)
+    return table[key]
+
+
+def umi_string(code: int, names: dict | None = None) -> str:
+    if names is not None and code in names:
+        return names[code]
+    if code >> 63:
+        return "U%x" % (code & ((1 << 63) - 1))
+    s = []
+    while code > 1:
+        s.append("ACGT"[code & 3])
+        code >>= 2
+    return "".join(reversed(s))
+
+
+def pack_seq(seq: str) -> np.ndarray:
+    codes = _NT16_LUT[np.frombuffer(seq.encode(), dtype=np.uint8)]
+    if len(codes) & 1:
+        codes = np.concatenate((codes, np.zeros(1, dtype=np.uint8)))
+    return ((codes[0::2] << 4) | codes[1::2]).astype(np.uint8)
+
+
+def records_to_soa(records, chroms=None) -> ReadsSoA:
+    """Build the SoA from pysam-free records (qname chrom pos flag mapq nm cigar seq qual), BAM order.
+
+    Restates the identity parsing of smCounter.py:319-325: ``readid = ':'.join(parts[:-2])``, ``BC = parts[-2]``.
+    """
+    if chroms is None:
+        chroms = []
+        for r in records:
+            if r.chrom not in chroms:
+                chroms.append(r.chrom)
+    cidx = {c: i for i, c in enumerate(chroms)}
+    n = len(records)
+    ref_id = np.zeros(n, np.int32); pos = np.zeros(n, np.int32); flag = np.zeros(n, np.uint16)
+    mapq = np.zeros(n, np.uint8); nm = np.zeros(n, np.int32); l_seq = np.zeros(n, np.int32)
+    seq_off = np.zeros(n, np.int64); qual_off = np.zeros(n, np.int64); cigar_off = np.zeros(n, np.int64)
+    n_cigar = np.zeros(n, np.uint16); umi = np.zeros(n, np.uint64); frag_id = np.zeros(n, np.uint32)
+    seqs, quals, cigs = [], [], []
+    so = qo = co = 0
+    umitab, fragtab, names = {}, {}, {}
+    for i, r in enumerate(records):
+        parts = r.qname.split(":")
+        bc = parts[-2]
+        readid = ":".join(parts[:-2])
+        code = umi_code(bc, umitab)
+        names[code] = bc
+        fk = (bc, readid)
+        if fk not in fragtab:
+            fragtab[fk] = len(fragtab)
+        ref_id[i] = cidx[r.chrom]; pos[i] = r.pos; flag[i] = r.flag; mapq[i] = r.mapq
+        nm[i] = 0 if r.nm is None else r.nm
+        l_seq[i] = len(r.seq); seq_off[i] = so; qual_off[i] = qo; cigar_off[i] = co; n_cigar[i] = len(r.cigar)
+        umi[i] = code; frag_id[i] = fragtab[fk]
+        ps = pack_seq(r.seq)
+        seqs.append(ps); so += len(ps)
+        quals.append(np.asarray(r.qual, dtype=np.uint8)); qo += len(r.seq)
+        cigs.append(np.asarray([(l << 4) | op for (op, l) in r.cigar], dtype=np.uint32)); co += len(r.cigar)
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+    return ReadsSoA(ref_id, pos, flag, mapq, nm, l_seq, seq_off, qual_off, cigar_off, n_cigar, umi, frag_id,
+                    cat(seqs, np.uint8), cat(quals, np.uint8), cat(cigs, np.uint32), list(chroms), names)
+
+
+def soa_to_records(soa: ReadsSoA, record_type=None):
+    """Inverse of records_to_soa (used by tests to feed the same data to the oracle).  qname is synthesised as
+    ``F<frag_id>:<barcode>:x`` so that (barcode, readid) round-trips."""
+    from collections import namedtuple
+    R = record_type or namedtuple("Read", "qname chrom pos flag mapq nm cigar seq qual")
+    out = []
+    for i in range(soa.n):
+        L = int(soa.l_seq[i])
+        so = int(soa.seq_off[i])
+        b = soa.seq[so: so + (L + 1) // 2]
+        nib = np.empty(2 * len(b), np.uint8)
+        nib[0::2] = b >> 4
+        nib[1::2] = b & 15
+        seq = _NT16_CHARS[nib[:L]].tobytes().decode()
+        qo = int(soa.qual_off[i])
+        qual = soa.qual[qo: qo + L].tolist()
+        co = int(soa.cigar_off[i])
+        cig = [(int(w) & 15, int(w) >> 4) for w in soa.cigar[co: co + int(soa.n_cigar[i])]]
+        bc = umi_string(int(soa.umi[i]), soa.umi_names)
+        out.append(R("F%d:%s:x" % (int(soa.frag_id[i]), bc), soa.chroms[int(soa.ref_id[i])], int(soa.pos[i]),
+                     int(soa.flag[i]), int(soa.mapq[i]), int(soa.nm[i]), cig, seq, qual))
+    return out
