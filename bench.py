@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- target loci called / s on the synthetic N0030 panel (BASELINE.json config 2), one process per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's algorithm on the host CPU (oracle port)
+
+A "step" is one pass of the hot path (K1 prep -> K2 sorts -> K3 tile pileup -> K4 statistics) over one batch:
+``--intervals`` seeded intervals of the N0030 panel BED per GPU, ~3 000 barcodes per locus, ~4 read pairs per
+barcode, 2 x 150 bp.  ``value`` is measured with the batch resident in HBM, ``e2e`` through
+``GpuCaller.call()`` with pinned host buffers (H2D + kernels + D2H inside the timed region).  The panel is sharded
+across GPUs by BED interval (weak scaling: every rank gets its own ``--intervals`` intervals); loci are independent,
+so there is no data-path collective -- torch.distributed is used for the barrier and the max-over-ranks only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PANEL_BED = os.path.join(ROOT, "tests", "golden", "n0030_panel.bed")
+METRIC = "target_loci_called_per_sec"
+UNIT = "loci/s"
+ALGO_BYTES_PER_EVENT = 35.0     # reads in once (2.7 B/event) + every 16-byte event written once and read once
+UMIS_PER_LOCUS, RPB = 3000, 4.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    ap.add_argument("--intervals", type=int, default=96, help="panel intervals per GPU in one batch")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cpu-loci", type=int, default=0, help="loci in the CPU-baseline sample (0 = 2 per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_batch(args, rank, world):
+    from smcounter_b200.synth import SynthSpec, make_panel_mp, panel_intervals_from_bed
+    from smcounter_b200.targets import build_loci
+    ivs = panel_intervals_from_bed(PANEL_BED, limit=args.intervals * world, seed=args.seed)
+    mine = ivs[rank * args.intervals:(rank + 1) * args.intervals]
+    spec = SynthSpec(umis_per_locus=UMIS_PER_LOCUS, rpb=RPB, snv_every=1000, snv_vaf=0.01, indel_every=12000, indel_vaf=0.01)
+    soa, refs, truth = make_panel_mp(mine, spec, seed=args.seed + 17 * rank)
+    loci, bed_order = build_loci(mine, soa.chroms, refs)
+    return mine, soa, refs, loci, bed_order
+
+
+def vc_params():
+    from smcounter_b200.caller import VcParams
+    # --mtDepth 3000 --rpb 4.0 --mtDrop 0 --minBQ 20 --minMQ 30 --hpLen 10 (ds = 6000: no down-sampling)
+    return VcParams(mtDepth=3000, rpb=4.0, minBQ=20, minMQ=30, hpLen=10, mismatchThr=6.0, mtDrop=0, maxMT=0, primerDist=2)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md 'clocks' line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device = device
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(s[1]) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit()]
+        mx = [float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's vc() on the host cores (bounded sample of the same workload)
+# --------------------------------------------------------------------------------------------------------------
+_G = {}
+
+
+def _cpu_worker(job):
+    from oracle import smcounter_oracle as orc
+    chrom, pos = job
+    p = _G["prm"]
+    return orc.vc(_G["index"], chrom, pos, p.minBQ, p.minMQ, p.mtDepth, p.rpb, p.hpLen, p.mismatchThr, p.mtDrop, p.maxMT,
+                  p.primerDist, _G["refs"])
+
+
+def cpu_sample_setup(soa, refs, loci, n_loci_sample):
+    """Pick consecutive loci from the middle of the batch and the reads that overlap them (host objects for the oracle)."""
+    import numpy as np
+    from oracle import smcounter_oracle as orc
+    from smcounter_b200.soa import soa_to_records
+    mid = loci.n // 2
+    sel = np.arange(max(0, mid - n_loci_sample // 2), min(loci.n, mid - n_loci_sample // 2 + n_loci_sample))
+    rid = int(loci.ref_id[sel[0]])
+    sel = sel[loci.ref_id[sel] == rid]
+    lo, hi = int(loci.pos0[sel[0]]), int(loci.pos0[sel[-1]]) + 1
+    ends = soa.ref_end()
+    ridx = np.flatnonzero((soa.ref_id == rid) & (soa.pos < hi) & (ends > lo))
+    recs = soa_to_records(soa.select(ridx), orc.Read)
+    _G["index"] = orc.ReadIndex(recs)
+    _G["refs"] = refs
+    _G["prm"] = vc_params()
+    jobs = [(soa.chroms[rid], str(int(loci.pos0[i]) + 1)) for i in sel]
+    return jobs, len(recs)
+
+
+def cpu_run(jobs, cores):
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    if cores > 1:
+        with mp.get_context("fork").Pool(cores) as pool:
+            rows = pool.map(_cpu_worker, jobs, chunksize=1)
+    else:
+        rows = [_cpu_worker(j) for j in jobs]
+    dt = time.perf_counter() - t0
+    events = sum(int(r.split("\t")[5]) for r in rows if r.split("\t")[5])
+    return len(jobs) / dt, dt, events
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        # The Python-2 reference cannot run (no python2 / pysam); its algorithm is timed through the oracle port, on
+        # rank 0 only, with all host cores.  Each step is a bounded sample of the same workload.
+        if rank != 0:
+            return 0
+        args.intervals = min(args.intervals, 4)      # the sample only needs the reads around its loci
+        mine, soa, refs, loci, bed_order = make_batch(args, 0, 1)
+        n_sample = args.cpu_loci or 2 * cores
+        jobs, nrec = cpu_sample_setup(soa, refs, loci, n_sample)
+        for _ in range(min(args.warmup, 1)):
+            cpu_run(jobs[:max(1, cores)], cores)
+        vals, times, ev = [], [], 0
+        for _ in range(args.steps):
+            v, dt, ev = cpu_run(jobs, cores)
+            vals.append(v); times.append(dt)
+        value = len(jobs) * len(times) / sum(times)
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+                "config": {"workload": "cfg2 synthetic N0030 194-gene panel, 3000 UMIs/locus, rpb 4, 2x150bp",
+                           "sample": "%d consecutive loci, %d reads, %d pileup events per step" % (len(jobs), nrec, ev)},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": "%d loci per step x %d steps (oracle/smcounter_oracle.py, multiprocessing.Pool)" % (len(jobs), args.steps)},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from smcounter_b200.caller import GpuCaller, LocusResults
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    mine, soa, refs, loci, bed_order = make_batch(args, rank, world)
+
+    # pinned host copies of every buffer that crosses the ABI
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy()
+    for f in ("ref_id", "pos", "flag", "mapq", "nm", "l_seq", "seq_off", "qual_off", "cigar_off", "n_cigar", "umi", "frag_id", "seq",
+              "qual", "cigar"):
+        setattr(soa, f, pin(getattr(soa, f)))
+    for f in ("ref_id", "pos0", "ref_base"):
+        setattr(loci, f, pin(getattr(loci, f)))
+
+    caller = GpuCaller(vc_params(), device=local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- kernel-only: batch resident in HBM
+    caller.upload(soa, loci)
+    for _ in range(args.warmup):
+        caller.run()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, kp_ms, launches, tms = 0.0, 0.0, 0, None
+    for _ in range(args.steps):
+        caller.run()
+        tms = caller.timings()
+        dev_ms += tms["ms_total_device"]; kp_ms += tms["ms_k_pileup"]; launches += tms["kernel_launches"]
+    barrier()
+    wall_s = time.perf_counter() - t0
+    out = caller.download(LocusResults(loci.n, max(int(tms["n_dyn"]), 16), pinned=True))
+    n_dyn = out.n_dyn
+
+    # ---------------- end to end: host buffers in, host buffers out, every step
+    for _ in range(min(args.warmup, 2)):
+        caller.call(soa, loci, out=out)
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        caller.call(soa, loci, out=out)
+        e2e_tm = caller.timings()
+    barrier()
+    e2e_s = time.perf_counter() - t1
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    dev_s_max = allmax(dev_ms / 1000.0)
+    wall_s_max = allmax(wall_s)
+    e2e_s_max = allmax(e2e_s)
+    loci_total = allsum(float(loci.n))
+    events_total = allsum(float(tms["n_pileup_events"]))
+    reads_total = allsum(float(soa.n))
+    # device time is what the CUDA events on the library's launch stream bracket for each step (it contains the
+    # few host round-trips a step needs); wall clock is reported beside it.
+    value = loci_total * args.steps / dev_s_max
+    e2e_value = loci_total * args.steps / e2e_s_max
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        algo_bytes = ALGO_BYTES_PER_EVENT * float(tms["n_pileup_events"])
+        kp_avg_s = (kp_ms / args.steps) / 1000.0
+        achieved = algo_bytes / kp_avg_s / 1e9 if kp_avg_s > 0 else 0.0
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1000.0 * dev_s_max / args.steps, "wall_ms_per_step": 1000.0 * wall_s_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+                "config": {"workload": "cfg2 synthetic N0030 194-gene panel (primers...coding.bed geometry), 3000 UMIs/locus, rpb 4, "
+                                       "2x150bp; one batch = %d seeded panel intervals per GPU" % args.intervals,
+                           "intervals_per_gpu": args.intervals, "loci_total": int(loci_total), "reads_total": int(reads_total),
+                           "pileup_events_per_step": int(events_total), "tile_events_per_step_rank0": int(tms["n_tile_events"]),
+                           "params": "mtDepth 3000 rpb 4.0 mtDrop 0 minBQ 20 minMQ 30",
+                           "l2": "inputs larger than L2 (%.0f MB resident per GPU), no flush needed" % (soa.nbytes() / 1e6),
+                           "parallelism": "panel sharded by BED interval, no collective"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_tm["bytes_h2d"]),
+                        "d2h_bytes_per_step": int(e2e_tm["bytes_d2h"]), "ms_per_step": 1000.0 * e2e_s_max / args.steps,
+                        "ms_h2d": e2e_tm["ms_h2d"], "ms_device": e2e_tm["ms_total_device"], "ms_d2h": e2e_tm["ms_d2h"]},
+                "gpu_launches": int(launches),
+                "stage_ms_rank0": {k: tms[k] for k in ("ms_prep", "ms_sort", "ms_pileup", "ms_stats", "ms_k_pileup")},
+                "roofline": {"bound": "hbm", "kernel": "k_pileup (fused event expansion + fragment merge + calProb + tallies)",
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                             "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_event": ALGO_BYTES_PER_EVENT,
+                             "ms_per_launch": 1000.0 * kp_avg_s, "traffic": None,
+                             "events_per_s": float(tms["n_pileup_events"]) / kp_avg_s if kp_avg_s > 0 else 0.0},
+                "clocks": sampler.summary(), "n_dyn_alleles_rank0": int(n_dyn), "n_fisher_rank0": int(tms["n_fisher"])}
+    caller.close()
+
+    if rank == 0 and not args.no_cpu_baseline:
+        n_sample = args.cpu_loci or 2 * cores
+        jobs, nrec = cpu_sample_setup(soa, refs, loci, n_sample)
+        v, dt, ev = cpu_run(jobs, cores)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d consecutive loci of the rank-0 batch (%d reads, %d pileup events), oracle/smcounter_oracle.py "
+                                          "with multiprocessing.Pool(%d), %.1f s" % (len(jobs), nrec, ev, cores, dt),
+                                "archived_reference": "4.15 loci/s on 10 processes at DP~58k (example run log, 2017 hardware)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

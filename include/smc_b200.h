@@ -1,0 +1,241 @@
+/*
+ * smc_b200.h -- C ABI of libsmc_b200.so: smCounter's per-locus calling hot path on one B200.
+ *
+ * This library replaces the body of the reference's per-locus worker
+ *     vc(bamFile, chrom, pos, minBQ, minMQ, mtDepth, rpb, hpLen, mismatchThr, mtDrop, maxMT, primerDist, refGenome)
+ *         (reference smCounter.py:274-600, fanned out one locus at a time by
+ *          multiprocessing.Pool.apply_async(vc_wrapper, ...) at smCounter.py:683-685)
+ * with ONE batched call per GPU: all target loci of a shard and all reads overlapping them go in as flat
+ * structure-of-arrays buffers, all per-locus integer tallies, prediction indices, Fisher statistics and
+ * filter bits come out as flat arrays.  String work (row formatting smCounter.py:575-600, HP/LowC
+ * smCounter.py:122-177, repeat filters :699-785, writers :787-901) stays on the host.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every pointer is HOST memory owned by the caller (pinned memory makes the
+ *     copies faster but is not required); the library owns all device memory and grows it lazily.
+ *   - every function returns 0 on success or a negative SMC_E_* code; the message is in smc_last_error().
+ *     Nothing throws or exits across the ABI (the reference's vc_wrapper turns exceptions into a string,
+ *     smCounter.py:605-611; the Python binding raises RuntimeError naming the locus range instead).
+ *   - one smc_ctx per GPU; a ctx is not thread-safe, different ctxs may be driven from different host threads.
+ *   - there is no CPU fallback: without a CUDA device smc_ctx_create fails with SMC_E_CUDA.
+ */
+#ifndef SMC_B200_H
+#define SMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMC_ABI_VERSION 1
+
+/* error codes */
+#define SMC_OK            0
+#define SMC_E_CUDA       -1   /* CUDA runtime error / no device */
+#define SMC_E_ARG        -2   /* bad argument */
+#define SMC_E_LIMIT      -3   /* input exceeds a documented batch limit (split the batch) */
+#define SMC_E_OVERFLOW   -4   /* an internal table overflowed even after regrowth */
+#define SMC_E_STATE      -5   /* call order violated (e.g. run before upload) */
+
+/* Parameters of vc() that reach the device (reference smCounter.py:274, CLI :619-633). */
+typedef struct smc_params {
+    int32_t minBQ;        /* --minBQ       (smCounter.py:626) */
+    int32_t minMQ;        /* --minMQ       (:627) */
+    int32_t mtDepth;      /* --mtDepth     (:623)  ds = maxMT or round(2*mtDepth), :486 */
+    int32_t mtDrop;       /* --mtDrop      (:630) */
+    int32_t maxMT;        /* --maxMT       (:631) */
+    int32_t primerDist;   /* --primerDist  (:632) */
+    double  rpb;          /* --rpb         (:624)  strong-MT bar 2/3/4, :303-308 */
+    double  mismatchThr;  /* --mismatchThr (:629) */
+} smc_params;
+
+/*
+ * Reads, one entry per BAM record, in BAM (coordinate) order: the index of a read is its pileup order
+ * (fragment merge at smCounter.py:467-479 is order dependent).  Replaces what the reference pulls out of
+ * pysam per pileup read at smCounter.py:319-365, 372-375, 424-425.
+ */
+typedef struct smc_reads_soa {
+    int64_t         n_reads;
+    const int32_t  *ref_id;     /* contig index */
+    const int32_t  *pos;        /* 0-based leftmost reference position */
+    const uint16_t *flag;       /* BAM flag: 0x4 unmapped (skipped), 0x10 reverse, 0x40 read1, 0x80 read2 */
+    const uint8_t  *mapq;
+    const int32_t  *nm;         /* NM tag, 0 when absent (smCounter.py:329-334) */
+    const int32_t  *l_seq;      /* query length incl. soft clips (<= 65535) */
+    const int64_t  *seq_off;    /* byte offset of the read's bases in seq[] */
+    const int64_t  *qual_off;   /* byte offset of the read's qualities in qual[] */
+    const int64_t  *cigar_off;  /* index of the read's first word in cigar[] */
+    const uint16_t *n_cigar;
+    const uint64_t *umi;        /* injective 64-bit code of the barcode string  (BC, smCounter.py:323) */
+    const uint32_t *frag_id;    /* id of (BC, readid) (smCounter.py:321), numbered by first appearance in BAM order:
+                                   ascending frag_id is the canonical fragment order inside a barcode */
+    const uint8_t  *seq;        /* BAM 4-bit bases, high nibble first, every read byte aligned */
+    int64_t         seq_bytes;  /* < 4 GiB per batch */
+    const uint8_t  *qual;       /* phred */
+    int64_t         qual_bytes; /* < 4 GiB per batch */
+    const uint32_t *cigar;      /* BAM cigar words: len<<4 | op (M0 I1 D2 N3 S4 H5 P6 =7 X8) */
+    int64_t         n_cigar_words; /* < 2^32 per batch */
+} smc_reads_soa;
+
+/* Target loci: unique, sorted by (ref_id, pos0).  At most 4 194 302 per batch. */
+typedef struct smc_loci {
+    int64_t         n_loci;
+    const int32_t  *ref_id;
+    const int32_t  *pos0;       /* 0-based position (reference's pos is 1-based: pos0 = int(pos) - 1) */
+    const uint8_t  *ref_base;   /* upper-case ASCII reference base (origRef, smCounter.py:311-313) */
+} smc_loci;
+
+/*
+ * Optional down-sampling mask (smCounter.py:496-500): for the listed loci only the listed barcodes are used.
+ * The selection itself (random.seed(pos); random.sample(bcDict.keys(), ds)) depends on CPython-2 dict order and
+ * is made on the host; the device only applies it.
+ */
+typedef struct smc_umi_keep {
+    int64_t         n_loci;     /* number of masked loci */
+    const int64_t  *locus;      /* ascending indices into smc_loci */
+    const int64_t  *off;        /* n_loci + 1 offsets into umi[] */
+    const uint64_t *umi;        /* kept barcode codes, ascending inside each locus */
+} smc_umi_keep;
+
+/* ---- outputs -------------------------------------------------------------------------------------------- */
+
+/* Fixed allele slots (index a of the per-allele arrays), in the library's canonical allele order. */
+#define SMC_A_A    0
+#define SMC_A_C    1
+#define SMC_A_DEL  2   /* locus lies inside a deletion ('DEL', smCounter.py:416-421) */
+#define SMC_A_T    3
+#define SMC_A_G    4
+#define SMC_NFIXED 5
+/* Allele references in smc_out (alt/max/second): 0..4 = fixed slot, 5 + j = row j of the dyn_* arrays, -1 none. */
+
+/* per-allele counters (index c) */
+#define SMC_C_ALLELE   0   /* alleleCnt        :379,401,459 */
+#define SMC_C_FWD      1   /* forwardCnt       :389,411,457 */
+#define SMC_C_REV      2   /* reverseCnt       :387,409,455 */
+#define SMC_C_LOWQ     3   /* lowQReads        :429 */
+#define SMC_C_R1LE     4   /* #r1BcEndPos <= 20      :234-237 */
+#define SMC_C_R1TOT    5   /* len(r1BcEndPos)        */
+#define SMC_C_R2LE     6   /* #r2BcEndPos <= 20      :244-247 */
+#define SMC_C_R2TOT    7   /* len(r2BcEndPos) == len(r2PrimerEndPos) */
+#define SMC_C_R2PLE    8   /* #r2PrimerEndPos <= primerDist :256-259 */
+#define SMC_C_CONCORD  9   /* concordPairCnt   :476 */
+#define SMC_C_DISCORD 10   /* discordPairCnt   :479 */
+#define SMC_C_MT      11   /* MTCnt            :517,523 */
+#define SMC_C_STRONG  12   /* strongMTCnt      :519 */
+#define SMC_NCNT      13
+
+/* per-locus scalars (index k) */
+#define SMC_L_CVG      0   /* cvg       :368 */
+#define SMC_L_ALLFRAG  1   /* allFrag   :483 */
+#define SMC_L_ALLMT    2   /* allMT     :482 */
+#define SMC_L_USEDFRAG 3   /* usedFrag  :501 */
+#define SMC_L_NBC      4   /* len(bcDict) before down-sampling */
+#define SMC_L_USEDMT   5   /* barcodes actually used (== min(ds, len(bcDict)) when the mask is right) */
+#define SMC_L_MT3      6
+#define SMC_L_MT5      7
+#define SMC_L_MT7      8
+#define SMC_L_MT10     9
+#define SMC_L_KEYMASK 10   /* bit a set: fixed allele a is a key of finalDict (:512) */
+#define SMC_L_STATUS  11   /* SMC_ST_* bits */
+#define SMC_NLOC      12
+
+#define SMC_ST_ZERO_COVERAGE   1u   /* usedMT == 0 (:492-494) */
+#define SMC_ST_NEED_DOWNSAMPLE 2u   /* len(bcDict) > ds and no mask given: tallies cover ALL barcodes; re-run with a mask */
+#define SMC_ST_UMI_OVERFLOW    4u   /* a barcode showed > 2 distinct non-ACGT/DEL alleles at this locus (unsupported) */
+#define SMC_ST_BAD_MASK        8u   /* mask given but kept count != ds */
+
+/* dynamic allele kinds (dyn_kind) */
+#define SMC_K_BASE 0   /* single non-ACGT base (N or IUPAC): dyn_site = BAM nibble */
+#define SMC_K_INS  1   /* 'INS|s|s+inserted'  (:371-375): dyn_site = nibble of s, dyn_len = inserted length */
+#define SMC_K_DEL  2   /* 'DEL|s+deleted|s'   (:392-396): dyn_site = nibble of s (the READ's base), dyn_len = deleted length */
+
+/* filter bits (fl1 / fl2): the device-evaluated part of filterVariants(), smCounter.py:182-269 */
+#define SMC_F_LM        (1u << 0)
+#define SMC_F_LSM       (1u << 1)
+#define SMC_F_DP        (1u << 2)
+#define SMC_F_SB        (1u << 3)
+#define SMC_F_LOWQ      (1u << 4)
+#define SMC_F_R1CP      (1u << 5)
+#define SMC_F_R2CP      (1u << 6)
+#define SMC_F_PRIMERCP  (1u << 7)
+#define SMC_F_HPGATE    (1u << 16)  /* MTCnt[alt]/usedMT < 0.99: HP / LowC apply if the host finds the region (:198,202) */
+#define SMC_F_EVALUATED (1u << 17)  /* filterVariants() was entered for this candidate (:549 / :563) */
+
+/* Fisher tests per candidate (index t) */
+#define SMC_T_SB     0
+#define SMC_T_R1     1
+#define SMC_T_R2     2
+#define SMC_T_PRIMER 3
+
+/*
+ * All arrays are caller-allocated.  Per-locus arrays use the layout [field][locus] so that the device writes
+ * them coalesced:  loc[k * n_loci + i],  cnt[(a * SMC_NCNT + c) * n_loci + i],  pi[a * n_loci + i],
+ * fisher_p[((cand * 4) + t) * n_loci + i].
+ */
+typedef struct smc_out {
+    int64_t   n_loci;        /* capacity of the per-locus arrays (must equal smc_loci.n_loci) */
+    int32_t  *loc;           /* [SMC_NLOC][n_loci] */
+    int32_t  *cnt;           /* [SMC_NFIXED][SMC_NCNT][n_loci] */
+    double   *pi;            /* [SMC_NFIXED][n_loci]  finalDict: exactly rounded sum of per-barcode terms (:512) */
+    /* call-level results (smCounter.py:534-573) */
+    int32_t  *max_allele;    /* [n_loci] maxBase        (allele reference) */
+    int32_t  *second_allele; /* [n_loci] secondMaxBase */
+    int32_t  *alt_allele;    /* [n_loci] origAlt before the bi-allelic step (:541) */
+    double   *alt_pi;        /* [n_loci] altPI (unrounded) */
+    double   *second_pi;     /* [n_loci] secondMaxPI */
+    uint32_t *fl1;           /* [n_loci] filter bits of candidate 1 = origAlt */
+    uint32_t *fl2;           /* [n_loci] filter bits of candidate 2 = secondMaxBase when the bi-allelic test (:555) holds */
+    uint8_t  *biallelic;     /* [n_loci] 1 when the condition at :555 holds */
+    double   *fisher_p;      /* [2][4][n_loci]  NaN when the test was not evaluated */
+    double   *fisher_or;     /* [2][4][n_loci] */
+    /* dynamic alleles (anything that is not A/C/G/T/'DEL'), sorted by (locus, kind, site, len, bases) */
+    int64_t   dyn_capacity;  /* rows available in the dyn_* arrays */
+    int64_t   n_dyn;         /* OUT: rows written (if > dyn_capacity the call fails with SMC_E_LIMIT) */
+    int32_t  *dyn_locus;     /* [dyn_capacity] */
+    uint8_t  *dyn_kind;      /* SMC_K_* */
+    uint8_t  *dyn_site;
+    int32_t  *dyn_len;
+    uint32_t *dyn_rep_read;  /* a read (index into smc_reads_soa) that carries the allele ... */
+    int32_t  *dyn_rep_qpos;  /* ... and the query position of its site base: inserted bases are seq[qpos+1 .. qpos+len] */
+    uint8_t  *dyn_iskey;     /* 1 when the allele is a key of finalDict */
+    int32_t  *dyn_cnt;       /* [dyn_capacity][SMC_NCNT] (row major) */
+    double   *dyn_pi;        /* [dyn_capacity] */
+    int64_t  *dyn_first;     /* [n_loci + 1] rows of locus i are dyn_first[i] .. dyn_first[i+1]-1 */
+} smc_out;
+
+/* CUDA-event timings and work counts of the last smc_run_resident() / smc_call_batch(). */
+typedef struct smc_timings {
+    float   ms_h2d, ms_prep, ms_sort, ms_pileup, ms_stats, ms_d2h, ms_total_device;
+    float   ms_k_pileup;   /* the k_pileup launch alone (dominant kernel; roofline numerator / this) */
+    int64_t n_reads, n_loci, n_tile_events, n_pileup_events /* sum of cvg */, n_umi_groups, n_dyn, n_fisher;
+    int64_t bytes_h2d, bytes_d2h;
+    int32_t kernel_launches;
+} smc_timings;
+
+typedef struct smc_ctx smc_ctx;
+
+int         smc_version(void);
+int         smc_ctx_create(int device, const smc_params *params, smc_ctx **out);
+void        smc_ctx_destroy(smc_ctx *ctx);
+const char *smc_last_error(smc_ctx *ctx);            /* ctx may be NULL: last error of smc_ctx_create */
+
+/* One call = host buffers in, host buffers out (H2D, all kernels, D2H). */
+int smc_call_batch(smc_ctx *ctx, const smc_reads_soa *reads, const smc_loci *loci, const smc_umi_keep *keep /* nullable */,
+                   smc_out *out);
+
+/* The same three phases separately, so that the kernels can be timed with inputs resident in HBM. */
+int smc_upload(smc_ctx *ctx, const smc_reads_soa *reads, const smc_loci *loci, const smc_umi_keep *keep /* nullable */);
+int smc_run_resident(smc_ctx *ctx);
+int smc_download(smc_ctx *ctx, smc_out *out);
+
+int smc_get_timings(smc_ctx *ctx, smc_timings *t);
+
+/* For loci flagged SMC_ST_NEED_DOWNSAMPLE: list the barcodes of bcDict (those with >= 1 read passing incCond) so the
+ * host can draw the sample.  umi_out receives, locus after locus, the ascending barcode codes; off_out[n+1]. */
+int smc_list_barcodes(smc_ctx *ctx, int64_t n, const int64_t *locus, int64_t *off_out, uint64_t *umi_out, int64_t umi_capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMC_B200_H */

@@ -1,0 +1,202 @@
+"""Host side of the hot path: one batched call per GPU into libsmc_b200.so, replacing the reference's
+``Pool.apply_async(vc_wrapper, ...)`` fan-out (smCounter.py:683-685) and the body of ``vc()`` (:274-600).
+
+``GpuCaller.call(reads, loci)`` returns ``LocusResults`` (flat numpy arrays, one entry per target locus);
+``smcounter_b200.rows.format_rows`` turns those into the reference's 45-column rows.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _ffi
+from .soa import Loci, ReadsSoA
+
+
+@dataclass
+class VcParams:
+    """The parameters of vc() (smCounter.py:274) with the CLI defaults of smCounter.py:619-633."""
+    mtDepth: int
+    rpb: float
+    minBQ: int = 20
+    minMQ: int = 30
+    hpLen: int = 10
+    mismatchThr: float = 6.0
+    mtDrop: int = 0
+    maxMT: int = 0
+    primerDist: int = 2
+
+    @property
+    def ds(self) -> int:
+        """Down-sampling cap (smCounter.py:486); Python-2 round() is half away from zero, exact for 2*int."""
+        return self.maxMT if self.maxMT > 0 else int(2 * self.mtDepth)
+
+
+def _alloc(shape, dtype, pinned):
+    if pinned:
+        import torch
+        t = torch.empty(int(np.prod(shape)) * np.dtype(dtype).itemsize, dtype=torch.uint8, pin_memory=True)
+        return t.numpy().view(dtype).reshape(shape)
+    return np.empty(shape, dtype=dtype)
+
+
+class LocusResults:
+    """Per-locus outputs of the device path (include/smc_b200.h: smc_out)."""
+
+    def __init__(self, n_loci: int, dyn_capacity: int, pinned: bool = False):
+        self.n_loci = n_loci
+        self.dyn_capacity = dyn_capacity
+        n = max(n_loci, 1)
+        d = max(dyn_capacity, 1)
+        self.loc = _alloc((_ffi.SMC_NLOC, n), np.int32, pinned)
+        self.cnt = _alloc((_ffi.SMC_NFIXED, _ffi.SMC_NCNT, n), np.int32, pinned)
+        self.pi = _alloc((_ffi.SMC_NFIXED, n), np.float64, pinned)
+        self.max_allele = _alloc((n,), np.int32, pinned)
+        self.second_allele = _alloc((n,), np.int32, pinned)
+        self.alt_allele = _alloc((n,), np.int32, pinned)
+        self.alt_pi = _alloc((n,), np.float64, pinned)
+        self.second_pi = _alloc((n,), np.float64, pinned)
+        self.fl1 = _alloc((n,), np.uint32, pinned)
+        self.fl2 = _alloc((n,), np.uint32, pinned)
+        self.biallelic = _alloc((n,), np.uint8, pinned)
+        self.fisher_p = _alloc((2, 4, n), np.float64, pinned)
+        self.fisher_or = _alloc((2, 4, n), np.float64, pinned)
+        self.dyn_locus = _alloc((d,), np.int32, pinned)
+        self.dyn_kind = _alloc((d,), np.uint8, pinned)
+        self.dyn_site = _alloc((d,), np.uint8, pinned)
+        self.dyn_len = _alloc((d,), np.int32, pinned)
+        self.dyn_rep_read = _alloc((d,), np.uint32, pinned)
+        self.dyn_rep_qpos = _alloc((d,), np.int32, pinned)
+        self.dyn_iskey = _alloc((d,), np.uint8, pinned)
+        self.dyn_cnt = _alloc((d, _ffi.SMC_NCNT), np.int32, pinned)
+        self.dyn_pi = _alloc((d,), np.float64, pinned)
+        self.dyn_first = _alloc((n + 1,), np.int64, pinned)
+        self.n_dyn = 0
+
+    def as_struct(self) -> _ffi.smc_out:
+        p = _ffi.ptr
+        o = _ffi.smc_out()
+        o.n_loci = self.n_loci
+        o.loc, o.cnt, o.pi = p(self.loc), p(self.cnt), p(self.pi)
+        o.max_allele, o.second_allele, o.alt_allele = p(self.max_allele), p(self.second_allele), p(self.alt_allele)
+        o.alt_pi, o.second_pi, o.fl1, o.fl2, o.biallelic = p(self.alt_pi), p(self.second_pi), p(self.fl1), p(self.fl2), p(self.biallelic)
+        o.fisher_p, o.fisher_or = p(self.fisher_p), p(self.fisher_or)
+        o.dyn_capacity = self.dyn_capacity
+        o.n_dyn = 0
+        o.dyn_locus, o.dyn_kind, o.dyn_site, o.dyn_len = p(self.dyn_locus), p(self.dyn_kind), p(self.dyn_site), p(self.dyn_len)
+        o.dyn_rep_read, o.dyn_rep_qpos, o.dyn_iskey = p(self.dyn_rep_read), p(self.dyn_rep_qpos), p(self.dyn_iskey)
+        o.dyn_cnt, o.dyn_pi, o.dyn_first = p(self.dyn_cnt), p(self.dyn_pi), p(self.dyn_first)
+        return o
+
+    def nbytes(self) -> int:
+        return sum(v.nbytes for v in self.__dict__.values() if isinstance(v, np.ndarray))
+
+
+class UmiKeep:
+    """Down-sampling mask (smCounter.py:496-500): {locus index -> iterable of kept barcode codes}."""
+
+    def __init__(self, mapping: dict):
+        items = sorted((int(k), np.sort(np.asarray(list(v), dtype=np.uint64))) for k, v in mapping.items())
+        self.locus = np.asarray([k for k, _ in items], dtype=np.int64)
+        self.off = np.zeros(len(items) + 1, dtype=np.int64)
+        for i, (_, v) in enumerate(items):
+            self.off[i + 1] = self.off[i] + len(v)
+        self.umi = np.concatenate([v for _, v in items]) if items else np.zeros(0, np.uint64)
+
+    def as_struct(self) -> _ffi.smc_umi_keep:
+        k = _ffi.smc_umi_keep()
+        k.n_loci = len(self.locus)
+        k.locus, k.off, k.umi = _ffi.ptr(self.locus), _ffi.ptr(self.off), _ffi.ptr(self.umi)
+        return k
+
+
+class GpuCaller:
+    """One context per GPU (not thread-safe per context; ctypes releases the GIL during calls)."""
+
+    def __init__(self, params: VcParams, device: int = 0):
+        self.lib = _ffi.load()
+        self.params = params
+        p = _ffi.smc_params(params.minBQ, params.minMQ, params.mtDepth, params.mtDrop, params.maxMT, params.primerDist,
+                            float(params.rpb), float(params.mismatchThr))
+        h = C.c_void_p()
+        rc = self.lib.smc_ctx_create(int(device), C.byref(p), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("smc_ctx_create failed (%d): %s" % (rc, self.lib.smc_last_error(None).decode()))
+        self.h = h
+        self._keepalive = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.smc_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self, what, rc, loci=None):
+        msg = self.lib.smc_last_error(self.h).decode()
+        where = ""
+        if loci is not None and loci.n:
+            where = " in locus range (%d:%d .. %d:%d)" % (loci.ref_id[0], loci.pos0[0] + 1, loci.ref_id[-1], loci.pos0[-1] + 1)
+        # mirrors smCounter.py:694 "Exception thrown in vc() at location: ..."
+        return RuntimeError("Exception thrown in %s%s: [%d] %s" % (what, where, rc, msg))
+
+    @staticmethod
+    def _reads_struct(r: ReadsSoA) -> _ffi.smc_reads_soa:
+        p = _ffi.ptr
+        s = _ffi.smc_reads_soa()
+        s.n_reads = r.n
+        s.ref_id, s.pos, s.flag, s.mapq, s.nm, s.l_seq = p(r.ref_id), p(r.pos), p(r.flag), p(r.mapq), p(r.nm), p(r.l_seq)
+        s.seq_off, s.qual_off, s.cigar_off, s.n_cigar = p(r.seq_off), p(r.qual_off), p(r.cigar_off), p(r.n_cigar)
+        s.umi, s.frag_id = p(r.umi), p(r.frag_id)
+        s.seq, s.seq_bytes, s.qual, s.qual_bytes = p(r.seq), r.seq.nbytes, p(r.qual), r.qual.nbytes
+        s.cigar, s.n_cigar_words = p(r.cigar), r.cigar.shape[0]
+        return s
+
+    @staticmethod
+    def _loci_struct(l: Loci) -> _ffi.smc_loci:
+        s = _ffi.smc_loci()
+        s.n_loci = l.n
+        s.ref_id, s.pos0, s.ref_base = _ffi.ptr(l.ref_id), _ffi.ptr(l.pos0), _ffi.ptr(l.ref_base)
+        return s
+
+    def upload(self, reads: ReadsSoA, loci: Loci, keep: UmiKeep | None = None):
+        rs, ls = self._reads_struct(reads), self._loci_struct(loci)
+        ks = keep.as_struct() if keep is not None else None
+        self._keepalive = (reads, loci, keep)
+        rc = self.lib.smc_upload(self.h, C.byref(rs), C.byref(ls), C.byref(ks) if ks is not None else None)
+        if rc != 0:
+            raise self._err("smc_upload", rc, loci)
+        self._n_loci = loci.n
+
+    def run(self):
+        rc = self.lib.smc_run_resident(self.h)
+        if rc != 0:
+            raise self._err("smc_run_resident", rc, self._keepalive[1] if self._keepalive else None)
+
+    def download(self, out: LocusResults | None = None) -> LocusResults:
+        n_dyn = self.timings()["n_dyn"]
+        if out is None or out.n_loci != self._n_loci or out.dyn_capacity < n_dyn:
+            out = LocusResults(self._n_loci, max(int(n_dyn), 16))
+        o = out.as_struct()
+        rc = self.lib.smc_download(self.h, C.byref(o))
+        if rc != 0:
+            raise self._err("smc_download", rc)
+        out.n_dyn = int(o.n_dyn)
+        return out
+
+    def call(self, reads: ReadsSoA, loci: Loci, keep: UmiKeep | None = None, out: LocusResults | None = None) -> LocusResults:
+        """H2D + kernels + D2H; the drop-in for the per-locus vc() fan-out."""
+        self.upload(reads, loci, keep)
+        self.run()
+        return self.download(out)
+
+    def timings(self) -> dict:
+        t = _ffi.smc_timings()
+        self.lib.smc_get_timings(self.h, C.byref(t))
+        return {f: getattr(t, f) for f, _ in _ffi.smc_timings._fields_}

@@ -1,0 +1,611 @@
+// libsmc_b200.so -- C ABI (include/smc_b200.h) and pipeline orchestration.
+//
+//   H2D -> K1 read prep (CIGAR walk, QC gate, locus range)        smc_pileup.cuh
+//       -> K2 segmented radix sort: reads by (barcode, fragment), tile events by tile   smc_sort.cuh
+//       -> K3 tile pileup: lane = locus, fragment merge, calProb, tallies              smc_pileup.cuh
+//       -> K4 FP64 statistics: PI, ALT, filters, Fisher                                smc_stats.cuh
+//   -> D2H
+#include <cmath>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "smc_common.cuh"
+#include "smc_sort.cuh"
+#include "smc_pileup.cuh"
+#include "smc_stats.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+#define PCR_NMAX 192
+
+struct smc_ctx {
+    int device = 0;
+    smc_params prm{};
+    std::string err;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[10]{};
+    // resident inputs
+    int64_t n_reads = 0, n_loci = 0, n_keep_loci = 0, n_keep_umi = 0;
+    int64_t seq_bytes = 0, qual_bytes = 0, n_cigar_words = 0;
+    DevBuf d_ref_id, d_pos, d_flag, d_mapq, d_nm, d_lseq, d_seq_off, d_qual_off, d_cig_off, d_ncig, d_umi, d_frag, d_seq, d_qual,
+        d_cigar;
+    DevBuf d_loci_ref, d_loci_pos, d_loci_base, d_loci_key;
+    DevBuf d_keep_idx, d_keep_off, d_keep_umi;
+    bool has_keep = false, uploaded = false, ran = false;
+    // tables
+    DevBuf d_bqtab, d_pcrtab;
+    // scratch
+    DevBuf d_k0, d_k1, d_v0, d_v1, d_hist, d_scan, d_flags32a, d_flags32b, d_urank, d_frank, d_umi_of_urank, d_recs, d_ntiles,
+        d_evoff, d_ek0, d_ek1, d_ev0, d_ev1, d_tile_off, d_unit_cnt, d_unit_off, d_small;
+    // per-locus accumulators / outputs
+    DevBuf d_loc, d_cnt, d_limb, d_pi, d_max, d_second, d_alt, d_altpi, d_secondpi, d_fl1, d_fl2, d_bial, d_fp, d_for;
+    // dynamic allele table + sorted rows
+    uint32_t dyn_cap = 0;
+    DevBuf d_dkey, d_drep_read, d_drep_qpos, d_dlen, d_dcnt, d_dlimb, d_diskey;
+    DevBuf d_lk0, d_lk1, d_lv0, d_lv1;
+    DevBuf d_s_key, d_s_cnt, d_s_limb, d_s_iskey, d_s_pi, d_s_rep_read, d_s_rep_qpos, d_s_len, d_dyn_first;
+    int64_t n_dyn = 0;
+    DevBuf d_tasks;
+    uint32_t task_cap = 0;
+    // barcode listing
+    DevBuf d_list_idx, d_list_count, d_list_off, d_list_umi;
+    smc_timings tm{};
+    uint32_t chunk = 8192;
+    const uint32_t* ev_read_sorted = nullptr;   // tile-sorted event -> srank map (lives in d_ev0 or d_ev1)
+    uint32_t n_tiles = 0; int64_t n_tile_events = 0;
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                              \
+            return SMC_E_CUDA;                                                                           \
+        }                                                                                                \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// small kernels used only by the orchestration
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_loci_keys(const int32_t* ref_id, const int32_t* pos0, int64_t n, uint64_t* key) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) key[i] = ((uint64_t)(uint32_t)ref_id[i] << 32) | (uint32_t)pos0[i];
+}
+__global__ void k_init_pairs_frag(const uint32_t* frag, int64_t n, uint64_t* k, uint32_t* v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { k[i] = frag[i]; v[i] = (uint32_t)i; }
+}
+__global__ void k_gather_umi_keys(const uint64_t* umi, const uint32_t* v, int64_t n, uint64_t* k) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) k[i] = umi[v[i]];
+}
+__global__ void k_heads(const uint64_t* umi, const uint32_t* frag, const uint32_t* perm, int64_t n, uint32_t* uhead, uint32_t* fhead) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t r = perm[s];
+    bool uh = true, fh = true;
+    if (s > 0) {
+        uint32_t q = perm[s - 1];
+        uh = umi[r] != umi[q];
+        fh = uh || frag[r] != frag[q];
+    }
+    uhead[s] = uh; fhead[s] = fh;
+}
+__global__ void k_ranks(const uint32_t* uhead, const uint32_t* fhead, const uint32_t* uex, const uint32_t* fex, const uint64_t* umi,
+                        const uint32_t* perm, int64_t n, uint32_t* urank, uint32_t* frank, uint64_t* umi_of_urank) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t ur = uex[s] + uhead[s] - 1, fr = fex[s] + fhead[s] - 1;
+    urank[s] = ur; frank[s] = fr;
+    if (uhead[s]) umi_of_urank[ur] = umi[perm[s]];
+}
+__global__ void k_tile_offsets(const uint64_t* ev_key, int64_t ne, uint32_t n_tiles, uint32_t* tile_off) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    tile_off[t] = (uint32_t)lower_bound_u64(ev_key, ne, (uint64_t)t);
+}
+__global__ void k_unit_counts(const uint32_t* tile_off, uint32_t n_tiles, uint32_t chunk, uint32_t* cnt) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    uint32_t n = t < n_tiles ? tile_off[t + 1] - tile_off[t] : 0;
+    cnt[t] = (n + chunk - 1) / chunk;
+}
+__global__ void k_fill_u64(unsigned long long* p, int64_t n, unsigned long long v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_scatter_idx(const int64_t* locus, int64_t n, int32_t* idx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) idx[locus[i]] = (int32_t)i;
+}
+__global__ void k_dyn_collect(const unsigned long long* dkey, uint32_t cap, uint64_t* lk, uint32_t* lv, uint32_t* count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    unsigned long long k = dkey[i];
+    if (k != DYN_EMPTY) { uint32_t o = atomicAdd(count, 1u); lk[o] = k; lv[o] = i; }
+}
+__global__ void k_dyn_gather(const uint64_t* lk, const uint32_t* lv, int64_t n, const int32_t* dcnt, const unsigned long long* dlimb,
+                             const uint8_t* diskey, const uint32_t* drep_read, const int32_t* drep_qpos, const int32_t* dlen,
+                             unsigned long long* s_key, int32_t* s_cnt, unsigned long long* s_limb, uint8_t* s_iskey,
+                             uint32_t* s_rep_read, int32_t* s_rep_qpos, int32_t* s_len) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t e = lv[j];
+    s_key[j] = lk[j];
+    for (int c = 0; c < SMC_NCNT; ++c) s_cnt[j * SMC_NCNT + c] = dcnt[(size_t)e * SMC_NCNT + c];
+    s_cnt[j * SMC_NCNT + SMC_C_REV] = dcnt[(size_t)e * SMC_NCNT + SMC_C_ALLELE] - dcnt[(size_t)e * SMC_NCNT + SMC_C_FWD];
+    for (int t = 0; t < 3; ++t) s_limb[j * 3 + t] = dlimb[(size_t)e * 3 + t];
+    s_iskey[j] = diskey[e];
+    s_rep_read[j] = drep_read[e]; s_rep_qpos[j] = drep_qpos[e]; s_len[j] = dlen[e];
+}
+__global__ void k_dyn_first(const unsigned long long* s_key, int64_t n_dyn, int64_t n_loci, uint32_t* first) {
+    int64_t L = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (L > n_loci) return;
+    first[L] = (uint32_t)lower_bound_u64((const uint64_t*)s_key, n_dyn, (uint64_t)L << DYN_LOCUS_SHIFT);
+}
+__global__ void k_sum_cvg(const int32_t* cvg, int64_t n, unsigned long long* out) {
+    unsigned long long s = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += (unsigned)cvg[i];
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(FULL_MASK, s, d);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+#define LAUNCH(kern, grid, block, smem, ...)                        \
+    do {                                                            \
+        if ((grid) > 0) {                                           \
+            kern<<<(grid), (block), (smem), ctx->st>>>(__VA_ARGS__); \
+            ++g_launches;                                           \
+        }                                                           \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int smc_version(void) { return SMC_ABI_VERSION; }
+
+extern "C" const char* smc_last_error(smc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int smc_ctx_create(int device, const smc_params* params, smc_ctx** out) {
+    if (!params || !out) { g_create_error = "smc_ctx_create: null argument"; return SMC_E_ARG; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("smc_ctx_create: no CUDA device (") + cudaGetErrorString(e) + "); libsmc_b200 has no CPU fallback";
+        return SMC_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "smc_ctx_create: bad device index"; return SMC_E_ARG; }
+    smc_ctx* ctx = new (std::nothrow) smc_ctx();
+    if (!ctx) { g_create_error = "smc_ctx_create: out of host memory"; return SMC_E_ARG; }
+    ctx->device = device; ctx->prm = *params;
+    auto fail = [&](const char* what, cudaError_t ce) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        delete ctx; return SMC_E_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
+    // host-computed tables (glibc pow, the same libm CPython calls): 10^(-bq/10) and the PCR prior
+    std::vector<double> bq(256);
+    for (int q = 0; q < 256; ++q) bq[q] = std::pow(10.0, -(double)q / 10.0);                          // smCounter.py:469
+    const size_t per = (size_t)(PCR_NMAX + 1) * (PCR_NMAX + 2) / 2;
+    std::vector<double> pcr(3 * per);
+    for (int k = 4; k <= 6; ++k)
+        for (int n = 0; n <= PCR_NMAX; ++n)
+            for (int c = 0; c <= n; ++c) {
+                double ratio = ((double)c + 0.5) / ((double)n + 0.5 * (double)k);                       // :80
+                pcr[(size_t)(k - 4) * per + (size_t)n * (n + 1) / 2 + c] = std::pow(10.0, -6.0 * ratio); // :81
+            }
+    if ((e = ctx->d_bqtab.ensure(256 * 8)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = ctx->d_pcrtab.ensure(pcr.size() * 8)) != cudaSuccess) return fail("cudaMalloc", e);
+    cudaMemcpy(ctx->d_bqtab.p, bq.data(), 256 * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(ctx->d_pcrtab.p, pcr.data(), pcr.size() * 8, cudaMemcpyHostToDevice);
+    if ((e = cudaFuncSetAttribute(k_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_BYTES)) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(k_pileup)", e);
+    if ((e = ctx->d_small.ensure(4096)) != cudaSuccess) return fail("cudaMalloc", e);
+    *out = ctx;
+    return SMC_OK;
+}
+
+extern "C" void smc_ctx_destroy(smc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    DevBuf* bufs[] = {&ctx->d_ref_id, &ctx->d_pos, &ctx->d_flag, &ctx->d_mapq, &ctx->d_nm, &ctx->d_lseq, &ctx->d_seq_off, &ctx->d_qual_off,
+                      &ctx->d_cig_off, &ctx->d_ncig, &ctx->d_umi, &ctx->d_frag, &ctx->d_seq, &ctx->d_qual, &ctx->d_cigar, &ctx->d_loci_ref,
+                      &ctx->d_loci_pos, &ctx->d_loci_base, &ctx->d_loci_key, &ctx->d_keep_idx, &ctx->d_keep_off, &ctx->d_keep_umi,
+                      &ctx->d_bqtab, &ctx->d_pcrtab, &ctx->d_k0, &ctx->d_k1, &ctx->d_v0, &ctx->d_v1, &ctx->d_hist, &ctx->d_scan,
+                      &ctx->d_flags32a, &ctx->d_flags32b, &ctx->d_urank, &ctx->d_frank, &ctx->d_umi_of_urank, &ctx->d_recs, &ctx->d_ntiles,
+                      &ctx->d_evoff, &ctx->d_ek0, &ctx->d_ek1, &ctx->d_ev0, &ctx->d_ev1, &ctx->d_tile_off, &ctx->d_unit_cnt,
+                      &ctx->d_unit_off, &ctx->d_small, &ctx->d_loc, &ctx->d_cnt, &ctx->d_limb, &ctx->d_pi, &ctx->d_max, &ctx->d_second,
+                      &ctx->d_alt, &ctx->d_altpi, &ctx->d_secondpi, &ctx->d_fl1, &ctx->d_fl2, &ctx->d_bial, &ctx->d_fp, &ctx->d_for,
+                      &ctx->d_dkey, &ctx->d_drep_read, &ctx->d_drep_qpos, &ctx->d_dlen, &ctx->d_dcnt, &ctx->d_dlimb, &ctx->d_diskey,
+                      &ctx->d_lk0, &ctx->d_lk1, &ctx->d_lv0, &ctx->d_lv1, &ctx->d_s_key, &ctx->d_s_cnt, &ctx->d_s_limb, &ctx->d_s_iskey,
+                      &ctx->d_s_pi, &ctx->d_s_rep_read, &ctx->d_s_rep_qpos, &ctx->d_s_len, &ctx->d_dyn_first, &ctx->d_tasks,
+                      &ctx->d_list_idx, &ctx->d_list_count, &ctx->d_list_off, &ctx->d_list_umi};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int smc_upload(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc, const smc_umi_keep* K) {
+    if (!ctx) return SMC_E_ARG;
+    if (!R || !Lc) { ctx->err = "smc_upload: null reads/loci"; return SMC_E_ARG; }
+    if (R->n_reads < 0 || Lc->n_loci < 0) { ctx->err = "smc_upload: negative size"; return SMC_E_ARG; }
+    if (Lc->n_loci > SMC_MAX_LOCI) { ctx->err = "smc_upload: more than 4194302 loci in one batch"; return SMC_E_LIMIT; }
+    if (R->n_reads >= (1ll << 31) || R->seq_bytes >= (1ll << 32) || R->qual_bytes >= (1ll << 32) || R->n_cigar_words >= (1ll << 32)) {
+        ctx->err = "smc_upload: batch exceeds 2^31 reads or 4 GiB of bases/qualities/cigar; split the batch"; return SMC_E_LIMIT;
+    }
+    CK(cudaSetDevice(ctx->device));
+    ctx->uploaded = false; ctx->ran = false;
+    const int64_t n = R->n_reads, nl = Lc->n_loci;
+    CK(cudaEventRecord(ctx->ev[0], ctx->st));
+    int64_t bytes = 0;
+#define UP(buf, src, count, T)                                                                                   \
+    do {                                                                                                         \
+        size_t b__ = (size_t)(count) * sizeof(T);                                                                \
+        CK((buf).ensure(b__ ? b__ : 16));                                                                        \
+        if (b__) { CK(cudaMemcpyAsync((buf).p, (src), b__, cudaMemcpyHostToDevice, ctx->st)); bytes += b__; }     \
+    } while (0)
+    UP(ctx->d_ref_id, R->ref_id, n, int32_t); UP(ctx->d_pos, R->pos, n, int32_t); UP(ctx->d_flag, R->flag, n, uint16_t);
+    UP(ctx->d_mapq, R->mapq, n, uint8_t); UP(ctx->d_nm, R->nm, n, int32_t); UP(ctx->d_lseq, R->l_seq, n, int32_t);
+    UP(ctx->d_seq_off, R->seq_off, n, int64_t); UP(ctx->d_qual_off, R->qual_off, n, int64_t); UP(ctx->d_cig_off, R->cigar_off, n, int64_t);
+    UP(ctx->d_ncig, R->n_cigar, n, uint16_t); UP(ctx->d_umi, R->umi, n, uint64_t); UP(ctx->d_frag, R->frag_id, n, uint32_t);
+    UP(ctx->d_seq, R->seq, R->seq_bytes, uint8_t); UP(ctx->d_qual, R->qual, R->qual_bytes, uint8_t);
+    UP(ctx->d_cigar, R->cigar, R->n_cigar_words, uint32_t);
+    UP(ctx->d_loci_ref, Lc->ref_id, nl, int32_t); UP(ctx->d_loci_pos, Lc->pos0, nl, int32_t); UP(ctx->d_loci_base, Lc->ref_base, nl, uint8_t);
+    ctx->has_keep = K && K->n_loci > 0;
+    if (ctx->has_keep) {
+        UP(ctx->d_keep_off, K->off, K->n_loci + 1, int64_t);
+        UP(ctx->d_keep_umi, K->umi, K->off[K->n_loci], uint64_t);
+        DevBuf tmp = ctx->d_k0;  // reuse: locus list staging
+        CK(ctx->d_k0.ensure((size_t)K->n_loci * 8));
+        CK(cudaMemcpyAsync(ctx->d_k0.p, K->locus, (size_t)K->n_loci * 8, cudaMemcpyHostToDevice, ctx->st));
+        bytes += K->n_loci * 8;
+        CK(ctx->d_keep_idx.ensure((size_t)(nl ? nl : 1) * 4));
+        LAUNCH(k_fill_i32, nblk(nl, 256), 256, 0, ctx->d_keep_idx.as<int32_t>(), nl, -1);
+        LAUNCH(k_scatter_idx, nblk(K->n_loci, 256), 256, 0, ctx->d_k0.as<int64_t>(), K->n_loci, ctx->d_keep_idx.as<int32_t>());
+        (void)tmp;
+        ctx->n_keep_loci = K->n_loci;
+    }
+#undef UP
+    CK(ctx->d_loci_key.ensure((size_t)(nl ? nl : 1) * 8));
+    LAUNCH(k_loci_keys, nblk(nl, 256), 256, 0, ctx->d_loci_ref.as<int32_t>(), ctx->d_loci_pos.as<int32_t>(), nl, ctx->d_loci_key.as<uint64_t>());
+    CK(cudaEventRecord(ctx->ev[1], ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->n_reads = n; ctx->n_loci = nl;
+    ctx->seq_bytes = R->seq_bytes; ctx->qual_bytes = R->qual_bytes; ctx->n_cigar_words = R->n_cigar_words;
+    ctx->tm = smc_timings{};
+    cudaEventElapsedTime(&ctx->tm.ms_h2d, ctx->ev[0], ctx->ev[1]);
+    ctx->tm.bytes_h2d = bytes; ctx->tm.n_reads = n; ctx->tm.n_loci = nl;
+    ctx->uploaded = true;
+    return SMC_OK;
+}
+
+static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE);
+
+extern "C" int smc_run_resident(smc_ctx* ctx) {
+    if (!ctx) return SMC_E_ARG;
+    if (!ctx->uploaded) { ctx->err = "smc_run_resident: nothing uploaded"; return SMC_E_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    g_launches = 0;
+    const int64_t n = ctx->n_reads, nl = ctx->n_loci;
+    const uint32_t n_tiles = (uint32_t)((nl + 31) / 32);
+    uint32_t* small = ctx->d_small.as<uint32_t>();          // [0..1] u64 or/and  [4] NE  [5] gflags  [6] dyn count  [7] n_tasks  [8..9] u64 cvg sum
+    CK(cudaEventRecord(ctx->ev[2], ctx->st));
+    int64_t NE = 0;
+    if (n > 0 && nl > 0) {
+        // ---------------- K2a: order reads by (umi, frag_id, BAM index)
+        CK(ctx->d_k0.ensure((size_t)n * 8)); CK(ctx->d_k1.ensure((size_t)n * 8));
+        CK(ctx->d_v0.ensure((size_t)n * 4)); CK(ctx->d_v1.ensure((size_t)n * 4));
+        const uint32_t rs_blocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+        CK(ctx->d_hist.ensure((size_t)256 * rs_blocks * 4 + 1024));
+        CK(ctx->d_scan.ensure((size_t)scan_scratch_words(std::max<int64_t>((int64_t)256 * rs_blocks, n + 1)) * 4 + 1024));
+        uint64_t* k0 = ctx->d_k0.as<uint64_t>(); uint64_t* k1 = ctx->d_k1.as<uint64_t>();
+        uint32_t* v0 = ctx->d_v0.as<uint32_t>(); uint32_t* v1 = ctx->d_v1.as<uint32_t>();
+        unsigned long long orand[2];
+        auto sort_on = [&](uint64_t*& ka, uint32_t*& va, uint64_t*& kb, uint32_t*& vb) -> int {
+            unsigned long long init[2] = {0ull, ~0ull};
+            CK(cudaMemcpyAsync(small, init, 16, cudaMemcpyHostToDevice, ctx->st));
+            LAUNCH(k_or_and_u64, std::min<unsigned>(nblk(n, 256), 1184u), 256, 0, ka, n, (unsigned long long*)small);
+            CK(cudaMemcpyAsync(orand, small, 16, cudaMemcpyDeviceToHost, ctx->st));
+            CK(cudaStreamSynchronize(ctx->st));
+            uint32_t bm = varying_byte_mask(orand[0], orand[1]);
+            int res = radix_sort_pairs(ka, va, kb, vb, n, bm, ctx->d_hist.as<uint32_t>(), ctx->d_scan.as<uint32_t>(), ctx->st);
+            if (res) { std::swap(ka, kb); std::swap(va, vb); }
+            return SMC_OK;
+        };
+        LAUNCH(k_init_pairs_frag, nblk(n, 256), 256, 0, ctx->d_frag.as<uint32_t>(), n, k0, v0);
+        { int rc = sort_on(k0, v0, k1, v1); if (rc) return rc; }
+        LAUNCH(k_gather_umi_keys, nblk(n, 256), 256, 0, ctx->d_umi.as<uint64_t>(), v0, n, k0);
+        { int rc = sort_on(k0, v0, k1, v1); if (rc) return rc; }
+        const uint32_t* perm = v0;
+        // dense barcode / fragment ranks
+        CK(ctx->d_flags32a.ensure((size_t)n * 4)); CK(ctx->d_flags32b.ensure((size_t)n * 4));
+        CK(ctx->d_urank.ensure((size_t)n * 4)); CK(ctx->d_frank.ensure((size_t)n * 4));
+        CK(ctx->d_umi_of_urank.ensure((size_t)n * 8));
+        uint32_t* uhead = ctx->d_flags32a.as<uint32_t>(); uint32_t* fhead = ctx->d_flags32b.as<uint32_t>();
+        uint32_t* uex = ctx->d_urank.as<uint32_t>(); uint32_t* fex = ctx->d_frank.as<uint32_t>();
+        LAUNCH(k_heads, nblk(n, 256), 256, 0, ctx->d_umi.as<uint64_t>(), ctx->d_frag.as<uint32_t>(), perm, n, uhead, fhead);
+        exclusive_scan_u32(uhead, uex, n, ctx->d_scan.as<uint32_t>(), small + 10, ctx->st);
+        exclusive_scan_u32(fhead, fex, n, ctx->d_scan.as<uint32_t>(), nullptr, ctx->st);
+        LAUNCH(k_ranks, nblk(n, 256), 256, 0, uhead, fhead, uex, fex, ctx->d_umi.as<uint64_t>(), perm, n, uex, fex,
+               ctx->d_umi_of_urank.as<uint64_t>());
+        // ---------------- K1: per-read records in srank order
+        CK(ctx->d_recs.ensure((size_t)n * sizeof(ReadRec))); CK(ctx->d_ntiles.ensure((size_t)(n + 1) * 4));
+        CK(ctx->d_evoff.ensure((size_t)(n + 1) * 4));
+        CK(cudaMemsetAsync(small + 4, 0, 32, ctx->st));
+        PrepArgs P{};
+        P.n_reads = n; P.perm = perm; P.urank = uex; P.frank = fex;
+        P.ref_id = ctx->d_ref_id.as<int32_t>(); P.pos = ctx->d_pos.as<int32_t>(); P.flag = ctx->d_flag.as<uint16_t>();
+        P.mapq = ctx->d_mapq.as<uint8_t>(); P.nm = ctx->d_nm.as<int32_t>(); P.l_seq = ctx->d_lseq.as<int32_t>();
+        P.seq_off = ctx->d_seq_off.as<int64_t>(); P.qual_off = ctx->d_qual_off.as<int64_t>(); P.cigar_off = ctx->d_cig_off.as<int64_t>();
+        P.n_cigar = ctx->d_ncig.as<uint16_t>(); P.cigar = ctx->d_cigar.as<uint32_t>();
+        P.loci_key = ctx->d_loci_key.as<uint64_t>(); P.n_loci = nl;
+        P.minMQ = ctx->prm.minMQ; P.mismatchThr = ctx->prm.mismatchThr;
+        P.recs = ctx->d_recs.as<ReadRec>(); P.ntiles = ctx->d_ntiles.as<uint32_t>(); P.gflags = small + 5;
+        LAUNCH(k_read_prep, nblk(n, 256), 256, 0, P);
+        exclusive_scan_u32(ctx->d_ntiles.as<uint32_t>(), ctx->d_evoff.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + 4, ctx->st);
+        uint32_t h[2];
+        CK(cudaMemcpyAsync(h, small + 4, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        if (h[1] & GF_BAD_READ) { ctx->err = "a read has l_seq or clip length > 65535 (unsupported)"; return SMC_E_LIMIT; }
+        NE = h[0];
+    }
+    CK(cudaEventRecord(ctx->ev[3], ctx->st));
+    // ---------------- K2b: (read x tile) events, stable sort by tile
+    const uint64_t* ev_key_sorted = nullptr; const uint32_t* ev_read_sorted = nullptr;
+    CK(ctx->d_tile_off.ensure((size_t)(n_tiles + 2) * 4)); CK(ctx->d_unit_cnt.ensure((size_t)(n_tiles + 2) * 4));
+    CK(ctx->d_unit_off.ensure((size_t)(n_tiles + 2) * 4));
+    if (NE > 0) {
+        CK(ctx->d_ek0.ensure((size_t)NE * 8)); CK(ctx->d_ek1.ensure((size_t)NE * 8));
+        CK(ctx->d_ev0.ensure((size_t)NE * 4)); CK(ctx->d_ev1.ensure((size_t)NE * 4));
+        const uint32_t rs_blocks = (uint32_t)((NE + RS_TILE - 1) / RS_TILE);
+        CK(ctx->d_hist.ensure((size_t)256 * rs_blocks * 4 + 1024));
+        CK(ctx->d_scan.ensure((size_t)scan_scratch_words(std::max<int64_t>((int64_t)256 * rs_blocks, (int64_t)n_tiles + 2)) * 4 + 1024));
+        LAUNCH(k_expand, nblk(n, 256), 256, 0, ctx->d_recs.as<ReadRec>(), ctx->d_evoff.as<uint32_t>(), n, ctx->d_ek0.as<uint64_t>(),
+               ctx->d_ev0.as<uint32_t>());
+        uint32_t bm = 0;
+        for (int b = 0; b < 4; ++b) if (((uint64_t)(n_tiles - 1) >> (8 * b)) & 0xff) bm |= 1u << b;
+        int res = radix_sort_pairs(ctx->d_ek0.as<uint64_t>(), ctx->d_ev0.as<uint32_t>(), ctx->d_ek1.as<uint64_t>(), ctx->d_ev1.as<uint32_t>(),
+                                   NE, bm, ctx->d_hist.as<uint32_t>(), ctx->d_scan.as<uint32_t>(), ctx->st);
+        ev_key_sorted = res ? ctx->d_ek1.as<uint64_t>() : ctx->d_ek0.as<uint64_t>();
+        ev_read_sorted = res ? ctx->d_ev1.as<uint32_t>() : ctx->d_ev0.as<uint32_t>();
+        LAUNCH(k_tile_offsets, nblk((int64_t)n_tiles + 1, 256), 256, 0, ev_key_sorted, NE, n_tiles, ctx->d_tile_off.as<uint32_t>());
+    } else {
+        CK(cudaMemsetAsync(ctx->d_tile_off.p, 0, (size_t)(n_tiles + 2) * 4, ctx->st));
+        CK(ctx->d_scan.ensure((size_t)scan_scratch_words((int64_t)n_tiles + 2) * 4 + 1024));
+    }
+    LAUNCH(k_unit_counts, nblk((int64_t)n_tiles + 1, 256), 256, 0, ctx->d_tile_off.as<uint32_t>(), n_tiles, ctx->chunk,
+           ctx->d_unit_cnt.as<uint32_t>());
+    exclusive_scan_u32(ctx->d_unit_cnt.as<uint32_t>(), ctx->d_unit_off.as<uint32_t>(), (int64_t)n_tiles + 1, ctx->d_scan.as<uint32_t>(),
+                       nullptr, ctx->st);
+    ctx->tm.n_tile_events = NE;
+    ctx->ev_read_sorted = ev_read_sorted;
+    ctx->n_tiles = n_tiles; ctx->n_tile_events = NE;
+    (void)ev_key_sorted;
+    CK(cudaEventRecord(ctx->ev[4], ctx->st));
+    return run_pileup_and_stats(ctx, n_tiles, NE);
+}
+
+static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
+    const int64_t nl = ctx->n_loci;
+    uint32_t* small = ctx->d_small.as<uint32_t>();
+    const uint32_t* ev_read = ctx->ev_read_sorted;
+    const size_t nlz = (size_t)(nl ? nl : 1);
+    CK(ctx->d_loc.ensure(nlz * SMC_NLOC * 4)); CK(ctx->d_cnt.ensure(nlz * SMC_NFIXED * SMC_NCNT * 4));
+    CK(ctx->d_limb.ensure(nlz * SMC_NFIXED * 3 * 8)); CK(ctx->d_pi.ensure(nlz * SMC_NFIXED * 8));
+    CK(ctx->d_max.ensure(nlz * 4)); CK(ctx->d_second.ensure(nlz * 4)); CK(ctx->d_alt.ensure(nlz * 4));
+    CK(ctx->d_altpi.ensure(nlz * 8)); CK(ctx->d_secondpi.ensure(nlz * 8)); CK(ctx->d_fl1.ensure(nlz * 4)); CK(ctx->d_fl2.ensure(nlz * 4));
+    CK(ctx->d_bial.ensure(nlz)); CK(ctx->d_fp.ensure(nlz * 8 * 8)); CK(ctx->d_for.ensure(nlz * 8 * 8));
+    CK(ctx->d_dyn_first.ensure((nlz + 2) * 4));
+    if (ctx->dyn_cap == 0) {
+        uint32_t want = 1u << 16;
+        while ((int64_t)want < 2 * nl && want < (1u << 28)) want <<= 1;
+        ctx->dyn_cap = want;
+    }
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        const uint32_t cap = ctx->dyn_cap;
+        CK(ctx->d_dkey.ensure((size_t)cap * 8)); CK(ctx->d_drep_read.ensure((size_t)cap * 4)); CK(ctx->d_drep_qpos.ensure((size_t)cap * 4));
+        CK(ctx->d_dlen.ensure((size_t)cap * 4)); CK(ctx->d_dcnt.ensure((size_t)cap * SMC_NCNT * 4)); CK(ctx->d_dlimb.ensure((size_t)cap * 24));
+        CK(ctx->d_diskey.ensure(cap));
+        CK(cudaMemsetAsync(ctx->d_dkey.p, 0xff, (size_t)cap * 8, ctx->st));
+        CK(cudaMemsetAsync(ctx->d_dcnt.p, 0, (size_t)cap * SMC_NCNT * 4, ctx->st));
+        CK(cudaMemsetAsync(ctx->d_dlimb.p, 0, (size_t)cap * 24, ctx->st));
+        CK(cudaMemsetAsync(ctx->d_diskey.p, 0, cap, ctx->st));
+        CK(cudaMemsetAsync(ctx->d_loc.p, 0, nlz * SMC_NLOC * 4, ctx->st));
+        CK(cudaMemsetAsync(ctx->d_cnt.p, 0, nlz * SMC_NFIXED * SMC_NCNT * 4, ctx->st));
+        CK(cudaMemsetAsync(ctx->d_limb.p, 0, nlz * SMC_NFIXED * 3 * 8, ctx->st));
+        CK(cudaMemsetAsync(small + 5, 0, 24, ctx->st));     // gflags, dyn count, n_tasks, cvg sum
+        if (NE > 0) {
+            K3Args A{};
+            A.recs = ctx->d_recs.as<ReadRec>(); A.ev_read = ev_read; A.tile_off = ctx->d_tile_off.as<uint32_t>();
+            A.unit_off = ctx->d_unit_off.as<uint32_t>(); A.n_tiles = n_tiles; A.chunk = ctx->chunk;
+            A.loci_pos = ctx->d_loci_pos.as<int32_t>(); A.n_loci = nl;
+            A.seq = ctx->d_seq.as<uint8_t>(); A.qual = ctx->d_qual.as<uint8_t>(); A.cigar = ctx->d_cigar.as<uint32_t>();
+            A.bqtab = ctx->d_bqtab.as<double>(); A.pcrtab = ctx->d_pcrtab.as<double>(); A.pcr_nmax = PCR_NMAX;
+            A.minBQ = ctx->prm.minBQ; A.mtDrop = ctx->prm.mtDrop; A.primerDist = ctx->prm.primerDist;
+            A.smt = ctx->prm.rpb < 1.5 ? 2.0 : ctx->prm.rpb < 3.0 ? 3.0 : 4.0;                     // smCounter.py:303-308
+            A.keep_idx = ctx->has_keep ? ctx->d_keep_idx.as<int32_t>() : nullptr;
+            A.keep_off = ctx->d_keep_off.as<int64_t>(); A.keep_umi = ctx->d_keep_umi.as<uint64_t>();
+            A.umi_of_urank = ctx->d_umi_of_urank.as<uint64_t>();
+            A.loc = ctx->d_loc.as<int32_t>(); A.cnt = ctx->d_cnt.as<int32_t>(); A.limb = ctx->d_limb.as<unsigned long long>();
+            A.dkey = ctx->d_dkey.as<unsigned long long>(); A.dmask = cap - 1; A.drep_read = ctx->d_drep_read.as<uint32_t>();
+            A.drep_qpos = ctx->d_drep_qpos.as<int32_t>(); A.dlen = ctx->d_dlen.as<int32_t>(); A.dcnt = ctx->d_dcnt.as<int32_t>();
+            A.dlimb = ctx->d_dlimb.as<unsigned long long>(); A.diskey = ctx->d_diskey.as<uint8_t>(); A.dcount = small + 6; A.gflags = small + 5;
+            A.list_idx = nullptr;
+            const int64_t max_units = (int64_t)n_tiles + NE / ctx->chunk + 1;
+            CK(cudaEventRecord(ctx->ev[8], ctx->st));
+            LAUNCH(k_pileup, nblk(max_units, K3_WARPS), K3_WARPS * 32, K3_SMEM_BYTES, A);
+            CK(cudaEventRecord(ctx->ev[9], ctx->st));
+        }
+        uint32_t h[3];
+        CK(cudaMemcpyAsync(h, small + 5, 12, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        CK(cudaGetLastError());
+        if (!(h[0] & GF_DYN_FULL)) { ctx->n_dyn = h[1]; break; }
+        if (ctx->dyn_cap >= (1u << 28) || attempt == 5) { ctx->err = "dynamic allele table overflow"; return SMC_E_OVERFLOW; }
+        ctx->dyn_cap <<= 2;
+    }
+    CK(cudaEventRecord(ctx->ev[5], ctx->st));
+    // ---------------- dynamic alleles -> sorted rows
+    const int64_t nd = ctx->n_dyn;
+    const size_t ndz = (size_t)(nd ? nd : 1);
+    CK(ctx->d_s_key.ensure(ndz * 8)); CK(ctx->d_s_cnt.ensure(ndz * SMC_NCNT * 4)); CK(ctx->d_s_limb.ensure(ndz * 24));
+    CK(ctx->d_s_iskey.ensure(ndz)); CK(ctx->d_s_pi.ensure(ndz * 8)); CK(ctx->d_s_rep_read.ensure(ndz * 4));
+    CK(ctx->d_s_rep_qpos.ensure(ndz * 4)); CK(ctx->d_s_len.ensure(ndz * 4));
+    if (nd > 0) {
+        CK(ctx->d_lk0.ensure(ndz * 8)); CK(ctx->d_lk1.ensure(ndz * 8)); CK(ctx->d_lv0.ensure(ndz * 4)); CK(ctx->d_lv1.ensure(ndz * 4));
+        CK(cudaMemsetAsync(small + 6, 0, 4, ctx->st));
+        LAUNCH(k_dyn_collect, nblk(ctx->dyn_cap, 256), 256, 0, ctx->d_dkey.as<unsigned long long>(), ctx->dyn_cap, ctx->d_lk0.as<uint64_t>(),
+               ctx->d_lv0.as<uint32_t>(), small + 6);
+        const uint32_t rs_blocks = (uint32_t)((nd + RS_TILE - 1) / RS_TILE);
+        CK(ctx->d_hist.ensure((size_t)256 * rs_blocks * 4 + 1024));
+        CK(ctx->d_scan.ensure((size_t)scan_scratch_words((int64_t)256 * rs_blocks) * 4 + 1024));
+        int res = radix_sort_pairs(ctx->d_lk0.as<uint64_t>(), ctx->d_lv0.as<uint32_t>(), ctx->d_lk1.as<uint64_t>(), ctx->d_lv1.as<uint32_t>(), nd,
+                                   0xffu, ctx->d_hist.as<uint32_t>(), ctx->d_scan.as<uint32_t>(), ctx->st);
+        const uint64_t* lk = res ? ctx->d_lk1.as<uint64_t>() : ctx->d_lk0.as<uint64_t>();
+        const uint32_t* lv = res ? ctx->d_lv1.as<uint32_t>() : ctx->d_lv0.as<uint32_t>();
+        LAUNCH(k_dyn_gather, nblk(nd, 128), 128, 0, lk, lv, nd, ctx->d_dcnt.as<int32_t>(), ctx->d_dlimb.as<unsigned long long>(),
+               ctx->d_diskey.as<uint8_t>(), ctx->d_drep_read.as<uint32_t>(), ctx->d_drep_qpos.as<int32_t>(), ctx->d_dlen.as<int32_t>(),
+               ctx->d_s_key.as<unsigned long long>(), ctx->d_s_cnt.as<int32_t>(), ctx->d_s_limb.as<unsigned long long>(),
+               ctx->d_s_iskey.as<uint8_t>(), ctx->d_s_rep_read.as<uint32_t>(), ctx->d_s_rep_qpos.as<int32_t>(), ctx->d_s_len.as<int32_t>());
+    }
+    LAUNCH(k_dyn_first, nblk(nl + 1, 256), 256, 0, ctx->d_s_key.as<unsigned long long>(), nd, nl, ctx->d_dyn_first.as<uint32_t>());
+    // ---------------- K4
+    uint32_t n_tasks_h = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (ctx->task_cap == 0) ctx->task_cap = 1u << 16;
+        CK(ctx->d_tasks.ensure((size_t)ctx->task_cap * sizeof(FisherTask)));
+        CK(cudaMemsetAsync(small + 7, 0, 4, ctx->st));
+        K4Args B{};
+        B.n_loci = nl; B.ref_base = ctx->d_loci_base.as<uint8_t>(); B.loc = ctx->d_loc.as<int32_t>(); B.cnt = ctx->d_cnt.as<int32_t>();
+        B.limb = ctx->d_limb.as<unsigned long long>(); B.pi = ctx->d_pi.as<double>();
+        B.n_dyn = nd; B.dyn_key = ctx->d_s_key.as<unsigned long long>(); B.dyn_cnt = ctx->d_s_cnt.as<int32_t>();
+        B.dyn_limb = ctx->d_s_limb.as<unsigned long long>(); B.dyn_iskey = ctx->d_s_iskey.as<uint8_t>(); B.dyn_pi = ctx->d_s_pi.as<double>();
+        B.dyn_first = ctx->d_dyn_first.as<uint32_t>();
+        B.keep_idx = ctx->has_keep ? ctx->d_keep_idx.as<int32_t>() : nullptr;
+        B.ds = ctx->prm.maxMT > 0 ? ctx->prm.maxMT : (int)std::llround(2.0 * (double)ctx->prm.mtDepth);   // smCounter.py:486
+        B.max_allele = ctx->d_max.as<int32_t>(); B.second_allele = ctx->d_second.as<int32_t>(); B.alt_allele = ctx->d_alt.as<int32_t>();
+        B.alt_pi = ctx->d_altpi.as<double>(); B.second_pi = ctx->d_secondpi.as<double>(); B.fl1 = ctx->d_fl1.as<uint32_t>();
+        B.fl2 = ctx->d_fl2.as<uint32_t>(); B.biallelic = ctx->d_bial.as<uint8_t>(); B.fisher_p = ctx->d_fp.as<double>();
+        B.fisher_or = ctx->d_for.as<double>(); B.tasks = ctx->d_tasks.as<FisherTask>(); B.n_tasks = small + 7; B.task_cap = ctx->task_cap;
+        LAUNCH(k_call, nblk(nl, 128), 128, 0, B);
+        CK(cudaMemcpyAsync(&n_tasks_h, small + 7, 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        if (n_tasks_h <= ctx->task_cap) break;
+        ctx->task_cap = n_tasks_h + n_tasks_h / 4 + 1024;      // grow and redo the (cheap) call kernel
+    }
+    if (n_tasks_h > 0)
+        LAUNCH(k_fisher, nblk(n_tasks_h, 128), 128, 0, ctx->d_tasks.as<FisherTask>(), small + 7, ctx->task_cap, nl, ctx->d_fp.as<double>(),
+               ctx->d_for.as<double>(), ctx->d_fl1.as<uint32_t>(), ctx->d_fl2.as<uint32_t>());
+    LAUNCH(k_sum_cvg, std::min<unsigned>(nblk(nl, 256), 592u), 256, 0, ctx->d_loc.as<int32_t>() + (size_t)SMC_L_CVG * nl, nl,
+           (unsigned long long*)(small + 8));
+    CK(cudaEventRecord(ctx->ev[6], ctx->st));
+    unsigned long long cvgsum = 0;
+    CK(cudaMemcpyAsync(&cvgsum, small + 8, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaGetLastError());
+    cudaEventElapsedTime(&ctx->tm.ms_prep, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->tm.ms_sort, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&ctx->tm.ms_pileup, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&ctx->tm.ms_stats, ctx->ev[5], ctx->ev[6]);
+    cudaEventElapsedTime(&ctx->tm.ms_total_device, ctx->ev[2], ctx->ev[6]);
+    ctx->tm.ms_k_pileup = 0.f;
+    if (NE > 0) cudaEventElapsedTime(&ctx->tm.ms_k_pileup, ctx->ev[8], ctx->ev[9]);
+    ctx->tm.n_pileup_events = (int64_t)cvgsum;
+    ctx->tm.n_dyn = nd; ctx->tm.n_fisher = n_tasks_h;
+    ctx->tm.kernel_launches = g_launches;
+    ctx->ran = true;
+    return SMC_OK;
+}
+
+extern "C" int smc_download(smc_ctx* ctx, smc_out* out) {
+    if (!ctx) return SMC_E_ARG;
+    if (!ctx->ran) { ctx->err = "smc_download: nothing has been run"; return SMC_E_STATE; }
+    if (!out || out->n_loci != ctx->n_loci) { ctx->err = "smc_download: smc_out.n_loci does not match the uploaded loci"; return SMC_E_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    const size_t nl = (size_t)ctx->n_loci;
+    const int64_t nd = ctx->n_dyn;
+    out->n_dyn = nd;
+    if (nd > out->dyn_capacity) { ctx->err = "smc_download: dyn_capacity too small (n_dyn reported in smc_out.n_dyn)"; return SMC_E_LIMIT; }
+    int64_t bytes = 0;
+    CK(cudaEventRecord(ctx->ev[0], ctx->st));
+#define DOWN(dst, buf, count, T)                                                                                \
+    do {                                                                                                        \
+        size_t b__ = (size_t)(count) * sizeof(T);                                                               \
+        if (b__ && (dst)) { CK(cudaMemcpyAsync((dst), (buf).p, b__, cudaMemcpyDeviceToHost, ctx->st)); bytes += b__; } \
+    } while (0)
+    DOWN(out->loc, ctx->d_loc, nl * SMC_NLOC, int32_t); DOWN(out->cnt, ctx->d_cnt, nl * SMC_NFIXED * SMC_NCNT, int32_t);
+    DOWN(out->pi, ctx->d_pi, nl * SMC_NFIXED, double); DOWN(out->max_allele, ctx->d_max, nl, int32_t);
+    DOWN(out->second_allele, ctx->d_second, nl, int32_t); DOWN(out->alt_allele, ctx->d_alt, nl, int32_t);
+    DOWN(out->alt_pi, ctx->d_altpi, nl, double); DOWN(out->second_pi, ctx->d_secondpi, nl, double);
+    DOWN(out->fl1, ctx->d_fl1, nl, uint32_t); DOWN(out->fl2, ctx->d_fl2, nl, uint32_t); DOWN(out->biallelic, ctx->d_bial, nl, uint8_t);
+    DOWN(out->fisher_p, ctx->d_fp, nl * 8, double); DOWN(out->fisher_or, ctx->d_for, nl * 8, double);
+    DOWN(out->dyn_cnt, ctx->d_s_cnt, (size_t)nd * SMC_NCNT, int32_t); DOWN(out->dyn_pi, ctx->d_s_pi, nd, double);
+    DOWN(out->dyn_iskey, ctx->d_s_iskey, nd, uint8_t); DOWN(out->dyn_rep_read, ctx->d_s_rep_read, nd, uint32_t);
+    DOWN(out->dyn_rep_qpos, ctx->d_s_rep_qpos, nd, int32_t); DOWN(out->dyn_len, ctx->d_s_len, nd, int32_t);
+#undef DOWN
+    std::vector<unsigned long long> keys((size_t)nd);
+    std::vector<uint32_t> first(nl + 1);
+    if (nd) CK(cudaMemcpyAsync(keys.data(), ctx->d_s_key.p, (size_t)nd * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(first.data(), ctx->d_dyn_first.p, (nl + 1) * 4, cudaMemcpyDeviceToHost, ctx->st));
+    bytes += nd * 8 + (int64_t)(nl + 1) * 4;
+    CK(cudaEventRecord(ctx->ev[1], ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    for (int64_t j = 0; j < nd; ++j) {
+        unsigned long long k = keys[(size_t)j];
+        if (out->dyn_locus) out->dyn_locus[j] = (int32_t)(k >> DYN_LOCUS_SHIFT);
+        if (out->dyn_kind) out->dyn_kind[j] = (uint8_t)((k >> 40) & 3u);
+        if (out->dyn_site) out->dyn_site[j] = (uint8_t)((k >> 36) & 15u);
+    }
+    if (out->dyn_first) for (size_t i = 0; i <= nl; ++i) out->dyn_first[i] = first[i];
+    cudaEventElapsedTime(&ctx->tm.ms_d2h, ctx->ev[0], ctx->ev[1]);
+    ctx->tm.bytes_d2h = bytes;
+    return SMC_OK;
+}
+
+extern "C" int smc_call_batch(smc_ctx* ctx, const smc_reads_soa* reads, const smc_loci* loci, const smc_umi_keep* keep, smc_out* out) {
+    int rc = smc_upload(ctx, reads, loci, keep);
+    if (rc) return rc;
+    rc = smc_run_resident(ctx);
+    if (rc) return rc;
+    return smc_download(ctx, out);
+}
+
+extern "C" int smc_get_timings(smc_ctx* ctx, smc_timings* t) {
+    if (!ctx || !t) return SMC_E_ARG;
+    *t = ctx->tm;
+    return SMC_OK;
+}
+
+extern "C" int smc_list_barcodes(smc_ctx* ctx, int64_t n, const int64_t* locus, int64_t* off_out, uint64_t* umi_out, int64_t umi_capacity) {
+    if (!ctx) return SMC_E_ARG;
+    (void)n; (void)locus; (void)off_out; (void)umi_out; (void)umi_capacity;
+    ctx->err = "smc_list_barcodes: not implemented yet";
+    return SMC_E_STATE;
+}

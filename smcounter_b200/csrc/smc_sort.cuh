@@ -1,0 +1,215 @@
+// Hand-written device-wide exclusive scan and stable LSD radix sort (u64 key, u32 payload).
+//
+// K2 of the pipeline ("segmented radix sort"): reads are ordered by (barcode, fragment, BAM index) and the
+// (read x 32-locus tile) events by tile, so that every tile's events form one segment in which barcodes and
+// fragments are contiguous runs in BAM order.  Both sorts are LSD passes of 8 bits over only the bits that vary.
+// HBM-bound: each pass reads 12 B and writes 12 B per element; histogram, scan and scatter are separate kernels.
+#pragma once
+#include "smc_common.cuh"
+
+// ---------------------------------------------------------------- scan -------------------------------------
+#define SCAN_THREADS 256
+#define SCAN_ITEMS   8
+#define SCAN_TILE    (SCAN_THREADS * SCAN_ITEMS)
+
+// Exclusive scan of one tile per block; block totals to sums[blockIdx.x].
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_tile(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* sums) {   // in == out allowed
+    __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0u;
+        tsum += v[i];
+    }
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane_id() >= (uint32_t)d) incl += t;
+    }
+    int w = threadIdx.x >> 5;
+    if (lane_id() == 31) warp_tot[w] = incl;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_THREADS / 32; ++i) {
+        uint32_t t = warp_tot[i];
+        if (i < w) woff += t;
+        total += t;
+    }
+    uint32_t run = woff + incl - tsum;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+    }
+    if (threadIdx.x == 0 && sums) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_add(uint32_t* __restrict__ out, int64_t n, const uint32_t* __restrict__ offs) {
+    uint32_t o = offs[blockIdx.x];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < n) out[base + i] += o;
+}
+
+// scratch must hold at least scan_scratch_words(n) uint32.  If total != nullptr the grand total is stored there.
+static inline int64_t scan_scratch_words(int64_t n) {
+    int64_t w = 0;
+    while (n > 1) { n = (n + SCAN_TILE - 1) / SCAN_TILE; w += n + 1; }
+    return w + 2;
+}
+
+static int g_launches = 0;   // kernel launch counter (reported through smc_timings)
+
+static void exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* scratch, uint32_t* total,
+                               cudaStream_t st) {
+    if (n <= 0) {
+        if (total) cudaMemsetAsync(total, 0, sizeof(uint32_t), st);
+        return;
+    }
+    int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (nb == 1) {
+        k_scan_tile<<<1, SCAN_THREADS, 0, st>>>(in, out, n, total);
+        ++g_launches;
+        return;
+    }
+    uint32_t* sums = scratch;
+    k_scan_tile<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, sums);
+    ++g_launches;
+    exclusive_scan_u32(sums, sums, nb, scratch + nb + 1, total, st);
+    k_scan_add<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(out, n, sums);
+    ++g_launches;
+}
+
+// ---------------------------------------------------------------- radix sort --------------------------------
+#define RS_WARPS   8
+#define RS_THREADS (RS_WARPS * 32)
+#define RS_ITEMS   8
+#define RS_TILE    (RS_THREADS * RS_ITEMS)
+
+// Element order inside a tile: warp w owns [w*256, w*256+256), iteration it covers 32 consecutive elements.
+__device__ __forceinline__ int64_t rs_index(int64_t tile_base, int w, int it, int lane) {
+    return tile_base + (int64_t)w * (32 * RS_ITEMS) + it * 32 + lane;
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_radix_hist(const uint64_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ hist, uint32_t nblocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t tb = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; ++it) {
+        int64_t i = rs_index(tb, w, it, lane);
+        if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_radix_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t* __restrict__ keys_out,
+                uint32_t* __restrict__ vals_out, int64_t n, int shift, const uint32_t* __restrict__ hist_scanned,
+                uint32_t nblocks) {
+    __shared__ uint32_t wh[RS_WARPS][256];
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wh[0][0])[i] = 0;
+    __syncthreads();
+    int64_t tb = (int64_t)blockIdx.x * RS_TILE;
+    uint64_t k[RS_ITEMS];
+    uint32_t v[RS_ITEMS];
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; ++it) {
+        int64_t i = rs_index(tb, w, it, lane);
+        if (i < n) {
+            k[it] = keys[i];
+            v[it] = vals[i];
+            atomicAdd(&wh[w][(uint32_t)(k[it] >> shift) & 255u], 1u);
+        }
+    }
+    __syncthreads();
+    {   // per digit: global base of this block, then exclusive prefix over the warps
+        uint32_t d = threadIdx.x;
+        uint32_t run = hist_scanned[(size_t)d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) {
+            uint32_t t = wh[ww][d];
+            wh[ww][d] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; ++it) {
+        int64_t i = rs_index(tb, w, it, lane);
+        bool valid = i < n;
+        uint32_t active = __ballot_sync(FULL_MASK, valid);
+        if (valid) {
+            uint32_t d = (uint32_t)(k[it] >> shift) & 255u;
+            uint32_t peers = __match_any_sync(active, d);
+            uint32_t rank = __popc(peers & lt);
+            int leader = __ffs(peers) - 1;
+            uint32_t off = 0;
+            if (lane == leader) {
+                off = wh[w][d];
+                wh[w][d] = off + __popc(peers);
+            }
+            off = __shfl_sync(peers, off, leader);
+            keys_out[off + rank] = k[it];
+            vals_out[off + rank] = v[it];
+        }
+        __syncwarp();
+    }
+}
+
+// Stable sort of (keys, vals) on the key bytes selected by `byte_mask` (bit b set = byte b varies).
+// Ping-pongs between (k0,v0) and (k1,v1); returns 0 if the result is in (k0,v0), 1 if in (k1,v1).
+static int radix_sort_pairs(uint64_t* k0, uint32_t* v0, uint64_t* k1, uint32_t* v1, int64_t n, uint32_t byte_mask,
+                            uint32_t* hist, uint32_t* scan_scratch, cudaStream_t st) {
+    if (n <= 1) return 0;
+    uint32_t nblocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+    int cur = 0;
+    for (int b = 0; b < 8; ++b) {
+        if (!((byte_mask >> b) & 1u)) continue;
+        uint64_t* ki = cur ? k1 : k0; uint32_t* vi = cur ? v1 : v0;
+        uint64_t* ko = cur ? k0 : k1; uint32_t* vo = cur ? v0 : v1;
+        k_radix_hist<<<nblocks, RS_THREADS, 0, st>>>(ki, n, b * 8, hist, nblocks);
+        ++g_launches;
+        exclusive_scan_u32(hist, hist, (int64_t)256 * nblocks, scan_scratch, nullptr, st);
+        k_radix_scatter<<<nblocks, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n, b * 8, hist, nblocks);
+        ++g_launches;
+        cur ^= 1;
+    }
+    return cur;
+}
+
+// bitwise OR / AND of an array of u64 (to find the key bytes that vary)
+__global__ void k_or_and_u64(const uint64_t* __restrict__ a, int64_t n, unsigned long long* __restrict__ out /* [2]: or, and */) {
+    unsigned long long o = 0, d = ~0ull;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long x = a[i];
+        o |= x; d &= x;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        o |= __shfl_xor_sync(FULL_MASK, o, s);
+        d &= __shfl_xor_sync(FULL_MASK, d, s);
+    }
+    if (lane_id() == 0) { atomicOr(&out[0], o); atomicAnd(&out[1], d); }
+}
+
+static inline uint32_t varying_byte_mask(uint64_t orv, uint64_t andv) {
+    uint64_t diff = orv ^ andv;   // bits that are not constant over the array
+    uint32_t m = 0;
+    for (int b = 0; b < 8; ++b)
+        if ((diff >> (8 * b)) & 0xffull) m |= 1u << b;
+    return m;
+}

@@ -1,0 +1,217 @@
+"""Host-side string work of the hot path: turns the device results into the reference's 45-column rows.
+
+Covers what stays on the host by design:
+  * allele strings ('INS|s|s+ins', 'DEL|s+del|s', smCounter.py:374,396) -- built from a representative read / the FASTA;
+  * convertToVcf()            smCounter.py:103-117;
+  * isHPorLowComp()           smCounter.py:122-177 (needs reference windows; only for candidates with PI >= 5);
+  * FILTER string assembly    smCounter.py:184-269 (device supplies the bits, order of tags as in the reference);
+  * bi-allelic resolution     smCounter.py:553-573;
+  * the output vector         smCounter.py:575-600 with Python-2 round()/str() semantics.
+"""
+from __future__ import annotations
+
+from decimal import Decimal, ROUND_HALF_UP
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import (A_A, A_C, A_G, A_T, C_ALLELE, C_MT, C_STRONG, F_DP, F_EVALUATED, F_HPGATE, F_LM, F_LOWQ, F_LSM, F_PRIMERCP,
+                   F_R1CP, F_R2CP, F_SB, FIXED_NAMES, K_BASE, K_DEL, K_INS, L_ALLFRAG, L_ALLMT, L_CVG, L_MT3, L_MT5, L_MT7,
+                   L_MT10, L_STATUS, L_USEDFRAG, L_USEDMT, SMC_NFIXED, ST_BAD_MASK, ST_NEED_DOWNSAMPLE, ST_UMI_OVERFLOW,
+                   ST_ZERO_COVERAGE)
+from .soa import NT16
+
+headerAll = ('CHROM', 'POS', 'REF', 'ALT', 'TYPE', 'DP', 'FR', 'MT', 'UFR', 'UMT', 'PI', 'VDP', 'VAF', 'VMT', 'VMF', 'VSM',
+             'DP_A', 'DP_T', 'DP_G', 'DP_C', 'AF_A', 'AF_T', 'AF_G', 'AF_C', 'MT_3RPM', 'MT_5RPM', 'MT_7RPM', 'MT_10RPM',
+             'UMT_A', 'UMT_T', 'UMT_G', 'UMT_C', 'UMF_A', 'UMF_T', 'UMF_G', 'UMF_C', 'VSM_A', 'VSM_T', 'VSM_G', 'VSM_C',
+             'PI_A', 'PI_T', 'PI_G', 'PI_C', 'FILTER')                          # smCounter.py:743
+headerVariants = ('CHROM', 'POS', 'REF', 'ALT', 'TYPE', 'DP', 'MT', 'UMT', 'PI', 'THR', 'VMT', 'VMF', 'VSM', 'FILTER')   # :744
+
+
+def py2round(x: float, nd: int) -> float:
+    """Python-2.7 round(): correctly rounded, exact decimal ties away from zero (Py3 rounds them to even)."""
+    r = round(x, nd)
+    s = x * (2 * 10 ** nd)
+    if s == int(s):       # possibly an exact halfway case -> decide on the exact binary value
+        return float(Decimal(x).quantize(Decimal(1).scaleb(-nd), rounding=ROUND_HALF_UP))
+    return r
+
+
+def py2str(v) -> str:
+    """Python-2.7 str() of the value types that reach the output vector (smCounter.py:599)."""
+    if isinstance(v, float):
+        s = "%.12g" % v
+        if "." not in s and "e" not in s and "n" not in s:
+            s += ".0"
+        return s
+    if isinstance(v, (int, np.integer)):
+        return "%d" % int(v)
+    return str(v)
+
+
+def convert_to_vcf(origRef: str, origAlt: str):
+    """smCounter.py:103-117."""
+    vtype, ref, alt = ".", origRef, origAlt
+    if len(origAlt) == 1:
+        vtype = "SNP"
+    elif origAlt == "DEL":
+        vtype = "SDEL"
+    else:
+        vals = origAlt.split("|")
+        if vals[0] in ("DEL", "INS"):
+            vtype = "INDEL"
+            ref, alt = vals[1], vals[2]
+    return ref, alt, vtype
+
+
+def is_hp_or_low_comp(chrom, pos, length, refb, altb, refs):
+    """smCounter.py:122-177: homopolymer >= length and low-complexity (top-2 nt >= 99 % in a 2*length window)."""
+    chromLength = refs.get_reference_length(chrom)
+    pos0 = int(pos) - 1
+    L = refs.fetch(chrom, max(0, pos0 - length), pos0).upper()
+    Rr = refs.fetch(chrom, pos0 + len(refb), min(pos0 + len(refb) + length, chromLength)).upper()
+    Ra = refs.fetch(chrom, pos0 + len(altb), min(pos0 + len(altb) + length, chromLength)).upper()
+    refSeq, altSeq = L + refb + Rr, L + altb + Ra
+    homop = any((c * length) in refSeq or (c * length) in altSeq for c in "ATGC")
+    len2 = 2 * length
+    L2 = refs.fetch(chrom, max(0, pos0 - len2), pos0).upper()
+    Rr2 = refs.fetch(chrom, pos0 + len(refb), min(pos0 + len(refb) + len2, chromLength)).upper()
+    Ra2 = refs.fetch(chrom, pos0 + len(altb), min(pos0 + len(altb) + len2, chromLength)).upper()
+    lowcomp = False
+    for seq in (L2 + refb + Rr2, L2 + altb + Ra2):
+        for i in range(len(seq) - len2):
+            sub = seq[i:i + len2]
+            cs = sorted((sub.count("A"), sub.count("T"), sub.count("G"), sub.count("C")), reverse=True)
+            if 1.0 * (cs[0] + cs[1]) / len2 >= 0.99:
+                lowcomp = True
+                break
+        if lowcomp:
+            break
+    return homop, lowcomp
+
+
+class AlleleNamer:
+    """Allele reference (0..4 fixed, 5+j dynamic row j) -> the reference's allele string."""
+
+    def __init__(self, res, reads, loci, chroms, refs):
+        self.res, self.reads, self.loci, self.chroms, self.refs = res, reads, loci, chroms, refs
+        self._cache = {}
+
+    def _read_bases(self, r, q0, n):
+        so = int(self.reads.seq_off[r])
+        out = []
+        for q in range(q0, q0 + n):
+            b = int(self.reads.seq[so + (q >> 1)])
+            out.append(NT16[(b & 15) if (q & 1) else (b >> 4)])
+        return "".join(out)
+
+    def name(self, a: int) -> str:
+        if a < SMC_NFIXED:
+            return FIXED_NAMES[a]
+        j = a - SMC_NFIXED
+        if j in self._cache:
+            return self._cache[j]
+        res = self.res
+        kind, site, ln = int(res.dyn_kind[j]), NT16[int(res.dyn_site[j])], int(res.dyn_len[j])
+        if kind == K_BASE:
+            s = site
+        elif kind == K_INS:                                                     # smCounter.py:372-374
+            ins = self._read_bases(int(res.dyn_rep_read[j]), int(res.dyn_rep_qpos[j]) + 1, ln)
+            s = "INS|" + site + "|" + site + ins
+        else:                                                                   # smCounter.py:393-396
+            i = int(res.dyn_locus[j])
+            chrom = self.chroms[int(self.loci.ref_id[i])]
+            p1 = int(self.loci.pos0[i]) + 1
+            deleted = self.refs.fetch(chrom, p1, p1 + ln).upper()
+            s = "DEL|" + site + deleted + "|" + site
+        self._cache[j] = s
+        return s
+
+
+_FILTER_TAGS = ((F_LM, "LM;"), (F_LSM, "LSM;"))
+_FILTER_TAGS2 = ((F_DP, "DP;"), (F_SB, "SB;"), (F_LOWQ, "LowQ;"), (F_R1CP, "R1CP;"), (F_R2CP, "R2CP;"), (F_PRIMERCP, "PrimerCP;"))
+
+
+def _filter_string(bits, chrom, pos, hpLen, ref, alt, refs):
+    """FILTER accumulator of filterVariants() (';' = nothing fired), tags in the reference's order."""
+    if not (bits & F_EVALUATED):
+        return ";"
+    f = ";"
+    for b, t in _FILTER_TAGS:
+        if bits & b:
+            f += t
+    hp, lc = is_hp_or_low_comp(chrom, pos, hpLen, ref, alt, refs)              # smCounter.py:195-203
+    if hp and (bits & F_HPGATE):
+        f += "HP;"
+    if lc and (bits & F_HPGATE):
+        f += "LowC;"
+    for b, t in _FILTER_TAGS2:
+        if bits & b:
+            f += t
+    return f
+
+
+def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None):
+    """The 45-field rows of vc() (smCounter.py:575-600) for ``locus_order`` (indices into loci; default all, in order).
+
+    Raises RuntimeError for loci the device flagged as needing a down-sampling mask or as unsupported.
+    """
+    namer = AlleleNamer(res, reads, loci, chroms, refs)
+    n = loci.n
+    order = range(n) if locus_order is None else locus_order
+    loc, cnt, pi = res.loc, res.cnt, res.pi
+    rows = []
+    for i in order:
+        i = int(i)
+        chrom = chroms[int(loci.ref_id[i])]
+        pos = str(int(loci.pos0[i]) + 1)
+        origRef = chr(int(loci.ref_base[i]))
+        status = int(loc[L_STATUS, i])
+        if status & (ST_NEED_DOWNSAMPLE | ST_UMI_OVERFLOW | ST_BAD_MASK):
+            raise RuntimeError("Exception thrown in vc() at location: %s (device status 0x%x)" % ((chrom, pos), status))
+        if status & ST_ZERO_COVERAGE:                                           # smCounter.py:492-494
+            rows.append("\t".join([chrom, pos, origRef] + [""] * 41 + ["Zero_Coverage"]))
+            continue
+        d0 = int(res.dyn_first[i])
+
+        def C_(a, c):          # counter c of allele reference a
+            return int(cnt[a, c, i]) if a < SMC_NFIXED else int(res.dyn_cnt[a - SMC_NFIXED, c])
+
+        def PI_(a):
+            return float(pi[a, i]) if a < SMC_NFIXED else float(res.dyn_pi[a - SMC_NFIXED])
+
+        cvg, usedMT = int(loc[L_CVG, i]), int(loc[L_USEDMT, i])
+        a1 = int(res.alt_allele[i])
+        origAlt = namer.name(a1)
+        ref, alt, vtype = convert_to_vcf(origRef, origAlt)
+        fltr = _filter_string(int(res.fl1[i]), chrom, pos, hpLen, ref, alt, refs)
+        alt_ref = a1
+        if res.biallelic[i]:                                                    # smCounter.py:555-573
+            a2 = int(res.second_allele[i])
+            origAlt2 = namer.name(a2)
+            ref2, alt2, vtype2 = convert_to_vcf(origRef, origAlt2)
+            fltr2 = _filter_string(int(res.fl2[i]), chrom, pos, hpLen, ref2, alt2, refs)
+            if fltr == ";" and fltr2 == ";":
+                alt = alt + "," + alt2
+                vtype = vtype.lower() + "," + vtype2.lower()
+            elif fltr != ";" and fltr2 == ";":
+                alt = alt2
+                fltr = fltr2
+                alt_ref = a2
+        acnt = [int(cnt[a, C_ALLELE, i]) for a in (A_A, A_T, A_G, A_C)]
+        mt = [int(cnt[a, C_MT, i]) for a in (A_A, A_T, A_G, A_C)]
+        sm = [int(cnt[a, C_STRONG, i]) for a in (A_A, A_T, A_G, A_C)]
+        outvec = [chrom, pos, ref, alt, vtype, cvg, int(loc[L_ALLFRAG, i]), int(loc[L_ALLMT, i]), int(loc[L_USEDFRAG, i]), usedMT,
+                  py2round(PI_(alt_ref), 2), C_(alt_ref, C_ALLELE), py2round(1.0 * C_(alt_ref, C_ALLELE) / cvg, 4),
+                  C_(alt_ref, C_MT), py2round(1.0 * C_(alt_ref, C_MT) / usedMT, 4), C_(alt_ref, C_STRONG)]
+        outvec.extend(acnt)
+        outvec.extend(py2round(1.0 * c / cvg, 4) for c in acnt)
+        outvec.extend(int(loc[k, i]) for k in (L_MT3, L_MT5, L_MT7, L_MT10))
+        outvec.extend(mt)
+        outvec.extend(py2round(1.0 * m / usedMT, 4) for m in mt)
+        outvec.extend(sm)
+        outvec.extend(py2round(float(pi[a, i]), 2) for a in (A_A, A_T, A_G, A_C))
+        outvec.append(fltr)
+        rows.append("\t".join(py2str(x) for x in outvec))
+        del d0
+    return rows

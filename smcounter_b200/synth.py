@@ -62,7 +62,7 @@ def _ref_windows(intervals, chroms, lengths, rng, margin):
     return ref
 
 
-def make_panel(intervals, spec: SynthSpec | None = None, seed: int = 1, chroms=None, lengths=None):
+def make_panel(intervals, spec: SynthSpec | None = None, seed: int = 1, chroms=None, lengths=None, umi_base: int = 0):
     """Generate reads for target ``intervals`` = [(chrom, start, end), ...] (0-based half-open, BED style).
 
     Returns (ReadsSoA in coordinate order, SparseRef, truth dict).
@@ -87,10 +87,21 @@ def make_panel(intervals, spec: SynthSpec | None = None, seed: int = 1, chroms=N
     cov_factor = 1.0 + 0.5 * spec.frag_extra / spec.spacing          # barcodes seen per locus / per amplicon
     U_mean = spec.umis_per_locus / cov_factor
 
+    # quality model as lookup tables: a uint8 draw -> quality class, class -> phred / error threshold (of 65536)
+    q_lut = np.zeros(256, dtype=np.uint8)
+    edges = np.round(np.cumsum(spec.q_probs) * 256).astype(int)
+    lo_ = 0
+    for qi, hi_ in enumerate(edges):
+        q_lut[lo_:hi_] = qi
+        lo_ = hi_
+    q_lut[lo_:] = len(spec.q_values) - 1
+    q_vals8 = np.asarray(spec.q_values, dtype=np.uint8)
+    err_thr = np.round(np.power(10.0, -np.asarray(spec.q_values, dtype=np.float64) / 10.0) * 65536).astype(np.uint16)
+
     cols = {k: [] for k in ("ref_id", "pos", "flag", "mapq", "nm", "umi", "frag", "kind", "k", "ilen")}
     seq_rows, qual_rows = [], []
     truth = {"snv": [], "ins": [], "del": []}
-    umi_counter = 0
+    umi_counter = int(umi_base)
     frag_counter = 0
 
     for (c, s, e) in intervals:
@@ -100,6 +111,8 @@ def make_panel(intervals, spec: SynthSpec | None = None, seed: int = 1, chroms=N
         w1 = min(lengths[c], e + margin)
         refarr = ref.fetch_array(c, w0, w1)
         refcode = np.searchsorted(_ACGT, refarr).astype(np.int64) % 4          # A0 C1 G2 T3 (N -> 0)
+        refcode8 = refcode.astype(np.uint8)
+        swv = np.lib.stride_tricks.sliding_window_view(refcode8, rl)
         # variant sites of this interval (absolute 0-based positions)
         snv_sites = np.array([p for p in range(s, e) if spec.snv_every and p % spec.snv_every == 17 % spec.snv_every],
                              dtype=np.int64)
@@ -149,6 +162,7 @@ def make_panel(intervals, spec: SynthSpec | None = None, seed: int = 1, chroms=N
             pcr_pos = fs[f_umi] + rng.integers(0, rl, size=F)
             pcr_base = rng.integers(0, 4, size=F)
             # two reads per fragment: R2 at the primer end, R1 at the barcode end
+            ia = np.array(all_indels, dtype=np.int64).reshape(-1, 2)
             for which in ("R2", "R1"):
                 at_start = (which == "R2") == fwd_primer                # read anchored at fragment start?
                 reverse = not at_start
@@ -158,8 +172,7 @@ def make_panel(intervals, spec: SynthSpec | None = None, seed: int = 1, chroms=N
                 kind = np.zeros(F, dtype=np.int8)                       # 0 plain, 1 ins, 2 del
                 ilen = np.zeros(F, dtype=np.int64)
                 vpos = np.zeros(F, dtype=np.int64)
-                if all_indels:
-                    ia = np.array(all_indels, dtype=np.int64)
+                if len(ia):
                     has = ind >= 0
                     vpos[has] = ia[ind[has], 0]
                     ilen[has] = np.abs(ia[ind[has], 1])
@@ -178,38 +191,63 @@ def make_panel(intervals, spec: SynthSpec | None = None, seed: int = 1, chroms=N
                 if neg.any():                                           # cannot happen for sane BEDs; keep plain
                     start = np.where(neg, 0, start)
                     kind = np.where(neg, 0, kind).astype(np.int8)
-                # query index j -> reference index
-                j = np.arange(rl, dtype=np.int64)[None, :]
-                k_ = kk[:, None]
-                il = ilen[:, None]
-                kd = kind[:, None]
-                refidx = start[:, None] + j
-                refidx = np.where((kd == 2) & (j >= k_), refidx + il, refidx)
-                refidx = np.where((kd == 1) & (j >= k_ + il), refidx - il, refidx)
-                inserted = (kd == 1) & (j >= k_) & (j < k_ + il)
-                loc = np.clip(refidx - w0, 0, len(refcode) - 1)
-                base = refcode[loc]
+                    ilen = np.where(neg, 0, ilen)
+                    kk = np.where(neg, 0, kk)
+
+                def col_of(p):
+                    """query column of reference position p (array per read) or -1"""
+                    d = p - start
+                    c = np.where(kind == 2, np.where(d < kk, d, np.where(d >= kk + ilen, d - ilen, -1)),
+                                 np.where(kind == 1, np.where(d < kk, d, d + ilen), d))
+                    return np.where((d >= 0) & (c >= 0) & (c < rl), c, -1)
+
+                # dense: reference bases as if every read were plain, then fix the rows with an indel
+                base = swv[np.clip(start - w0, 0, len(refcode8) - rl)].copy()          # (F, rl) uint8 codes 0..3
+                rows_i = np.flatnonzero(kind > 0)
+                inserted_cells = None
+                if len(rows_i):
+                    j = np.arange(rl, dtype=np.int64)[None, :]
+                    k_ = kk[rows_i, None]
+                    il = ilen[rows_i, None]
+                    kd = kind[rows_i, None]
+                    refidx = start[rows_i, None] + j
+                    refidx = np.where((kd == 2) & (j >= k_), refidx + il, refidx)
+                    refidx = np.where((kd == 1) & (j >= k_ + il), refidx - il, refidx)
+                    ins_m = (kd == 1) & (j >= k_) & (j < k_ + il)
+                    sub = refcode8[np.clip(refidx - w0, 0, len(refcode8) - 1)]
+                    sub = np.where(ins_m, ((vpos[rows_i, None] + (j - k_)) % 4).astype(np.uint8), sub)
+                    base[rows_i] = sub
+                    inserted_cells = (rows_i, ins_m)
                 truebase = base.copy()
-                # molecule SNVs
+                if inserted_cells is not None:                                  # inserted bases never count as mismatches
+                    pass
+                # molecule SNVs (sparse edits)
                 for si, p in enumerate(snv_sites):
-                    carr = mol_snv[f_umi, si][:, None] & (refidx == p) & ~inserted
-                    base = np.where(carr, (refcode[p - w0] + 1) % 4, base)
-                # inserted bases: deterministic function of the site so that all carriers agree
-                if inserted.any():
-                    ins_b = (vpos[:, None] + (j - k_)) % 4
-                    base = np.where(inserted, ins_b, base)
+                    carr = np.flatnonzero(mol_snv[f_umi, si])
+                    if len(carr):
+                        cc = col_of(np.full(F, p, dtype=np.int64))[carr]
+                        m = cc >= 0
+                        base[carr[m], cc[m]] = (refcode8[p - w0] + 1) % 4
                 # PCR error shared by both reads of the fragment
-                pe = pcr_has[:, None] & (refidx == pcr_pos[:, None]) & ~inserted
-                base = np.where(pe, pcr_base[:, None], base)
-                # qualities and sequencing errors
-                qsel = rng.choice(len(spec.q_values), size=(F, rl), p=spec.q_probs)
-                qual = np.asarray(spec.q_values, dtype=np.uint8)[qsel]
-                perr = np.power(10.0, -qual.astype(np.float64) / 10.0)
-                err = rng.random((F, rl)) < perr
-                base = np.where(err, (base + rng.integers(1, 4, size=(F, rl))) % 4, base)
-                isN = rng.random((F, rl)) < spec.n_frac
-                qual = np.where(isN, 2, qual).astype(np.uint8)
-                nib = np.where(isN, 15, _NIB[base]).astype(np.uint8)
+                rows_p = np.flatnonzero(pcr_has)
+                if len(rows_p):
+                    cc = col_of(pcr_pos)[rows_p]
+                    m = cc >= 0
+                    base[rows_p[m], cc[m]] = pcr_base[rows_p[m]].astype(np.uint8)
+                # qualities and sequencing errors (dense uint8 / uint16 passes)
+                qsel = q_lut[rng.integers(0, 256, size=(F, rl), dtype=np.uint8)]
+                qual = q_vals8[qsel]
+                err = rng.integers(0, 65536, size=(F, rl), dtype=np.uint16) < err_thr[qsel]
+                er, ec = np.nonzero(err)
+                if len(er):
+                    base[er, ec] = (base[er, ec] + rng.integers(1, 4, size=len(er), dtype=np.uint8)) % 4
+                nib = _NIB[base]
+                nN = rng.binomial(F * rl, spec.n_frac) if spec.n_frac > 0 else 0
+                if nN:
+                    nr = rng.integers(0, F, size=nN)
+                    nc = rng.integers(0, rl, size=nN)
+                    nib[nr, nc] = 15
+                    qual[nr, nc] = 2
                 # soft clips on plain reads only
                 sc = (kind == 0) & (rng.random(F) < spec.softclip_frac)
                 sclen = np.where(sc, rng.integers(1, 9, size=F), 0)
@@ -217,12 +255,23 @@ def make_panel(intervals, spec: SynthSpec | None = None, seed: int = 1, chroms=N
                 sc_right = sc & ~sc_left
                 lclip = np.where(sc_left, sclen, 0)
                 rclip = np.where(sc_right, sclen, 0)
-                clipped = (j < lclip[:, None]) | (j >= rl - rclip[:, None])
-                if clipped.any():
-                    nib = np.where(clipped, _NIB[rng.integers(0, 4, size=(F, rl))], nib).astype(np.uint8)
+                mismatch_cells = nib != _NIB[truebase]
+                if inserted_cells is not None:
+                    sub = mismatch_cells[inserted_cells[0]]
+                    sub[inserted_cells[1]] = False
+                    mismatch_cells[inserted_cells[0]] = sub
+                rows_c = np.flatnonzero(sc)
+                if len(rows_c):
+                    j = np.arange(rl, dtype=np.int64)[None, :]
+                    clipped = (j < lclip[rows_c, None]) | (j >= rl - rclip[rows_c, None])
+                    sub = nib[rows_c]
+                    sub[clipped] = _NIB[rng.integers(0, 4, size=int(clipped.sum()))]
+                    nib[rows_c] = sub
+                    subm = mismatch_cells[rows_c]
+                    subm[clipped] = False
+                    mismatch_cells[rows_c] = subm
                 # NM = mismatches of aligned, non-inserted bases vs the reference + indel length
-                mism = (~clipped) & (~inserted) & ((nib != _NIB[truebase]))
-                nm = mism.sum(axis=1) + ilen
+                nm = mismatch_cells.sum(axis=1) + ilen
                 pos = start + lclip
                 flag = np.full(F, 0x1 | 0x2, dtype=np.uint16)
                 flag |= np.uint16(0x40 if which == "R1" else 0x80)
@@ -253,11 +302,7 @@ def make_panel(intervals, spec: SynthSpec | None = None, seed: int = 1, chroms=N
         cat[k] = cat[k][order]
     nibs = nibs[order]
     quals = quals[order]
-    # frag ids in order of first appearance (the canonical fragment order of the C-ABI)
-    _, first = np.unique(cat["frag"], return_index=True)
-    rank_of_first = np.argsort(np.argsort(first))
-    uniq_sorted = np.sort(np.unique(cat["frag"]))
-    frag_id = rank_of_first[np.searchsorted(uniq_sorted, cat["frag"])].astype(np.uint32)
+    frag_id = relabel_frag_ids(cat["frag"])
     # cigars
     kc, kk, il = cat["kind"], cat["k"], cat["ilen"]
     n_cigar = np.where(kc == 0, 1, np.where(kc >= 3, 2, 3)).astype(np.uint16)
@@ -287,6 +332,74 @@ def make_panel(intervals, spec: SynthSpec | None = None, seed: int = 1, chroms=N
         cigar_off=cigar_off.astype(np.int64), n_cigar=n_cigar, umi=cat["umi"].astype(np.uint64), frag_id=frag_id,
         seq=np.ascontiguousarray(packed).reshape(-1), qual=np.ascontiguousarray(quals).reshape(-1), cigar=cigar,
         chroms=list(chroms))
+    return soa, ref, truth
+
+
+def relabel_frag_ids(frag: np.ndarray) -> np.ndarray:
+    """Dense fragment ids in order of first appearance (the canonical fragment order of the C-ABI)."""
+    uniq, first, inv = np.unique(frag, return_index=True, return_inverse=True)
+    rank = np.empty(len(uniq), dtype=np.int64)
+    rank[np.argsort(first, kind="stable")] = np.arange(len(uniq))
+    return rank[inv].astype(np.uint32)
+
+
+def merge_soas(parts, chroms):
+    """Concatenate ReadsSoA batches generated for disjoint interval groups and restore coordinate order."""
+    parts = [p for p in parts if p.n]
+    if not parts:
+        raise ValueError("no reads")
+    cat = lambda name: np.concatenate([getattr(p, name) for p in parts])
+    frag_off = np.cumsum([0] + [int(p.frag_id.max()) + 1 for p in parts])[:-1]
+    frag = np.concatenate([p.frag_id.astype(np.int64) + o for p, o in zip(parts, frag_off)])
+    seq_off = np.concatenate([p.seq_off + o for p, o in zip(parts, np.cumsum([0] + [p.seq.nbytes for p in parts])[:-1])])
+    qual_off = np.concatenate([p.qual_off + o for p, o in zip(parts, np.cumsum([0] + [p.qual.nbytes for p in parts])[:-1])])
+    cig_off = np.concatenate([p.cigar_off + o for p, o in zip(parts, np.cumsum([0] + [len(p.cigar) for p in parts])[:-1])])
+    ref_id, pos = cat("ref_id"), cat("pos")
+    order = np.lexsort((np.arange(len(pos)), pos, ref_id))
+    return ReadsSoA(ref_id=ref_id[order], pos=pos[order], flag=cat("flag")[order], mapq=cat("mapq")[order], nm=cat("nm")[order],
+                    l_seq=cat("l_seq")[order], seq_off=seq_off[order], qual_off=qual_off[order], cigar_off=cig_off[order],
+                    n_cigar=cat("n_cigar")[order], umi=cat("umi")[order], frag_id=relabel_frag_ids(frag[order]),
+                    seq=cat("seq"), qual=cat("qual"), cigar=cat("cigar"), chroms=list(chroms))
+
+
+def _mp_job(args):
+    intervals, spec, seed, chroms, lengths, umi_base = args
+    return make_panel(intervals, spec, seed=seed, chroms=chroms, lengths=lengths, umi_base=umi_base)
+
+
+def make_panel_mp(intervals, spec: SynthSpec | None = None, seed: int = 1, workers: int | None = None):
+    """make_panel() over groups of intervals in worker processes (bench-scale inputs).  Deterministic for a given
+    (intervals, spec, seed, number of groups)."""
+    import multiprocessing as mp
+    import os
+
+    spec = spec or SynthSpec()
+    workers = workers or min(16, os.cpu_count() or 1)
+    chroms = []
+    for (c, _, _) in intervals:
+        if c not in chroms:
+            chroms.append(c)
+    margin = spec.read_len + spec.frag_extra + 64
+    lengths = {c: 0 for c in chroms}
+    for (c, s, e) in intervals:
+        lengths[c] = max(lengths[c], e + 2 * margin)
+    ngroups = max(1, min(len(intervals), workers * 4))
+    groups = [intervals[i::ngroups] for i in range(ngroups)]
+    jobs = [(g, spec, seed * 1000003 + i, chroms, lengths, i << 24) for i, g in enumerate(groups)]
+    if workers > 1 and ngroups > 1:
+        with mp.get_context("fork").Pool(workers) as pool:
+            outs = pool.map(_mp_job, jobs)
+    else:
+        outs = [_mp_job(j) for j in jobs]
+    soa = merge_soas([o[0] for o in outs], chroms)
+    ref = SparseRef(lengths)
+    truth = {"snv": [], "ins": [], "del": []}
+    for (_, r, t) in outs:
+        for c, ws in r.windows.items():
+            for (st, arr) in ws:
+                ref.add_window(c, st, arr)
+        for k in truth:
+            truth[k].extend(t[k])
     return soa, ref, truth
 
 
