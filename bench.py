@@ -155,9 +155,9 @@ def main():
         # rank 0 only, with all host cores.  Each step is a bounded sample of the same workload.
         if rank != 0:
             return 0
-        args.intervals = min(args.intervals, 4)      # the sample only needs the reads around its loci
+        args.intervals = min(args.intervals, 16)     # the sample only needs the reads around its loci
         mine, soa, refs, loci, bed_order = make_batch(args, 0, 1)
-        n_sample = args.cpu_loci or 2 * cores
+        n_sample = args.cpu_loci or 48 * cores
         jobs, nrec = cpu_sample_setup(soa, refs, loci, n_sample)
         for _ in range(min(args.warmup, 1)):
             cpu_run(jobs[:max(1, cores)], cores)
@@ -297,7 +297,7 @@ def main():
     caller.close()
 
     if rank == 0 and not args.no_cpu_baseline:
-        n_sample = args.cpu_loci or 2 * cores
+        n_sample = args.cpu_loci or 48 * cores
         jobs, nrec = cpu_sample_setup(soa, refs, loci, n_sample)
         v, dt, ev = cpu_run(jobs, cores)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -71,10 +71,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("SMC_B200_LIB", LIB_PATH)      # A/B builds of the same ABI (tuning only)
+    if not os.path.exists(path):
         raise ImportError("libsmc_b200.so is not built (%s); run `python -m smcounter_b200.build`. "
                           "smcounter_b200 has no CPU fallback." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     lib.smc_version.restype = C.c_int
     lib.smc_ctx_create.argtypes = [C.c_int, C.POINTER(smc_params), C.POINTER(_vp)]
     lib.smc_ctx_create.restype = C.c_int

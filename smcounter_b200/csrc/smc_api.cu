@@ -6,6 +6,7 @@
 //       -> K4 FP64 statistics: PI, ALT, filters, Fisher                                smc_stats.cuh
 //   -> D2H
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -70,7 +71,7 @@ struct smc_ctx {
     // barcode listing
     DevBuf d_list_idx, d_list_count, d_list_off, d_list_umi;
     smc_timings tm{};
-    uint32_t chunk = 8192;
+    uint32_t chunk = 2048;
     const uint32_t* ev_read_sorted = nullptr;   // tile-sorted event -> srank map (lives in d_ev0 or d_ev1)
     uint32_t n_tiles = 0; int64_t n_tile_events = 0;
 };
@@ -200,6 +201,7 @@ extern "C" int smc_ctx_create(int device, const smc_params* params, smc_ctx** ou
     smc_ctx* ctx = new (std::nothrow) smc_ctx();
     if (!ctx) { g_create_error = "smc_ctx_create: out of host memory"; return SMC_E_ARG; }
     ctx->device = device; ctx->prm = *params;
+    if (const char* ev = getenv("SMC_CHUNK")) { long v = atol(ev); if (v >= 64 && v <= 1000000) ctx->chunk = (uint32_t)v; }   // tuning knob
     auto fail = [&](const char* what, cudaError_t ce) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
         delete ctx; return SMC_E_CUDA;

@@ -100,21 +100,32 @@ k_expand(const ReadRec* __restrict__ recs, const uint32_t* __restrict__ ev_off, 
 // ------------------------------------------------------------------------------------------------------------
 // K3: tile pileup
 // ------------------------------------------------------------------------------------------------------------
+#ifndef K3_WARPS
 #define K3_WARPS 4
+#endif
+#ifndef K3_MINBLOCKS
+#define K3_MINBLOCKS 4
+#endif
 #define NF SMC_NFIXED
 #define NSLOT 7            // per-barcode allele slots: 5 fixed + 2 dynamic
-enum { KC_ALLELE = 0, KC_FWD, KC_LOWQ, KC_R1LE, KC_R1TOT, KC_R2LE, KC_R2TOT, KC_R2PLE, KC_CONCORD, KC_DISCORD, KC_MT,
-       KC_STRONG, K3_NC };
+// Per-lane shared-memory counters of the fixed alleles, two 16-bit counters per word (flushed to the global 32-bit
+// accumulators before any of them can reach 65536):
+enum { KW_ALLELE_FWD = 0,   // alleleCnt | forwardCnt << 16
+       KW_R1,               // len(r1BcEndPos) | #<=20 << 16
+       KW_R2,               // len(r2BcEndPos) | #<=20 << 16
+       KW_LOWQ_R2P,         // lowQReads | #r2PrimerEndPos<=primerDist << 16
+       KW_PAIR,             // concordPairCnt | discordPairCnt << 16
+       KW_MT,               // MTCnt | strongMTCnt << 16
+       K3_NW };
+#define K3_FLUSH_EVERY 49152u      // tile events between counter flushes (each event adds at most 1 to a field)
 #define K3_STAGE_WORDS 512
-#define K3_FC_WORDS    (NF * K3_NC * 32)
+#define K3_FC_WORDS    (NF * K3_NW * 32)
 #define K3_LIMB_WORDS  (NF * 3 * 64)
 #define K3_UCNT_WORDS  (NSLOT * 32)
 #define K3_UPROD_WORDS (NSLOT * 64)
-#define K3_WARP_WORDS  (K3_STAGE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS + K3_UCNT_WORDS + K3_UPROD_WORDS)
+#define K3_UT_WORDS    (NSLOT * 64)
+#define K3_WARP_WORDS  (K3_STAGE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS + K3_UCNT_WORDS + K3_UPROD_WORDS + K3_UT_WORDS)
 #define K3_SMEM_BYTES  (K3_WARPS * K3_WARP_WORDS * 4)
-
-__constant__ int c_kc2out[K3_NC] = {SMC_C_ALLELE, SMC_C_FWD, SMC_C_LOWQ, SMC_C_R1LE, SMC_C_R1TOT, SMC_C_R2LE, SMC_C_R2TOT,
-                                    SMC_C_R2PLE, SMC_C_CONCORD, SMC_C_DISCORD, SMC_C_MT, SMC_C_STRONG};
 
 struct K3Args {
     const ReadRec* recs; const uint32_t* ev_read; const uint32_t* tile_off; const uint32_t* unit_off;
@@ -133,28 +144,34 @@ struct K3Args {
     const int32_t* list_idx; uint32_t* list_count; const int64_t* list_off; uint64_t* list_umi; int64_t list_cap;
 };
 
-__device__ __forceinline__ int nib_to_fixed(uint32_t nib) {     // A C G T nibbles -> fixed slot, else -1
-    return nib == 1 ? SMC_A_A : nib == 2 ? SMC_A_C : nib == 4 ? SMC_A_G : nib == 8 ? SMC_A_T : -1;
+// BAM nibble of A, C, G, T -> fixed slot (A0 C1 T3 G4), anything else -> -1
+__device__ __forceinline__ int nib_to_fixed(uint32_t nib) {
+    // nib 1,2,4,8 -> ffs 1,2,3,4 -> slots 0,1,4,3
+    return (__popc(nib) == 1) ? (int)((0x3410u >> (4 * (__ffs(nib) - 1))) & 15u) : -1;
 }
 
-__device__ __noinline__ uint32_t dyn_lookup(const K3Args& A, unsigned long long key, uint32_t rep_read, int rep_qpos, int len) {
-    uint32_t h = hash64to32(key) & A.dmask;
-    for (uint32_t probe = 0; probe <= A.dmask; ++probe) {
-        unsigned long long cur = __ldcg(&A.dkey[h]);
+// open-addressing table of the non-ACGT/DEL alleles; arguments by value so that the kernel parameter block never has
+// to be spilled to local memory for this (rare) call
+__device__ __noinline__ uint32_t dyn_lookup(unsigned long long* dkey, uint32_t dmask, uint32_t* drep_read, int32_t* drep_qpos,
+                                            int32_t* dlen, uint32_t* dcount, uint32_t* gflags, unsigned long long key,
+                                            uint32_t rep_read, int rep_qpos, int len) {
+    uint32_t h = hash64to32(key) & dmask;
+    for (uint32_t probe = 0; probe <= dmask; ++probe) {
+        unsigned long long cur = __ldcg(&dkey[h]);
         if (cur == key) return h;
         if (cur == DYN_EMPTY) {
-            unsigned long long prev = atomicCAS(&A.dkey[h], DYN_EMPTY, key);
+            unsigned long long prev = atomicCAS(&dkey[h], DYN_EMPTY, key);
             if (prev == DYN_EMPTY) {
-                A.drep_read[h] = rep_read; A.drep_qpos[h] = rep_qpos; A.dlen[h] = len;
-                uint32_t c = atomicAdd(A.dcount, 1u);
-                if (2ull * (c + 1ull) > (unsigned long long)A.dmask + 1ull) atomicOr(A.gflags, GF_DYN_FULL);
+                drep_read[h] = rep_read; drep_qpos[h] = rep_qpos; dlen[h] = len;
+                uint32_t c = atomicAdd(dcount, 1u);
+                if (2ull * (c + 1ull) > (unsigned long long)dmask + 1ull) atomicOr(gflags, GF_DYN_FULL);
                 return h;
             }
             if (prev == key) return h;
         }
-        h = (h + 1) & A.dmask;
+        h = (h + 1) & dmask;
     }
-    atomicOr(A.gflags, GF_DYN_FULL);
+    atomicOr(gflags, GF_DYN_FULL);
     return 0;
 }
 
@@ -186,14 +203,21 @@ struct LaneState {
     bool frag_seen, f_exists, f_paired; uint32_t f_aid; int f_bq;
 };
 
-#define FC(c, a)    fc[((a) * K3_NC + (c)) * 32 + lane]
+#define FCW(w, a)   fc[((a) * K3_NW + (w)) * 32 + lane]
 #define LIMB(a, j)  limb[((a) * 3 + (j)) * 32 + lane]
 #define UCNT(s)     ucnt[(s) * 32 + lane]
 #define UPROD(s)    uprod[(s) * 32 + lane]
+#define UT(s)       ut[(s) * 32 + lane]
 
-__device__ __forceinline__ void inc_allele_counter(const K3Args& A, int* fc, int lane, uint32_t aid, int kc) {
-    if (aid < NF) FC(kc, aid) += 1;
-    else atomicAdd(&A.dcnt[(size_t)(aid - NF) * SMC_NCNT + c_kc2out[kc]], 1);
+// counter update for an allele that may be dynamic: `word`/`add` address the packed shared-memory counter of a fixed
+// allele, c_lo / c_hi are the smc_out counter indices the low / high half stand for.
+__device__ __forceinline__ void bump(const K3Args& A, int* fc, int lane, uint32_t aid, int word, uint32_t add, int c_lo, int c_hi) {
+    if (aid < NF) FCW(word, aid) += (int)add;
+    else {
+        int32_t* row = A.dcnt + (size_t)(aid - NF) * SMC_NCNT;
+        if (add & 0xffffu) atomicAdd(&row[c_lo], 1);
+        if (add >> 16) atomicAdd(&row[c_hi], 1);
+    }
 }
 
 __device__ __forceinline__ void fragment_finalize(const K3Args& A, int lane, int* ucnt, double* uprod, LaneState& S) {
@@ -225,18 +249,8 @@ __device__ __forceinline__ void fragment_finalize(const K3Args& A, int lane, int
     S.last_aid = S.f_aid;
 }
 
-__device__ __forceinline__ double pcr_value(const K3Args& A, int k, int n, int cnt) {
-    if (k <= 6 && n <= A.pcr_nmax) {
-        size_t per = (size_t)(A.pcr_nmax + 1) * (A.pcr_nmax + 2) / 2;
-        return __ldg(&A.pcrtab[(size_t)(k - 4) * per + (size_t)n * (n + 1) / 2 + cnt]);
-    }
-    double ratio = ((double)cnt + 0.5) / ((double)n + 0.5 * (double)k);
-    return pow(10.0, -6.0 * ratio);
-}
-
-__device__ __forceinline__ void pi_add(const K3Args& A, int lane, unsigned long long* limb, LaneState& S, int slot, double l) {
-    unsigned long long a0, a1, a2;
-    pi_limbs(l, a0, a1, a2);
+__device__ __forceinline__ void pi_add_limbs(const K3Args& A, int lane, unsigned long long* limb, LaneState& S, int slot,
+                                             unsigned long long a0, unsigned long long a1, unsigned long long a2) {
     if (slot < NF) {
         LIMB(slot, 0) += a0; LIMB(slot, 1) += a1; LIMB(slot, 2) += a2;
         S.keymask |= 1u << slot;
@@ -249,9 +263,21 @@ __device__ __forceinline__ void pi_add(const K3Args& A, int lane, unsigned long 
     }
 }
 
+// PCR prior outside the host-built table (barcodes with > pcr_nmax fragments or > 6 distinct alleles): device pow()
+__device__ __noinline__ double pcr_slow(int cnt, double denom) {
+    return pow(10.0, -6.0 * (((double)cnt + 0.5) / denom));
+}
+
+__device__ __forceinline__ uint32_t slot_to_aid(const LaneState& S, int slot) {
+    return slot < NF ? (uint32_t)slot : NF + (slot == 5 ? S.udyn0 : S.udyn1);
+}
+
 // calProb + the per-barcode part of vc() (smCounter.py:26-98, 506-532) for the lane's locus.
+// The heavy FP64 work (PCR prior lookup, division, log10) runs over the COMPACTED list of alleles present in the
+// barcode, so lanes whose loci have different reference bases still execute the same instructions; only the cheap,
+// order-sensitive sums walk the slots in canonical order.
 __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int64_t L, uint32_t urank, int* fc, unsigned long long* limb,
-                                          int* ucnt, double* uprod, LaneState& S) {
+                                             int* ucnt, double* uprod, double* ut, LaneState& S) {
     if (S.umi_seen) S.allMT++;
     bool used = S.umi_bc;
     if (used) {
@@ -275,13 +301,10 @@ __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int64_t 
     if (used) {
         const int n = S.n;
         S.usedMT++; S.usedFrag += n;
-        if (n >= 3) S.mt3++;
-        if (n >= 5) S.mt5++;
-        if (n >= 7) S.mt7++;
-        if (n >= 10) S.mt10++;
+        S.mt3 += n >= 3; S.mt5 += n >= 5; S.mt7 += n >= 7; S.mt10 += n >= 10;
         if (n <= A.mtDrop) {                              // :28-32 -> four zeros, a 4-way tie (:514-523)
             S.keymask |= (1u << SMC_A_A) | (1u << SMC_A_T) | (1u << SMC_A_G) | (1u << SMC_A_C);
-            if (n == 1) inc_allele_counter(A, fc, lane, S.last_aid, KC_MT);
+            if (n == 1) bump(A, fc, lane, S.last_aid, KW_MT, 1u, SMC_C_MT, SMC_C_STRONG);
         } else {
             // canonical order of the dynamic slots = ascending allele key
             if (S.ndyn == 2 && __ldcg(&A.dkey[S.udyn0]) > __ldcg(&A.dkey[S.udyn1])) {
@@ -290,7 +313,6 @@ __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int64_t 
                 uint32_t b5 = (S.exist >> 5) & 1u, b6 = (S.exist >> 6) & 1u;
                 UCNT(5) = c6; UCNT(6) = c5; UPROD(5) = p6; UPROD(6) = p5;
                 S.exist = (S.exist & 0x1fu) | (b6 << 5) | (b5 << 6);
-                if (S.last_aid >= NF) { /* aid32 refers to the table entry, unaffected by the slot swap */ }
             }
             const uint32_t exist = S.exist;
             int k = __popc(exist);
@@ -301,55 +323,60 @@ __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int64_t 
             if (k < 4 && !((exist >> SMC_A_C) & 1u)) { pad |= 1u << SMC_A_C; ++k; }
             const uint32_t uniq = exist | pad;
             const double rightP = S.rightP;
-            const double pcr_pad = pcr_value(A, k, n, 0);
-            double pcr[NSLOT], tt[NSLOT];
-            double tpad = rightP;                         // :88-91
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s) {
-                pcr[s] = pcr_pad;
-                if ((exist >> s) & 1u) { pcr[s] = pcr_value(A, k, n, UCNT(s)); tpad = __dmul_rn(tpad, pcr[s]); }
+            const double INF = __longlong_as_double(0x7ff0000000000000ll);
+            // ---- PCR prior of every allele of the barcode (:79-81): table lookups (host glibc pow) or pow()
+            const bool tab = (k <= 6 && n <= A.pcr_nmax);
+            const double* trow = A.pcrtab + ((size_t)(k - 4) * ((size_t)(A.pcr_nmax + 1) * (A.pcr_nmax + 2) / 2) + (size_t)n * (n + 1) / 2);
+            const double denom = (double)n + 0.5 * (double)k;
+            const double pcr_pad = tab ? __ldg(trow) : pcr_slow(0, denom);
+            double m1 = pad ? pcr_pad : INF, m2 = INF; int arg1 = -1;      // smallest / second smallest prior and its slot
+            double tpad = rightP;                                         // :88-91
+            for (uint32_t m = exist; m; m &= m - 1) {
+                const int s = __ffs(m) - 1;
+                const int c = UCNT(s);
+                const double v = tab ? __ldg(trow + c) : pcr_slow(c, denom);
+                UT(s) = v;
+                tpad = __dmul_rn(tpad, v);
+                if (v < m1) { m2 = m1; m1 = v; arg1 = s; } else if (v < m2) m2 = v;
             }
-            const double PCR_NO_ERROR = 1.0 - 3e-5;       // smCounter.py:20
-            double sumP = 0.0;
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s) {
-                tt[s] = 0.0;
-                if ((uniq >> s) & 1u) {
-                    if ((exist >> s) & 1u) {              // :86
-                        double minp = __longlong_as_double(0x7ff0000000000000ll);
-#pragma unroll
-                        for (int c = 0; c < NSLOT; ++c)
-                            if (c != s && ((uniq >> c) & 1u)) minp = fmin(minp, pcr[c]);
-                        tt[s] = __dadd_rn(__dmul_rn(PCR_NO_ERROR, UPROD(s)), __dmul_rn(rightP, minp));
-                    } else tt[s] = tpad;
-                    sumP = __dadd_rn(sumP, tt[s]);        // :93
-                }
+            // ---- likelihood of each present allele (:86); pads all share tpad
+            const double PCR_NO_ERROR = 1.0 - 3e-5;                       // smCounter.py:20
+            for (uint32_t m = exist; m; m &= m - 1) {
+                const int s = __ffs(m) - 1;
+                const double minp = (s == arg1) ? m2 : m1;                // min over the OTHER members of uniq
+                UT(s) = __dadd_rn(__dmul_rn(PCR_NO_ERROR, UPROD(s)), __dmul_rn(rightP, minp));
             }
+            double sumP = 0.0;                                            // :93, in canonical slot order
+            for (uint32_t m = uniq; m; m &= m - 1) {
+                const int s = __ffs(m) - 1;
+                sumP = __dadd_rn(sumP, ((exist >> s) & 1u) ? UT(s) : tpad);
+            }
+            // ---- posterior -> -log10(1-p) (:96, :509-510), PI accumulation (:512), consensus (:514-523)
             double best = -1.0; int nbest = 0, cons = -1;
-            double lpad = 0.0; bool have_pad = false;
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s) {
-                if ((uniq >> s) & 1u) {
-                    double l;
-                    bool is_pad = !((exist >> s) & 1u);
-                    if (is_pad && have_pad) l = lpad;
-                    else {
-                        double p = sumP <= 0.0 ? 0.0 : tt[s] / sumP;          // :96
-                        double x = 1.0 - p;                                   // :509-510
-                        l = x > 0.0 ? -log10(x) : 16.0;
-                        if (is_pad) { lpad = l; have_pad = true; }
-                    }
-                    pi_add(A, lane, limb, S, s, l);                           // :512
-                    if (l > best) { best = l; nbest = 1; cons = s; }
-                    else if (l == best) nbest++;
-                }
+            if (pad) {
+                const double p = sumP <= 0.0 ? 0.0 : tpad / sumP;
+                const double x = 1.0 - p;
+                const double l = x > 0.0 ? -log10(x) : 16.0;
+                unsigned long long a0, a1, a2;
+                pi_limbs(l, a0, a1, a2);
+                for (uint32_t m = pad; m; m &= m - 1) pi_add_limbs(A, lane, limb, S, __ffs(m) - 1, a0, a1, a2);
+                best = l; nbest = __popc(pad); cons = __ffs(pad) - 1;
             }
-            if (nbest == 1) {                                                 // :515-519
-                uint32_t aid = cons < NF ? (uint32_t)cons : NF + (cons == 5 ? S.udyn0 : S.udyn1);
-                inc_allele_counter(A, fc, lane, aid, KC_MT);
-                if (best > A.smt) inc_allele_counter(A, fc, lane, aid, KC_STRONG);
-            } else if (n == 1) {                                              // :521-523
-                inc_allele_counter(A, fc, lane, S.last_aid, KC_MT);
+            for (uint32_t m = exist; m; m &= m - 1) {
+                const int s = __ffs(m) - 1;
+                const double p = sumP <= 0.0 ? 0.0 : UT(s) / sumP;
+                const double x = 1.0 - p;
+                const double l = x > 0.0 ? -log10(x) : 16.0;
+                unsigned long long a0, a1, a2;
+                pi_limbs(l, a0, a1, a2);
+                pi_add_limbs(A, lane, limb, S, s, a0, a1, a2);
+                if (l > best) { best = l; nbest = 1; cons = s; }
+                else if (l == best) nbest++;
+            }
+            if (nbest == 1) {                                             // :515-519
+                bump(A, fc, lane, slot_to_aid(S, cons), KW_MT, best > A.smt ? 0x10001u : 1u, SMC_C_MT, SMC_C_STRONG);
+            } else if (n == 1) {                                          // :521-523
+                bump(A, fc, lane, S.last_aid, KW_MT, 1u, SMC_C_MT, SMC_C_STRONG);
             }
         }
     }
@@ -369,7 +396,29 @@ __device__ __forceinline__ uint32_t chunk_boundary(const K3Args& A, uint32_t x, 
     return te;
 }
 
-__global__ void __launch_bounds__(K3_WARPS * 32) k_pileup(const K3Args A) {
+// add the lane's packed shared-memory counters to the global 32-bit accumulators and clear them
+__device__ __forceinline__ void flush_counters(const K3Args& A, int* fc, int lane, int64_t L, bool lane_valid) {
+    if (!lane_valid) return;
+    const size_t nl = (size_t)A.n_loci;
+    const int lo_idx[K3_NW] = {SMC_C_ALLELE, SMC_C_R1TOT, SMC_C_R2TOT, SMC_C_LOWQ, SMC_C_CONCORD, SMC_C_MT};
+    const int hi_idx[K3_NW] = {SMC_C_FWD, SMC_C_R1LE, SMC_C_R2LE, SMC_C_R2PLE, SMC_C_DISCORD, SMC_C_STRONG};
+#pragma unroll
+    for (int a = 0; a < NF; ++a) {
+#pragma unroll
+        for (int w = 0; w < K3_NW; ++w) {
+            const uint32_t v = (uint32_t)FCW(w, a);
+            if (v) {
+                FCW(w, a) = 0;
+                const int lo = (int)(v & 0xffffu), hi = (int)(v >> 16);
+                if (lo) atomicAdd(&A.cnt[((size_t)a * SMC_NCNT + lo_idx[w]) * nl + L], lo);
+                if (hi) atomicAdd(&A.cnt[((size_t)a * SMC_NCNT + hi_idx[w]) * nl + L], hi);
+                if (w == KW_ALLELE_FWD && a != SMC_A_DEL && lo - hi) atomicAdd(&A.cnt[((size_t)a * SMC_NCNT + SMC_C_REV) * nl + L], lo - hi);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup(const K3Args A) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* ws = smem + (size_t)w * K3_WARP_WORDS;
@@ -377,6 +426,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_pileup(const K3Args A) {
     unsigned long long* limb = (unsigned long long*)(ws + K3_STAGE_WORDS + K3_FC_WORDS);
     int* ucnt = (int*)(ws + K3_STAGE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS);
     double* uprod = (double*)(ws + K3_STAGE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS + K3_UCNT_WORDS);
+    double* ut = (double*)(ws + K3_STAGE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS + K3_UCNT_WORDS + K3_UPROD_WORDS);
 
     const uint32_t unit = blockIdx.x * K3_WARPS + w;
     if (unit >= A.unit_off[A.n_tiles]) return;
@@ -406,6 +456,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_pileup(const K3Args A) {
     uint32_t prev_urank = 0xffffffffu, prev_frank = 0xffffffffu;
     bool first = true;
     const int minBQ = A.minBQ;
+    uint32_t since_flush = 0;
 
     for (uint32_t base = eb; base < ee; base += 32) {
         {   // stage the next 32 read records in shared memory (4 x 128-bit loads per lane)
@@ -417,22 +468,27 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_pileup(const K3Args A) {
                 dst[0] = r0; dst[1] = r1; dst[2] = r2; dst[3] = r3;
             }
         }
+        since_flush += 32;
+        if (since_flush > K3_FLUSH_EVERY) { flush_counters(A, fc, lane, L, lane_valid); since_flush = 0; }
         __syncwarp();
-        const int cntj = (int)min(32u, ee - base);
+        // the last batch runs one extra (sentinel) iteration that only closes the open fragment and barcode
+        const int cntj = (int)min(32u, ee - base) + (base + 32 >= ee ? 1 : 0);
         for (int j = 0; j < cntj; ++j) {
-            const uint32_t* rw = ws + j * 16;
+            const bool sentinel = base + (uint32_t)j >= ee;
+            const uint32_t* rw = ws + (j & 31) * 16;
             const uint4 q0 = *reinterpret_cast<const uint4*>(rw);        // start lo hi meta
             const uint4 q1 = *reinterpret_cast<const uint4*>(rw + 4);    // sp_aln seq_off qual_off cigar_off
             const uint2 q2 = *reinterpret_cast<const uint2*>(rw + 8);    // urank frank
             const int32_t start = (int32_t)q0.x, lo = (int32_t)q0.y, hi = (int32_t)q0.z;
             const uint32_t meta = q0.w;
-            const uint32_t urank = q2.x, frank = q2.y;
+            const uint32_t urank = sentinel ? 0xfffffffeu : q2.x, frank = sentinel ? 0xfffffffeu : q2.y;
             // ---- barcode / fragment boundaries (warp uniform)
             if (!first) {
                 if (frank != prev_frank) fragment_finalize(A, lane, ucnt, uprod, S);
-                if (urank != prev_urank) umi_finalize(A, lane, L, prev_urank, fc, limb, ucnt, uprod, S);
+                if (urank != prev_urank) umi_finalize(A, lane, L, prev_urank, fc, limb, ucnt, uprod, ut, S);
             }
             first = false; prev_urank = urank; prev_frank = frank;
+            if (sentinel) break;
             // ---- does the read cover my locus?
             const bool covered = lane_valid && Li >= lo && Li < hi;
             int qpos = 0, indel = 0; bool isdel = false;
@@ -481,7 +537,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_pileup(const K3Args A) {
                 uint32_t aid; int bq; bool regular = false, isN = false;
                 if (indel == 0 && isdel) {                                 // :416-421
                     aid = SMC_A_DEL; bq = minBQ;
-                    FC(KC_ALLELE, SMC_A_DEL) += 1;
+                    FCW(KW_ALLELE_FWD, SMC_A_DEL) += 1;
                 } else {
                     const uint32_t sb = __ldg(&A.seq[(size_t)q1.y + (qpos >> 1)]);
                     const uint32_t nib = (qpos & 1) ? (sb & 15u) : (sb >> 4);
@@ -489,8 +545,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_pileup(const K3Args A) {
                     const int fa = nib_to_fixed(nib);
                     if (indel == 0 && fa >= 0) {                           // :423-457 regular base, A/C/G/T
                         aid = (uint32_t)fa; regular = true;
-                        FC(KC_ALLELE, fa) += 1;
-                        if (!reverse) FC(KC_FWD, fa) += 1;
+                        FCW(KW_ALLELE_FWD, fa) += reverse ? 1 : 0x10001;
                     } else {
                         // dynamic allele: N / IUPAC base, insertion start (:371-389) or deletion start (:392-411)
                         unsigned long long key; int len = 0;
@@ -522,7 +577,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_pileup(const K3Args A) {
                             key = dyn_make_key((uint32_t)Li, SMC_K_BASE, nib, 0ull);
                             regular = true; isN = (nib == 15u);
                         }
-                        const uint32_t e = dyn_lookup(A, key, rw[14], qpos, len);
+                        const uint32_t e = dyn_lookup(A.dkey, A.dmask, A.drep_read, A.drep_qpos, A.dlen, A.dcount, A.gflags, key, rw[14], qpos, len);
                         aid = NF + e;
                         atomicAdd(&A.dcnt[(size_t)e * SMC_NCNT + SMC_C_ALLELE], 1);
                         if (!reverse) atomicAdd(&A.dcnt[(size_t)e * SMC_NCNT + SMC_C_FWD], 1);
@@ -530,19 +585,17 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_pileup(const K3Args A) {
                 }
                 const bool inc = (bq >= minBQ) && (meta & RM_OK);          // :378,400,421,431
                 if (regular) {
-                    if (bq < minBQ) inc_allele_counter(A, fc, lane, aid, KC_LOWQ);            // :428-429
-                    if (inc) {                                                                // :432-452
+                    if (bq < minBQ) bump(A, fc, lane, aid, KW_LOWQ_R2P, 1u, SMC_C_LOWQ, SMC_C_R2PLE);          // :428-429
+                    if (inc) {                                                                                  // :432-452
                         const int d = qpos - leftSP;
                         if (!read2) {
                             const int dist = reverse ? alnlen - d : d;
-                            inc_allele_counter(A, fc, lane, aid, KC_R1TOT);
-                            if (dist <= 20) inc_allele_counter(A, fc, lane, aid, KC_R1LE);
+                            bump(A, fc, lane, aid, KW_R1, dist <= 20 ? 0x10001u : 1u, SMC_C_R1TOT, SMC_C_R1LE);
                         } else {
                             const int dbc = reverse ? d : alnlen - d;
                             const int dpr = reverse ? alnlen - d : d;
-                            inc_allele_counter(A, fc, lane, aid, KC_R2TOT);
-                            if (dbc <= 20) inc_allele_counter(A, fc, lane, aid, KC_R2LE);
-                            if (dpr <= A.primerDist) inc_allele_counter(A, fc, lane, aid, KC_R2PLE);
+                            bump(A, fc, lane, aid, KW_R2, dbc <= 20 ? 0x10001u : 1u, SMC_C_R2TOT, SMC_C_R2LE);
+                            if (dpr <= A.primerDist) bump(A, fc, lane, aid, KW_LOWQ_R2P, 0x10000u, SMC_C_LOWQ, SMC_C_R2PLE);
                         }
                     }
                 }
@@ -552,30 +605,19 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_pileup(const K3Args A) {
                     if (!S.f_exists) { S.f_exists = true; S.f_aid = aid; S.f_bq = bq; S.f_paired = false; }
                     else if (aid == S.f_aid || isN) {
                         S.f_bq = min(S.f_bq, bq); S.f_paired = true;
-                        if (aid == S.f_aid) inc_allele_counter(A, fc, lane, aid, KC_CONCORD);
-                    } else { S.f_exists = false; inc_allele_counter(A, fc, lane, aid, KC_DISCORD); }
+                        if (aid == S.f_aid) bump(A, fc, lane, aid, KW_PAIR, 1u, SMC_C_CONCORD, SMC_C_DISCORD);
+                    } else { S.f_exists = false; bump(A, fc, lane, aid, KW_PAIR, 0x10000u, SMC_C_CONCORD, SMC_C_DISCORD); }
                 }
             }
         }
         __syncwarp();
     }
-    fragment_finalize(A, lane, ucnt, uprod, S);
-    umi_finalize(A, lane, L, prev_urank, fc, limb, ucnt, uprod, S);
-
     // ---- flush the lane's locus to the per-locus accumulators ([field][locus] layout: coalesced across lanes)
+    flush_counters(A, fc, lane, L, lane_valid);
     if (lane_valid) {
         const size_t nl = (size_t)A.n_loci;
 #pragma unroll
         for (int a = 0; a < NF; ++a) {
-#pragma unroll
-            for (int kc = 0; kc < K3_NC; ++kc) {
-                int v = FC(kc, a);
-                if (v) atomicAdd(&A.cnt[((size_t)a * SMC_NCNT + c_kc2out[kc]) * nl + L], v);
-            }
-            if (a != SMC_A_DEL) {
-                int rv = FC(KC_ALLELE, a) - FC(KC_FWD, a);
-                if (rv) atomicAdd(&A.cnt[((size_t)a * SMC_NCNT + SMC_C_REV) * nl + L], rv);
-            }
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 unsigned long long v = LIMB(a, j);
