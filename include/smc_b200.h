@@ -231,9 +231,15 @@ int smc_download(smc_ctx *ctx, smc_out *out);
 
 int smc_get_timings(smc_ctx *ctx, smc_timings *t);
 
-/* For loci flagged SMC_ST_NEED_DOWNSAMPLE: list the barcodes of bcDict (those with >= 1 read passing incCond) so the
- * host can draw the sample.  umi_out receives, locus after locus, the ascending barcode codes; off_out[n+1]. */
-int smc_list_barcodes(smc_ctx *ctx, int64_t n, const int64_t *locus, int64_t *off_out, uint64_t *umi_out, int64_t umi_capacity);
+/* For loci flagged SMC_ST_NEED_DOWNSAMPLE (after smc_run_resident / smc_call_batch): list the barcodes of bcDict (those
+ * with >= 1 read passing incCond, smCounter.py:467) so that the host can draw the reference's sample (:496-500).
+ * locus[n] ascending; off_out[n+1] receives the offsets (off_out[k+1]-off_out[k] == loc[SMC_L_NBC] of locus k); umi_out /
+ * first_read_out receive, per locus in unspecified order, the barcode codes and the index (into smc_reads_soa) of the
+ * barcode's first passing read at that locus (ascending first_read = the insertion order of bcDict).  Returns
+ * SMC_E_LIMIT with off_out filled when umi_capacity < off_out[n].  The listing pass invalidates the batch results: run
+ * the batch again (with the mask) before smc_download. */
+int smc_list_barcodes(smc_ctx *ctx, int64_t n, const int64_t *locus, int64_t *off_out, uint64_t *umi_out,
+                      uint32_t *first_read_out, int64_t umi_capacity);
 
 #ifdef __cplusplus
 }

@@ -93,7 +93,7 @@ def load():
     lib.smc_download.restype = C.c_int
     lib.smc_get_timings.argtypes = [_vp, C.POINTER(smc_timings)]
     lib.smc_get_timings.restype = C.c_int
-    lib.smc_list_barcodes.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, C.c_int64]
+    lib.smc_list_barcodes.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64]
     lib.smc_list_barcodes.restype = C.c_int
     _lib = lib
     return lib

@@ -196,6 +196,23 @@ class GpuCaller:
         self.run()
         return self.download(out)
 
+    def list_barcodes(self, locus_idx):
+        """Barcodes of bcDict for the given (ascending) loci of the last batch: (off[n+1], umi codes, first passing read)."""
+        locus = np.ascontiguousarray(np.asarray(locus_idx, dtype=np.int64))
+        n = int(locus.shape[0])
+        off = np.zeros(n + 1, dtype=np.int64)
+        rc = self.lib.smc_list_barcodes(self.h, n, _ffi.ptr(locus), _ffi.ptr(off), None, None, 0)
+        if rc not in (0, -3):
+            raise self._err("smc_list_barcodes", rc)
+        total = int(off[n])
+        umi = np.zeros(max(total, 1), dtype=np.uint64)
+        first = np.zeros(max(total, 1), dtype=np.uint32)
+        if total:
+            rc = self.lib.smc_list_barcodes(self.h, n, _ffi.ptr(locus), _ffi.ptr(off), _ffi.ptr(umi), _ffi.ptr(first), total)
+            if rc != 0:
+                raise self._err("smc_list_barcodes", rc)
+        return off, umi[:total], first[:total]
+
     def timings(self) -> dict:
         t = _ffi.smc_timings()
         self.lib.smc_get_timings(self.h, C.byref(t))

@@ -69,7 +69,7 @@ struct smc_ctx {
     DevBuf d_tasks;
     uint32_t task_cap = 0;
     // barcode listing
-    DevBuf d_list_idx, d_list_count, d_list_off, d_list_umi;
+    DevBuf d_list_idx, d_list_count, d_list_off, d_list_umi, d_list_first;
     smc_timings tm{};
     uint32_t chunk = 2048;
     const uint32_t* ev_read_sorted = nullptr;   // tile-sorted event -> srank map (lives in d_ev0 or d_ev1)
@@ -246,7 +246,7 @@ extern "C" void smc_ctx_destroy(smc_ctx* ctx) {
                       &ctx->d_dkey, &ctx->d_drep_read, &ctx->d_drep_qpos, &ctx->d_dlen, &ctx->d_dcnt, &ctx->d_dlimb, &ctx->d_diskey,
                       &ctx->d_lk0, &ctx->d_lk1, &ctx->d_lv0, &ctx->d_lv1, &ctx->d_s_key, &ctx->d_s_cnt, &ctx->d_s_limb, &ctx->d_s_iskey,
                       &ctx->d_s_pi, &ctx->d_s_rep_read, &ctx->d_s_rep_qpos, &ctx->d_s_len, &ctx->d_dyn_first, &ctx->d_tasks,
-                      &ctx->d_list_idx, &ctx->d_list_count, &ctx->d_list_off, &ctx->d_list_umi};
+                      &ctx->d_list_idx, &ctx->d_list_count, &ctx->d_list_off, &ctx->d_list_umi, &ctx->d_list_first};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->st) cudaStreamDestroy(ctx->st);
@@ -414,10 +414,30 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
     return run_pileup_and_stats(ctx, n_tiles, NE);
 }
 
+
+static void fill_k3args(smc_ctx* ctx, K3Args& A, uint32_t n_tiles) {
+    uint32_t* small = ctx->d_small.as<uint32_t>();
+    const uint32_t cap = ctx->dyn_cap;
+    A.recs = ctx->d_recs.as<ReadRec>(); A.ev_read = ctx->ev_read_sorted; A.tile_off = ctx->d_tile_off.as<uint32_t>();
+    A.unit_off = ctx->d_unit_off.as<uint32_t>(); A.n_tiles = n_tiles; A.chunk = ctx->chunk;
+    A.loci_pos = ctx->d_loci_pos.as<int32_t>(); A.n_loci = ctx->n_loci;
+    A.seq = ctx->d_seq.as<uint8_t>(); A.qual = ctx->d_qual.as<uint8_t>(); A.cigar = ctx->d_cigar.as<uint32_t>();
+    A.bqtab = ctx->d_bqtab.as<double>(); A.pcrtab = ctx->d_pcrtab.as<double>(); A.pcr_nmax = PCR_NMAX;
+    A.minBQ = ctx->prm.minBQ; A.mtDrop = ctx->prm.mtDrop; A.primerDist = ctx->prm.primerDist;
+    A.smt = ctx->prm.rpb < 1.5 ? 2.0 : ctx->prm.rpb < 3.0 ? 3.0 : 4.0;                     // smCounter.py:303-308
+    A.keep_idx = ctx->has_keep ? ctx->d_keep_idx.as<int32_t>() : nullptr;
+    A.keep_off = ctx->d_keep_off.as<int64_t>(); A.keep_umi = ctx->d_keep_umi.as<uint64_t>();
+    A.umi_of_urank = ctx->d_umi_of_urank.as<uint64_t>();
+    A.loc = ctx->d_loc.as<int32_t>(); A.cnt = ctx->d_cnt.as<int32_t>(); A.limb = ctx->d_limb.as<unsigned long long>();
+    A.dkey = ctx->d_dkey.as<unsigned long long>(); A.dmask = cap - 1; A.drep_read = ctx->d_drep_read.as<uint32_t>();
+    A.drep_qpos = ctx->d_drep_qpos.as<int32_t>(); A.dlen = ctx->d_dlen.as<int32_t>(); A.dcnt = ctx->d_dcnt.as<int32_t>();
+    A.dlimb = ctx->d_dlimb.as<unsigned long long>(); A.diskey = ctx->d_diskey.as<uint8_t>(); A.dcount = small + 6; A.gflags = small + 5;
+    A.list_idx = nullptr;
+}
+
 static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
     const int64_t nl = ctx->n_loci;
     uint32_t* small = ctx->d_small.as<uint32_t>();
-    const uint32_t* ev_read = ctx->ev_read_sorted;
     const size_t nlz = (size_t)(nl ? nl : 1);
     CK(ctx->d_loc.ensure(nlz * SMC_NLOC * 4)); CK(ctx->d_cnt.ensure(nlz * SMC_NFIXED * SMC_NCNT * 4));
     CK(ctx->d_limb.ensure(nlz * SMC_NFIXED * 3 * 8)); CK(ctx->d_pi.ensure(nlz * SMC_NFIXED * 8));
@@ -445,21 +465,7 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
         CK(cudaMemsetAsync(small + 5, 0, 24, ctx->st));     // gflags, dyn count, n_tasks, cvg sum
         if (NE > 0) {
             K3Args A{};
-            A.recs = ctx->d_recs.as<ReadRec>(); A.ev_read = ev_read; A.tile_off = ctx->d_tile_off.as<uint32_t>();
-            A.unit_off = ctx->d_unit_off.as<uint32_t>(); A.n_tiles = n_tiles; A.chunk = ctx->chunk;
-            A.loci_pos = ctx->d_loci_pos.as<int32_t>(); A.n_loci = nl;
-            A.seq = ctx->d_seq.as<uint8_t>(); A.qual = ctx->d_qual.as<uint8_t>(); A.cigar = ctx->d_cigar.as<uint32_t>();
-            A.bqtab = ctx->d_bqtab.as<double>(); A.pcrtab = ctx->d_pcrtab.as<double>(); A.pcr_nmax = PCR_NMAX;
-            A.minBQ = ctx->prm.minBQ; A.mtDrop = ctx->prm.mtDrop; A.primerDist = ctx->prm.primerDist;
-            A.smt = ctx->prm.rpb < 1.5 ? 2.0 : ctx->prm.rpb < 3.0 ? 3.0 : 4.0;                     // smCounter.py:303-308
-            A.keep_idx = ctx->has_keep ? ctx->d_keep_idx.as<int32_t>() : nullptr;
-            A.keep_off = ctx->d_keep_off.as<int64_t>(); A.keep_umi = ctx->d_keep_umi.as<uint64_t>();
-            A.umi_of_urank = ctx->d_umi_of_urank.as<uint64_t>();
-            A.loc = ctx->d_loc.as<int32_t>(); A.cnt = ctx->d_cnt.as<int32_t>(); A.limb = ctx->d_limb.as<unsigned long long>();
-            A.dkey = ctx->d_dkey.as<unsigned long long>(); A.dmask = cap - 1; A.drep_read = ctx->d_drep_read.as<uint32_t>();
-            A.drep_qpos = ctx->d_drep_qpos.as<int32_t>(); A.dlen = ctx->d_dlen.as<int32_t>(); A.dcnt = ctx->d_dcnt.as<int32_t>();
-            A.dlimb = ctx->d_dlimb.as<unsigned long long>(); A.diskey = ctx->d_diskey.as<uint8_t>(); A.dcount = small + 6; A.gflags = small + 5;
-            A.list_idx = nullptr;
+            fill_k3args(ctx, A, n_tiles);
             const int64_t max_units = (int64_t)n_tiles + NE / ctx->chunk + 1;
             CK(cudaEventRecord(ctx->ev[8], ctx->st));
             LAUNCH(k_pileup, nblk(max_units, K3_WARPS), K3_WARPS * 32, K3_SMEM_BYTES, A);
@@ -605,9 +611,48 @@ extern "C" int smc_get_timings(smc_ctx* ctx, smc_timings* t) {
     return SMC_OK;
 }
 
-extern "C" int smc_list_barcodes(smc_ctx* ctx, int64_t n, const int64_t* locus, int64_t* off_out, uint64_t* umi_out, int64_t umi_capacity) {
+extern "C" int smc_list_barcodes(smc_ctx* ctx, int64_t n, const int64_t* locus, int64_t* off_out, uint64_t* umi_out,
+                                 uint32_t* first_read_out, int64_t umi_capacity) {
     if (!ctx) return SMC_E_ARG;
-    (void)n; (void)locus; (void)off_out; (void)umi_out; (void)umi_capacity;
-    ctx->err = "smc_list_barcodes: not implemented yet";
-    return SMC_E_STATE;
+    if (!ctx->ran) { ctx->err = "smc_list_barcodes: run a batch first"; return SMC_E_STATE; }
+    if (n < 0 || (n > 0 && (!locus || !off_out))) { ctx->err = "smc_list_barcodes: bad arguments"; return SMC_E_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    const int64_t nl = ctx->n_loci;
+    std::vector<int32_t> nbc((size_t)(nl ? nl : 1));
+    if (nl) CK(cudaMemcpy(nbc.data(), ctx->d_loc.as<int32_t>() + (size_t)SMC_L_NBC * nl, (size_t)nl * 4, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> idx((size_t)(nl ? nl : 1), -1);
+    off_out[0] = 0;
+    for (int64_t k = 0; k < n; ++k) {
+        if (locus[k] < 0 || locus[k] >= nl || (k > 0 && locus[k] <= locus[k - 1])) {
+            ctx->err = "smc_list_barcodes: locus indices must be ascending and inside the batch"; return SMC_E_ARG;
+        }
+        idx[(size_t)locus[k]] = (int32_t)k;
+        off_out[k + 1] = off_out[k] + nbc[(size_t)locus[k]];
+    }
+    const int64_t total = n ? off_out[n] : 0;
+    if (total > umi_capacity || (total > 0 && (!umi_out || !first_read_out))) {
+        ctx->err = "smc_list_barcodes: umi_capacity too small (needed count is off_out[n])"; return SMC_E_LIMIT;
+    }
+    if (total == 0 || ctx->n_tile_events == 0) return SMC_OK;
+    CK(ctx->d_list_idx.ensure((size_t)nl * 4)); CK(ctx->d_list_count.ensure((size_t)n * 4)); CK(ctx->d_list_off.ensure((size_t)(n + 1) * 8));
+    CK(ctx->d_list_umi.ensure((size_t)total * 8)); CK(ctx->d_list_first.ensure((size_t)total * 4));
+    CK(cudaMemcpyAsync(ctx->d_list_idx.p, idx.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->d_list_off.p, off_out, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(ctx->d_list_count.p, 0, (size_t)n * 4, ctx->st));
+    // The listing pass re-runs the pileup kernel; it adds to the accumulators again, so the batch must be re-run
+    // (with the mask) before the next download.
+    ctx->ran = false;
+    K3Args A{};
+    fill_k3args(ctx, A, ctx->n_tiles);
+    A.keep_idx = nullptr;
+    A.list_idx = ctx->d_list_idx.as<int32_t>(); A.list_count = ctx->d_list_count.as<uint32_t>();
+    A.list_off = ctx->d_list_off.as<int64_t>(); A.list_umi = ctx->d_list_umi.as<uint64_t>();
+    A.list_first = ctx->d_list_first.as<uint32_t>(); A.list_cap = total;
+    const int64_t max_units = (int64_t)ctx->n_tiles + ctx->n_tile_events / ctx->chunk + 1;
+    LAUNCH(k_pileup, nblk(max_units, K3_WARPS), K3_WARPS * 32, K3_SMEM_BYTES, A);
+    CK(cudaMemcpyAsync(umi_out, ctx->d_list_umi.p, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(first_read_out, ctx->d_list_first.p, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaGetLastError());
+    return SMC_OK;
 }

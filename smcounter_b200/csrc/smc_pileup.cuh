@@ -141,7 +141,7 @@ struct K3Args {
     unsigned long long* dkey; uint32_t dmask; uint32_t* drep_read; int32_t* drep_qpos; int32_t* dlen;
     int32_t* dcnt; unsigned long long* dlimb; uint8_t* diskey; uint32_t* dcount; uint32_t* gflags;
     // optional: list the barcodes of bcDict for flagged loci (down-sampling support)
-    const int32_t* list_idx; uint32_t* list_count; const int64_t* list_off; uint64_t* list_umi; int64_t list_cap;
+    const int32_t* list_idx; uint32_t* list_count; const int64_t* list_off; uint64_t* list_umi; uint32_t* list_first; int64_t list_cap;
 };
 
 // BAM nibble of A, C, G, T -> fixed slot (A0 C1 T3 G4), anything else -> -1
@@ -198,7 +198,7 @@ struct LaneState {
     uint32_t keymask, status;
     // barcode-level
     int n; uint32_t exist; double Q, rightP; uint32_t last_aid; uint32_t udyn0, udyn1; int ndyn;
-    bool umi_seen, umi_bc;
+    bool umi_seen, umi_bc; uint32_t first_read;     // BAM index of the barcode's first passing read at this locus
     // fragment-level
     bool frag_seen, f_exists, f_paired; uint32_t f_aid; int f_bq;
 };
@@ -294,7 +294,7 @@ __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int64_t 
             if (li >= 0) {
                 uint32_t slot = atomicAdd(&A.list_count[li], 1u);
                 int64_t o = A.list_off[li] + slot;
-                if (o < A.list_off[li + 1] && o < A.list_cap) A.list_umi[o] = A.umi_of_urank[urank];
+                if (o < A.list_off[li + 1] && o < A.list_cap) { A.list_umi[o] = A.umi_of_urank[urank]; A.list_first[o] = S.first_read; }
             }
         }
     }
@@ -380,7 +380,7 @@ __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int64_t 
             }
         }
     }
-    S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.ndyn = 0; S.umi_seen = false; S.umi_bc = false;
+    S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.ndyn = 0; S.umi_seen = false; S.umi_bc = false; S.first_read = 0xffffffffu;
 }
 
 // first event index >= x (x > tb) at which the barcode changes, or te
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup(const K3
     S.cvg = S.allFrag = S.allMT = S.usedFrag = S.nBC = S.usedMT = S.mt3 = S.mt5 = S.mt7 = S.mt10 = 0;
     S.keymask = 0; S.status = 0;
     S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.last_aid = 0; S.udyn0 = S.udyn1 = 0; S.ndyn = 0;
-    S.umi_seen = S.umi_bc = false;
+    S.umi_seen = S.umi_bc = false; S.first_read = 0xffffffffu;
     S.frag_seen = S.f_exists = S.f_paired = false; S.f_aid = 0; S.f_bq = 0;
 
     uint32_t prev_urank = 0xffffffffu, prev_frank = 0xffffffffu;
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup(const K3
                 }
                 S.umi_seen = true; S.frag_seen = true;                     // :463-464
                 if (inc) {                                                 // :467-479
-                    S.umi_bc = true;
+                    S.umi_bc = true; S.first_read = min(S.first_read, rw[14]);
                     if (!S.f_exists) { S.f_exists = true; S.f_aid = aid; S.f_bq = bq; S.f_paired = false; }
                     else if (aid == S.f_aid || isN) {
                         S.f_bq = min(S.f_bq, bq); S.f_paired = true;

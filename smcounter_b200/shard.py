@@ -1,0 +1,95 @@
+"""Sharding of the target across GPUs: loci are independent (vc() takes one position and
+shares nothing, smCounter.py:274,684), so BED intervals are split into per-GPU groups balanced by estimated pileup
+depth and each GPU receives only the reads that overlap its intervals.  No collective is needed: the host
+concatenates the per-locus rows in BED order (the reference gathers ``p.get()`` in submission order, :685).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .soa import Loci, ReadsSoA
+
+
+def estimate_interval_events(reads: ReadsSoA, intervals, chroms) -> np.ndarray:
+    """Estimated pileup read-events per interval = sum over reads of the overlap length with the interval."""
+    cidx = {c: i for i, c in enumerate(chroms)}
+    ends = reads.ref_end()
+    starts = reads.pos.astype(np.int64)
+    out = np.zeros(len(intervals), dtype=np.float64)
+    order_by_ref = {}
+    for r in np.unique(reads.ref_id):
+        m = np.flatnonzero(reads.ref_id == r)
+        order_by_ref[int(r)] = (starts[m], ends[m])
+    for k, (c, s, e) in enumerate(intervals):
+        t = order_by_ref.get(cidx.get(c, -1))
+        if t is None or e <= s:
+            continue
+        st, en = t
+        lo = np.searchsorted(st, e, side="left")          # reads starting before the interval end (st is sorted: BAM order)
+        ov = np.minimum(en[:lo], e) - np.maximum(st[:lo], s)
+        out[k] = float(ov[ov > 0].sum())
+    return out
+
+
+def assign_intervals(weights, n_shards: int):
+    """Greedy longest-processing-time assignment; returns shard index per interval (deterministic)."""
+    w = np.asarray(weights, dtype=np.float64)
+    order = np.argsort(-w, kind="stable")
+    load = np.zeros(n_shards, dtype=np.float64)
+    shard = np.zeros(len(w), dtype=np.int64)
+    for k in order:
+        g = int(np.argmin(load))
+        shard[k] = g
+        load[g] += w[k] + 1.0          # +1 so that empty intervals still spread out
+    return shard, load
+
+
+def reads_for_intervals(reads: ReadsSoA, intervals, chroms) -> np.ndarray:
+    """Ascending indices of the reads whose reference span touches one of ``intervals`` (BAM order is kept)."""
+    cidx = {c: i for i, c in enumerate(chroms)}
+    ends = reads.ref_end()
+    starts = reads.pos.astype(np.int64)
+    keep = np.zeros(reads.n, dtype=bool)
+    for (c, s, e) in intervals:
+        r = cidx.get(c)
+        if r is None or e <= s:
+            continue
+        keep |= (reads.ref_id == r) & (starts < e) & (ends > s)
+    return np.flatnonzero(keep)
+
+
+def subset_loci(loci: Loci, intervals, chroms):
+    """Indices (into ``loci``) of the unique loci that fall inside ``intervals``."""
+    cidx = {c: i for i, c in enumerate(chroms)}
+    keep = np.zeros(loci.n, dtype=bool)
+    for (c, s, e) in intervals:
+        r = cidx.get(c)
+        if r is None:
+            continue
+        keep |= (loci.ref_id == r) & (loci.pos0 >= s) & (loci.pos0 < e)
+    return np.flatnonzero(keep)
+
+
+def plan_shards(reads: ReadsSoA, intervals, chroms, n_shards: int):
+    """[(interval indices, estimated events)] per shard; intervals keep their BED order inside a shard."""
+    if n_shards <= 1:
+        return [(list(range(len(intervals))), float(estimate_interval_events(reads, intervals, chroms).sum()))]
+    w = estimate_interval_events(reads, intervals, chroms)
+    shard, load = assign_intervals(w, n_shards)
+    return [([int(k) for k in np.flatnonzero(shard == g)], float(load[g])) for g in range(n_shards)]
+
+
+def interleave_rows(plan, intervals, shard_rows):
+    """Per-shard row lists (each in the BED order of the shard's own intervals) -> one list in the BED order of
+    ``intervals`` (what the reference's in-order ``p.get()`` gather produces, smCounter.py:685)."""
+    per_interval = {}
+    for g, (idxs, _) in enumerate(plan):
+        o = 0
+        for k in idxs:
+            n = max(0, intervals[k][2] - intervals[k][1])
+            per_interval[k] = shard_rows[g][o:o + n]
+            o += n
+    out = []
+    for k in range(len(intervals)):
+        out.extend(per_interval.get(k, ()))
+    return out

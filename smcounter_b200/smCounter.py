@@ -1,0 +1,165 @@
+"""smCounter command line and ``main(args)`` with the reference's contract (smCounter.py:616-640, 645-909), running the
+per-locus calling hot path on B200 GPUs through libsmc_b200.so.
+
+Same parameters (bamFile, bedTarget, refGenome, mtDepth, rpb, minBQ, minMQ, hpLen, mismatchThr, mtDrop, maxMT, primerDist,
+threshold, bedTandemRepeats, bedRepeatMaskerSubset, runPath, logFile, paramFile, nCPU, bedtoolsPath), same three output
+files with the same columns, same return value (the PI threshold).  What changes underneath:
+
+  * the BAM is decoded once into flat SoA buffers (smcounter_b200.bam) instead of once per locus through pysam;
+  * ``Pool(nCPU).apply_async(vc_wrapper, ...)`` per locus (smCounter.py:683-685) becomes one batched
+    ``GpuCaller.call`` per GPU over depth-balanced BED-interval shards (``--gpus``; ``--nCPU`` is accepted and only
+    bounds the host threads of the BAM decoder);
+  * bedtools (smCounter.py:700-710) is replaced by in-process interval arithmetic (smcounter_b200.repeats);
+    ``--bedtoolsPath`` is accepted and ignored.
+
+There is no CPU implementation of the calling path in this package: without libsmc_b200.so or without a CUDA device
+``main`` raises.
+"""
+from __future__ import annotations
+
+import argparse
+import datetime
+import os
+import threading
+
+import numpy as np
+
+from . import repeats, writers
+from .bam import read_bam
+from .caller import GpuCaller, UmiKeep, VcParams
+from .downsample import draw_keep_masks
+from .fasta import FastaFile
+from .rows import format_rows
+from .shard import interleave_rows, plan_shards, reads_for_intervals
+from .targets import build_loci, intervals_from_bed_lines
+
+parser = None
+
+
+def argParseInit():
+    """smCounter.py:617-640, plus --gpus (how many B200s to shard the target over)."""
+    global parser
+    parser = argparse.ArgumentParser(description='Variant calling using molecular barcodes', fromfile_prefix_chars='@')
+    parser.add_argument('--outPrefix', default=None, required=True, help='prefix for output files')
+    parser.add_argument('--bamFile', default=None, required=True, help='BAM file')
+    parser.add_argument('--bedTarget', default=None, required=True, help='BED file for target region')
+    parser.add_argument('--mtDepth', default=None, required=True, type=int, help='Mean MT depth')
+    parser.add_argument('--rpb', default=None, required=True, type=float, help='Mean read pairs per MT')
+    parser.add_argument('--nCPU', type=int, default=1, help='number of CPUs to use in parallel')
+    parser.add_argument('--minBQ', type=int, default=20, help='minimum base quality allowed for analysis')
+    parser.add_argument('--minMQ', type=int, default=30, help='minimum mapping quality allowed for analysis')
+    parser.add_argument('--hpLen', type=int, default=10, help='Minimum length for homopolymers')
+    parser.add_argument('--mismatchThr', type=float, default=6.0, help='average number of mismatches per 100 bases allowed')
+    parser.add_argument('--mtDrop', type=int, default=0, help='Drop MTs with lower than or equal to X reads.')
+    parser.add_argument('--maxMT', type=int, default=0, help='Randomly downsample to X MTs (max number of MTs at any position). If set to 0 (default), maxMT = 2.0 * mean MT depth')
+    parser.add_argument('--primerDist', type=int, default=2, help='filter variants that are within X bases to primer')
+    parser.add_argument('--threshold', type=int, default=0, help='Minimum prediction index for a variant to be called. Must be non-negative. Typically ranges from 10 to 60. If set to 0 (default), smCounter will choose the appropriate cutoff based on the mean MT depth.')
+    parser.add_argument('--refGenome', default='/qgen/home/rvijaya/downloads/alt_hap_masked_ref/ucsc.hg19.fasta')
+    parser.add_argument('--bedTandemRepeats', default='/qgen/home/xuc/UCSC/simpleRepeat.bed', help='bed for UCSC tandem repeats')
+    parser.add_argument('--bedRepeatMaskerSubset', default='/qgen/home/xuc/UCSC/SR_LC_SL.nochr.bed', help='bed for RepeatMasker simple repeats, low complexity, microsatellite regions')
+    parser.add_argument('--bedtoolsPath', default='/qgen/bin/bedtools-2.25.0/bin/', help='path to bedtools (accepted for compatibility; interval arithmetic is done in-process)')
+    parser.add_argument('--runPath', default=None, help='path to working directory')
+    parser.add_argument('--logFile', default=None, help='log file')
+    parser.add_argument('--paramFile', default=None, help='optional parameter file that contains the above paramters. if specified, this must be the only parameter, except for --logFile.')
+    parser.add_argument('--gpus', type=int, default=1, help='number of B200 GPUs to shard the target over (BED intervals, balanced by depth)')
+
+
+def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None):
+    """The drop-in for the reference's per-locus fan-out: rows of vc() (45 tab-joined fields each, FILTER still in
+    accumulator form) for every position of ``intervals`` in BED order.
+
+    ``reads``: ReadsSoA of the BAM; ``refs``: object with fetch()/get_reference_length().  One host thread per GPU
+    (ctypes drops the GIL); a failing shard fails the run like smCounter.py:690-694."""
+    chroms = reads.chroms
+    devices = list(devices) if devices is not None else list(range(max(1, gpus)))
+    plan = plan_shards(reads, intervals, chroms, len(devices))
+    shard_rows = [None] * len(plan)
+    errors = [None] * len(plan)
+
+    def work(g):
+        try:
+            ivs = [intervals[k] for k in plan[g][0]]
+            if not ivs:
+                shard_rows[g] = []
+                return
+            sub = reads if len(plan) == 1 else reads.select(reads_for_intervals(reads, ivs, chroms))
+            loci, bed_order = build_loci(ivs, chroms, refs)
+            caller = GpuCaller(prm, devices[g])
+            try:
+                res = caller.call(sub, loci)
+                keep = draw_keep_masks(caller, res, sub, loci, chroms, prm)        # smCounter.py:496-500
+                if keep is not None:
+                    res = caller.call(sub, loci, keep)
+            finally:
+                caller.close()
+            shard_rows[g] = format_rows(res, sub, loci, chroms, refs, prm.hpLen, bed_order)
+        except BaseException as e:          # noqa: BLE001 -- re-raised on the main thread
+            errors[g] = e
+
+    if len(plan) == 1:
+        work(0)
+    else:
+        ts = [threading.Thread(target=work, args=(g,)) for g in range(len(plan))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    for e in errors:
+        if e is not None:
+            raise e
+    return interleave_rows(plan, intervals, shard_rows)
+
+
+def main(args):
+    timeStart = datetime.datetime.now()
+    print("smCounter started at " + str(timeStart))
+    if parser is None:
+        argParseInit()
+    if type(args) is not argparse.Namespace:                               # smCounter.py:656-660 (dict from a pipeline)
+        argsList = []
+        for argName, argVal in args.items():
+            argsList.append("--{0}={1}".format(argName, argVal))
+        args = parser.parse_args(argsList)
+    elif args.paramFile is not None:                                       # :663-664
+        args = parser.parse_args(("@" + args.paramFile,))
+    for argName, argVal in vars(args).items():                             # :667-668
+        print(argName, argVal)
+    if args.runPath is not None:                                           # :671-672
+        os.chdir(args.runPath)
+
+    with open(args.bedTarget, 'r') as fh:                                  # :675-680
+        bed_lines = fh.readlines()
+    intervals = intervals_from_bed_lines(bed_lines)
+    refs = FastaFile(args.refGenome)
+    reads = read_bam(args.bamFile, intervals, threads=max(1, args.nCPU))
+    prm = VcParams(mtDepth=args.mtDepth, rpb=args.rpb, minBQ=args.minBQ, minMQ=args.minMQ, hpLen=args.hpLen,
+                   mismatchThr=args.mismatchThr, mtDrop=args.mtDrop, maxMT=args.maxMT, primerDist=args.primerDist)
+    try:
+        output = call_loci(reads, intervals, refs, prm, gpus=args.gpus)
+    except Exception as e:
+        print(str(e))
+        raise
+
+    print("begin variant filtering and output")                           # :697
+    target_rows = [tuple(l.strip().split('\t')[0:3]) for l in bed_lines if not l.startswith("track ") and l.strip()]
+    trf_rows = repeats.read_bed_rows(args.bedTandemRepeats) if args.bedTandemRepeats and os.path.exists(args.bedTandemRepeats) else []
+    rm_rows = repeats.read_bed_rows(args.bedRepeatMaskerSubset, 4) if args.bedRepeatMaskerSubset and os.path.exists(args.bedRepeatMaskerSubset) else []
+    if not trf_rows and not rm_rows:
+        print("warning: repeat tracks not found; RepT/RepS/LowC/SL filters are not applied")
+    trf, rm = repeats.build_repeat_regions(target_rows, trf_rows, rm_rows)
+    output = repeats.apply_repeat_filters(output, trf, rm)
+    threshold = writers.write_outputs(output, args.outPrefix, args.mtDepth, args.threshold)
+
+    timeEnd = datetime.datetime.now()
+    print("smCounter completed running at " + str(timeEnd))
+    print("smCounter total time: " + str(timeEnd - timeStart))
+    return threshold                                                       # :909
+
+
+if __name__ == "__main__":
+    argParseInit()
+    _args = parser.parse_args()
+    if _args.logFile:
+        from . import run_log
+        run_log.init(_args.logFile)
+    main(_args)

@@ -1,0 +1,106 @@
+"""BAM/BGZF decode -> ReadsSoA (smcounter_b200/bam.py): write a synthetic panel as a BAM, read it back, compare every
+buffer; identity parsing follows smCounter.py:319-325 and the NM lookup :329-334."""
+import gzip
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from smcounter_b200 import bam
+from smcounter_b200.synth import SynthSpec, make_panel
+
+FIELDS = ("ref_id", "pos", "flag", "mapq", "nm", "l_seq", "seq_off", "qual_off", "cigar_off", "n_cigar", "umi", "frag_id", "seq",
+          "qual", "cigar")
+
+
+def _panel(seed=2):
+    spec = SynthSpec(umis_per_locus=15, rpb=2.5, snv_every=30, snv_vaf=0.2, indel_every=40, indel_vaf=0.2, softclip_frac=0.2)
+    ivs = [("chr1", 400, 460), ("chr2", 150, 170)]
+    s, refs, _ = make_panel(ivs, spec, seed=seed)
+    return s, refs, ivs
+
+
+def _decoders():
+    out = [False]
+    try:
+        from smcounter_b200 import _bamio
+        _bamio.load()
+        out.append(True)
+    except ImportError:
+        pass
+    return out
+
+
+@pytest.mark.parametrize("native", _decoders())
+def test_bam_roundtrip(tmp_path, native):
+    s, refs, ivs = _panel()
+    path = str(tmp_path / "t.bam")
+    bam.write_bam(path, s, refs.lengths)
+    back = bam.read_bam(path, native=native)
+    assert back.chroms == s.chroms and back.n == s.n
+    for f in FIELDS:
+        assert np.array_equal(getattr(s, f), getattr(back, f)), f
+    assert {bam.umi_code(v, {}) for v in back.umi_names.values()} == set(back.umi.tolist())
+    # it is a valid gzip stream and ends with the BGZF EOF marker
+    raw = open(path, "rb").read()
+    assert raw.endswith(bam._BGZF_EOF)
+    assert gzip.decompress(raw)[:4] == b"BAM\x01"
+
+
+@pytest.mark.parametrize("native", _decoders())
+def test_bam_interval_filter_and_tags(tmp_path, native):
+    s, refs, ivs = _panel(seed=5)
+    path = str(tmp_path / "t.bam")
+    # NM stored as a 32-bit int after other tags of every encoding class
+    extra = b"RGZgrp1\x00" + b"XAc\xff" + b"XBS\x01\x02" + b"XCf\x00\x00\x80\x3f" + b"XDBc\x03\x00\x00\x00\x01\x02\x03" + b"XEH1AE3\x00"
+    bam.write_bam(path, s, refs.lengths, nm_type="i", extra_tags=extra,
+                  qname_fn=lambda i, fid, bc: "INST:1:FC:%d:%s:%d" % (fid, bc, 7))
+    target = [ivs[1]]
+    back = bam.read_bam(path, intervals=target, native=native)
+    ends = s.ref_end()
+    keep = np.flatnonzero((s.ref_id == 1) & (s.pos < target[0][2]) & (ends > target[0][1]))
+    assert back.n == len(keep) > 0
+    for f in ("pos", "flag", "mapq", "nm", "l_seq", "n_cigar", "umi"):
+        assert np.array_equal(getattr(s, f)[keep], getattr(back, f)), f
+    # fragment ids: same partition as the original, numbered by first appearance
+    pairs = set(zip(s.frag_id[keep].tolist(), back.frag_id.tolist()))
+    assert len(pairs) == len(set(back.frag_id.tolist())) == len(set(s.frag_id[keep].tolist()))
+    assert np.array_equal(np.unique(back.frag_id, return_index=True)[1], np.sort(np.unique(back.frag_id, return_index=True)[1]))
+    first_seen = [back.frag_id[i] for i in sorted(np.unique(back.frag_id, return_index=True)[1])]
+    assert first_seen == list(range(len(first_seen)))
+
+
+@pytest.mark.parametrize("native", _decoders())
+def test_unmapped_dropped_and_missing_nm(tmp_path, native):
+    s, refs, ivs = _panel(seed=8)
+    s.flag = s.flag.copy()
+    s.flag[3] |= 0x4
+    path = str(tmp_path / "t.bam")
+    bam.write_bam(path, s, refs.lengths)
+    # strip the NM tag of every record by rewriting the raw stream
+    raw = bam.bgzf_decompress(open(path, "rb").read())
+    _, refs_hdr, first = bam.parse_header(raw)
+    out = [raw[:first]]
+    p = first
+    while p < len(raw):
+        bs = struct.unpack_from("<i", raw, p)[0]
+        body = raw[p + 4:p + 4 + bs]
+        assert body[-4:-1] == b"NMC"
+        body = body[:-4]
+        out.append(struct.pack("<i", len(body)) + body)
+        p += 4 + bs
+    with open(path, "wb") as fh:
+        fh.write(bam.bgzf_compress(b"".join(out)))
+    back = bam.read_bam(path, native=native)
+    assert back.n == s.n - 1 and not (back.flag & 0x4).any()
+    assert (back.nm == 0).all()                                    # smCounter.py:329-334: NM defaults to 0
+
+
+def test_bgzf_multi_block_roundtrip():
+    rng = np.random.default_rng(0)
+    data = rng.integers(0, 4, size=300000, dtype=np.uint8).tobytes()
+    comp = bam.bgzf_compress(data, block=40000)
+    assert bam.bgzf_decompress(comp) == data
+    with pytest.raises(ValueError):
+        bam.bgzf_decompress(b"\x1f\x8b\x08\x00" + b"\x00" * 30)

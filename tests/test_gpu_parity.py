@@ -26,3 +26,72 @@ def test_parity_case(name):
     print(name, stats)
     assert not problems, "\n".join(problems)
     assert stats["events"] > 0
+
+
+def test_downsampling_mask_from_oracle():
+    """mtDepth far below the real depth: ds = 2*mtDepth fires on most loci; the CUDA path applies the read-selection mask
+    the oracle produced (north_star) and must agree on everything downstream of it."""
+    from helpers import run_case
+    spec = SynthSpec(umis_per_locus=60, rpb=3.0, snv_every=35, snv_vaf=0.15)
+    problems, stats, _ = run_case([("chr1", 1000, 1080)], spec, VcParams(mtDepth=18, rpb=3.0), seed=17)
+    assert stats["n_downsampled"] > 20
+    assert not problems, "\n".join(problems)
+
+
+def test_downsampling_drawn_by_the_product_matches_oracle_py2_sampler():
+    """No external mask: the product lists the barcodes on the device (smc_list_barcodes), emulates CPython-2
+    random.seed(pos)/random.sample over the Py2 dict order on the host, and re-runs with its own mask.  The oracle does
+    the same with its independent restatement (sampler='py2'); rows must be byte-identical."""
+    from helpers import oracle_run
+    from smcounter_b200.smCounter import call_loci
+    from smcounter_b200.synth import make_panel
+    ivs = [("chr1", 2000, 2050), ("chr2", 400, 420)]
+    prm = VcParams(mtDepth=15, rpb=3.0)
+    soa, refs, _ = make_panel(ivs, SynthSpec(umis_per_locus=50, rpb=3.0, snv_every=30, snv_vaf=0.2, indel_every=45, indel_vaf=0.1), seed=23)
+    o_rows, details = oracle_run(soa, ivs, refs, prm)
+    assert sum(1 for d in details if d.get("nBC", 0) > d.get("ds", 1 << 30)) > 10
+    g_rows = call_loci(soa, ivs, refs, prm, gpus=1)
+    assert g_rows == o_rows
+
+
+def test_cli_end_to_end_files(tmp_path):
+    """smCounter.main(): BAM + BED + FASTA + repeat tracks on disk -> .all.txt / .cut.txt / .cut.vcf, byte-identical to
+    the oracle's restatement of main() (smCounter.py:645-909) on the same inputs."""
+    import argparse
+    from oracle import smcounter_oracle as orc
+    from smcounter_b200 import bam, smCounter
+    from smcounter_b200.soa import soa_to_records
+    from smcounter_b200.synth import make_panel
+    ivs = [("chr1", 1000, 1150), ("chr2", 600, 640), ("chr1", 1100, 1120)]
+    spec = SynthSpec(umis_per_locus=80, rpb=3.0, snv_every=40, snv_vaf=0.2, indel_every=60, indel_vaf=0.15)
+    soa, refs, _ = make_panel(ivs, spec, seed=31)
+    # files
+    fa = tmp_path / "ref.fa"
+    with open(fa, "w") as fh:
+        for c in soa.chroms:
+            s = refs.fetch(c, 0, refs.get_reference_length(c))
+            fh.write(">%s\n" % c)
+            for i in range(0, len(s), 60):
+                fh.write(s[i:i + 60] + "\n")
+    bed = tmp_path / "target.bed"
+    bed_lines = ["track name=t\n"] + ["%s\t%d\t%d\n" % iv for iv in ivs]
+    bed.write_text("".join(bed_lines))
+    trf_rows = [("chr1", "1010", "1040"), ("chr2", "0", "700")]
+    rm_rows = [("chr1", "1030", "1060", "Simple_repeat"), ("chr1", "1055", "1100", "Low_complexity"), ("chr1", "1101", "1105", "Satellite"),
+               ("chr2", "610", "620", "L1")]
+    trf = tmp_path / "trf.bed"; trf.write_text("".join("\t".join(r) + "\n" for r in trf_rows))
+    rm = tmp_path / "rm.bed"; rm.write_text("".join("\t".join(r) + "\n" for r in rm_rows))
+    bam_path = tmp_path / "reads.bam"
+    bam.write_bam(str(bam_path), soa, refs.lengths)
+    prefix = str(tmp_path / "out")
+    smCounter.argParseInit()
+    thr = smCounter.main({"outPrefix": prefix, "bamFile": str(bam_path), "bedTarget": str(bed), "mtDepth": 80, "rpb": 3.0,
+                          "refGenome": str(fa), "bedTandemRepeats": str(trf), "bedRepeatMaskerSubset": str(rm), "threshold": 20})
+    assert thr == 20
+    # oracle on the same inputs (FASTA contents identical to SparseRef: windows + N elsewhere)
+    want_thr, all_txt, cut_txt, cut_vcf = orc.run(soa_to_records(soa, orc.Read), bed_lines, refs, mtDepth=80, rpb=3.0, threshold=20,
+                                                   outPrefix=prefix, trf_rows=trf_rows, rm_rows=rm_rows)
+    assert open(prefix + ".smCounter.all.txt").read() == all_txt
+    assert open(prefix + ".smCounter.cut.txt").read() == cut_txt
+    assert open(prefix + ".smCounter.cut.vcf").read() == cut_vcf
+    assert cut_txt.count("\n") > 3 and "RepT" in all_txt and ("RepS" in all_txt or "LowC" in all_txt)

@@ -1,0 +1,249 @@
+"""CPU tests of the host side of the product package (no compute calls): formatting with Python-2 semantics, target
+list, FASTA access, SoA containers, repeat filters, writers, down-sampling emulation, sharding, BAM round trip.
+Where the oracle restates the same reference code independently, the two implementations are checked against each
+other; the writers are also checked against the reference's committed example outputs."""
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import py2compat
+from oracle import smcounter_oracle as orc
+from smcounter_b200 import downsample, repeats, rows, shard, soa, targets, writers
+from smcounter_b200.caller import UmiKeep, VcParams
+from smcounter_b200.fasta import FastaFile, SparseRef
+from smcounter_b200.synth import SynthSpec, make_panel
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ---------------------------------------------------------------------------------------------- Py2 formatting
+@settings(max_examples=300, deadline=None)
+@given(st.integers(0, 200000), st.integers(1, 200000), st.sampled_from([2, 4]))
+def test_py2round_matches_oracle_on_ratios(a, b, nd):
+    x = 1.0 * a / b
+    assert rows.py2round(x, nd) == py2compat.py2round(x, nd)
+
+
+@pytest.mark.parametrize("x,nd,want", [(0.03125, 4, 0.0313), (0.00005, 4, 0.0001), (2.675, 2, 2.67), (0.125, 2, 0.13),
+                                        (1.0, 4, 1.0), (0.0, 2, 0.0), (10892.584999999999, 2, 10892.58)])
+def test_py2round_cases(x, nd, want):
+    assert rows.py2round(x, nd) == want == py2compat.py2round(x, nd)
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.floats(min_value=0.0, max_value=1e6, allow_nan=False))
+def test_py2str_matches_oracle(x):
+    assert rows.py2str(x) == py2compat.py2str(x)
+    assert rows.py2str(round(x, 4)) == py2compat.py2str(round(x, 4))
+
+
+def test_convert_to_vcf():
+    for origRef, origAlt in (("A", "C"), ("G", "DEL"), ("T", "INS|T|TAC"), ("C", "DEL|CAG|C"), ("A", "N"), ("A", "XYZ")):
+        assert rows.convert_to_vcf(origRef, origAlt) == orc.convert_to_vcf(origRef, origAlt)
+    assert rows.convert_to_vcf("T", "INS|T|TAC") == ("T", "TAC", "INDEL")
+    assert rows.convert_to_vcf("G", "DEL") == ("G", "DEL", "SDEL")
+
+
+def test_hp_lowcomp_matches_oracle():
+    rng = random.Random(3)
+    seq = "".join(rng.choice("ACGT") for _ in range(300)) + "A" * 12 + "".join(rng.choice("ACGT") for _ in range(100)) + \
+        "AT" * 15 + "".join(rng.choice("ACGT") for _ in range(200))
+    ref = orc.DictFasta({"c": seq})
+    hits = set()
+    for pos in range(1, len(seq) + 1, 3):
+        for (r, a) in (("A", "C"), ("A", "ATT"), ("ACG", "A")):
+            got = rows.is_hp_or_low_comp("c", str(pos), 8, r, a, ref)
+            assert got == orc.is_hp_or_low_comp("c", str(pos), 8, r, a, ref)
+            hits.add(got)
+    assert (True, False) in hits or (True, True) in hits
+    assert any(h[1] for h in hits)
+
+
+# ---------------------------------------------------------------------------------------------- targets / fasta / SoA
+def test_loc_list_and_build_loci(tmp_path):
+    lines = ["track name=x\n", "chr2\t10\t14\textra\n", "chr1\t5\t8\n", "chr2\t12\t16\n", "chr1\t7\t7\n"]
+    ivs = targets.intervals_from_bed_lines(lines)
+    assert ivs == [("chr2", 10, 14), ("chr1", 5, 8), ("chr2", 12, 16), ("chr1", 7, 7)]
+    assert targets.loc_list(ivs) == orc.loci_from_bed(lines)
+    ref = SparseRef({"chr1": 100, "chr2": 100})
+    ref.add_window("chr1", 0, np.frombuffer(b"ACGTACGTACGTACGT", dtype=np.uint8))
+    loci, order = targets.build_loci(ivs, ["chr1", "chr2"], ref)
+    assert loci.n == 3 + 6 and len(order) == 4 + 3 + 4
+    keys = (loci.ref_id.astype(np.int64) << 32) | loci.pos0
+    assert np.all(np.diff(keys) > 0)
+    ll = targets.loc_list(ivs)
+    for k, (c, p) in enumerate(ll):
+        i = order[k]
+        assert ["chr1", "chr2"][loci.ref_id[i]] == c and loci.pos0[i] + 1 == int(p)
+    assert bytes(loci.ref_base[:3]) == b"CGT" and bytes(loci.ref_base[3:]) == b"NNNNNN"
+
+
+def test_fasta_reader(tmp_path):
+    p = tmp_path / "r.fa"
+    p.write_text(">c1 desc\nACGTAC\nGTACGT\nAC\n>c2\nTTTT\n")
+    fa = FastaFile(str(p))
+    assert fa.get_reference_length("c1") == 14 and fa.get_reference_length("c2") == 4
+    full = "ACGTACGTACGTAC"
+    for s in range(14):
+        for e in range(s, 18):
+            assert fa.fetch("c1", s, e) == full[s:min(e, 14)]
+    assert fa.fetch("c2", 1, 3) == "TT"
+    with pytest.raises(ValueError):
+        fa.fetch("c1", -1, 3)
+    # with a .fai on disk
+    (tmp_path / "r.fa.fai").write_text("c1\t14\t9\t6\t7\nc2\t4\t30\t4\t5\n")
+    fb = FastaFile(str(p))
+    assert fb.fetch("c1", 5, 13) == full[5:13] and fb.fetch("c2", 0, 99) == "TTTT"
+
+
+def test_soa_roundtrip_and_select():
+    spec = SynthSpec(umis_per_locus=12, rpb=2.0, snv_every=20, snv_vaf=0.3, indel_every=25, indel_vaf=0.3, softclip_frac=0.3)
+    s, refs, _ = make_panel([("chr1", 300, 340), ("chr2", 100, 120)], spec, seed=4)
+    recs = soa.soa_to_records(s, orc.Read)
+    s2 = soa.records_to_soa(recs, s.chroms)
+    for f in ("ref_id", "pos", "flag", "mapq", "nm", "l_seq", "seq_off", "qual_off", "cigar_off", "n_cigar", "umi", "seq", "qual", "cigar"):
+        assert np.array_equal(getattr(s, f), getattr(s2, f)), f
+    # frag ids are renumbered by first appearance: same partition
+    assert len(set(zip(s.frag_id.tolist(), s2.frag_id.tolist()))) == len(set(s.frag_id.tolist()))
+    idx = np.arange(0, s.n, 3)
+    sub = s.select(idx)
+    r_sub = soa.soa_to_records(sub, orc.Read)
+    assert [r[2:] for r in r_sub] == [recs[i][2:] for i in idx]
+    assert np.array_equal(s.ref_end()[idx], sub.ref_end())
+    assert all(orc.reference_end(r) == e for r, e in zip(recs, s.ref_end()))
+
+
+def test_umi_code_injective():
+    tab = {}
+    codes = {}
+    for bc in ["", "A", "AA", "C", "ACGT", "TTTT", "ACGTN", "A" * 31, "A" * 32, "ACGTACGTACGTACGTACGTACGTACGTACGTACGT", "acgt"]:
+        c = soa.umi_code(bc, tab)
+        assert c not in codes.values() or codes.get(bc) == c
+        codes[bc] = c
+    assert soa.umi_string(codes["ACGT"]) == "ACGT" and soa.umi_string(codes["A" * 31]) == "A" * 31
+    assert soa.umi_code("ACGTN", tab) == codes["ACGTN"]
+
+
+def test_umikeep_layout():
+    k = UmiKeep({7: [5, 3, 9], 2: [8]})
+    assert k.locus.tolist() == [2, 7] and k.off.tolist() == [0, 1, 4] and k.umi.tolist() == [8, 3, 5, 9]
+    assert VcParams(mtDepth=3612, rpb=8.6).ds == 7224 and VcParams(mtDepth=10, rpb=1.0, maxMT=7).ds == 7
+
+
+# ---------------------------------------------------------------------------------------------- repeats / writers
+def _rand_bed(rng, chroms, n, lo, hi, names=None):
+    out = []
+    for _ in range(n):
+        c = rng.choice(chroms)
+        s = rng.randrange(lo, hi)
+        e = s + rng.randrange(1, 40)
+        out.append((c, str(s), str(e)) + ((rng.choice(names),) if names else ()))
+    return out
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_repeat_filters_match_oracle(seed):
+    rng = random.Random(seed)
+    chroms = ["chr1", "chr2", "1"]
+    target = sorted(_rand_bed(rng, chroms[:2], 12, 0, 600), key=lambda r: (r[0], int(r[1])))
+    trf = sorted(_rand_bed(rng, chroms, 25, 0, 600), key=lambda r: (r[0], int(r[1])))
+    rm = sorted(_rand_bed(rng, chroms, 25, 0, 600, ["Simple_repeat", "Low_complexity", "Satellite", "L1"]), key=lambda r: (r[0], int(r[1])))
+    out_rows = []
+    for (c, s, e) in target:
+        for p in range(int(s), int(e)):
+            f = [c, str(p + 1), "A", rng.choice(["C", "DEL", "ACT"]), "SNP"] + ["1"] * 5 + \
+                [orc.py2str(orc.py2round(rng.random() * 12, 2))] + ["1"] * 3 + ["0.5"] + ["0"] * 29 + [rng.choice([";", ";LSM;", ";LM;LSM;"])]
+            out_rows.append("\t".join(f))
+    out_rows.append("\t".join(["chr1", "9", "G"] + [""] * 41 + ["Zero_Coverage"]))
+    trf_r, rm_r = repeats.build_repeat_regions(target, trf, rm)
+    got = repeats.apply_repeat_filters(out_rows, trf_r, rm_r)
+    want = orc.repeat_filter_rows(out_rows, target, trf, rm)
+    assert got == want
+    tags = {t for r in got for t in r.split("\t")[-1].split(";")}
+    assert "RepT" in tags and ({"RepS", "LowC", "SL", "Other_Repeat"} & tags)
+    assert got[-1].endswith("Zero_Coverage")
+
+
+def test_bed_ops():
+    rows_ = [("c", "1", "5", "x"), ("c", "5", "9", "y"), ("c", "20", "30", "x"), ("c", "25", "27", "x"), ("d", "0", "3", "z")]
+    assert repeats.bed_merge(rows_) == [("c", 1, 9), ("c", 20, 30), ("d", 0, 3)]                    # book-ended features merge
+    assert repeats.bed_merge(rows_, True) == [("c", 1, 9, "x,y"), ("c", 20, 30, "x"), ("d", 0, 3, "z")]
+    assert repeats.bed_intersect([("c", 0, 25, "k")], [("c", 1, 9), ("c", 20, 30)]) == [("c", 1, 9, "k"), ("c", 20, 25, "k")]
+    assert repeats.bed_sort([("d", 0, 3), ("c", 20, 30), ("c", 1, 9)]) == [("c", 1, 9), ("c", 20, 30), ("d", 0, 3)]
+
+
+def test_writers_regenerate_golden_files(tmp_path):
+    with open(os.path.join(GOLD, "example.smCounter.all.txt")) as fh:
+        body = fh.read().split("\n")[1:-1]
+    thr = writers.write_outputs(body, str(tmp_path / "example"), 3612, 0)
+    assert thr == 58 == writers.pi_threshold(3612) and writers.pi_threshold(3612, 40) == 40
+    for ext in ("all.txt", "cut.txt", "cut.vcf"):
+        got = (tmp_path / ("example.smCounter." + ext)).read_text()
+        want = open(os.path.join(GOLD, "example.smCounter." + ext)).read()
+        if ext == "cut.vcf":        # the sample column is named after outPrefix (a path here)
+            got = got.replace(str(tmp_path / "example"), "example")
+        assert got == want, ext
+    assert writers.vcf_header("s1") == orc.vcf_header("s1")
+    # genotype hack branches (smCounter.py:868-882)
+    base = body[299].split("\t")
+    for alt, vmf, chrom, gt, ad in (("C,T", "0.5", "chr1", "1/2", ",1"), ("C", "0.97", "chr1", "1/1", ""), ("C", "0.5", "chrY", "1", ""),
+                                    ("C", "0.5", "chr1", "0/1", "")):
+        f = list(base)
+        f[0], f[3], f[10], f[14] = chrom, alt, "99.0", vmf
+        vcf, short = writers.called_lines(f, 58)
+        assert vcf.rstrip("\n").split("\t")[-1].startswith(gt + ":") and short.split("\t")[3] == alt
+        assert vcf.rstrip("\n").split("\t")[-1].split(":")[1].endswith(f[13] + ad)
+    f = list(base); f[3] = "DEL"; f[10] = "99.0"
+    assert writers.called_lines(f, 58) is None
+
+
+# ---------------------------------------------------------------------------------------------- down-sampling emulation
+def test_downsample_emulation_matches_oracle_restatement():
+    assert downsample.py2_string_hash("a") == 12416037344 == py2compat.py2hash("a")
+    rng = random.Random(11)
+    for n, k in ((30, 12), (300, 120), (2000, 1500), (5000, 600)):
+        bcs = ["".join(rng.choice("ACGT") for _ in range(12)) for _ in range(n)]
+        bcs = list(dict.fromkeys(bcs))
+        for s in bcs[:50]:
+            assert downsample.py2_string_hash(s) == py2compat.py2hash(s)
+        assert downsample.py2_dict_key_order(bcs) == py2compat.py2_dict_order(bcs)
+        pop = downsample.py2_dict_key_order(bcs)
+        assert downsample.py2_seeded_sample("41245237", pop, k) == py2compat.py2_sample("41245237", pop, k)
+    assert downsample.py2_dict_key_order(["A", "T", "G", "C", "DEL", "N"]) == ["A", "C", "G", "N", "DEL", "T"]
+
+
+# ---------------------------------------------------------------------------------------------- sharding
+def test_shard_plan_covers_everything_and_balances():
+    spec = SynthSpec(umis_per_locus=10, rpb=2.0, depth_sigma=0.8)
+    ivs = [("chr1", 1000 + 400 * i, 1000 + 400 * i + 30 + 7 * (i % 5)) for i in range(12)] + [("chr2", 500, 520), ("chr2", 510, 530)]
+    s, refs, _ = make_panel(ivs, spec, seed=9)
+    w = shard.estimate_interval_events(s, ivs, s.chroms)
+    assert w.shape == (len(ivs),) and (w > 0).all()
+    # brute force check of one weight
+    ends = s.ref_end()
+    c, a, b = ivs[3]
+    m = (s.ref_id == s.chroms.index(c))
+    ov = np.minimum(ends[m], b) - np.maximum(s.pos[m].astype(np.int64), a)
+    assert w[3] == ov[ov > 0].sum()
+    for n in (1, 2, 3, 8):
+        plan = shard.plan_shards(s, ivs, s.chroms, n)
+        assert len(plan) == n
+        allk = sorted(k for idxs, _ in plan for k in idxs)
+        assert allk == list(range(len(ivs)))
+        assert all(idxs == sorted(idxs) for idxs, _ in plan)
+        if n == 2:
+            loads = [sum(w[k] for k in idxs) for idxs, _ in plan]
+            assert max(loads) / sum(loads) < 0.62
+    plan = shard.plan_shards(s, ivs, s.chroms, 3)
+    fake = [["%d:%d" % (k, j) for k in idxs for j in range(ivs[k][2] - ivs[k][1])] for idxs, _ in plan]
+    merged = shard.interleave_rows(plan, ivs, fake)
+    assert merged == ["%d:%d" % (k, j) for k in range(len(ivs)) for j in range(ivs[k][2] - ivs[k][1])]
+    idx = shard.reads_for_intervals(s, [ivs[0], ivs[12]], s.chroms)
+    assert len(idx) and np.all(np.diff(idx) > 0)
+    for i in range(s.n):
+        touches = any(s.chroms[s.ref_id[i]] == c and s.pos[i] < b and ends[i] > a for (c, a, b) in (ivs[0], ivs[12]))
+        assert touches == (i in set(idx.tolist()))
