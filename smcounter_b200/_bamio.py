@@ -1,0 +1,101 @@
+"""ctypes binding of libsmc_bamio.so (include/smc_bamio.h): threaded BGZF inflate + BAM record walk in C++."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .soa import ReadsSoA, umi_string
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsmc_bamio.so")
+EXPORTS = ("smc_bam_open", "smc_bam_close", "smc_bam_last_error", "smc_bam_n_refs", "smc_bam_ref_name", "smc_bam_ref_length",
+           "smc_bam_decode", "smc_bam_dict_umi")
+_vp = C.c_void_p
+
+
+class smc_bam_reads(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("ref_id", _vp), ("pos", _vp), ("flag", _vp), ("mapq", _vp), ("nm", _vp), ("l_seq", _vp),
+                ("seq_off", _vp), ("qual_off", _vp), ("cigar_off", _vp), ("n_cigar", _vp), ("umi", _vp), ("frag_id", _vp),
+                ("seq", _vp), ("seq_bytes", C.c_int64), ("qual", _vp), ("qual_bytes", C.c_int64), ("cigar", _vp),
+                ("n_cigar_words", C.c_int64), ("n_dict_umis", C.c_int64)]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libsmc_bamio.so is not built (%s); run `python -m smcounter_b200.build`" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.smc_bam_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(_vp)]
+    lib.smc_bam_open.restype = C.c_int
+    lib.smc_bam_close.argtypes = [_vp]
+    lib.smc_bam_close.restype = None
+    lib.smc_bam_last_error.argtypes = [_vp]
+    lib.smc_bam_last_error.restype = C.c_char_p
+    lib.smc_bam_n_refs.argtypes = [_vp]
+    lib.smc_bam_n_refs.restype = C.c_int
+    lib.smc_bam_ref_name.argtypes = [_vp, C.c_int]
+    lib.smc_bam_ref_name.restype = C.c_char_p
+    lib.smc_bam_ref_length.argtypes = [_vp, C.c_int]
+    lib.smc_bam_ref_length.restype = C.c_int64
+    lib.smc_bam_decode.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, C.POINTER(smc_bam_reads)]
+    lib.smc_bam_decode.restype = C.c_int
+    lib.smc_bam_dict_umi.argtypes = [_vp, C.c_int64]
+    lib.smc_bam_dict_umi.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def _arr(ptr, n, dtype):
+    n = int(n)
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+
+def read_bam_native(path: str, intervals=None, threads: int = 0) -> ReadsSoA:
+    lib = load()
+    h = _vp()
+    rc = lib.smc_bam_open(os.fsencode(path), int(threads), C.byref(h))
+    if rc != 0:
+        raise ValueError(lib.smc_bam_last_error(None).decode())
+    try:
+        chroms = [lib.smc_bam_ref_name(h, i).decode() for i in range(lib.smc_bam_n_refs(h))]
+        cidx = {c: i for i, c in enumerate(chroms)}
+        ivs = [(cidx[c], s, e) for (c, s, e) in (intervals or ()) if c in cidx and e > s]
+        iv_ref = np.asarray([v[0] for v in ivs], dtype=np.int32)
+        iv_s = np.asarray([v[1] for v in ivs], dtype=np.int32)
+        iv_e = np.asarray([v[2] for v in ivs], dtype=np.int32)
+        out = smc_bam_reads()
+        if intervals is not None and not ivs:
+            n_iv, args = 1, (np.asarray([-1], np.int32), np.zeros(1, np.int32), np.zeros(1, np.int32))   # nothing can match
+        else:
+            n_iv, args = len(ivs), (iv_ref, iv_s, iv_e)
+        rc = lib.smc_bam_decode(h, n_iv, args[0].ctypes.data, args[1].ctypes.data, args[2].ctypes.data, C.byref(out))
+        if rc != 0:
+            raise ValueError(lib.smc_bam_last_error(h).decode())
+        n = out.n_reads
+        umi = _arr(out.umi, n, np.uint64)
+        names = {}
+        for i in range(out.n_dict_umis):
+            names[(1 << 63) | i] = lib.smc_bam_dict_umi(h, i).decode()
+        for code in np.unique(umi):
+            code = int(code)
+            if not code >> 63:
+                names[code] = umi_string(code)
+        return ReadsSoA(
+            ref_id=_arr(out.ref_id, n, np.int32), pos=_arr(out.pos, n, np.int32), flag=_arr(out.flag, n, np.uint16),
+            mapq=_arr(out.mapq, n, np.uint8), nm=_arr(out.nm, n, np.int32), l_seq=_arr(out.l_seq, n, np.int32),
+            seq_off=_arr(out.seq_off, n, np.int64), qual_off=_arr(out.qual_off, n, np.int64), cigar_off=_arr(out.cigar_off, n, np.int64),
+            n_cigar=_arr(out.n_cigar, n, np.uint16), umi=umi, frag_id=_arr(out.frag_id, n, np.uint32),
+            seq=_arr(out.seq, out.seq_bytes, np.uint8), qual=_arr(out.qual, out.qual_bytes, np.uint8),
+            cigar=_arr(out.cigar, out.n_cigar_words, np.uint32), chroms=chroms, umi_names=names)
+    finally:
+        lib.smc_bam_close(h)

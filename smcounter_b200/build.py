@@ -22,7 +22,25 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+BAMIO_OUT = os.path.join(HERE, "libsmc_bamio.so")
+BAMIO_SRC = os.path.join(CSRC, "smc_bamio.cpp")
+BAMIO_HDR = os.path.join(HERE, "..", "include", "smc_bamio.h")
+
+
+def build_bamio(force: bool = False) -> str:
+    """Host-side BAM decoder (C++17, zlib, threads) -> libsmc_bamio.so."""
+    if not force and os.path.exists(BAMIO_OUT) and os.path.getmtime(BAMIO_OUT) >= max(os.path.getmtime(BAMIO_SRC), os.path.getmtime(BAMIO_HDR)):
+        return BAMIO_OUT
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", BAMIO_OUT, BAMIO_SRC, "-lz"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building libsmc_bamio.so")
+    return BAMIO_OUT
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    build_bamio(force)
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -1,0 +1,273 @@
+// libsmc_bamio.so -- BAM (BGZF) -> flat SoA read buffers (include/smc_bamio.h).  Host-side input decoding only.
+// Container format restated from the SAM/BAM specification (SAMv1 sections 4.1-4.2); zlib does the inflating.
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/smc_bamio.h"
+
+namespace {
+thread_local std::string g_open_error;
+
+inline uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline int32_t rdi32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; }
+
+struct Block { size_t coff, clen; size_t uoff; uint32_t isize; };
+}  // namespace
+
+struct smc_bam {
+    std::string err;
+    std::vector<uint8_t> raw;                 // inflated stream
+    std::vector<std::string> ref_names;
+    std::vector<int64_t> ref_lens;
+    size_t first_record = 0;
+    // decoded buffers
+    std::vector<int32_t> ref_id, pos, nm, l_seq;
+    std::vector<uint16_t> flag, n_cigar;
+    std::vector<uint8_t> mapq, seq, qual;
+    std::vector<int64_t> seq_off, qual_off, cigar_off;
+    std::vector<uint64_t> umi;
+    std::vector<uint32_t> frag_id, cigar;
+    std::vector<std::string> dict_umis;
+};
+
+static int inflate_all(const std::vector<uint8_t>& file, int threads, std::vector<uint8_t>& out, std::string& err) {
+    std::vector<Block> blocks;
+    size_t off = 0, uoff = 0;
+    const size_t n = file.size();
+    while (off < n) {
+        if (off + 18 > n || file[off] != 0x1f || file[off + 1] != 0x8b || file[off + 2] != 8 || !(file[off + 3] & 4)) {
+            err = "not a BGZF block at offset " + std::to_string(off); return -1;
+        }
+        const uint16_t xlen = rd16(&file[off + 10]);
+        size_t p = off + 12, end = p + xlen;
+        int64_t bsize = -1;
+        while (p + 4 <= end && end <= n) {
+            const uint16_t slen = rd16(&file[p + 2]);
+            if (file[p] == 66 && file[p + 1] == 67 && slen == 2) bsize = rd16(&file[p + 4]);
+            p += 4 + slen;
+        }
+        if (bsize < 0 || off + (size_t)bsize + 1 > n) { err = "truncated or malformed BGZF block at offset " + std::to_string(off); return -1; }
+        Block b;
+        b.coff = off + 12 + xlen;
+        b.clen = (size_t)bsize + 1 - 12 - xlen - 8;
+        b.isize = rd32(&file[off + bsize + 1 - 4]);
+        b.uoff = uoff;
+        uoff += b.isize;
+        blocks.push_back(b);
+        off += (size_t)bsize + 1;
+    }
+    out.resize(uoff);
+    std::atomic<size_t> next(0);
+    std::atomic<int> bad(0);
+    auto work = [&]() {
+        z_stream zs;
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= blocks.size() || bad.load()) break;
+            const Block& b = blocks[i];
+            if (b.isize == 0) continue;
+            memset(&zs, 0, sizeof(zs));
+            if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; break; }
+            zs.next_in = const_cast<Bytef*>(&file[b.coff]); zs.avail_in = (uInt)b.clen;
+            zs.next_out = &out[b.uoff]; zs.avail_out = b.isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = 1; break; }
+        }
+    };
+    const int nt = std::max(1, std::min<int>(threads, (int)blocks.size()));
+    std::vector<std::thread> ts;
+    for (int t = 1; t < nt; ++t) ts.emplace_back(work);
+    work();
+    for (auto& t : ts) t.join();
+    if (bad.load()) { err = "zlib inflate failed on a BGZF block"; return -1; }
+    return 0;
+}
+
+extern "C" int smc_bam_open(const char* path, int threads, smc_bam** out) {
+    if (!path || !out) { g_open_error = "smc_bam_open: null argument"; return -2; }
+    FILE* fh = fopen(path, "rb");
+    if (!fh) { g_open_error = std::string("smc_bam_open: cannot open ") + path; return -1; }
+    std::vector<uint8_t> file;
+    fseek(fh, 0, SEEK_END);
+    const long sz = ftell(fh);
+    fseek(fh, 0, SEEK_SET);
+    file.resize(sz > 0 ? (size_t)sz : 0);
+    const size_t got = file.empty() ? 0 : fread(file.data(), 1, file.size(), fh);
+    fclose(fh);
+    if (got != file.size()) { g_open_error = "smc_bam_open: short read"; return -1; }
+    smc_bam* h = new smc_bam();
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (inflate_all(file, threads, h->raw, g_open_error) != 0) { delete h; return -1; }
+    const std::vector<uint8_t>& r = h->raw;
+    if (r.size() < 12 || memcmp(r.data(), "BAM\1", 4) != 0) { g_open_error = "not a BAM file (bad magic)"; delete h; return -1; }
+    size_t p = 8 + (size_t)rdi32(&r[4]);
+    if (p + 4 > r.size()) { g_open_error = "truncated BAM header"; delete h; return -1; }
+    const int32_t n_ref = rdi32(&r[p]);
+    p += 4;
+    for (int32_t i = 0; i < n_ref; ++i) {
+        if (p + 4 > r.size()) { g_open_error = "truncated BAM reference list"; delete h; return -1; }
+        const int32_t l_name = rdi32(&r[p]);
+        if (l_name < 1 || p + 8 + (size_t)l_name > r.size()) { g_open_error = "truncated BAM reference list"; delete h; return -1; }
+        h->ref_names.emplace_back(reinterpret_cast<const char*>(&r[p + 4]), (size_t)l_name - 1);
+        h->ref_lens.push_back(rdi32(&r[p + 4 + l_name]));
+        p += 8 + (size_t)l_name;
+    }
+    h->first_record = p;
+    *out = h;
+    return 0;
+}
+
+extern "C" void smc_bam_close(smc_bam* h) { delete h; }
+extern "C" const char* smc_bam_last_error(smc_bam* h) { return h ? h->err.c_str() : g_open_error.c_str(); }
+extern "C" int smc_bam_n_refs(smc_bam* h) { return h ? (int)h->ref_names.size() : 0; }
+extern "C" const char* smc_bam_ref_name(smc_bam* h, int i) { return (h && i >= 0 && i < (int)h->ref_names.size()) ? h->ref_names[i].c_str() : ""; }
+extern "C" int64_t smc_bam_ref_length(smc_bam* h, int i) { return (h && i >= 0 && i < (int)h->ref_lens.size()) ? h->ref_lens[i] : -1; }
+extern "C" const char* smc_bam_dict_umi(smc_bam* h, int64_t i) { return (h && i >= 0 && i < (int64_t)h->dict_umis.size()) ? h->dict_umis[(size_t)i].c_str() : ""; }
+
+// value of the first NM tag in [p, end), 0 when absent (smCounter.py:329-334)
+static int32_t first_nm(const uint8_t* p, const uint8_t* end) {
+    while (p + 3 <= end) {
+        const uint8_t t0 = p[0], t1 = p[1], ty = p[2];
+        p += 3;
+        size_t sz = 0;
+        switch (ty) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'Z': case 'H': { const void* q = memchr(p, 0, (size_t)(end - p)); if (!q) return 0; p = (const uint8_t*)q + 1; continue; }
+            case 'B': {
+                if (p + 5 > end) return 0;
+                const uint8_t sub = p[0];
+                const int32_t cnt = rdi32(p + 1);
+                const size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+                p += 5 + (size_t)cnt * es;
+                continue;
+            }
+            default: return 0;
+        }
+        if (p + sz > end) return 0;
+        if (t0 == 'N' && t1 == 'M' && ty != 'A' && ty != 'f') {
+            switch (ty) {
+                case 'c': return (int8_t)p[0];
+                case 'C': return p[0];
+                case 's': { int16_t v; memcpy(&v, p, 2); return v; }
+                case 'S': return rd16(p);
+                case 'i': return rdi32(p);
+                default:  return (int32_t)rd32(p);
+            }
+        }
+        p += sz;
+    }
+    return 0;
+}
+
+extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, const int32_t* iv_start, const int32_t* iv_end,
+                              smc_bam_reads* out) {
+    if (!h || !out || (n_iv > 0 && (!iv_ref || !iv_start || !iv_end))) { if (h) h->err = "smc_bam_decode: null argument"; return -2; }
+    // per reference: interval starts (sorted) and the running maximum of their ends
+    const size_t nref = h->ref_names.size();
+    std::vector<std::vector<std::pair<int64_t, int64_t>>> iv(nref);
+    for (int64_t k = 0; k < n_iv; ++k)
+        if (iv_ref[k] >= 0 && (size_t)iv_ref[k] < nref && iv_end[k] > iv_start[k]) iv[iv_ref[k]].push_back({iv_start[k], iv_end[k]});
+    for (auto& v : iv) {
+        std::sort(v.begin(), v.end());
+        int64_t mx = INT64_MIN;
+        for (auto& pr : v) { mx = std::max(mx, pr.second); pr.second = mx; }
+    }
+    auto touches = [&](int32_t rid, int64_t s, int64_t e) -> bool {
+        const auto& v = iv[rid];
+        // intervals with start < e
+        size_t lo = 0, hi = v.size();
+        while (lo < hi) { size_t mid = (lo + hi) / 2; if (v[mid].first < e) lo = mid + 1; else hi = mid; }
+        return lo > 0 && v[lo - 1].second > s;
+    };
+    h->ref_id.clear(); h->pos.clear(); h->nm.clear(); h->l_seq.clear(); h->flag.clear(); h->n_cigar.clear(); h->mapq.clear();
+    h->seq.clear(); h->qual.clear(); h->seq_off.clear(); h->qual_off.clear(); h->cigar_off.clear(); h->umi.clear(); h->frag_id.clear();
+    h->cigar.clear(); h->dict_umis.clear();
+    std::unordered_map<std::string, uint64_t> umi_dict;
+    std::unordered_map<std::string, uint32_t> frag_dict;
+    frag_dict.reserve(1 << 20);
+    const std::vector<uint8_t>& r = h->raw;
+    size_t p = h->first_record;
+    std::string fkey;
+    while (p + 4 <= r.size()) {
+        const int32_t bs = rdi32(&r[p]);
+        if (bs < 32 || p + 4 + (size_t)bs > r.size()) { h->err = "truncated BAM record at offset " + std::to_string(p); return -1; }
+        const uint8_t* b = &r[p + 4];
+        const uint8_t* rec_end = b + bs;
+        p += 4 + (size_t)bs;
+        const int32_t refID = rdi32(b), pos = rdi32(b + 4);
+        const uint8_t l_rn = b[8], mapq = b[9];
+        const uint16_t n_cig = rd16(b + 12), flag = rd16(b + 14);
+        const int32_t l_seq = rdi32(b + 16);
+        const char* qname = reinterpret_cast<const char*>(b + 32);
+        const uint8_t* cig = b + 32 + l_rn;
+        const uint8_t* sq = cig + 4 * (size_t)n_cig;
+        const size_t sb = ((size_t)l_seq + 1) / 2;
+        const uint8_t* ql = sq + sb;
+        if (l_seq < 0 || ql + l_seq > rec_end) { h->err = "malformed BAM record (field lengths exceed block_size)"; return -1; }
+        if ((flag & 0x4) || refID < 0 || (size_t)refID >= nref) continue;
+        if (n_iv > 0) {
+            int64_t reflen = 0;
+            for (uint16_t k = 0; k < n_cig; ++k) {
+                const uint32_t cw = rd32(cig + 4 * k), op = cw & 15u;
+                if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) reflen += cw >> 4;
+            }
+            if (!touches(refID, pos, (int64_t)pos + reflen)) continue;
+        }
+        // identity: BC = parts[-2], readid = ':'.join(parts[:-2])   (smCounter.py:319-325)
+        const size_t qn = l_rn ? (size_t)l_rn - 1 : 0;
+        long c1 = -1, c2 = -1;                  // last and second-to-last ':'
+        for (long i = (long)qn - 1; i >= 0; --i)
+            if (qname[i] == ':') { if (c1 < 0) c1 = i; else { c2 = i; break; } }
+        std::string bc, readid;
+        if (c1 < 0) { bc = ""; readid = ""; }                                   // fewer than 2 fields: parts[-2] would raise in Python
+        else if (c2 < 0) { bc.assign(qname, (size_t)c1); readid = ""; }
+        else { bc.assign(qname + c2 + 1, (size_t)(c1 - c2 - 1)); readid.assign(qname, (size_t)c2); }
+        uint64_t code = 1;
+        bool packable = bc.size() <= 31;
+        if (packable)
+            for (char ch : bc) {
+                const int k = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : -1;
+                if (k < 0) { packable = false; break; }
+                code = (code << 2) | (uint64_t)k;
+            }
+        if (!packable) {
+            auto it = umi_dict.find(bc);
+            if (it == umi_dict.end()) {
+                code = (1ull << 63) | (uint64_t)umi_dict.size();
+                umi_dict.emplace(bc, code);
+                h->dict_umis.push_back(bc);
+            } else code = it->second;
+        }
+        fkey.assign(bc); fkey.push_back('\x1f'); fkey.append(readid);
+        auto fit = frag_dict.find(fkey);
+        uint32_t fid;
+        if (fit == frag_dict.end()) { fid = (uint32_t)frag_dict.size(); frag_dict.emplace(fkey, fid); } else fid = fit->second;
+        h->ref_id.push_back(refID); h->pos.push_back(pos); h->flag.push_back(flag); h->mapq.push_back(mapq);
+        h->nm.push_back(first_nm(ql + l_seq, rec_end)); h->l_seq.push_back(l_seq); h->n_cigar.push_back(n_cig);
+        h->seq_off.push_back((int64_t)h->seq.size()); h->qual_off.push_back((int64_t)h->qual.size());
+        h->cigar_off.push_back((int64_t)h->cigar.size());
+        h->umi.push_back(code); h->frag_id.push_back(fid);
+        h->seq.insert(h->seq.end(), sq, sq + sb);
+        h->qual.insert(h->qual.end(), ql, ql + l_seq);
+        for (uint16_t k = 0; k < n_cig; ++k) h->cigar.push_back(rd32(cig + 4 * k));
+    }
+    out->n_reads = (int64_t)h->ref_id.size();
+    out->ref_id = h->ref_id.data(); out->pos = h->pos.data(); out->flag = h->flag.data(); out->mapq = h->mapq.data();
+    out->nm = h->nm.data(); out->l_seq = h->l_seq.data(); out->seq_off = h->seq_off.data(); out->qual_off = h->qual_off.data();
+    out->cigar_off = h->cigar_off.data(); out->n_cigar = h->n_cigar.data(); out->umi = h->umi.data(); out->frag_id = h->frag_id.data();
+    out->seq = h->seq.data(); out->seq_bytes = (int64_t)h->seq.size(); out->qual = h->qual.data(); out->qual_bytes = (int64_t)h->qual.size();
+    out->cigar = h->cigar.data(); out->n_cigar_words = (int64_t)h->cigar.size(); out->n_dict_umis = (int64_t)h->dict_umis.size();
+    return 0;
+}

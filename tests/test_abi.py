@@ -100,3 +100,30 @@ def test_product_package_never_imports_the_oracle():
     code = "import sys; import smcounter_b200.smCounter, smcounter_b200.caller, smcounter_b200.rows; " \
            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'"
     subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
+
+
+def test_bamio_library_exports_and_layout(tmp_path):
+    """include/smc_bamio.h (host-side BAM decoder): every declared symbol is exported, struct layout matches ctypes."""
+    from smcounter_b200 import _bamio, build
+    build.build_bamio()
+    lib = _bamio.load()
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "smc_bamio.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(smc_bam_[a-z_]+)\s*\(", src)))
+    assert set(names) == set(_bamio.EXPORTS)
+    for n in names:
+        assert getattr(lib, n) is not None
+    cls = _bamio.smc_bam_reads
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "smc_bamio.h"', 'int main(void){',
+             'printf("size %zu\\n", sizeof(smc_bam_reads));']
+    for f, _ in cls._fields_:
+        lines.append('printf("%s %%zu\\n", offsetof(smc_bam_reads, %s));' % (f, f))
+    lines.append('return 0;}')
+    (tmp_path / "l.c").write_text("\n".join(lines))
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(tmp_path / "l"), str(tmp_path / "l.c")])
+    got = dict(l.split() for l in subprocess.check_output([str(tmp_path / "l")], text=True).splitlines())
+    assert int(got["size"]) == C.sizeof(cls)
+    for f, _ in cls._fields_:
+        assert int(got[f]) == getattr(cls, f).offset, f
+    h = C.c_void_p()
+    assert lib.smc_bam_open(str(tmp_path / "missing.bam").encode(), 1, C.byref(h)) != 0
+    assert b"cannot open" in lib.smc_bam_last_error(None)
