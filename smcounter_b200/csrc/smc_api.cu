@@ -224,8 +224,10 @@ extern "C" int smc_ctx_create(int device, const smc_params* params, smc_ctx** ou
     if ((e = ctx->d_pcrtab.ensure(pcr.size() * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     cudaMemcpy(ctx->d_bqtab.p, bq.data(), 256 * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(ctx->d_pcrtab.p, pcr.data(), pcr.size() * 8, cudaMemcpyHostToDevice);
-    if ((e = cudaFuncSetAttribute(k_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_BYTES)) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(k_pileup_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_BYTES)) != cudaSuccess)
         return fail("cudaFuncSetAttribute(k_pileup)", e);
+    if ((e = cudaFuncSetAttribute(k_pileup_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_BYTES)) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(k_pileup list)", e);
     if ((e = ctx->d_small.ensure(4096)) != cudaSuccess) return fail("cudaMalloc", e);
     *out = ctx;
     return SMC_OK;
@@ -468,7 +470,7 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
             fill_k3args(ctx, A, n_tiles);
             const int64_t max_units = (int64_t)n_tiles + NE / ctx->chunk + 1;
             CK(cudaEventRecord(ctx->ev[8], ctx->st));
-            LAUNCH(k_pileup, nblk(max_units, K3_WARPS), K3_WARPS * 32, K3_SMEM_BYTES, A);
+            LAUNCH(k_pileup_t<false>, nblk(max_units, K3_WARPS), K3_WARPS * 32, K3_SMEM_BYTES, A);
             CK(cudaEventRecord(ctx->ev[9], ctx->st));
         }
         uint32_t h[3];
@@ -649,7 +651,7 @@ extern "C" int smc_list_barcodes(smc_ctx* ctx, int64_t n, const int64_t* locus, 
     A.list_off = ctx->d_list_off.as<int64_t>(); A.list_umi = ctx->d_list_umi.as<uint64_t>();
     A.list_first = ctx->d_list_first.as<uint32_t>(); A.list_cap = total;
     const int64_t max_units = (int64_t)ctx->n_tiles + ctx->n_tile_events / ctx->chunk + 1;
-    LAUNCH(k_pileup, nblk(max_units, K3_WARPS), K3_WARPS * 32, K3_SMEM_BYTES, A);
+    LAUNCH(k_pileup_t<true>, nblk(max_units, K3_WARPS), K3_WARPS * 32, K3_SMEM_BYTES, A);
     CK(cudaMemcpyAsync(umi_out, ctx->d_list_umi.p, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(first_read_out, ctx->d_list_first.p, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));

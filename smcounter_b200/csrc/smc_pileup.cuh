@@ -98,7 +98,20 @@ k_expand(const ReadRec* __restrict__ recs, const uint32_t* __restrict__ ev_off, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K3: tile pileup
+// K3: tile pileup (v3)
+//
+// A warp owns one unit = a run of <= `chunk` tile events of one 32-locus tile, cut at barcode boundaries.  It works in
+// batches of 32 reads:
+//   stage   : 32 ReadRec (64 B each, gathered through ev_read[]) -> shared memory, 4 x 128-bit loads per lane;
+//   pass A  : "gather" -- for each staged read every lane computes the query position of ITS locus and loads the base
+//             nibble and the quality.  The 32 reads are independent, so the loads are issued 8 reads at a time
+//             (16 loads in flight per lane) and their results are packed into 16-bit event codes in shared memory.
+//             This is where all the DRAM/L2 latency of the kernel is, and it is hidden by ILP instead of occupancy;
+//   pass B  : "reduce" -- the order-dependent state machine (fragment merge, per-barcode posterior, tallies) walks the
+//             codes.  The hot counters live in registers as 4 x 8-bit fields (A, C, T, G) per 32-bit word and are
+//             spilled to the 16-bit shared-memory counters every 224 events; those go to the global 32-bit
+//             accumulators every 49 152 events and at the end of the unit.
+// Reads with indels / hard clips / several aligned segments ("not simple") take the per-event CIGAR walk in pass B.
 // ------------------------------------------------------------------------------------------------------------
 #ifndef K3_WARPS
 #define K3_WARPS 4
@@ -108,8 +121,7 @@ k_expand(const ReadRec* __restrict__ recs, const uint32_t* __restrict__ ev_off, 
 #endif
 #define NF SMC_NFIXED
 #define NSLOT 7            // per-barcode allele slots: 5 fixed + 2 dynamic
-// Per-lane shared-memory counters of the fixed alleles, two 16-bit counters per word (flushed to the global 32-bit
-// accumulators before any of them can reach 65536):
+// Per-lane shared-memory counters of the fixed alleles, two 16-bit counters per word:
 enum { KW_ALLELE_FWD = 0,   // alleleCnt | forwardCnt << 16
        KW_R1,               // len(r1BcEndPos) | #<=20 << 16
        KW_R2,               // len(r2BcEndPos) | #<=20 << 16
@@ -117,15 +129,24 @@ enum { KW_ALLELE_FWD = 0,   // alleleCnt | forwardCnt << 16
        KW_PAIR,             // concordPairCnt | discordPairCnt << 16
        KW_MT,               // MTCnt | strongMTCnt << 16
        K3_NW };
-#define K3_FLUSH_EVERY 49152u      // tile events between counter flushes (each event adds at most 1 to a field)
-#define K3_STAGE_WORDS 512
+#define K3_FLUSH_EVERY 49152u      // tile events between shared -> global flushes (each event adds at most 1 to a field)
+#define K3_REG_FLUSH   224u        // tile events between register -> shared flushes (8-bit fields)
+#define K3_STAGE_WORDS 512                     // 32 ReadRec
+#define K3_CODE_WORDS  512                     // 32 x 32 event codes, 16 bit
 #define K3_FC_WORDS    (NF * K3_NW * 32)
-#define K3_LIMB_WORDS  (NF * 3 * 64)
+#define K3_LIMB_WORDS  (NF * 4 * 32)           // 128-bit fixed-point PI accumulator per fixed allele and lane
 #define K3_UCNT_WORDS  (NSLOT * 32)
 #define K3_UPROD_WORDS (NSLOT * 64)
-#define K3_UT_WORDS    (NSLOT * 64)
-#define K3_WARP_WORDS  (K3_STAGE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS + K3_UCNT_WORDS + K3_UPROD_WORDS + K3_UT_WORDS)
-#define K3_SMEM_BYTES  (K3_WARPS * K3_WARP_WORDS * 4)
+#define K3_WARP_WORDS  (K3_STAGE_WORDS + K3_CODE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS + K3_UCNT_WORDS + K3_UPROD_WORDS)
+#define K3_BQTAB_BYTES 2048                    // 256 doubles, shared by the block
+#define K3_SMEM_BYTES  (K3_BQTAB_BYTES + K3_WARPS * K3_WARP_WORDS * 4)
+
+// 16-bit event code written by pass A (simple reads only)
+#define EC_FIELD_SH 8u            // bits 8-9: A0 C1 T2 G3
+#define EC_COVERED  (1u << 10)
+#define EC_DYN      (1u << 11)    // base is not A/C/G/T (N / IUPAC): dynamic allele, the nibble is re-read in pass B
+#define EC_LE20     (1u << 12)    // distance to the barcode end <= 20 (R1: :434-441, R2: :443-452)
+#define EC_PLE      (1u << 13)    // R2 and distance to the primer end <= primerDist
 
 struct K3Args {
     const ReadRec* recs; const uint32_t* ev_read; const uint32_t* tile_off; const uint32_t* unit_off;
@@ -144,10 +165,12 @@ struct K3Args {
     const int32_t* list_idx; uint32_t* list_count; const int64_t* list_off; uint64_t* list_umi; uint32_t* list_first; int64_t list_cap;
 };
 
-// BAM nibble of A, C, G, T -> fixed slot (A0 C1 T3 G4), anything else -> -1
+// BAM nibble of A, C, G, T (1, 2, 4, 8) -> field A0 C1 T2 G3; fixed slot (A0 C1 T3 G4) = field + (field >> 1)
+__device__ __forceinline__ uint32_t nib_field(uint32_t nib) { return (0x20310u >> (2u * nib)) & 3u; }
+__device__ __forceinline__ bool nib_is_acgt(uint32_t nib) { return (0x0116u >> nib) & 1u; }
 __device__ __forceinline__ int nib_to_fixed(uint32_t nib) {
-    // nib 1,2,4,8 -> ffs 1,2,3,4 -> slots 0,1,4,3
-    return (__popc(nib) == 1) ? (int)((0x3410u >> (4 * (__ffs(nib) - 1))) & 15u) : -1;
+    const uint32_t f = nib_field(nib);
+    return nib_is_acgt(nib) ? (int)(f + (f >> 1)) : -1;
 }
 
 // open-addressing table of the non-ACGT/DEL alleles; arguments by value so that the kernel parameter block never has
@@ -175,17 +198,27 @@ __device__ __noinline__ uint32_t dyn_lookup(unsigned long long* dkey, uint32_t d
     return 0;
 }
 
-// split a non-negative double < 2^20 into three 44-bit limbs of a fixed-point number with LSB 2^-108
-__device__ __forceinline__ void pi_limbs(double l, unsigned long long& a0, unsigned long long& a1, unsigned long long& a2) {
-    unsigned long long bits = (unsigned long long)__double_as_longlong(l);
-    int e = (int)((bits >> 52) & 0x7ffull);
-    unsigned long long m = (bits & 0xFFFFFFFFFFFFFull) | (1ull << 52);
-    int sh = e - 967;                                   // value = m * 2^(e-1075) = (m << sh) * 2^-108
-    if (e == 0 || sh <= -53) { a0 = a1 = a2 = 0; return; }
-    unsigned long long lo, hi;
+// A non-negative double < 2^20 as a 128-bit fixed-point integer with LSB 2^-108 (exact: the terms are 0 or >= 2^-55).
+__device__ __forceinline__ void pi_fixed128(double l, unsigned long long& lo, unsigned long long& hi) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(l);
+    const int e = (int)((bits >> 52) & 0x7ffull);
+    const unsigned long long m = (bits & 0xFFFFFFFFFFFFFull) | (1ull << 52);
+    const int sh = e - 967;                             // value = m * 2^(e-1075) = (m << sh) * 2^-108
+    if (e == 0 || sh <= -53) { lo = hi = 0; return; }
     if (sh <= 0) { lo = m >> (-sh); hi = 0; }
     else if (sh < 64) { lo = m << sh; hi = m >> (64 - sh); }
     else { lo = 0; hi = m << (sh - 64); }
+}
+__device__ __forceinline__ void add128(unsigned long long& lo, unsigned long long& hi, unsigned long long alo, unsigned long long ahi) {
+    lo += alo; hi += ahi + (lo < alo ? 1ull : 0ull);
+}
+__device__ __forceinline__ void sub128(unsigned long long& lo, unsigned long long& hi, unsigned long long blo, unsigned long long bhi) {
+    const unsigned long long borrow = lo < blo ? 1ull : 0ull;
+    lo -= blo; hi -= bhi + borrow;
+}
+// 128-bit value -> three 44-bit carry-save limbs of the global accumulators (v = l0 + l1*2^44 + l2*2^88)
+__device__ __forceinline__ void split_limbs(unsigned long long lo, unsigned long long hi, unsigned long long& a0, unsigned long long& a1,
+                                            unsigned long long& a2) {
     const unsigned long long M44 = (1ull << 44) - 1ull;
     a0 = lo & M44;
     a1 = ((lo >> 44) | (hi << 20)) & M44;
@@ -196,6 +229,9 @@ struct LaneState {
     // locus-level
     int cvg, allFrag, allMT, usedFrag, nBC, usedMT, mt3, mt5, mt7, mt10;
     uint32_t keymask, status;
+    unsigned long long pad_lo, pad_hi;      // PI terms that go to all of A, C, G, T (single-allele barcodes, see umi_finalize)
+    // hot counters, 4 x 8-bit fields (A, C, T, G)
+    uint32_t r_allele, r_fwd, r_r1tot, r_r1le, r_r2tot, r_r2le;
     // barcode-level
     int n; uint32_t exist; double Q, rightP; uint32_t last_aid; uint32_t udyn0, udyn1; int ndyn;
     bool umi_seen, umi_bc; uint32_t first_read;     // BAM index of the barcode's first passing read at this locus
@@ -204,10 +240,9 @@ struct LaneState {
 };
 
 #define FCW(w, a)   fc[((a) * K3_NW + (w)) * 32 + lane]
-#define LIMB(a, j)  limb[((a) * 3 + (j)) * 32 + lane]
+#define LIMB(a)     limb[(a) * 32 + lane]
 #define UCNT(s)     ucnt[(s) * 32 + lane]
 #define UPROD(s)    uprod[(s) * 32 + lane]
-#define UT(s)       ut[(s) * 32 + lane]
 
 // counter update for an allele that may be dynamic: `word`/`add` address the packed shared-memory counter of a fixed
 // allele, c_lo / c_hi are the smc_out counter indices the low / high half stand for.
@@ -220,7 +255,29 @@ __device__ __forceinline__ void bump(const K3Args& A, int* fc, int lane, uint32_
     }
 }
 
-__device__ __forceinline__ void fragment_finalize(const K3Args& A, int lane, int* ucnt, double* uprod, LaneState& S) {
+// registers -> shared-memory counters
+__device__ __forceinline__ void flush_regs(int* fc, int lane, LaneState& S) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        const int a = f + (f >> 1);                                     // A0 C1 T3 G4
+        const uint32_t al = (S.r_allele >> (8 * f)) & 255u, fw = (S.r_fwd >> (8 * f)) & 255u;
+        const uint32_t t1 = (S.r_r1tot >> (8 * f)) & 255u, l1 = (S.r_r1le >> (8 * f)) & 255u;
+        const uint32_t t2 = (S.r_r2tot >> (8 * f)) & 255u, l2 = (S.r_r2le >> (8 * f)) & 255u;
+        if (al) FCW(KW_ALLELE_FWD, a) += (int)(al | (fw << 16));
+        if (t1) FCW(KW_R1, a) += (int)(t1 | (l1 << 16));
+        if (t2) FCW(KW_R2, a) += (int)(t2 | (l2 << 16));
+    }
+    S.r_allele = S.r_fwd = S.r_r1tot = S.r_r1le = S.r_r2tot = S.r_r2le = 0;
+}
+
+// first use of the per-barcode shared-memory arrays: a barcode that has shown a single allele so far keeps its state in
+// registers only (its product over fragments IS rightP, its count IS n)
+__device__ __forceinline__ void umi_materialize(int lane, int* ucnt, double* uprod, const LaneState& S) {
+    const int s0 = __ffs(S.exist) - 1;
+    UCNT(s0) = S.n; UPROD(s0) = S.rightP;
+}
+
+__device__ __forceinline__ void fragment_finalize(const K3Args& A, const double* bqtab_s, int lane, int* ucnt, double* uprod, LaneState& S) {
     if (S.frag_seen) { S.allFrag++; S.frag_seen = false; }
     if (!S.f_exists) return;
     S.f_exists = false;
@@ -234,28 +291,40 @@ __device__ __forceinline__ void fragment_finalize(const K3Args& A, int lane, int
         else if (S.ndyn == 1) { S.udyn1 = e; S.ndyn = 2; slot = 6; }
         else { S.status |= SMC_ST_UMI_OVERFLOW; slot = 5; }
     }
-    double p = S.f_paired ? __ldg(&A.bqtab[S.f_bq]) : 0.1;          // smCounter.py:65-68
-    double q1 = 1.0 - p;
-    if (!((S.exist >> slot) & 1u)) { S.exist |= 1u << slot; UCNT(slot) = 0; UPROD(slot) = S.Q; }
-    uint32_t m = S.exist;
-    while (m) {                                                      // :70-74
-        int s = __ffs(m) - 1; m &= m - 1;
-        UPROD(s) = __dmul_rn(UPROD(s), s == slot ? q1 : p);
+    const double p = S.f_paired ? bqtab_s[S.f_bq] : 0.1;             // smCounter.py:65-68
+    const double q1 = 1.0 - p;
+    const uint32_t bit = 1u << slot;
+    if (S.exist == 0) S.exist = bit;
+    else {
+        const bool multi = (S.exist & (S.exist - 1u)) != 0u;
+        if (multi || S.exist != bit) {
+            if (!multi) umi_materialize(lane, ucnt, uprod, S);
+            if (!(S.exist & bit)) { S.exist |= bit; UCNT(slot) = 0; UPROD(slot) = S.Q; }
+            uint32_t m = S.exist;
+            while (m) {                                                  // :70-74
+                int s = __ffs(m) - 1; m &= m - 1;
+                UPROD(s) = __dmul_rn(UPROD(s), s == slot ? q1 : p);
+            }
+            UCNT(slot) += 1;
+        }
     }
-    UCNT(slot) += 1;
     S.Q = __dmul_rn(S.Q, p);
     S.rightP = __dmul_rn(S.rightP, q1);                              // :77
     S.n += 1;
     S.last_aid = S.f_aid;
 }
 
-__device__ __forceinline__ void pi_add_limbs(const K3Args& A, int lane, unsigned long long* limb, LaneState& S, int slot,
-                                             unsigned long long a0, unsigned long long a1, unsigned long long a2) {
+__device__ __forceinline__ void pi_add(const K3Args& A, int lane, ulonglong2* limb, LaneState& S, int slot, unsigned long long lo,
+                                       unsigned long long hi) {
     if (slot < NF) {
-        LIMB(slot, 0) += a0; LIMB(slot, 1) += a1; LIMB(slot, 2) += a2;
+        ulonglong2 v = LIMB(slot);
+        add128(v.x, v.y, lo, hi);
+        LIMB(slot) = v;
         S.keymask |= 1u << slot;
     } else {
         uint32_t e = slot == 5 ? S.udyn0 : S.udyn1;
+        unsigned long long a0, a1, a2;
+        split_limbs(lo, hi, a0, a1, a2);
         if (a0) atomicAdd(&A.dlimb[(size_t)e * 3 + 0], a0);
         if (a1) atomicAdd(&A.dlimb[(size_t)e * 3 + 1], a1);
         if (a2) atomicAdd(&A.dlimb[(size_t)e * 3 + 2], a2);
@@ -272,40 +341,73 @@ __device__ __forceinline__ uint32_t slot_to_aid(const LaneState& S, int slot) {
     return slot < NF ? (uint32_t)slot : NF + (slot == 5 ? S.udyn0 : S.udyn1);
 }
 
+__device__ __forceinline__ double neg_log10_1m(double p) {              // smCounter.py:509-510
+    const double x = 1.0 - p;
+    return x > 0.0 ? -log10(x) : 16.0;
+}
+
 // calProb + the per-barcode part of vc() (smCounter.py:26-98, 506-532) for the lane's locus.
-// The heavy FP64 work (PCR prior lookup, division, log10) runs over the COMPACTED list of alleles present in the
-// barcode, so lanes whose loci have different reference bases still execute the same instructions; only the cheap,
-// order-sensitive sums walk the slots in canonical order.
-__device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int64_t L, uint32_t urank, int* fc, unsigned long long* limb,
-                                             int* ucnt, double* uprod, double* ut, LaneState& S) {
+template <bool LIST>
+__device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int ki, int li, uint32_t urank, int* fc, ulonglong2* limb,
+                                             int* ucnt, double* uprod, LaneState& S) {
     if (S.umi_seen) S.allMT++;
     bool used = S.umi_bc;
     if (used) {
         S.nBC++;
-        int ki = A.keep_idx ? A.keep_idx[L] : -1;
         if (ki >= 0) {                                   // down-sampling mask (smCounter.py:496-500)
             unsigned long long u = A.umi_of_urank[urank];
             int64_t lo = A.keep_off[ki], hi = A.keep_off[ki + 1];
             int64_t pos = lower_bound_u64((const uint64_t*)A.keep_umi + lo, hi - lo, u);
             used = (pos < hi - lo) && (A.keep_umi[lo + pos] == u);
         }
-        if (A.list_idx) {
-            int li = A.list_idx[L];
-            if (li >= 0) {
-                uint32_t slot = atomicAdd(&A.list_count[li], 1u);
-                int64_t o = A.list_off[li] + slot;
-                if (o < A.list_off[li + 1] && o < A.list_cap) { A.list_umi[o] = A.umi_of_urank[urank]; A.list_first[o] = S.first_read; }
-            }
+        if (LIST && li >= 0) {
+            uint32_t slot = atomicAdd(&A.list_count[li], 1u);
+            int64_t o = A.list_off[li] + slot;
+            if (o < A.list_off[li + 1] && o < A.list_cap) { A.list_umi[o] = A.umi_of_urank[urank]; A.list_first[o] = S.first_read; }
         }
     }
     if (used) {
         const int n = S.n;
         S.usedMT++; S.usedFrag += n;
         S.mt3 += n >= 3; S.mt5 += n >= 5; S.mt7 += n >= 7; S.mt10 += n >= 10;
+        const bool multi = (S.exist & (S.exist - 1u)) != 0u;
+        const uint32_t ACGT = (1u << SMC_A_A) | (1u << SMC_A_T) | (1u << SMC_A_G) | (1u << SMC_A_C);
         if (n <= A.mtDrop) {                              // :28-32 -> four zeros, a 4-way tie (:514-523)
-            S.keymask |= (1u << SMC_A_A) | (1u << SMC_A_T) | (1u << SMC_A_G) | (1u << SMC_A_C);
+            S.keymask |= ACGT;
             if (n == 1) bump(A, fc, lane, S.last_aid, KW_MT, 1u, SMC_C_MT, SMC_C_STRONG);
+        } else if (!multi && (S.exist & ACGT) && n <= A.pcr_nmax) {
+            // ---- fast path: every fragment of the barcode shows the same base a0 in {A,C,G,T}; uniq = {A,C,G,T} (:49-54).
+            // Same operations in the same order as the general path below (prodP[a0] == rightP, one present allele,
+            // three pads sharing one value), with all intermediates in registers.
+            const int a0 = __ffs(S.exist) - 1;
+            const double rightP = S.rightP;
+            const double* trow = A.pcrtab + (size_t)n * (n + 1) / 2;                       // k = 4
+            const double v_e = __ldg(trow + n), v_pad = __ldg(trow);                       // :79-81
+            const double tpad = __dmul_rn(rightP, v_e);                                    // :88-91
+            const double PCR_NO_ERROR = 1.0 - 3e-5;
+            const double t_e = __dadd_rn(__dmul_rn(PCR_NO_ERROR, rightP), __dmul_rn(rightP, v_pad));   // :86 (min over the others = a pad's prior)
+            const int posidx = a0 - (a0 > SMC_A_DEL ? 1 : 0);                              // rank of a0 in slot order A C T G
+            double sumP = posidx == 0 ? t_e : tpad;                                        // :93 (0.0 + x == x)
+            sumP = __dadd_rn(sumP, posidx == 1 ? t_e : tpad);
+            sumP = __dadd_rn(sumP, posidx == 2 ? t_e : tpad);
+            sumP = __dadd_rn(sumP, posidx == 3 ? t_e : tpad);
+            const double l_pad = neg_log10_1m(sumP <= 0.0 ? 0.0 : tpad / sumP);
+            const double l_e = neg_log10_1m(sumP <= 0.0 ? 0.0 : t_e / sumP);
+            // PI: l_pad goes to all four bases through the register accumulator, a0 gets the difference (mod 2^128)
+            unsigned long long plo, phi, elo, ehi;
+            pi_fixed128(l_pad, plo, phi);
+            pi_fixed128(l_e, elo, ehi);
+            add128(S.pad_lo, S.pad_hi, plo, phi);
+            sub128(elo, ehi, plo, phi);
+            ulonglong2 v = LIMB(a0);
+            add128(v.x, v.y, elo, ehi);
+            LIMB(a0) = v;
+            S.keymask |= ACGT;
+            // consensus (:514-523): three pads tie at l_pad; a0 wins iff l_e > l_pad
+            if (l_e > l_pad) FCW(KW_MT, a0) += (l_e > A.smt) ? 0x10001 : 1;
+            else if (n == 1) FCW(KW_MT, a0) += 1;
         } else {
+            if (!multi) umi_materialize(lane, ucnt, uprod, S);
             // canonical order of the dynamic slots = ascending allele key
             if (S.ndyn == 2 && __ldcg(&A.dkey[S.udyn0]) > __ldcg(&A.dkey[S.udyn1])) {
                 uint32_t t = S.udyn0; S.udyn0 = S.udyn1; S.udyn1 = t;
@@ -335,41 +437,36 @@ __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int64_t 
                 const int s = __ffs(m) - 1;
                 const int c = UCNT(s);
                 const double v = tab ? __ldg(trow + c) : pcr_slow(c, denom);
-                UT(s) = v;
                 tpad = __dmul_rn(tpad, v);
                 if (v < m1) { m2 = m1; m1 = v; arg1 = s; } else if (v < m2) m2 = v;
             }
-            // ---- likelihood of each present allele (:86); pads all share tpad
+            // ---- likelihood of each present allele (:86), stored over its (no longer needed) product; pads all share tpad
             const double PCR_NO_ERROR = 1.0 - 3e-5;                       // smCounter.py:20
             for (uint32_t m = exist; m; m &= m - 1) {
                 const int s = __ffs(m) - 1;
                 const double minp = (s == arg1) ? m2 : m1;                // min over the OTHER members of uniq
-                UT(s) = __dadd_rn(__dmul_rn(PCR_NO_ERROR, UPROD(s)), __dmul_rn(rightP, minp));
+                UPROD(s) = __dadd_rn(__dmul_rn(PCR_NO_ERROR, UPROD(s)), __dmul_rn(rightP, minp));
             }
             double sumP = 0.0;                                            // :93, in canonical slot order
             for (uint32_t m = uniq; m; m &= m - 1) {
                 const int s = __ffs(m) - 1;
-                sumP = __dadd_rn(sumP, ((exist >> s) & 1u) ? UT(s) : tpad);
+                sumP = __dadd_rn(sumP, ((exist >> s) & 1u) ? UPROD(s) : tpad);
             }
             // ---- posterior -> -log10(1-p) (:96, :509-510), PI accumulation (:512), consensus (:514-523)
             double best = -1.0; int nbest = 0, cons = -1;
             if (pad) {
-                const double p = sumP <= 0.0 ? 0.0 : tpad / sumP;
-                const double x = 1.0 - p;
-                const double l = x > 0.0 ? -log10(x) : 16.0;
-                unsigned long long a0, a1, a2;
-                pi_limbs(l, a0, a1, a2);
-                for (uint32_t m = pad; m; m &= m - 1) pi_add_limbs(A, lane, limb, S, __ffs(m) - 1, a0, a1, a2);
+                const double l = neg_log10_1m(sumP <= 0.0 ? 0.0 : tpad / sumP);
+                unsigned long long lo, hi;
+                pi_fixed128(l, lo, hi);
+                for (uint32_t m = pad; m; m &= m - 1) pi_add(A, lane, limb, S, __ffs(m) - 1, lo, hi);
                 best = l; nbest = __popc(pad); cons = __ffs(pad) - 1;
             }
             for (uint32_t m = exist; m; m &= m - 1) {
                 const int s = __ffs(m) - 1;
-                const double p = sumP <= 0.0 ? 0.0 : UT(s) / sumP;
-                const double x = 1.0 - p;
-                const double l = x > 0.0 ? -log10(x) : 16.0;
-                unsigned long long a0, a1, a2;
-                pi_limbs(l, a0, a1, a2);
-                pi_add_limbs(A, lane, limb, S, s, a0, a1, a2);
+                const double l = neg_log10_1m(sumP <= 0.0 ? 0.0 : UPROD(s) / sumP);
+                unsigned long long lo, hi;
+                pi_fixed128(l, lo, hi);
+                pi_add(A, lane, limb, S, s, lo, hi);
                 if (l > best) { best = l; nbest = 1; cons = s; }
                 else if (l == best) nbest++;
             }
@@ -418,15 +515,19 @@ __device__ __forceinline__ void flush_counters(const K3Args& A, int* fc, int lan
     }
 }
 
-__global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup(const K3Args A) {
+template <bool LIST>
+__global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup_t(const K3Args A) {
     extern __shared__ __align__(16) uint32_t smem[];
+    double* bqtab_s = reinterpret_cast<double*>(smem);
+    for (int i = threadIdx.x; i < 256; i += K3_WARPS * 32) bqtab_s[i] = __ldg(&A.bqtab[i]);
+    __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* ws = smem + (size_t)w * K3_WARP_WORDS;
-    int* fc = (int*)(ws + K3_STAGE_WORDS);
-    unsigned long long* limb = (unsigned long long*)(ws + K3_STAGE_WORDS + K3_FC_WORDS);
-    int* ucnt = (int*)(ws + K3_STAGE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS);
-    double* uprod = (double*)(ws + K3_STAGE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS + K3_UCNT_WORDS);
-    double* ut = (double*)(ws + K3_STAGE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS + K3_UCNT_WORDS + K3_UPROD_WORDS);
+    uint32_t* ws = smem + K3_BQTAB_BYTES / 4 + (size_t)w * K3_WARP_WORDS;
+    uint16_t* codes = reinterpret_cast<uint16_t*>(ws + K3_STAGE_WORDS);
+    int* fc = (int*)(ws + K3_STAGE_WORDS + K3_CODE_WORDS);
+    ulonglong2* limb = (ulonglong2*)(ws + K3_STAGE_WORDS + K3_CODE_WORDS + K3_FC_WORDS);
+    int* ucnt = (int*)(ws + K3_STAGE_WORDS + K3_CODE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS);
+    double* uprod = (double*)(ws + K3_STAGE_WORDS + K3_CODE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS + K3_UCNT_WORDS);
 
     const uint32_t unit = blockIdx.x * K3_WARPS + w;
     if (unit >= A.unit_off[A.n_tiles]) return;
@@ -442,166 +543,232 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup(const K3
     const bool lane_valid = L < A.n_loci;
     const int32_t p = lane_valid ? A.loci_pos[L] : 0;
     const int32_t Li = (int32_t)L;
+    const int ki = (lane_valid && A.keep_idx) ? A.keep_idx[L] : -1;
+    const int li = (LIST && lane_valid) ? A.list_idx[L] : -1;
 
-    for (int i = lane; i < K3_FC_WORDS + K3_LIMB_WORDS; i += 32) ws[K3_STAGE_WORDS + i] = 0;
+    for (int i = lane; i < K3_FC_WORDS + K3_LIMB_WORDS; i += 32) ws[K3_STAGE_WORDS + K3_CODE_WORDS + i] = 0;
     __syncwarp();
 
     LaneState S;
     S.cvg = S.allFrag = S.allMT = S.usedFrag = S.nBC = S.usedMT = S.mt3 = S.mt5 = S.mt7 = S.mt10 = 0;
-    S.keymask = 0; S.status = 0;
+    S.keymask = 0; S.status = 0; S.pad_lo = S.pad_hi = 0;
+    S.r_allele = S.r_fwd = S.r_r1tot = S.r_r1le = S.r_r2tot = S.r_r2le = 0;
     S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.last_aid = 0; S.udyn0 = S.udyn1 = 0; S.ndyn = 0;
     S.umi_seen = S.umi_bc = false; S.first_read = 0xffffffffu;
     S.frag_seen = S.f_exists = S.f_paired = false; S.f_aid = 0; S.f_bq = 0;
 
     uint32_t prev_urank = 0xffffffffu, prev_frank = 0xffffffffu;
     bool first = true;
-    const int minBQ = A.minBQ;
-    uint32_t since_flush = 0;
+    const int minBQ = A.minBQ, primerDist = A.primerDist;
+    uint32_t since_flush = 0, since_reg_flush = 0;
 
     for (uint32_t base = eb; base < ee; base += 32) {
+        const int nb = (int)min(32u, ee - base);
         {   // stage the next 32 read records in shared memory (4 x 128-bit loads per lane)
-            uint32_t e = base + lane;
-            if (e < ee) {
-                const uint4* src = reinterpret_cast<const uint4*>(&A.recs[A.ev_read[e]]);
+            if (lane < nb) {
+                const uint4* src = reinterpret_cast<const uint4*>(&A.recs[A.ev_read[base + lane]]);
                 uint4* dst = reinterpret_cast<uint4*>(ws + lane * 16);
                 uint4 r0 = __ldg(src), r1 = __ldg(src + 1), r2 = __ldg(src + 2), r3 = __ldg(src + 3);
                 dst[0] = r0; dst[1] = r1; dst[2] = r2; dst[3] = r3;
             }
         }
-        since_flush += 32;
-        if (since_flush > K3_FLUSH_EVERY) { flush_counters(A, fc, lane, L, lane_valid); since_flush = 0; }
+        since_flush += 32; since_reg_flush += 32;
+        if (since_reg_flush > K3_REG_FLUSH) { flush_regs(fc, lane, S); since_reg_flush = 32; }
+        if (since_flush > K3_FLUSH_EVERY) { flush_regs(fc, lane, S); flush_counters(A, fc, lane, L, lane_valid); since_flush = 32; since_reg_flush = 32; }
         __syncwarp();
-        // the last batch runs one extra (sentinel) iteration that only closes the open fragment and barcode
-        const int cntj = (int)min(32u, ee - base) + (base + 32 >= ee ? 1 : 0);
+        // ---------------- pass A: gather base + quality of my locus for 8 reads at a time (simple reads only)
+        for (int g = 0; g < nb; g += 8) {
+            uint32_t sbv[8], bqv[8], cdv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t* rw = ws + (g + u) * 16;
+                const uint4 q0 = *reinterpret_cast<const uint4*>(rw);        // start lo hi meta
+                const uint4 q1 = *reinterpret_cast<const uint4*>(rw + 4);    // sp_aln seq_off qual_off cigar_off
+                const bool cov = (g + u < nb) && lane_valid && Li >= (int32_t)q0.y && Li < (int32_t)q0.z && (q0.w & RM_SIMPLE);
+                const int d = p - (int32_t)q0.x;                              // qpos - leftSP
+                const int qpos = (int)(q1.x & 0xffffu) + d;
+                const int alnlen = (int)(q1.x >> 16);
+                sbv[u] = 0; bqv[u] = 0;
+                if (cov) {
+                    sbv[u] = __ldg(&A.seq[(size_t)q1.y + (qpos >> 1)]);
+                    bqv[u] = __ldg(&A.qual[(size_t)q1.z + qpos]);
+                }
+                const bool rev = q0.w & RM_REVERSE, r2 = q0.w & RM_READ2;
+                const int da = rev ? alnlen - d : d, db = rev ? d : alnlen - d;   // R1: bc end = da; R2: bc end = db, primer end = da
+                const bool le20 = (r2 ? db : da) <= 20;
+                const bool ple = r2 && da <= primerDist;
+                cdv[u] = (cov ? EC_COVERED : 0u) | (le20 ? EC_LE20 : 0u) | (ple ? EC_PLE : 0u) | ((uint32_t)(qpos & 1) << 15);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t nib = (cdv[u] >> 15) ? (sbv[u] & 15u) : (sbv[u] >> 4);
+                uint32_t cd = (cdv[u] & 0x7fffu) | bqv[u] | (nib_field(nib) << EC_FIELD_SH);
+                if (!nib_is_acgt(nib)) cd |= EC_DYN;
+                codes[(g + u) * 32 + lane] = (uint16_t)cd;
+            }
+        }
+        __syncwarp();
+        // ---------------- pass B: the order-dependent reduction.  The last batch runs one extra (sentinel) iteration
+        // that only closes the open fragment and barcode.
+        const int cntj = nb + (base + 32 >= ee ? 1 : 0);
         for (int j = 0; j < cntj; ++j) {
-            const bool sentinel = base + (uint32_t)j >= ee;
+            const bool sentinel = j >= nb;
             const uint32_t* rw = ws + (j & 31) * 16;
-            const uint4 q0 = *reinterpret_cast<const uint4*>(rw);        // start lo hi meta
-            const uint4 q1 = *reinterpret_cast<const uint4*>(rw + 4);    // sp_aln seq_off qual_off cigar_off
             const uint2 q2 = *reinterpret_cast<const uint2*>(rw + 8);    // urank frank
-            const int32_t start = (int32_t)q0.x, lo = (int32_t)q0.y, hi = (int32_t)q0.z;
-            const uint32_t meta = q0.w;
+            const uint32_t meta = rw[3];
             const uint32_t urank = sentinel ? 0xfffffffeu : q2.x, frank = sentinel ? 0xfffffffeu : q2.y;
             // ---- barcode / fragment boundaries (warp uniform)
             if (!first) {
-                if (frank != prev_frank) fragment_finalize(A, lane, ucnt, uprod, S);
-                if (urank != prev_urank) umi_finalize(A, lane, L, prev_urank, fc, limb, ucnt, uprod, ut, S);
+                if (frank != prev_frank) fragment_finalize(A, bqtab_s, lane, ucnt, uprod, S);
+                if (urank != prev_urank) umi_finalize<LIST>(A, lane, ki, li, prev_urank, fc, limb, ucnt, uprod, S);
             }
             first = false; prev_urank = urank; prev_frank = frank;
             if (sentinel) break;
-            // ---- does the read cover my locus?
-            const bool covered = lane_valid && Li >= lo && Li < hi;
-            int qpos = 0, indel = 0; bool isdel = false;
-            const uint32_t ncig = meta >> 8;
-            const int leftSP = (int)(q1.x & 0xffffu), alnlen = (int)(q1.x >> 16);
-            if (meta & RM_SIMPLE) {
-                qpos = leftSP + (p - start);
+            const bool reverse = meta & RM_REVERSE, read2 = meta & RM_READ2;
+            bool covered, regular = false, isN = false, le20 = false, ple = false;
+            uint32_t aid = 0; int bq = 0;
+            if (meta & RM_SIMPLE) {                                        // warp uniform
+                const uint32_t cd = codes[j * 32 + lane];
+                covered = cd & EC_COVERED;
+                bq = (int)(cd & 255u); le20 = cd & EC_LE20; ple = cd & EC_PLE; regular = true;
+                const uint32_t f = (cd >> EC_FIELD_SH) & 3u;
+                aid = f + (f >> 1);
+                if (covered && (cd & EC_DYN)) {                            // N / IUPAC base (:423-457 with a non-ACGT key)
+                    const int qpos = (int)(rw[4] & 0xffffu) + (p - (int32_t)rw[0]);
+                    const uint32_t sb = __ldg(&A.seq[(size_t)rw[5] + (qpos >> 1)]);
+                    const uint32_t nib = (qpos & 1) ? (sb & 15u) : (sb >> 4);
+                    const unsigned long long key = dyn_make_key((uint32_t)Li, SMC_K_BASE, nib, 0ull);
+                    const uint32_t e = dyn_lookup(A.dkey, A.dmask, A.drep_read, A.drep_qpos, A.dlen, A.dcount, A.gflags, key, rw[14], qpos, 0);
+                    aid = NF + e; isN = (nib == 15u);
+                    atomicAdd(&A.dcnt[(size_t)e * SMC_NCNT + SMC_C_ALLELE], 1);
+                    if (!reverse) atomicAdd(&A.dcnt[(size_t)e * SMC_NCNT + SMC_C_FWD], 1);
+                }
             } else {
-                // htslib resolve_cigar2: find the reference-consuming op that covers p
-                int x = start, y = 0; bool found = false;
-                for (uint32_t k = 0; k < ncig; ++k) {
-                    uint32_t cw = k < 4 ? rw[10 + k] : __ldg(&A.cigar[q1.w + k]);
-                    uint32_t op = cw & 15u; int len = (int)(cw >> 4);
-                    bool refop = (op == 0 || op == 7 || op == 8 || op == 2 || op == 3);
-                    if (refop) {
-                        if (covered && !found && p < x + len) {
-                            found = true;
-                            isdel = (op == 2 || op == 3);
-                            qpos = isdel ? y : y + (p - x);
-                            if (p == x + len - 1 && k + 1 < ncig) {       // peek the next op
-                                uint32_t c2 = (k + 1) < 4 ? rw[10 + k + 1] : __ldg(&A.cigar[q1.w + k + 1]);
-                                uint32_t op2 = c2 & 15u; int l2 = (int)(c2 >> 4);
-                                if (op2 == 2) indel = -l2;
-                                else if (op2 == 1) indel = l2;
-                                else if (op2 == 6 && k + 2 < ncig) {
-                                    int l3 = 0;
-                                    for (uint32_t kk = k + 2; kk < ncig; ++kk) {
-                                        uint32_t c3 = kk < 4 ? rw[10 + kk] : __ldg(&A.cigar[q1.w + kk]);
-                                        uint32_t op3 = c3 & 15u;
-                                        if (op3 == 1) l3 += (int)(c3 >> 4);
-                                        else if (op3 == 2 || op3 == 0 || op3 == 3 || op3 == 7 || op3 == 8) break;
+                // ---- htslib resolve_cigar2: find the reference-consuming op that covers p
+                const int32_t start = (int32_t)rw[0], lo = (int32_t)rw[1], hi = (int32_t)rw[2];
+                covered = lane_valid && Li >= lo && Li < hi;
+                const uint32_t ncig = meta >> 8;
+                const int leftSP = (int)(rw[4] & 0xffffu), alnlen = (int)(rw[4] >> 16);
+                const uint32_t seq_off = rw[5], qual_off = rw[6], cigar_off = rw[7];
+                int qpos = 0, indel = 0; bool isdel = false;
+                {
+                    int x = start, y = 0; bool found = false;
+                    for (uint32_t k = 0; k < ncig; ++k) {
+                        uint32_t cw = k < 4 ? rw[10 + k] : __ldg(&A.cigar[cigar_off + k]);
+                        uint32_t op = cw & 15u; int len = (int)(cw >> 4);
+                        bool refop = (op == 0 || op == 7 || op == 8 || op == 2 || op == 3);
+                        if (refop) {
+                            if (covered && !found && p < x + len) {
+                                found = true;
+                                isdel = (op == 2 || op == 3);
+                                qpos = isdel ? y : y + (p - x);
+                                if (p == x + len - 1 && k + 1 < ncig) {       // peek the next op
+                                    uint32_t c2 = (k + 1) < 4 ? rw[10 + k + 1] : __ldg(&A.cigar[cigar_off + k + 1]);
+                                    uint32_t op2 = c2 & 15u; int l2 = (int)(c2 >> 4);
+                                    if (op2 == 2) indel = -l2;
+                                    else if (op2 == 1) indel = l2;
+                                    else if (op2 == 6 && k + 2 < ncig) {
+                                        int l3 = 0;
+                                        for (uint32_t kk = k + 2; kk < ncig; ++kk) {
+                                            uint32_t c3 = kk < 4 ? rw[10 + kk] : __ldg(&A.cigar[cigar_off + kk]);
+                                            uint32_t op3 = c3 & 15u;
+                                            if (op3 == 1) l3 += (int)(c3 >> 4);
+                                            else if (op3 == 2 || op3 == 0 || op3 == 3 || op3 == 7 || op3 == 8) break;
+                                        }
+                                        if (l3 > 0) indel = l3;
                                     }
-                                    if (l3 > 0) indel = l3;
                                 }
                             }
+                            x += len;
+                            if (op == 0 || op == 7 || op == 8) y += len;
+                        } else if (op == 1 || op == 4) y += len;
+                        if (__all_sync(FULL_MASK, found || !covered)) break;
+                    }
+                }
+                if (covered) {
+                    if (indel == 0 && isdel) {                                 // :416-421
+                        aid = SMC_A_DEL; bq = minBQ;
+                    } else {
+                        const uint32_t sb = __ldg(&A.seq[(size_t)seq_off + (qpos >> 1)]);
+                        const uint32_t nib = (qpos & 1) ? (sb & 15u) : (sb >> 4);
+                        bq = (int)__ldg(&A.qual[(size_t)qual_off + qpos]);
+                        const int fa = nib_to_fixed(nib);
+                        if (indel == 0 && fa >= 0) {                           // :423-457 regular base, A/C/G/T
+                            aid = (uint32_t)fa; regular = true;
+                        } else {
+                            // dynamic allele: N / IUPAC base, insertion start (:371-389) or deletion start (:392-411)
+                            unsigned long long key; int len = 0;
+                            if (indel > 0) {
+                                len = indel;
+                                unsigned long long payload;
+                                if (len <= 8) {
+                                    unsigned long long nibs = 0;
+                                    for (int t = 0; t < len; ++t) {
+                                        int qq = qpos + 1 + t;
+                                        uint32_t b2 = __ldg(&A.seq[(size_t)seq_off + (qq >> 1)]);
+                                        nibs |= (unsigned long long)((qq & 1) ? (b2 & 15u) : (b2 >> 4)) << (28 - 4 * t);
+                                    }
+                                    payload = ((unsigned long long)len << 32) | nibs;
+                                } else {
+                                    uint32_t hsh = 2166136261u ^ (uint32_t)len;
+                                    for (int t = 0; t < len; ++t) {
+                                        int qq = qpos + 1 + t;
+                                        uint32_t b2 = __ldg(&A.seq[(size_t)seq_off + (qq >> 1)]);
+                                        hsh = (hsh ^ ((qq & 1) ? (b2 & 15u) : (b2 >> 4))) * 16777619u;
+                                    }
+                                    payload = (15ull << 32) | hsh;
+                                }
+                                key = dyn_make_key((uint32_t)Li, SMC_K_INS, nib, payload);
+                            } else if (indel < 0) {
+                                len = -indel;
+                                key = dyn_make_key((uint32_t)Li, SMC_K_DEL, nib, (unsigned long long)len);
+                            } else {
+                                key = dyn_make_key((uint32_t)Li, SMC_K_BASE, nib, 0ull);
+                                regular = true; isN = (nib == 15u);
+                            }
+                            const uint32_t e = dyn_lookup(A.dkey, A.dmask, A.drep_read, A.drep_qpos, A.dlen, A.dcount, A.gflags, key, rw[14], qpos, len);
+                            aid = NF + e;
+                            atomicAdd(&A.dcnt[(size_t)e * SMC_NCNT + SMC_C_ALLELE], 1);
+                            if (!reverse) atomicAdd(&A.dcnt[(size_t)e * SMC_NCNT + SMC_C_FWD], 1);
                         }
-                        x += len;
-                        if (op == 0 || op == 7 || op == 8) y += len;
-                    } else if (op == 1 || op == 4) y += len;
-                    if (__all_sync(FULL_MASK, found || !covered)) break;
+                    }
+                    if (regular) {                                             // :432-452
+                        const int d = qpos - leftSP;
+                        const int da = reverse ? alnlen - d : d, db = reverse ? d : alnlen - d;
+                        le20 = (read2 ? db : da) <= 20;
+                        ple = read2 && da <= primerDist;
+                    }
                 }
             }
             if (covered) {
                 S.cvg++;                                                   // smCounter.py:368
-                const bool reverse = meta & RM_REVERSE, read2 = meta & RM_READ2;
-                uint32_t aid; int bq; bool regular = false, isN = false;
-                if (indel == 0 && isdel) {                                 // :416-421
-                    aid = SMC_A_DEL; bq = minBQ;
-                    FCW(KW_ALLELE_FWD, SMC_A_DEL) += 1;
-                } else {
-                    const uint32_t sb = __ldg(&A.seq[(size_t)q1.y + (qpos >> 1)]);
-                    const uint32_t nib = (qpos & 1) ? (sb & 15u) : (sb >> 4);
-                    bq = (int)__ldg(&A.qual[(size_t)q1.z + qpos]);
-                    const int fa = nib_to_fixed(nib);
-                    if (indel == 0 && fa >= 0) {                           // :423-457 regular base, A/C/G/T
-                        aid = (uint32_t)fa; regular = true;
-                        FCW(KW_ALLELE_FWD, fa) += reverse ? 1 : 0x10001;
-                    } else {
-                        // dynamic allele: N / IUPAC base, insertion start (:371-389) or deletion start (:392-411)
-                        unsigned long long key; int len = 0;
-                        if (indel > 0) {
-                            len = indel;
-                            unsigned long long payload;
-                            if (len <= 8) {
-                                unsigned long long nibs = 0;
-                                for (int t = 0; t < len; ++t) {
-                                    int qq = qpos + 1 + t;
-                                    uint32_t b2 = __ldg(&A.seq[(size_t)q1.y + (qq >> 1)]);
-                                    nibs |= (unsigned long long)((qq & 1) ? (b2 & 15u) : (b2 >> 4)) << (28 - 4 * t);
-                                }
-                                payload = ((unsigned long long)len << 32) | nibs;
-                            } else {
-                                uint32_t hsh = 2166136261u ^ (uint32_t)len;
-                                for (int t = 0; t < len; ++t) {
-                                    int qq = qpos + 1 + t;
-                                    uint32_t b2 = __ldg(&A.seq[(size_t)q1.y + (qq >> 1)]);
-                                    hsh = (hsh ^ ((qq & 1) ? (b2 & 15u) : (b2 >> 4))) * 16777619u;
-                                }
-                                payload = (15ull << 32) | hsh;
-                            }
-                            key = dyn_make_key((uint32_t)Li, SMC_K_INS, nib, payload);
-                        } else if (indel < 0) {
-                            len = -indel;
-                            key = dyn_make_key((uint32_t)Li, SMC_K_DEL, nib, (unsigned long long)len);
-                        } else {
-                            key = dyn_make_key((uint32_t)Li, SMC_K_BASE, nib, 0ull);
-                            regular = true; isN = (nib == 15u);
-                        }
-                        const uint32_t e = dyn_lookup(A.dkey, A.dmask, A.drep_read, A.drep_qpos, A.dlen, A.dcount, A.gflags, key, rw[14], qpos, len);
-                        aid = NF + e;
-                        atomicAdd(&A.dcnt[(size_t)e * SMC_NCNT + SMC_C_ALLELE], 1);
-                        if (!reverse) atomicAdd(&A.dcnt[(size_t)e * SMC_NCNT + SMC_C_FWD], 1);
+                const bool lowq = bq < minBQ;
+                const bool inc = !lowq && (meta & RM_OK);                  // :378,400,421,431
+                if (regular && aid < NF) {                                 // A/C/G/T: register counters
+                    const uint32_t one = 1u << (8u * (aid - (aid >> 1) + (aid >> 2)));   // slot 0,1,3,4 -> field 0,1,2,3
+                    S.r_allele += one;
+                    if (!reverse) S.r_fwd += one;
+                    if (lowq) FCW(KW_LOWQ_R2P, aid) += 1;                  // :428-429
+                    if (inc) {
+                        if (!read2) { S.r_r1tot += one; if (le20) S.r_r1le += one; }
+                        else { S.r_r2tot += one; if (le20) S.r_r2le += one; if (ple) FCW(KW_LOWQ_R2P, aid) += 0x10000; }
                     }
-                }
-                const bool inc = (bq >= minBQ) && (meta & RM_OK);          // :378,400,421,431
-                if (regular) {
-                    if (bq < minBQ) bump(A, fc, lane, aid, KW_LOWQ_R2P, 1u, SMC_C_LOWQ, SMC_C_R2PLE);          // :428-429
-                    if (inc) {                                                                                  // :432-452
-                        const int d = qpos - leftSP;
-                        if (!read2) {
-                            const int dist = reverse ? alnlen - d : d;
-                            bump(A, fc, lane, aid, KW_R1, dist <= 20 ? 0x10001u : 1u, SMC_C_R1TOT, SMC_C_R1LE);
-                        } else {
-                            const int dbc = reverse ? d : alnlen - d;
-                            const int dpr = reverse ? alnlen - d : d;
-                            bump(A, fc, lane, aid, KW_R2, dbc <= 20 ? 0x10001u : 1u, SMC_C_R2TOT, SMC_C_R2LE);
-                            if (dpr <= A.primerDist) bump(A, fc, lane, aid, KW_LOWQ_R2P, 0x10000u, SMC_C_LOWQ, SMC_C_R2PLE);
+                } else if (aid == SMC_A_DEL) {
+                    FCW(KW_ALLELE_FWD, SMC_A_DEL) += 1;                    // alleleCnt only (:416-421, :459)
+                } else if (regular) {                                      // N / IUPAC base: dynamic row, same tallies
+                    if (lowq) bump(A, fc, lane, aid, KW_LOWQ_R2P, 1u, SMC_C_LOWQ, SMC_C_R2PLE);
+                    if (inc) {
+                        if (!read2) bump(A, fc, lane, aid, KW_R1, le20 ? 0x10001u : 1u, SMC_C_R1TOT, SMC_C_R1LE);
+                        else {
+                            bump(A, fc, lane, aid, KW_R2, le20 ? 0x10001u : 1u, SMC_C_R2TOT, SMC_C_R2LE);
+                            if (ple) bump(A, fc, lane, aid, KW_LOWQ_R2P, 0x10000u, SMC_C_LOWQ, SMC_C_R2PLE);
                         }
                     }
                 }
                 S.umi_seen = true; S.frag_seen = true;                     // :463-464
                 if (inc) {                                                 // :467-479
-                    S.umi_bc = true; S.first_read = min(S.first_read, rw[14]);
+                    S.umi_bc = true;
+                    if (LIST) S.first_read = min(S.first_read, rw[14]);
                     if (!S.f_exists) { S.f_exists = true; S.f_aid = aid; S.f_bq = bq; S.f_paired = false; }
                     else if (aid == S.f_aid || isN) {
                         S.f_bq = min(S.f_bq, bq); S.f_paired = true;
@@ -613,16 +780,19 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup(const K3
         __syncwarp();
     }
     // ---- flush the lane's locus to the per-locus accumulators ([field][locus] layout: coalesced across lanes)
+    flush_regs(fc, lane, S);
     flush_counters(A, fc, lane, L, lane_valid);
     if (lane_valid) {
         const size_t nl = (size_t)A.n_loci;
 #pragma unroll
         for (int a = 0; a < NF; ++a) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                unsigned long long v = LIMB(a, j);
-                if (v) atomicAdd(&A.limb[((size_t)a * 3 + j) * nl + L], v);
-            }
+            ulonglong2 v = LIMB(a);
+            if (a != SMC_A_DEL) add128(v.x, v.y, S.pad_lo, S.pad_hi);
+            unsigned long long a0, a1, a2;
+            split_limbs(v.x, v.y, a0, a1, a2);
+            if (a0) atomicAdd(&A.limb[((size_t)a * 3 + 0) * nl + L], a0);
+            if (a1) atomicAdd(&A.limb[((size_t)a * 3 + 1) * nl + L], a1);
+            if (a2) atomicAdd(&A.limb[((size_t)a * 3 + 2) * nl + L], a2);
         }
         int32_t* loc = A.loc;
         if (S.cvg) atomicAdd(&loc[SMC_L_CVG * nl + L], S.cvg);
