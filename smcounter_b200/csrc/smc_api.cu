@@ -370,7 +370,7 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         P.seq_off = ctx->d_seq_off.as<int64_t>(); P.qual_off = ctx->d_qual_off.as<int64_t>(); P.cigar_off = ctx->d_cig_off.as<int64_t>();
         P.n_cigar = ctx->d_ncig.as<uint16_t>(); P.cigar = ctx->d_cigar.as<uint32_t>();
         P.loci_key = ctx->d_loci_key.as<uint64_t>(); P.n_loci = nl;
-        P.minMQ = ctx->prm.minMQ; P.mismatchThr = ctx->prm.mismatchThr;
+        P.minMQ = ctx->prm.minMQ; P.primerDist = ctx->prm.primerDist; P.mismatchThr = ctx->prm.mismatchThr;
         P.recs = ctx->d_recs.as<ReadRec>(); P.ntiles = ctx->d_ntiles.as<uint32_t>(); P.gflags = small + 5;
         LAUNCH(k_read_prep, nblk(n, 256), 256, 0, P);
         exclusive_scan_u32(ctx->d_ntiles.as<uint32_t>(), ctx->d_evoff.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + 4, ctx->st);

@@ -23,7 +23,7 @@ struct PrepArgs {
     const int32_t* l_seq; const int64_t* seq_off; const int64_t* qual_off; const int64_t* cigar_off;
     const uint16_t* n_cigar; const uint32_t* cigar;
     const uint64_t* loci_key; int64_t n_loci;
-    int minMQ; double mismatchThr;
+    int minMQ; int primerDist; double mismatchThr;
     ReadRec* recs; uint32_t* ntiles; uint32_t* gflags;
 };
 
@@ -70,13 +70,28 @@ __global__ void __launch_bounds__(256) k_read_prep(PrepArgs A) {
     if (lseq > 65535 || leftSP > 65535 || alnlen < 0 || alnlen > 65535) { atomicOr(A.gflags, GF_BAD_READ); lo = hi = 0; }
     ReadRec rec;
     rec.start = start; rec.lo = (int32_t)lo; rec.hi = (int32_t)hi;
-    rec.meta = (ok ? RM_OK : 0u) | ((fl & 0x10u) ? RM_REVERSE : 0u) | ((fl & 0x80u) ? RM_READ2 : 0u) |
-               (simple ? RM_SIMPLE : 0u) | (ncig << 8);
-    rec.sp_aln = (uint32_t)leftSP | ((uint32_t)alnlen << 16);
+    const bool rev = fl & 0x10u, r2 = fl & 0x80u;
+    rec.meta = (ok ? RM_OK : 0u) | (rev ? RM_REVERSE : 0u) | (r2 ? RM_READ2 : 0u) | (simple ? RM_SIMPLE : 0u) | (ncig << 8);
     rec.seq_off = (uint32_t)A.seq_off[r]; rec.qual_off = (uint32_t)A.qual_off[r]; rec.cigar_off = (uint32_t)co;
     rec.urank = A.urank[s]; rec.frank = A.frank[s];
-    rec.cig[0] = c4[0]; rec.cig[1] = c4[1]; rec.cig[2] = c4[2]; rec.cig[3] = c4[3];
     rec.read_idx = r; rec.pad = 0;
+    if (simple) {
+        // One aligned run: d = p - start is the distance from the alignment start, alnlen - d from its end.
+        //   R1: distToBcEnd = rev ? alnlen - d : d;   R2: distToBcEnd = rev ? d : alnlen - d, distToPrimerEnd = rev ? alnlen - d : d
+        // "<= X from the start" is the window [start, start + X], "<= X from the end" is [start + alnlen - X, inf).
+        rec.sp_aln = (uint32_t)(leftSP - start);
+        const uint32_t EMPTY_LO = 0x7fffffffu;
+        auto from_start = [&](int X, uint32_t& wlo, uint32_t& wspan) { if (X < 0) { wlo = EMPTY_LO; wspan = 0; } else { wlo = (uint32_t)start; wspan = (uint32_t)X; } };
+        auto from_end = [&](int X, uint32_t& wlo, uint32_t& wspan) { wlo = (uint32_t)(start + alnlen - X); wspan = 0x7fffffffu; };
+        const bool bc_at_start = (r2 == rev);                 // R1 fwd / R2 rev measure the barcode end from the start
+        if (bc_at_start) from_start(20, rec.cig[0], rec.cig[1]); else from_end(20, rec.cig[0], rec.cig[1]);
+        if (!r2) { rec.cig[2] = EMPTY_LO; rec.cig[3] = 0; }
+        else if (rev) from_end(A.primerDist, rec.cig[2], rec.cig[3]);
+        else from_start(A.primerDist, rec.cig[2], rec.cig[3]);
+    } else {
+        rec.sp_aln = (uint32_t)leftSP | ((uint32_t)alnlen << 16);
+        rec.cig[0] = c4[0]; rec.cig[1] = c4[1]; rec.cig[2] = c4[2]; rec.cig[3] = c4[3];
+    }
     const uint4* src = reinterpret_cast<const uint4*>(&rec);
     uint4* dst = reinterpret_cast<uint4*>(&A.recs[s]);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
@@ -98,26 +113,32 @@ k_expand(const ReadRec* __restrict__ recs, const uint32_t* __restrict__ ev_off, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K3: tile pileup (v3)
+// K3: tile pileup (v5)
 //
-// A warp owns one unit = a run of <= `chunk` tile events of one 32-locus tile, cut at barcode boundaries.  It works in
-// batches of 32 reads:
-//   stage   : 32 ReadRec (64 B each, gathered through ev_read[]) -> shared memory, 4 x 128-bit loads per lane;
-//   pass A  : "gather" -- for each staged read every lane computes the query position of ITS locus and loads the base
-//             nibble and the quality.  The 32 reads are independent, so the loads are issued 8 reads at a time
-//             (16 loads in flight per lane) and their results are packed into 16-bit event codes in shared memory.
-//             This is where all the DRAM/L2 latency of the kernel is, and it is hidden by ILP instead of occupancy;
-//   pass B  : "reduce" -- the order-dependent state machine (fragment merge, per-barcode posterior, tallies) walks the
-//             codes.  The hot counters live in registers as 4 x 8-bit fields (A, C, T, G) per 32-bit word and are
-//             spilled to the 16-bit shared-memory counters every 224 events; those go to the global 32-bit
-//             accumulators every 49 152 events and at the end of the unit.
-// Reads with indels / hard clips / several aligned segments ("not simple") take the per-event CIGAR walk in pass B.
+// A warp owns one unit = a run of <= `chunk` tile events of one 32-locus tile, cut at barcode boundaries; LANE = LOCUS.
+// It works in batches of 32 reads:
+//   stage   : 32 ReadRec (64 B each, gathered through ev_read[]) -> shared memory, 4 x 128-bit loads per lane; barcode /
+//             fragment boundaries and "simple read" flags become warp-uniform bit masks (ballots);
+//   pass A  : "gather + tally" -- for each staged read every lane computes the query position of ITS locus, loads the
+//             base nibble and the quality, and adds the event to the order-independent tallies (cvg, alleleCnt,
+//             forward, lowQ, R1/R2 end-distance counts) held in registers as 4 x 8-bit fields (A, C, T, G) per word.
+//             The reads of a batch are independent, so the loads are issued 4 reads at a time (8 loads in flight per
+//             lane): this is where all the DRAM/L2 latency of the kernel is, and it is hidden by ILP plus the other
+//             warps' pass B.  What the ordered pass still needs is packed into a 16-bit event code in shared memory;
+//   pass B  : "merge" -- the order-dependent state machine (fragment merge :467-479, per-barcode posterior, consensus)
+//             walks the codes.  Register counters are spilled to the 16-bit shared-memory counters every 224 events;
+//             those go to the global 32-bit accumulators every 49 152 events and at the end of the unit.
+// Everything rare is out of line (__noinline__) so that the hot loop stays small in the instruction cache: reads with
+// indels / hard clips / several aligned runs (per-event CIGAR walk), non-ACGT bases, barcodes showing several alleles.
 // ------------------------------------------------------------------------------------------------------------
 #ifndef K3_WARPS
 #define K3_WARPS 4
 #endif
 #ifndef K3_MINBLOCKS
 #define K3_MINBLOCKS 4
+#endif
+#ifndef K3_GATHER
+#define K3_GATHER 4        // reads per gather group in pass A
 #endif
 #define NF SMC_NFIXED
 #define NSLOT 7            // per-barcode allele slots: 5 fixed + 2 dynamic
@@ -141,12 +162,14 @@ enum { KW_ALLELE_FWD = 0,   // alleleCnt | forwardCnt << 16
 #define K3_BQTAB_BYTES 2048                    // 256 doubles, shared by the block
 #define K3_SMEM_BYTES  (K3_BQTAB_BYTES + K3_WARPS * K3_WARP_WORDS * 4)
 
-// 16-bit event code written by pass A (simple reads only)
-#define EC_FIELD_SH 8u            // bits 8-9: A0 C1 T2 G3
+// 16-bit event code
+#define EC_FIELD_SH 8u            // bits 8-9: A0 C1 T2 G3 (regular A/C/G/T base)
 #define EC_COVERED  (1u << 10)
-#define EC_DYN      (1u << 11)    // base is not A/C/G/T (N / IUPAC): dynamic allele, the nibble is re-read in pass B
-#define EC_LE20     (1u << 12)    // distance to the barcode end <= 20 (R1: :434-441, R2: :443-452)
-#define EC_PLE      (1u << 13)    // R2 and distance to the primer end <= primerDist
+#define EC_DYN      (1u << 11)    // regular base that is not A/C/G/T (N / IUPAC): dynamic allele row
+#define EC_INC      (1u << 12)    // event passes incCond (:431): it enters bcDict
+#define EC_LE20     (1u << 13)    // distance to the barcode end <= 20
+#define EC_PLE      (1u << 14)    // R2 and distance to the primer end <= primerDist
+#define EC_REGULAR  (1u << 15)    // (slow path only) a plain base, not an indel start / in-deletion event
 
 struct K3Args {
     const ReadRec* recs; const uint32_t* ev_read; const uint32_t* tile_off; const uint32_t* unit_off;
@@ -165,36 +188,41 @@ struct K3Args {
     const int32_t* list_idx; uint32_t* list_count; const int64_t* list_off; uint64_t* list_umi; uint32_t* list_first; int64_t list_cap;
 };
 
+// The dynamic-allele table, passed BY VALUE to the out-of-line helpers (taking the address of the kernel parameter block
+// would copy all of it to local memory).
+struct DynTab {
+    unsigned long long* dkey; uint32_t dmask; uint32_t* drep_read; int32_t* drep_qpos; int32_t* dlen;
+    int32_t* dcnt; unsigned long long* dlimb; uint8_t* diskey; uint32_t* dcount; uint32_t* gflags;
+};
+__device__ __forceinline__ DynTab dyn_tab(const K3Args& A) {
+    DynTab T; T.dkey = A.dkey; T.dmask = A.dmask; T.drep_read = A.drep_read; T.drep_qpos = A.drep_qpos; T.dlen = A.dlen;
+    T.dcnt = A.dcnt; T.dlimb = A.dlimb; T.diskey = A.diskey; T.dcount = A.dcount; T.gflags = A.gflags;
+    return T;
+}
+
 // BAM nibble of A, C, G, T (1, 2, 4, 8) -> field A0 C1 T2 G3; fixed slot (A0 C1 T3 G4) = field + (field >> 1)
 __device__ __forceinline__ uint32_t nib_field(uint32_t nib) { return (0x20310u >> (2u * nib)) & 3u; }
 __device__ __forceinline__ bool nib_is_acgt(uint32_t nib) { return (0x0116u >> nib) & 1u; }
-__device__ __forceinline__ int nib_to_fixed(uint32_t nib) {
-    const uint32_t f = nib_field(nib);
-    return nib_is_acgt(nib) ? (int)(f + (f >> 1)) : -1;
-}
 
-// open-addressing table of the non-ACGT/DEL alleles; arguments by value so that the kernel parameter block never has
-// to be spilled to local memory for this (rare) call
-__device__ __noinline__ uint32_t dyn_lookup(unsigned long long* dkey, uint32_t dmask, uint32_t* drep_read, int32_t* drep_qpos,
-                                            int32_t* dlen, uint32_t* dcount, uint32_t* gflags, unsigned long long key,
-                                            uint32_t rep_read, int rep_qpos, int len) {
-    uint32_t h = hash64to32(key) & dmask;
-    for (uint32_t probe = 0; probe <= dmask; ++probe) {
-        unsigned long long cur = __ldcg(&dkey[h]);
+// open-addressing table of the non-ACGT/DEL alleles
+__device__ __noinline__ uint32_t dyn_lookup(DynTab T, unsigned long long key, uint32_t rep_read, int rep_qpos, int len) {
+    uint32_t h = hash64to32(key) & T.dmask;
+    for (uint32_t probe = 0; probe <= T.dmask; ++probe) {
+        unsigned long long cur = __ldcg(&T.dkey[h]);
         if (cur == key) return h;
         if (cur == DYN_EMPTY) {
-            unsigned long long prev = atomicCAS(&dkey[h], DYN_EMPTY, key);
+            unsigned long long prev = atomicCAS(&T.dkey[h], DYN_EMPTY, key);
             if (prev == DYN_EMPTY) {
-                drep_read[h] = rep_read; drep_qpos[h] = rep_qpos; dlen[h] = len;
-                uint32_t c = atomicAdd(dcount, 1u);
-                if (2ull * (c + 1ull) > (unsigned long long)dmask + 1ull) atomicOr(gflags, GF_DYN_FULL);
+                T.drep_read[h] = rep_read; T.drep_qpos[h] = rep_qpos; T.dlen[h] = len;
+                uint32_t c = atomicAdd(T.dcount, 1u);
+                if (2ull * (c + 1ull) > (unsigned long long)T.dmask + 1ull) atomicOr(T.gflags, GF_DYN_FULL);
                 return h;
             }
             if (prev == key) return h;
         }
-        h = (h + 1) & dmask;
+        h = (h + 1) & T.dmask;
     }
-    atomicOr(gflags, GF_DYN_FULL);
+    atomicOr(T.gflags, GF_DYN_FULL);
     return 0;
 }
 
@@ -231,7 +259,7 @@ struct LaneState {
     uint32_t keymask, status;
     unsigned long long pad_lo, pad_hi;      // PI terms that go to all of A, C, G, T (single-allele barcodes, see umi_finalize)
     // hot counters, 4 x 8-bit fields (A, C, T, G)
-    uint32_t r_allele, r_fwd, r_r1tot, r_r1le, r_r2tot, r_r2le;
+    uint32_t r_allele, r_fwd, r_lowq, r_r1tot, r_r1le, r_r2tot, r_r2le, r_r2ple, r_conc;
     // barcode-level
     int n; uint32_t exist; double Q, rightP; uint32_t last_aid; uint32_t udyn0, udyn1; int ndyn;
     bool umi_seen, umi_bc; uint32_t first_read;     // BAM index of the barcode's first passing read at this locus
@@ -246,10 +274,10 @@ struct LaneState {
 
 // counter update for an allele that may be dynamic: `word`/`add` address the packed shared-memory counter of a fixed
 // allele, c_lo / c_hi are the smc_out counter indices the low / high half stand for.
-__device__ __forceinline__ void bump(const K3Args& A, int* fc, int lane, uint32_t aid, int word, uint32_t add, int c_lo, int c_hi) {
+__device__ __forceinline__ void bump(int32_t* dcnt, int* fc, int lane, uint32_t aid, int word, uint32_t add, int c_lo, int c_hi) {
     if (aid < NF) FCW(word, aid) += (int)add;
     else {
-        int32_t* row = A.dcnt + (size_t)(aid - NF) * SMC_NCNT;
+        int32_t* row = dcnt + (size_t)(aid - NF) * SMC_NCNT;
         if (add & 0xffffu) atomicAdd(&row[c_lo], 1);
         if (add >> 16) atomicAdd(&row[c_hi], 1);
     }
@@ -263,21 +291,160 @@ __device__ __forceinline__ void flush_regs(int* fc, int lane, LaneState& S) {
         const uint32_t al = (S.r_allele >> (8 * f)) & 255u, fw = (S.r_fwd >> (8 * f)) & 255u;
         const uint32_t t1 = (S.r_r1tot >> (8 * f)) & 255u, l1 = (S.r_r1le >> (8 * f)) & 255u;
         const uint32_t t2 = (S.r_r2tot >> (8 * f)) & 255u, l2 = (S.r_r2le >> (8 * f)) & 255u;
+        const uint32_t lq = (S.r_lowq >> (8 * f)) & 255u, pl = (S.r_r2ple >> (8 * f)) & 255u;
+        const uint32_t cc = (S.r_conc >> (8 * f)) & 255u;
         if (al) FCW(KW_ALLELE_FWD, a) += (int)(al | (fw << 16));
         if (t1) FCW(KW_R1, a) += (int)(t1 | (l1 << 16));
         if (t2) FCW(KW_R2, a) += (int)(t2 | (l2 << 16));
+        if (lq | pl) FCW(KW_LOWQ_R2P, a) += (int)(lq | (pl << 16));
+        if (cc) FCW(KW_PAIR, a) += (int)cc;
     }
-    S.r_allele = S.r_fwd = S.r_r1tot = S.r_r1le = S.r_r2tot = S.r_r2le = 0;
+    S.r_allele = S.r_fwd = S.r_lowq = S.r_r1tot = S.r_r1le = S.r_r2tot = S.r_r2le = S.r_r2ple = S.r_conc = 0;
+}
+
+// order-independent tallies of a regular A/C/G/T event (smCounter.py:423-459) into the register counters
+__device__ __forceinline__ void tally_regular(LaneState& S, uint32_t one, uint32_t onei, bool reverse, bool read2, bool lowq, bool le20, bool ple) {
+    S.r_allele += one;                                               // :459
+    S.r_fwd += reverse ? 0u : one;                                   // :454-457
+    S.r_lowq += lowq ? one : 0u;                                     // :428-429
+    if (!read2) {                                                    // :432-441
+        S.r_r1tot += onei; S.r_r1le += le20 ? onei : 0u;
+    } else {                                                         // :442-452
+        S.r_r2tot += onei; S.r_r2le += le20 ? onei : 0u; S.r_r2ple += ple ? onei : 0u;
+    }
+}
+
+// Tallies of one pileup event whose base is not A/C/G/T (N / IUPAC, smCounter.py:423-457 with that key): rare, so it goes
+// straight to the dynamic-allele row with atomics.  Returns the row | (nibble == N) << 31.
+__device__ __noinline__ uint32_t dyn_base_event(DynTab T, const uint8_t* seq_read, uint32_t locus, uint32_t read_idx, int qpos,
+                                                uint32_t flags /* 1 fwd 2 lowq 4 inc 8 r2 16 le20 32 ple */) {
+    const uint32_t sb = __ldg(seq_read + (qpos >> 1));
+    const uint32_t nib = (qpos & 1) ? (sb & 15u) : (sb >> 4);
+    const uint32_t e = dyn_lookup(T, dyn_make_key(locus, SMC_K_BASE, nib, 0ull), read_idx, qpos, 0);
+    int32_t* row = T.dcnt + (size_t)e * SMC_NCNT;
+    atomicAdd(&row[SMC_C_ALLELE], 1);
+    if (flags & 1u) atomicAdd(&row[SMC_C_FWD], 1);
+    if (flags & 2u) atomicAdd(&row[SMC_C_LOWQ], 1);
+    if (flags & 4u) {
+        if (!(flags & 8u)) { atomicAdd(&row[SMC_C_R1TOT], 1); if (flags & 16u) atomicAdd(&row[SMC_C_R1LE], 1); }
+        else {
+            atomicAdd(&row[SMC_C_R2TOT], 1);
+            if (flags & 16u) atomicAdd(&row[SMC_C_R2LE], 1);
+            if (flags & 32u) atomicAdd(&row[SMC_C_R2PLE], 1);
+        }
+    }
+    return e | (nib == 15u ? 0x80000000u : 0u);
+}
+
+// Pileup event of a read that is NOT one plain aligned run (indels, hard clips, ...): htslib resolve_cigar2 for the
+// lane's position p, then the allele classification of smCounter.py:371-457.  Returns {event code, aid}:
+//   regular A/C/G/T base : code has EC_REGULAR and the field; the caller tallies it
+//   regular other base   : EC_REGULAR | EC_DYN, aid = query position (the caller calls dyn_base_event)
+//   inside a deletion    : aid = SMC_A_DEL, bq = minBQ (:416-421)
+//   insertion / deletion start (:371-411): aid = NF + row; alleleCnt and strand are tallied here
+__device__ __noinline__ uint2 slow_event(DynTab T, const uint32_t* rw /* staged ReadRec */, const uint32_t* __restrict__ cigar,
+                                         const uint8_t* __restrict__ seqp, const uint8_t* __restrict__ qualp, int32_t p, int32_t Li,
+                                         int minBQ, int primerDist) {
+    const uint32_t meta = rw[3];
+    const int32_t start = (int32_t)rw[0], lo = (int32_t)rw[1], hi = (int32_t)rw[2];
+    if (!(Li >= lo && Li < hi)) return make_uint2(0u, 0u);
+    const bool reverse = meta & RM_REVERSE, read2 = meta & RM_READ2;
+    const uint32_t ncig = meta >> 8;
+    const int leftSP = (int)(rw[4] & 0xffffu), alnlen = (int)(rw[4] >> 16);
+    const uint32_t seq_off = rw[5], qual_off = rw[6], cigar_off = rw[7];
+    int qpos = 0, indel = 0; bool isdel = false;
+    {
+        int x = start, y = 0;
+        for (uint32_t k = 0; k < ncig; ++k) {
+            const uint32_t cw = k < 4 ? rw[12 + k] : __ldg(&cigar[cigar_off + k]);
+            const uint32_t op = cw & 15u; const int len = (int)(cw >> 4);
+            if (op == 0 || op == 7 || op == 8 || op == 2 || op == 3) {
+                if (p < x + len) {                                           // the op that covers p
+                    isdel = (op == 2 || op == 3);
+                    qpos = isdel ? y : y + (p - x);
+                    if (p == x + len - 1 && k + 1 < ncig) {                   // peek the next op
+                        const uint32_t c2 = (k + 1) < 4 ? rw[12 + k + 1] : __ldg(&cigar[cigar_off + k + 1]);
+                        const uint32_t op2 = c2 & 15u; const int l2 = (int)(c2 >> 4);
+                        if (op2 == 2) indel = -l2;
+                        else if (op2 == 1) indel = l2;
+                        else if (op2 == 6 && k + 2 < ncig) {
+                            int l3 = 0;
+                            for (uint32_t kk = k + 2; kk < ncig; ++kk) {
+                                const uint32_t c3 = kk < 4 ? rw[12 + kk] : __ldg(&cigar[cigar_off + kk]);
+                                const uint32_t op3 = c3 & 15u;
+                                if (op3 == 1) l3 += (int)(c3 >> 4);
+                                else if (op3 == 2 || op3 == 0 || op3 == 3 || op3 == 7 || op3 == 8) break;
+                            }
+                            if (l3 > 0) indel = l3;
+                        }
+                    }
+                    break;
+                }
+                x += len;
+                if (op == 0 || op == 7 || op == 8) y += len;
+            } else if (op == 1 || op == 4) y += len;
+        }
+    }
+    if (indel == 0 && isdel) {                                                 // :416-421
+        const bool inc = (meta & RM_OK);                                       // bq = minBQ passes the quality gate
+        return make_uint2((uint32_t)minBQ | EC_COVERED | (inc ? EC_INC : 0u), (uint32_t)SMC_A_DEL);
+    }
+    const uint32_t sb = __ldg(seqp + ((size_t)seq_off + (size_t)(qpos >> 1)));
+    const uint32_t nib = (qpos & 1) ? (sb & 15u) : (sb >> 4);
+    const uint32_t bq = __ldg(qualp + ((size_t)qual_off + (size_t)qpos));
+    const bool lowq = (int)bq < minBQ;
+    const bool inc = !lowq && (meta & RM_OK);                                  // :378,400,431
+    uint32_t code = bq | EC_COVERED | (inc ? EC_INC : 0u);
+    if (indel == 0) {                                                          // :423-457 regular base
+        const int d = qpos - leftSP;
+        const int da = reverse ? alnlen - d : d, db = reverse ? d : alnlen - d;
+        if ((read2 ? db : da) <= 20) code |= EC_LE20;
+        if (read2 && da <= primerDist) code |= EC_PLE;
+        code |= EC_REGULAR;
+        if (nib_is_acgt(nib)) return make_uint2(code | (nib_field(nib) << EC_FIELD_SH), 0u);
+        return make_uint2(code | EC_DYN, (uint32_t)qpos);
+    }
+    // insertion start (:371-389) or deletion start (:392-411): alleleCnt and strand only
+    unsigned long long key; int len;
+    if (indel > 0) {
+        len = indel;
+        unsigned long long payload;
+        if (len <= 8) {
+            unsigned long long nibs = 0;
+            for (int t = 0; t < len; ++t) {
+                const int qq = qpos + 1 + t;
+                const uint32_t b2 = __ldg(seqp + ((size_t)seq_off + (size_t)(qq >> 1)));
+                nibs |= (unsigned long long)((qq & 1) ? (b2 & 15u) : (b2 >> 4)) << (28 - 4 * t);
+            }
+            payload = ((unsigned long long)len << 32) | nibs;
+        } else {
+            uint32_t hsh = 2166136261u ^ (uint32_t)len;
+            for (int t = 0; t < len; ++t) {
+                const int qq = qpos + 1 + t;
+                const uint32_t b2 = __ldg(seqp + ((size_t)seq_off + (size_t)(qq >> 1)));
+                hsh = (hsh ^ ((qq & 1) ? (b2 & 15u) : (b2 >> 4))) * 16777619u;
+            }
+            payload = (15ull << 32) | hsh;
+        }
+        key = dyn_make_key((uint32_t)Li, SMC_K_INS, nib, payload);
+    } else {
+        len = -indel;
+        key = dyn_make_key((uint32_t)Li, SMC_K_DEL, nib, (unsigned long long)len);
+    }
+    const uint32_t e = dyn_lookup(T, key, rw[10], qpos, len);
+    atomicAdd(&T.dcnt[(size_t)e * SMC_NCNT + SMC_C_ALLELE], 1);
+    if (!reverse) atomicAdd(&T.dcnt[(size_t)e * SMC_NCNT + SMC_C_FWD], 1);
+    return make_uint2(code, NF + e);
 }
 
 // first use of the per-barcode shared-memory arrays: a barcode that has shown a single allele so far keeps its state in
 // registers only (its product over fragments IS rightP, its count IS n)
-__device__ __forceinline__ void umi_materialize(int lane, int* ucnt, double* uprod, const LaneState& S) {
-    const int s0 = __ffs(S.exist) - 1;
-    UCNT(s0) = S.n; UPROD(s0) = S.rightP;
+__device__ __forceinline__ void umi_materialize(int lane, int* ucnt, double* uprod, uint32_t exist, int n, double rightP) {
+    const int s0 = __ffs(exist) - 1;
+    UCNT(s0) = n; UPROD(s0) = rightP;
 }
 
-__device__ __forceinline__ void fragment_finalize(const K3Args& A, const double* bqtab_s, int lane, int* ucnt, double* uprod, LaneState& S) {
+__device__ __forceinline__ void fragment_finalize(const double* bqtab_s, int lane, int* ucnt, double* uprod, LaneState& S) {
     if (S.frag_seen) { S.allFrag++; S.frag_seen = false; }
     if (!S.f_exists) return;
     S.f_exists = false;
@@ -298,7 +465,7 @@ __device__ __forceinline__ void fragment_finalize(const K3Args& A, const double*
     else {
         const bool multi = (S.exist & (S.exist - 1u)) != 0u;
         if (multi || S.exist != bit) {
-            if (!multi) umi_materialize(lane, ucnt, uprod, S);
+            if (!multi) umi_materialize(lane, ucnt, uprod, S.exist, S.n, S.rightP);
             if (!(S.exist & bit)) { S.exist |= bit; UCNT(slot) = 0; UPROD(slot) = S.Q; }
             uint32_t m = S.exist;
             while (m) {                                                  // :70-74
@@ -314,36 +481,104 @@ __device__ __forceinline__ void fragment_finalize(const K3Args& A, const double*
     S.last_aid = S.f_aid;
 }
 
-__device__ __forceinline__ void pi_add(const K3Args& A, int lane, ulonglong2* limb, LaneState& S, int slot, unsigned long long lo,
-                                       unsigned long long hi) {
-    if (slot < NF) {
-        ulonglong2 v = LIMB(slot);
-        add128(v.x, v.y, lo, hi);
-        LIMB(slot) = v;
-        S.keymask |= 1u << slot;
-    } else {
-        uint32_t e = slot == 5 ? S.udyn0 : S.udyn1;
-        unsigned long long a0, a1, a2;
-        split_limbs(lo, hi, a0, a1, a2);
-        if (a0) atomicAdd(&A.dlimb[(size_t)e * 3 + 0], a0);
-        if (a1) atomicAdd(&A.dlimb[(size_t)e * 3 + 1], a1);
-        if (a2) atomicAdd(&A.dlimb[(size_t)e * 3 + 2], a2);
-        A.diskey[e] = 1;
-    }
-}
-
 // PCR prior outside the host-built table (barcodes with > pcr_nmax fragments or > 6 distinct alleles): device pow()
 __device__ __noinline__ double pcr_slow(int cnt, double denom) {
     return pow(10.0, -6.0 * (((double)cnt + 0.5) / denom));
 }
 
-__device__ __forceinline__ uint32_t slot_to_aid(const LaneState& S, int slot) {
-    return slot < NF ? (uint32_t)slot : NF + (slot == 5 ? S.udyn0 : S.udyn1);
-}
-
 __device__ __forceinline__ double neg_log10_1m(double p) {              // smCounter.py:509-510
     const double x = 1.0 - p;
     return x > 0.0 ? -log10(x) : 16.0;
+}
+
+// calProb + consensus for a barcode that shows several alleles, a DEL / dynamic allele, or more fragments than the prior
+// table holds (smCounter.py:26-98, 506-523) -- the general form; the per-barcode arrays are in shared memory.
+// Returns the finalDict keys it touched among the fixed alleles.
+__device__ __noinline__ uint32_t umi_general(DynTab T, const double* __restrict__ pcrtab, int pcr_nmax, double smt, int lane, int n,
+                                             uint32_t exist, double rightP, int ndyn, uint32_t udyn0, uint32_t udyn1, uint32_t last_aid,
+                                             int* fc, ulonglong2* limb, int* ucnt, double* uprod) {
+    uint32_t keymask = 0;
+    // canonical order of the dynamic slots = ascending allele key
+    if (ndyn == 2 && __ldcg(&T.dkey[udyn0]) > __ldcg(&T.dkey[udyn1])) {
+        uint32_t t = udyn0; udyn0 = udyn1; udyn1 = t;
+        int c5 = UCNT(5), c6 = UCNT(6); double p5 = UPROD(5), p6 = UPROD(6);
+        uint32_t b5 = (exist >> 5) & 1u, b6 = (exist >> 6) & 1u;
+        UCNT(5) = c6; UCNT(6) = c5; UPROD(5) = p6; UPROD(6) = p5;
+        exist = (exist & 0x1fu) | (b6 << 5) | (b5 << 6);
+    }
+    int k = __popc(exist);
+    uint32_t pad = 0;                             // :49-54  pad with A, T, G, C until 4
+    if (k < 4 && !((exist >> SMC_A_A) & 1u)) { pad |= 1u << SMC_A_A; ++k; }
+    if (k < 4 && !((exist >> SMC_A_T) & 1u)) { pad |= 1u << SMC_A_T; ++k; }
+    if (k < 4 && !((exist >> SMC_A_G) & 1u)) { pad |= 1u << SMC_A_G; ++k; }
+    if (k < 4 && !((exist >> SMC_A_C) & 1u)) { pad |= 1u << SMC_A_C; ++k; }
+    const uint32_t uniq = exist | pad;
+    const double INF = __longlong_as_double(0x7ff0000000000000ll);
+    // ---- PCR prior of every allele of the barcode (:79-81): table lookups (host glibc pow) or pow()
+    const bool tab = (k <= 6 && n <= pcr_nmax);
+    const double* trow = pcrtab + ((size_t)(k - 4) * ((size_t)(pcr_nmax + 1) * (pcr_nmax + 2) / 2) + (size_t)n * (n + 1) / 2);
+    const double denom = (double)n + 0.5 * (double)k;
+    const double pcr_pad = tab ? __ldg(trow) : pcr_slow(0, denom);
+    double m1 = pad ? pcr_pad : INF, m2 = INF; int arg1 = -1;      // smallest / second smallest prior and its slot
+    double tpad = rightP;                                         // :88-91
+    for (uint32_t m = exist; m; m &= m - 1) {
+        const int s = __ffs(m) - 1;
+        const int c = UCNT(s);
+        const double v = tab ? __ldg(trow + c) : pcr_slow(c, denom);
+        tpad = __dmul_rn(tpad, v);
+        if (v < m1) { m2 = m1; m1 = v; arg1 = s; } else if (v < m2) m2 = v;
+    }
+    // ---- likelihood of each present allele (:86), stored over its (no longer needed) product; pads all share tpad
+    const double PCR_NO_ERROR = 1.0 - 3e-5;                       // smCounter.py:20
+    for (uint32_t m = exist; m; m &= m - 1) {
+        const int s = __ffs(m) - 1;
+        const double minp = (s == arg1) ? m2 : m1;                // min over the OTHER members of uniq
+        UPROD(s) = __dadd_rn(__dmul_rn(PCR_NO_ERROR, UPROD(s)), __dmul_rn(rightP, minp));
+    }
+    double sumP = 0.0;                                            // :93, in canonical slot order
+    for (uint32_t m = uniq; m; m &= m - 1) {
+        const int s = __ffs(m) - 1;
+        sumP = __dadd_rn(sumP, ((exist >> s) & 1u) ? UPROD(s) : tpad);
+    }
+    // ---- posterior -> -log10(1-p) (:96, :509-510), PI accumulation (:512), consensus (:514-523).
+    // One loop over the members of uniq in slot order; the pads share one value (computed at the first pad).
+    double best = -1.0, l_pad = 0.0; int nbest = 0, cons = -1; bool have_pad = false;
+    unsigned long long plo = 0, phi = 0;
+#pragma unroll 1
+    for (uint32_t m = uniq; m; m &= m - 1) {
+        const int s = __ffs(m) - 1;
+        const bool is_pad = (pad >> s) & 1u;
+        double l; unsigned long long lo, hi;
+        if (is_pad && have_pad) { l = l_pad; lo = plo; hi = phi; }
+        else {
+            l = neg_log10_1m(sumP <= 0.0 ? 0.0 : (is_pad ? tpad : UPROD(s)) / sumP);
+            pi_fixed128(l, lo, hi);
+            if (is_pad) { have_pad = true; l_pad = l; plo = lo; phi = hi; }
+        }
+        if (s < NF) {
+            ulonglong2 v = LIMB(s);
+            add128(v.x, v.y, lo, hi);
+            LIMB(s) = v;
+            keymask |= 1u << s;
+        } else {
+            const uint32_t e = s == 5 ? udyn0 : udyn1;
+            unsigned long long a0, a1, a2;
+            split_limbs(lo, hi, a0, a1, a2);
+            if (a0) atomicAdd(&T.dlimb[(size_t)e * 3 + 0], a0);
+            if (a1) atomicAdd(&T.dlimb[(size_t)e * 3 + 1], a1);
+            if (a2) atomicAdd(&T.dlimb[(size_t)e * 3 + 2], a2);
+            T.diskey[e] = 1;
+        }
+        if (l > best) { best = l; nbest = 1; cons = s; }
+        else if (l == best) nbest++;
+    }
+    if (nbest == 1) {                                             // :515-519
+        const uint32_t aid = cons < NF ? (uint32_t)cons : NF + (cons == 5 ? udyn0 : udyn1);
+        bump(T.dcnt, fc, lane, aid, KW_MT, best > smt ? 0x10001u : 1u, SMC_C_MT, SMC_C_STRONG);
+    } else if (n == 1) {                                          // :521-523
+        bump(T.dcnt, fc, lane, last_aid, KW_MT, 1u, SMC_C_MT, SMC_C_STRONG);
+    }
+    return keymask;
 }
 
 // calProb + the per-barcode part of vc() (smCounter.py:26-98, 506-532) for the lane's locus.
@@ -374,11 +609,11 @@ __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int ki, 
         const uint32_t ACGT = (1u << SMC_A_A) | (1u << SMC_A_T) | (1u << SMC_A_G) | (1u << SMC_A_C);
         if (n <= A.mtDrop) {                              // :28-32 -> four zeros, a 4-way tie (:514-523)
             S.keymask |= ACGT;
-            if (n == 1) bump(A, fc, lane, S.last_aid, KW_MT, 1u, SMC_C_MT, SMC_C_STRONG);
+            if (n == 1) bump(A.dcnt, fc, lane, S.last_aid, KW_MT, 1u, SMC_C_MT, SMC_C_STRONG);
         } else if (!multi && (S.exist & ACGT) && n <= A.pcr_nmax) {
             // ---- fast path: every fragment of the barcode shows the same base a0 in {A,C,G,T}; uniq = {A,C,G,T} (:49-54).
-            // Same operations in the same order as the general path below (prodP[a0] == rightP, one present allele,
-            // three pads sharing one value), with all intermediates in registers.
+            // Same operations in the same order as umi_general (prodP[a0] == rightP, one present allele, three pads
+            // sharing one value), with all intermediates in registers.
             const int a0 = __ffs(S.exist) - 1;
             const double rightP = S.rightP;
             const double* trow = A.pcrtab + (size_t)n * (n + 1) / 2;                       // k = 4
@@ -391,12 +626,17 @@ __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int ki, 
             sumP = __dadd_rn(sumP, posidx == 1 ? t_e : tpad);
             sumP = __dadd_rn(sumP, posidx == 2 ? t_e : tpad);
             sumP = __dadd_rn(sumP, posidx == 3 ? t_e : tpad);
-            const double l_pad = neg_log10_1m(sumP <= 0.0 ? 0.0 : tpad / sumP);
-            const double l_e = neg_log10_1m(sumP <= 0.0 ? 0.0 : t_e / sumP);
+            // -log10(1 - t/sumP) for the pads (it = 0) and for a0 (it = 1): one copy of the log10 code, run twice
+            double l_pad = 0.0, l_e = 0.0;
+            unsigned long long plo = 0, phi = 0, elo = 0, ehi = 0;
+#pragma unroll 1
+            for (int it = 0; it < 2; ++it) {
+                const double l = neg_log10_1m(sumP <= 0.0 ? 0.0 : (it ? t_e : tpad) / sumP);
+                unsigned long long lo, hi;
+                pi_fixed128(l, lo, hi);
+                if (it) { l_e = l; elo = lo; ehi = hi; } else { l_pad = l; plo = lo; phi = hi; }
+            }
             // PI: l_pad goes to all four bases through the register accumulator, a0 gets the difference (mod 2^128)
-            unsigned long long plo, phi, elo, ehi;
-            pi_fixed128(l_pad, plo, phi);
-            pi_fixed128(l_e, elo, ehi);
             add128(S.pad_lo, S.pad_hi, plo, phi);
             sub128(elo, ehi, plo, phi);
             ulonglong2 v = LIMB(a0);
@@ -407,74 +647,9 @@ __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int ki, 
             if (l_e > l_pad) FCW(KW_MT, a0) += (l_e > A.smt) ? 0x10001 : 1;
             else if (n == 1) FCW(KW_MT, a0) += 1;
         } else {
-            if (!multi) umi_materialize(lane, ucnt, uprod, S);
-            // canonical order of the dynamic slots = ascending allele key
-            if (S.ndyn == 2 && __ldcg(&A.dkey[S.udyn0]) > __ldcg(&A.dkey[S.udyn1])) {
-                uint32_t t = S.udyn0; S.udyn0 = S.udyn1; S.udyn1 = t;
-                int c5 = UCNT(5), c6 = UCNT(6); double p5 = UPROD(5), p6 = UPROD(6);
-                uint32_t b5 = (S.exist >> 5) & 1u, b6 = (S.exist >> 6) & 1u;
-                UCNT(5) = c6; UCNT(6) = c5; UPROD(5) = p6; UPROD(6) = p5;
-                S.exist = (S.exist & 0x1fu) | (b6 << 5) | (b5 << 6);
-            }
-            const uint32_t exist = S.exist;
-            int k = __popc(exist);
-            uint32_t pad = 0;                             // :49-54  pad with A, T, G, C until 4
-            if (k < 4 && !((exist >> SMC_A_A) & 1u)) { pad |= 1u << SMC_A_A; ++k; }
-            if (k < 4 && !((exist >> SMC_A_T) & 1u)) { pad |= 1u << SMC_A_T; ++k; }
-            if (k < 4 && !((exist >> SMC_A_G) & 1u)) { pad |= 1u << SMC_A_G; ++k; }
-            if (k < 4 && !((exist >> SMC_A_C) & 1u)) { pad |= 1u << SMC_A_C; ++k; }
-            const uint32_t uniq = exist | pad;
-            const double rightP = S.rightP;
-            const double INF = __longlong_as_double(0x7ff0000000000000ll);
-            // ---- PCR prior of every allele of the barcode (:79-81): table lookups (host glibc pow) or pow()
-            const bool tab = (k <= 6 && n <= A.pcr_nmax);
-            const double* trow = A.pcrtab + ((size_t)(k - 4) * ((size_t)(A.pcr_nmax + 1) * (A.pcr_nmax + 2) / 2) + (size_t)n * (n + 1) / 2);
-            const double denom = (double)n + 0.5 * (double)k;
-            const double pcr_pad = tab ? __ldg(trow) : pcr_slow(0, denom);
-            double m1 = pad ? pcr_pad : INF, m2 = INF; int arg1 = -1;      // smallest / second smallest prior and its slot
-            double tpad = rightP;                                         // :88-91
-            for (uint32_t m = exist; m; m &= m - 1) {
-                const int s = __ffs(m) - 1;
-                const int c = UCNT(s);
-                const double v = tab ? __ldg(trow + c) : pcr_slow(c, denom);
-                tpad = __dmul_rn(tpad, v);
-                if (v < m1) { m2 = m1; m1 = v; arg1 = s; } else if (v < m2) m2 = v;
-            }
-            // ---- likelihood of each present allele (:86), stored over its (no longer needed) product; pads all share tpad
-            const double PCR_NO_ERROR = 1.0 - 3e-5;                       // smCounter.py:20
-            for (uint32_t m = exist; m; m &= m - 1) {
-                const int s = __ffs(m) - 1;
-                const double minp = (s == arg1) ? m2 : m1;                // min over the OTHER members of uniq
-                UPROD(s) = __dadd_rn(__dmul_rn(PCR_NO_ERROR, UPROD(s)), __dmul_rn(rightP, minp));
-            }
-            double sumP = 0.0;                                            // :93, in canonical slot order
-            for (uint32_t m = uniq; m; m &= m - 1) {
-                const int s = __ffs(m) - 1;
-                sumP = __dadd_rn(sumP, ((exist >> s) & 1u) ? UPROD(s) : tpad);
-            }
-            // ---- posterior -> -log10(1-p) (:96, :509-510), PI accumulation (:512), consensus (:514-523)
-            double best = -1.0; int nbest = 0, cons = -1;
-            if (pad) {
-                const double l = neg_log10_1m(sumP <= 0.0 ? 0.0 : tpad / sumP);
-                unsigned long long lo, hi;
-                pi_fixed128(l, lo, hi);
-                for (uint32_t m = pad; m; m &= m - 1) pi_add(A, lane, limb, S, __ffs(m) - 1, lo, hi);
-                best = l; nbest = __popc(pad); cons = __ffs(pad) - 1;
-            }
-            for (uint32_t m = exist; m; m &= m - 1) {
-                const int s = __ffs(m) - 1;
-                const double l = neg_log10_1m(sumP <= 0.0 ? 0.0 : UPROD(s) / sumP);
-                unsigned long long lo, hi;
-                pi_fixed128(l, lo, hi);
-                pi_add(A, lane, limb, S, s, lo, hi);
-                if (l > best) { best = l; nbest = 1; cons = s; }
-                else if (l == best) nbest++;
-            }
-            if (nbest == 1) {                                             // :515-519
-                bump(A, fc, lane, slot_to_aid(S, cons), KW_MT, best > A.smt ? 0x10001u : 1u, SMC_C_MT, SMC_C_STRONG);
-            } else if (n == 1) {                                          // :521-523
-                bump(A, fc, lane, S.last_aid, KW_MT, 1u, SMC_C_MT, SMC_C_STRONG);
-            }
+            if (!multi) umi_materialize(lane, ucnt, uprod, S.exist, n, S.rightP);
+            S.keymask |= umi_general(dyn_tab(A), A.pcrtab, A.pcr_nmax, A.smt, lane, n, S.exist, S.rightP, S.ndyn, S.udyn0, S.udyn1,
+                                     S.last_aid, fc, limb, ucnt, uprod);
         }
     }
     S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.ndyn = 0; S.umi_seen = false; S.umi_bc = false; S.first_read = 0xffffffffu;
@@ -494,9 +669,7 @@ __device__ __forceinline__ uint32_t chunk_boundary(const K3Args& A, uint32_t x, 
 }
 
 // add the lane's packed shared-memory counters to the global 32-bit accumulators and clear them
-__device__ __forceinline__ void flush_counters(const K3Args& A, int* fc, int lane, int64_t L, bool lane_valid) {
-    if (!lane_valid) return;
-    const size_t nl = (size_t)A.n_loci;
+__device__ __noinline__ void flush_counters(int32_t* cnt, size_t nl, int* fc, int lane, int64_t L) {
     const int lo_idx[K3_NW] = {SMC_C_ALLELE, SMC_C_R1TOT, SMC_C_R2TOT, SMC_C_LOWQ, SMC_C_CONCORD, SMC_C_MT};
     const int hi_idx[K3_NW] = {SMC_C_FWD, SMC_C_R1LE, SMC_C_R2LE, SMC_C_R2PLE, SMC_C_DISCORD, SMC_C_STRONG};
 #pragma unroll
@@ -507,9 +680,9 @@ __device__ __forceinline__ void flush_counters(const K3Args& A, int* fc, int lan
             if (v) {
                 FCW(w, a) = 0;
                 const int lo = (int)(v & 0xffffu), hi = (int)(v >> 16);
-                if (lo) atomicAdd(&A.cnt[((size_t)a * SMC_NCNT + lo_idx[w]) * nl + L], lo);
-                if (hi) atomicAdd(&A.cnt[((size_t)a * SMC_NCNT + hi_idx[w]) * nl + L], hi);
-                if (w == KW_ALLELE_FWD && a != SMC_A_DEL && lo - hi) atomicAdd(&A.cnt[((size_t)a * SMC_NCNT + SMC_C_REV) * nl + L], lo - hi);
+                if (lo) atomicAdd(&cnt[((size_t)a * SMC_NCNT + lo_idx[w]) * nl + L], lo);
+                if (hi) atomicAdd(&cnt[((size_t)a * SMC_NCNT + hi_idx[w]) * nl + L], hi);
+                if (w == KW_ALLELE_FWD && a != SMC_A_DEL && lo - hi) atomicAdd(&cnt[((size_t)a * SMC_NCNT + SMC_C_REV) * nl + L], lo - hi);
             }
         }
     }
@@ -542,7 +715,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup_t(const 
     const int64_t L = (int64_t)tile * 32 + lane;
     const bool lane_valid = L < A.n_loci;
     const int32_t p = lane_valid ? A.loci_pos[L] : 0;
-    const int32_t Li = (int32_t)L;
+    const int32_t Li = lane_valid ? (int32_t)L : -1;                     // -1 is never inside a read's [lo, hi)
     const int ki = (lane_valid && A.keep_idx) ? A.keep_idx[L] : -1;
     const int li = (LIST && lane_valid) ? A.list_idx[L] : -1;
 
@@ -552,238 +725,147 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup_t(const 
     LaneState S;
     S.cvg = S.allFrag = S.allMT = S.usedFrag = S.nBC = S.usedMT = S.mt3 = S.mt5 = S.mt7 = S.mt10 = 0;
     S.keymask = 0; S.status = 0; S.pad_lo = S.pad_hi = 0;
-    S.r_allele = S.r_fwd = S.r_r1tot = S.r_r1le = S.r_r2tot = S.r_r2le = 0;
+    S.r_allele = S.r_fwd = S.r_lowq = S.r_r1tot = S.r_r1le = S.r_r2tot = S.r_r2le = S.r_r2ple = S.r_conc = 0;
     S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.last_aid = 0; S.udyn0 = S.udyn1 = 0; S.ndyn = 0;
     S.umi_seen = S.umi_bc = false; S.first_read = 0xffffffffu;
     S.frag_seen = S.f_exists = S.f_paired = false; S.f_aid = 0; S.f_bq = 0;
 
-    uint32_t prev_urank = 0xffffffffu, prev_frank = 0xffffffffu;
-    bool first = true;
-    const int minBQ = A.minBQ, primerDist = A.primerDist;
+    uint32_t carry_urank = 0xffffffffu, carry_frank = 0xffffffffu;       // barcode / fragment of the last read of the previous batch
+    const int minBQ = A.minBQ;
+    const uint8_t* __restrict__ seqp = A.seq;
+    const uint8_t* __restrict__ qualp = A.qual;
     uint32_t since_flush = 0, since_reg_flush = 0;
 
     for (uint32_t base = eb; base < ee; base += 32) {
         const int nb = (int)min(32u, ee - base);
-        {   // stage the next 32 read records in shared memory (4 x 128-bit loads per lane)
-            if (lane < nb) {
-                const uint4* src = reinterpret_cast<const uint4*>(&A.recs[A.ev_read[base + lane]]);
-                uint4* dst = reinterpret_cast<uint4*>(ws + lane * 16);
-                uint4 r0 = __ldg(src), r1 = __ldg(src + 1), r2 = __ldg(src + 2), r3 = __ldg(src + 3);
-                dst[0] = r0; dst[1] = r1; dst[2] = r2; dst[3] = r3;
-            }
+        // ---------------- stage the next 32 read records in shared memory (4 x 128-bit loads per lane); boundaries and
+        // per-read flags as warp-uniform bit masks
+        uint32_t my_urank = 0xfffffffdu, my_frank = 0xfffffffdu, my_meta = 0;
+        if (lane < nb) {
+            const uint4* src = reinterpret_cast<const uint4*>(&A.recs[A.ev_read[base + lane]]);
+            uint4* dst = reinterpret_cast<uint4*>(ws + lane * 16);
+            uint4 r0 = __ldg(src), r1 = __ldg(src + 1), r2 = __ldg(src + 2), r3 = __ldg(src + 3);
+            dst[0] = r0; dst[1] = r1; dst[2] = r2; dst[3] = r3;
+            my_urank = r2.x; my_frank = r2.y; my_meta = r0.w;
         }
+        uint32_t pu = __shfl_up_sync(FULL_MASK, my_urank, 1), pf = __shfl_up_sync(FULL_MASK, my_frank, 1);
+        if (lane == 0) { pu = carry_urank; pf = carry_frank; }
+        const bool first_ever = (base == eb) && lane == 0;               // nothing is open before the first read of the unit
+        const uint32_t valid = nb == 32 ? FULL_MASK : ((1u << nb) - 1u);
+        const uint32_t fragmask = __ballot_sync(FULL_MASK, my_frank != pf && !first_ever) & valid;
+        const uint32_t umimask = __ballot_sync(FULL_MASK, my_urank != pu && !first_ever) & valid;
+        const uint32_t simplemask = __ballot_sync(FULL_MASK, my_meta & RM_SIMPLE) & valid;
+        const uint32_t batch_prev_urank = carry_urank;                    // barcode that is open when this batch starts
+        carry_urank = __shfl_sync(FULL_MASK, my_urank, nb - 1); carry_frank = __shfl_sync(FULL_MASK, my_frank, nb - 1);
         since_flush += 32; since_reg_flush += 32;
         if (since_reg_flush > K3_REG_FLUSH) { flush_regs(fc, lane, S); since_reg_flush = 32; }
-        if (since_flush > K3_FLUSH_EVERY) { flush_regs(fc, lane, S); flush_counters(A, fc, lane, L, lane_valid); since_flush = 32; since_reg_flush = 32; }
+        if (since_flush > K3_FLUSH_EVERY) {
+            flush_regs(fc, lane, S);
+            if (lane_valid) flush_counters(A.cnt, (size_t)A.n_loci, fc, lane, L);
+            since_flush = 32; since_reg_flush = 32;
+        }
         __syncwarp();
-        // ---------------- pass A: gather base + quality of my locus for 8 reads at a time (simple reads only)
-        for (int g = 0; g < nb; g += 8) {
-            uint32_t sbv[8], bqv[8], cdv[8];
+        // ---------------- pass A: gather base + quality of my locus, K3_GATHER reads at a time, and tally (simple reads only)
+#pragma unroll 1
+        for (int g = 0; g < nb; g += K3_GATHER) {
+            uint32_t sbv[K3_GATHER], bqv[K3_GATHER], cdv[K3_GATHER];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < K3_GATHER; ++u) {
                 const uint32_t* rw = ws + (g + u) * 16;
                 const uint4 q0 = *reinterpret_cast<const uint4*>(rw);        // start lo hi meta
-                const uint4 q1 = *reinterpret_cast<const uint4*>(rw + 4);    // sp_aln seq_off qual_off cigar_off
-                const bool cov = (g + u < nb) && lane_valid && Li >= (int32_t)q0.y && Li < (int32_t)q0.z && (q0.w & RM_SIMPLE);
-                const int d = p - (int32_t)q0.x;                              // qpos - leftSP
-                const int qpos = (int)(q1.x & 0xffffu) + d;
-                const int alnlen = (int)(q1.x >> 16);
+                const uint4 q1 = *reinterpret_cast<const uint4*>(rw + 4);    // qk seq_off qual_off cigar_off
+                const uint4 q3 = *reinterpret_cast<const uint4*>(rw + 12);   // le_lo le_span ple_lo ple_span
+                const bool cov = (g + u < nb) && (uint32_t)(Li - (int32_t)q0.y) < (uint32_t)((int32_t)q0.z - (int32_t)q0.y) && (q0.w & RM_SIMPLE);
+                const int qpos = p + (int32_t)q1.x;
                 sbv[u] = 0; bqv[u] = 0;
                 if (cov) {
-                    sbv[u] = __ldg(&A.seq[(size_t)q1.y + (qpos >> 1)]);
-                    bqv[u] = __ldg(&A.qual[(size_t)q1.z + qpos]);
+                    sbv[u] = __ldg(seqp + ((size_t)q1.y + (size_t)(qpos >> 1)));
+                    bqv[u] = __ldg(qualp + ((size_t)q1.z + (size_t)qpos));
                 }
-                const bool rev = q0.w & RM_REVERSE, r2 = q0.w & RM_READ2;
-                const int da = rev ? alnlen - d : d, db = rev ? d : alnlen - d;   // R1: bc end = da; R2: bc end = db, primer end = da
-                const bool le20 = (r2 ? db : da) <= 20;
-                const bool ple = r2 && da <= primerDist;
-                cdv[u] = (cov ? EC_COVERED : 0u) | (le20 ? EC_LE20 : 0u) | (ple ? EC_PLE : 0u) | ((uint32_t)(qpos & 1) << 15);
+                const bool le20 = (uint32_t)(p - (int32_t)q3.x) <= q3.y;
+                const bool ple = (uint32_t)(p - (int32_t)q3.z) <= q3.w;
+                cdv[u] = (cov ? EC_COVERED : 0u) | (le20 ? EC_LE20 : 0u) | (ple ? EC_PLE : 0u) | ((uint32_t)(qpos & 1) << 15) | (q0.w << 16);
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t nib = (cdv[u] >> 15) ? (sbv[u] & 15u) : (sbv[u] >> 4);
-                uint32_t cd = (cdv[u] & 0x7fffu) | bqv[u] | (nib_field(nib) << EC_FIELD_SH);
-                if (!nib_is_acgt(nib)) cd |= EC_DYN;
-                codes[(g + u) * 32 + lane] = (uint16_t)cd;
+            for (int u = 0; u < K3_GATHER; ++u) {
+                const uint32_t cd = cdv[u];
+                const uint32_t meta = cd >> 16;                                  // RM_* bits (uniform)
+                const uint32_t nib = (cd & 0x8000u) ? (sbv[u] & 15u) : (sbv[u] >> 4);
+                const uint32_t bq = bqv[u];
+                const bool cov = cd & EC_COVERED;
+                const bool acgt = nib_is_acgt(nib);
+                const uint32_t f = nib_field(nib);
+                const bool lowq = (int)bq < minBQ;
+                const bool inc = cov && !lowq && (meta & RM_OK);                 // :431
+                const uint32_t one = (cov && acgt) ? (1u << (8u * f)) : 0u;
+                S.cvg += cov ? 1 : 0;                                            // :368
+                tally_regular(S, one, inc ? one : 0u, meta & RM_REVERSE, meta & RM_READ2, lowq, cd & EC_LE20, cd & EC_PLE);
+                codes[(g + u) * 32 + lane] = (uint16_t)(bq | (f << EC_FIELD_SH) | (cd & (EC_COVERED | EC_LE20 | EC_PLE)) |
+                                                        ((cov && !acgt) ? EC_DYN : 0u) | (inc ? EC_INC : 0u));
             }
         }
         __syncwarp();
-        // ---------------- pass B: the order-dependent reduction.  The last batch runs one extra (sentinel) iteration
-        // that only closes the open fragment and barcode.
-        const int cntj = nb + (base + 32 >= ee ? 1 : 0);
-        for (int j = 0; j < cntj; ++j) {
-            const bool sentinel = j >= nb;
-            const uint32_t* rw = ws + (j & 31) * 16;
-            const uint2 q2 = *reinterpret_cast<const uint2*>(rw + 8);    // urank frank
-            const uint32_t meta = rw[3];
-            const uint32_t urank = sentinel ? 0xfffffffeu : q2.x, frank = sentinel ? 0xfffffffeu : q2.y;
+        // ---------------- pass B: the order-dependent part
+#pragma unroll 1
+        for (int j = 0; j < nb; ++j) {
+            const uint32_t* rw = ws + j * 16;
             // ---- barcode / fragment boundaries (warp uniform)
-            if (!first) {
-                if (frank != prev_frank) fragment_finalize(A, bqtab_s, lane, ucnt, uprod, S);
-                if (urank != prev_urank) umi_finalize<LIST>(A, lane, ki, li, prev_urank, fc, limb, ucnt, uprod, S);
-            }
-            first = false; prev_urank = urank; prev_frank = frank;
-            if (sentinel) break;
-            const bool reverse = meta & RM_REVERSE, read2 = meta & RM_READ2;
-            bool covered, regular = false, isN = false, le20 = false, ple = false;
-            uint32_t aid = 0; int bq = 0;
-            if (meta & RM_SIMPLE) {                                        // warp uniform
-                const uint32_t cd = codes[j * 32 + lane];
-                covered = cd & EC_COVERED;
-                bq = (int)(cd & 255u); le20 = cd & EC_LE20; ple = cd & EC_PLE; regular = true;
+            if ((fragmask >> j) & 1u) fragment_finalize(bqtab_s, lane, ucnt, uprod, S);
+            if ((umimask >> j) & 1u) umi_finalize<LIST>(A, lane, ki, li, j ? rw[8 - 16] : batch_prev_urank, fc, limb, ucnt, uprod, S);
+            uint32_t cd, aid;
+            const bool simple = (simplemask >> j) & 1u;
+            if (simple) {
+                cd = codes[j * 32 + lane];
                 const uint32_t f = (cd >> EC_FIELD_SH) & 3u;
                 aid = f + (f >> 1);
-                if (covered && (cd & EC_DYN)) {                            // N / IUPAC base (:423-457 with a non-ACGT key)
-                    const int qpos = (int)(rw[4] & 0xffffu) + (p - (int32_t)rw[0]);
-                    const uint32_t sb = __ldg(&A.seq[(size_t)rw[5] + (qpos >> 1)]);
-                    const uint32_t nib = (qpos & 1) ? (sb & 15u) : (sb >> 4);
-                    const unsigned long long key = dyn_make_key((uint32_t)Li, SMC_K_BASE, nib, 0ull);
-                    const uint32_t e = dyn_lookup(A.dkey, A.dmask, A.drep_read, A.drep_qpos, A.dlen, A.dcount, A.gflags, key, rw[14], qpos, 0);
-                    aid = NF + e; isN = (nib == 15u);
-                    atomicAdd(&A.dcnt[(size_t)e * SMC_NCNT + SMC_C_ALLELE], 1);
-                    if (!reverse) atomicAdd(&A.dcnt[(size_t)e * SMC_NCNT + SMC_C_FWD], 1);
-                }
-            } else {
-                // ---- htslib resolve_cigar2: find the reference-consuming op that covers p
-                const int32_t start = (int32_t)rw[0], lo = (int32_t)rw[1], hi = (int32_t)rw[2];
-                covered = lane_valid && Li >= lo && Li < hi;
-                const uint32_t ncig = meta >> 8;
-                const int leftSP = (int)(rw[4] & 0xffffu), alnlen = (int)(rw[4] >> 16);
-                const uint32_t seq_off = rw[5], qual_off = rw[6], cigar_off = rw[7];
-                int qpos = 0, indel = 0; bool isdel = false;
-                {
-                    int x = start, y = 0; bool found = false;
-                    for (uint32_t k = 0; k < ncig; ++k) {
-                        uint32_t cw = k < 4 ? rw[10 + k] : __ldg(&A.cigar[cigar_off + k]);
-                        uint32_t op = cw & 15u; int len = (int)(cw >> 4);
-                        bool refop = (op == 0 || op == 7 || op == 8 || op == 2 || op == 3);
-                        if (refop) {
-                            if (covered && !found && p < x + len) {
-                                found = true;
-                                isdel = (op == 2 || op == 3);
-                                qpos = isdel ? y : y + (p - x);
-                                if (p == x + len - 1 && k + 1 < ncig) {       // peek the next op
-                                    uint32_t c2 = (k + 1) < 4 ? rw[10 + k + 1] : __ldg(&A.cigar[cigar_off + k + 1]);
-                                    uint32_t op2 = c2 & 15u; int l2 = (int)(c2 >> 4);
-                                    if (op2 == 2) indel = -l2;
-                                    else if (op2 == 1) indel = l2;
-                                    else if (op2 == 6 && k + 2 < ncig) {
-                                        int l3 = 0;
-                                        for (uint32_t kk = k + 2; kk < ncig; ++kk) {
-                                            uint32_t c3 = kk < 4 ? rw[10 + kk] : __ldg(&A.cigar[cigar_off + kk]);
-                                            uint32_t op3 = c3 & 15u;
-                                            if (op3 == 1) l3 += (int)(c3 >> 4);
-                                            else if (op3 == 2 || op3 == 0 || op3 == 3 || op3 == 7 || op3 == 8) break;
-                                        }
-                                        if (l3 > 0) indel = l3;
-                                    }
-                                }
-                            }
-                            x += len;
-                            if (op == 0 || op == 7 || op == 8) y += len;
-                        } else if (op == 1 || op == 4) y += len;
-                        if (__all_sync(FULL_MASK, found || !covered)) break;
-                    }
-                }
-                if (covered) {
-                    if (indel == 0 && isdel) {                                 // :416-421
-                        aid = SMC_A_DEL; bq = minBQ;
-                    } else {
-                        const uint32_t sb = __ldg(&A.seq[(size_t)seq_off + (qpos >> 1)]);
-                        const uint32_t nib = (qpos & 1) ? (sb & 15u) : (sb >> 4);
-                        bq = (int)__ldg(&A.qual[(size_t)qual_off + qpos]);
-                        const int fa = nib_to_fixed(nib);
-                        if (indel == 0 && fa >= 0) {                           // :423-457 regular base, A/C/G/T
-                            aid = (uint32_t)fa; regular = true;
-                        } else {
-                            // dynamic allele: N / IUPAC base, insertion start (:371-389) or deletion start (:392-411)
-                            unsigned long long key; int len = 0;
-                            if (indel > 0) {
-                                len = indel;
-                                unsigned long long payload;
-                                if (len <= 8) {
-                                    unsigned long long nibs = 0;
-                                    for (int t = 0; t < len; ++t) {
-                                        int qq = qpos + 1 + t;
-                                        uint32_t b2 = __ldg(&A.seq[(size_t)seq_off + (qq >> 1)]);
-                                        nibs |= (unsigned long long)((qq & 1) ? (b2 & 15u) : (b2 >> 4)) << (28 - 4 * t);
-                                    }
-                                    payload = ((unsigned long long)len << 32) | nibs;
-                                } else {
-                                    uint32_t hsh = 2166136261u ^ (uint32_t)len;
-                                    for (int t = 0; t < len; ++t) {
-                                        int qq = qpos + 1 + t;
-                                        uint32_t b2 = __ldg(&A.seq[(size_t)seq_off + (qq >> 1)]);
-                                        hsh = (hsh ^ ((qq & 1) ? (b2 & 15u) : (b2 >> 4))) * 16777619u;
-                                    }
-                                    payload = (15ull << 32) | hsh;
-                                }
-                                key = dyn_make_key((uint32_t)Li, SMC_K_INS, nib, payload);
-                            } else if (indel < 0) {
-                                len = -indel;
-                                key = dyn_make_key((uint32_t)Li, SMC_K_DEL, nib, (unsigned long long)len);
-                            } else {
-                                key = dyn_make_key((uint32_t)Li, SMC_K_BASE, nib, 0ull);
-                                regular = true; isN = (nib == 15u);
-                            }
-                            const uint32_t e = dyn_lookup(A.dkey, A.dmask, A.drep_read, A.drep_qpos, A.dlen, A.dcount, A.gflags, key, rw[14], qpos, len);
-                            aid = NF + e;
-                            atomicAdd(&A.dcnt[(size_t)e * SMC_NCNT + SMC_C_ALLELE], 1);
-                            if (!reverse) atomicAdd(&A.dcnt[(size_t)e * SMC_NCNT + SMC_C_FWD], 1);
-                        }
-                    }
-                    if (regular) {                                             // :432-452
-                        const int d = qpos - leftSP;
-                        const int da = reverse ? alnlen - d : d, db = reverse ? d : alnlen - d;
-                        le20 = (read2 ? db : da) <= 20;
-                        ple = read2 && da <= primerDist;
-                    }
+            } else {                                                             // rare: per-event CIGAR walk, out of line
+                const uint2 ev = slow_event(dyn_tab(A), rw, A.cigar, seqp, qualp, p, Li, minBQ, A.primerDist);
+                cd = ev.x; aid = ev.y;
+                if (cd & EC_COVERED) {
+                    S.cvg++;                                                     // :368
+                    if ((cd & EC_REGULAR) && !(cd & EC_DYN)) {
+                        const uint32_t f = (cd >> EC_FIELD_SH) & 3u;
+                        const uint32_t one = 1u << (8u * f);
+                        aid = f + (f >> 1);
+                        tally_regular(S, one, (cd & EC_INC) ? one : 0u, rw[3] & RM_REVERSE, rw[3] & RM_READ2, (int)(cd & 255u) < minBQ,
+                                      cd & EC_LE20, cd & EC_PLE);
+                    } else if (!(cd & EC_REGULAR) && aid == SMC_A_DEL) FCW(KW_ALLELE_FWD, SMC_A_DEL) += 1;   // alleleCnt only (:416-421, :459)
                 }
             }
-            if (covered) {
-                S.cvg++;                                                   // smCounter.py:368
-                const bool lowq = bq < minBQ;
-                const bool inc = !lowq && (meta & RM_OK);                  // :378,400,421,431
-                if (regular && aid < NF) {                                 // A/C/G/T: register counters
-                    const uint32_t one = 1u << (8u * (aid - (aid >> 1) + (aid >> 2)));   // slot 0,1,3,4 -> field 0,1,2,3
-                    S.r_allele += one;
-                    if (!reverse) S.r_fwd += one;
-                    if (lowq) FCW(KW_LOWQ_R2P, aid) += 1;                  // :428-429
-                    if (inc) {
-                        if (!read2) { S.r_r1tot += one; if (le20) S.r_r1le += one; }
-                        else { S.r_r2tot += one; if (le20) S.r_r2le += one; if (ple) FCW(KW_LOWQ_R2P, aid) += 0x10000; }
+            if (cd & EC_COVERED) { S.umi_seen = true; S.frag_seen = true; }      // :463-464
+            bool isN = false;
+            if (cd & EC_DYN) {                                                   // rare: N / IUPAC base -> dynamic allele row
+                const uint32_t meta = rw[3];
+                const int qpos = simple ? p + (int32_t)rw[4] : (int)aid;
+                const uint32_t fl = ((meta & RM_REVERSE) ? 0u : 1u) | ((int)(cd & 255u) < minBQ ? 2u : 0u) | ((cd & EC_INC) ? 4u : 0u) |
+                                    ((meta & RM_READ2) ? 8u : 0u) | ((cd & EC_LE20) ? 16u : 0u) | ((cd & EC_PLE) ? 32u : 0u);
+                const uint32_t e = dyn_base_event(dyn_tab(A), seqp + rw[5], (uint32_t)Li, rw[10], qpos, fl);
+                aid = NF + (e & 0x7fffffffu); isN = e >> 31;
+            }
+            if (cd & EC_INC) {                                                   // :467-479
+                const int bq = (int)(cd & 255u);
+                S.umi_bc = true;
+                if (LIST) S.first_read = min(S.first_read, rw[10]);
+                if (!S.f_exists) { S.f_exists = true; S.f_aid = aid; S.f_bq = bq; S.f_paired = false; }
+                else if (aid == S.f_aid || isN) {
+                    S.f_bq = min(S.f_bq, bq); S.f_paired = true;
+                    if (aid == S.f_aid) {
+                        if (aid < NF && aid != SMC_A_DEL) S.r_conc += 1u << (8u * (aid - (aid >> 1) + (aid >> 2)));   // slot 0,1,3,4 -> field
+                        else bump(A.dcnt, fc, lane, aid, KW_PAIR, 1u, SMC_C_CONCORD, SMC_C_DISCORD);
                     }
-                } else if (aid == SMC_A_DEL) {
-                    FCW(KW_ALLELE_FWD, SMC_A_DEL) += 1;                    // alleleCnt only (:416-421, :459)
-                } else if (regular) {                                      // N / IUPAC base: dynamic row, same tallies
-                    if (lowq) bump(A, fc, lane, aid, KW_LOWQ_R2P, 1u, SMC_C_LOWQ, SMC_C_R2PLE);
-                    if (inc) {
-                        if (!read2) bump(A, fc, lane, aid, KW_R1, le20 ? 0x10001u : 1u, SMC_C_R1TOT, SMC_C_R1LE);
-                        else {
-                            bump(A, fc, lane, aid, KW_R2, le20 ? 0x10001u : 1u, SMC_C_R2TOT, SMC_C_R2LE);
-                            if (ple) bump(A, fc, lane, aid, KW_LOWQ_R2P, 0x10000u, SMC_C_LOWQ, SMC_C_R2PLE);
-                        }
-                    }
-                }
-                S.umi_seen = true; S.frag_seen = true;                     // :463-464
-                if (inc) {                                                 // :467-479
-                    S.umi_bc = true;
-                    if (LIST) S.first_read = min(S.first_read, rw[14]);
-                    if (!S.f_exists) { S.f_exists = true; S.f_aid = aid; S.f_bq = bq; S.f_paired = false; }
-                    else if (aid == S.f_aid || isN) {
-                        S.f_bq = min(S.f_bq, bq); S.f_paired = true;
-                        if (aid == S.f_aid) bump(A, fc, lane, aid, KW_PAIR, 1u, SMC_C_CONCORD, SMC_C_DISCORD);
-                    } else { S.f_exists = false; bump(A, fc, lane, aid, KW_PAIR, 0x10000u, SMC_C_CONCORD, SMC_C_DISCORD); }
-                }
+                } else { S.f_exists = false; bump(A.dcnt, fc, lane, aid, KW_PAIR, 0x10000u, SMC_C_CONCORD, SMC_C_DISCORD); }
             }
         }
         __syncwarp();
     }
+    // ---- close the last fragment and barcode of the unit
+    fragment_finalize(bqtab_s, lane, ucnt, uprod, S);
+    umi_finalize<LIST>(A, lane, ki, li, carry_urank, fc, limb, ucnt, uprod, S);
     // ---- flush the lane's locus to the per-locus accumulators ([field][locus] layout: coalesced across lanes)
     flush_regs(fc, lane, S);
-    flush_counters(A, fc, lane, L, lane_valid);
     if (lane_valid) {
         const size_t nl = (size_t)A.n_loci;
+        flush_counters(A.cnt, nl, fc, lane, L);
 #pragma unroll
         for (int a = 0; a < NF; ++a) {
             ulonglong2 v = LIMB(a);
