@@ -16,21 +16,22 @@
 // (umi, frag_id, BAM index), so that every 32-locus tile sees barcodes and fragments as contiguous runs.
 // ----------------------------------------------------------------------------------------------------------
 struct __align__(16) ReadRec {
-    // word 0-3
-    int32_t  start;      // 0-based leftmost reference position
-    int32_t  lo, hi;     // covered target loci: indices [lo, hi) into the sorted locus list
-    uint32_t meta;       // bit0 passes MQ+mismatch gate, bit1 reverse, bit2 read2, bit3 single ref-consuming M run; bits 8.. n_cigar
-    // word 4-7
+    // word 0-3: everything the gather pass needs first
+    int32_t  lo;         // covered target loci: indices [lo, hi) into the sorted locus list
+    uint32_t gspan;      // simple reads: hi - lo; other reads: 0 (the gather pass never covers them)
     uint32_t sp_aln;     // simple reads: qk = leftSP - start (query position of locus position p is p + qk);
                          // other reads: leftSP (low 16) | query_alignment_length (high 16)
+    uint32_t meta;       // bit0 passes MQ+mismatch gate, bit1 reverse, bit2 read2, bit3 single ref-consuming M run; bits 8.. n_cigar
+    // word 4-7
     uint32_t seq_off;    // byte offset into seq[]
     uint32_t qual_off;   // byte offset into qual[]
-    uint32_t cigar_off;  // word offset into cigar[]
+    int32_t  start;      // 0-based leftmost reference position
+    int32_t  hi;
     // word 8-11
     uint32_t urank;      // dense rank of the barcode
     uint32_t frank;      // dense rank of the fragment
     uint32_t read_idx;   // index of the read in the caller's SoA (BAM order)
-    uint32_t pad;
+    uint32_t cigar_off;  // word offset into cigar[]
     // word 12-15
     uint32_t cig[4];     // simple reads: {le_lo, le_span, ple_lo, ple_span}: a base at position p is within 20 of the barcode end
                          // iff (uint32)(p - le_lo) <= le_span, within primerDist of the R2 primer end iff (uint32)(p - ple_lo) <= ple_span

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) k_read_prep(PrepArgs A) {
     rec.meta = (ok ? RM_OK : 0u) | (rev ? RM_REVERSE : 0u) | (r2 ? RM_READ2 : 0u) | (simple ? RM_SIMPLE : 0u) | (ncig << 8);
     rec.seq_off = (uint32_t)A.seq_off[r]; rec.qual_off = (uint32_t)A.qual_off[r]; rec.cigar_off = (uint32_t)co;
     rec.urank = A.urank[s]; rec.frank = A.frank[s];
-    rec.read_idx = r; rec.pad = 0;
+    rec.read_idx = r; rec.gspan = simple ? (uint32_t)(hi - lo) : 0u;
     if (simple) {
         // One aligned run: d = p - start is the distance from the alignment start, alnlen - d from its end.
         //   R1: distToBcEnd = rev ? alnlen - d : d;   R2: distToBcEnd = rev ? d : alnlen - d, distToPrimerEnd = rev ? alnlen - d : d
@@ -113,7 +113,7 @@ k_expand(const ReadRec* __restrict__ recs, const uint32_t* __restrict__ ev_off, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K3: tile pileup (v5)
+// K3: tile pileup (v6)
 //
 // A warp owns one unit = a run of <= `chunk` tile events of one 32-locus tile, cut at barcode boundaries; LANE = LOCUS.
 // It works in batches of 32 reads:
@@ -122,9 +122,9 @@ k_expand(const ReadRec* __restrict__ recs, const uint32_t* __restrict__ ev_off, 
 //   pass A  : "gather + tally" -- for each staged read every lane computes the query position of ITS locus, loads the
 //             base nibble and the quality, and adds the event to the order-independent tallies (cvg, alleleCnt,
 //             forward, lowQ, R1/R2 end-distance counts) held in registers as 4 x 8-bit fields (A, C, T, G) per word.
-//             The reads of a batch are independent, so the loads are issued 4 reads at a time (8 loads in flight per
-//             lane): this is where all the DRAM/L2 latency of the kernel is, and it is hidden by ILP plus the other
-//             warps' pass B.  What the ordered pass still needs is packed into a 16-bit event code in shared memory;
+//             The reads of a batch are independent, so the loads are issued K3_GATHER reads at a time: this is where
+//             all the DRAM/L2 latency of the kernel is, and it is hidden by ILP plus the other warps' pass B.
+//             What the ordered pass still needs is packed into a 16-bit event code in shared memory;
 //   pass B  : "merge" -- the order-dependent state machine (fragment merge :467-479, per-barcode posterior, consensus)
 //             walks the codes.  Register counters are spilled to the 16-bit shared-memory counters every 224 events;
 //             those go to the global 32-bit accumulators every 49 152 events and at the end of the unit.
@@ -159,17 +159,33 @@ enum { KW_ALLELE_FWD = 0,   // alleleCnt | forwardCnt << 16
 #define K3_UCNT_WORDS  (NSLOT * 32)
 #define K3_UPROD_WORDS (NSLOT * 64)
 #define K3_WARP_WORDS  (K3_STAGE_WORDS + K3_CODE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS + K3_UCNT_WORDS + K3_UPROD_WORDS)
-#define K3_BQTAB_BYTES 2048                    // 256 doubles, shared by the block
-#define K3_SMEM_BYTES  (K3_BQTAB_BYTES + K3_WARPS * K3_WARP_WORDS * 4)
+#define K3_TAB_BYTES   (2048 + 64)             // block-wide tables: 10^(-q/10) (256 doubles), nibble -> counter field increment
+#define K3_SMEM_BYTES  (K3_TAB_BYTES + K3_WARPS * K3_WARP_WORDS * 4)
 
-// 16-bit event code
-#define EC_FIELD_SH 8u            // bits 8-9: A0 C1 T2 G3 (regular A/C/G/T base)
-#define EC_COVERED  (1u << 10)
-#define EC_DYN      (1u << 11)    // regular base that is not A/C/G/T (N / IUPAC): dynamic allele row
-#define EC_INC      (1u << 12)    // event passes incCond (:431): it enters bcDict
-#define EC_LE20     (1u << 13)    // distance to the barcode end <= 20
-#define EC_PLE      (1u << 14)    // R2 and distance to the primer end <= primerDist
-#define EC_REGULAR  (1u << 15)    // (slow path only) a plain base, not an indel start / in-deletion event
+// event code: 16 bits from the gather pass (simple reads), a few more from the out-of-line CIGAR walk
+#define EC_NIB_SH   8u            // bits 8-11: BAM nibble of the base (regular events)
+#define EC_COVERED  (1u << 12)
+#define EC_DYN      (1u << 13)    // regular base that is not A/C/G/T (N / IUPAC): dynamic allele row
+#define EC_INC      (1u << 14)    // event passes incCond (:431): it enters bcDict
+#define EC_REGULAR  (1u << 15)    // (slow path) a plain base, not an indel start / in-deletion event
+#define EC_LE20     (1u << 16)    // (slow path) distance to the barcode end <= 20
+#define EC_PLE      (1u << 17)    // (slow path) R2 and distance to the primer end <= primerDist
+
+// Allele ids inside the merge state machine ("mid"): A/C/G/T = their BAM nibble (1, 2, 4, 8), in-deletion 'DEL' = 16,
+// dynamic row e = 32 + e.  Slots / smc_out allele references (A0 C1 DEL2 T3 G4, 5 + row) are derived once per fragment.
+#define MID_DEL 16u
+#define MID_DYN 32u
+__device__ __forceinline__ uint32_t mid_to_aid(uint32_t mid) {
+    if (mid >= MID_DYN) return NF + (mid - MID_DYN);
+    return mid == MID_DEL ? (uint32_t)SMC_A_DEL : ((0x3410u >> (4 * (__ffs(mid) - 1))) & 15u);   // nibble 1,2,4,8 -> slot 0,1,4,3
+}
+
+// per-lane flags
+#define LF_FRAG_SEEN EC_COVERED   // a read of the open fragment covers the locus (same bit as EC_COVERED: one OR per event)
+#define LF_UMI_SEEN  (1u << 0)
+#define LF_UMI_BC    (1u << 1)    // the open barcode is in bcDict (a read passed incCond)
+#define LF_F_EXISTS  (1u << 2)
+#define LF_F_PAIRED  (1u << 3)
 
 struct K3Args {
     const ReadRec* recs; const uint32_t* ev_read; const uint32_t* tile_off; const uint32_t* unit_off;
@@ -200,7 +216,7 @@ __device__ __forceinline__ DynTab dyn_tab(const K3Args& A) {
     return T;
 }
 
-// BAM nibble of A, C, G, T (1, 2, 4, 8) -> field A0 C1 T2 G3; fixed slot (A0 C1 T3 G4) = field + (field >> 1)
+// BAM nibble of A, C, G, T (1, 2, 4, 8) -> field A0 C1 T2 G3 of the packed register counters
 __device__ __forceinline__ uint32_t nib_field(uint32_t nib) { return (0x20310u >> (2u * nib)) & 3u; }
 __device__ __forceinline__ bool nib_is_acgt(uint32_t nib) { return (0x0116u >> nib) & 1u; }
 
@@ -260,11 +276,12 @@ struct LaneState {
     unsigned long long pad_lo, pad_hi;      // PI terms that go to all of A, C, G, T (single-allele barcodes, see umi_finalize)
     // hot counters, 4 x 8-bit fields (A, C, T, G)
     uint32_t r_allele, r_fwd, r_lowq, r_r1tot, r_r1le, r_r2tot, r_r2le, r_r2ple, r_conc;
+    uint32_t flags;                         // LF_*
     // barcode-level
     int n; uint32_t exist; double Q, rightP; uint32_t last_aid; uint32_t udyn0, udyn1; int ndyn;
-    bool umi_seen, umi_bc; uint32_t first_read;     // BAM index of the barcode's first passing read at this locus
+    uint32_t first_read;                    // BAM index of the barcode's first passing read at this locus (listing only)
     // fragment-level
-    bool frag_seen, f_exists, f_paired; uint32_t f_aid; int f_bq;
+    uint32_t f_mid; int f_bq;
 };
 
 #define FCW(w, a)   fc[((a) * K3_NW + (w)) * 32 + lane]
@@ -302,16 +319,16 @@ __device__ __forceinline__ void flush_regs(int* fc, int lane, LaneState& S) {
     S.r_allele = S.r_fwd = S.r_lowq = S.r_r1tot = S.r_r1le = S.r_r2tot = S.r_r2le = S.r_r2ple = S.r_conc = 0;
 }
 
-// order-independent tallies of a regular A/C/G/T event (smCounter.py:423-459) into the register counters
+// order-independent tallies of a regular A/C/G/T event (smCounter.py:423-459) into the register counters;
+// `one` = the field increment of the base (0 when the event does not count), `onei` = the same if it passes incCond
 __device__ __forceinline__ void tally_regular(LaneState& S, uint32_t one, uint32_t onei, bool reverse, bool read2, bool lowq, bool le20, bool ple) {
     S.r_allele += one;                                               // :459
-    S.r_fwd += reverse ? 0u : one;                                   // :454-457
-    S.r_lowq += lowq ? one : 0u;                                     // :428-429
-    if (!read2) {                                                    // :432-441
-        S.r_r1tot += onei; S.r_r1le += le20 ? onei : 0u;
-    } else {                                                         // :442-452
-        S.r_r2tot += onei; S.r_r2le += le20 ? onei : 0u; S.r_r2ple += ple ? onei : 0u;
-    }
+    if (!reverse) S.r_fwd += one;                                    // :454-457
+    if (lowq) S.r_lowq += one;                                       // :428-429
+    const uint32_t onel = le20 ? onei : 0u;
+    if (!read2) { S.r_r1tot += onei; S.r_r1le += onel; }             // :432-441
+    else { S.r_r2tot += onei; S.r_r2le += onel; }                    // :442-452
+    if (ple) S.r_r2ple += onei;                                      // the primer window of an R1 read is empty
 }
 
 // Tallies of one pileup event whose base is not A/C/G/T (N / IUPAC, smCounter.py:423-457 with that key): rare, so it goes
@@ -337,21 +354,20 @@ __device__ __noinline__ uint32_t dyn_base_event(DynTab T, const uint8_t* seq_rea
 }
 
 // Pileup event of a read that is NOT one plain aligned run (indels, hard clips, ...): htslib resolve_cigar2 for the
-// lane's position p, then the allele classification of smCounter.py:371-457.  Returns {event code, aid}:
-//   regular A/C/G/T base : code has EC_REGULAR and the field; the caller tallies it
-//   regular other base   : EC_REGULAR | EC_DYN, aid = query position (the caller calls dyn_base_event)
-//   inside a deletion    : aid = SMC_A_DEL, bq = minBQ (:416-421)
-//   insertion / deletion start (:371-411): aid = NF + row; alleleCnt and strand are tallied here
+// lane's position p, then the allele classification of smCounter.py:371-457.  Returns {event code, x}:
+//   regular base          : EC_REGULAR, nibble in the code (EC_DYN when it is not A/C/G/T; then x = query position)
+//   inside a deletion     : x = MID_DEL, bq = minBQ (:416-421)
+//   insertion / deletion start (:371-411): x = MID_DYN + row; alleleCnt and strand are tallied here
 __device__ __noinline__ uint2 slow_event(DynTab T, const uint32_t* rw /* staged ReadRec */, const uint32_t* __restrict__ cigar,
                                          const uint8_t* __restrict__ seqp, const uint8_t* __restrict__ qualp, int32_t p, int32_t Li,
                                          int minBQ, int primerDist) {
     const uint32_t meta = rw[3];
-    const int32_t start = (int32_t)rw[0], lo = (int32_t)rw[1], hi = (int32_t)rw[2];
+    const int32_t start = (int32_t)rw[6], lo = (int32_t)rw[0], hi = (int32_t)rw[7];
     if (!(Li >= lo && Li < hi)) return make_uint2(0u, 0u);
     const bool reverse = meta & RM_REVERSE, read2 = meta & RM_READ2;
     const uint32_t ncig = meta >> 8;
-    const int leftSP = (int)(rw[4] & 0xffffu), alnlen = (int)(rw[4] >> 16);
-    const uint32_t seq_off = rw[5], qual_off = rw[6], cigar_off = rw[7];
+    const int leftSP = (int)(rw[2] & 0xffffu), alnlen = (int)(rw[2] >> 16);
+    const uint32_t seq_off = rw[4], qual_off = rw[5], cigar_off = rw[11];
     int qpos = 0, indel = 0; bool isdel = false;
     {
         int x = start, y = 0;
@@ -387,21 +403,21 @@ __device__ __noinline__ uint2 slow_event(DynTab T, const uint32_t* rw /* staged 
     }
     if (indel == 0 && isdel) {                                                 // :416-421
         const bool inc = (meta & RM_OK);                                       // bq = minBQ passes the quality gate
-        return make_uint2((uint32_t)minBQ | EC_COVERED | (inc ? EC_INC : 0u), (uint32_t)SMC_A_DEL);
+        return make_uint2(((uint32_t)minBQ & 255u) | EC_COVERED | (inc ? EC_INC : 0u), MID_DEL);
     }
     const uint32_t sb = __ldg(seqp + ((size_t)seq_off + (size_t)(qpos >> 1)));
     const uint32_t nib = (qpos & 1) ? (sb & 15u) : (sb >> 4);
     const uint32_t bq = __ldg(qualp + ((size_t)qual_off + (size_t)qpos));
     const bool lowq = (int)bq < minBQ;
     const bool inc = !lowq && (meta & RM_OK);                                  // :378,400,431
-    uint32_t code = bq | EC_COVERED | (inc ? EC_INC : 0u);
+    uint32_t code = bq | (nib << EC_NIB_SH) | EC_COVERED | (inc ? EC_INC : 0u);
     if (indel == 0) {                                                          // :423-457 regular base
         const int d = qpos - leftSP;
         const int da = reverse ? alnlen - d : d, db = reverse ? d : alnlen - d;
         if ((read2 ? db : da) <= 20) code |= EC_LE20;
         if (read2 && da <= primerDist) code |= EC_PLE;
         code |= EC_REGULAR;
-        if (nib_is_acgt(nib)) return make_uint2(code | (nib_field(nib) << EC_FIELD_SH), 0u);
+        if (nib_is_acgt(nib)) return make_uint2(code, 0u);
         return make_uint2(code | EC_DYN, (uint32_t)qpos);
     }
     // insertion start (:371-389) or deletion start (:392-411): alleleCnt and strand only
@@ -434,7 +450,7 @@ __device__ __noinline__ uint2 slow_event(DynTab T, const uint32_t* rw /* staged 
     const uint32_t e = dyn_lookup(T, key, rw[10], qpos, len);
     atomicAdd(&T.dcnt[(size_t)e * SMC_NCNT + SMC_C_ALLELE], 1);
     if (!reverse) atomicAdd(&T.dcnt[(size_t)e * SMC_NCNT + SMC_C_FWD], 1);
-    return make_uint2(code, NF + e);
+    return make_uint2(code, MID_DYN + e);
 }
 
 // first use of the per-barcode shared-memory arrays: a barcode that has shown a single allele so far keeps its state in
@@ -445,20 +461,20 @@ __device__ __forceinline__ void umi_materialize(int lane, int* ucnt, double* upr
 }
 
 __device__ __forceinline__ void fragment_finalize(const double* bqtab_s, int lane, int* ucnt, double* uprod, LaneState& S) {
-    if (S.frag_seen) { S.allFrag++; S.frag_seen = false; }
-    if (!S.f_exists) return;
-    S.f_exists = false;
-    int slot;
-    if (S.f_aid < NF) slot = (int)S.f_aid;
-    else {
-        uint32_t e = S.f_aid - NF;
+    if (S.flags & LF_FRAG_SEEN) { S.allFrag++; S.flags = (S.flags & ~LF_FRAG_SEEN) | LF_UMI_SEEN; }      // :463-464
+    if (!(S.flags & LF_F_EXISTS)) return;
+    const double p = (S.flags & LF_F_PAIRED) ? bqtab_s[S.f_bq] : 0.1;  // smCounter.py:65-68
+    S.flags &= ~LF_F_EXISTS;
+    const uint32_t aid = mid_to_aid(S.f_mid);
+    int slot = (int)aid;
+    if (aid >= NF) {
+        const uint32_t e = aid - NF;
         if (S.ndyn > 0 && S.udyn0 == e) slot = 5;
         else if (S.ndyn > 1 && S.udyn1 == e) slot = 6;
         else if (S.ndyn == 0) { S.udyn0 = e; S.ndyn = 1; slot = 5; }
         else if (S.ndyn == 1) { S.udyn1 = e; S.ndyn = 2; slot = 6; }
         else { S.status |= SMC_ST_UMI_OVERFLOW; slot = 5; }
     }
-    const double p = S.f_paired ? bqtab_s[S.f_bq] : 0.1;             // smCounter.py:65-68
     const double q1 = 1.0 - p;
     const uint32_t bit = 1u << slot;
     if (S.exist == 0) S.exist = bit;
@@ -478,7 +494,7 @@ __device__ __forceinline__ void fragment_finalize(const double* bqtab_s, int lan
     S.Q = __dmul_rn(S.Q, p);
     S.rightP = __dmul_rn(S.rightP, q1);                              // :77
     S.n += 1;
-    S.last_aid = S.f_aid;
+    S.last_aid = aid;
 }
 
 // PCR prior outside the host-built table (barcodes with > pcr_nmax fragments or > 6 distinct alleles): device pow()
@@ -489,6 +505,21 @@ __device__ __noinline__ double pcr_slow(int cnt, double denom) {
 __device__ __forceinline__ double neg_log10_1m(double p) {              // smCounter.py:509-510
     const double x = 1.0 - p;
     return x > 0.0 ? -log10(x) : 16.0;
+}
+
+// -log10(x) for x = fl(1 - p) when p is tiny: with q = 1 - x (exact, Sterbenz) the series q + q^2/2 + ... + q^6/6 is within
+// 2e-16 relative of -ln(x) for q < 2^-10, so the result agrees with log10(x) to the last bit or two -- and it costs a
+// sixth of the library call.  (The posterior of a padded allele is ~1e-5: every barcode takes this branch once.)
+__device__ __forceinline__ double neg_log10_1m_small(double p) {
+    const double x = 1.0 - p;
+    const double q = 1.0 - x;
+    if (!(q < 0.0009765625)) return x > 0.0 ? -log10(x) : 16.0;
+    double s = fma(q, 1.0 / 6.0, 0.2);
+    s = fma(s, q, 0.25);
+    s = fma(s, q, 1.0 / 3.0);
+    s = fma(s, q, 0.5);
+    s = fma(s, q, 1.0);
+    return (s * q) * 0.43429448190325182765;             // 1 / ln(10)
 }
 
 // calProb + consensus for a barcode that shows several alleles, a DEL / dynamic allele, or more fragments than the prior
@@ -585,8 +616,8 @@ __device__ __noinline__ uint32_t umi_general(DynTab T, const double* __restrict_
 template <bool LIST>
 __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int ki, int li, uint32_t urank, int* fc, ulonglong2* limb,
                                              int* ucnt, double* uprod, LaneState& S) {
-    if (S.umi_seen) S.allMT++;
-    bool used = S.umi_bc;
+    if (S.flags & LF_UMI_SEEN) S.allMT++;
+    bool used = S.flags & LF_UMI_BC;
     if (used) {
         S.nBC++;
         if (ki >= 0) {                                   // down-sampling mask (smCounter.py:496-500)
@@ -626,17 +657,13 @@ __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int ki, 
             sumP = __dadd_rn(sumP, posidx == 1 ? t_e : tpad);
             sumP = __dadd_rn(sumP, posidx == 2 ? t_e : tpad);
             sumP = __dadd_rn(sumP, posidx == 3 ? t_e : tpad);
-            // -log10(1 - t/sumP) for the pads (it = 0) and for a0 (it = 1): one copy of the log10 code, run twice
-            double l_pad = 0.0, l_e = 0.0;
-            unsigned long long plo = 0, phi = 0, elo = 0, ehi = 0;
-#pragma unroll 1
-            for (int it = 0; it < 2; ++it) {
-                const double l = neg_log10_1m(sumP <= 0.0 ? 0.0 : (it ? t_e : tpad) / sumP);
-                unsigned long long lo, hi;
-                pi_fixed128(l, lo, hi);
-                if (it) { l_e = l; elo = lo; ehi = hi; } else { l_pad = l; plo = lo; phi = hi; }
-            }
+            const bool pos = sumP > 0.0;
+            const double l_pad = neg_log10_1m_small(pos ? tpad / sumP : 0.0);              // :96, :509-510
+            const double l_e = neg_log10_1m(pos ? t_e / sumP : 0.0);
             // PI: l_pad goes to all four bases through the register accumulator, a0 gets the difference (mod 2^128)
+            unsigned long long plo, phi, elo, ehi;
+            pi_fixed128(l_pad, plo, phi);
+            pi_fixed128(l_e, elo, ehi);
             add128(S.pad_lo, S.pad_hi, plo, phi);
             sub128(elo, ehi, plo, phi);
             ulonglong2 v = LIMB(a0);
@@ -652,7 +679,7 @@ __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int ki, 
                                      S.last_aid, fc, limb, ucnt, uprod);
         }
     }
-    S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.ndyn = 0; S.umi_seen = false; S.umi_bc = false; S.first_read = 0xffffffffu;
+    S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.ndyn = 0; S.flags &= ~(LF_UMI_SEEN | LF_UMI_BC); S.first_read = 0xffffffffu;
 }
 
 // first event index >= x (x > tb) at which the barcode changes, or te
@@ -692,10 +719,12 @@ template <bool LIST>
 __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup_t(const K3Args A) {
     extern __shared__ __align__(16) uint32_t smem[];
     double* bqtab_s = reinterpret_cast<double*>(smem);
+    uint32_t* one_lut = smem + 512;                                      // nibble -> 1 << 8 * field (0 for non-ACGT)
     for (int i = threadIdx.x; i < 256; i += K3_WARPS * 32) bqtab_s[i] = __ldg(&A.bqtab[i]);
+    if (threadIdx.x < 16) one_lut[threadIdx.x] = nib_is_acgt(threadIdx.x) ? (1u << (8u * nib_field(threadIdx.x))) : 0u;
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* ws = smem + K3_BQTAB_BYTES / 4 + (size_t)w * K3_WARP_WORDS;
+    uint32_t* ws = smem + K3_TAB_BYTES / 4 + (size_t)w * K3_WARP_WORDS;
     uint16_t* codes = reinterpret_cast<uint16_t*>(ws + K3_STAGE_WORDS);
     int* fc = (int*)(ws + K3_STAGE_WORDS + K3_CODE_WORDS);
     ulonglong2* limb = (ulonglong2*)(ws + K3_STAGE_WORDS + K3_CODE_WORDS + K3_FC_WORDS);
@@ -726,9 +755,10 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup_t(const 
     S.cvg = S.allFrag = S.allMT = S.usedFrag = S.nBC = S.usedMT = S.mt3 = S.mt5 = S.mt7 = S.mt10 = 0;
     S.keymask = 0; S.status = 0; S.pad_lo = S.pad_hi = 0;
     S.r_allele = S.r_fwd = S.r_lowq = S.r_r1tot = S.r_r1le = S.r_r2tot = S.r_r2le = S.r_r2ple = S.r_conc = 0;
+    S.flags = 0;
     S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.last_aid = 0; S.udyn0 = S.udyn1 = 0; S.ndyn = 0;
-    S.umi_seen = S.umi_bc = false; S.first_read = 0xffffffffu;
-    S.frag_seen = S.f_exists = S.f_paired = false; S.f_aid = 0; S.f_bq = 0;
+    S.first_read = 0xffffffffu;
+    S.f_mid = 0; S.f_bq = 0;
 
     uint32_t carry_urank = 0xffffffffu, carry_frank = 0xffffffffu;       // barcode / fragment of the last read of the previous batch
     const int minBQ = A.minBQ;
@@ -738,15 +768,18 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup_t(const 
 
     for (uint32_t base = eb; base < ee; base += 32) {
         const int nb = (int)min(32u, ee - base);
-        // ---------------- stage the next 32 read records in shared memory (4 x 128-bit loads per lane); boundaries and
-        // per-read flags as warp-uniform bit masks
+        // ---------------- stage the next 32 read records in shared memory (4 x 128-bit loads per lane; slots past the
+        // end of the unit get an empty record); boundaries and per-read flags as warp-uniform bit masks
         uint32_t my_urank = 0xfffffffdu, my_frank = 0xfffffffdu, my_meta = 0;
-        if (lane < nb) {
-            const uint4* src = reinterpret_cast<const uint4*>(&A.recs[A.ev_read[base + lane]]);
+        {
+            uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0, r2 = r0, r3 = r0;
+            if (lane < nb) {
+                const uint4* src = reinterpret_cast<const uint4*>(&A.recs[A.ev_read[base + lane]]);
+                r0 = __ldg(src); r1 = __ldg(src + 1); r2 = __ldg(src + 2); r3 = __ldg(src + 3);
+                my_urank = r2.x; my_frank = r2.y; my_meta = r0.w;
+            }
             uint4* dst = reinterpret_cast<uint4*>(ws + lane * 16);
-            uint4 r0 = __ldg(src), r1 = __ldg(src + 1), r2 = __ldg(src + 2), r3 = __ldg(src + 3);
             dst[0] = r0; dst[1] = r1; dst[2] = r2; dst[3] = r3;
-            my_urank = r2.x; my_frank = r2.y; my_meta = r0.w;
         }
         uint32_t pu = __shfl_up_sync(FULL_MASK, my_urank, 1), pf = __shfl_up_sync(FULL_MASK, my_frank, 1);
         if (lane == 0) { pu = carry_urank; pf = carry_frank; }
@@ -765,43 +798,42 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup_t(const 
             since_flush = 32; since_reg_flush = 32;
         }
         __syncwarp();
-        // ---------------- pass A: gather base + quality of my locus, K3_GATHER reads at a time, and tally (simple reads only)
+        // ---------------- pass A: gather base + quality of my locus, K3_GATHER reads at a time, and tally (simple reads only;
+        // the gather span of any other record is 0)
 #pragma unroll 1
         for (int g = 0; g < nb; g += K3_GATHER) {
-            uint32_t sbv[K3_GATHER], bqv[K3_GATHER], cdv[K3_GATHER];
+            uint32_t sbv[K3_GATHER], bqv[K3_GATHER], fl[K3_GATHER];
 #pragma unroll
             for (int u = 0; u < K3_GATHER; ++u) {
                 const uint32_t* rw = ws + (g + u) * 16;
-                const uint4 q0 = *reinterpret_cast<const uint4*>(rw);        // start lo hi meta
-                const uint4 q1 = *reinterpret_cast<const uint4*>(rw + 4);    // qk seq_off qual_off cigar_off
-                const uint4 q3 = *reinterpret_cast<const uint4*>(rw + 12);   // le_lo le_span ple_lo ple_span
-                const bool cov = (g + u < nb) && (uint32_t)(Li - (int32_t)q0.y) < (uint32_t)((int32_t)q0.z - (int32_t)q0.y) && (q0.w & RM_SIMPLE);
-                const int qpos = p + (int32_t)q1.x;
+                const uint4 qa = *reinterpret_cast<const uint4*>(rw);        // lo gspan qk meta
+                const uint2 qb = *reinterpret_cast<const uint2*>(rw + 4);    // seq_off qual_off
+                const uint4 qw = *reinterpret_cast<const uint4*>(rw + 12);   // le_lo le_span ple_lo ple_span
+                const bool cov = (uint32_t)(Li - (int32_t)qa.x) < qa.y;
+                const uint32_t qpos = (uint32_t)(p + (int32_t)qa.z);
                 sbv[u] = 0; bqv[u] = 0;
                 if (cov) {
-                    sbv[u] = __ldg(seqp + ((size_t)q1.y + (size_t)(qpos >> 1)));
-                    bqv[u] = __ldg(qualp + ((size_t)q1.z + (size_t)qpos));
+                    sbv[u] = __ldg(seqp + (qb.x + (qpos >> 1)));
+                    bqv[u] = __ldg(qualp + (qb.y + qpos));
                 }
-                const bool le20 = (uint32_t)(p - (int32_t)q3.x) <= q3.y;
-                const bool ple = (uint32_t)(p - (int32_t)q3.z) <= q3.w;
-                cdv[u] = (cov ? EC_COVERED : 0u) | (le20 ? EC_LE20 : 0u) | (ple ? EC_PLE : 0u) | ((uint32_t)(qpos & 1) << 15) | (q0.w << 16);
+                const bool le20 = (uint32_t)(p - (int32_t)qw.x) <= qw.y;
+                const bool ple = (uint32_t)(p - (int32_t)qw.z) <= qw.w;
+                // bits 0-3 RM_*, 4 covered, 5 le20, 6 ple, 7 odd query position
+                fl[u] = (qa.w & 15u) | (cov ? 16u : 0u) | (le20 ? 32u : 0u) | (ple ? 64u : 0u) | ((qpos & 1u) << 7);
             }
 #pragma unroll
             for (int u = 0; u < K3_GATHER; ++u) {
-                const uint32_t cd = cdv[u];
-                const uint32_t meta = cd >> 16;                                  // RM_* bits (uniform)
-                const uint32_t nib = (cd & 0x8000u) ? (sbv[u] & 15u) : (sbv[u] >> 4);
+                const uint32_t f = fl[u];
+                const uint32_t nib = (f & 128u) ? (sbv[u] & 15u) : (sbv[u] >> 4);   // 0 when not covered
                 const uint32_t bq = bqv[u];
-                const bool cov = cd & EC_COVERED;
-                const bool acgt = nib_is_acgt(nib);
-                const uint32_t f = nib_field(nib);
+                const bool cov = f & 16u;
+                const uint32_t one = one_lut[nib];                                   // 0 when not covered or not A/C/G/T
                 const bool lowq = (int)bq < minBQ;
-                const bool inc = cov && !lowq && (meta & RM_OK);                 // :431
-                const uint32_t one = (cov && acgt) ? (1u << (8u * f)) : 0u;
-                S.cvg += cov ? 1 : 0;                                            // :368
-                tally_regular(S, one, inc ? one : 0u, meta & RM_REVERSE, meta & RM_READ2, lowq, cd & EC_LE20, cd & EC_PLE);
-                codes[(g + u) * 32 + lane] = (uint16_t)(bq | (f << EC_FIELD_SH) | (cd & (EC_COVERED | EC_LE20 | EC_PLE)) |
-                                                        ((cov && !acgt) ? EC_DYN : 0u) | (inc ? EC_INC : 0u));
+                const bool inc = cov && !lowq && (f & RM_OK);                        // :431
+                S.cvg += cov ? 1 : 0;                                                // :368
+                tally_regular(S, one, inc ? one : 0u, f & RM_REVERSE, f & RM_READ2, lowq, f & 32u, f & 64u);
+                codes[(g + u) * 32 + lane] = (uint16_t)(bq | (nib << EC_NIB_SH) | (cov ? EC_COVERED : 0u) | ((cov && !one) ? EC_DYN : 0u) |
+                                                        (inc ? EC_INC : 0u));
             }
         }
         __syncwarp();
@@ -812,48 +844,48 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup_t(const 
             // ---- barcode / fragment boundaries (warp uniform)
             if ((fragmask >> j) & 1u) fragment_finalize(bqtab_s, lane, ucnt, uprod, S);
             if ((umimask >> j) & 1u) umi_finalize<LIST>(A, lane, ki, li, j ? rw[8 - 16] : batch_prev_urank, fc, limb, ucnt, uprod, S);
-            uint32_t cd, aid;
+            uint32_t cd, mid;
             const bool simple = (simplemask >> j) & 1u;
             if (simple) {
                 cd = codes[j * 32 + lane];
-                const uint32_t f = (cd >> EC_FIELD_SH) & 3u;
-                aid = f + (f >> 1);
+                mid = (cd >> EC_NIB_SH) & 15u;
             } else {                                                             // rare: per-event CIGAR walk, out of line
                 const uint2 ev = slow_event(dyn_tab(A), rw, A.cigar, seqp, qualp, p, Li, minBQ, A.primerDist);
-                cd = ev.x; aid = ev.y;
+                cd = ev.x; mid = ev.y;
                 if (cd & EC_COVERED) {
                     S.cvg++;                                                     // :368
                     if ((cd & EC_REGULAR) && !(cd & EC_DYN)) {
-                        const uint32_t f = (cd >> EC_FIELD_SH) & 3u;
-                        const uint32_t one = 1u << (8u * f);
-                        aid = f + (f >> 1);
+                        mid = (cd >> EC_NIB_SH) & 15u;
+                        const uint32_t one = one_lut[mid];
                         tally_regular(S, one, (cd & EC_INC) ? one : 0u, rw[3] & RM_REVERSE, rw[3] & RM_READ2, (int)(cd & 255u) < minBQ,
                                       cd & EC_LE20, cd & EC_PLE);
-                    } else if (!(cd & EC_REGULAR) && aid == SMC_A_DEL) FCW(KW_ALLELE_FWD, SMC_A_DEL) += 1;   // alleleCnt only (:416-421, :459)
+                    } else if (!(cd & EC_REGULAR) && mid == MID_DEL) FCW(KW_ALLELE_FWD, SMC_A_DEL) += 1;   // alleleCnt only (:416-421, :459)
                 }
             }
-            if (cd & EC_COVERED) { S.umi_seen = true; S.frag_seen = true; }      // :463-464
+            S.flags |= cd & EC_COVERED;                                          // LF_FRAG_SEEN (:463-464)
             bool isN = false;
             if (cd & EC_DYN) {                                                   // rare: N / IUPAC base -> dynamic allele row
                 const uint32_t meta = rw[3];
-                const int qpos = simple ? p + (int32_t)rw[4] : (int)aid;
+                const int qpos = simple ? p + (int32_t)rw[2] : (int)mid;
+                const bool le20 = simple ? (uint32_t)(p - (int32_t)rw[12]) <= rw[13] : (cd & EC_LE20) != 0u;
+                const bool ple = simple ? (uint32_t)(p - (int32_t)rw[14]) <= rw[15] : (cd & EC_PLE) != 0u;
                 const uint32_t fl = ((meta & RM_REVERSE) ? 0u : 1u) | ((int)(cd & 255u) < minBQ ? 2u : 0u) | ((cd & EC_INC) ? 4u : 0u) |
-                                    ((meta & RM_READ2) ? 8u : 0u) | ((cd & EC_LE20) ? 16u : 0u) | ((cd & EC_PLE) ? 32u : 0u);
-                const uint32_t e = dyn_base_event(dyn_tab(A), seqp + rw[5], (uint32_t)Li, rw[10], qpos, fl);
-                aid = NF + (e & 0x7fffffffu); isN = e >> 31;
+                                    ((meta & RM_READ2) ? 8u : 0u) | (le20 ? 16u : 0u) | (ple ? 32u : 0u);
+                const uint32_t e = dyn_base_event(dyn_tab(A), seqp + rw[4], (uint32_t)Li, rw[10], qpos, fl);
+                mid = MID_DYN + (e & 0x7fffffffu); isN = e >> 31;
             }
             if (cd & EC_INC) {                                                   // :467-479
                 const int bq = (int)(cd & 255u);
-                S.umi_bc = true;
+                S.flags |= LF_UMI_BC;
                 if (LIST) S.first_read = min(S.first_read, rw[10]);
-                if (!S.f_exists) { S.f_exists = true; S.f_aid = aid; S.f_bq = bq; S.f_paired = false; }
-                else if (aid == S.f_aid || isN) {
-                    S.f_bq = min(S.f_bq, bq); S.f_paired = true;
-                    if (aid == S.f_aid) {
-                        if (aid < NF && aid != SMC_A_DEL) S.r_conc += 1u << (8u * (aid - (aid >> 1) + (aid >> 2)));   // slot 0,1,3,4 -> field
-                        else bump(A.dcnt, fc, lane, aid, KW_PAIR, 1u, SMC_C_CONCORD, SMC_C_DISCORD);
+                if (!(S.flags & LF_F_EXISTS)) { S.flags = (S.flags | LF_F_EXISTS) & ~LF_F_PAIRED; S.f_mid = mid; S.f_bq = bq; }
+                else if (mid == S.f_mid || isN) {
+                    S.f_bq = min(S.f_bq, bq); S.flags |= LF_F_PAIRED;
+                    if (mid == S.f_mid) {
+                        if (mid < MID_DEL) S.r_conc += one_lut[mid];
+                        else bump(A.dcnt, fc, lane, mid_to_aid(mid), KW_PAIR, 1u, SMC_C_CONCORD, SMC_C_DISCORD);
                     }
-                } else { S.f_exists = false; bump(A.dcnt, fc, lane, aid, KW_PAIR, 0x10000u, SMC_C_CONCORD, SMC_C_DISCORD); }
+                } else { S.flags &= ~LF_F_EXISTS; bump(A.dcnt, fc, lane, mid_to_aid(mid), KW_PAIR, 0x10000u, SMC_C_CONCORD, SMC_C_DISCORD); }
             }
         }
         __syncwarp();
