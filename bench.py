@@ -271,6 +271,13 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         algo_bytes = ALGO_BYTES_PER_EVENT * float(tms["n_pileup_events"])
         kp_avg_s = (kp_ms / args.steps) / 1000.0
+        traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one k_pileup launch (ncu --set full, same batch)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "k_pileup_traffic.json")))
+            if int(tr["pileup_events"]) == int(tms["n_pileup_events"]):
+                traffic = int(tr["dram_bytes_read"]) + int(tr["dram_bytes_write"])
+        except Exception:
+            pass
         achieved = algo_bytes / kp_avg_s / 1e9 if kp_avg_s > 0 else 0.0
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1000.0 * dev_s_max / args.steps, "wall_ms_per_step": 1000.0 * wall_s_max / args.steps,
@@ -291,7 +298,7 @@ def main():
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                              "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_event": ALGO_BYTES_PER_EVENT,
-                             "ms_per_launch": 1000.0 * kp_avg_s, "traffic": None,
+                             "ms_per_launch": 1000.0 * kp_avg_s, "traffic": traffic,
                              "events_per_s": float(tms["n_pileup_events"]) / kp_avg_s if kp_avg_s > 0 else 0.0},
                 "clocks": sampler.summary(), "n_dyn_alleles_rank0": int(n_dyn), "n_fisher_rank0": int(tms["n_fisher"])}
     caller.close()

@@ -71,7 +71,7 @@ struct smc_ctx {
     // barcode listing
     DevBuf d_list_idx, d_list_count, d_list_off, d_list_umi, d_list_first;
     smc_timings tm{};
-    uint32_t chunk = 2048;
+    uint32_t chunk = 256;       // tile events per warp unit (A/B on B200: 64 -> 4.39 ms, 256 -> 3.37, 384 -> 3.37, 2048 -> 4.0, 4096 -> 4.3)
     const uint32_t* ev_read_sorted = nullptr;   // tile-sorted event -> srank map (lives in d_ev0 or d_ev1)
     uint32_t n_tiles = 0; int64_t n_tile_events = 0;
 };
