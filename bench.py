@@ -293,7 +293,7 @@ def main():
                         "d2h_bytes_per_step": int(e2e_tm["bytes_d2h"]), "ms_per_step": 1000.0 * e2e_s_max / args.steps,
                         "ms_h2d": e2e_tm["ms_h2d"], "ms_device": e2e_tm["ms_total_device"], "ms_d2h": e2e_tm["ms_d2h"]},
                 "gpu_launches": int(launches),
-                "stage_ms_rank0": {k: tms[k] for k in ("ms_prep", "ms_sort", "ms_pileup", "ms_stats", "ms_k_pileup")},
+                "stage_ms_rank0": {k: tms[k] for k in ("ms_prep", "ms_sort", "ms_pileup", "ms_stats", "ms_k_pileup", "ms_k_gather", "ms_k_merge")},
                 "roofline": {"bound": "hbm", "kernel": "k_pileup (fused event expansion + fragment merge + calProb + tallies)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",

@@ -207,10 +207,12 @@ typedef struct smc_out {
 /* CUDA-event timings and work counts of the last smc_run_resident() / smc_call_batch(). */
 typedef struct smc_timings {
     float   ms_h2d, ms_prep, ms_sort, ms_pileup, ms_stats, ms_d2h, ms_total_device;
-    float   ms_k_pileup;   /* the k_pileup launch alone (dominant kernel; roofline numerator / this) */
+    float   ms_k_pileup;   /* k_gather + k_merge (the pileup stage without its memsets) */
     int64_t n_reads, n_loci, n_tile_events, n_pileup_events /* sum of cvg */, n_umi_groups, n_dyn, n_fisher;
     int64_t bytes_h2d, bytes_d2h;
     int32_t kernel_launches;
+    float   ms_k_gather;   /* K3a alone: base/quality gather, read tallies, fragment merge (the HBM-facing kernel) */
+    float   ms_k_merge;    /* K3b alone: per-barcode posterior, prediction index, consensus (FP64) */
 } smc_timings;
 
 typedef struct smc_ctx smc_ctx;

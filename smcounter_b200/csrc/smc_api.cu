@@ -2,7 +2,8 @@
 //
 //   H2D -> K1 read prep (CIGAR walk, QC gate, locus range)        smc_pileup.cuh
 //       -> K2 segmented radix sort: reads by (barcode, fragment), tile events by tile   smc_sort.cuh
-//       -> K3 tile pileup: lane = locus, fragment merge, calProb, tallies              smc_pileup.cuh
+//       -> K3a k_gather: lane = locus, base/quality gather, read tallies, fragment merge smc_pileup.cuh
+//       -> K3b k_merge: per-barcode posterior (calProb), prediction index, consensus    smc_pileup.cuh
 //       -> K4 FP64 statistics: PI, ALT, filters, Fisher                                smc_stats.cuh
 //   -> D2H
 #include <cmath>
@@ -44,7 +45,7 @@ struct smc_ctx {
     smc_params prm{};
     std::string err;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev[10]{};
+    cudaEvent_t ev[12]{};
     // resident inputs
     int64_t n_reads = 0, n_loci = 0, n_keep_loci = 0, n_keep_umi = 0;
     int64_t seq_bytes = 0, qual_bytes = 0, n_cigar_words = 0;
@@ -57,7 +58,10 @@ struct smc_ctx {
     DevBuf d_bqtab, d_pcrtab;
     // scratch
     DevBuf d_k0, d_k1, d_v0, d_v1, d_hist, d_scan, d_flags32a, d_flags32b, d_urank, d_frank, d_umi_of_urank, d_recs, d_ntiles,
-        d_evoff, d_ek0, d_ek1, d_ev0, d_ev1, d_tile_off, d_unit_cnt, d_unit_off, d_small;
+        d_evoff, d_ek0, d_ek1, d_ev0, d_ev1, d_tile_off, d_unit_cnt, d_unit_off, d_small,
+        d_grec, d_ev_flags, d_unit_eb, d_unit_ee, d_unit_tile, d_unit_nfrag, d_codes, d_frag_first, d_umi_urank;
+    uint32_t code_mult = 1;                     // fragment-code storage per tile event (1, or 3 = worst case after GF_CODE_FULL)
+    uint32_t n_units_cap = 0;
     // per-locus accumulators / outputs
     DevBuf d_loc, d_cnt, d_limb, d_pi, d_max, d_second, d_alt, d_altpi, d_secondpi, d_fl1, d_fl2, d_bial, d_fp, d_for;
     // dynamic allele table + sorted rows
@@ -224,10 +228,14 @@ extern "C" int smc_ctx_create(int device, const smc_params* params, smc_ctx** ou
     if ((e = ctx->d_pcrtab.ensure(pcr.size() * 8)) != cudaSuccess) return fail("cudaMalloc", e);
     cudaMemcpy(ctx->d_bqtab.p, bq.data(), 256 * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(ctx->d_pcrtab.p, pcr.data(), pcr.size() * 8, cudaMemcpyHostToDevice);
-    if ((e = cudaFuncSetAttribute(k_pileup_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_BYTES)) != cudaSuccess)
-        return fail("cudaFuncSetAttribute(k_pileup)", e);
-    if ((e = cudaFuncSetAttribute(k_pileup_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_BYTES)) != cudaSuccess)
-        return fail("cudaFuncSetAttribute(k_pileup list)", e);
+    if ((e = cudaFuncSetAttribute(k_merge_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KB_SMEM_BYTES)) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(k_merge)", e);
+    if ((e = cudaFuncSetAttribute(k_merge_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KB_SMEM_BYTES)) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(k_merge list)", e);
+    if ((e = cudaFuncSetAttribute(k_gather_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KA_SMEM_BYTES(false))) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(k_gather)", e);
+    if ((e = cudaFuncSetAttribute(k_gather_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KA_SMEM_BYTES(true))) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(k_gather list)", e);
     if ((e = ctx->d_small.ensure(4096)) != cudaSuccess) return fail("cudaMalloc", e);
     *out = ctx;
     return SMC_OK;
@@ -243,7 +251,8 @@ extern "C" void smc_ctx_destroy(smc_ctx* ctx) {
                       &ctx->d_bqtab, &ctx->d_pcrtab, &ctx->d_k0, &ctx->d_k1, &ctx->d_v0, &ctx->d_v1, &ctx->d_hist, &ctx->d_scan,
                       &ctx->d_flags32a, &ctx->d_flags32b, &ctx->d_urank, &ctx->d_frank, &ctx->d_umi_of_urank, &ctx->d_recs, &ctx->d_ntiles,
                       &ctx->d_evoff, &ctx->d_ek0, &ctx->d_ek1, &ctx->d_ev0, &ctx->d_ev1, &ctx->d_tile_off, &ctx->d_unit_cnt,
-                      &ctx->d_unit_off, &ctx->d_small, &ctx->d_loc, &ctx->d_cnt, &ctx->d_limb, &ctx->d_pi, &ctx->d_max, &ctx->d_second,
+                      &ctx->d_unit_off, &ctx->d_small, &ctx->d_grec, &ctx->d_ev_flags, &ctx->d_unit_eb, &ctx->d_unit_ee, &ctx->d_unit_tile,
+                      &ctx->d_unit_nfrag, &ctx->d_codes, &ctx->d_frag_first, &ctx->d_umi_urank, &ctx->d_loc, &ctx->d_cnt, &ctx->d_limb, &ctx->d_pi, &ctx->d_max, &ctx->d_second,
                       &ctx->d_alt, &ctx->d_altpi, &ctx->d_secondpi, &ctx->d_fl1, &ctx->d_fl2, &ctx->d_bial, &ctx->d_fp, &ctx->d_for,
                       &ctx->d_dkey, &ctx->d_drep_read, &ctx->d_drep_qpos, &ctx->d_dlen, &ctx->d_dcnt, &ctx->d_dlimb, &ctx->d_diskey,
                       &ctx->d_lk0, &ctx->d_lk1, &ctx->d_lv0, &ctx->d_lv1, &ctx->d_s_key, &ctx->d_s_cnt, &ctx->d_s_limb, &ctx->d_s_iskey,
@@ -360,7 +369,8 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         LAUNCH(k_ranks, nblk(n, 256), 256, 0, uhead, fhead, uex, fex, ctx->d_umi.as<uint64_t>(), perm, n, uex, fex,
                ctx->d_umi_of_urank.as<uint64_t>());
         // ---------------- K1: per-read records in srank order
-        CK(ctx->d_recs.ensure((size_t)n * sizeof(ReadRec))); CK(ctx->d_ntiles.ensure((size_t)(n + 1) * 4));
+        CK(ctx->d_recs.ensure((size_t)n * sizeof(ReadRec))); CK(ctx->d_grec.ensure((size_t)n * sizeof(GRec)));
+        CK(ctx->d_ntiles.ensure((size_t)(n + 1) * 4));
         CK(ctx->d_evoff.ensure((size_t)(n + 1) * 4));
         CK(cudaMemsetAsync(small + 4, 0, 32, ctx->st));
         PrepArgs P{};
@@ -371,7 +381,7 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         P.n_cigar = ctx->d_ncig.as<uint16_t>(); P.cigar = ctx->d_cigar.as<uint32_t>();
         P.loci_key = ctx->d_loci_key.as<uint64_t>(); P.n_loci = nl;
         P.minMQ = ctx->prm.minMQ; P.primerDist = ctx->prm.primerDist; P.mismatchThr = ctx->prm.mismatchThr;
-        P.recs = ctx->d_recs.as<ReadRec>(); P.ntiles = ctx->d_ntiles.as<uint32_t>(); P.gflags = small + 5;
+        P.recs = ctx->d_recs.as<ReadRec>(); P.grec = ctx->d_grec.as<GRec>(); P.ntiles = ctx->d_ntiles.as<uint32_t>(); P.gflags = small + 5;
         LAUNCH(k_read_prep, nblk(n, 256), 256, 0, P);
         exclusive_scan_u32(ctx->d_ntiles.as<uint32_t>(), ctx->d_evoff.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + 4, ctx->st);
         uint32_t h[2];
@@ -400,6 +410,9 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         ev_key_sorted = res ? ctx->d_ek1.as<uint64_t>() : ctx->d_ek0.as<uint64_t>();
         ev_read_sorted = res ? ctx->d_ev1.as<uint32_t>() : ctx->d_ev0.as<uint32_t>();
         LAUNCH(k_tile_offsets, nblk((int64_t)n_tiles + 1, 256), 256, 0, ev_key_sorted, NE, n_tiles, ctx->d_tile_off.as<uint32_t>());
+        CK(ctx->d_ev_flags.ensure((size_t)NE));
+        LAUNCH(k_event_flags, nblk(NE, 256), 256, 0, ev_key_sorted, ev_read_sorted, ctx->d_urank.as<uint32_t>(), ctx->d_frank.as<uint32_t>(),
+               ctx->d_grec.as<GRec>(), NE, ctx->d_ev_flags.as<uint8_t>());
     } else {
         CK(cudaMemsetAsync(ctx->d_tile_off.p, 0, (size_t)(n_tiles + 2) * 4, ctx->st));
         CK(ctx->d_scan.ensure((size_t)scan_scratch_words((int64_t)n_tiles + 2) * 4 + 1024));
@@ -408,6 +421,15 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
            ctx->d_unit_cnt.as<uint32_t>());
     exclusive_scan_u32(ctx->d_unit_cnt.as<uint32_t>(), ctx->d_unit_off.as<uint32_t>(), (int64_t)n_tiles + 1, ctx->d_scan.as<uint32_t>(),
                        nullptr, ctx->st);
+    {   // unit geometry: [eb, ee) of every unit, cut at barcode boundaries
+        const int64_t max_units = (int64_t)n_tiles + NE / ctx->chunk + 1;
+        ctx->n_units_cap = (uint32_t)max_units;
+        CK(ctx->d_unit_eb.ensure((size_t)max_units * 4)); CK(ctx->d_unit_ee.ensure((size_t)max_units * 4));
+        CK(ctx->d_unit_tile.ensure((size_t)max_units * 4)); CK(ctx->d_unit_nfrag.ensure((size_t)max_units * 4));
+        LAUNCH(k_unit_bounds, nblk(max_units, 256), 256, 0, ctx->d_tile_off.as<uint32_t>(), ctx->d_unit_off.as<uint32_t>(), n_tiles, ctx->chunk,
+               ctx->d_ev_flags.as<uint8_t>(), ctx->d_unit_eb.as<uint32_t>(), ctx->d_unit_ee.as<uint32_t>(), ctx->d_unit_tile.as<uint32_t>(),
+               ctx->n_units_cap);
+    }
     ctx->tm.n_tile_events = NE;
     ctx->ev_read_sorted = ev_read_sorted;
     ctx->n_tiles = n_tiles; ctx->n_tile_events = NE;
@@ -417,24 +439,52 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
 }
 
 
-static void fill_k3args(smc_ctx* ctx, K3Args& A, uint32_t n_tiles) {
+static DynTab make_dyntab(smc_ctx* ctx) {
     uint32_t* small = ctx->d_small.as<uint32_t>();
-    const uint32_t cap = ctx->dyn_cap;
-    A.recs = ctx->d_recs.as<ReadRec>(); A.ev_read = ctx->ev_read_sorted; A.tile_off = ctx->d_tile_off.as<uint32_t>();
-    A.unit_off = ctx->d_unit_off.as<uint32_t>(); A.n_tiles = n_tiles; A.chunk = ctx->chunk;
+    DynTab T;
+    T.dkey = ctx->d_dkey.as<unsigned long long>(); T.dmask = ctx->dyn_cap - 1; T.drep_read = ctx->d_drep_read.as<uint32_t>();
+    T.drep_qpos = ctx->d_drep_qpos.as<int32_t>(); T.dlen = ctx->d_dlen.as<int32_t>(); T.dcnt = ctx->d_dcnt.as<int32_t>();
+    T.dlimb = ctx->d_dlimb.as<unsigned long long>(); T.diskey = ctx->d_diskey.as<uint8_t>(); T.dcount = small + 6; T.gflags = small + 5;
+    return T;
+}
+
+// Scratch of the K3a -> K3b hand-over: fragment codes (+ first-read indices when listing, + barcode ranks when a mask or a
+// listing needs the barcode of a closing run).
+static int ensure_code_storage(smc_ctx* ctx, bool list, bool need_uranks) {
+    const uint64_t slots = code_slots_total((uint64_t)ctx->n_tile_events, ctx->n_units_cap, ctx->code_mult);
+    CK(ctx->d_codes.ensure((size_t)slots * 64));
+    if (list) CK(ctx->d_frag_first.ensure((size_t)slots * 128));
+    if (need_uranks) CK(ctx->d_umi_urank.ensure((size_t)(ctx->n_tile_events + 1) * 4));
+    return SMC_OK;
+}
+
+static void fill_kargs(smc_ctx* ctx, KAArgs& A, KBArgs& B, bool list, bool need_uranks) {
+    A = KAArgs{}; B = KBArgs{};
+    A.grec = ctx->d_grec.as<GRec>(); A.recs = ctx->d_recs.as<ReadRec>(); A.ev_read = ctx->ev_read_sorted;
+    A.ev_flags = ctx->d_ev_flags.as<uint8_t>(); A.urank_s = ctx->d_urank.as<uint32_t>();
+    A.unit_eb = ctx->d_unit_eb.as<uint32_t>(); A.unit_ee = ctx->d_unit_ee.as<uint32_t>(); A.unit_tile = ctx->d_unit_tile.as<uint32_t>();
+    A.n_units = ctx->n_units_cap; A.code_mult = ctx->code_mult;
     A.loci_pos = ctx->d_loci_pos.as<int32_t>(); A.n_loci = ctx->n_loci;
     A.seq = ctx->d_seq.as<uint8_t>(); A.qual = ctx->d_qual.as<uint8_t>(); A.cigar = ctx->d_cigar.as<uint32_t>();
-    A.bqtab = ctx->d_bqtab.as<double>(); A.pcrtab = ctx->d_pcrtab.as<double>(); A.pcr_nmax = PCR_NMAX;
-    A.minBQ = ctx->prm.minBQ; A.mtDrop = ctx->prm.mtDrop; A.primerDist = ctx->prm.primerDist;
-    A.smt = ctx->prm.rpb < 1.5 ? 2.0 : ctx->prm.rpb < 3.0 ? 3.0 : 4.0;                     // smCounter.py:303-308
-    A.keep_idx = ctx->has_keep ? ctx->d_keep_idx.as<int32_t>() : nullptr;
-    A.keep_off = ctx->d_keep_off.as<int64_t>(); A.keep_umi = ctx->d_keep_umi.as<uint64_t>();
-    A.umi_of_urank = ctx->d_umi_of_urank.as<uint64_t>();
-    A.loc = ctx->d_loc.as<int32_t>(); A.cnt = ctx->d_cnt.as<int32_t>(); A.limb = ctx->d_limb.as<unsigned long long>();
-    A.dkey = ctx->d_dkey.as<unsigned long long>(); A.dmask = cap - 1; A.drep_read = ctx->d_drep_read.as<uint32_t>();
-    A.drep_qpos = ctx->d_drep_qpos.as<int32_t>(); A.dlen = ctx->d_dlen.as<int32_t>(); A.dcnt = ctx->d_dcnt.as<int32_t>();
-    A.dlimb = ctx->d_dlimb.as<unsigned long long>(); A.diskey = ctx->d_diskey.as<uint8_t>(); A.dcount = small + 6; A.gflags = small + 5;
-    A.list_idx = nullptr;
+    A.minBQ = ctx->prm.minBQ; A.primerDist = ctx->prm.primerDist;
+    A.codes = ctx->d_codes.as<uint4>(); A.unit_nfrag = ctx->d_unit_nfrag.as<uint32_t>();
+    A.frag_first = list ? ctx->d_frag_first.as<uint32_t>() : nullptr;
+    A.umi_urank = need_uranks ? ctx->d_umi_urank.as<uint32_t>() : nullptr;
+    A.loc = ctx->d_loc.as<int32_t>(); A.cnt = ctx->d_cnt.as<int32_t>();
+    A.T = make_dyntab(ctx);
+
+    B.codes = ctx->d_codes.as<uint4>(); B.unit_nfrag = ctx->d_unit_nfrag.as<uint32_t>(); B.frag_first = A.frag_first; B.umi_urank = A.umi_urank;
+    B.unit_eb = A.unit_eb; B.unit_ee = A.unit_ee; B.unit_tile = A.unit_tile; B.n_units = A.n_units; B.code_mult = A.code_mult;
+    B.n_loci = ctx->n_loci;
+    B.bqtab = ctx->d_bqtab.as<double>(); B.pcrtab = ctx->d_pcrtab.as<double>(); B.pcr_nmax = PCR_NMAX;
+    B.mtDrop = ctx->prm.mtDrop;
+    B.smt = ctx->prm.rpb < 1.5 ? 2.0 : ctx->prm.rpb < 3.0 ? 3.0 : 4.0;                     // smCounter.py:303-308
+    B.keep_idx = ctx->has_keep ? ctx->d_keep_idx.as<int32_t>() : nullptr;
+    B.keep_off = ctx->d_keep_off.as<int64_t>(); B.keep_umi = ctx->d_keep_umi.as<uint64_t>();
+    B.umi_of_urank = ctx->d_umi_of_urank.as<uint64_t>();
+    B.loc = ctx->d_loc.as<int32_t>(); B.cnt = ctx->d_cnt.as<int32_t>(); B.limb = ctx->d_limb.as<unsigned long long>();
+    B.T = A.T;
+    B.list_idx = nullptr;
 }
 
 static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
@@ -466,20 +516,26 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
         CK(cudaMemsetAsync(ctx->d_limb.p, 0, nlz * SMC_NFIXED * 3 * 8, ctx->st));
         CK(cudaMemsetAsync(small + 5, 0, 24, ctx->st));     // gflags, dyn count, n_tasks, cvg sum
         if (NE > 0) {
-            K3Args A{};
-            fill_k3args(ctx, A, n_tiles);
-            const int64_t max_units = (int64_t)n_tiles + NE / ctx->chunk + 1;
+            { int rc = ensure_code_storage(ctx, false, ctx->has_keep); if (rc) return rc; }
+            KAArgs A; KBArgs B;
+            fill_kargs(ctx, A, B, false, ctx->has_keep);
             CK(cudaEventRecord(ctx->ev[8], ctx->st));
-            LAUNCH(k_pileup_t<false>, nblk(max_units, K3_WARPS), K3_WARPS * 32, K3_SMEM_BYTES, A);
+            LAUNCH(k_gather_t<false>, nblk(ctx->n_units_cap, KA_WARPS), KA_WARPS * 32, KA_SMEM_BYTES(false), A);
             CK(cudaEventRecord(ctx->ev[9], ctx->st));
+            LAUNCH(k_merge_t<false>, nblk(ctx->n_units_cap, KB_WARPS), KB_WARPS * 32, KB_SMEM_BYTES, B);
+            CK(cudaEventRecord(ctx->ev[10], ctx->st));
         }
         uint32_t h[3];
         CK(cudaMemcpyAsync(h, small + 5, 12, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         CK(cudaGetLastError());
-        if (!(h[0] & GF_DYN_FULL)) { ctx->n_dyn = h[1]; break; }
-        if (ctx->dyn_cap >= (1u << 28) || attempt == 5) { ctx->err = "dynamic allele table overflow"; return SMC_E_OVERFLOW; }
-        ctx->dyn_cap <<= 2;
+        if (!(h[0] & (GF_DYN_FULL | GF_CODE_FULL))) { ctx->n_dyn = h[1]; break; }
+        if (attempt == 5) { ctx->err = "dynamic allele table / fragment code storage overflow"; return SMC_E_OVERFLOW; }
+        if (h[0] & GF_CODE_FULL) ctx->code_mult = 3;             // worst-case layout: always fits
+        if (h[0] & GF_DYN_FULL) {
+            if (ctx->dyn_cap >= (1u << 28)) { ctx->err = "dynamic allele table overflow"; return SMC_E_OVERFLOW; }
+            ctx->dyn_cap <<= 2;
+        }
     }
     CK(cudaEventRecord(ctx->ev[5], ctx->st));
     // ---------------- dynamic alleles -> sorted rows
@@ -545,8 +601,12 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
     cudaEventElapsedTime(&ctx->tm.ms_pileup, ctx->ev[4], ctx->ev[5]);
     cudaEventElapsedTime(&ctx->tm.ms_stats, ctx->ev[5], ctx->ev[6]);
     cudaEventElapsedTime(&ctx->tm.ms_total_device, ctx->ev[2], ctx->ev[6]);
-    ctx->tm.ms_k_pileup = 0.f;
-    if (NE > 0) cudaEventElapsedTime(&ctx->tm.ms_k_pileup, ctx->ev[8], ctx->ev[9]);
+    ctx->tm.ms_k_pileup = ctx->tm.ms_k_gather = ctx->tm.ms_k_merge = 0.f;
+    if (NE > 0) {
+        cudaEventElapsedTime(&ctx->tm.ms_k_pileup, ctx->ev[8], ctx->ev[10]);
+        cudaEventElapsedTime(&ctx->tm.ms_k_gather, ctx->ev[8], ctx->ev[9]);
+        cudaEventElapsedTime(&ctx->tm.ms_k_merge, ctx->ev[9], ctx->ev[10]);
+    }
     ctx->tm.n_pileup_events = (int64_t)cvgsum;
     ctx->tm.n_dyn = nd; ctx->tm.n_fisher = n_tasks_h;
     ctx->tm.kernel_launches = g_launches;
@@ -644,14 +704,15 @@ extern "C" int smc_list_barcodes(smc_ctx* ctx, int64_t n, const int64_t* locus, 
     // The listing pass re-runs the pileup kernel; it adds to the accumulators again, so the batch must be re-run
     // (with the mask) before the next download.
     ctx->ran = false;
-    K3Args A{};
-    fill_k3args(ctx, A, ctx->n_tiles);
-    A.keep_idx = nullptr;
-    A.list_idx = ctx->d_list_idx.as<int32_t>(); A.list_count = ctx->d_list_count.as<uint32_t>();
-    A.list_off = ctx->d_list_off.as<int64_t>(); A.list_umi = ctx->d_list_umi.as<uint64_t>();
-    A.list_first = ctx->d_list_first.as<uint32_t>(); A.list_cap = total;
-    const int64_t max_units = (int64_t)ctx->n_tiles + ctx->n_tile_events / ctx->chunk + 1;
-    LAUNCH(k_pileup_t<true>, nblk(max_units, K3_WARPS), K3_WARPS * 32, K3_SMEM_BYTES, A);
+    { int rc = ensure_code_storage(ctx, true, true); if (rc) return rc; }
+    KAArgs A; KBArgs B;
+    fill_kargs(ctx, A, B, true, true);
+    B.keep_idx = nullptr;
+    B.list_idx = ctx->d_list_idx.as<int32_t>(); B.list_count = ctx->d_list_count.as<uint32_t>();
+    B.list_off = ctx->d_list_off.as<int64_t>(); B.list_umi = ctx->d_list_umi.as<uint64_t>();
+    B.list_first = ctx->d_list_first.as<uint32_t>(); B.list_cap = total;
+    LAUNCH(k_gather_t<true>, nblk(ctx->n_units_cap, KA_WARPS), KA_WARPS * 32, KA_SMEM_BYTES(true), A);
+    LAUNCH(k_merge_t<true>, nblk(ctx->n_units_cap, KB_WARPS), KB_WARPS * 32, KB_SMEM_BYTES, B);
     CK(cudaMemcpyAsync(umi_out, ctx->d_list_umi.p, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(first_read_out, ctx->d_list_first.p, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));

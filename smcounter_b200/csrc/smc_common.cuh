@@ -39,6 +39,9 @@ struct __align__(16) ReadRec {
 };
 static_assert(sizeof(ReadRec) == 64, "ReadRec must be 64 bytes");
 
+// prediction-index accumulators: fixed point, LSB 2^-PI_FIX_LSB (k_merge adds, k_call rounds once)
+#define PI_FIX_LSB 80
+
 #define RM_OK      1u
 #define RM_REVERSE 2u
 #define RM_READ2   4u

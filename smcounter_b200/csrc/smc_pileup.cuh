@@ -1,11 +1,17 @@
-// K1 (read prep / CIGAR walk) and K3 (tile pileup + fragment merge + per-barcode posterior) kernels.
+// K1 (read prep / CIGAR walk) and K3 (tile pileup) kernels.
 //
-// Thread mapping of the pileup kernel ("the transpose"): one warp owns a tile of 32 consecutive target loci,
-// LANE = LOCUS.  The warp streams the tile's reads in (barcode, fragment, BAM index) order; every lane applies
-// the read to its own locus.  Barcode and fragment boundaries are therefore warp-uniform, every counter is
-// lane-private (no atomics in the loop), and the reference's order-dependent semantics (first read of a
-// fragment defines its base, discordant mates delete the fragment, a third read may recreate it --
-// smCounter.py:467-479) are reproduced by a plain per-lane state machine.
+// Thread mapping of the pileup kernels ("the transpose"): one warp owns a run of tile events of one tile of 32 consecutive
+// target loci, LANE = LOCUS.  The warp streams the tile's reads in (barcode, fragment, BAM index) order; every lane applies
+// the read to its own locus.  Barcode and fragment boundaries are therefore warp-uniform, every counter is lane-private
+// (no atomics in the loops), and the reference's order-dependent semantics (first read of a fragment defines its base,
+// discordant mates delete the fragment, a third read may recreate it -- smCounter.py:467-479) are reproduced by a plain
+// per-lane state machine.
+//
+// K3 is two kernels that meet at a 16-bit "fragment code" per (fragment, locus):
+//   k_gather  (K3a)  smCounter.py:368-479   pileup of every read event: base / quality gather, read-level tallies, fragment
+//                    merge.  No FP64, few registers, high occupancy: this is where all the DRAM / L2 latency of the path is.
+//   k_merge   (K3b)  smCounter.py:26-98, 482-532   per-barcode posterior (calProb), prediction index, consensus counters.
+//                    FP64 and 128-bit fixed point; its only input is the coalesced stream of fragment codes.
 #pragma once
 #include "smc_common.cuh"
 
@@ -14,6 +20,23 @@
 // Restates smCounter.py:327-356 (mapq, NM, nIndel, leftSP, mismatchPer100b) and the htslib column membership
 // pos <= p < reference_end, once per read instead of once per pileup event.
 // ------------------------------------------------------------------------------------------------------------
+
+// The 32 bytes of a read the gather loop needs (the 64-byte ReadRec keeps everything, for the rare paths).
+struct __align__(16) GRec {
+    int32_t  lo;         // first covered locus index
+    uint32_t gspan;      // simple reads: hi - lo; other reads: 0 (the gather loop never covers them)
+    uint32_t qk;         // leftSP - start: the query position of reference position p is p + qk
+    uint32_t meta;       // RM_* bits 0-3, GM_LE_INF, GM_PLE_INF
+    uint32_t seq_off, qual_off;
+    uint32_t le_lo;      // p is within 20 of the barcode end iff (uint32)(p - le_lo) <= (GM_LE_INF ? 2^31-1 : 20)        (:432-452)
+    uint32_t ple_lo;     // R2: p is within primerDist of the primer end iff (uint32)(p - ple_lo) <= (GM_PLE_INF ? 2^31-1 : primerDist)
+};
+static_assert(sizeof(GRec) == 32, "GRec must be 32 bytes");
+#define GM_LE_INF  16u
+#define GM_PLE_INF 32u
+#define WIN_EMPTY  0x7fffffffu
+#define WIN_INF    0x7fffffffu
+
 struct PrepArgs {
     int64_t n_reads;
     const uint32_t* perm;         // srank -> read index
@@ -24,11 +47,12 @@ struct PrepArgs {
     const uint16_t* n_cigar; const uint32_t* cigar;
     const uint64_t* loci_key; int64_t n_loci;
     int minMQ; int primerDist; double mismatchThr;
-    ReadRec* recs; uint32_t* ntiles; uint32_t* gflags;
+    ReadRec* recs; GRec* grec; uint32_t* ntiles; uint32_t* gflags;
 };
 
 #define GF_DYN_FULL   1u
 #define GF_BAD_READ   2u     // l_seq / clip length beyond the 16-bit record fields
+#define GF_CODE_FULL  4u     // a unit ran out of fragment-code storage (host retries with the worst-case layout)
 
 __global__ void __launch_bounds__(256) k_read_prep(PrepArgs A) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -75,26 +99,31 @@ __global__ void __launch_bounds__(256) k_read_prep(PrepArgs A) {
     rec.seq_off = (uint32_t)A.seq_off[r]; rec.qual_off = (uint32_t)A.qual_off[r]; rec.cigar_off = (uint32_t)co;
     rec.urank = A.urank[s]; rec.frank = A.frank[s];
     rec.read_idx = r; rec.gspan = simple ? (uint32_t)(hi - lo) : 0u;
+    rec.sp_aln = (uint32_t)leftSP | ((uint32_t)alnlen << 16);
+    rec.cig[0] = c4[0]; rec.cig[1] = c4[1]; rec.cig[2] = c4[2]; rec.cig[3] = c4[3];
+    GRec g;
+    g.lo = (int32_t)lo; g.gspan = rec.gspan; g.qk = (uint32_t)(leftSP - start); g.meta = rec.meta & 15u;
+    g.seq_off = rec.seq_off; g.qual_off = rec.qual_off; g.le_lo = WIN_EMPTY; g.ple_lo = WIN_EMPTY;
     if (simple) {
         // One aligned run: d = p - start is the distance from the alignment start, alnlen - d from its end.
         //   R1: distToBcEnd = rev ? alnlen - d : d;   R2: distToBcEnd = rev ? d : alnlen - d, distToPrimerEnd = rev ? alnlen - d : d
         // "<= X from the start" is the window [start, start + X], "<= X from the end" is [start + alnlen - X, inf).
-        rec.sp_aln = (uint32_t)(leftSP - start);
-        const uint32_t EMPTY_LO = 0x7fffffffu;
-        auto from_start = [&](int X, uint32_t& wlo, uint32_t& wspan) { if (X < 0) { wlo = EMPTY_LO; wspan = 0; } else { wlo = (uint32_t)start; wspan = (uint32_t)X; } };
-        auto from_end = [&](int X, uint32_t& wlo, uint32_t& wspan) { wlo = (uint32_t)(start + alnlen - X); wspan = 0x7fffffffu; };
         const bool bc_at_start = (r2 == rev);                 // R1 fwd / R2 rev measure the barcode end from the start
-        if (bc_at_start) from_start(20, rec.cig[0], rec.cig[1]); else from_end(20, rec.cig[0], rec.cig[1]);
-        if (!r2) { rec.cig[2] = EMPTY_LO; rec.cig[3] = 0; }
-        else if (rev) from_end(A.primerDist, rec.cig[2], rec.cig[3]);
-        else from_start(A.primerDist, rec.cig[2], rec.cig[3]);
-    } else {
-        rec.sp_aln = (uint32_t)leftSP | ((uint32_t)alnlen << 16);
-        rec.cig[0] = c4[0]; rec.cig[1] = c4[1]; rec.cig[2] = c4[2]; rec.cig[3] = c4[3];
+        if (bc_at_start) g.le_lo = (uint32_t)start;
+        else { g.le_lo = (uint32_t)(start + alnlen - 20); g.meta |= GM_LE_INF; }
+        if (r2) {
+            if (rev) { g.ple_lo = (uint32_t)(start + alnlen - A.primerDist); g.meta |= GM_PLE_INF; }
+            else if (A.primerDist >= 0) g.ple_lo = (uint32_t)start;
+        }
     }
-    const uint4* src = reinterpret_cast<const uint4*>(&rec);
-    uint4* dst = reinterpret_cast<uint4*>(&A.recs[s]);
-    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(&rec);
+        uint4* dst = reinterpret_cast<uint4*>(&A.recs[s]);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        const uint4* gs = reinterpret_cast<const uint4*>(&g);
+        uint4* gd = reinterpret_cast<uint4*>(&A.grec[s]);
+        gd[0] = gs[0]; gd[1] = gs[1];
+    }
     A.ntiles[s] = hi > lo ? (uint32_t)(((hi - 1) >> 5) - (lo >> 5) + 1) : 0u;
 }
 
@@ -112,111 +141,91 @@ k_expand(const ReadRec* __restrict__ recs, const uint32_t* __restrict__ ev_off, 
     for (uint32_t t = t0; t <= t1; ++t, ++o) { ev_key[o] = t; ev_val[o] = (uint32_t)s; }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// K3: tile pileup (v6)
-//
-// A warp owns one unit = a run of <= `chunk` tile events of one 32-locus tile, cut at barcode boundaries; LANE = LOCUS.
-// It works in batches of 32 reads:
-//   stage   : 32 ReadRec (64 B each, gathered through ev_read[]) -> shared memory, 4 x 128-bit loads per lane; barcode /
-//             fragment boundaries and "simple read" flags become warp-uniform bit masks (ballots);
-//   pass A  : "gather + tally" -- for each staged read every lane computes the query position of ITS locus, loads the
-//             base nibble and the quality, and adds the event to the order-independent tallies (cvg, alleleCnt,
-//             forward, lowQ, R1/R2 end-distance counts) held in registers as 4 x 8-bit fields (A, C, T, G) per word.
-//             The reads of a batch are independent, so the loads are issued K3_GATHER reads at a time: this is where
-//             all the DRAM/L2 latency of the kernel is, and it is hidden by ILP plus the other warps' pass B.
-//             What the ordered pass still needs is packed into a 16-bit event code in shared memory;
-//   pass B  : "merge" -- the order-dependent state machine (fragment merge :467-479, per-barcode posterior, consensus)
-//             walks the codes.  Register counters are spilled to the 16-bit shared-memory counters every 224 events;
-//             those go to the global 32-bit accumulators every 49 152 events and at the end of the unit.
-// Everything rare is out of line (__noinline__) so that the hot loop stays small in the instruction cache: reads with
-// indels / hard clips / several aligned runs (per-event CIGAR walk), non-ACGT bases, barcodes showing several alleles.
-// ------------------------------------------------------------------------------------------------------------
-#ifndef K3_WARPS
-#define K3_WARPS 4
-#endif
-#ifndef K3_MINBLOCKS
-#define K3_MINBLOCKS 4
-#endif
-#ifndef K3_GATHER
-#define K3_GATHER 4        // reads per gather group in pass A
-#endif
-#define NF SMC_NFIXED
-#define NSLOT 7            // per-barcode allele slots: 5 fixed + 2 dynamic
-// Per-lane shared-memory counters of the fixed alleles, two 16-bit counters per word:
-enum { KW_ALLELE_FWD = 0,   // alleleCnt | forwardCnt << 16
-       KW_R1,               // len(r1BcEndPos) | #<=20 << 16
-       KW_R2,               // len(r2BcEndPos) | #<=20 << 16
-       KW_LOWQ_R2P,         // lowQReads | #r2PrimerEndPos<=primerDist << 16
-       KW_PAIR,             // concordPairCnt | discordPairCnt << 16
-       KW_MT,               // MTCnt | strongMTCnt << 16
-       K3_NW };
-#define K3_FLUSH_EVERY 49152u      // tile events between shared -> global flushes (each event adds at most 1 to a field)
-#define K3_REG_FLUSH   224u        // tile events between register -> shared flushes (8-bit fields)
-#define K3_STAGE_WORDS 512                     // 32 ReadRec
-#define K3_CODE_WORDS  512                     // 32 x 32 event codes, 16 bit
-#define K3_FC_WORDS    (NF * K3_NW * 32)
-#define K3_LIMB_WORDS  (NF * 4 * 32)           // 128-bit fixed-point PI accumulator per fixed allele and lane
-#define K3_UCNT_WORDS  (NSLOT * 32)
-#define K3_UPROD_WORDS (NSLOT * 64)
-#define K3_WARP_WORDS  (K3_STAGE_WORDS + K3_CODE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS + K3_UCNT_WORDS + K3_UPROD_WORDS)
-#define K3_TAB_BYTES   (2048 + 64)             // block-wide tables: 10^(-q/10) (256 doubles), nibble -> counter field increment
-#define K3_SMEM_BYTES  (K3_TAB_BYTES + K3_WARPS * K3_WARP_WORDS * 4)
-
-// event code: 16 bits from the gather pass (simple reads), a few more from the out-of-line CIGAR walk
-#define EC_NIB_SH   8u            // bits 8-11: BAM nibble of the base (regular events)
-#define EC_COVERED  (1u << 12)
-#define EC_DYN      (1u << 13)    // regular base that is not A/C/G/T (N / IUPAC): dynamic allele row
-#define EC_INC      (1u << 14)    // event passes incCond (:431): it enters bcDict
-#define EC_REGULAR  (1u << 15)    // (slow path) a plain base, not an indel start / in-deletion event
-#define EC_LE20     (1u << 16)    // (slow path) distance to the barcode end <= 20
-#define EC_PLE      (1u << 17)    // (slow path) R2 and distance to the primer end <= primerDist
-
-// Allele ids inside the merge state machine ("mid"): A/C/G/T = their BAM nibble (1, 2, 4, 8), in-deletion 'DEL' = 16,
-// dynamic row e = 32 + e.  Slots / smc_out allele references (A0 C1 DEL2 T3 G4, 5 + row) are derived once per fragment.
-#define MID_DEL 16u
-#define MID_DYN 32u
-__device__ __forceinline__ uint32_t mid_to_aid(uint32_t mid) {
-    if (mid >= MID_DYN) return NF + (mid - MID_DYN);
-    return mid == MID_DEL ? (uint32_t)SMC_A_DEL : ((0x3410u >> (4 * (__ffs(mid) - 1))) & 15u);   // nibble 1,2,4,8 -> slot 0,1,4,3
+// Per tile event (tile-sorted): bit 0 a new fragment starts here, bit 1 a new barcode starts here (both set at the first
+// event of a tile), bit 2 the read is one plain aligned run.
+#define EF_FRAG   1u
+#define EF_UMI    2u
+#define EF_SIMPLE 4u
+__global__ void __launch_bounds__(256)
+k_event_flags(const uint64_t* __restrict__ ev_key, const uint32_t* __restrict__ ev_read, const uint32_t* __restrict__ urank,
+              const uint32_t* __restrict__ frank, const GRec* __restrict__ grec, int64_t ne, uint8_t* __restrict__ flags) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    const uint32_t sr = ev_read[e];
+    bool ub = true, fb = true;
+    if (e > 0 && ev_key[e - 1] == ev_key[e]) {
+        const uint32_t pr = ev_read[e - 1];
+        ub = urank[sr] != urank[pr];
+        fb = ub || frank[sr] != frank[pr];
+    }
+    flags[e] = (uint8_t)((fb ? EF_FRAG : 0u) | (ub ? EF_UMI : 0u) | ((__ldg(&grec[sr].meta) & RM_SIMPLE) ? EF_SIMPLE : 0u));
 }
 
-// per-lane flags
-#define LF_FRAG_SEEN EC_COVERED   // a read of the open fragment covers the locus (same bit as EC_COVERED: one OR per event)
-#define LF_UMI_SEEN  (1u << 0)
-#define LF_UMI_BC    (1u << 1)    // the open barcode is in bcDict (a read passed incCond)
-#define LF_F_EXISTS  (1u << 2)
-#define LF_F_PAIRED  (1u << 3)
+// Units: a tile's events are cut every `chunk` events, moved forward to the next barcode boundary.  One warp per unit.
+__global__ void __launch_bounds__(256)
+k_unit_bounds(const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ unit_off, uint32_t n_tiles, uint32_t chunk,
+              const uint8_t* __restrict__ flags, uint32_t* __restrict__ unit_eb, uint32_t* __restrict__ unit_ee,
+              uint32_t* __restrict__ unit_tile, uint32_t n_units_cap) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units_cap) return;
+    if (u >= unit_off[n_tiles]) { unit_eb[u] = unit_ee[u] = 0; unit_tile[u] = 0; return; }
+    const uint32_t tile = (uint32_t)upper_slot_u32(unit_off, (int64_t)n_tiles + 1, u);
+    const uint32_t c = u - unit_off[tile];
+    const uint32_t tb = tile_off[tile], te = tile_off[tile + 1];
+    auto boundary = [&](uint64_t x64) -> uint32_t {
+        if (x64 >= te) return te;
+        uint32_t x = (uint32_t)x64;
+        while (x < te && !(flags[x] & EF_UMI)) ++x;
+        return x;
+    };
+    const uint32_t eb = c == 0 ? tb : boundary((uint64_t)tb + (uint64_t)c * chunk);
+    const uint32_t ee = boundary((uint64_t)tb + (uint64_t)(c + 1) * chunk);
+    unit_eb[u] = eb; unit_ee[u] = ee; unit_tile[u] = tile;
+}
 
-struct K3Args {
-    const ReadRec* recs; const uint32_t* ev_read; const uint32_t* tile_off; const uint32_t* unit_off;
-    uint32_t n_tiles; uint32_t chunk;
-    const int32_t* loci_pos; int64_t n_loci;
-    const uint8_t* seq; const uint8_t* qual; const uint32_t* cigar;
-    const double* bqtab;            // [256]  10^(-bq/10), host glibc pow (smCounter.py:469)
-    const double* pcrtab;           // [3][(nmax+1)(nmax+2)/2]  10^(-6 (cnt+.5)/(n+.5k)), k = 4,5,6 (smCounter.py:80-81)
-    int pcr_nmax;
-    int minBQ, mtDrop, primerDist; double smt;
-    const int32_t* keep_idx; const int64_t* keep_off; const uint64_t* keep_umi; const uint64_t* umi_of_urank;
-    int32_t* loc; int32_t* cnt; unsigned long long* limb;
-    unsigned long long* dkey; uint32_t dmask; uint32_t* drep_read; int32_t* drep_qpos; int32_t* dlen;
-    int32_t* dcnt; unsigned long long* dlimb; uint8_t* diskey; uint32_t* dcount; uint32_t* gflags;
-    // optional: list the barcodes of bcDict for flagged loci (down-sampling support)
-    const int32_t* list_idx; uint32_t* list_count; const int64_t* list_off; uint64_t* list_umi; uint32_t* list_first; int64_t list_cap;
-};
+// ------------------------------------------------------------------------------------------------------------
+// Fragment codes: what k_gather hands to k_merge, 16 bits per (fragment, locus); a unit's codes are stored in groups of
+// eight per lane (one 128-bit word), so both kernels move them with fully coalesced 512-byte warp transactions.
+//   bits 0-7   effective base quality of the fragment (min over a concordant pair)
+//   bits 8-10  allele slot A0 C1 DEL2 T3 G4, or 7 = dynamic allele (its row is in the fragment's extension row)
+//   bits 11-12 0 no read of the fragment covers the locus; 1 covered (allBcDict, smCounter.py:463-464); 2 covered and a read
+//              passed incCond, but no fragment is left (the barcode is a key of bcDict all the same); 3 the fragment is in
+//              bcDict when it closes (:467-479)
+//   bit  13    ... and it is 'Paired'
+//   bit  14    an extension row belongs to this fragment (warp uniform)
+//   bit  15    first fragment of a barcode (warp uniform)
+// Storage of unit u (events [eb, ee), len = ee - eb): slots [base, base + cap), one slot = 32 lanes x 16 bit;
+// codes grow upward in groups of 8 slots, extension rows (32 lanes x u32 = 2 slots: dynamic-allele rows) grow downward.
+// With mult = 1 the codes always fit and there is room for (cap - codes) / 2 extension rows; a unit that needs more sets
+// GF_CODE_FULL and the host re-runs the batch with mult = 3, which always fits.
+// ------------------------------------------------------------------------------------------------------------
+#define FC_AID_SH   8u
+#define FC_AID_DYN  7u
+#define FC_ST_SH    11u
+#define FC_PAIRED   (1u << 13)
+#define FC_EXT      (1u << 14)
+#define FC_UMIFIRST (1u << 15)
 
-// The dynamic-allele table, passed BY VALUE to the out-of-line helpers (taking the address of the kernel parameter block
-// would copy all of it to local memory).
+__host__ __device__ inline uint64_t unit_slot_base(uint32_t eb, uint32_t u, uint32_t mult) {
+    return 8ull * (((uint64_t)mult * eb + 7ull) / 8ull + 3ull * u);
+}
+__host__ __device__ inline uint32_t unit_slot_cap(uint32_t len, uint32_t mult) {
+    return (uint32_t)(8ull * (((uint64_t)mult * len) / 8ull + 2ull));
+}
+static inline uint64_t code_slots_total(uint64_t ne, uint64_t n_units, uint32_t mult) {
+    return 8ull * ((mult * ne + 7ull) / 8ull + 3ull * (n_units + 1ull)) + 16ull;
+}
+
+#define NF SMC_NFIXED
+#define NSLOT 7            // per-barcode allele slots: 5 fixed + 2 dynamic
+
+// The dynamic-allele table, passed BY VALUE to the out-of-line helpers.
 struct DynTab {
     unsigned long long* dkey; uint32_t dmask; uint32_t* drep_read; int32_t* drep_qpos; int32_t* dlen;
     int32_t* dcnt; unsigned long long* dlimb; uint8_t* diskey; uint32_t* dcount; uint32_t* gflags;
 };
-__device__ __forceinline__ DynTab dyn_tab(const K3Args& A) {
-    DynTab T; T.dkey = A.dkey; T.dmask = A.dmask; T.drep_read = A.drep_read; T.drep_qpos = A.drep_qpos; T.dlen = A.dlen;
-    T.dcnt = A.dcnt; T.dlimb = A.dlimb; T.diskey = A.diskey; T.dcount = A.dcount; T.gflags = A.gflags;
-    return T;
-}
 
-// BAM nibble of A, C, G, T (1, 2, 4, 8) -> field A0 C1 T2 G3 of the packed register counters
+// BAM nibble of A, C, G, T (1, 2, 4, 8) -> field A0 C1 T2 G3 of the packed register counters / allele slot A0 C1 T3 G4
 __device__ __forceinline__ uint32_t nib_field(uint32_t nib) { return (0x20310u >> (2u * nib)) & 3u; }
 __device__ __forceinline__ bool nib_is_acgt(uint32_t nib) { return (0x0116u >> nib) & 1u; }
 
@@ -242,94 +251,54 @@ __device__ __noinline__ uint32_t dyn_lookup(DynTab T, unsigned long long key, ui
     return 0;
 }
 
-// A non-negative double < 2^20 as a 128-bit fixed-point integer with LSB 2^-108 (exact: the terms are 0 or >= 2^-55).
-__device__ __forceinline__ void pi_fixed128(double l, unsigned long long& lo, unsigned long long& hi) {
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(l);
-    const int e = (int)((bits >> 52) & 0x7ffull);
-    const unsigned long long m = (bits & 0xFFFFFFFFFFFFFull) | (1ull << 52);
-    const int sh = e - 967;                             // value = m * 2^(e-1075) = (m << sh) * 2^-108
-    if (e == 0 || sh <= -53) { lo = hi = 0; return; }
-    if (sh <= 0) { lo = m >> (-sh); hi = 0; }
-    else if (sh < 64) { lo = m << sh; hi = m >> (64 - sh); }
-    else { lo = 0; hi = m << (sh - 64); }
-}
-__device__ __forceinline__ void add128(unsigned long long& lo, unsigned long long& hi, unsigned long long alo, unsigned long long ahi) {
-    lo += alo; hi += ahi + (lo < alo ? 1ull : 0ull);
-}
-__device__ __forceinline__ void sub128(unsigned long long& lo, unsigned long long& hi, unsigned long long blo, unsigned long long bhi) {
-    const unsigned long long borrow = lo < blo ? 1ull : 0ull;
-    lo -= blo; hi -= bhi + borrow;
-}
-// 128-bit value -> three 44-bit carry-save limbs of the global accumulators (v = l0 + l1*2^44 + l2*2^88)
-__device__ __forceinline__ void split_limbs(unsigned long long lo, unsigned long long hi, unsigned long long& a0, unsigned long long& a1,
-                                            unsigned long long& a2) {
-    const unsigned long long M44 = (1ull << 44) - 1ull;
-    a0 = lo & M44;
-    a1 = ((lo >> 44) | (hi << 20)) & M44;
-    a2 = hi >> 24;
-}
+// ============================================================================================================
+// K3a: k_gather
+//
+// A warp owns one unit; it works in batches of 32 tile events:
+//   stage  : 32 GRec (32 B each, gathered through ev_read[]) -> shared memory; boundary / "simple read" flags of the
+//            batch become warp-uniform bit masks (one byte load + three ballots);
+//   gather : KA_GATHER reads at a time every lane computes the query position of ITS locus and loads the base nibble
+//            and the quality (the loads of a group are independent: ILP + occupancy hide the latency);
+//   apply  : in event order, the read-level tallies (cvg, alleleCnt, strand, lowQ, R1/R2 end distances: registers, 4 x 8-bit
+//            fields A C T G per word) and the fragment merge; at every fragment boundary the lane's fragment code goes to a
+//            shared-memory staging row, eight rows are written out as one 128-bit word per lane.
+// Everything rare is out of line: reads with indels / hard clips / several aligned runs (per-event CIGAR walk),
+// non-ACGT bases, pairs on a deletion or a dynamic allele.
+// ============================================================================================================
+#ifndef KA_WARPS
+#define KA_WARPS 8
+#endif
+#ifndef KA_MINBLOCKS
+#define KA_MINBLOCKS 3
+#endif
+#ifndef KA_GATHER
+#define KA_GATHER 4
+#endif
+#define KA_REG_FLUSH 224u                       // tile events between register -> global flushes (8-bit fields)
+#define KA_WARP_WORDS(LIST) (256 + 32 + 512 + 128 + ((LIST) ? 256 : 0))   // GRec stage | srank | event codes | fragment-code staging | first-read staging
+#define KA_SMEM_BYTES(LIST) (64 + KA_WARPS * KA_WARP_WORDS(LIST) * 4)
 
-struct LaneState {
-    // locus-level
-    int cvg, allFrag, allMT, usedFrag, nBC, usedMT, mt3, mt5, mt7, mt10;
-    uint32_t keymask, status;
-    unsigned long long pad_lo, pad_hi;      // PI terms that go to all of A, C, G, T (single-allele barcodes, see umi_finalize)
-    // hot counters, 4 x 8-bit fields (A, C, T, G)
-    uint32_t r_allele, r_fwd, r_lowq, r_r1tot, r_r1le, r_r2tot, r_r2le, r_r2ple, r_conc;
-    uint32_t flags;                         // LF_*
-    // barcode-level
-    int n; uint32_t exist; double Q, rightP; uint32_t last_aid; uint32_t udyn0, udyn1; int ndyn;
-    uint32_t first_read;                    // BAM index of the barcode's first passing read at this locus (listing only)
-    // fragment-level
-    uint32_t f_mid; int f_bq;
+// slow-path event code (internal to k_gather)
+#define EC_NIB_SH   8u
+#define EC_COVERED  (1u << 12)
+#define EC_DYN      (1u << 13)    // regular base that is not A/C/G/T (N / IUPAC): dynamic allele row
+#define EC_INC      (1u << 14)    // event passes incCond (:431): it enters bcDict
+#define EC_REGULAR  (1u << 15)    // a plain base, not an indel start / in-deletion event
+#define EC_LE20     (1u << 16)    // distance to the barcode end <= 20
+#define EC_PLE      (1u << 17)    // R2 and distance to the primer end <= primerDist
+
+struct KAArgs {
+    const GRec* grec; const ReadRec* recs; const uint32_t* ev_read; const uint8_t* ev_flags; const uint32_t* urank_s;
+    const uint32_t* unit_eb; const uint32_t* unit_ee; const uint32_t* unit_tile; uint32_t n_units; uint32_t code_mult;
+    const int32_t* loci_pos; int64_t n_loci;
+    const uint8_t* seq; const uint8_t* qual; const uint32_t* cigar;
+    int minBQ, primerDist;
+    uint4* codes; uint32_t* unit_nfrag;
+    uint32_t* frag_first;         // LIST only: BAM index of the fragment's first passing read, per (slot, lane)
+    uint32_t* umi_urank;          // optional (mask / listing): urank of the k-th barcode of unit u at [eb + k]
+    int32_t* loc; int32_t* cnt;
+    DynTab T;
 };
-
-#define FCW(w, a)   fc[((a) * K3_NW + (w)) * 32 + lane]
-#define LIMB(a)     limb[(a) * 32 + lane]
-#define UCNT(s)     ucnt[(s) * 32 + lane]
-#define UPROD(s)    uprod[(s) * 32 + lane]
-
-// counter update for an allele that may be dynamic: `word`/`add` address the packed shared-memory counter of a fixed
-// allele, c_lo / c_hi are the smc_out counter indices the low / high half stand for.
-__device__ __forceinline__ void bump(int32_t* dcnt, int* fc, int lane, uint32_t aid, int word, uint32_t add, int c_lo, int c_hi) {
-    if (aid < NF) FCW(word, aid) += (int)add;
-    else {
-        int32_t* row = dcnt + (size_t)(aid - NF) * SMC_NCNT;
-        if (add & 0xffffu) atomicAdd(&row[c_lo], 1);
-        if (add >> 16) atomicAdd(&row[c_hi], 1);
-    }
-}
-
-// registers -> shared-memory counters
-__device__ __forceinline__ void flush_regs(int* fc, int lane, LaneState& S) {
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-        const int a = f + (f >> 1);                                     // A0 C1 T3 G4
-        const uint32_t al = (S.r_allele >> (8 * f)) & 255u, fw = (S.r_fwd >> (8 * f)) & 255u;
-        const uint32_t t1 = (S.r_r1tot >> (8 * f)) & 255u, l1 = (S.r_r1le >> (8 * f)) & 255u;
-        const uint32_t t2 = (S.r_r2tot >> (8 * f)) & 255u, l2 = (S.r_r2le >> (8 * f)) & 255u;
-        const uint32_t lq = (S.r_lowq >> (8 * f)) & 255u, pl = (S.r_r2ple >> (8 * f)) & 255u;
-        const uint32_t cc = (S.r_conc >> (8 * f)) & 255u;
-        if (al) FCW(KW_ALLELE_FWD, a) += (int)(al | (fw << 16));
-        if (t1) FCW(KW_R1, a) += (int)(t1 | (l1 << 16));
-        if (t2) FCW(KW_R2, a) += (int)(t2 | (l2 << 16));
-        if (lq | pl) FCW(KW_LOWQ_R2P, a) += (int)(lq | (pl << 16));
-        if (cc) FCW(KW_PAIR, a) += (int)cc;
-    }
-    S.r_allele = S.r_fwd = S.r_lowq = S.r_r1tot = S.r_r1le = S.r_r2tot = S.r_r2le = S.r_r2ple = S.r_conc = 0;
-}
-
-// order-independent tallies of a regular A/C/G/T event (smCounter.py:423-459) into the register counters;
-// `one` = the field increment of the base (0 when the event does not count), `onei` = the same if it passes incCond
-__device__ __forceinline__ void tally_regular(LaneState& S, uint32_t one, uint32_t onei, bool reverse, bool read2, bool lowq, bool le20, bool ple) {
-    S.r_allele += one;                                               // :459
-    if (!reverse) S.r_fwd += one;                                    // :454-457
-    if (lowq) S.r_lowq += one;                                       // :428-429
-    const uint32_t onel = le20 ? onei : 0u;
-    if (!read2) { S.r_r1tot += onei; S.r_r1le += onel; }             // :432-441
-    else { S.r_r2tot += onei; S.r_r2le += onel; }                    // :442-452
-    if (ple) S.r_r2ple += onei;                                      // the primer window of an R1 read is empty
-}
 
 // Tallies of one pileup event whose base is not A/C/G/T (N / IUPAC, smCounter.py:423-457 with that key): rare, so it goes
 // straight to the dynamic-allele row with atomics.  Returns the row | (nibble == N) << 31.
@@ -354,39 +323,41 @@ __device__ __noinline__ uint32_t dyn_base_event(DynTab T, const uint8_t* seq_rea
 }
 
 // Pileup event of a read that is NOT one plain aligned run (indels, hard clips, ...): htslib resolve_cigar2 for the
-// lane's position p, then the allele classification of smCounter.py:371-457.  Returns {event code, x}:
+// lane's position p, then the allele classification of smCounter.py:371-457.  `rw` = the read's ReadRec (global memory).
+// Returns {event code, x}:
 //   regular base          : EC_REGULAR, nibble in the code (EC_DYN when it is not A/C/G/T; then x = query position)
-//   inside a deletion     : x = MID_DEL, bq = minBQ (:416-421)
-//   insertion / deletion start (:371-411): x = MID_DYN + row; alleleCnt and strand are tallied here
-__device__ __noinline__ uint2 slow_event(DynTab T, const uint32_t* rw /* staged ReadRec */, const uint32_t* __restrict__ cigar,
+//   inside a deletion     : x = SMC_A_DEL, bq = minBQ (:416-421)
+//   insertion / deletion start (:371-411): x = NF + row; alleleCnt and strand are tallied here
+__device__ __noinline__ uint2 slow_event(DynTab T, const uint32_t* __restrict__ rw, const uint32_t* __restrict__ cigar,
                                          const uint8_t* __restrict__ seqp, const uint8_t* __restrict__ qualp, int32_t p, int32_t Li,
                                          int minBQ, int primerDist) {
-    const uint32_t meta = rw[3];
-    const int32_t start = (int32_t)rw[6], lo = (int32_t)rw[0], hi = (int32_t)rw[7];
+    const uint32_t meta = __ldg(rw + 3);
+    const int32_t start = (int32_t)__ldg(rw + 6), lo = (int32_t)__ldg(rw + 0), hi = (int32_t)__ldg(rw + 7);
     if (!(Li >= lo && Li < hi)) return make_uint2(0u, 0u);
     const bool reverse = meta & RM_REVERSE, read2 = meta & RM_READ2;
     const uint32_t ncig = meta >> 8;
-    const int leftSP = (int)(rw[2] & 0xffffu), alnlen = (int)(rw[2] >> 16);
-    const uint32_t seq_off = rw[4], qual_off = rw[5], cigar_off = rw[11];
+    const uint32_t spa = __ldg(rw + 2);
+    const int leftSP = (int)(spa & 0xffffu), alnlen = (int)(spa >> 16);
+    const uint32_t seq_off = __ldg(rw + 4), qual_off = __ldg(rw + 5), cigar_off = __ldg(rw + 11);
     int qpos = 0, indel = 0; bool isdel = false;
     {
         int x = start, y = 0;
         for (uint32_t k = 0; k < ncig; ++k) {
-            const uint32_t cw = k < 4 ? rw[12 + k] : __ldg(&cigar[cigar_off + k]);
+            const uint32_t cw = __ldg(&cigar[cigar_off + k]);
             const uint32_t op = cw & 15u; const int len = (int)(cw >> 4);
             if (op == 0 || op == 7 || op == 8 || op == 2 || op == 3) {
                 if (p < x + len) {                                           // the op that covers p
                     isdel = (op == 2 || op == 3);
                     qpos = isdel ? y : y + (p - x);
                     if (p == x + len - 1 && k + 1 < ncig) {                   // peek the next op
-                        const uint32_t c2 = (k + 1) < 4 ? rw[12 + k + 1] : __ldg(&cigar[cigar_off + k + 1]);
+                        const uint32_t c2 = __ldg(&cigar[cigar_off + k + 1]);
                         const uint32_t op2 = c2 & 15u; const int l2 = (int)(c2 >> 4);
                         if (op2 == 2) indel = -l2;
                         else if (op2 == 1) indel = l2;
                         else if (op2 == 6 && k + 2 < ncig) {
                             int l3 = 0;
                             for (uint32_t kk = k + 2; kk < ncig; ++kk) {
-                                const uint32_t c3 = kk < 4 ? rw[12 + kk] : __ldg(&cigar[cigar_off + kk]);
+                                const uint32_t c3 = __ldg(&cigar[cigar_off + kk]);
                                 const uint32_t op3 = c3 & 15u;
                                 if (op3 == 1) l3 += (int)(c3 >> 4);
                                 else if (op3 == 2 || op3 == 0 || op3 == 3 || op3 == 7 || op3 == 8) break;
@@ -403,7 +374,7 @@ __device__ __noinline__ uint2 slow_event(DynTab T, const uint32_t* rw /* staged 
     }
     if (indel == 0 && isdel) {                                                 // :416-421
         const bool inc = (meta & RM_OK);                                       // bq = minBQ passes the quality gate
-        return make_uint2(((uint32_t)minBQ & 255u) | EC_COVERED | (inc ? EC_INC : 0u), MID_DEL);
+        return make_uint2(((uint32_t)minBQ & 255u) | EC_COVERED | (inc ? EC_INC : 0u), (uint32_t)SMC_A_DEL);
     }
     const uint32_t sb = __ldg(seqp + ((size_t)seq_off + (size_t)(qpos >> 1)));
     const uint32_t nib = (qpos & 1) ? (sb & 15u) : (sb >> 4);
@@ -447,10 +418,370 @@ __device__ __noinline__ uint2 slow_event(DynTab T, const uint32_t* rw /* staged 
         len = -indel;
         key = dyn_make_key((uint32_t)Li, SMC_K_DEL, nib, (unsigned long long)len);
     }
-    const uint32_t e = dyn_lookup(T, key, rw[10], qpos, len);
+    const uint32_t e = dyn_lookup(T, key, __ldg(rw + 10), qpos, len);
     atomicAdd(&T.dcnt[(size_t)e * SMC_NCNT + SMC_C_ALLELE], 1);
     if (!reverse) atomicAdd(&T.dcnt[(size_t)e * SMC_NCNT + SMC_C_FWD], 1);
-    return make_uint2(code, MID_DYN + e);
+    return make_uint2(code, NF + e);
+}
+
+// concordPairCnt / discordPairCnt of an allele that has no register field ('DEL' or a dynamic allele): rare, atomics
+__device__ __noinline__ void pair_bump_global(int32_t* cnt, size_t nl, int64_t L, int32_t* dcnt, uint32_t aid, int which /* SMC_C_CONCORD | SMC_C_DISCORD */) {
+    if (aid < NF) atomicAdd(&cnt[((size_t)aid * SMC_NCNT + which) * nl + L], 1);
+    else atomicAdd(&dcnt[(size_t)(aid - NF) * SMC_NCNT + which], 1);
+}
+
+// state of the lane's open fragment
+#define FS_SEEN   1u      // a read of the fragment covers the locus
+#define FS_HADINC 2u      // a read passed incCond
+#define FS_EXISTS 4u      // the fragment is in bcDict
+#define FS_PAIRED 8u
+
+struct GatherRegs {          // 4 x 8-bit fields (A, C, T, G) per word
+    uint32_t allele, fwd, lowq, r1tot, r1le, r2tot, r2le, r2ple, conc, disc;
+};
+
+// registers -> the per-locus global accumulators ([field][locus]: coalesced across lanes)
+__device__ __forceinline__ void flush_gather_regs(int32_t* cnt, size_t nl, int64_t L, bool lane_valid, GatherRegs& R) {
+    if (lane_valid) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const int a = f + (f >> 1);                                     // A0 C1 T3 G4
+            int32_t* base = cnt + (size_t)a * SMC_NCNT * nl + L;
+            const uint32_t al = (R.allele >> (8 * f)) & 255u;
+            if (al) {
+                const uint32_t fw = (R.fwd >> (8 * f)) & 255u, lq = (R.lowq >> (8 * f)) & 255u;
+                const uint32_t t1 = (R.r1tot >> (8 * f)) & 255u, l1 = (R.r1le >> (8 * f)) & 255u;
+                const uint32_t t2 = (R.r2tot >> (8 * f)) & 255u, l2 = (R.r2le >> (8 * f)) & 255u, pl = (R.r2ple >> (8 * f)) & 255u;
+                const uint32_t cc = (R.conc >> (8 * f)) & 255u, dc = (R.disc >> (8 * f)) & 255u;
+                atomicAdd(base + (size_t)SMC_C_ALLELE * nl, (int)al);
+                if (fw) atomicAdd(base + (size_t)SMC_C_FWD * nl, (int)fw);
+                if (al - fw) atomicAdd(base + (size_t)SMC_C_REV * nl, (int)(al - fw));
+                if (lq) atomicAdd(base + (size_t)SMC_C_LOWQ * nl, (int)lq);
+                if (t1) atomicAdd(base + (size_t)SMC_C_R1TOT * nl, (int)t1);
+                if (l1) atomicAdd(base + (size_t)SMC_C_R1LE * nl, (int)l1);
+                if (t2) atomicAdd(base + (size_t)SMC_C_R2TOT * nl, (int)t2);
+                if (l2) atomicAdd(base + (size_t)SMC_C_R2LE * nl, (int)l2);
+                if (pl) atomicAdd(base + (size_t)SMC_C_R2PLE * nl, (int)pl);
+                if (cc) atomicAdd(base + (size_t)SMC_C_CONCORD * nl, (int)cc);
+                if (dc) atomicAdd(base + (size_t)SMC_C_DISCORD * nl, (int)dc);
+            }
+        }
+    }
+    R.allele = R.fwd = R.lowq = R.r1tot = R.r1le = R.r2tot = R.r2le = R.r2ple = R.conc = R.disc = 0;
+}
+
+// order-independent tallies of a regular A/C/G/T event (smCounter.py:423-459) into the register counters;
+// `one` = the field increment of the base (0 when the event does not count), `onei` = the same if it passes incCond
+__device__ __forceinline__ void tally_regular(GatherRegs& R, uint32_t one, uint32_t onei, bool reverse, bool read2, bool lowq, bool le20, bool ple) {
+    R.allele += one;                                               // :459
+    if (!reverse) R.fwd += one;                                    // :454-457
+    if (lowq) R.lowq += one;                                       // :428-429
+    const uint32_t onel = le20 ? onei : 0u;
+    if (!read2) { R.r1tot += onei; R.r1le += onel; }               // :432-441
+    else { R.r2tot += onei; R.r2le += onel; }                      // :442-452
+    if (ple) R.r2ple += onei;                                      // the primer window of an R1 read is empty
+}
+
+template <bool LIST>
+__global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const KAArgs A) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* lut = smem;                          // nibble -> field increment 1 << 8*field | allele slot << 28 (0: not A/C/G/T)
+    if (threadIdx.x < 16) {
+        const uint32_t n = threadIdx.x;
+        const uint32_t f = nib_field(n);
+        lut[n] = nib_is_acgt(n) ? ((1u << (8u * f)) | ((f + (f >> 1)) << 28)) : 0u;
+    }
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* ws = smem + 16 + (size_t)w * KA_WARP_WORDS(LIST);     // 32 GRec
+    uint32_t* srank_s = ws + 256;
+    uint16_t* evc = reinterpret_cast<uint16_t*>(ws + 256 + 32);       // 32 x 32 event codes of the batch
+    uint32_t* cst = ws + 256 + 32 + 512;                              // fragment-code staging: word [k >> 1][lane], half k & 1
+    uint32_t* fst = ws + 256 + 32 + 512 + 128;                        // LIST: [k][lane]
+
+    const uint32_t unit = blockIdx.x * KA_WARPS + w;
+    if (unit >= A.n_units) return;
+    const uint32_t eb = A.unit_eb[unit], ee = A.unit_ee[unit];
+    if (eb >= ee) { if (lane == 0) A.unit_nfrag[unit] = 0; return; }
+    const uint32_t tile = A.unit_tile[unit];
+    const uint64_t so = unit_slot_base(eb, unit, A.code_mult);
+    const uint32_t cap = unit_slot_cap(ee - eb, A.code_mult);
+
+    const int64_t L = (int64_t)tile * 32 + lane;
+    const bool lane_valid = L < A.n_loci;
+    const int32_t p = lane_valid ? A.loci_pos[L] : 0;
+    const int32_t Li = lane_valid ? (int32_t)L : -1;                  // -1 is never inside a read's [lo, hi)
+    const size_t nl = (size_t)A.n_loci;
+    const int minBQ = A.minBQ;
+    const uint32_t pspan = A.primerDist > 0 ? (uint32_t)A.primerDist : 0u;
+    const uint8_t* __restrict__ seqp = A.seq;
+    const uint8_t* __restrict__ qualp = A.qual;
+
+    GatherRegs R;
+    R.allele = R.fwd = R.lowq = R.r1tot = R.r1le = R.r2tot = R.r2le = R.r2ple = R.conc = R.disc = 0;
+    int cvg = 0;
+    // open fragment of this lane: FS_* bits, allele (slot, or NF + dynamic row), effective quality
+    uint32_t fs = 0, f_mid = 0, f_bq = 0, f_first = 0xffffffffu;
+    // warp-uniform
+    uint32_t fcount = 0, ext = 0, umi_k = 0, since_flush = 0;
+    bool open = false, umi_first = true, dead = false;
+    uint16_t* const cst16 = reinterpret_cast<uint16_t*>(cst) + 2 * lane;
+
+    auto flush_codes = [&](uint32_t f0) {
+        if (f0 + 8u + 2u * ext > cap) { if (!dead && lane == 0) atomicOr(A.T.gflags, GF_CODE_FULL); dead = true; }
+        if (dead) return;
+        const uint4 v = make_uint4(cst[lane], cst[32 + lane], cst[64 + lane], cst[96 + lane]);
+        A.codes[((so + f0) >> 3) * 32 + lane] = v;
+        if (LIST) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) A.frag_first[(so + f0 + k) * 32 + lane] = fst[k * 32 + lane];
+        }
+    };
+    // close the open fragment: its code goes to the staging rows, eight rows are written out as one 128-bit word per lane
+    auto emit = [&]() {
+        const bool dynl = (fs & FS_EXISTS) && f_mid >= NF;
+        const bool any_dyn = __any_sync(FULL_MASK, dynl);
+        const uint32_t st = (fs & FS_EXISTS) ? 3u : ((fs & 3u) - ((fs >> 1) & 1u));
+        const uint32_t code = (st << FC_ST_SH) | ((fs & FS_PAIRED) ? FC_PAIRED : 0u) | (any_dyn ? FC_EXT : 0u) | (umi_first ? FC_UMIFIRST : 0u) |
+                              ((f_mid < NF ? f_mid : FC_AID_DYN) << FC_AID_SH) | f_bq;
+        const uint32_t k = fcount & 7u;
+        cst16[((k >> 1) << 6) + (k & 1u)] = (uint16_t)code;
+        if (LIST) fst[k * 32 + lane] = f_first;
+        if (any_dyn) {                                                   // extension row: the dynamic-allele rows of this fragment
+            if (8u * ((fcount >> 3) + 1u) + 2u * (ext + 1u) > cap) { if (!dead && lane == 0) atomicOr(A.T.gflags, GF_CODE_FULL); dead = true; }
+            if (!dead) reinterpret_cast<uint32_t*>(A.codes)[(so + cap - 2u * (ext + 1u)) * 16 + lane] = dynl ? f_mid - NF : 0u;
+            ++ext;
+        }
+        ++fcount;
+        if ((fcount & 7u) == 0u) flush_codes(fcount - 8u);
+        fs = 0; f_first = 0xffffffffu; umi_first = false;
+    };
+    // warp-uniform bookkeeping at the first event of a fragment
+    auto boundary = [&](bool umi_start, int j) {
+        if (open) emit();
+        if (umi_start) {
+            umi_first = true;
+            if (A.umi_urank) { if (lane == 0) A.umi_urank[eb + umi_k] = __ldg(&A.urank_s[srank_s[j]]); ++umi_k; }
+        }
+        open = true;
+    };
+    // fragment merge of an event that passed incCond (smCounter.py:467-479); `one` = register field of an A/C/G/T base, else 0
+    auto merge = [&](uint32_t mid, uint32_t bq, bool isN, uint32_t one, int j) {
+        if (LIST) f_first = min(f_first, __ldg(&A.recs[srank_s[j]].read_idx));
+        if (!(fs & FS_EXISTS)) { fs = (fs | FS_HADINC | FS_EXISTS) & ~FS_PAIRED; f_mid = mid; f_bq = bq; }
+        else if (mid == f_mid || isN) {
+            f_bq = min(f_bq, bq); fs |= FS_PAIRED;
+            if (mid == f_mid) {
+                if (one) R.conc += one;
+                else pair_bump_global(A.cnt, nl, L, A.T.dcnt, mid, SMC_C_CONCORD);
+            }
+        } else {
+            fs &= ~FS_EXISTS;
+            if (one) R.disc += one;
+            else pair_bump_global(A.cnt, nl, L, A.T.dcnt, mid, SMC_C_DISCORD);
+        }
+    };
+
+    for (uint32_t base = eb; base < ee; base += 32) {
+        const int nb = (int)min(32u, ee - base);
+        // ---------------- stage
+        uint32_t fl8 = EF_SIMPLE;                                        // slots past the end: an empty simple read, no boundary
+        {
+            uint4 g0 = make_uint4(0u, 0u, 0u, 0u), g1 = g0; uint32_t sr = 0;
+            if (lane < nb) {
+                sr = __ldg(&A.ev_read[base + lane]);
+                fl8 = __ldg(&A.ev_flags[base + lane]);
+                const uint4* src = reinterpret_cast<const uint4*>(&A.grec[sr]);
+                g0 = __ldg(src); g1 = __ldg(src + 1);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(ws + lane * 8);
+            dst[0] = g0; dst[1] = g1;
+            srank_s[lane] = sr;
+        }
+        const uint32_t fragmask = __ballot_sync(FULL_MASK, fl8 & EF_FRAG);
+        const uint32_t umimask = __ballot_sync(FULL_MASK, fl8 & EF_UMI);
+        const uint32_t simplemask = __ballot_sync(FULL_MASK, fl8 & EF_SIMPLE);
+        if (since_flush + 32u > 255u) { flush_gather_regs(A.cnt, nl, L, lane_valid, R); since_flush = 0; }
+        since_flush += 32u;
+        __syncwarp();
+        // ---------------- gather + tally (order independent), KA_GATHER reads at a time; what the ordered pass needs goes to
+        // shared memory as a 16-bit event code
+#pragma unroll 1
+        for (int g = 0; g < nb; g += KA_GATHER) {
+            uint32_t sbv[KA_GATHER], bqv[KA_GATHER], fl[KA_GATHER];
+#pragma unroll
+            for (int u = 0; u < KA_GATHER; ++u) {
+                const uint32_t* rw = ws + (g + u) * 8;
+                const uint4 qa = *reinterpret_cast<const uint4*>(rw);        // lo gspan qk meta
+                const uint4 qb = *reinterpret_cast<const uint4*>(rw + 4);    // seq_off qual_off le_lo ple_lo
+                const bool cov = (uint32_t)(Li - (int32_t)qa.x) < qa.y;
+                const uint32_t qpos = (uint32_t)(p + (int32_t)qa.z);
+                sbv[u] = 0; bqv[u] = 0;
+                if (cov) {
+                    sbv[u] = __ldg(seqp + (qb.x + (qpos >> 1)));
+                    bqv[u] = __ldg(qualp + (qb.y + qpos));
+                }
+                const bool le20 = (uint32_t)(p - (int32_t)qb.z) <= ((qa.w & GM_LE_INF) ? WIN_INF : 20u);
+                const bool ple = (uint32_t)(p - (int32_t)qb.w) <= ((qa.w & GM_PLE_INF) ? WIN_INF : pspan);
+                // bits 0-3 RM_*, 4 covered, 5 le20, 6 ple, 7 odd query position
+                fl[u] = (qa.w & 15u) | (cov ? 16u : 0u) | (le20 ? 32u : 0u) | (ple ? 64u : 0u) | ((qpos & 1u) << 7);
+            }
+#pragma unroll
+            for (int u = 0; u < KA_GATHER; ++u) {
+                const uint32_t f = fl[u];
+                const bool cov = f & 16u;
+                const uint32_t nib = (f & 128u) ? (sbv[u] & 15u) : (sbv[u] >> 4);   // 0 when not covered
+                const uint32_t bq = bqv[u];
+                const uint32_t one = lut[nib] & 0x0fffffffu;                         // 0 when not covered or not A/C/G/T
+                const bool lowq = (int)bq < minBQ;
+                const bool inc = cov && !lowq && (f & RM_OK);                        // :431
+                cvg += cov ? 1 : 0;                                                  // :368
+                tally_regular(R, one, inc ? one : 0u, f & RM_REVERSE, f & RM_READ2, lowq, f & 32u, f & 64u);
+                evc[(g + u) * 32 + lane] = (uint16_t)(bq | (nib << EC_NIB_SH) | (cov ? EC_COVERED : 0u) | ((cov && !one) ? EC_DYN : 0u) |
+                                                      (inc ? EC_INC : 0u));
+            }
+        }
+        // ---------------- ordered pass: fragment boundaries, fragment merge (smCounter.py:467-479), the rare events
+#pragma unroll 1
+        for (int j = 0; j < nb; ++j) {
+            if ((fragmask >> j) & 1u) boundary((umimask >> j) & 1u, j);              // warp uniform
+            uint32_t cd, mid, one; bool isN = false;
+            if ((simplemask >> j) & 1u) {
+                cd = evc[j * 32 + lane];
+                const uint32_t lv = lut[(cd >> EC_NIB_SH) & 15u];
+                one = lv & 0x0fffffffu; mid = lv >> 28;
+                if (cd & EC_DYN) {                                                   // rare: N / IUPAC base -> dynamic allele row
+                    const uint32_t* rw = ws + j * 8;
+                    const uint32_t meta = rw[3];
+                    const bool le20 = (uint32_t)(p - (int32_t)rw[6]) <= ((meta & GM_LE_INF) ? WIN_INF : 20u);
+                    const bool ple = (uint32_t)(p - (int32_t)rw[7]) <= ((meta & GM_PLE_INF) ? WIN_INF : pspan);
+                    const uint32_t dfl = ((meta & RM_REVERSE) ? 0u : 1u) | ((int)(cd & 255u) < minBQ ? 2u : 0u) | ((cd & EC_INC) ? 4u : 0u) |
+                                         ((meta & RM_READ2) ? 8u : 0u) | (le20 ? 16u : 0u) | (ple ? 32u : 0u);
+                    const uint32_t e = dyn_base_event(A.T, seqp + rw[4], (uint32_t)Li, __ldg(&A.recs[srank_s[j]].read_idx), p + (int32_t)rw[2], dfl);
+                    mid = NF + (e & 0x7fffffffu); isN = e >> 31;
+                }
+            } else {                                                                 // rare: per-event CIGAR walk, out of line
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(&A.recs[srank_s[j]]);
+                const uint2 ev = slow_event(A.T, rw, A.cigar, seqp, qualp, p, Li, minBQ, A.primerDist);
+                cd = ev.x; mid = ev.y; one = 0;
+                if (cd & EC_COVERED) {
+                    const uint32_t meta = __ldg(rw + 3);
+                    const bool lowq = (int)(cd & 255u) < minBQ;
+                    cvg++;
+                    if (cd & EC_REGULAR) {
+                        if (!(cd & EC_DYN)) {
+                            const uint32_t lv = lut[(cd >> EC_NIB_SH) & 15u];
+                            one = lv & 0x0fffffffu; mid = lv >> 28;
+                            tally_regular(R, one, (cd & EC_INC) ? one : 0u, meta & RM_REVERSE, meta & RM_READ2, lowq, cd & EC_LE20, cd & EC_PLE);
+                        } else {
+                            const uint32_t dfl = ((meta & RM_REVERSE) ? 0u : 1u) | (lowq ? 2u : 0u) | ((cd & EC_INC) ? 4u : 0u) |
+                                                 ((meta & RM_READ2) ? 8u : 0u) | ((cd & EC_LE20) ? 16u : 0u) | ((cd & EC_PLE) ? 32u : 0u);
+                            const uint32_t e = dyn_base_event(A.T, seqp + __ldg(rw + 4), (uint32_t)Li, __ldg(rw + 10), (int)ev.y, dfl);
+                            mid = NF + (e & 0x7fffffffu); isN = e >> 31;
+                        }
+                    } else if (mid == (uint32_t)SMC_A_DEL) {
+                        atomicAdd(&A.cnt[((size_t)SMC_A_DEL * SMC_NCNT + SMC_C_ALLELE) * nl + L], 1);   // alleleCnt only (:416-421, :459)
+                    }
+                }
+            }
+            if (cd & EC_COVERED) fs |= FS_SEEN;                                      // :463-464
+            if (cd & EC_INC) merge(mid, cd & 255u, isN, one, j);                     // :467-479
+        }
+        __syncwarp();
+    }
+    // ---- close the last fragment, write the partial group, flush the tallies
+    emit();
+    if (fcount & 7u) flush_codes(fcount & ~7u);
+    if (lane == 0) A.unit_nfrag[unit] = dead ? 0u : fcount;
+    flush_gather_regs(A.cnt, nl, L, lane_valid, R);
+    if (lane_valid && cvg) atomicAdd(&A.loc[(size_t)SMC_L_CVG * nl + L], cvg);
+}
+
+// ============================================================================================================
+// K3b: k_merge -- per-barcode posterior, prediction index, consensus (smCounter.py:26-98, 482-532)
+// ============================================================================================================
+#ifndef KB_WARPS
+#define KB_WARPS 4
+#endif
+#ifndef KB_MINBLOCKS
+#define KB_MINBLOCKS 5
+#endif
+#define KB_FC_WORDS    (NF * 32)                // MTCnt | strongMTCnt << 16 per fixed allele and lane
+#define KB_LIMB_WORDS  (NF * 4 * 32)            // 128-bit fixed-point PI accumulator per fixed allele and lane
+#define KB_UCNT_WORDS  (NSLOT * 32)
+#define KB_UPROD_WORDS (NSLOT * 64)
+#define KB_WARP_WORDS  (KB_FC_WORDS + KB_LIMB_WORDS + KB_UCNT_WORDS + KB_UPROD_WORDS)
+#define KB_TAB_BYTES   8192                     // {p, 1 - p} of a fragment, indexed by 'Paired' << 8 | quality (512 x double2)
+#define KB_SMEM_BYTES  (KB_TAB_BYTES + KB_WARPS * KB_WARP_WORDS * 4)
+
+struct KBArgs {
+    const uint4* codes; const uint32_t* unit_nfrag; const uint32_t* frag_first; const uint32_t* umi_urank;
+    const uint32_t* unit_eb; const uint32_t* unit_ee; const uint32_t* unit_tile; uint32_t n_units; uint32_t code_mult;
+    int64_t n_loci;
+    const double* bqtab;            // [256]  10^(-bq/10), host glibc pow (smCounter.py:469)
+    const double* pcrtab;           // [3][(nmax+1)(nmax+2)/2]  10^(-6 (cnt+.5)/(n+.5k)), k = 4,5,6 (smCounter.py:80-81)
+    int pcr_nmax; int mtDrop; double smt;
+    const int32_t* keep_idx; const int64_t* keep_off; const uint64_t* keep_umi; const uint64_t* umi_of_urank;
+    int32_t* loc; int32_t* cnt; unsigned long long* limb;
+    DynTab T;
+    // optional: list the barcodes of bcDict for flagged loci (down-sampling support)
+    const int32_t* list_idx; uint32_t* list_count; const int64_t* list_off; uint64_t* list_umi; uint32_t* list_first; int64_t list_cap;
+};
+
+// A non-negative double < 2^20 as a 128-bit fixed-point integer with LSB 2^-PI_FIX_LSB (= 2^-80), truncated: the integer part
+// of l * 2^16 is the high word, the fraction * 2^64 the low word.  Both scalings and the subtraction are exact; the
+// truncation drops < 2^-80 per term and is the same whatever the order of the terms, so the sums stay order independent.
+__device__ __forceinline__ void pi_fixed128(double l, unsigned long long& lo, unsigned long long& hi) {
+    static_assert(PI_FIX_LSB == 80, "pi_fixed128 assumes LSB 2^-80");
+    const double t = l * 65536.0;
+    hi = __double2ull_rz(t);
+    const double frac = t - __ull2double_rz(hi);
+    lo = __double2ull_rz(frac * 18446744073709551616.0);
+}
+__device__ __forceinline__ void add128(unsigned long long& lo, unsigned long long& hi, unsigned long long alo, unsigned long long ahi) {
+    lo += alo; hi += ahi + (lo < alo ? 1ull : 0ull);
+}
+__device__ __forceinline__ void sub128(unsigned long long& lo, unsigned long long& hi, unsigned long long blo, unsigned long long bhi) {
+    const unsigned long long borrow = lo < blo ? 1ull : 0ull;
+    lo -= blo; hi -= bhi + borrow;
+}
+// 128-bit value -> three 44-bit carry-save limbs of the global accumulators (v = l0 + l1*2^44 + l2*2^88)
+__device__ __forceinline__ void split_limbs(unsigned long long lo, unsigned long long hi, unsigned long long& a0, unsigned long long& a1,
+                                            unsigned long long& a2) {
+    const unsigned long long M44 = (1ull << 44) - 1ull;
+    a0 = lo & M44;
+    a1 = ((lo >> 44) | (hi << 20)) & M44;
+    a2 = hi >> 24;
+}
+
+// per-lane flags of the open barcode
+#define LF_UMI_SEEN  (1u << 0)    // a read of the barcode covers the locus
+#define LF_UMI_BC    (1u << 1)    // the barcode is in bcDict (a read passed incCond)
+
+struct MergeState {
+    // locus-level
+    int allFrag, allMT, usedFrag, nBC, usedMT, mt3, mt5, mt7, mt10;
+    uint32_t keymask, status;
+    unsigned long long pad_lo, pad_hi;      // PI terms that go to all of A, C, G, T (single-allele barcodes, see umi_finalize)
+    uint32_t flags;                         // LF_*
+    // barcode-level
+    int n; uint32_t exist; double Q, rightP; uint32_t last_aid; uint32_t udyn0, udyn1; int ndyn;
+    uint32_t first_read;                    // BAM index of the barcode's first passing read at this locus (listing only)
+};
+
+#define FCW(a)      fc[(a) * 32 + lane]
+#define LIMB(a)     limb[(a) * 32 + lane]
+#define UCNT(s)     ucnt[(s) * 32 + lane]
+#define UPROD(s)    uprod[(s) * 32 + lane]
+
+// MTCnt / strongMTCnt of an allele that may be dynamic; add = 1 (MTCnt) or 0x10001 (both)
+__device__ __forceinline__ void bump_mt(int32_t* dcnt, int* fc, int lane, uint32_t aid, uint32_t add) {
+    if (aid < NF) FCW(aid) += (int)add;
+    else {
+        int32_t* row = dcnt + (size_t)(aid - NF) * SMC_NCNT;
+        atomicAdd(&row[SMC_C_MT], 1);
+        if (add >> 16) atomicAdd(&row[SMC_C_STRONG], 1);
+    }
 }
 
 // first use of the per-barcode shared-memory arrays: a barcode that has shown a single allele so far keeps its state in
@@ -460,12 +791,8 @@ __device__ __forceinline__ void umi_materialize(int lane, int* ucnt, double* upr
     UCNT(s0) = n; UPROD(s0) = rightP;
 }
 
-__device__ __forceinline__ void fragment_finalize(const double* bqtab_s, int lane, int* ucnt, double* uprod, LaneState& S) {
-    if (S.flags & LF_FRAG_SEEN) { S.allFrag++; S.flags = (S.flags & ~LF_FRAG_SEEN) | LF_UMI_SEEN; }      // :463-464
-    if (!(S.flags & LF_F_EXISTS)) return;
-    const double p = (S.flags & LF_F_PAIRED) ? bqtab_s[S.f_bq] : 0.1;  // smCounter.py:65-68
-    S.flags &= ~LF_F_EXISTS;
-    const uint32_t aid = mid_to_aid(S.f_mid);
+// one fragment of bcDict joins the open barcode (the per-fragment part of calProb, smCounter.py:56-77)
+__device__ __forceinline__ void fragment_join(double p, double q1, uint32_t aid, int lane, int* ucnt, double* uprod, MergeState& S) {
     int slot = (int)aid;
     if (aid >= NF) {
         const uint32_t e = aid - NF;
@@ -475,7 +802,6 @@ __device__ __forceinline__ void fragment_finalize(const double* bqtab_s, int lan
         else if (S.ndyn == 1) { S.udyn1 = e; S.ndyn = 2; slot = 6; }
         else { S.status |= SMC_ST_UMI_OVERFLOW; slot = 5; }
     }
-    const double q1 = 1.0 - p;
     const uint32_t bit = 1u << slot;
     if (S.exist == 0) S.exist = bit;
     else {
@@ -502,9 +828,27 @@ __device__ __noinline__ double pcr_slow(int cnt, double denom) {
     return pow(10.0, -6.0 * (((double)cnt + 0.5) / denom));
 }
 
+// -log10(x) for a normal x > 0: x = 2^e m with m in [sqrt(1/2), sqrt(2)), log(m) = 2 atanh(s), s = (m - 1) / (m + 1),
+// |s| <= 0.1716; the series is cut after s^21 / 21 (next term < 3e-17 relative).  Within ~2 ulp of the correctly rounded
+// value, i.e. ~4e-16 relative on a prediction index that has to match to 1e-9 -- at half the instructions of log10().
+__device__ __forceinline__ double neg_log10_normal(double x) {
+    const long long b = __double_as_longlong(x);
+    int e = (int)(b >> 52) - 1023;
+    double m = __longlong_as_double((b & 0x000fffffffffffffll) | 0x3ff0000000000000ll);
+    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+    const double s = (m - 1.0) / (m + 1.0);
+    const double z = s * s;
+    double t = 1.0 / 21.0;
+    t = fma(t, z, 1.0 / 19.0); t = fma(t, z, 1.0 / 17.0); t = fma(t, z, 1.0 / 15.0); t = fma(t, z, 1.0 / 13.0);
+    t = fma(t, z, 1.0 / 11.0); t = fma(t, z, 1.0 / 9.0); t = fma(t, z, 1.0 / 7.0); t = fma(t, z, 0.2); t = fma(t, z, 1.0 / 3.0);
+    const double lm = fma(s * z, t, s);                               // atanh(s)
+    return -fma((double)e, 0.30102999566398119521, lm * 0.86858896380650365530);   // log10(2), 2 / ln(10)
+}
 __device__ __forceinline__ double neg_log10_1m(double p) {              // smCounter.py:509-510
     const double x = 1.0 - p;
-    return x > 0.0 ? -log10(x) : 16.0;
+    if (!(x > 0.0)) return 16.0;
+    if (x < 2.2250738585072014e-308) return -log10(x);                  // subnormal: library call
+    return neg_log10_normal(x);
 }
 
 // -log10(x) for x = fl(1 - p) when p is tiny: with q = 1 - x (exact, Sterbenz) the series q + q^2/2 + ... + q^6/6 is within
@@ -513,7 +857,7 @@ __device__ __forceinline__ double neg_log10_1m(double p) {              // smCou
 __device__ __forceinline__ double neg_log10_1m_small(double p) {
     const double x = 1.0 - p;
     const double q = 1.0 - x;
-    if (!(q < 0.0009765625)) return x > 0.0 ? -log10(x) : 16.0;
+    if (!(q < 0.0009765625)) return neg_log10_1m(p);
     double s = fma(q, 1.0 / 6.0, 0.2);
     s = fma(s, q, 0.25);
     s = fma(s, q, 1.0 / 3.0);
@@ -605,31 +949,48 @@ __device__ __noinline__ uint32_t umi_general(DynTab T, const double* __restrict_
     }
     if (nbest == 1) {                                             // :515-519
         const uint32_t aid = cons < NF ? (uint32_t)cons : NF + (cons == 5 ? udyn0 : udyn1);
-        bump(T.dcnt, fc, lane, aid, KW_MT, best > smt ? 0x10001u : 1u, SMC_C_MT, SMC_C_STRONG);
+        bump_mt(T.dcnt, fc, lane, aid, best > smt ? 0x10001u : 1u);
     } else if (n == 1) {                                          // :521-523
-        bump(T.dcnt, fc, lane, last_aid, KW_MT, 1u, SMC_C_MT, SMC_C_STRONG);
+        bump_mt(T.dcnt, fc, lane, last_aid, 1u);
     }
     return keymask;
 }
 
+// down-sampling mask / barcode listing for the barcode that closes (both rare: only loci with more barcodes than ds)
+struct MaskListArgs {        // by value: taking the address of the kernel parameter block would copy it to local memory
+    const int64_t* keep_off; const uint64_t* keep_umi; const uint64_t* umi_of_urank;
+    uint32_t* list_count; const int64_t* list_off; uint64_t* list_umi; uint32_t* list_first; int64_t list_cap;
+};
+template <bool LIST>
+__device__ __noinline__ bool umi_mask_and_list(MaskListArgs A, int ki, int li, uint32_t urank, uint32_t first_read) {
+    bool used = true;
+    const unsigned long long u = A.umi_of_urank[urank];
+    if (ki >= 0) {                                   // smCounter.py:496-500
+        int64_t lo = A.keep_off[ki], hi = A.keep_off[ki + 1];
+        int64_t pos = lower_bound_u64((const uint64_t*)A.keep_umi + lo, hi - lo, u);
+        used = (pos < hi - lo) && (A.keep_umi[lo + pos] == u);
+    }
+    if (LIST && li >= 0) {
+        uint32_t slot = atomicAdd(&A.list_count[li], 1u);
+        int64_t o = A.list_off[li] + slot;
+        if (o < A.list_off[li + 1] && o < A.list_cap) { A.list_umi[o] = u; A.list_first[o] = first_read; }
+    }
+    return used;
+}
+
 // calProb + the per-barcode part of vc() (smCounter.py:26-98, 506-532) for the lane's locus.
 template <bool LIST>
-__device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int ki, int li, uint32_t urank, int* fc, ulonglong2* limb,
-                                             int* ucnt, double* uprod, LaneState& S) {
+__device__ __forceinline__ void umi_finalize(const KBArgs& A, int lane, int ki, int li, uint32_t umi_slot, int* fc, ulonglong2* limb,
+                                             int* ucnt, double* uprod, MergeState& S) {
     if (S.flags & LF_UMI_SEEN) S.allMT++;
     bool used = S.flags & LF_UMI_BC;
     if (used) {
         S.nBC++;
-        if (ki >= 0) {                                   // down-sampling mask (smCounter.py:496-500)
-            unsigned long long u = A.umi_of_urank[urank];
-            int64_t lo = A.keep_off[ki], hi = A.keep_off[ki + 1];
-            int64_t pos = lower_bound_u64((const uint64_t*)A.keep_umi + lo, hi - lo, u);
-            used = (pos < hi - lo) && (A.keep_umi[lo + pos] == u);
-        }
-        if (LIST && li >= 0) {
-            uint32_t slot = atomicAdd(&A.list_count[li], 1u);
-            int64_t o = A.list_off[li] + slot;
-            if (o < A.list_off[li + 1] && o < A.list_cap) { A.list_umi[o] = A.umi_of_urank[urank]; A.list_first[o] = S.first_read; }
+        if (ki >= 0 || (LIST && li >= 0)) {
+            MaskListArgs M;
+            M.keep_off = A.keep_off; M.keep_umi = A.keep_umi; M.umi_of_urank = A.umi_of_urank; M.list_count = A.list_count;
+            M.list_off = A.list_off; M.list_umi = A.list_umi; M.list_first = A.list_first; M.list_cap = A.list_cap;
+            used = umi_mask_and_list<LIST>(M, ki, li, A.umi_urank[umi_slot], S.first_read);
         }
     }
     if (used) {
@@ -640,7 +1001,7 @@ __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int ki, 
         const uint32_t ACGT = (1u << SMC_A_A) | (1u << SMC_A_T) | (1u << SMC_A_G) | (1u << SMC_A_C);
         if (n <= A.mtDrop) {                              // :28-32 -> four zeros, a 4-way tie (:514-523)
             S.keymask |= ACGT;
-            if (n == 1) bump(A.dcnt, fc, lane, S.last_aid, KW_MT, 1u, SMC_C_MT, SMC_C_STRONG);
+            if (n == 1) bump_mt(A.T.dcnt, fc, lane, S.last_aid, 1u);
         } else if (!multi && (S.exist & ACGT) && n <= A.pcr_nmax) {
             // ---- fast path: every fragment of the barcode shows the same base a0 in {A,C,G,T}; uniq = {A,C,G,T} (:49-54).
             // Same operations in the same order as umi_general (prodP[a0] == rightP, one present allele, three pads
@@ -671,245 +1032,109 @@ __device__ __forceinline__ void umi_finalize(const K3Args& A, int lane, int ki, 
             LIMB(a0) = v;
             S.keymask |= ACGT;
             // consensus (:514-523): three pads tie at l_pad; a0 wins iff l_e > l_pad
-            if (l_e > l_pad) FCW(KW_MT, a0) += (l_e > A.smt) ? 0x10001 : 1;
-            else if (n == 1) FCW(KW_MT, a0) += 1;
+            if (l_e > l_pad) FCW(a0) += (l_e > A.smt) ? 0x10001 : 1;
+            else if (n == 1) FCW(a0) += 1;
         } else {
             if (!multi) umi_materialize(lane, ucnt, uprod, S.exist, n, S.rightP);
-            S.keymask |= umi_general(dyn_tab(A), A.pcrtab, A.pcr_nmax, A.smt, lane, n, S.exist, S.rightP, S.ndyn, S.udyn0, S.udyn1,
+            S.keymask |= umi_general(A.T, A.pcrtab, A.pcr_nmax, A.smt, lane, n, S.exist, S.rightP, S.ndyn, S.udyn0, S.udyn1,
                                      S.last_aid, fc, limb, ucnt, uprod);
         }
     }
-    S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.ndyn = 0; S.flags &= ~(LF_UMI_SEEN | LF_UMI_BC); S.first_read = 0xffffffffu;
-}
-
-// first event index >= x (x > tb) at which the barcode changes, or te
-__device__ __forceinline__ uint32_t chunk_boundary(const K3Args& A, uint32_t x, uint32_t te, int lane) {
-    while (x < te) {
-        uint32_t i = x + lane;
-        bool b = true;
-        if (i < te) b = A.recs[A.ev_read[i]].urank != A.recs[A.ev_read[i - 1]].urank;
-        uint32_t m = __ballot_sync(FULL_MASK, b);
-        if (m) { uint32_t r = x + (__ffs(m) - 1); return r < te ? r : te; }
-        x += 32;
-    }
-    return te;
-}
-
-// add the lane's packed shared-memory counters to the global 32-bit accumulators and clear them
-__device__ __noinline__ void flush_counters(int32_t* cnt, size_t nl, int* fc, int lane, int64_t L) {
-    const int lo_idx[K3_NW] = {SMC_C_ALLELE, SMC_C_R1TOT, SMC_C_R2TOT, SMC_C_LOWQ, SMC_C_CONCORD, SMC_C_MT};
-    const int hi_idx[K3_NW] = {SMC_C_FWD, SMC_C_R1LE, SMC_C_R2LE, SMC_C_R2PLE, SMC_C_DISCORD, SMC_C_STRONG};
-#pragma unroll
-    for (int a = 0; a < NF; ++a) {
-#pragma unroll
-        for (int w = 0; w < K3_NW; ++w) {
-            const uint32_t v = (uint32_t)FCW(w, a);
-            if (v) {
-                FCW(w, a) = 0;
-                const int lo = (int)(v & 0xffffu), hi = (int)(v >> 16);
-                if (lo) atomicAdd(&cnt[((size_t)a * SMC_NCNT + lo_idx[w]) * nl + L], lo);
-                if (hi) atomicAdd(&cnt[((size_t)a * SMC_NCNT + hi_idx[w]) * nl + L], hi);
-                if (w == KW_ALLELE_FWD && a != SMC_A_DEL && lo - hi) atomicAdd(&cnt[((size_t)a * SMC_NCNT + SMC_C_REV) * nl + L], lo - hi);
-            }
-        }
-    }
+    S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.ndyn = 0; S.flags = 0; S.first_read = 0xffffffffu;
 }
 
 template <bool LIST>
-__global__ void __launch_bounds__(K3_WARPS * 32, K3_MINBLOCKS) k_pileup_t(const K3Args A) {
+__global__ void __launch_bounds__(KB_WARPS * 32, KB_MINBLOCKS) k_merge_t(const KBArgs A) {
     extern __shared__ __align__(16) uint32_t smem[];
-    double* bqtab_s = reinterpret_cast<double*>(smem);
-    uint32_t* one_lut = smem + 512;                                      // nibble -> 1 << 8 * field (0 for non-ACGT)
-    for (int i = threadIdx.x; i < 256; i += K3_WARPS * 32) bqtab_s[i] = __ldg(&A.bqtab[i]);
-    if (threadIdx.x < 16) one_lut[threadIdx.x] = nib_is_acgt(threadIdx.x) ? (1u << (8u * nib_field(threadIdx.x))) : 0u;
+    double2* pq_s = reinterpret_cast<double2*>(smem);        // fragment probability (smCounter.py:65-68) and its complement (:72, :77)
+    for (int i = threadIdx.x; i < 512; i += KB_WARPS * 32) {
+        const double pf = i < 256 ? 0.1 : __ldg(&A.bqtab[i - 256]);
+        pq_s[i] = make_double2(pf, 1.0 - pf);
+    }
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* ws = smem + K3_TAB_BYTES / 4 + (size_t)w * K3_WARP_WORDS;
-    uint16_t* codes = reinterpret_cast<uint16_t*>(ws + K3_STAGE_WORDS);
-    int* fc = (int*)(ws + K3_STAGE_WORDS + K3_CODE_WORDS);
-    ulonglong2* limb = (ulonglong2*)(ws + K3_STAGE_WORDS + K3_CODE_WORDS + K3_FC_WORDS);
-    int* ucnt = (int*)(ws + K3_STAGE_WORDS + K3_CODE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS);
-    double* uprod = (double*)(ws + K3_STAGE_WORDS + K3_CODE_WORDS + K3_FC_WORDS + K3_LIMB_WORDS + K3_UCNT_WORDS);
+    uint32_t* ws = smem + KB_TAB_BYTES / 4 + (size_t)w * KB_WARP_WORDS;
+    int* fc = (int*)ws;
+    ulonglong2* limb = (ulonglong2*)(ws + KB_FC_WORDS);
+    int* ucnt = (int*)(ws + KB_FC_WORDS + KB_LIMB_WORDS);
+    double* uprod = (double*)(ws + KB_FC_WORDS + KB_LIMB_WORDS + KB_UCNT_WORDS);
 
-    const uint32_t unit = blockIdx.x * K3_WARPS + w;
-    if (unit >= A.unit_off[A.n_tiles]) return;
-    const uint32_t tile = (uint32_t)upper_slot_u32(A.unit_off, (int64_t)A.n_tiles + 1, unit);
-    const uint32_t c = unit - A.unit_off[tile];
-    const uint32_t tb = A.tile_off[tile], te = A.tile_off[tile + 1];
-    uint32_t eb = tb + c * A.chunk, ee = tb + (c + 1) * A.chunk;
-    eb = c == 0 ? tb : chunk_boundary(A, eb, te, lane);
-    ee = ee >= te ? te : chunk_boundary(A, ee, te, lane);
-    if (eb >= ee) return;
+    const uint32_t unit = blockIdx.x * KB_WARPS + w;
+    if (unit >= A.n_units) return;
+    const uint32_t F = A.unit_nfrag[unit];
+    if (F == 0) return;
+    const uint32_t eb = A.unit_eb[unit], ee = A.unit_ee[unit];
+    const uint32_t tile = A.unit_tile[unit];
+    const uint64_t so = unit_slot_base(eb, unit, A.code_mult);
+    const uint32_t cap = unit_slot_cap(ee - eb, A.code_mult);
 
     const int64_t L = (int64_t)tile * 32 + lane;
     const bool lane_valid = L < A.n_loci;
-    const int32_t p = lane_valid ? A.loci_pos[L] : 0;
-    const int32_t Li = lane_valid ? (int32_t)L : -1;                     // -1 is never inside a read's [lo, hi)
     const int ki = (lane_valid && A.keep_idx) ? A.keep_idx[L] : -1;
     const int li = (LIST && lane_valid) ? A.list_idx[L] : -1;
 
-    for (int i = lane; i < K3_FC_WORDS + K3_LIMB_WORDS; i += 32) ws[K3_STAGE_WORDS + K3_CODE_WORDS + i] = 0;
+    for (int i = lane; i < KB_FC_WORDS + KB_LIMB_WORDS; i += 32) ws[i] = 0;
     __syncwarp();
 
-    LaneState S;
-    S.cvg = S.allFrag = S.allMT = S.usedFrag = S.nBC = S.usedMT = S.mt3 = S.mt5 = S.mt7 = S.mt10 = 0;
+    MergeState S;
+    S.allFrag = S.allMT = S.usedFrag = S.nBC = S.usedMT = S.mt3 = S.mt5 = S.mt7 = S.mt10 = 0;
     S.keymask = 0; S.status = 0; S.pad_lo = S.pad_hi = 0;
-    S.r_allele = S.r_fwd = S.r_lowq = S.r_r1tot = S.r_r1le = S.r_r2tot = S.r_r2le = S.r_r2ple = S.r_conc = 0;
     S.flags = 0;
     S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.last_aid = 0; S.udyn0 = S.udyn1 = 0; S.ndyn = 0;
     S.first_read = 0xffffffffu;
-    S.f_mid = 0; S.f_bq = 0;
 
-    uint32_t carry_urank = 0xffffffffu, carry_frank = 0xffffffffu;       // barcode / fragment of the last read of the previous batch
-    const int minBQ = A.minBQ;
-    const uint8_t* __restrict__ seqp = A.seq;
-    const uint8_t* __restrict__ qualp = A.qual;
-    uint32_t since_flush = 0, since_reg_flush = 0;
-
-    for (uint32_t base = eb; base < ee; base += 32) {
-        const int nb = (int)min(32u, ee - base);
-        // ---------------- stage the next 32 read records in shared memory (4 x 128-bit loads per lane; slots past the
-        // end of the unit get an empty record); boundaries and per-read flags as warp-uniform bit masks
-        uint32_t my_urank = 0xfffffffdu, my_frank = 0xfffffffdu, my_meta = 0;
-        {
-            uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0, r2 = r0, r3 = r0;
-            if (lane < nb) {
-                const uint4* src = reinterpret_cast<const uint4*>(&A.recs[A.ev_read[base + lane]]);
-                r0 = __ldg(src); r1 = __ldg(src + 1); r2 = __ldg(src + 2); r3 = __ldg(src + 3);
-                my_urank = r2.x; my_frank = r2.y; my_meta = r0.w;
-            }
-            uint4* dst = reinterpret_cast<uint4*>(ws + lane * 16);
-            dst[0] = r0; dst[1] = r1; dst[2] = r2; dst[3] = r3;
-        }
-        uint32_t pu = __shfl_up_sync(FULL_MASK, my_urank, 1), pf = __shfl_up_sync(FULL_MASK, my_frank, 1);
-        if (lane == 0) { pu = carry_urank; pf = carry_frank; }
-        const bool first_ever = (base == eb) && lane == 0;               // nothing is open before the first read of the unit
-        const uint32_t valid = nb == 32 ? FULL_MASK : ((1u << nb) - 1u);
-        const uint32_t fragmask = __ballot_sync(FULL_MASK, my_frank != pf && !first_ever) & valid;
-        const uint32_t umimask = __ballot_sync(FULL_MASK, my_urank != pu && !first_ever) & valid;
-        const uint32_t simplemask = __ballot_sync(FULL_MASK, my_meta & RM_SIMPLE) & valid;
-        const uint32_t batch_prev_urank = carry_urank;                    // barcode that is open when this batch starts
-        carry_urank = __shfl_sync(FULL_MASK, my_urank, nb - 1); carry_frank = __shfl_sync(FULL_MASK, my_frank, nb - 1);
-        since_flush += 32; since_reg_flush += 32;
-        if (since_reg_flush > K3_REG_FLUSH) { flush_regs(fc, lane, S); since_reg_flush = 32; }
-        if (since_flush > K3_FLUSH_EVERY) {
-            flush_regs(fc, lane, S);
-            if (lane_valid) flush_counters(A.cnt, (size_t)A.n_loci, fc, lane, L);
-            since_flush = 32; since_reg_flush = 32;
-        }
-        __syncwarp();
-        // ---------------- pass A: gather base + quality of my locus, K3_GATHER reads at a time, and tally (simple reads only;
-        // the gather span of any other record is 0)
+    uint32_t umi_slot = eb;                                        // warp uniform: umi_urank[] slot of the open barcode
+    const uint4* cp = A.codes + (so >> 3) * 32 + lane;
+    const uint32_t* extp = reinterpret_cast<const uint32_t*>(A.codes) + (so + cap) * 16 + lane;   // extension rows, downward
+    const uint32_t* ffp = LIST ? A.frag_first + so * 32 + lane : nullptr;
+    uint4 v = __ldg(cp), vn = v;
+    // One pass over the F fragment codes plus a virtual "next barcode" code that closes the last barcode: a single
+    // umi_finalize site keeps the loop small in the instruction cache.
 #pragma unroll 1
-        for (int g = 0; g < nb; g += K3_GATHER) {
-            uint32_t sbv[K3_GATHER], bqv[K3_GATHER], fl[K3_GATHER];
-#pragma unroll
-            for (int u = 0; u < K3_GATHER; ++u) {
-                const uint32_t* rw = ws + (g + u) * 16;
-                const uint4 qa = *reinterpret_cast<const uint4*>(rw);        // lo gspan qk meta
-                const uint2 qb = *reinterpret_cast<const uint2*>(rw + 4);    // seq_off qual_off
-                const uint4 qw = *reinterpret_cast<const uint4*>(rw + 12);   // le_lo le_span ple_lo ple_span
-                const bool cov = (uint32_t)(Li - (int32_t)qa.x) < qa.y;
-                const uint32_t qpos = (uint32_t)(p + (int32_t)qa.z);
-                sbv[u] = 0; bqv[u] = 0;
-                if (cov) {
-                    sbv[u] = __ldg(seqp + (qb.x + (qpos >> 1)));
-                    bqv[u] = __ldg(qualp + (qb.y + qpos));
-                }
-                const bool le20 = (uint32_t)(p - (int32_t)qw.x) <= qw.y;
-                const bool ple = (uint32_t)(p - (int32_t)qw.z) <= qw.w;
-                // bits 0-3 RM_*, 4 covered, 5 le20, 6 ple, 7 odd query position
-                fl[u] = (qa.w & 15u) | (cov ? 16u : 0u) | (le20 ? 32u : 0u) | (ple ? 64u : 0u) | ((qpos & 1u) << 7);
-            }
-#pragma unroll
-            for (int u = 0; u < K3_GATHER; ++u) {
-                const uint32_t f = fl[u];
-                const uint32_t nib = (f & 128u) ? (sbv[u] & 15u) : (sbv[u] >> 4);   // 0 when not covered
-                const uint32_t bq = bqv[u];
-                const bool cov = f & 16u;
-                const uint32_t one = one_lut[nib];                                   // 0 when not covered or not A/C/G/T
-                const bool lowq = (int)bq < minBQ;
-                const bool inc = cov && !lowq && (f & RM_OK);                        // :431
-                S.cvg += cov ? 1 : 0;                                                // :368
-                tally_regular(S, one, inc ? one : 0u, f & RM_REVERSE, f & RM_READ2, lowq, f & 32u, f & 64u);
-                codes[(g + u) * 32 + lane] = (uint16_t)(bq | (nib << EC_NIB_SH) | (cov ? EC_COVERED : 0u) | ((cov && !one) ? EC_DYN : 0u) |
-                                                        (inc ? EC_INC : 0u));
-            }
+    for (uint32_t f = 0; f <= F; ++f) {
+        if ((f & 7u) == 0u) {
+            v = vn;
+            cp += 32;
+            if (f + 8u < F) vn = __ldg(cp);                            // prefetch the next group of eight
         }
-        __syncwarp();
-        // ---------------- pass B: the order-dependent part
-#pragma unroll 1
-        for (int j = 0; j < nb; ++j) {
-            const uint32_t* rw = ws + j * 16;
-            // ---- barcode / fragment boundaries (warp uniform)
-            if ((fragmask >> j) & 1u) fragment_finalize(bqtab_s, lane, ucnt, uprod, S);
-            if ((umimask >> j) & 1u) umi_finalize<LIST>(A, lane, ki, li, j ? rw[8 - 16] : batch_prev_urank, fc, limb, ucnt, uprod, S);
-            uint32_t cd, mid;
-            const bool simple = (simplemask >> j) & 1u;
-            if (simple) {
-                cd = codes[j * 32 + lane];
-                mid = (cd >> EC_NIB_SH) & 15u;
-            } else {                                                             // rare: per-event CIGAR walk, out of line
-                const uint2 ev = slow_event(dyn_tab(A), rw, A.cigar, seqp, qualp, p, Li, minBQ, A.primerDist);
-                cd = ev.x; mid = ev.y;
-                if (cd & EC_COVERED) {
-                    S.cvg++;                                                     // :368
-                    if ((cd & EC_REGULAR) && !(cd & EC_DYN)) {
-                        mid = (cd >> EC_NIB_SH) & 15u;
-                        const uint32_t one = one_lut[mid];
-                        tally_regular(S, one, (cd & EC_INC) ? one : 0u, rw[3] & RM_REVERSE, rw[3] & RM_READ2, (int)(cd & 255u) < minBQ,
-                                      cd & EC_LE20, cd & EC_PLE);
-                    } else if (!(cd & EC_REGULAR) && mid == MID_DEL) FCW(KW_ALLELE_FWD, SMC_A_DEL) += 1;   // alleleCnt only (:416-421, :459)
-                }
-            }
-            S.flags |= cd & EC_COVERED;                                          // LF_FRAG_SEEN (:463-464)
-            bool isN = false;
-            if (cd & EC_DYN) {                                                   // rare: N / IUPAC base -> dynamic allele row
-                const uint32_t meta = rw[3];
-                const int qpos = simple ? p + (int32_t)rw[2] : (int)mid;
-                const bool le20 = simple ? (uint32_t)(p - (int32_t)rw[12]) <= rw[13] : (cd & EC_LE20) != 0u;
-                const bool ple = simple ? (uint32_t)(p - (int32_t)rw[14]) <= rw[15] : (cd & EC_PLE) != 0u;
-                const uint32_t fl = ((meta & RM_REVERSE) ? 0u : 1u) | ((int)(cd & 255u) < minBQ ? 2u : 0u) | ((cd & EC_INC) ? 4u : 0u) |
-                                    ((meta & RM_READ2) ? 8u : 0u) | (le20 ? 16u : 0u) | (ple ? 32u : 0u);
-                const uint32_t e = dyn_base_event(dyn_tab(A), seqp + rw[4], (uint32_t)Li, rw[10], qpos, fl);
-                mid = MID_DYN + (e & 0x7fffffffu); isN = e >> 31;
-            }
-            if (cd & EC_INC) {                                                   // :467-479
-                const int bq = (int)(cd & 255u);
-                S.flags |= LF_UMI_BC;
-                if (LIST) S.first_read = min(S.first_read, rw[10]);
-                if (!(S.flags & LF_F_EXISTS)) { S.flags = (S.flags | LF_F_EXISTS) & ~LF_F_PAIRED; S.f_mid = mid; S.f_bq = bq; }
-                else if (mid == S.f_mid || isN) {
-                    S.f_bq = min(S.f_bq, bq); S.flags |= LF_F_PAIRED;
-                    if (mid == S.f_mid) {
-                        if (mid < MID_DEL) S.r_conc += one_lut[mid];
-                        else bump(A.dcnt, fc, lane, mid_to_aid(mid), KW_PAIR, 1u, SMC_C_CONCORD, SMC_C_DISCORD);
-                    }
-                } else { S.flags &= ~LF_F_EXISTS; bump(A.dcnt, fc, lane, mid_to_aid(mid), KW_PAIR, 0x10000u, SMC_C_CONCORD, SMC_C_DISCORD); }
-            }
+        const uint32_t cd = f < F ? (v.x & 0xffffu) : FC_UMIFIRST;
+        v.x = __funnelshift_r(v.x, v.y, 16); v.y = __funnelshift_r(v.y, v.z, 16); v.z = __funnelshift_r(v.z, v.w, 16); v.w >>= 16;
+        if ((cd & FC_UMIFIRST) && f != 0u) {                           // warp uniform: the previous barcode is complete
+            umi_finalize<LIST>(A, lane, ki, li, umi_slot, fc, limb, ucnt, uprod, S);
+            ++umi_slot;
         }
-        __syncwarp();
+        const uint32_t st = (cd >> FC_ST_SH) & 3u;
+        S.allFrag += st ? 1 : 0;                                       // :463-464
+        S.flags |= (st ? LF_UMI_SEEN : 0u) | (st & LF_UMI_BC);         // st >= 2: the barcode is a key of bcDict
+        if (LIST) { S.first_read = min(S.first_read, f < F ? __ldg(ffp) : 0xffffffffu); ffp += 32; }
+        uint32_t aid = (cd >> FC_AID_SH) & 7u;
+        if (cd & FC_EXT) {                                             // warp uniform
+            extp -= 32;
+            const uint32_t e = __ldg(extp);
+            if (aid == FC_AID_DYN) aid = NF + e;
+        }
+        if (st == 3u) {
+            const double2 pq = pq_s[((cd >> 5) & 0x100u) | (cd & 0xffu)];            // smCounter.py:65-68
+            fragment_join(pq.x, pq.y, aid, lane, ucnt, uprod, S);
+        }
     }
-    // ---- close the last fragment and barcode of the unit
-    fragment_finalize(bqtab_s, lane, ucnt, uprod, S);
-    umi_finalize<LIST>(A, lane, ki, li, carry_urank, fc, limb, ucnt, uprod, S);
     // ---- flush the lane's locus to the per-locus accumulators ([field][locus] layout: coalesced across lanes)
-    flush_regs(fc, lane, S);
     if (lane_valid) {
         const size_t nl = (size_t)A.n_loci;
-        flush_counters(A.cnt, nl, fc, lane, L);
 #pragma unroll
         for (int a = 0; a < NF; ++a) {
-            ulonglong2 v = LIMB(a);
-            if (a != SMC_A_DEL) add128(v.x, v.y, S.pad_lo, S.pad_hi);
+            const uint32_t mv = (uint32_t)FCW(a);
+            if (mv & 0xffffu) atomicAdd(&A.cnt[((size_t)a * SMC_NCNT + SMC_C_MT) * nl + L], (int)(mv & 0xffffu));
+            if (mv >> 16) atomicAdd(&A.cnt[((size_t)a * SMC_NCNT + SMC_C_STRONG) * nl + L], (int)(mv >> 16));
+            ulonglong2 v2 = LIMB(a);
+            if (a != SMC_A_DEL) add128(v2.x, v2.y, S.pad_lo, S.pad_hi);
             unsigned long long a0, a1, a2;
-            split_limbs(v.x, v.y, a0, a1, a2);
+            split_limbs(v2.x, v2.y, a0, a1, a2);
             if (a0) atomicAdd(&A.limb[((size_t)a * 3 + 0) * nl + L], a0);
             if (a1) atomicAdd(&A.limb[((size_t)a * 3 + 1) * nl + L], a1);
             if (a2) atomicAdd(&A.limb[((size_t)a * 3 + 2) * nl + L], a2);
         }
         int32_t* loc = A.loc;
-        if (S.cvg) atomicAdd(&loc[SMC_L_CVG * nl + L], S.cvg);
         if (S.allFrag) atomicAdd(&loc[SMC_L_ALLFRAG * nl + L], S.allFrag);
         if (S.allMT) atomicAdd(&loc[SMC_L_ALLMT * nl + L], S.allMT);
         if (S.usedFrag) atomicAdd(&loc[SMC_L_USEDFRAG * nl + L], S.usedFrag);
