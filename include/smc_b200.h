@@ -213,6 +213,8 @@ typedef struct smc_timings {
     int32_t kernel_launches;
     float   ms_k_gather;   /* K3a alone: base/quality gather, read tallies, fragment merge (the HBM-facing kernel) */
     float   ms_k_merge;    /* K3b alone: per-barcode posterior, prediction index, consensus (FP64) */
+    int32_t code_mult;     /* fragment-code slots per tile event in the last run: 1, or 3 after a unit overflowed (worst-case layout) */
+    int32_t dyn_capacity;  /* capacity of the dynamic-allele table in the last run (grows x4 on overflow) */
 } smc_timings;
 
 typedef struct smc_ctx smc_ctx;

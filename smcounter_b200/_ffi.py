@@ -57,7 +57,8 @@ class smc_timings(C.Structure):
                 ("ms_stats", C.c_float), ("ms_d2h", C.c_float), ("ms_total_device", C.c_float), ("ms_k_pileup", C.c_float),
                 ("n_reads", C.c_int64), ("n_loci", C.c_int64), ("n_tile_events", C.c_int64), ("n_pileup_events", C.c_int64),
                 ("n_umi_groups", C.c_int64), ("n_dyn", C.c_int64), ("n_fisher", C.c_int64), ("bytes_h2d", C.c_int64),
-                ("bytes_d2h", C.c_int64), ("kernel_launches", C.c_int32), ("ms_k_gather", C.c_float), ("ms_k_merge", C.c_float)]
+                ("bytes_d2h", C.c_int64), ("kernel_launches", C.c_int32), ("ms_k_gather", C.c_float), ("ms_k_merge", C.c_float), ("code_mult", C.c_int32),
+                ("dyn_capacity", C.c_int32)]
 
 
 EXPORTS = ("smc_version", "smc_ctx_create", "smc_ctx_destroy", "smc_last_error", "smc_call_batch", "smc_upload",

@@ -500,6 +500,10 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
     if (ctx->dyn_cap == 0) {
         uint32_t want = 1u << 16;
         while ((int64_t)want < 2 * nl && want < (1u << 28)) want <<= 1;
+        if (const char* ev = getenv("SMC_DYN_CAP0")) {            // test hook: start small to exercise the regrowth path
+            long v = atol(ev);
+            if (v >= 16 && v <= (1l << 28) && (v & (v - 1)) == 0) want = (uint32_t)v;
+        }
         ctx->dyn_cap = want;
     }
     for (int attempt = 0; attempt < 6; ++attempt) {
@@ -610,6 +614,7 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
     ctx->tm.n_pileup_events = (int64_t)cvgsum;
     ctx->tm.n_dyn = nd; ctx->tm.n_fisher = n_tasks_h;
     ctx->tm.kernel_launches = g_launches;
+    ctx->tm.code_mult = (int32_t)ctx->code_mult; ctx->tm.dyn_capacity = (int32_t)ctx->dyn_cap;
     ctx->ran = true;
     return SMC_OK;
 }

@@ -165,15 +165,17 @@ def keep_from_oracle(details, bed_order, soa):
     return UmiKeep(mapping) if mapping else None
 
 
-def run_case(intervals, spec: SynthSpec, prm: VcParams, seed: int, verbose=False):
+def run_case(intervals, spec: SynthSpec, prm: VcParams, seed: int, verbose=False, mutate=None):
     soa, refs, truth = make_panel(intervals, spec, seed=seed)
+    if mutate is not None:
+        soa = mutate(soa)
     o_rows, details = oracle_run(soa, intervals, refs, prm)
     _, bo = build_loci(intervals, soa.chroms, refs)
     keep = keep_from_oracle(details, bo, soa)
     g_rows, res, loci, bed_order, tm = gpu_run(soa, intervals, refs, prm, keep)
     problems, stats = diff_details(res, loci, bed_order, details, soa, refs)
     problems += diff_rows(g_rows, o_rows)
-    stats.update(n_downsampled=0 if keep is None else len(keep.locus), n_reads=soa.n, n_loci=loci.n, events=tm["n_pileup_events"], n_dyn=tm["n_dyn"], ms_device=tm["ms_total_device"],
+    stats.update(n_downsampled=0 if keep is None else len(keep.locus), n_reads=soa.n, n_loci=loci.n, events=tm["n_pileup_events"], n_dyn=tm["n_dyn"], code_mult=tm["code_mult"], dyn_capacity=tm["dyn_capacity"], ms_device=tm["ms_total_device"],
                  ms_pileup=tm["ms_pileup"])
     if verbose:
         print(stats)

@@ -95,3 +95,67 @@ def test_cli_end_to_end_files(tmp_path):
     assert open(prefix + ".smCounter.cut.txt").read() == cut_txt
     assert open(prefix + ".smCounter.cut.vcf").read() == cut_vcf
     assert cut_txt.count("\n") > 3 and "RepT" in all_txt and ("RepS" in all_txt or "LowC" in all_txt)
+
+
+def test_fragment_code_storage_overflow_retries_with_worst_case_layout():
+    """Single-read fragments (R1 only) with dynamic alleles nearly everywhere: a unit needs more extension rows than the
+    compact fragment-code layout holds, k_gather raises GF_CODE_FULL and the batch is re-run with the 3x layout.
+    Results must still be bit-exact."""
+    from helpers import run_case
+    import numpy as np
+    spec = SynthSpec(umis_per_locus=90, rpb=2.0, snv_every=40, snv_vaf=0.1, indel_every=9, indel_vaf=0.9, n_frac=0.02)
+
+    def r1_only(soa):
+        return soa.select(np.flatnonzero((soa.flag & 0x40) != 0))
+
+    problems, stats, _ = run_case([("chr1", 3000, 3090)], spec, VcParams(mtDepth=90, rpb=2.0), seed=41, mutate=r1_only)
+    print(stats)
+    assert stats["code_mult"] == 3, "the test input no longer overflows the compact layout"
+    assert not problems, "\n".join(problems)
+
+
+def test_barcodes_deeper_than_the_prior_table():
+    """> 192 fragments in one barcode: the PCR prior comes from device pow() instead of the host-built table."""
+    from helpers import run_case
+    spec = SynthSpec(umis_per_locus=3, rpb=260.0, snv_every=30, snv_vaf=0.3)
+    problems, stats, _ = run_case([("chr2", 900, 960)], spec, VcParams(mtDepth=3, rpb=8.0, maxMT=50), seed=43)
+    print(stats)
+    assert not problems, "\n".join(problems)
+
+
+def test_many_dynamic_alleles_grow_the_table():
+    """More distinct indel / N alleles than the initial dynamic-allele table holds: GF_DYN_FULL -> x4 -> re-run."""
+    import os
+    from helpers import run_case
+    spec = SynthSpec(umis_per_locus=40, rpb=2.0, snv_every=50, snv_vaf=0.1, indel_every=7, indel_vaf=0.3, n_frac=0.05)
+    os.environ["SMC_DYN_CAP0"] = "64"
+    try:
+        problems, stats, _ = run_case([("chr1", 500, 700)], spec, VcParams(mtDepth=40, rpb=2.0), seed=47)
+    finally:
+        del os.environ["SMC_DYN_CAP0"]
+    print(stats)
+    assert stats["dyn_capacity"] > 64 and stats["n_dyn"] > 32
+    assert not problems, "\n".join(problems)
+
+
+def test_empty_and_uncovered_batches():
+    """No reads, no loci, and reads that miss every locus: zero-coverage rows, no kernel faults."""
+    import numpy as np
+    from helpers import gpu_run, oracle_run
+    from smcounter_b200.synth import make_panel
+    ivs = [("chr1", 1000, 1040)]
+    prm = VcParams(mtDepth=20, rpb=3.0)
+    soa, refs, _ = make_panel(ivs, SynthSpec(umis_per_locus=20, rpb=3.0), seed=3)
+    # (a) no reads at all
+    empty = soa.select(np.zeros(0, dtype=np.int64))
+    rows, res, loci, _, tm = gpu_run(empty, ivs, refs, prm)
+    o_rows, _ = oracle_run(empty, ivs, refs, prm)
+    assert rows == o_rows and tm["n_pileup_events"] == 0 and all(r.endswith("Zero_Coverage") for r in rows)
+    # (b) reads that do not overlap the targets
+    far = [("chr1", 1500, 1520)]        # inside the contig, beyond every read
+    rows, res, loci, _, tm = gpu_run(soa, far, refs, prm)
+    o_rows, _ = oracle_run(soa, far, refs, prm)
+    assert rows == o_rows and tm["n_pileup_events"] == 0
+    # (c) no loci
+    rows, res, loci, _, tm = gpu_run(soa, [], refs, prm)
+    assert rows == [] and loci.n == 0
