@@ -63,37 +63,69 @@ def vc_params():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md 'clocks' line)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md 'clocks' line): NVML every 5 ms when
+    nvidia_ml_py is importable (the timed region is only a few hundred ms), else nvidia-smi every ~0.1 s."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         super().__init__(daemon=True)
         self.device = device
-        self.samples = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self.stop_flag = False
+        self.source = "nvidia-smi"
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        # torch's device index follows CUDA_VISIBLE_DEVICES; NVML's does not
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.device
+        if vis:
+            try:
+                idx = int(vis.split(",")[self.device])
+            except Exception:
+                pass
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+        names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        self.source = "nvml"
+        while not self.stop_flag:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for name, bit in names:
+                if r & bit:
+                    self.reasons.add(name)
+            time.sleep(0.005)
+
+    def _run_smi(self):
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                s = [x.strip() for x in out.split(",")] if out else []
+                if len(s) >= 8:
+                    if s[1].replace(".", "").isdigit():
+                        self.sm.append(float(s[1]))
+                    if s[2].replace(".", "").isdigit():
+                        self.mx.append(float(s[2]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
             except Exception:
                 pass
             time.sleep(0.1)
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
     def summary(self):
-        sm = [float(s[1]) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit()]
-        mx = [float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
-        reasons = set()
-        for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -291,10 +323,13 @@ def main():
                            "parallelism": "panel sharded by BED interval, no collective"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_tm["bytes_h2d"]),
                         "d2h_bytes_per_step": int(e2e_tm["bytes_d2h"]), "ms_per_step": 1000.0 * e2e_s_max / args.steps,
-                        "ms_h2d": e2e_tm["ms_h2d"], "ms_device": e2e_tm["ms_total_device"], "ms_d2h": e2e_tm["ms_d2h"]},
+                        "ms_h2d": e2e_tm["ms_h2d"], "ms_device": e2e_tm["ms_total_device"], "ms_d2h": e2e_tm["ms_d2h"],
+                        "h2d_gbs": e2e_tm["bytes_h2d"] / e2e_tm["ms_h2d"] / 1e6 if e2e_tm["ms_h2d"] > 0 else None,
+                        "upload": "pipelined: scalars first, bases/qualities in %d chunks on a copy stream, %d pileup launch pairs as they "
+                                  "arrive (ms_device overlaps ms_h2d)" % (e2e_tm["pipe_chunks"], e2e_tm["pipe_launches"])},
                 "gpu_launches": int(launches),
                 "stage_ms_rank0": {k: tms[k] for k in ("ms_prep", "ms_sort", "ms_pileup", "ms_stats", "ms_k_pileup", "ms_k_gather", "ms_k_merge")},
-                "roofline": {"bound": "hbm", "kernel": "k_pileup (fused event expansion + fragment merge + calProb + tallies)",
+                "roofline": {"bound": "hbm", "kernel": "k_gather + k_merge (K3: tile pileup = event expansion + fragment merge, then calProb / PI / consensus)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                              "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_event": ALGO_BYTES_PER_EVENT,
@@ -304,7 +339,7 @@ def main():
     caller.close()
 
     if rank == 0 and not args.no_cpu_baseline:
-        n_sample = args.cpu_loci or 48 * cores
+        n_sample = args.cpu_loci or 160 * cores          # ~10-15 s of host work
         jobs, nrec = cpu_sample_setup(soa, refs, loci, n_sample)
         v, dt, ev = cpu_run(jobs, cores)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

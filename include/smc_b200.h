@@ -215,6 +215,8 @@ typedef struct smc_timings {
     float   ms_k_merge;    /* K3b alone: per-barcode posterior, prediction index, consensus (FP64) */
     int32_t code_mult;     /* fragment-code slots per tile event in the last run: 1, or 3 after a unit overflowed (worst-case layout) */
     int32_t dyn_capacity;  /* capacity of the dynamic-allele table in the last run (grows x4 on overflow) */
+    int32_t pipe_chunks;   /* smc_call_batch: chunks the bases / qualities were uploaded in (1 = no overlap, small batch) */
+    int32_t pipe_launches; /* smc_call_batch: (k_gather, k_merge) launch pairs issued as the chunks arrived */
 } smc_timings;
 
 typedef struct smc_ctx smc_ctx;
@@ -224,7 +226,10 @@ int         smc_ctx_create(int device, const smc_params *params, smc_ctx **out);
 void        smc_ctx_destroy(smc_ctx *ctx);
 const char *smc_last_error(smc_ctx *ctx);            /* ctx may be NULL: last error of smc_ctx_create */
 
-/* One call = host buffers in, host buffers out (H2D, all kernels, D2H). */
+/* One call = host buffers in, host buffers out (H2D, all kernels, D2H).  For batches with >= 96 MiB of bases + qualities
+ * the upload is pipelined: the per-read scalars, CIGARs and loci go first; the read sort, read prep and tile sort run while
+ * the bases / qualities follow in chunks of consecutive reads on a second stream, and the pileup kernels are launched per
+ * chunk for the units whose reads have arrived.  Results are identical to smc_upload + smc_run_resident + smc_download. */
 int smc_call_batch(smc_ctx *ctx, const smc_reads_soa *reads, const smc_loci *loci, const smc_umi_keep *keep /* nullable */,
                    smc_out *out);
 

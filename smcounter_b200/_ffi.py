@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmc_b200.so")
 
 SMC_NFIXED, SMC_NCNT, SMC_NLOC = 5, 13, 12
+SMC_OK, SMC_E_CUDA, SMC_E_ARG, SMC_E_LIMIT, SMC_E_OVERFLOW, SMC_E_STATE = 0, -1, -2, -3, -4, -5
 (C_ALLELE, C_FWD, C_REV, C_LOWQ, C_R1LE, C_R1TOT, C_R2LE, C_R2TOT, C_R2PLE, C_CONCORD, C_DISCORD, C_MT,
  C_STRONG) = range(13)
 (L_CVG, L_ALLFRAG, L_ALLMT, L_USEDFRAG, L_NBC, L_USEDMT, L_MT3, L_MT5, L_MT7, L_MT10, L_KEYMASK, L_STATUS) = range(12)
@@ -58,7 +59,7 @@ class smc_timings(C.Structure):
                 ("n_reads", C.c_int64), ("n_loci", C.c_int64), ("n_tile_events", C.c_int64), ("n_pileup_events", C.c_int64),
                 ("n_umi_groups", C.c_int64), ("n_dyn", C.c_int64), ("n_fisher", C.c_int64), ("bytes_h2d", C.c_int64),
                 ("bytes_d2h", C.c_int64), ("kernel_launches", C.c_int32), ("ms_k_gather", C.c_float), ("ms_k_merge", C.c_float), ("code_mult", C.c_int32),
-                ("dyn_capacity", C.c_int32)]
+                ("dyn_capacity", C.c_int32), ("pipe_chunks", C.c_int32), ("pipe_launches", C.c_int32)]
 
 
 EXPORTS = ("smc_version", "smc_ctx_create", "smc_ctx_destroy", "smc_last_error", "smc_call_batch", "smc_upload",

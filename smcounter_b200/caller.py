@@ -191,10 +191,24 @@ class GpuCaller:
         return out
 
     def call(self, reads: ReadsSoA, loci: Loci, keep: UmiKeep | None = None, out: LocusResults | None = None) -> LocusResults:
-        """H2D + kernels + D2H; the drop-in for the per-locus vc() fan-out."""
-        self.upload(reads, loci, keep)
-        self.run()
-        return self.download(out)
+        """One ``smc_call_batch``: host buffers in, host buffers out -- the drop-in for the per-locus vc() fan-out
+        (smCounter.py:683-685).  The library overlaps the upload of the bases / qualities with the kernels that do not
+        need them.  ``out`` is reused when it fits; if the batch has more dynamic-allele rows than ``out`` holds, only the
+        download is repeated with a larger buffer (the results stay resident)."""
+        if out is None or out.n_loci != loci.n:
+            out = LocusResults(loci.n, max(4096, 4 * loci.n))
+        rs, ls = self._reads_struct(reads), self._loci_struct(loci)
+        ks = keep.as_struct() if keep is not None else None
+        self._keepalive = (reads, loci, keep)
+        self._n_loci = loci.n
+        o = out.as_struct()
+        rc = self.lib.smc_call_batch(self.h, C.byref(rs), C.byref(ls), C.byref(ks) if ks is not None else None, C.byref(o))
+        if rc == _ffi.SMC_E_LIMIT and int(o.n_dyn) > out.dyn_capacity:
+            return self.download(None)
+        if rc != 0:
+            raise self._err("smc_call_batch", rc, loci)
+        out.n_dyn = int(o.n_dyn)
+        return out
 
     def list_barcodes(self, locus_idx):
         """Barcodes of bcDict for the given (ascending) loci of the last batch: (off[n+1], umi codes, first passing read)."""

@@ -46,6 +46,11 @@ struct smc_ctx {
     std::string err;
     cudaStream_t st = nullptr;
     cudaEvent_t ev[12]{};
+    // pipelined upload of smc_call_batch: bases / qualities arrive in chunks on st_copy while st already computes
+    cudaStream_t st_copy = nullptr;
+    cudaEvent_t ev_scal = nullptr, ev_chunk[SMC_PIPE_MAX]{};
+    PipeBounds pipe{};                          // pipe.n > 1: the chunk events of the current batch are pending / recorded
+    uint32_t pipe_end[SMC_PIPE_MAX]{};          // launch c of the pileup kernels covers units [pipe_end[c-1], pipe_end[c])
     // resident inputs
     int64_t n_reads = 0, n_loci = 0, n_keep_loci = 0, n_keep_umi = 0;
     int64_t seq_bytes = 0, qual_bytes = 0, n_cigar_words = 0;
@@ -213,6 +218,9 @@ extern "C" int smc_ctx_create(int device, const smc_params* params, smc_ctx** ou
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_scal, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    for (auto& ev : ctx->ev_chunk) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     // host-computed tables (glibc pow, the same libm CPython calls): 10^(-bq/10) and the PCR prior
     std::vector<double> bq(256);
     for (int q = 0; q < 256; ++q) bq[q] = std::pow(10.0, -(double)q / 10.0);                          // smCounter.py:469
@@ -244,6 +252,7 @@ extern "C" int smc_ctx_create(int device, const smc_params* params, smc_ctx** ou
 extern "C" void smc_ctx_destroy(smc_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->st_copy) cudaStreamSynchronize(ctx->st_copy);
     cudaStreamSynchronize(ctx->st);
     DevBuf* bufs[] = {&ctx->d_ref_id, &ctx->d_pos, &ctx->d_flag, &ctx->d_mapq, &ctx->d_nm, &ctx->d_lseq, &ctx->d_seq_off, &ctx->d_qual_off,
                       &ctx->d_cig_off, &ctx->d_ncig, &ctx->d_umi, &ctx->d_frag, &ctx->d_seq, &ctx->d_qual, &ctx->d_cigar, &ctx->d_loci_ref,
@@ -260,12 +269,27 @@ extern "C" void smc_ctx_destroy(smc_ctx* ctx) {
                       &ctx->d_list_idx, &ctx->d_list_count, &ctx->d_list_off, &ctx->d_list_umi, &ctx->d_list_first};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_chunk) if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_scal) cudaEventDestroy(ctx->ev_scal);
+    if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-extern "C" int smc_upload(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc, const smc_umi_keep* K) {
+// Number of chunks the bases / qualities of a batch are uploaded in by smc_call_batch (1 = plain upload).
+static int pipe_chunks_for(const smc_reads_soa* R) {
+    if (const char* ev = getenv("SMC_PIPE_CHUNKS")) { long v = atol(ev); if (v >= 1 && v <= SMC_PIPE_MAX) return (int)v; }
+    const int64_t payload = R->seq_bytes + R->qual_bytes;
+    if (R->n_reads < 65536 || payload < (96ll << 20)) return 1;
+    const int64_t g = payload / (48ll << 20);
+    return (int)(g < 2 ? 2 : g > 12 ? 12 : g);
+}
+
+// pipelined = false: everything on ctx->st, synchronised on return (smc_upload).
+// pipelined = true : scalars / CIGAR / loci on ctx->st; bases and qualities in ctx->pipe.n chunks of consecutive reads on
+//                    ctx->st_copy, one event per chunk; returns without waiting (smc_call_batch synchronises both streams).
+static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc, const smc_umi_keep* K, bool pipelined) {
     if (!ctx) return SMC_E_ARG;
     if (!R || !Lc) { ctx->err = "smc_upload: null reads/loci"; return SMC_E_ARG; }
     if (R->n_reads < 0 || Lc->n_loci < 0) { ctx->err = "smc_upload: negative size"; return SMC_E_ARG; }
@@ -276,6 +300,8 @@ extern "C" int smc_upload(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* 
     CK(cudaSetDevice(ctx->device));
     ctx->uploaded = false; ctx->ran = false;
     const int64_t n = R->n_reads, nl = Lc->n_loci;
+    const int G = pipelined ? pipe_chunks_for(R) : 1;
+    ctx->pipe.n = 0;
     CK(cudaEventRecord(ctx->ev[0], ctx->st));
     int64_t bytes = 0;
 #define UP(buf, src, count, T)                                                                                   \
@@ -288,7 +314,7 @@ extern "C" int smc_upload(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* 
     UP(ctx->d_mapq, R->mapq, n, uint8_t); UP(ctx->d_nm, R->nm, n, int32_t); UP(ctx->d_lseq, R->l_seq, n, int32_t);
     UP(ctx->d_seq_off, R->seq_off, n, int64_t); UP(ctx->d_qual_off, R->qual_off, n, int64_t); UP(ctx->d_cig_off, R->cigar_off, n, int64_t);
     UP(ctx->d_ncig, R->n_cigar, n, uint16_t); UP(ctx->d_umi, R->umi, n, uint64_t); UP(ctx->d_frag, R->frag_id, n, uint32_t);
-    UP(ctx->d_seq, R->seq, R->seq_bytes, uint8_t); UP(ctx->d_qual, R->qual, R->qual_bytes, uint8_t);
+    if (G == 1) { UP(ctx->d_seq, R->seq, R->seq_bytes, uint8_t); UP(ctx->d_qual, R->qual, R->qual_bytes, uint8_t); }
     UP(ctx->d_cigar, R->cigar, R->n_cigar_words, uint32_t);
     UP(ctx->d_loci_ref, Lc->ref_id, nl, int32_t); UP(ctx->d_loci_pos, Lc->pos0, nl, int32_t); UP(ctx->d_loci_base, Lc->ref_base, nl, uint8_t);
     ctx->has_keep = K && K->n_loci > 0;
@@ -308,15 +334,47 @@ extern "C" int smc_upload(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* 
 #undef UP
     CK(ctx->d_loci_key.ensure((size_t)(nl ? nl : 1) * 8));
     LAUNCH(k_loci_keys, nblk(nl, 256), 256, 0, ctx->d_loci_ref.as<int32_t>(), ctx->d_loci_pos.as<int32_t>(), nl, ctx->d_loci_key.as<uint64_t>());
-    CK(cudaEventRecord(ctx->ev[1], ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
     ctx->n_reads = n; ctx->n_loci = nl;
     ctx->seq_bytes = R->seq_bytes; ctx->qual_bytes = R->qual_bytes; ctx->n_cigar_words = R->n_cigar_words;
     ctx->tm = smc_timings{};
-    cudaEventElapsedTime(&ctx->tm.ms_h2d, ctx->ev[0], ctx->ev[1]);
-    ctx->tm.bytes_h2d = bytes; ctx->tm.n_reads = n; ctx->tm.n_loci = nl;
+    ctx->tm.n_reads = n; ctx->tm.n_loci = nl;
+    if (G == 1) {
+        CK(cudaEventRecord(ctx->ev[1], ctx->st));
+        if (!pipelined) {
+            CK(cudaStreamSynchronize(ctx->st));
+            cudaEventElapsedTime(&ctx->tm.ms_h2d, ctx->ev[0], ctx->ev[1]);
+        }
+    } else {
+        // the chunks follow the scalars on the link; everything up to the first pileup launch needs the scalars only
+        CK(ctx->d_seq.ensure((size_t)R->seq_bytes + 16)); CK(ctx->d_qual.ensure((size_t)R->qual_bytes + 16));
+        PipeBounds& B = ctx->pipe;
+        for (int c = 0; c <= G; ++c) {
+            const int64_t r = c == G ? n : (n / G) * c;
+            B.r[c] = r;
+            B.seq[c] = c == G ? R->seq_bytes : std::min<int64_t>(std::max<int64_t>(R->seq_off[r], c ? B.seq[c - 1] : 0), R->seq_bytes);
+            B.qual[c] = c == G ? R->qual_bytes : std::min<int64_t>(std::max<int64_t>(R->qual_off[r], c ? B.qual[c - 1] : 0), R->qual_bytes);
+        }
+        B.seq[0] = 0; B.qual[0] = 0;                        // bytes before the first read's offset travel with chunk 0
+        CK(cudaEventRecord(ctx->ev_scal, ctx->st));
+        CK(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_scal, 0));
+        for (int c = 0; c < G; ++c) {
+            const size_t sb = (size_t)(B.seq[c + 1] - B.seq[c]), qb = (size_t)(B.qual[c + 1] - B.qual[c]);
+            if (sb) CK(cudaMemcpyAsync(ctx->d_seq.as<uint8_t>() + B.seq[c], R->seq + B.seq[c], sb, cudaMemcpyHostToDevice, ctx->st_copy));
+            if (qb) CK(cudaMemcpyAsync(ctx->d_qual.as<uint8_t>() + B.qual[c], R->qual + B.qual[c], qb, cudaMemcpyHostToDevice, ctx->st_copy));
+            CK(cudaEventRecord(ctx->ev_chunk[c], ctx->st_copy));
+            bytes += (int64_t)(sb + qb);
+        }
+        CK(cudaEventRecord(ctx->ev[1], ctx->st_copy));
+        B.n = G;
+    }
+    ctx->tm.pipe_chunks = pipelined ? G : 0;
+    ctx->tm.bytes_h2d = bytes;
     ctx->uploaded = true;
     return SMC_OK;
+}
+
+extern "C" int smc_upload(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc, const smc_umi_keep* K) {
+    return upload_impl(ctx, R, Lc, K, false);
 }
 
 static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE);
@@ -434,6 +492,27 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
     ctx->ev_read_sorted = ev_read_sorted;
     ctx->n_tiles = n_tiles; ctx->n_tile_events = NE;
     (void)ev_key_sorted;
+    if (ctx->pipe.n > 1 && NE > 0) {
+        // which units may start after which chunk: a unit needs the chunk that holds its last read (BAM index)
+        const int G = ctx->pipe.n;
+        uint32_t init[1 + SMC_PIPE_MAX];
+        init[0] = 0u;
+        for (int c = 0; c < SMC_PIPE_MAX; ++c) init[1 + c] = ctx->n_units_cap;
+        uint32_t* pd = small + 16;                      // [16] layout flag, [17 ..] first blocked unit per chunk
+        CK(cudaMemcpyAsync(pd, init, sizeof(init), cudaMemcpyHostToDevice, ctx->st));
+        LAUNCH(k_pipe_check_layout, nblk(n, 256), 256, 0, ctx->d_lseq.as<int32_t>(), ctx->d_seq_off.as<int64_t>(),
+               ctx->d_qual_off.as<int64_t>(), n, ctx->pipe, pd);
+        LAUNCH(k_pipe_unit_need, nblk((int64_t)ctx->n_units_cap * 32, 256), 256, 0, ctx->d_unit_eb.as<uint32_t>(),
+               ctx->d_unit_ee.as<uint32_t>(), ev_read_sorted, ctx->d_recs.as<ReadRec>(), ctx->n_units_cap, ctx->pipe, pd + 1);
+        uint32_t h[1 + SMC_PIPE_MAX];
+        CK(cudaMemcpyAsync(h, pd, sizeof(h), cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        uint32_t run = ctx->n_units_cap;
+        for (int c = G - 1; c >= 0; --c) {
+            if (c < G - 1) run = std::min(run, h[1 + c]);
+            ctx->pipe_end[c] = (h[0] && c < G - 1) ? 0u : run;      // layout not in read order: everything waits for the last chunk
+        }
+    }
     CK(cudaEventRecord(ctx->ev[4], ctx->st));
     return run_pileup_and_stats(ctx, n_tiles, NE);
 }
@@ -524,9 +603,25 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
             KAArgs A; KBArgs B;
             fill_kargs(ctx, A, B, false, ctx->has_keep);
             CK(cudaEventRecord(ctx->ev[8], ctx->st));
-            LAUNCH(k_gather_t<false>, nblk(ctx->n_units_cap, KA_WARPS), KA_WARPS * 32, KA_SMEM_BYTES(false), A);
-            CK(cudaEventRecord(ctx->ev[9], ctx->st));
-            LAUNCH(k_merge_t<false>, nblk(ctx->n_units_cap, KB_WARPS), KB_WARPS * 32, KB_SMEM_BYTES, B);
+            if (ctx->pipe.n > 1) {
+                // pipelined upload: units [pipe_end[c-1], pipe_end[c]) start as soon as chunk c of the bases / qualities is in
+                uint32_t u0 = 0;
+                ctx->tm.pipe_launches = 0;
+                for (int c = 0; c < ctx->pipe.n; ++c) {
+                    CK(cudaStreamWaitEvent(ctx->st, ctx->ev_chunk[c], 0));
+                    const uint32_t u1 = ctx->pipe_end[c];
+                    if (u1 <= u0) continue;
+                    A.unit0 = B.unit0 = u0; A.n_units = B.n_units = u1;
+                    LAUNCH(k_gather_t<false>, nblk(u1 - u0, KA_WARPS), KA_WARPS * 32, KA_SMEM_BYTES(false), A);
+                    LAUNCH(k_merge_t<false>, nblk(u1 - u0, KB_WARPS), KB_WARPS * 32, KB_SMEM_BYTES, B);
+                    u0 = u1; ++ctx->tm.pipe_launches;
+                }
+                CK(cudaEventRecord(ctx->ev[9], ctx->st));
+            } else {
+                LAUNCH(k_gather_t<false>, nblk(ctx->n_units_cap, KA_WARPS), KA_WARPS * 32, KA_SMEM_BYTES(false), A);
+                CK(cudaEventRecord(ctx->ev[9], ctx->st));
+                LAUNCH(k_merge_t<false>, nblk(ctx->n_units_cap, KB_WARPS), KB_WARPS * 32, KB_SMEM_BYTES, B);
+            }
             CK(cudaEventRecord(ctx->ev[10], ctx->st));
         }
         uint32_t h[3];
@@ -665,9 +760,19 @@ extern "C" int smc_download(smc_ctx* ctx, smc_out* out) {
 }
 
 extern "C" int smc_call_batch(smc_ctx* ctx, const smc_reads_soa* reads, const smc_loci* loci, const smc_umi_keep* keep, smc_out* out) {
-    int rc = smc_upload(ctx, reads, loci, keep);
-    if (rc) return rc;
-    rc = smc_run_resident(ctx);
+    // Bases and qualities (3/4 of the bytes) are uploaded in chunks on a second stream while the kernels that only need the
+    // per-read scalars already run; the pileup kernels are launched per chunk as the data arrives (upload_impl,
+    // smc_run_resident).  Whatever happens, no copy may still read the caller's buffers when this returns.
+    int rc = upload_impl(ctx, reads, loci, keep, true);
+    if (rc == SMC_OK) rc = smc_run_resident(ctx);
+    if (ctx) {
+        cudaError_t e1 = cudaStreamSynchronize(ctx->st_copy), e2 = cudaStreamSynchronize(ctx->st);
+        if (rc == SMC_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+            ctx->err = std::string("smc_call_batch: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2); rc = SMC_E_CUDA;
+        }
+        if (rc == SMC_OK && ctx->uploaded) cudaEventElapsedTime(&ctx->tm.ms_h2d, ctx->ev[0], ctx->ev[1]);
+        ctx->pipe.n = 0;                                 // the batch is resident now: later smc_run_resident calls run it in one go
+    }
     if (rc) return rc;
     return smc_download(ctx, out);
 }

@@ -184,6 +184,46 @@ k_unit_bounds(const uint32_t* __restrict__ tile_off, const uint32_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Pipelined upload (smc_call_batch): bases and qualities arrive in up to SMC_PIPE_MAX chunks of consecutive reads while
+// the read sort / prep / tile sort already run; a unit may start once the chunk holding its LAST read (BAM index) is on
+// the device.  Chunk c holds reads [r[c], r[c+1]), i.e. bytes [seq[c], seq[c+1]) of seq[] and [qual[c], qual[c+1]) of qual[].
+// ------------------------------------------------------------------------------------------------------------
+#define SMC_PIPE_MAX 16
+struct PipeBounds { int n; int64_t r[SMC_PIPE_MAX + 1]; int64_t seq[SMC_PIPE_MAX + 1]; int64_t qual[SMC_PIPE_MAX + 1]; };
+
+__device__ __forceinline__ int pipe_chunk_of(const PipeBounds& B, int64_t read) {
+    int c = 0;
+    while (c + 1 < B.n && read >= B.r[c + 1]) ++c;
+    return c;
+}
+// every read's bases / qualities must lie inside its chunk's byte range (true for any SoA laid out in read order);
+// otherwise *bad is set and the host waits for the whole upload before the first pileup launch
+__global__ void __launch_bounds__(256)
+k_pipe_check_layout(const int32_t* __restrict__ l_seq, const int64_t* __restrict__ seq_off, const int64_t* __restrict__ qual_off,
+                    int64_t n, const PipeBounds B, uint32_t* __restrict__ bad) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int c = pipe_chunk_of(B, r);
+    const int64_t l = l_seq[r], s0 = seq_off[r], q0 = qual_off[r];
+    if (l > 0 && (s0 < B.seq[c] || s0 + (l + 1) / 2 > B.seq[c + 1] || q0 < B.qual[c] || q0 + l > B.qual[c + 1])) *bad = 1u;
+}
+// first_blocked[c] = smallest unit that has to wait for chunk c + 1 (one warp per unit)
+__global__ void __launch_bounds__(256)
+k_pipe_unit_need(const uint32_t* __restrict__ unit_eb, const uint32_t* __restrict__ unit_ee, const uint32_t* __restrict__ ev_read,
+                 const ReadRec* __restrict__ recs, uint32_t n_units, const PipeBounds B, uint32_t* __restrict__ first_blocked) {
+    const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (u >= n_units) return;
+    const uint32_t eb = unit_eb[u], ee = unit_ee[u];
+    uint32_t m = 0;
+    for (uint32_t e = eb + lane; e < ee; e += 32) m = max(m, __ldg(&recs[__ldg(&ev_read[e])].read_idx));
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(FULL_MASK, m, d));
+    if (lane == 0 && eb < ee) {
+        const int c = pipe_chunk_of(B, (int64_t)m);
+        if (c > 0) atomicMin(&first_blocked[c - 1], u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Fragment codes: what k_gather hands to k_merge, 16 bits per (fragment, locus); a unit's codes are stored in groups of
 // eight per lane (one 128-bit word), so both kernels move them with fully coalesced 512-byte warp transactions.
 //   bits 0-7   effective base quality of the fragment (min over a concordant pair)
@@ -289,7 +329,9 @@ __device__ __noinline__ uint32_t dyn_lookup(DynTab T, unsigned long long key, ui
 
 struct KAArgs {
     const GRec* grec; const ReadRec* recs; const uint32_t* ev_read; const uint8_t* ev_flags; const uint32_t* urank_s;
-    const uint32_t* unit_eb; const uint32_t* unit_ee; const uint32_t* unit_tile; uint32_t n_units; uint32_t code_mult;
+    const uint32_t* unit_eb; const uint32_t* unit_ee; const uint32_t* unit_tile;
+    uint32_t unit0, n_units;      // this launch covers units [unit0, n_units)
+    uint32_t code_mult;
     const int32_t* loci_pos; int64_t n_loci;
     const uint8_t* seq; const uint8_t* qual; const uint32_t* cigar;
     int minBQ, primerDist;
@@ -499,7 +541,7 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
     uint32_t* cst = ws + 256 + 32 + 512;                              // fragment-code staging: word [k >> 1][lane], half k & 1
     uint32_t* fst = ws + 256 + 32 + 512 + 128;                        // LIST: [k][lane]
 
-    const uint32_t unit = blockIdx.x * KA_WARPS + w;
+    const uint32_t unit = A.unit0 + blockIdx.x * KA_WARPS + w;
     if (unit >= A.n_units) return;
     const uint32_t eb = A.unit_eb[unit], ee = A.unit_ee[unit];
     if (eb >= ee) { if (lane == 0) A.unit_nfrag[unit] = 0; return; }
@@ -716,7 +758,9 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
 
 struct KBArgs {
     const uint4* codes; const uint32_t* unit_nfrag; const uint32_t* frag_first; const uint32_t* umi_urank;
-    const uint32_t* unit_eb; const uint32_t* unit_ee; const uint32_t* unit_tile; uint32_t n_units; uint32_t code_mult;
+    const uint32_t* unit_eb; const uint32_t* unit_ee; const uint32_t* unit_tile;
+    uint32_t unit0, n_units;      // this launch covers units [unit0, n_units)
+    uint32_t code_mult;
     int64_t n_loci;
     const double* bqtab;            // [256]  10^(-bq/10), host glibc pow (smCounter.py:469)
     const double* pcrtab;           // [3][(nmax+1)(nmax+2)/2]  10^(-6 (cnt+.5)/(n+.5k)), k = 4,5,6 (smCounter.py:80-81)
@@ -1059,7 +1103,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32, KB_MINBLOCKS) k_merge_t(const K
     int* ucnt = (int*)(ws + KB_FC_WORDS + KB_LIMB_WORDS);
     double* uprod = (double*)(ws + KB_FC_WORDS + KB_LIMB_WORDS + KB_UCNT_WORDS);
 
-    const uint32_t unit = blockIdx.x * KB_WARPS + w;
+    const uint32_t unit = A.unit0 + blockIdx.x * KB_WARPS + w;
     if (unit >= A.n_units) return;
     const uint32_t F = A.unit_nfrag[unit];
     if (F == 0) return;

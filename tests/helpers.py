@@ -175,7 +175,7 @@ def run_case(intervals, spec: SynthSpec, prm: VcParams, seed: int, verbose=False
     g_rows, res, loci, bed_order, tm = gpu_run(soa, intervals, refs, prm, keep)
     problems, stats = diff_details(res, loci, bed_order, details, soa, refs)
     problems += diff_rows(g_rows, o_rows)
-    stats.update(n_downsampled=0 if keep is None else len(keep.locus), n_reads=soa.n, n_loci=loci.n, events=tm["n_pileup_events"], n_dyn=tm["n_dyn"], code_mult=tm["code_mult"], dyn_capacity=tm["dyn_capacity"], ms_device=tm["ms_total_device"],
+    stats.update(n_downsampled=0 if keep is None else len(keep.locus), n_reads=soa.n, n_loci=loci.n, events=tm["n_pileup_events"], n_dyn=tm["n_dyn"], code_mult=tm["code_mult"], dyn_capacity=tm["dyn_capacity"], pipe_chunks=tm["pipe_chunks"], pipe_launches=tm["pipe_launches"], ms_device=tm["ms_total_device"],
                  ms_pileup=tm["ms_pileup"])
     if verbose:
         print(stats)

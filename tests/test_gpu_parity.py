@@ -159,3 +159,88 @@ def test_empty_and_uncovered_batches():
     # (c) no loci
     rows, res, loci, _, tm = gpu_run(soa, [], refs, prm)
     assert rows == [] and loci.n == 0
+
+
+def _with_env(name, value, fn):
+    import os
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
+
+
+PIPE_IVS = [("chr1", 1000, 1150), ("chr1", 4000, 4100), ("chr2", 300, 420), ("chr3", 50, 130)]
+PIPE_SPEC = dict(umis_per_locus=50, rpb=3.0, snv_every=40, snv_vaf=0.1, indel_every=35, indel_vaf=0.1, n_frac=0.01)
+
+
+def test_pipelined_upload_chunks_match_oracle():
+    """smc_call_batch with the bases / qualities uploaded in 5 chunks on the copy stream (forced: the test batch is far
+    below the size where the library pipelines on its own): the pileup kernels are launched per chunk for the units
+    whose reads have arrived; every tally, PI and row must still match the oracle."""
+    from helpers import run_case
+    problems, stats, _ = _with_env("SMC_PIPE_CHUNKS", "5", lambda: run_case(PIPE_IVS, SynthSpec(**PIPE_SPEC), VcParams(mtDepth=50, rpb=3.0), seed=53))
+    print(stats)
+    assert stats["pipe_chunks"] == 5 and stats["pipe_launches"] >= 3
+    assert not problems, "\n".join(problems)
+
+
+def test_pipelined_upload_with_payload_out_of_read_order():
+    """Bases / qualities stored in REVERSE read order: a read's bytes are not in its chunk, the layout check fires and
+    every unit waits for the last chunk (one launch pair).  Results unchanged."""
+    import numpy as np
+    from helpers import run_case
+
+    def reverse_payload(soa):
+        sb = (soa.l_seq.astype(np.int64) + 1) // 2
+        lq = soa.l_seq.astype(np.int64)
+        order = np.arange(soa.n)[::-1]
+        new_seq_off = np.zeros(soa.n, np.int64); new_qual_off = np.zeros(soa.n, np.int64)
+        new_seq_off[order] = np.concatenate(([0], np.cumsum(sb[order])))[:-1]
+        new_qual_off[order] = np.concatenate(([0], np.cumsum(lq[order])))[:-1]
+        seq = np.zeros_like(soa.seq); qual = np.zeros_like(soa.qual)
+        for r in range(soa.n):
+            seq[new_seq_off[r]:new_seq_off[r] + sb[r]] = soa.seq[soa.seq_off[r]:soa.seq_off[r] + sb[r]]
+            qual[new_qual_off[r]:new_qual_off[r] + lq[r]] = soa.qual[soa.qual_off[r]:soa.qual_off[r] + lq[r]]
+        soa.seq, soa.qual, soa.seq_off, soa.qual_off = seq, qual, new_seq_off, new_qual_off
+        return soa
+
+    problems, stats, _ = _with_env("SMC_PIPE_CHUNKS", "4", lambda: run_case(PIPE_IVS[:2], SynthSpec(**PIPE_SPEC), VcParams(mtDepth=50, rpb=3.0),
+                                                                          seed=59, mutate=reverse_payload))
+    print(stats)
+    assert stats["pipe_chunks"] == 4 and stats["pipe_launches"] == 1
+    assert not problems, "\n".join(problems)
+
+
+def test_pipelined_call_equals_resident_rerun():
+    """smc_call_batch (pipelined) and a later smc_run_resident + smc_download of the same, now resident, batch give
+    bit-identical outputs -- including the FP64 ones (the PI sums are order independent by construction)."""
+    import numpy as np
+    from smcounter_b200.caller import GpuCaller
+    from smcounter_b200.synth import make_panel
+    from smcounter_b200.targets import build_loci
+    prm = VcParams(mtDepth=50, rpb=3.0)
+    soa, refs, _ = make_panel(PIPE_IVS, SynthSpec(**PIPE_SPEC), seed=61)
+    loci, _ = build_loci(PIPE_IVS, soa.chroms, refs)
+
+    def go():
+        c = GpuCaller(prm, 0)
+        a = c.call(soa, loci)
+        assert c.timings()["pipe_chunks"] == 6
+        c.run()
+        b = c.download(None)
+        c.close()
+        return a, b
+
+    a, b = _with_env("SMC_PIPE_CHUNKS", "6", go)
+    assert a.n_dyn == b.n_dyn and a.n_dyn > 0
+    for f in ("loc", "cnt", "pi", "max_allele", "second_allele", "alt_allele", "alt_pi", "second_pi", "fl1", "fl2", "biallelic"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    for f in ("fisher_p", "fisher_or"):
+        assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), f
+    for f in ("dyn_locus", "dyn_kind", "dyn_site", "dyn_len", "dyn_iskey", "dyn_cnt", "dyn_pi"):
+        assert np.array_equal(getattr(a, f)[:a.n_dyn], getattr(b, f)[:a.n_dyn]), f
