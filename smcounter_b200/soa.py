@@ -75,6 +75,30 @@ class ReadsSoA:
             seq=gather(self.seq, self.seq_off[idx], sb), qual=gather(self.qual, self.qual_off[idx], l_seq),
             cigar=gather(self.cigar, self.cigar_off[idx], nc), chroms=self.chroms, umi_names=self.umi_names)
 
+    def repack(self, block: int = 1 << 18) -> "ReadsSoA":
+        """Same reads, with bases / qualities / CIGARs stored in read order (what a BAM decode produces).  libsmc_b200
+        accepts any layout, but only a read-ordered payload lets smc_call_batch overlap the upload with the kernels."""
+        l_seq = self.l_seq.astype(np.int64)
+        sb = (l_seq + 1) // 2
+        nc = self.n_cigar.astype(np.int64)
+        out = {}
+        for name, src, offs, lens in (("seq", self.seq, self.seq_off, sb), ("qual", self.qual, self.qual_off, l_seq),
+                                      ("cigar", self.cigar, self.cigar_off, nc)):
+            new_off = np.concatenate(([0], np.cumsum(lens)))
+            dst = np.empty(int(new_off[-1]), dtype=src.dtype)
+            for a in range(0, self.n, block):
+                b = min(self.n, a + block)
+                ln = lens[a:b]
+                tot = int(ln.sum())
+                if tot:
+                    starts = np.repeat(offs[a:b] - (new_off[a:b] - new_off[a]), ln)
+                    dst[new_off[a]:new_off[b]] = src[starts + np.arange(tot, dtype=np.int64)]
+            out[name] = (dst, new_off[:-1].copy())
+        return ReadsSoA(ref_id=self.ref_id, pos=self.pos, flag=self.flag, mapq=self.mapq, nm=self.nm, l_seq=self.l_seq,
+                        seq_off=out["seq"][1], qual_off=out["qual"][1], cigar_off=out["cigar"][1], n_cigar=self.n_cigar, umi=self.umi,
+                        frag_id=self.frag_id, seq=out["seq"][0], qual=out["qual"][0], cigar=out["cigar"][0], chroms=self.chroms,
+                        umi_names=self.umi_names)
+
     def ref_end(self) -> np.ndarray:
         """0-based exclusive reference end of every read (host-side helper for sharding)."""
         ops = self.cigar & 0xF

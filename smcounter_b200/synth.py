@@ -356,10 +356,11 @@ def merge_soas(parts, chroms):
     cig_off = np.concatenate([p.cigar_off + o for p, o in zip(parts, np.cumsum([0] + [len(p.cigar) for p in parts])[:-1])])
     ref_id, pos = cat("ref_id"), cat("pos")
     order = np.lexsort((np.arange(len(pos)), pos, ref_id))
-    return ReadsSoA(ref_id=ref_id[order], pos=pos[order], flag=cat("flag")[order], mapq=cat("mapq")[order], nm=cat("nm")[order],
-                    l_seq=cat("l_seq")[order], seq_off=seq_off[order], qual_off=qual_off[order], cigar_off=cig_off[order],
-                    n_cigar=cat("n_cigar")[order], umi=cat("umi")[order], frag_id=relabel_frag_ids(frag[order]),
-                    seq=cat("seq"), qual=cat("qual"), cigar=cat("cigar"), chroms=list(chroms))
+    soa = ReadsSoA(ref_id=ref_id[order], pos=pos[order], flag=cat("flag")[order], mapq=cat("mapq")[order], nm=cat("nm")[order],
+                   l_seq=cat("l_seq")[order], seq_off=seq_off[order], qual_off=qual_off[order], cigar_off=cig_off[order],
+                   n_cigar=cat("n_cigar")[order], umi=cat("umi")[order], frag_id=relabel_frag_ids(frag[order]),
+                   seq=cat("seq"), qual=cat("qual"), cigar=cat("cigar"), chroms=list(chroms))
+    return soa.repack()          # payload in read order, as a BAM decode delivers it
 
 
 def _mp_job(args):

@@ -247,3 +247,33 @@ def test_shard_plan_covers_everything_and_balances():
     for i in range(s.n):
         touches = any(s.chroms[s.ref_id[i]] == c and s.pos[i] < b and ends[i] > a for (c, a, b) in (ivs[0], ivs[12]))
         assert touches == (i in set(idx.tolist()))
+
+
+def test_repack_puts_payload_in_read_order():
+    """ReadsSoA.repack(): same reads, bases / qualities / CIGARs stored in read order (the layout a BAM decode delivers
+    and the one smc_call_batch can overlap with compute); merge_soas() output already has it."""
+    import numpy as np
+    from oracle import smcounter_oracle as orc
+    from smcounter_b200.soa import soa_to_records
+    from smcounter_b200.synth import SynthSpec, make_panel, make_panel_mp
+    ivs = [("chr1", 1000, 1100), ("chr2", 300, 380), ("chr1", 5000, 5060)]
+    spec = SynthSpec(umis_per_locus=30, rpb=3.0, indel_every=30, indel_vaf=0.1, softclip_frac=0.2)
+    soa, _, _ = make_panel(ivs, spec, seed=5)
+    rev = soa.select(np.arange(soa.n))
+    # scramble: store the payload back to front
+    order = np.arange(soa.n)[::-1]
+    sb = (soa.l_seq.astype(np.int64) + 1) // 2
+    so = np.zeros(soa.n, np.int64); so[order] = np.concatenate(([0], np.cumsum(sb[order])))[:-1]
+    seq = np.zeros_like(soa.seq)
+    for r in range(soa.n):
+        seq[so[r]:so[r] + sb[r]] = soa.seq[soa.seq_off[r]:soa.seq_off[r] + sb[r]]
+    rev.seq, rev.seq_off = seq, so
+    packed = rev.repack(block=37)
+    a, b = soa_to_records(soa, orc.Read), soa_to_records(packed, orc.Read)
+    assert all(x.seq == y.seq and x.qual == y.qual and x.cigar == y.cigar for x, y in zip(a, b))
+    for f in ("seq_off", "qual_off", "cigar_off"):
+        assert (np.diff(getattr(packed, f)) >= 0).all()
+    merged, _, _ = make_panel_mp(ivs, spec, seed=5, workers=2)
+    for f in ("seq_off", "qual_off", "cigar_off", ):
+        assert (np.diff(getattr(merged, f)) >= 0).all()
+    assert (np.diff(merged.ref_id.astype(np.int64) << 32 | merged.pos) >= 0).all()
