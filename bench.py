@@ -147,30 +147,42 @@ def cpu_sample_setup(soa, refs, loci, n_loci_sample):
     import numpy as np
     from oracle import smcounter_oracle as orc
     from smcounter_b200.soa import soa_to_records
-    mid = loci.n // 2
-    sel = np.arange(max(0, mid - n_loci_sample // 2), min(loci.n, mid - n_loci_sample // 2 + n_loci_sample))
-    rid = int(loci.ref_id[sel[0]])
-    sel = sel[loci.ref_id[sel] == rid]
-    lo, hi = int(loci.pos0[sel[0]]), int(loci.pos0[sel[-1]]) + 1
+    n_loci_sample = max(1, min(int(n_loci_sample), loci.n))
+    a = max(0, loci.n // 2 - n_loci_sample // 2)
+    sel = np.arange(a, min(loci.n, a + n_loci_sample))
     ends = soa.ref_end()
-    ridx = np.flatnonzero((soa.ref_id == rid) & (soa.pos < hi) & (ends > lo))
-    recs = soa_to_records(soa.select(ridx), orc.Read)
+    mask = np.zeros(soa.n, dtype=bool)
+    for rid in np.unique(loci.ref_id[sel]):
+        p = loci.pos0[sel[loci.ref_id[sel] == rid]]
+        # one window per run of nearby loci (an interval), so that reads between distant intervals are not dragged in
+        cuts = np.flatnonzero(np.diff(p) > 1000)
+        for lo_i, hi_i in zip(np.concatenate(([0], cuts + 1)), np.concatenate((cuts, [len(p) - 1]))):
+            lo, hi = int(p[lo_i]), int(p[hi_i]) + 1
+            mask |= (soa.ref_id == rid) & (soa.pos < hi) & (ends > lo)
+    recs = soa_to_records(soa.select(np.flatnonzero(mask)), orc.Read)
     _G["index"] = orc.ReadIndex(recs)
     _G["refs"] = refs
     _G["prm"] = vc_params()
-    jobs = [(soa.chroms[rid], str(int(loci.pos0[i]) + 1)) for i in sel]
+    jobs = [(soa.chroms[int(loci.ref_id[i])], str(int(loci.pos0[i]) + 1)) for i in sel]
     return jobs, len(recs)
 
 
-def cpu_run(jobs, cores):
+def cpu_run(jobs, cores, pool=None):
+    """loci/s of the oracle port over ``jobs`` on ``cores`` worker processes (the reference's Pool(nCPU) fan-out,
+    smCounter.py:683-685); the pool is created and warmed outside the timed region."""
     import multiprocessing as mp
+    own = None
+    if cores > 1 and pool is None:
+        own = pool = mp.get_context("fork").Pool(cores)
+        pool.map(_cpu_worker, jobs[:cores], chunksize=1)
     t0 = time.perf_counter()
     if cores > 1:
-        with mp.get_context("fork").Pool(cores) as pool:
-            rows = pool.map(_cpu_worker, jobs, chunksize=1)
+        rows = pool.map(_cpu_worker, jobs, chunksize=1)
     else:
         rows = [_cpu_worker(j) for j in jobs]
     dt = time.perf_counter() - t0
+    if own is not None:
+        own.close(); own.join()
     events = sum(int(r.split("\t")[5]) for r in rows if r.split("\t")[5])
     return len(jobs) / dt, dt, events
 
@@ -191,12 +203,16 @@ def main():
         mine, soa, refs, loci, bed_order = make_batch(args, 0, 1)
         n_sample = args.cpu_loci or 48 * cores
         jobs, nrec = cpu_sample_setup(soa, refs, loci, n_sample)
+        import multiprocessing as mp
+        pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
         for _ in range(min(args.warmup, 1)):
-            cpu_run(jobs[:max(1, cores)], cores)
+            cpu_run(jobs[:max(1, 2 * cores)], cores, pool)
         vals, times, ev = [], [], 0
         for _ in range(args.steps):
-            v, dt, ev = cpu_run(jobs, cores)
+            v, dt, ev = cpu_run(jobs, cores, pool)
             vals.append(v); times.append(dt)
+        if pool is not None:
+            pool.close(); pool.join()
         value = len(jobs) * len(times) / sum(times)
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
