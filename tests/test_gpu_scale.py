@@ -1,0 +1,180 @@
+"""-m gpu: the CUDA path at the sizes and shapes BASELINE.json names (configs 2, 3 and 5), where the oracle can no
+longer be run over every locus.  Each test checks
+
+  * size-independent properties of the outputs (coverage recomputed independently from the read spans, the counter
+    identities of smCounter.py:368-460 / :482-532, idempotence of a resident re-run, independence of the result from how
+    the BED intervals are sharded over contexts), and
+  * a seeded random sample of loci (always including the spiked variant sites) against the CPU oracle, row for row.
+"""
+import numpy as np
+import pytest
+
+from smcounter_b200 import _ffi
+from smcounter_b200.caller import GpuCaller, VcParams
+from smcounter_b200.rows import format_rows
+from smcounter_b200.synth import SynthSpec, make_panel_mp, panel_intervals_from_bed
+from smcounter_b200.targets import build_loci, loc_list
+
+pytestmark = pytest.mark.gpu
+
+
+def _coverage_from_spans(soa, loci):
+    """cvg per locus (smCounter.py:368) recomputed on the host: reads with pos <= p < reference_end (htslib column
+    membership; deletions count, there are no N ops in the synthetic reads)."""
+    ends = soa.ref_end()
+    out = np.zeros(loci.n, dtype=np.int64)
+    key = (loci.ref_id.astype(np.int64) << 32) | loci.pos0.astype(np.int64)
+    lo = np.searchsorted(key, (soa.ref_id.astype(np.int64) << 32) | soa.pos.astype(np.int64), side="left")
+    hi = np.searchsorted(key, (soa.ref_id.astype(np.int64) << 32) | ends, side="left")
+    diff = np.zeros(loci.n + 1, dtype=np.int64)
+    np.add.at(diff, lo, 1)
+    np.add.at(diff, hi, -1)
+    out[:] = np.cumsum(diff)[:-1]
+    return out
+
+
+def _check_properties(res, soa, loci):
+    L, Cn = res.loc, res.cnt
+    cvg = L[_ffi.L_CVG].astype(np.int64)
+    assert np.array_equal(cvg, _coverage_from_spans(soa, loci)), "cvg differs from the read spans"
+    n = loci.n
+    dyn_allele = np.zeros(n, dtype=np.int64)
+    if res.n_dyn:
+        np.add.at(dyn_allele, res.dyn_locus[:res.n_dyn], res.dyn_cnt[:res.n_dyn, _ffi.C_ALLELE])
+    # every pileup read is counted under exactly one allele (:379, :401, :459)
+    assert np.array_equal(Cn[:, _ffi.C_ALLELE, :].sum(axis=0) + dyn_allele, cvg)
+    for a in range(_ffi.SMC_NFIXED):
+        if a == _ffi.A_DEL:       # in-deletion reads have no strand tally (:454-457 sits in the regular-base branch)
+            assert not Cn[a, _ffi.C_FWD].any() and not Cn[a, _ffi.C_REV].any()
+            continue
+        assert np.array_equal(Cn[a, _ffi.C_FWD] + Cn[a, _ffi.C_REV], Cn[a, _ffi.C_ALLELE])
+        assert (Cn[a, _ffi.C_LOWQ] <= Cn[a, _ffi.C_ALLELE]).all()
+        assert (Cn[a, _ffi.C_R1LE] <= Cn[a, _ffi.C_R1TOT]).all() and (Cn[a, _ffi.C_R2LE] <= Cn[a, _ffi.C_R2TOT]).all()
+        assert (Cn[a, _ffi.C_R2PLE] <= Cn[a, _ffi.C_R2TOT]).all()
+        assert (Cn[a, _ffi.C_STRONG] <= Cn[a, _ffi.C_MT]).all()
+    assert (L[_ffi.L_USEDMT] <= L[_ffi.L_NBC]).all() and (L[_ffi.L_NBC] <= L[_ffi.L_ALLMT]).all()
+    assert (L[_ffi.L_USEDFRAG] <= L[_ffi.L_ALLFRAG]).all() and (L[_ffi.L_ALLFRAG] <= cvg).all()
+    assert (L[_ffi.L_ALLMT] <= L[_ffi.L_ALLFRAG]).all()
+    assert (L[_ffi.L_MT10] <= L[_ffi.L_MT7]).all() and (L[_ffi.L_MT7] <= L[_ffi.L_MT5]).all()
+    assert (L[_ffi.L_MT5] <= L[_ffi.L_MT3]).all() and (L[_ffi.L_MT3] <= L[_ffi.L_USEDMT]).all()
+    mt = Cn[:, _ffi.C_MT, :].sum(axis=0).astype(np.int64)
+    if res.n_dyn:
+        np.add.at(mt, res.dyn_locus[:res.n_dyn], res.dyn_cnt[:res.n_dyn, _ffi.C_MT])
+    assert (mt <= L[_ffi.L_USEDMT]).all()                       # at most one consensus allele per used barcode (:514-523)
+    assert not (L[_ffi.L_STATUS] & ~1).any(), "unexpected status bits (down-sampling / overflow)"
+    assert np.isfinite(res.pi).all() and (res.pi >= 0).all()
+
+
+def _oracle_rows_for(soa, refs, prm, positions):
+    """Oracle rows for [(chrom, pos0)] using only the reads that overlap them."""
+    from oracle import smcounter_oracle as orc
+    from smcounter_b200.soa import soa_to_records
+    cidx = {c: i for i, c in enumerate(soa.chroms)}
+    ends = soa.ref_end()
+    mask = np.zeros(soa.n, dtype=bool)
+    for (c, p) in positions:
+        mask |= (soa.ref_id == cidx[c]) & (soa.pos <= p) & (ends > p)
+    index = orc.ReadIndex(soa_to_records(soa.select(np.flatnonzero(mask)), orc.Read))
+    return [orc.vc(index, c, str(p + 1), prm.minBQ, prm.minMQ, prm.mtDepth, prm.rpb, prm.hpLen, prm.mismatchThr, prm.mtDrop,
+                   prm.maxMT, prm.primerDist, refs) for (c, p) in positions]
+
+
+def _sample_positions(intervals, truth, rng, n_random, n_truth):
+    allpos = [(c, p) for (c, s, e) in intervals for p in range(s, e)]
+    inside = set(allpos)
+    picks = [allpos[i] for i in rng.choice(len(allpos), size=min(n_random, len(allpos)), replace=False)]
+    spiked = [(c, p) for kind in ("snv", "ins", "del") for (c, p, *_) in truth[kind] if (c, p) in inside]
+    picks += spiked[:n_truth]
+    return list(dict.fromkeys(picks))
+
+
+def _run(soa, intervals, refs, prm):
+    loci, bed_order = build_loci(intervals, soa.chroms, refs)
+    caller = GpuCaller(prm, 0)
+    res = caller.call(soa, loci)
+    tm = caller.timings()
+    return caller, res, loci, bed_order, tm
+
+
+def _rows_by_position(rows, intervals):
+    return {cp: r for cp, r in zip([(c, int(p) - 1) for (c, p) in loc_list(intervals)], rows)}
+
+
+def _compare_with_oracle(g_rows, intervals, soa, refs, prm, truth, seed, n_random, n_truth):
+    from helpers import diff_rows
+    picks = _sample_positions(intervals, truth, np.random.default_rng(seed), n_random, n_truth)
+    want = _oracle_rows_for(soa, refs, prm, picks)
+    by_pos = _rows_by_position(g_rows, intervals)
+    problems = diff_rows([by_pos[cp] for cp in picks], want)
+    assert not problems, "\n".join(problems)
+    return len(picks)
+
+
+def test_cfg2_panel_batch_properties_sharding_and_oracle_sample():
+    """BASELINE config 2 at bench depth: N0030 panel intervals, ~3 000 barcodes per locus, rpb 4, 2 x 150 bp (a 24-interval
+    batch, ~0.7 M reads, large enough for the library to pipeline the upload on its own)."""
+    import os
+    from smcounter_b200.smCounter import call_loci
+    bed = os.path.join(os.path.dirname(__file__), "golden", "n0030_panel.bed")
+    ivs = panel_intervals_from_bed(bed, limit=24, seed=7)
+    spec = SynthSpec(umis_per_locus=3000, rpb=4.0, snv_every=400, snv_vaf=0.01, indel_every=1500, indel_vaf=0.01)
+    prm = VcParams(mtDepth=3000, rpb=4.0)
+    soa, refs, truth = make_panel_mp(ivs, spec, seed=11)
+    caller, res, loci, bed_order, tm = _run(soa, ivs, refs, prm)
+    try:
+        assert tm["pipe_chunks"] >= 2 and tm["pipe_launches"] >= 2, tm
+        assert tm["n_pileup_events"] > 3e7
+        _check_properties(res, soa, loci)
+        g_rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order)
+        # idempotence: the resident batch run again, one launch instead of per-chunk launches -> identical bits
+        caller.run()
+        again = caller.download(None)
+        for f in ("loc", "cnt", "pi", "alt_allele", "alt_pi", "fl1", "fl2"):
+            assert np.array_equal(getattr(res, f), getattr(again, f)), f
+    finally:
+        caller.close()
+    n = _compare_with_oracle(g_rows, ivs, soa, refs, prm, truth, seed=3, n_random=10, n_truth=6)
+    assert n >= 10
+    # the same panel as three shards (three contexts, depth-balanced interval groups): rows identical to the single batch
+    assert call_loci(soa, ivs, refs, prm, gpus=3, devices=[0, 0, 0]) == g_rows
+
+
+def test_cfg3_deep_low_vaf_shape():
+    """BASELINE config 3 shape: 20 000 barcodes per locus (E ~ 1e5 reads per locus, hundreds of units per tile), 0.5 % VAF
+    spike-ins, mtDepth 20000 (ds = 40 000: no down-sampling)."""
+    ivs = [("chr7", 55000, 55048)]
+    spec = SynthSpec(umis_per_locus=20000, rpb=4.0, snv_every=12, snv_vaf=0.005)
+    prm = VcParams(mtDepth=20000, rpb=4.0)
+    soa, refs, truth = make_panel_mp(ivs, spec, seed=2)
+    caller, res, loci, bed_order, tm = _run(soa, ivs, refs, prm)
+    try:
+        _check_properties(res, soa, loci)
+        assert int(res.loc[_ffi.L_USEDMT].max()) > 10000
+        g_rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order)
+    finally:
+        caller.close()
+    _compare_with_oracle(g_rows, ivs, soa, refs, prm, truth, seed=5, n_random=2, n_truth=2)
+
+
+def test_cfg5_many_loci_many_contigs_shape():
+    """BASELINE config 5 shape, scaled: 1 200 intervals x 200 bp over 24 contigs (240 000 loci, > 7 000 tiles), shallow and
+    with log-normal depth per interval; also run as 8 depth-balanced shards (the 8-GPU plan, here on one device)."""
+    from smcounter_b200.smCounter import call_loci
+    rng = np.random.default_rng(4)
+    ivs = []
+    for k in range(1200):
+        c = "chr%d" % (1 + k % 24)
+        s = 1000 + 700 * (k // 24) + int(rng.integers(0, 100))
+        ivs.append((c, s, s + 200))
+    spec = SynthSpec(umis_per_locus=10, rpb=2.0, snv_every=500, snv_vaf=0.3, indel_every=3000, indel_vaf=0.3, depth_sigma=0.5)
+    prm = VcParams(mtDepth=10, rpb=2.0, maxMT=400)
+    soa, refs, truth = make_panel_mp(ivs, spec, seed=4)
+    caller, res, loci, bed_order, tm = _run(soa, ivs, refs, prm)
+    try:
+        assert loci.n == 240000
+        _check_properties(res, soa, loci)
+        g_rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order)
+    finally:
+        caller.close()
+    _compare_with_oracle(g_rows, ivs, soa, refs, prm, truth, seed=9, n_random=40, n_truth=20)
+    assert call_loci(soa, ivs, refs, prm, gpus=8, devices=[0] * 8) == g_rows
