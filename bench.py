@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-loci", type=int, default=0, help="loci in the CPU-baseline sample (0 = 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline-intervals", type=int, default=12,
+                    help="intervals of the rank-0 batch run once through the whole CLI path (BAM decode -> files); 0 = skip")
     return ap.parse_args()
 
 
@@ -185,6 +187,44 @@ def cpu_run(jobs, cores, pool=None):
         own.close(); own.join()
     events = sum(int(r.split("\t")[5]) for r in rows if r.split("\t")[5])
     return len(jobs) / dt, dt, events
+
+
+def pipeline_leg(args, mine, soa, refs, device):
+    """The whole reference-facing path once, stage by stage, on the first ``--pipeline-intervals`` intervals of the rank-0
+    batch: BAM file -> libsmc_bamio decode -> SoA -> smc_call_batch -> 45-column rows -> repeat filters -> the three output
+    files (what smCounter.main() does, smCounter.py:645-909).  north_star asks for the end-to-end figure including the
+    BAM decode beside the kernel-only one; the BAM itself is written outside the timed stages."""
+    import shutil
+    import tempfile
+    import numpy as np
+    from smcounter_b200 import bam, repeats, writers
+    from smcounter_b200.shard import reads_for_intervals
+    from smcounter_b200.smCounter import call_loci
+    ivs = mine[:args.pipeline_intervals]
+    sub = soa.select(reads_for_intervals(soa, ivs, soa.chroms))
+    tmp = tempfile.mkdtemp(prefix="smc_pipe_")
+    try:
+        path = os.path.join(tmp, "reads.bam")
+        bam.write_bam(path, sub, refs.lengths)
+        t = [time.perf_counter()]
+        reads = bam.read_bam(path, ivs, threads=os.cpu_count() or 1)
+        t.append(time.perf_counter())
+        rows = call_loci(reads, ivs, refs, vc_params(), gpus=1, devices=[device], stage_times=(st := {}))
+        t.append(time.perf_counter())
+        target_rows = [(c, str(s), str(e)) for (c, s, e) in ivs]
+        trf, rm = repeats.build_repeat_regions(target_rows, [], [])
+        rows = repeats.apply_repeat_filters(rows, trf, rm)
+        writers.write_outputs(rows, os.path.join(tmp, "out"), 3000, 0)
+        t.append(time.perf_counter())
+        n_loci = sum(e - s for (_, s, e) in ivs)
+        return {"value": n_loci / (t[3] - t[0]), "unit": UNIT, "loci": n_loci, "reads": int(reads.n), "intervals": len(ivs),
+                "bam_mb": os.path.getsize(path) / 1e6, "ms_bam_decode": 1e3 * (t[1] - t[0]), "ms_call_loci": 1e3 * (t[2] - t[1]),
+                "ms_gpu_call": st.get("ms_gpu_call"), "ms_format_rows": st.get("ms_format_rows"),
+                "ms_filters_and_writers": 1e3 * (t[3] - t[2]),
+                "what": "BAM decode (libsmc_bamio, all host threads) + smc_call_batch + row formatting + repeat filters + the three "
+                        "output files, once, on a sub-batch of the rank-0 panel batch"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def main():
@@ -353,6 +393,12 @@ def main():
                              "events_per_s": float(tms["n_pileup_events"]) / kp_avg_s if kp_avg_s > 0 else 0.0},
                 "clocks": sampler.summary(), "n_dyn_alleles_rank0": int(n_dyn), "n_fisher_rank0": int(tms["n_fisher"])}
     caller.close()
+
+    if rank == 0 and args.pipeline_intervals > 0:
+        try:
+            line["pipeline"] = pipeline_leg(args, mine, soa, refs, local_rank)
+        except Exception as e:          # the extra leg must never cost the bench line
+            line["pipeline"] = {"error": repr(e)}
 
     if rank == 0 and not args.no_cpu_baseline:
         n_sample = args.cpu_loci or 160 * cores          # ~10-15 s of host work

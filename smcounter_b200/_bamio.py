@@ -6,7 +6,7 @@ import os
 
 import numpy as np
 
-from .soa import ReadsSoA, umi_string
+from .soa import ReadsSoA, umi_strings_bulk
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmc_bamio.so")
@@ -86,10 +86,9 @@ def read_bam_native(path: str, intervals=None, threads: int = 0) -> ReadsSoA:
         names = {}
         for i in range(out.n_dict_umis):
             names[(1 << 63) | i] = lib.smc_bam_dict_umi(h, i).decode()
-        for code in np.unique(umi):
-            code = int(code)
-            if not code >> 63:
-                names[code] = umi_string(code)
+        packed = np.unique(umi)
+        packed = packed[(packed >> np.uint64(63)) == 0]
+        names.update(zip(packed.tolist(), umi_strings_bulk(packed)))
         return ReadsSoA(
             ref_id=_arr(out.ref_id, n, np.int32), pos=_arr(out.pos, n, np.int32), flag=_arr(out.flag, n, np.uint16),
             mapq=_arr(out.mapq, n, np.uint8), nm=_arr(out.nm, n, np.int32), l_seq=_arr(out.l_seq, n, np.int32),

@@ -64,12 +64,14 @@ def argParseInit():
     parser.add_argument('--gpus', type=int, default=1, help='number of B200 GPUs to shard the target over (BED intervals, balanced by depth)')
 
 
-def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None):
+def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None, stage_times: dict | None = None):
     """The drop-in for the reference's per-locus fan-out: rows of vc() (45 tab-joined fields each, FILTER still in
     accumulator form) for every position of ``intervals`` in BED order.
 
     ``reads``: ReadsSoA of the BAM; ``refs``: object with fetch()/get_reference_length().  One host thread per GPU
-    (ctypes drops the GIL); a failing shard fails the run like smCounter.py:690-694."""
+    (ctypes drops the GIL); a failing shard fails the run like smCounter.py:690-694.  ``stage_times`` (optional dict)
+    receives the wall-clock ms of the device calls and of the row formatting, summed over shards."""
+    import time
     chroms = reads.chroms
     devices = list(devices) if devices is not None else list(range(max(1, gpus)))
     plan = plan_shards(reads, intervals, chroms, len(devices))
@@ -85,14 +87,20 @@ def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None
             sub = reads if len(plan) == 1 else reads.select(reads_for_intervals(reads, ivs, chroms))
             loci, bed_order = build_loci(ivs, chroms, refs)
             caller = GpuCaller(prm, devices[g])
+            t0 = time.perf_counter()
             try:
                 res = caller.call(sub, loci)
                 keep = draw_keep_masks(caller, res, sub, loci, chroms, prm)        # smCounter.py:496-500
                 if keep is not None:
                     res = caller.call(sub, loci, keep)
             finally:
+                t1 = time.perf_counter()
                 caller.close()
+            t2 = time.perf_counter()
             shard_rows[g] = format_rows(res, sub, loci, chroms, refs, prm.hpLen, bed_order)
+            if stage_times is not None:
+                stage_times["ms_gpu_call"] = stage_times.get("ms_gpu_call", 0.0) + 1e3 * (t1 - t0)
+                stage_times["ms_format_rows"] = stage_times.get("ms_format_rows", 0.0) + 1e3 * (time.perf_counter() - t2)
         except BaseException as e:          # noqa: BLE001 -- re-raised on the main thread
             errors[g] = e
 

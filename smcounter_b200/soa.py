@@ -153,6 +153,34 @@ def umi_string(code: int, names: dict | None = None) -> str:
     return "".join(reversed(s))
 
 
+def umi_strings_bulk(codes: np.ndarray) -> list:
+    """umi_string() for an array of 2-bit packed codes (top bit clear), vectorised per barcode length."""
+    codes = np.asarray(codes, dtype=np.uint64)
+    out = [None] * len(codes)
+    if len(codes) == 0:
+        return out
+    nbits = np.zeros(len(codes), dtype=np.int64)           # position of the length sentinel bit
+    v = codes.copy()
+    for sh in (32, 16, 8, 4, 2, 1):
+        m = (v >> np.uint64(sh)) != 0
+        nbits[m] += sh
+        v[m] >>= np.uint64(sh)
+    length = nbits // 2
+    for L in np.unique(length):
+        idx = np.flatnonzero(length == L)
+        if L == 0:
+            for i in idx:
+                out[i] = ""
+            continue
+        shifts = (2 * np.arange(L - 1, -1, -1)).astype(np.uint64)
+        digits = ((codes[idx, None] >> shifts[None, :]) & np.uint64(3)).astype(np.intp)
+        chars = np.frombuffer(b"ACGT", dtype=np.uint8)[digits]
+        strs = np.ascontiguousarray(chars).view("S%d" % L).ravel()
+        for i, b in zip(idx, strs):
+            out[i] = b.decode()
+    return out
+
+
 def pack_seq(seq: str) -> np.ndarray:
     codes = _NT16_LUT[np.frombuffer(seq.encode(), dtype=np.uint8)]
     if len(codes) & 1:
