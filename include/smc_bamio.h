@@ -7,7 +7,8 @@
  * (BC = qname.split(':')[-2], readid = ':'.join(parts[:-2])), NM follows :329-334 (first NM tag, else 0).
  * Unmapped records are dropped (htslib never piles them up); nothing else is filtered (stepper='nofilter').
  *
- * BGZF blocks are inflated by `threads` host threads (zlib); the record walk is sequential.
+ * BGZF blocks are inflated by `threads` host threads (zlib); the record decode runs on the same number of threads (only the
+ * numbering of fragments by first appearance is a sequential pass).
  * All returned pointers stay valid until smc_bam_close().  Functions return 0 or a negative code; message via
  * smc_bam_last_error().
  */

@@ -29,6 +29,7 @@ struct smc_bam {
     std::vector<std::string> ref_names;
     std::vector<int64_t> ref_lens;
     size_t first_record = 0;
+    int threads = 1;
     // decoded buffers
     std::vector<int32_t> ref_id, pos, nm, l_seq;
     std::vector<uint16_t> flag, n_cigar;
@@ -107,6 +108,7 @@ extern "C" int smc_bam_open(const char* path, int threads, smc_bam** out) {
     if (got != file.size()) { g_open_error = "smc_bam_open: short read"; return -1; }
     smc_bam* h = new smc_bam();
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    h->threads = threads;
     if (inflate_all(file, threads, h->raw, g_open_error) != 0) { delete h; return -1; }
     const std::vector<uint8_t>& r = h->raw;
     if (r.size() < 12 || memcmp(r.data(), "BAM\1", 4) != 0) { g_open_error = "not a BAM file (bad magic)"; delete h; return -1; }
@@ -171,6 +173,39 @@ static int32_t first_nm(const uint8_t* p, const uint8_t* end) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Record decode, four passes:
+//   1 (serial)    record boundaries (block_size chain);
+//   2 (threads)   per record: fields, interval filter, barcode code, 128-bit hash of the (barcode, readid) identity;
+//   3 (serial)    compaction offsets of the kept reads; fragment ids by first appearance (open-addressing table on the
+//                 hash, every hit verified on the name bytes, so ids are exact); dictionary of non-ACGT / long barcodes;
+//   4 (threads)   scalars and payloads copied to their final places.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+struct RecInfo {
+    uint32_t keep;                 // 1 kept, 0 dropped
+    uint32_t bc_off, bc_len;       // barcode bytes inside qname
+    uint32_t rid_len;              // readid = qname[0, rid_len)
+    uint64_t h1, h2;               // hash of (barcode, readid)
+    uint64_t code;                 // packed barcode, 0 = needs the dictionary
+};
+
+inline uint64_t mix64(uint64_t x) { x ^= x >> 32; x *= 0xd6e8feb86659fd93ull; x ^= x >> 32; x *= 0xd6e8feb86659fd93ull; x ^= x >> 32; return x; }
+inline void hash_bytes(const uint8_t* p, size_t n, uint64_t& a, uint64_t& b) {
+    while (n >= 8) { uint64_t w; memcpy(&w, p, 8); a = mix64(a ^ w); b = (b + w) * 0x9e3779b97f4a7c15ull; b ^= b >> 29; p += 8; n -= 8; }
+    uint64_t w = 0; memcpy(&w, p, n);
+    a = mix64(a ^ w ^ ((uint64_t)n << 56)); b = (b + w + n) * 0x9e3779b97f4a7c15ull; b ^= b >> 29;
+}
+
+template <class F> void parallel_for(size_t n, int threads, F f) {          // f(begin, end, thread)
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, (n + 4095) / 4096));
+    std::vector<std::thread> ts;
+    for (int t = 1; t < nt; ++t) ts.emplace_back([=]() { f(n * t / nt, n * (t + 1) / nt, t); });
+    f(0, n / nt, 0);
+    for (auto& t : ts) t.join();
+}
+}  // namespace
+
 extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, const int32_t* iv_start, const int32_t* iv_end,
                               smc_bam_reads* out) {
     if (!h || !out || (n_iv > 0 && (!iv_ref || !iv_start || !iv_end))) { if (h) h->err = "smc_bam_decode: null argument"; return -2; }
@@ -186,84 +221,154 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
     }
     auto touches = [&](int32_t rid, int64_t s, int64_t e) -> bool {
         const auto& v = iv[rid];
-        // intervals with start < e
-        size_t lo = 0, hi = v.size();
+        size_t lo = 0, hi = v.size();                                           // intervals with start < e
         while (lo < hi) { size_t mid = (lo + hi) / 2; if (v[mid].first < e) lo = mid + 1; else hi = mid; }
         return lo > 0 && v[lo - 1].second > s;
     };
-    h->ref_id.clear(); h->pos.clear(); h->nm.clear(); h->l_seq.clear(); h->flag.clear(); h->n_cigar.clear(); h->mapq.clear();
-    h->seq.clear(); h->qual.clear(); h->seq_off.clear(); h->qual_off.clear(); h->cigar_off.clear(); h->umi.clear(); h->frag_id.clear();
-    h->cigar.clear(); h->dict_umis.clear();
-    std::unordered_map<std::string, uint64_t> umi_dict;
-    std::unordered_map<std::string, uint32_t> frag_dict;
-    frag_dict.reserve(1 << 20);
     const std::vector<uint8_t>& r = h->raw;
-    size_t p = h->first_record;
-    std::string fkey;
-    while (p + 4 <= r.size()) {
+    const int threads = std::max(1, h->threads);
+    // ---- pass 1: record boundaries
+    std::vector<size_t> offs;
+    offs.reserve(r.size() / 200 + 16);
+    for (size_t p = h->first_record; p + 4 <= r.size();) {
         const int32_t bs = rdi32(&r[p]);
         if (bs < 32 || p + 4 + (size_t)bs > r.size()) { h->err = "truncated BAM record at offset " + std::to_string(p); return -1; }
-        const uint8_t* b = &r[p + 4];
-        const uint8_t* rec_end = b + bs;
+        offs.push_back(p);
         p += 4 + (size_t)bs;
-        const int32_t refID = rdi32(b), pos = rdi32(b + 4);
-        const uint8_t l_rn = b[8], mapq = b[9];
-        const uint16_t n_cig = rd16(b + 12), flag = rd16(b + 14);
-        const int32_t l_seq = rdi32(b + 16);
-        const char* qname = reinterpret_cast<const char*>(b + 32);
-        const uint8_t* cig = b + 32 + l_rn;
-        const uint8_t* sq = cig + 4 * (size_t)n_cig;
-        const size_t sb = ((size_t)l_seq + 1) / 2;
-        const uint8_t* ql = sq + sb;
-        if (l_seq < 0 || ql + l_seq > rec_end) { h->err = "malformed BAM record (field lengths exceed block_size)"; return -1; }
-        if ((flag & 0x4) || refID < 0 || (size_t)refID >= nref) continue;
-        if (n_iv > 0) {
-            int64_t reflen = 0;
-            for (uint16_t k = 0; k < n_cig; ++k) {
-                const uint32_t cw = rd32(cig + 4 * k), op = cw & 15u;
-                if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) reflen += cw >> 4;
-            }
-            if (!touches(refID, pos, (int64_t)pos + reflen)) continue;
-        }
-        // identity: BC = parts[-2], readid = ':'.join(parts[:-2])   (smCounter.py:319-325)
-        const size_t qn = l_rn ? (size_t)l_rn - 1 : 0;
-        long c1 = -1, c2 = -1;                  // last and second-to-last ':'
-        for (long i = (long)qn - 1; i >= 0; --i)
-            if (qname[i] == ':') { if (c1 < 0) c1 = i; else { c2 = i; break; } }
-        std::string bc, readid;
-        if (c1 < 0) { bc = ""; readid = ""; }                                   // fewer than 2 fields: parts[-2] would raise in Python
-        else if (c2 < 0) { bc.assign(qname, (size_t)c1); readid = ""; }
-        else { bc.assign(qname + c2 + 1, (size_t)(c1 - c2 - 1)); readid.assign(qname, (size_t)c2); }
-        uint64_t code = 1;
-        bool packable = bc.size() <= 31;
-        if (packable)
-            for (char ch : bc) {
-                const int k = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : -1;
-                if (k < 0) { packable = false; break; }
-                code = (code << 2) | (uint64_t)k;
-            }
-        if (!packable) {
-            auto it = umi_dict.find(bc);
-            if (it == umi_dict.end()) {
-                code = (1ull << 63) | (uint64_t)umi_dict.size();
-                umi_dict.emplace(bc, code);
-                h->dict_umis.push_back(bc);
-            } else code = it->second;
-        }
-        fkey.assign(bc); fkey.push_back('\x1f'); fkey.append(readid);
-        auto fit = frag_dict.find(fkey);
-        uint32_t fid;
-        if (fit == frag_dict.end()) { fid = (uint32_t)frag_dict.size(); frag_dict.emplace(fkey, fid); } else fid = fit->second;
-        h->ref_id.push_back(refID); h->pos.push_back(pos); h->flag.push_back(flag); h->mapq.push_back(mapq);
-        h->nm.push_back(first_nm(ql + l_seq, rec_end)); h->l_seq.push_back(l_seq); h->n_cigar.push_back(n_cig);
-        h->seq_off.push_back((int64_t)h->seq.size()); h->qual_off.push_back((int64_t)h->qual.size());
-        h->cigar_off.push_back((int64_t)h->cigar.size());
-        h->umi.push_back(code); h->frag_id.push_back(fid);
-        h->seq.insert(h->seq.end(), sq, sq + sb);
-        h->qual.insert(h->qual.end(), ql, ql + l_seq);
-        for (uint16_t k = 0; k < n_cig; ++k) h->cigar.push_back(rd32(cig + 4 * k));
     }
-    out->n_reads = (int64_t)h->ref_id.size();
+    const size_t nrec = offs.size();
+    // ---- pass 2: fields, filter, identity hash
+    std::vector<RecInfo> info(nrec);
+    std::atomic<size_t> bad_rec(SIZE_MAX);
+    parallel_for(nrec, threads, [&](size_t a, size_t e, int) {
+        for (size_t i = a; i < e; ++i) {
+            RecInfo& R = info[i];
+            R.keep = 0;
+            const uint8_t* b = &r[offs[i] + 4];
+            const int32_t bs = rdi32(&r[offs[i]]);
+            const uint8_t* rec_end = b + bs;
+            const int32_t refID = rdi32(b), pos = rdi32(b + 4);
+            const uint8_t l_rn = b[8];
+            const uint16_t n_cig = rd16(b + 12), flag = rd16(b + 14);
+            const int32_t l_seq = rdi32(b + 16);
+            const char* qname = reinterpret_cast<const char*>(b + 32);
+            const uint8_t* cig = b + 32 + l_rn;
+            const uint8_t* sq = cig + 4 * (size_t)n_cig;
+            const uint8_t* ql = sq + ((size_t)(l_seq < 0 ? 0 : l_seq) + 1) / 2;
+            if (l_seq < 0 || ql + l_seq > rec_end) {
+                size_t cur = bad_rec.load();
+                while (i < cur && !bad_rec.compare_exchange_weak(cur, i)) {}
+                continue;
+            }
+            if ((flag & 0x4) || refID < 0 || (size_t)refID >= nref) continue;
+            if (n_iv > 0) {
+                int64_t reflen = 0;
+                for (uint16_t k = 0; k < n_cig; ++k) {
+                    const uint32_t cw = rd32(cig + 4 * k), op = cw & 15u;
+                    if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) reflen += cw >> 4;
+                }
+                if (!touches(refID, pos, (int64_t)pos + reflen)) continue;
+            }
+            // identity: BC = parts[-2], readid = ':'.join(parts[:-2])   (smCounter.py:319-325)
+            const size_t qn = l_rn ? (size_t)l_rn - 1 : 0;
+            long c1 = -1, c2 = -1;                  // last and second-to-last ':'
+            for (long k = (long)qn - 1; k >= 0; --k)
+                if (qname[k] == ':') { if (c1 < 0) c1 = k; else { c2 = k; break; } }
+            if (c1 < 0) { R.bc_off = 0; R.bc_len = 0; R.rid_len = 0; }          // fewer than 2 fields: parts[-2] would raise in Python
+            else if (c2 < 0) { R.bc_off = 0; R.bc_len = (uint32_t)c1; R.rid_len = 0; }
+            else { R.bc_off = (uint32_t)(c2 + 1); R.bc_len = (uint32_t)(c1 - c2 - 1); R.rid_len = (uint32_t)c2; }
+            uint64_t code = 1;
+            bool packable = R.bc_len <= 31;
+            if (packable)
+                for (uint32_t k = 0; k < R.bc_len; ++k) {
+                    const char ch = qname[R.bc_off + k];
+                    const int v = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : -1;
+                    if (v < 0) { packable = false; break; }
+                    code = (code << 2) | (uint64_t)v;
+                }
+            R.code = packable ? code : 0;
+            uint64_t h1 = 0x243f6a8885a308d3ull ^ R.bc_len, h2 = 0x13198a2e03707344ull + R.rid_len;
+            hash_bytes(reinterpret_cast<const uint8_t*>(qname) + R.bc_off, R.bc_len, h1, h2);
+            hash_bytes(reinterpret_cast<const uint8_t*>(qname), R.rid_len, h1, h2);
+            R.h1 = h1; R.h2 = h2;
+            R.keep = 1;
+        }
+    });
+    if (bad_rec.load() != SIZE_MAX) { h->err = "malformed BAM record (field lengths exceed block_size)"; return -1; }
+    // ---- pass 3: output slots, payload offsets, fragment ids, barcode dictionary
+    std::vector<uint32_t> slot(nrec);
+    size_t n = 0, seq_tot = 0, qual_tot = 0, cig_tot = 0;
+    for (size_t i = 0; i < nrec; ++i) if (info[i].keep) ++n;
+    if (n >= (1ull << 31)) { h->err = "more than 2^31 reads"; return -1; }
+    h->ref_id.resize(n); h->pos.resize(n); h->nm.resize(n); h->l_seq.resize(n); h->flag.resize(n); h->n_cigar.resize(n);
+    h->mapq.resize(n); h->seq_off.resize(n); h->qual_off.resize(n); h->cigar_off.resize(n); h->umi.resize(n); h->frag_id.resize(n);
+    h->dict_umis.clear();
+    {
+        size_t cap = 16;
+        while (cap < 2 * n + 2) cap <<= 1;
+        struct Ent { uint64_t h1, h2; uint32_t rec, id; };
+        std::vector<Ent> tab(cap, Ent{0, 0, UINT32_MAX, 0});
+        std::unordered_map<std::string, uint64_t> umi_dict;
+        uint32_t next_id = 0;
+        size_t o = 0;
+        auto same_identity = [&](size_t i, size_t j) {
+            const RecInfo& A = info[i]; const RecInfo& B = info[j];
+            if (A.bc_len != B.bc_len || A.rid_len != B.rid_len) return false;
+            const uint8_t* qa = &r[offs[i] + 4 + 32]; const uint8_t* qb = &r[offs[j] + 4 + 32];
+            return memcmp(qa + A.bc_off, qb + B.bc_off, A.bc_len) == 0 && memcmp(qa, qb, A.rid_len) == 0;
+        };
+        for (size_t i = 0; i < nrec; ++i) {
+            RecInfo& R = info[i];
+            if (!R.keep) continue;
+            const uint8_t* b = &r[offs[i] + 4];
+            const int32_t l_seq = rdi32(b + 16);
+            const uint16_t n_cig = rd16(b + 12);
+            slot[i] = (uint32_t)o;
+            h->seq_off[o] = (int64_t)seq_tot; h->qual_off[o] = (int64_t)qual_tot; h->cigar_off[o] = (int64_t)cig_tot;
+            seq_tot += ((size_t)l_seq + 1) / 2; qual_tot += (size_t)l_seq; cig_tot += n_cig;
+            size_t k = (size_t)R.h1 & (cap - 1);
+            for (;;) {
+                Ent& E = tab[k];
+                if (E.rec == UINT32_MAX) { E = Ent{R.h1, R.h2, (uint32_t)i, next_id}; h->frag_id[o] = next_id++; break; }
+                if (E.h1 == R.h1 && E.h2 == R.h2 && same_identity(E.rec, i)) { h->frag_id[o] = E.id; break; }
+                k = (k + 1) & (cap - 1);
+            }
+            if (R.code == 0) {                                                  // barcode not packable: dictionary code
+                const std::string bc(reinterpret_cast<const char*>(b + 32) + R.bc_off, R.bc_len);
+                auto it = umi_dict.find(bc);
+                if (it == umi_dict.end()) {
+                    R.code = (1ull << 63) | (uint64_t)umi_dict.size();
+                    umi_dict.emplace(bc, R.code);
+                    h->dict_umis.push_back(bc);
+                } else R.code = it->second;
+            }
+            h->umi[o] = R.code;
+            ++o;
+        }
+    }
+    h->seq.resize(seq_tot); h->qual.resize(qual_tot); h->cigar.resize(cig_tot);
+    // ---- pass 4: scalars and payloads
+    parallel_for(nrec, threads, [&](size_t a, size_t e, int) {
+        for (size_t i = a; i < e; ++i) {
+            if (!info[i].keep) continue;
+            const size_t o = slot[i];
+            const uint8_t* b = &r[offs[i] + 4];
+            const uint8_t* rec_end = b + rdi32(&r[offs[i]]);
+            const uint8_t l_rn = b[8];
+            const uint16_t n_cig = rd16(b + 12);
+            const int32_t l_seq = rdi32(b + 16);
+            const uint8_t* cig = b + 32 + l_rn;
+            const uint8_t* sq = cig + 4 * (size_t)n_cig;
+            const size_t sb = ((size_t)l_seq + 1) / 2;
+            const uint8_t* ql = sq + sb;
+            h->ref_id[o] = rdi32(b); h->pos[o] = rdi32(b + 4); h->flag[o] = rd16(b + 14); h->mapq[o] = b[9];
+            h->nm[o] = first_nm(ql + l_seq, rec_end); h->l_seq[o] = l_seq; h->n_cigar[o] = n_cig;
+            if (sb) memcpy(&h->seq[(size_t)h->seq_off[o]], sq, sb);
+            if (l_seq) memcpy(&h->qual[(size_t)h->qual_off[o]], ql, (size_t)l_seq);
+            if (n_cig) memcpy(&h->cigar[(size_t)h->cigar_off[o]], cig, 4 * (size_t)n_cig);
+        }
+    });
+    out->n_reads = (int64_t)n;
     out->ref_id = h->ref_id.data(); out->pos = h->pos.data(); out->flag = h->flag.data(); out->mapq = h->mapq.data();
     out->nm = h->nm.data(); out->l_seq = h->l_seq.data(); out->seq_off = h->seq_off.data(); out->qual_off = h->qual_off.data();
     out->cigar_off = h->cigar_off.data(); out->n_cigar = h->n_cigar.data(); out->umi = h->umi.data(); out->frag_id = h->frag_id.data();

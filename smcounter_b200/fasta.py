@@ -59,8 +59,7 @@ class FastaFile:
             return ""
         b0 = offset + (start // linebases) * linewidth + start % linebases
         b1 = offset + ((end - 1) // linebases) * linewidth + (end - 1) % linebases + 1
-        self.fh.seek(b0)
-        raw = self.fh.read(b1 - b0)
+        raw = os.pread(self.fh.fileno(), b1 - b0, b0)        # positional read: no shared file offset (threads, forked workers)
         return raw.replace(b"\n", b"").replace(b"\r", b"").decode()
 
     def close(self):

@@ -151,11 +151,51 @@ def _filter_string(bits, chrom, pos, hpLen, ref, alt, refs):
     return f
 
 
-def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None):
+_POOL_JOB = None          # inputs of the forked formatting workers (inherited, never pickled)
+PARALLEL_MIN_ROWS = 4096
+
+
+def _format_slice(bounds):
+    res, reads, loci, chroms, refs, hpLen, order = _POOL_JOB
+    try:
+        return format_rows(res, reads, loci, chroms, refs, hpLen, order[bounds[0]:bounds[1]], workers=1)
+    except RuntimeError as e:                  # plain message: survives pickling back to the parent
+        return e
+
+
+def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, workers=None):
     """The 45-field rows of vc() (smCounter.py:575-600) for ``locus_order`` (indices into loci; default all, in order).
+
+    Row formatting is per-locus string work, as independent as the reference's per-locus workers (smCounter.py:683-685):
+    from PARALLEL_MIN_ROWS rows up it is fanned out over forked worker processes (``workers``: default = host cores, 1 =
+    inline); the device results are inherited through fork(), only the finished strings travel back.
 
     Raises RuntimeError for loci the device flagged as needing a down-sampling mask or as unsupported.
     """
+    global _POOL_JOB
+    import os
+    n_rows = loci.n if locus_order is None else len(locus_order)
+    if workers is None:
+        workers = os.cpu_count() or 1
+    import threading
+    if workers > 1 and n_rows >= PARALLEL_MIN_ROWS and threading.current_thread() is threading.main_thread() and hasattr(os, "fork"):
+        import multiprocessing as mp
+        import numpy as np
+        order = np.arange(loci.n) if locus_order is None else np.asarray(locus_order)
+        nchunk = min(n_rows // 512, workers * 4)
+        cuts = [(n_rows * k) // nchunk for k in range(nchunk + 1)]
+        _POOL_JOB = (res, reads, loci, chroms, refs, hpLen, order)
+        try:
+            with mp.get_context("fork").Pool(min(workers, nchunk)) as pool:
+                parts = pool.map(_format_slice, list(zip(cuts[:-1], cuts[1:])), chunksize=1)
+        finally:
+            _POOL_JOB = None
+        rows = []
+        for p in parts:
+            if isinstance(p, Exception):
+                raise p
+            rows.extend(p)
+        return rows
     namer = AlleleNamer(res, reads, loci, chroms, refs)
     n = loci.n
     order = range(n) if locus_order is None else locus_order

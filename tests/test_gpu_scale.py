@@ -173,7 +173,8 @@ def test_cfg5_many_loci_many_contigs_shape():
     try:
         assert loci.n == 240000
         _check_properties(res, soa, loci)
-        g_rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order)
+        g_rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order)          # forked formatting workers
+        assert format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order[:20000], workers=1) == g_rows[:20000]
     finally:
         caller.close()
     _compare_with_oracle(g_rows, ivs, soa, refs, prm, truth, seed=9, n_random=40, n_truth=20)
