@@ -219,7 +219,7 @@ def pipeline_leg(args, mine, soa, refs, device):
         n_loci = sum(e - s for (_, s, e) in ivs)
         return {"value": n_loci / (t[3] - t[0]), "unit": UNIT, "loci": n_loci, "reads": int(reads.n), "intervals": len(ivs),
                 "bam_mb": os.path.getsize(path) / 1e6, "ms_bam_decode": 1e3 * (t[1] - t[0]), "ms_call_loci": 1e3 * (t[2] - t[1]),
-                "ms_gpu_call": st.get("ms_gpu_call"), "ms_format_rows": st.get("ms_format_rows"),
+                "ms_gpu_call": st.get("ms_gpu_call"), "ms_format_rows": st.get("ms_format_rows"), "gpu_call_detail": {k: v for k, v in st.items() if k not in ("ms_gpu_call", "ms_format_rows")},
                 "ms_filters_and_writers": 1e3 * (t[3] - t[2]),
                 "what": "BAM decode (libsmc_bamio, all host threads) + smc_call_batch + row formatting + repeat filters + the three "
                         "output files, once, on a sub-batch of the rank-0 panel batch"}

@@ -250,6 +250,34 @@ int smc_get_timings(smc_ctx *ctx, smc_timings *t);
 int smc_list_barcodes(smc_ctx *ctx, int64_t n, const int64_t *locus, int64_t *off_out, uint64_t *umi_out,
                       uint32_t *first_read_out, int64_t umi_capacity);
 
+/*
+ * isHPorLowComp() (smCounter.py:122-177) for a batch of candidates in one launch: is the candidate inside / next to a
+ * homopolymer of >= hpLen bases, or a 2*hpLen window whose two most frequent nucleotides make up >= 99 %?  Replaces the six
+ * FastaFile.fetch() round trips per candidate of the reference (:127-129, :143-145).  For candidate k the caller passes
+ *   - one upper-case reference window  bases[win_off[k] .. +win_len[k])  =  reference[w0, w1)  with
+ *       w0 = max(0, pos0 - 2*hpLen),  w1 = min(contig length, pos0 + max(len(ref), len(alt)) + 2*hpLen),
+ *     and win_pos[k] = pos0 - w0 (the candidate's position inside the window);
+ *   - the VCF-style REF and ALT strings of convertToVcf() (:103-117) at ref_off/ref_len and alt_off/alt_len of bases[].
+ * flags_out[k]: bit 0 = homopolymer, bit 1 = low complexity.  Independent of any uploaded batch.
+ */
+typedef struct smc_hp_batch {
+    int64_t         n;          /* candidates */
+    int32_t         hpLen;      /* --hpLen (smCounter.py:628) */
+    const uint8_t  *bases;      /* windows and allele strings, concatenated */
+    int64_t         n_bases;
+    const int64_t  *win_off;
+    const int32_t  *win_len;
+    const int32_t  *win_pos;
+    const int64_t  *ref_off;
+    const int32_t  *ref_len;
+    const int64_t  *alt_off;
+    const int32_t  *alt_len;
+} smc_hp_batch;
+#define SMC_HP_HOMOPOLYMER 1u
+#define SMC_HP_LOWCOMP     2u
+
+int smc_hp_lowcomp(smc_ctx *ctx, const smc_hp_batch *batch, uint8_t *flags_out);
+
 #ifdef __cplusplus
 }
 #endif

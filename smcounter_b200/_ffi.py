@@ -62,8 +62,15 @@ class smc_timings(C.Structure):
                 ("dyn_capacity", C.c_int32), ("pipe_chunks", C.c_int32), ("pipe_launches", C.c_int32)]
 
 
+class smc_hp_batch(C.Structure):
+    _fields_ = [("n", C.c_int64), ("hpLen", C.c_int32), ("bases", _vp), ("n_bases", C.c_int64), ("win_off", _vp), ("win_len", _vp),
+                ("win_pos", _vp), ("ref_off", _vp), ("ref_len", _vp), ("alt_off", _vp), ("alt_len", _vp)]
+
+
+HP_HOMOPOLYMER, HP_LOWCOMP = 1, 2
+
 EXPORTS = ("smc_version", "smc_ctx_create", "smc_ctx_destroy", "smc_last_error", "smc_call_batch", "smc_upload",
-           "smc_run_resident", "smc_download", "smc_get_timings", "smc_list_barcodes")
+           "smc_run_resident", "smc_download", "smc_get_timings", "smc_list_barcodes", "smc_hp_lowcomp")
 
 _lib = None
 
@@ -97,6 +104,8 @@ def load():
     lib.smc_get_timings.restype = C.c_int
     lib.smc_list_barcodes.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64]
     lib.smc_list_barcodes.restype = C.c_int
+    lib.smc_hp_lowcomp.argtypes = [_vp, C.POINTER(smc_hp_batch), _vp]
+    lib.smc_hp_lowcomp.restype = C.c_int
     _lib = lib
     return lib
 

@@ -227,6 +227,32 @@ class GpuCaller:
                 raise self._err("smc_list_barcodes", rc)
         return off, umi[:total], first[:total]
 
+    def hp_lowcomp(self, hpLen: int, candidates) -> np.ndarray:
+        """isHPorLowComp() (smCounter.py:122-177) on the device for ``candidates`` = [(window, pos_in_window, ref, alt)]
+        (upper-case ``str``/``bytes``; window = reference[max(0, pos0 - 2*hpLen), min(contig end, pos0 + max(len(ref),
+        len(alt)) + 2*hpLen)), see include/smc_b200.h: smc_hp_batch).  Returns uint8 flags: bit 0 homopolymer, bit 1 low complexity."""
+        n = len(candidates)
+        flags = np.zeros(max(n, 1), dtype=np.uint8)
+        if n == 0:
+            return flags[:0]
+        parts, off = [], 0
+        win_off, ref_off, alt_off = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64)
+        win_len, win_pos, ref_len, alt_len = (np.zeros(n, np.int32) for _ in range(4))
+        for k, (win, wpos, ref, alt) in enumerate(candidates):
+            for arr_off, arr_len, sv in ((win_off, win_len, win), (ref_off, ref_len, ref), (alt_off, alt_len, alt)):
+                b = sv.encode() if isinstance(sv, str) else bytes(sv)
+                arr_off[k], arr_len[k] = off, len(b)
+                parts.append(b)
+                off += len(b)
+            win_pos[k] = wpos
+        bases = np.frombuffer(b"".join(parts) or b"\0", dtype=np.uint8)
+        hb = _ffi.smc_hp_batch(n, int(hpLen), _ffi.ptr(bases), off, _ffi.ptr(win_off), _ffi.ptr(win_len), _ffi.ptr(win_pos),
+                               _ffi.ptr(ref_off), _ffi.ptr(ref_len), _ffi.ptr(alt_off), _ffi.ptr(alt_len))
+        rc = self.lib.smc_hp_lowcomp(self.h, C.byref(hb), _ffi.ptr(flags))
+        if rc != 0:
+            raise self._err("smc_hp_lowcomp", rc)
+        return flags[:n]
+
     def timings(self) -> dict:
         t = _ffi.smc_timings()
         self.lib.smc_get_timings(self.h, C.byref(t))

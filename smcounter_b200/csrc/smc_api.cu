@@ -79,6 +79,7 @@ struct smc_ctx {
     uint32_t task_cap = 0;
     // barcode listing
     DevBuf d_list_idx, d_list_count, d_list_off, d_list_umi, d_list_first;
+    DevBuf d_hp_bases, d_hp_meta, d_hp_flags;     // smc_hp_lowcomp
     smc_timings tm{};
     uint32_t chunk = 256;       // tile events per warp unit (A/B on B200: 64 -> 4.39 ms, 256 -> 3.37, 384 -> 3.37, 2048 -> 4.0, 4096 -> 4.3)
     const uint32_t* ev_read_sorted = nullptr;   // tile-sorted event -> srank map (lives in d_ev0 or d_ev1)
@@ -266,7 +267,8 @@ extern "C" void smc_ctx_destroy(smc_ctx* ctx) {
                       &ctx->d_dkey, &ctx->d_drep_read, &ctx->d_drep_qpos, &ctx->d_dlen, &ctx->d_dcnt, &ctx->d_dlimb, &ctx->d_diskey,
                       &ctx->d_lk0, &ctx->d_lk1, &ctx->d_lv0, &ctx->d_lv1, &ctx->d_s_key, &ctx->d_s_cnt, &ctx->d_s_limb, &ctx->d_s_iskey,
                       &ctx->d_s_pi, &ctx->d_s_rep_read, &ctx->d_s_rep_qpos, &ctx->d_s_len, &ctx->d_dyn_first, &ctx->d_tasks,
-                      &ctx->d_list_idx, &ctx->d_list_count, &ctx->d_list_off, &ctx->d_list_umi, &ctx->d_list_first};
+                      &ctx->d_list_idx, &ctx->d_list_count, &ctx->d_list_off, &ctx->d_list_umi, &ctx->d_list_first,
+                      &ctx->d_hp_bases, &ctx->d_hp_meta, &ctx->d_hp_flags};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_chunk) if (ev) cudaEventDestroy(ev);
@@ -825,6 +827,43 @@ extern "C" int smc_list_barcodes(smc_ctx* ctx, int64_t n, const int64_t* locus, 
     LAUNCH(k_merge_t<true>, nblk(ctx->n_units_cap, KB_WARPS), KB_WARPS * 32, KB_SMEM_BYTES, B);
     CK(cudaMemcpyAsync(umi_out, ctx->d_list_umi.p, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(first_read_out, ctx->d_list_first.p, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaGetLastError());
+    return SMC_OK;
+}
+
+extern "C" int smc_hp_lowcomp(smc_ctx* ctx, const smc_hp_batch* Bt, uint8_t* flags_out) {
+    if (!ctx) return SMC_E_ARG;
+    if (!Bt || Bt->n < 0 || Bt->hpLen < 0 || (Bt->n > 0 && (!flags_out || !Bt->bases || !Bt->win_off || !Bt->win_len || !Bt->win_pos ||
+                                                             !Bt->ref_off || !Bt->ref_len || !Bt->alt_off || !Bt->alt_len))) {
+        ctx->err = "smc_hp_lowcomp: bad arguments"; return SMC_E_ARG;
+    }
+    const int64_t n = Bt->n;
+    if (n == 0) return SMC_OK;
+    for (int64_t k = 0; k < n; ++k) {                          // the kernel trusts these
+        const bool ok = Bt->win_len[k] >= 0 && Bt->win_pos[k] >= 0 && Bt->win_pos[k] <= Bt->win_len[k] && Bt->ref_len[k] >= 0 &&
+                        Bt->alt_len[k] >= 0 && Bt->win_off[k] >= 0 && Bt->win_off[k] + Bt->win_len[k] <= Bt->n_bases &&
+                        Bt->ref_off[k] >= 0 && Bt->ref_off[k] + Bt->ref_len[k] <= Bt->n_bases && Bt->alt_off[k] >= 0 &&
+                        Bt->alt_off[k] + Bt->alt_len[k] <= Bt->n_bases;
+        if (!ok) { ctx->err = "smc_hp_lowcomp: candidate " + std::to_string(k) + " points outside bases[]"; return SMC_E_ARG; }
+    }
+    CK(cudaSetDevice(ctx->device));
+    // device layout of the per-candidate metadata: three int64 arrays, then four int32 arrays
+    const size_t n8 = (size_t)n * 8, n4 = (size_t)n * 4;
+    CK(ctx->d_hp_bases.ensure((size_t)Bt->n_bases + 16)); CK(ctx->d_hp_meta.ensure(3 * n8 + 4 * n4)); CK(ctx->d_hp_flags.ensure((size_t)n));
+    uint8_t* m = ctx->d_hp_meta.as<uint8_t>();
+    CK(cudaMemcpyAsync(ctx->d_hp_bases.p, Bt->bases, (size_t)Bt->n_bases, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(m, Bt->win_off, n8, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(m + n8, Bt->ref_off, n8, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(m + 2 * n8, Bt->alt_off, n8, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(m + 3 * n8, Bt->win_len, n4, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(m + 3 * n8 + n4, Bt->win_pos, n4, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(m + 3 * n8 + 2 * n4, Bt->ref_len, n4, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(m + 3 * n8 + 3 * n4, Bt->alt_len, n4, cudaMemcpyHostToDevice, ctx->st));
+    k_hp_lowcomp<<<nblk(n * 32, 128), 128, 0, ctx->st>>>(n, Bt->hpLen, ctx->d_hp_bases.as<uint8_t>(), (const int64_t*)m,
+        (const int32_t*)(m + 3 * n8), (const int32_t*)(m + 3 * n8 + n4), (const int64_t*)(m + n8), (const int32_t*)(m + 3 * n8 + 2 * n4),
+        (const int64_t*)(m + 2 * n8), (const int32_t*)(m + 3 * n8 + 3 * n4), ctx->d_hp_flags.as<uint8_t>());
+    CK(cudaMemcpyAsync(flags_out, ctx->d_hp_flags.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     CK(cudaGetLastError());
     return SMC_OK;

@@ -3,7 +3,8 @@
 Covers what stays on the host by design:
   * allele strings ('INS|s|s+ins', 'DEL|s+del|s', smCounter.py:374,396) -- built from a representative read / the FASTA;
   * convertToVcf()            smCounter.py:103-117;
-  * isHPorLowComp()           smCounter.py:122-177 (needs reference windows; only for candidates with PI >= 5);
+  * isHPorLowComp()           smCounter.py:122-177: the reference windows are cut here (hp_window), the test itself runs on
+                              the device (smc_hp_lowcomp) for all candidates of a batch at once (device_hp_flags);
   * FILTER string assembly    smCounter.py:184-269 (device supplies the bits, order of tags as in the reference);
   * bi-allelic resolution     smCounter.py:553-573;
   * the output vector         smCounter.py:575-600 with Python-2 round()/str() semantics.
@@ -64,30 +65,33 @@ def convert_to_vcf(origRef: str, origAlt: str):
     return ref, alt, vtype
 
 
-def is_hp_or_low_comp(chrom, pos, length, refb, altb, refs):
-    """smCounter.py:122-177: homopolymer >= length and low-complexity (top-2 nt >= 99 % in a 2*length window)."""
-    chromLength = refs.get_reference_length(chrom)
-    pos0 = int(pos) - 1
-    L = refs.fetch(chrom, max(0, pos0 - length), pos0).upper()
-    Rr = refs.fetch(chrom, pos0 + len(refb), min(pos0 + len(refb) + length, chromLength)).upper()
-    Ra = refs.fetch(chrom, pos0 + len(altb), min(pos0 + len(altb) + length, chromLength)).upper()
-    refSeq, altSeq = L + refb + Rr, L + altb + Ra
-    homop = any((c * length) in refSeq or (c * length) in altSeq for c in "ATGC")
-    len2 = 2 * length
-    L2 = refs.fetch(chrom, max(0, pos0 - len2), pos0).upper()
-    Rr2 = refs.fetch(chrom, pos0 + len(refb), min(pos0 + len(refb) + len2, chromLength)).upper()
-    Ra2 = refs.fetch(chrom, pos0 + len(altb), min(pos0 + len(altb) + len2, chromLength)).upper()
-    lowcomp = False
-    for seq in (L2 + refb + Rr2, L2 + altb + Ra2):
-        for i in range(len(seq) - len2):
-            sub = seq[i:i + len2]
-            cs = sorted((sub.count("A"), sub.count("T"), sub.count("G"), sub.count("C")), reverse=True)
-            if 1.0 * (cs[0] + cs[1]) / len2 >= 0.99:
-                lowcomp = True
-                break
-        if lowcomp:
-            break
-    return homop, lowcomp
+def hp_window(chrom, pos0, hpLen, ref, alt, refs):
+    """(window, position inside it) for smc_hp_lowcomp: upper-case reference[max(0, pos0 - 2*hpLen), min(contig length,
+    pos0 + max(len(ref), len(alt)) + 2*hpLen)) -- every base isHPorLowComp() fetches (smCounter.py:127-129, 143-145)."""
+    w0 = max(0, pos0 - 2 * hpLen)
+    w1 = min(refs.get_reference_length(chrom), pos0 + max(len(ref), len(alt)) + 2 * hpLen)
+    return refs.fetch(chrom, w0, w1).upper(), pos0 - w0
+
+
+def device_hp_flags(caller, res, reads, loci, chroms, refs, hpLen):
+    """{(locus index, candidate 0/1): (homopolymer, low complexity)} for every candidate whose FILTER evaluation can append
+    HP / LowC (filterVariants() was entered and MTCnt[alt]/usedMT < 0.99, smCounter.py:195-203), computed by ONE
+    smc_hp_lowcomp call on the device of ``caller`` (any live GpuCaller)."""
+    namer = AlleleNamer(res, reads, loci, chroms, refs)
+    keys, cands = [], []
+    want = F_EVALUATED | F_HPGATE
+    idx1 = np.flatnonzero((res.fl1[:loci.n] & want) == want)
+    idx2 = np.flatnonzero((res.biallelic[:loci.n] != 0) & ((res.fl2[:loci.n] & want) == want))
+    for cand, idx, alleles in ((0, idx1, res.alt_allele), (1, idx2, res.second_allele)):
+        for i in idx:
+            i = int(i)
+            chrom = chroms[int(loci.ref_id[i])]
+            ref, alt, _ = convert_to_vcf(chr(int(loci.ref_base[i])), namer.name(int(alleles[i])))
+            win, wpos = hp_window(chrom, int(loci.pos0[i]), hpLen, ref, alt, refs)
+            keys.append((i, cand))
+            cands.append((win, wpos, ref, alt))
+    flags = caller.hp_lowcomp(hpLen, cands)
+    return {k: (bool(f & _ffi.HP_HOMOPOLYMER), bool(f & _ffi.HP_LOWCOMP)) for k, f in zip(keys, flags.tolist())}
 
 
 class AlleleNamer:
@@ -132,19 +136,23 @@ _FILTER_TAGS = ((F_LM, "LM;"), (F_LSM, "LSM;"))
 _FILTER_TAGS2 = ((F_DP, "DP;"), (F_SB, "SB;"), (F_LOWQ, "LowQ;"), (F_R1CP, "R1CP;"), (F_R2CP, "R2CP;"), (F_PRIMERCP, "PrimerCP;"))
 
 
-def _filter_string(bits, chrom, pos, hpLen, ref, alt, refs):
-    """FILTER accumulator of filterVariants() (';' = nothing fired), tags in the reference's order."""
+def _filter_string(bits, hp_lc):
+    """FILTER accumulator of filterVariants() (';' = nothing fired), tags in the reference's order.  ``hp_lc`` = the
+    device's isHPorLowComp() result for this candidate (present whenever F_HPGATE is set)."""
     if not (bits & F_EVALUATED):
         return ";"
     f = ";"
     for b, t in _FILTER_TAGS:
         if bits & b:
             f += t
-    hp, lc = is_hp_or_low_comp(chrom, pos, hpLen, ref, alt, refs)              # smCounter.py:195-203
-    if hp and (bits & F_HPGATE):
-        f += "HP;"
-    if lc and (bits & F_HPGATE):
-        f += "LowC;"
+    if bits & F_HPGATE:                                                        # smCounter.py:195-203
+        if hp_lc is None:
+            raise RuntimeError("format_rows: no device HP/LowC flags for a candidate that needs them (pass hp_flags=device_hp_flags(...))")
+        hp, lc = hp_lc
+        if hp:
+            f += "HP;"
+        if lc:
+            f += "LowC;"
     for b, t in _FILTER_TAGS2:
         if bits & b:
             f += t
@@ -156,23 +164,28 @@ PARALLEL_MIN_ROWS = 4096
 
 
 def _format_slice(bounds):
-    res, reads, loci, chroms, refs, hpLen, order = _POOL_JOB
+    res, reads, loci, chroms, refs, hpLen, order, hp_flags = _POOL_JOB
     try:
-        return format_rows(res, reads, loci, chroms, refs, hpLen, order[bounds[0]:bounds[1]], workers=1)
+        return format_rows(res, reads, loci, chroms, refs, hpLen, order[bounds[0]:bounds[1]], workers=1, hp_flags=hp_flags)
     except RuntimeError as e:                  # plain message: survives pickling back to the parent
         return e
 
 
-def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, workers=None):
+def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, workers=None, hp_flags=None):
     """The 45-field rows of vc() (smCounter.py:575-600) for ``locus_order`` (indices into loci; default all, in order).
 
     Row formatting is per-locus string work, as independent as the reference's per-locus workers (smCounter.py:683-685):
     from PARALLEL_MIN_ROWS rows up it is fanned out over forked worker processes (``workers``: default = host cores, 1 =
     inline); the device results are inherited through fork(), only the finished strings travel back.
 
+    ``hp_flags``: device_hp_flags(...) of the same results (the HP / LowC bits of smCounter.py:195-203 are computed on the
+    device, like every other filter bit); required as soon as a candidate reaches that test.
+
     Raises RuntimeError for loci the device flagged as needing a down-sampling mask or as unsupported.
     """
     global _POOL_JOB
+    if hp_flags is None:
+        hp_flags = {}
     import os
     n_rows = loci.n if locus_order is None else len(locus_order)
     if workers is None:
@@ -184,7 +197,7 @@ def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, workers
         order = np.arange(loci.n) if locus_order is None else np.asarray(locus_order)
         nchunk = min(n_rows // 512, workers * 4)
         cuts = [(n_rows * k) // nchunk for k in range(nchunk + 1)]
-        _POOL_JOB = (res, reads, loci, chroms, refs, hpLen, order)
+        _POOL_JOB = (res, reads, loci, chroms, refs, hpLen, order, hp_flags)
         try:
             with mp.get_context("fork").Pool(min(workers, nchunk)) as pool:
                 parts = pool.map(_format_slice, list(zip(cuts[:-1], cuts[1:])), chunksize=1)
@@ -224,13 +237,13 @@ def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, workers
         a1 = int(res.alt_allele[i])
         origAlt = namer.name(a1)
         ref, alt, vtype = convert_to_vcf(origRef, origAlt)
-        fltr = _filter_string(int(res.fl1[i]), chrom, pos, hpLen, ref, alt, refs)
+        fltr = _filter_string(int(res.fl1[i]), hp_flags.get((i, 0)))
         alt_ref = a1
         if res.biallelic[i]:                                                    # smCounter.py:555-573
             a2 = int(res.second_allele[i])
             origAlt2 = namer.name(a2)
             ref2, alt2, vtype2 = convert_to_vcf(origRef, origAlt2)
-            fltr2 = _filter_string(int(res.fl2[i]), chrom, pos, hpLen, ref2, alt2, refs)
+            fltr2 = _filter_string(int(res.fl2[i]), hp_flags.get((i, 1)))
             if fltr == ";" and fltr2 == ";":
                 alt = alt + "," + alt2
                 vtype = vtype.lower() + "," + vtype2.lower()

@@ -29,7 +29,7 @@ from .bam import read_bam
 from .caller import GpuCaller, UmiKeep, VcParams
 from .downsample import draw_keep_masks
 from .fasta import FastaFile
-from .rows import format_rows
+from .rows import device_hp_flags, format_rows
 from .shard import interleave_rows, plan_shards, reads_for_intervals
 from .targets import build_loci, intervals_from_bed_lines
 
@@ -86,18 +86,26 @@ def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None
                 return
             sub = reads if len(plan) == 1 else reads.select(reads_for_intervals(reads, ivs, chroms))
             loci, bed_order = build_loci(ivs, chroms, refs)
+            tc = time.perf_counter()
             caller = GpuCaller(prm, devices[g])
             t0 = time.perf_counter()
             try:
                 res = caller.call(sub, loci)
+                if stage_times is not None:
+                    tm = caller.timings()
+                    stage_times["ms_ctx_create"] = stage_times.get("ms_ctx_create", 0.0) + 1e3 * (t0 - tc)
+                    stage_times["ms_first_call"] = stage_times.get("ms_first_call", 0.0) + 1e3 * (time.perf_counter() - t0)
+                    for k in ("ms_h2d", "ms_total_device", "ms_d2h"):
+                        stage_times[k] = stage_times.get(k, 0.0) + float(tm[k])
                 keep = draw_keep_masks(caller, res, sub, loci, chroms, prm)        # smCounter.py:496-500
                 if keep is not None:
                     res = caller.call(sub, loci, keep)
+                hp = device_hp_flags(caller, res, sub, loci, chroms, refs, prm.hpLen)   # isHPorLowComp, smCounter.py:122-177
             finally:
                 t1 = time.perf_counter()
                 caller.close()
             t2 = time.perf_counter()
-            shard_rows[g] = format_rows(res, sub, loci, chroms, refs, prm.hpLen, bed_order)
+            shard_rows[g] = format_rows(res, sub, loci, chroms, refs, prm.hpLen, bed_order, hp_flags=hp)
             if stage_times is not None:
                 stage_times["ms_gpu_call"] = stage_times.get("ms_gpu_call", 0.0) + 1e3 * (t1 - t0)
                 stage_times["ms_format_rows"] = stage_times.get("ms_format_rows", 0.0) + 1e3 * (time.perf_counter() - t2)

@@ -8,7 +8,7 @@ import numpy as np
 from oracle import smcounter_oracle as orc
 from smcounter_b200 import _ffi
 from smcounter_b200.caller import GpuCaller, UmiKeep, VcParams
-from smcounter_b200.rows import AlleleNamer, format_rows
+from smcounter_b200.rows import AlleleNamer, device_hp_flags, format_rows
 from smcounter_b200.soa import soa_to_records
 from smcounter_b200.synth import SynthSpec, make_panel
 from smcounter_b200.targets import build_loci, loc_list
@@ -37,8 +37,9 @@ def gpu_run(soa, intervals, refs, prm: VcParams, keep: UmiKeep | None = None, de
     caller = GpuCaller(prm, device)
     res = caller.call(soa, loci, keep)
     tm = caller.timings()
+    hp = device_hp_flags(caller, res, soa, loci, soa.chroms, refs, prm.hpLen)
     caller.close()
-    rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order)
+    rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order, hp_flags=hp)
     return rows, res, loci, bed_order, tm
 
 

@@ -244,3 +244,37 @@ def test_pipelined_call_equals_resident_rerun():
         assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), f
     for f in ("dyn_locus", "dyn_kind", "dyn_site", "dyn_len", "dyn_iskey", "dyn_cnt", "dyn_pi"):
         assert np.array_equal(getattr(a, f)[:a.n_dyn], getattr(b, f)[:a.n_dyn]), f
+
+
+def test_device_hp_lowcomp_matches_oracle():
+    """smc_hp_lowcomp (k_hp_lowcomp, one warp per candidate) against the oracle's isHPorLowComp() restatement
+    (smCounter.py:122-177) on every position of a sequence with planted homopolymers and dinucleotide repeats, for SNP,
+    insertion and deletion alleles, three hpLen values, and positions at both contig ends."""
+    import random
+    from oracle import smcounter_oracle as orc
+    from smcounter_b200 import rows
+    from smcounter_b200.caller import GpuCaller
+    rng = random.Random(3)
+    rnd = lambda k: "".join(rng.choice("ACGT") for _ in range(k))
+    seq = "GGGGGGGGGGGG" + rnd(150) + "A" * 12 + rnd(60) + "AT" * 15 + rnd(40) + "CCCCCCCCCG" + rnd(90) + "TGTGTGTGTGTGTGTGTGTGTG" + "n" + rnd(7)
+    ref = orc.DictFasta({"c": seq})
+    caller = GpuCaller(VcParams(mtDepth=10, rpb=2.0), 0)
+    try:
+        seen = set()
+        for hp in (8, 10, 3):
+            cands, want = [], []
+            for pos0 in range(len(seq)):
+                for (r, a) in ((seq[pos0].upper(), "C"), (seq[pos0].upper(), seq[pos0].upper() + "TT"), (seq[pos0:pos0 + 3].upper(), seq[pos0].upper()),
+                               ("A", "AAAAAAAAAAAAA")):
+                    win, wpos = rows.hp_window("c", pos0, hp, r, a, ref)
+                    cands.append((win, wpos, r, a))
+                    want.append(orc.is_hp_or_low_comp("c", str(pos0 + 1), hp, r, a, ref))
+            flags = caller.hp_lowcomp(hp, cands)
+            got = [(bool(f & 1), bool(f & 2)) for f in flags.tolist()]
+            bad = [(k, cands[k], got[k], want[k]) for k in range(len(want)) if got[k] != tuple(want[k])]
+            assert not bad, bad[:5]
+            seen.update(got)
+        assert seen == {(False, False), (True, False), (False, True), (True, True)}
+        assert len(caller.hp_lowcomp(8, [])) == 0
+    finally:
+        caller.close()

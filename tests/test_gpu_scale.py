@@ -11,7 +11,7 @@ import pytest
 
 from smcounter_b200 import _ffi
 from smcounter_b200.caller import GpuCaller, VcParams
-from smcounter_b200.rows import format_rows
+from smcounter_b200.rows import device_hp_flags, format_rows
 from smcounter_b200.synth import SynthSpec, make_panel_mp, panel_intervals_from_bed
 from smcounter_b200.targets import build_loci, loc_list
 
@@ -125,7 +125,8 @@ def test_cfg2_panel_batch_properties_sharding_and_oracle_sample():
         assert tm["pipe_chunks"] >= 2 and tm["pipe_launches"] >= 2, tm
         assert tm["n_pileup_events"] > 3e7
         _check_properties(res, soa, loci)
-        g_rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order)
+        hp = device_hp_flags(caller, res, soa, loci, soa.chroms, refs, prm.hpLen)
+        g_rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order, hp_flags=hp)
         # idempotence: the resident batch run again, one launch instead of per-chunk launches -> identical bits
         caller.run()
         again = caller.download(None)
@@ -150,7 +151,8 @@ def test_cfg3_deep_low_vaf_shape():
     try:
         _check_properties(res, soa, loci)
         assert int(res.loc[_ffi.L_USEDMT].max()) > 10000
-        g_rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order)
+        hp = device_hp_flags(caller, res, soa, loci, soa.chroms, refs, prm.hpLen)
+        g_rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order, hp_flags=hp)
     finally:
         caller.close()
     _compare_with_oracle(g_rows, ivs, soa, refs, prm, truth, seed=5, n_random=2, n_truth=2)
@@ -173,8 +175,9 @@ def test_cfg5_many_loci_many_contigs_shape():
     try:
         assert loci.n == 240000
         _check_properties(res, soa, loci)
-        g_rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order)          # forked formatting workers
-        assert format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order[:20000], workers=1) == g_rows[:20000]
+        hp = device_hp_flags(caller, res, soa, loci, soa.chroms, refs, prm.hpLen)
+        g_rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order, hp_flags=hp)          # forked formatting workers
+        assert format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order[:20000], workers=1, hp_flags=hp) == g_rows[:20000]
     finally:
         caller.close()
     _compare_with_oracle(g_rows, ivs, soa, refs, prm, truth, seed=9, n_random=40, n_truth=20)

@@ -48,19 +48,24 @@ def test_convert_to_vcf():
     assert rows.convert_to_vcf("G", "DEL") == ("G", "DEL", "SDEL")
 
 
-def test_hp_lowcomp_matches_oracle():
+def test_hp_window_holds_every_base_the_reference_fetches():
+    """rows.hp_window(): the one reference window per candidate that smc_hp_lowcomp gets must contain all six fetch() ranges
+    of isHPorLowComp() (smCounter.py:127-129, 143-145), also at the contig ends."""
     rng = random.Random(3)
-    seq = "".join(rng.choice("ACGT") for _ in range(300)) + "A" * 12 + "".join(rng.choice("ACGT") for _ in range(100)) + \
-        "AT" * 15 + "".join(rng.choice("ACGT") for _ in range(200))
+    seq = "".join(rng.choice("ACGTacgt") for _ in range(120))
     ref = orc.DictFasta({"c": seq})
-    hits = set()
-    for pos in range(1, len(seq) + 1, 3):
-        for (r, a) in (("A", "C"), ("A", "ATT"), ("ACG", "A")):
-            got = rows.is_hp_or_low_comp("c", str(pos), 8, r, a, ref)
-            assert got == orc.is_hp_or_low_comp("c", str(pos), 8, r, a, ref)
-            hits.add(got)
-    assert (True, False) in hits or (True, True) in hits
-    assert any(h[1] for h in hits)
+    n = len(seq)
+    for hp in (3, 8, 10):
+        for pos0 in (0, 1, 5, 2 * hp, 60, n - 2 * hp - 1, n - 3, n - 1):
+            for (r, a) in (("A", "C"), ("A", "ATT"), ("ACGT", "A")):
+                win, wpos = rows.hp_window("c", pos0, hp, r, a, ref)
+                w0 = pos0 - wpos
+                assert w0 == max(0, pos0 - 2 * hp) and win == seq[w0:min(n, pos0 + max(len(r), len(a)) + 2 * hp)].upper()
+                for flank in (hp, 2 * hp):
+                    for b in (r, a):
+                        lo, hi = pos0 + len(b), min(pos0 + len(b) + flank, n)
+                        assert ref.fetch("c", max(0, pos0 - flank), pos0).upper() == win[max(0, wpos - flank):wpos]
+                        assert ref.fetch("c", lo, hi).upper() == (win[lo - w0:hi - w0] if hi > lo else "")
 
 
 # ---------------------------------------------------------------------------------------------- targets / fasta / SoA
