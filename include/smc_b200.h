@@ -63,9 +63,10 @@ typedef struct smc_reads_soa {
     const uint8_t  *mapq;
     const int32_t  *nm;         /* NM tag, 0 when absent (smCounter.py:329-334) */
     const int32_t  *l_seq;      /* query length incl. soft clips (<= 65535) */
-    const int64_t  *seq_off;    /* byte offset of the read's bases in seq[] */
-    const int64_t  *qual_off;   /* byte offset of the read's qualities in qual[] */
-    const int64_t  *cigar_off;  /* index of the read's first word in cigar[] */
+    const int64_t  *seq_off;    /* byte offset of the read's bases in seq[]           } each may be NULL = "packed": the payloads */
+    const int64_t  *qual_off;   /* byte offset of the read's qualities in qual[]      } lie back to back in read order (what a BAM  */
+    const int64_t  *cigar_off;  /* index of the read's first word in cigar[]          } decode produces); the offsets are then      */
+                                /* derived on the device from l_seq / n_cigar and 24 B per read never cross PCIe                  */
     const uint16_t *n_cigar;
     const uint64_t *umi;        /* injective 64-bit code of the barcode string  (BC, smCounter.py:323) */
     const uint32_t *frag_id;    /* id of (BC, readid) (smCounter.py:321), numbered by first appearance in BAM order:

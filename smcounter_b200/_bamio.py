@@ -95,6 +95,6 @@ def read_bam_native(path: str, intervals=None, threads: int = 0) -> ReadsSoA:
             seq_off=_arr(out.seq_off, n, np.int64), qual_off=_arr(out.qual_off, n, np.int64), cigar_off=_arr(out.cigar_off, n, np.int64),
             n_cigar=_arr(out.n_cigar, n, np.uint16), umi=umi, frag_id=_arr(out.frag_id, n, np.uint32),
             seq=_arr(out.seq, out.seq_bytes, np.uint8), qual=_arr(out.qual, out.qual_bytes, np.uint8),
-            cigar=_arr(out.cigar, out.n_cigar_words, np.uint32), chroms=chroms, umi_names=names)
+            cigar=_arr(out.cigar, out.n_cigar_words, np.uint32), chroms=chroms, umi_names=names, packed=True)
     finally:
         lib.smc_bam_close(h)

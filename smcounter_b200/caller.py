@@ -152,7 +152,11 @@ class GpuCaller:
         s = _ffi.smc_reads_soa()
         s.n_reads = r.n
         s.ref_id, s.pos, s.flag, s.mapq, s.nm, s.l_seq = p(r.ref_id), p(r.pos), p(r.flag), p(r.mapq), p(r.nm), p(r.l_seq)
-        s.seq_off, s.qual_off, s.cigar_off, s.n_cigar = p(r.seq_off), p(r.qual_off), p(r.cigar_off), p(r.n_cigar)
+        s.n_cigar = p(r.n_cigar)
+        if getattr(r, "packed", False):        # payload back to back in read order: the library derives the offsets on the device
+            s.seq_off = s.qual_off = s.cigar_off = None
+        else:
+            s.seq_off, s.qual_off, s.cigar_off = p(r.seq_off), p(r.qual_off), p(r.cigar_off)
         s.umi, s.frag_id = p(r.umi), p(r.frag_id)
         s.seq, s.seq_bytes, s.qual, s.qual_bytes = p(r.seq), r.seq.nbytes, p(r.qual), r.qual.nbytes
         s.cigar, s.n_cigar_words = p(r.cigar), r.cigar.shape[0]

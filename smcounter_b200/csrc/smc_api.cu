@@ -49,7 +49,10 @@ struct smc_ctx {
     // pipelined upload of smc_call_batch: bases / qualities arrive in chunks on st_copy while st already computes
     cudaStream_t st_copy = nullptr;
     cudaEvent_t ev_scal = nullptr, ev_chunk[SMC_PIPE_MAX]{};
-    PipeBounds pipe{};                          // pipe.n > 1: the chunk events of the current batch are pending / recorded
+    int pipe_n = 0;                             // > 1: the chunk events of the current batch are pending / recorded
+    uint32_t pipe_seq_chunk = 0, pipe_qual_chunk = 0;   // bytes of bases / qualities per chunk
+    DevBuf d_pipe_need;
+    bool packed_seq = false, packed_qual = false, packed_cigar = false;   // offsets were NULL: computed on the device
     uint32_t pipe_end[SMC_PIPE_MAX]{};          // launch c of the pileup kernels covers units [pipe_end[c-1], pipe_end[c])
     // resident inputs
     int64_t n_reads = 0, n_loci = 0, n_keep_loci = 0, n_keep_umi = 0;
@@ -268,7 +271,7 @@ extern "C" void smc_ctx_destroy(smc_ctx* ctx) {
                       &ctx->d_lk0, &ctx->d_lk1, &ctx->d_lv0, &ctx->d_lv1, &ctx->d_s_key, &ctx->d_s_cnt, &ctx->d_s_limb, &ctx->d_s_iskey,
                       &ctx->d_s_pi, &ctx->d_s_rep_read, &ctx->d_s_rep_qpos, &ctx->d_s_len, &ctx->d_dyn_first, &ctx->d_tasks,
                       &ctx->d_list_idx, &ctx->d_list_count, &ctx->d_list_off, &ctx->d_list_umi, &ctx->d_list_first,
-                      &ctx->d_hp_bases, &ctx->d_hp_meta, &ctx->d_hp_flags};
+                      &ctx->d_hp_bases, &ctx->d_hp_meta, &ctx->d_hp_flags, &ctx->d_pipe_need};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_chunk) if (ev) cudaEventDestroy(ev);
@@ -303,7 +306,7 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
     ctx->uploaded = false; ctx->ran = false;
     const int64_t n = R->n_reads, nl = Lc->n_loci;
     const int G = pipelined ? pipe_chunks_for(R) : 1;
-    ctx->pipe.n = 0;
+    ctx->pipe_n = 0;
     CK(cudaEventRecord(ctx->ev[0], ctx->st));
     int64_t bytes = 0;
 #define UP(buf, src, count, T)                                                                                   \
@@ -314,8 +317,23 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
     } while (0)
     UP(ctx->d_ref_id, R->ref_id, n, int32_t); UP(ctx->d_pos, R->pos, n, int32_t); UP(ctx->d_flag, R->flag, n, uint16_t);
     UP(ctx->d_mapq, R->mapq, n, uint8_t); UP(ctx->d_nm, R->nm, n, int32_t); UP(ctx->d_lseq, R->l_seq, n, int32_t);
-    UP(ctx->d_seq_off, R->seq_off, n, int64_t); UP(ctx->d_qual_off, R->qual_off, n, int64_t); UP(ctx->d_cig_off, R->cigar_off, n, int64_t);
     UP(ctx->d_ncig, R->n_cigar, n, uint16_t); UP(ctx->d_umi, R->umi, n, uint64_t); UP(ctx->d_frag, R->frag_id, n, uint32_t);
+    // offsets: uploaded, or -- NULL = payload packed in read order -- computed here from l_seq / n_cigar (saves 24 B per read of PCIe)
+    ctx->packed_seq = !R->seq_off; ctx->packed_qual = !R->qual_off; ctx->packed_cigar = !R->cigar_off;
+    {
+        uint32_t* small = ctx->d_small.as<uint32_t>();
+        const int64_t* host_off[3] = {R->seq_off, R->qual_off, R->cigar_off};
+        DevBuf* dev_off[3] = {&ctx->d_seq_off, &ctx->d_qual_off, &ctx->d_cig_off};
+        for (int kind = 0; kind < 3; ++kind) {
+            if (host_off[kind]) { UP(*dev_off[kind], host_off[kind], n, int64_t); continue; }
+            CK(dev_off[kind]->ensure((size_t)(n ? n : 1) * 8));
+            CK(ctx->d_v0.ensure((size_t)(n ? n : 1) * 4));
+            CK(ctx->d_scan.ensure((size_t)scan_scratch_words(n + 1) * 4 + 1024));
+            LAUNCH(k_pack_len, nblk(n, 256), 256, 0, ctx->d_lseq.as<int32_t>(), ctx->d_ncig.as<uint16_t>(), n, kind, ctx->d_v0.as<uint32_t>());
+            exclusive_scan_u32(ctx->d_v0.as<uint32_t>(), ctx->d_v0.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + 40 + kind, ctx->st);
+            LAUNCH(k_widen_u32, nblk(n, 256), 256, 0, ctx->d_v0.as<uint32_t>(), n, dev_off[kind]->as<int64_t>());
+        }
+    }
     if (G == 1) { UP(ctx->d_seq, R->seq, R->seq_bytes, uint8_t); UP(ctx->d_qual, R->qual, R->qual_bytes, uint8_t); }
     UP(ctx->d_cigar, R->cigar, R->n_cigar_words, uint32_t);
     UP(ctx->d_loci_ref, Lc->ref_id, nl, int32_t); UP(ctx->d_loci_pos, Lc->pos0, nl, int32_t); UP(ctx->d_loci_base, Lc->ref_base, nl, uint8_t);
@@ -349,25 +367,20 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
     } else {
         // the chunks follow the scalars on the link; everything up to the first pileup launch needs the scalars only
         CK(ctx->d_seq.ensure((size_t)R->seq_bytes + 16)); CK(ctx->d_qual.ensure((size_t)R->qual_bytes + 16));
-        PipeBounds& B = ctx->pipe;
-        for (int c = 0; c <= G; ++c) {
-            const int64_t r = c == G ? n : (n / G) * c;
-            B.r[c] = r;
-            B.seq[c] = c == G ? R->seq_bytes : std::min<int64_t>(std::max<int64_t>(R->seq_off[r], c ? B.seq[c - 1] : 0), R->seq_bytes);
-            B.qual[c] = c == G ? R->qual_bytes : std::min<int64_t>(std::max<int64_t>(R->qual_off[r], c ? B.qual[c - 1] : 0), R->qual_bytes);
-        }
-        B.seq[0] = 0; B.qual[0] = 0;                        // bytes before the first read's offset travel with chunk 0
+        auto chunk_bytes = [&](int64_t total) { int64_t c = (total + G - 1) / G; c = (c + 255) & ~255ll; return (uint32_t)std::max<int64_t>(c, 256); };
+        ctx->pipe_seq_chunk = chunk_bytes(R->seq_bytes); ctx->pipe_qual_chunk = chunk_bytes(R->qual_bytes);
         CK(cudaEventRecord(ctx->ev_scal, ctx->st));
         CK(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_scal, 0));
         for (int c = 0; c < G; ++c) {
-            const size_t sb = (size_t)(B.seq[c + 1] - B.seq[c]), qb = (size_t)(B.qual[c + 1] - B.qual[c]);
-            if (sb) CK(cudaMemcpyAsync(ctx->d_seq.as<uint8_t>() + B.seq[c], R->seq + B.seq[c], sb, cudaMemcpyHostToDevice, ctx->st_copy));
-            if (qb) CK(cudaMemcpyAsync(ctx->d_qual.as<uint8_t>() + B.qual[c], R->qual + B.qual[c], qb, cudaMemcpyHostToDevice, ctx->st_copy));
+            const int64_t s0 = std::min<int64_t>(R->seq_bytes, (int64_t)c * ctx->pipe_seq_chunk), s1 = std::min<int64_t>(R->seq_bytes, (int64_t)(c + 1) * ctx->pipe_seq_chunk);
+            const int64_t q0 = std::min<int64_t>(R->qual_bytes, (int64_t)c * ctx->pipe_qual_chunk), q1 = std::min<int64_t>(R->qual_bytes, (int64_t)(c + 1) * ctx->pipe_qual_chunk);
+            if (s1 > s0) CK(cudaMemcpyAsync(ctx->d_seq.as<uint8_t>() + s0, R->seq + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, ctx->st_copy));
+            if (q1 > q0) CK(cudaMemcpyAsync(ctx->d_qual.as<uint8_t>() + q0, R->qual + q0, (size_t)(q1 - q0), cudaMemcpyHostToDevice, ctx->st_copy));
             CK(cudaEventRecord(ctx->ev_chunk[c], ctx->st_copy));
-            bytes += (int64_t)(sb + qb);
+            bytes += (s1 - s0) + (q1 - q0);
         }
         CK(cudaEventRecord(ctx->ev[1], ctx->st_copy));
-        B.n = G;
+        ctx->pipe_n = G;
     }
     ctx->tm.pipe_chunks = pipelined ? G : 0;
     ctx->tm.bytes_h2d = bytes;
@@ -442,12 +455,23 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         P.loci_key = ctx->d_loci_key.as<uint64_t>(); P.n_loci = nl;
         P.minMQ = ctx->prm.minMQ; P.primerDist = ctx->prm.primerDist; P.mismatchThr = ctx->prm.mismatchThr;
         P.recs = ctx->d_recs.as<ReadRec>(); P.grec = ctx->d_grec.as<GRec>(); P.ntiles = ctx->d_ntiles.as<uint32_t>(); P.gflags = small + 5;
+        if (ctx->pipe_n > 1) {
+            CK(ctx->d_pipe_need.ensure((size_t)n));
+            P.pipe_need = ctx->d_pipe_need.as<uint8_t>(); P.pipe_n = (uint32_t)ctx->pipe_n;
+            P.pipe_seq_chunk = ctx->pipe_seq_chunk; P.pipe_qual_chunk = ctx->pipe_qual_chunk;
+        }
         LAUNCH(k_read_prep, nblk(n, 256), 256, 0, P);
         exclusive_scan_u32(ctx->d_ntiles.as<uint32_t>(), ctx->d_evoff.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + 4, ctx->st);
-        uint32_t h[2];
+        uint32_t h[2], tot[3];
         CK(cudaMemcpyAsync(h, small + 4, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(tot, small + 40, 12, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         if (h[1] & GF_BAD_READ) { ctx->err = "a read has l_seq or clip length > 65535 (unsupported)"; return SMC_E_LIMIT; }
+        if ((ctx->packed_seq && (int64_t)tot[0] != ctx->seq_bytes) || (ctx->packed_qual && (int64_t)tot[1] != ctx->qual_bytes) ||
+            (ctx->packed_cigar && (int64_t)tot[2] != ctx->n_cigar_words)) {
+            ctx->err = "packed payload (NULL offsets): seq_bytes / qual_bytes / n_cigar_words do not match the sums of (l_seq+1)/2, l_seq, n_cigar";
+            return SMC_E_ARG;
+        }
         NE = h[0];
     }
     CK(cudaEventRecord(ctx->ev[3], ctx->st));
@@ -494,25 +518,22 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
     ctx->ev_read_sorted = ev_read_sorted;
     ctx->n_tiles = n_tiles; ctx->n_tile_events = NE;
     (void)ev_key_sorted;
-    if (ctx->pipe.n > 1 && NE > 0) {
-        // which units may start after which chunk: a unit needs the chunk that holds its last read (BAM index)
-        const int G = ctx->pipe.n;
-        uint32_t init[1 + SMC_PIPE_MAX];
-        init[0] = 0u;
-        for (int c = 0; c < SMC_PIPE_MAX; ++c) init[1 + c] = ctx->n_units_cap;
-        uint32_t* pd = small + 16;                      // [16] layout flag, [17 ..] first blocked unit per chunk
+    if (ctx->pipe_n > 1 && NE > 0) {
+        // which units may start after which chunk: a unit needs the latest chunk any of its reads needs (k_read_prep: pipe_need)
+        const int G = ctx->pipe_n;
+        uint32_t init[SMC_PIPE_MAX];
+        for (int c = 0; c < SMC_PIPE_MAX; ++c) init[c] = ctx->n_units_cap;
+        uint32_t* pd = small + 16;                      // first blocked unit per chunk
         CK(cudaMemcpyAsync(pd, init, sizeof(init), cudaMemcpyHostToDevice, ctx->st));
-        LAUNCH(k_pipe_check_layout, nblk(n, 256), 256, 0, ctx->d_lseq.as<int32_t>(), ctx->d_seq_off.as<int64_t>(),
-               ctx->d_qual_off.as<int64_t>(), n, ctx->pipe, pd);
         LAUNCH(k_pipe_unit_need, nblk((int64_t)ctx->n_units_cap * 32, 256), 256, 0, ctx->d_unit_eb.as<uint32_t>(),
-               ctx->d_unit_ee.as<uint32_t>(), ev_read_sorted, ctx->d_recs.as<ReadRec>(), ctx->n_units_cap, ctx->pipe, pd + 1);
-        uint32_t h[1 + SMC_PIPE_MAX];
+               ctx->d_unit_ee.as<uint32_t>(), ev_read_sorted, ctx->d_pipe_need.as<uint8_t>(), ctx->n_units_cap, pd);
+        uint32_t h[SMC_PIPE_MAX];
         CK(cudaMemcpyAsync(h, pd, sizeof(h), cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         uint32_t run = ctx->n_units_cap;
         for (int c = G - 1; c >= 0; --c) {
-            if (c < G - 1) run = std::min(run, h[1 + c]);
-            ctx->pipe_end[c] = (h[0] && c < G - 1) ? 0u : run;      // layout not in read order: everything waits for the last chunk
+            if (c < G - 1) run = std::min(run, h[c]);
+            ctx->pipe_end[c] = run;
         }
     }
     CK(cudaEventRecord(ctx->ev[4], ctx->st));
@@ -605,11 +626,11 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
             KAArgs A; KBArgs B;
             fill_kargs(ctx, A, B, false, ctx->has_keep);
             CK(cudaEventRecord(ctx->ev[8], ctx->st));
-            if (ctx->pipe.n > 1) {
+            if (ctx->pipe_n > 1) {
                 // pipelined upload: units [pipe_end[c-1], pipe_end[c]) start as soon as chunk c of the bases / qualities is in
                 uint32_t u0 = 0;
                 ctx->tm.pipe_launches = 0;
-                for (int c = 0; c < ctx->pipe.n; ++c) {
+                for (int c = 0; c < ctx->pipe_n; ++c) {
                     CK(cudaStreamWaitEvent(ctx->st, ctx->ev_chunk[c], 0));
                     const uint32_t u1 = ctx->pipe_end[c];
                     if (u1 <= u0) continue;
@@ -773,7 +794,7 @@ extern "C" int smc_call_batch(smc_ctx* ctx, const smc_reads_soa* reads, const sm
             ctx->err = std::string("smc_call_batch: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2); rc = SMC_E_CUDA;
         }
         if (rc == SMC_OK && ctx->uploaded) cudaEventElapsedTime(&ctx->tm.ms_h2d, ctx->ev[0], ctx->ev[1]);
-        ctx->pipe.n = 0;                                 // the batch is resident now: later smc_run_resident calls run it in one go
+        ctx->pipe_n = 0;                                 // the batch is resident now: later smc_run_resident calls run it in one go
     }
     if (rc) return rc;
     return smc_download(ctx, out);

@@ -48,6 +48,7 @@ struct PrepArgs {
     const uint64_t* loci_key; int64_t n_loci;
     int minMQ; int primerDist; double mismatchThr;
     ReadRec* recs; GRec* grec; uint32_t* ntiles; uint32_t* gflags;
+    uint8_t* pipe_need; uint32_t pipe_n, pipe_seq_chunk, pipe_qual_chunk;     // pipelined upload only (else pipe_need == nullptr)
 };
 
 #define GF_DYN_FULL   1u
@@ -125,6 +126,15 @@ __global__ void __launch_bounds__(256) k_read_prep(PrepArgs A) {
         gd[0] = gs[0]; gd[1] = gs[1];
     }
     A.ntiles[s] = hi > lo ? (uint32_t)(((hi - 1) >> 5) - (lo >> 5) + 1) : 0u;
+    if (A.pipe_need) {                                         // last chunk that carries a byte of this read
+        uint32_t c = 0;
+        if (lseq > 0) {
+            const uint32_t cs = (uint32_t)((rec.seq_off + ((uint32_t)lseq + 1u) / 2u - 1u) / A.pipe_seq_chunk);
+            const uint32_t cq = (uint32_t)((rec.qual_off + (uint32_t)lseq - 1u) / A.pipe_qual_chunk);
+            c = min(max(cs, cq), A.pipe_n - 1u);
+        }
+        A.pipe_need[s] = (uint8_t)c;
+    }
 }
 
 // Expansion of reads into (tile, read) events -- the only "event" that is ever materialised: one 12-byte row per
@@ -184,43 +194,35 @@ k_unit_bounds(const uint32_t* __restrict__ tile_off, const uint32_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Pipelined upload (smc_call_batch): bases and qualities arrive in up to SMC_PIPE_MAX chunks of consecutive reads while
-// the read sort / prep / tile sort already run; a unit may start once the chunk holding its LAST read (BAM index) is on
-// the device.  Chunk c holds reads [r[c], r[c+1]), i.e. bytes [seq[c], seq[c+1]) of seq[] and [qual[c], qual[c+1]) of qual[].
+// Pipelined upload (smc_call_batch): bases and qualities arrive in up to SMC_PIPE_MAX chunks of equal byte size while the
+// read sort / prep / tile sort already run.  k_read_prep records, per read, the chunk that completes its bases AND its
+// qualities (PrepArgs::pipe_need); a unit may start once the latest chunk any of its reads needs is on the device.  Exact
+// for any payload layout; a payload stored in read order (a BAM decode) makes the units become ready front to back.
 // ------------------------------------------------------------------------------------------------------------
 #define SMC_PIPE_MAX 16
-struct PipeBounds { int n; int64_t r[SMC_PIPE_MAX + 1]; int64_t seq[SMC_PIPE_MAX + 1]; int64_t qual[SMC_PIPE_MAX + 1]; };
-
-__device__ __forceinline__ int pipe_chunk_of(const PipeBounds& B, int64_t read) {
-    int c = 0;
-    while (c + 1 < B.n && read >= B.r[c + 1]) ++c;
-    return c;
-}
-// every read's bases / qualities must lie inside its chunk's byte range (true for any SoA laid out in read order);
-// otherwise *bad is set and the host waits for the whole upload before the first pileup launch
-__global__ void __launch_bounds__(256)
-k_pipe_check_layout(const int32_t* __restrict__ l_seq, const int64_t* __restrict__ seq_off, const int64_t* __restrict__ qual_off,
-                    int64_t n, const PipeBounds B, uint32_t* __restrict__ bad) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const int c = pipe_chunk_of(B, r);
-    const int64_t l = l_seq[r], s0 = seq_off[r], q0 = qual_off[r];
-    if (l > 0 && (s0 < B.seq[c] || s0 + (l + 1) / 2 > B.seq[c + 1] || q0 < B.qual[c] || q0 + l > B.qual[c + 1])) *bad = 1u;
-}
 // first_blocked[c] = smallest unit that has to wait for chunk c + 1 (one warp per unit)
 __global__ void __launch_bounds__(256)
 k_pipe_unit_need(const uint32_t* __restrict__ unit_eb, const uint32_t* __restrict__ unit_ee, const uint32_t* __restrict__ ev_read,
-                 const ReadRec* __restrict__ recs, uint32_t n_units, const PipeBounds B, uint32_t* __restrict__ first_blocked) {
+                 const uint8_t* __restrict__ need, uint32_t n_units, uint32_t* __restrict__ first_blocked) {
     const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (u >= n_units) return;
     const uint32_t eb = unit_eb[u], ee = unit_ee[u];
     uint32_t m = 0;
-    for (uint32_t e = eb + lane; e < ee; e += 32) m = max(m, __ldg(&recs[__ldg(&ev_read[e])].read_idx));
+    for (uint32_t e = eb + lane; e < ee; e += 32) m = max(m, (uint32_t)__ldg(&need[__ldg(&ev_read[e])]));
     for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(FULL_MASK, m, d));
-    if (lane == 0 && eb < ee) {
-        const int c = pipe_chunk_of(B, (int64_t)m);
-        if (c > 0) atomicMin(&first_blocked[c - 1], u);
-    }
+    if (lane == 0 && eb < ee && m > 0) atomicMin(&first_blocked[m - 1], u);
+}
+// Packed payloads (smc_reads_soa offsets passed as NULL): per-read byte / word counts, scanned into the offsets on the device
+__global__ void __launch_bounds__(256)
+k_pack_len(const int32_t* __restrict__ l_seq, const uint16_t* __restrict__ n_cigar, int64_t n, int kind, uint32_t* __restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t l = kind == 2 ? 0u : (uint32_t)max(l_seq[r], 0);
+    out[r] = kind == 0 ? (l + 1u) / 2u : kind == 1 ? l : (uint32_t)n_cigar[r];
+}
+__global__ void __launch_bounds__(256) k_widen_u32(const uint32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) out[r] = (int64_t)in[r];
 }
 
 // ------------------------------------------------------------------------------------------------------------

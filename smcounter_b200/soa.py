@@ -41,6 +41,7 @@ class ReadsSoA:
     cigar: np.ndarray       # uint32  len<<4 | op
     chroms: list = field(default_factory=list)
     umi_names: dict | None = None   # optional code -> barcode string (host side only)
+    packed: bool = False            # payloads stored back to back in read order: the offsets need not cross the ABI (NULL)
 
     @property
     def n(self) -> int:
@@ -73,7 +74,7 @@ class ReadsSoA:
             l_seq=self.l_seq[idx], seq_off=new_seq_off, qual_off=new_qual_off, cigar_off=new_cig_off,
             n_cigar=self.n_cigar[idx], umi=self.umi[idx], frag_id=self.frag_id[idx],
             seq=gather(self.seq, self.seq_off[idx], sb), qual=gather(self.qual, self.qual_off[idx], l_seq),
-            cigar=gather(self.cigar, self.cigar_off[idx], nc), chroms=self.chroms, umi_names=self.umi_names)
+            cigar=gather(self.cigar, self.cigar_off[idx], nc), chroms=self.chroms, umi_names=self.umi_names, packed=True)
 
     def repack(self, block: int = 1 << 18) -> "ReadsSoA":
         """Same reads, with bases / qualities / CIGARs stored in read order (what a BAM decode produces).  libsmc_b200
@@ -97,7 +98,19 @@ class ReadsSoA:
         return ReadsSoA(ref_id=self.ref_id, pos=self.pos, flag=self.flag, mapq=self.mapq, nm=self.nm, l_seq=self.l_seq,
                         seq_off=out["seq"][1], qual_off=out["qual"][1], cigar_off=out["cigar"][1], n_cigar=self.n_cigar, umi=self.umi,
                         frag_id=self.frag_id, seq=out["seq"][0], qual=out["qual"][0], cigar=out["cigar"][0], chroms=self.chroms,
-                        umi_names=self.umi_names)
+                        umi_names=self.umi_names, packed=True)
+
+    def is_packed(self) -> bool:
+        """True when every payload is stored back to back in read order (checked, O(n))."""
+        l = self.l_seq.astype(np.int64)
+        for off, lens, tot in ((self.seq_off, (l + 1) // 2, self.seq.shape[0]), (self.qual_off, l, self.qual.shape[0]),
+                               (self.cigar_off, self.n_cigar.astype(np.int64), self.cigar.shape[0])):
+            ends = np.cumsum(lens)
+            if self.n and (not np.array_equal(off[1:], ends[:-1]) or off[0] != 0 or ends[-1] != tot):
+                return False
+            if not self.n and tot:
+                return False
+        return True
 
     def ref_end(self) -> np.ndarray:
         """0-based exclusive reference end of every read (host-side helper for sharding)."""

@@ -278,3 +278,36 @@ def test_device_hp_lowcomp_matches_oracle():
         assert len(caller.hp_lowcomp(8, [])) == 0
     finally:
         caller.close()
+
+
+def test_packed_payload_without_offsets():
+    """smc_reads_soa with seq_off / qual_off / cigar_off = NULL (payload packed in read order): the offsets are derived on
+    the device; results must match the oracle, with and without the chunked upload; a payload whose size contradicts the
+    per-read lengths is refused."""
+    import numpy as np
+    from helpers import run_case
+    from smcounter_b200.caller import GpuCaller
+    from smcounter_b200.synth import make_panel
+    from smcounter_b200.targets import build_loci
+    spec = SynthSpec(**PIPE_SPEC)
+    prm = VcParams(mtDepth=50, rpb=3.0)
+
+    def packed(soa):
+        out = soa.repack()
+        assert out.packed and out.is_packed()
+        return out
+
+    for chunks in ("1", "5"):
+        problems, stats, _ = _with_env("SMC_PIPE_CHUNKS", chunks, lambda: run_case(PIPE_IVS, spec, prm, seed=67, mutate=packed))
+        print(stats)
+        assert not problems, "\n".join(problems)
+    soa, refs, _ = make_panel(PIPE_IVS[:1], spec, seed=67)
+    soa = soa.repack()
+    soa.seq = np.ascontiguousarray(soa.seq[:-3])           # three bytes short
+    loci, _ = build_loci(PIPE_IVS[:1], soa.chroms, refs)
+    c = GpuCaller(prm, 0)
+    try:
+        with pytest.raises(RuntimeError, match="packed payload"):
+            c.call(soa, loci)
+    finally:
+        c.close()
