@@ -48,13 +48,23 @@ def parse_args():
 
 
 def make_batch(args, rank, world):
+    import pickle
     from smcounter_b200.synth import SynthSpec, make_panel_mp, panel_intervals_from_bed
     from smcounter_b200.targets import build_loci
+    cache = os.environ.get("SMC_BENCH_CACHE")           # tuning sessions: reuse the generated batch between runs
+    if cache:
+        cache = "%s.%d_%d_%d_%d" % (cache, args.intervals, args.seed, rank, world)
+        if os.path.exists(cache):
+            with open(cache, "rb") as fh:
+                return pickle.load(fh)
     ivs = panel_intervals_from_bed(PANEL_BED, limit=args.intervals * world, seed=args.seed)
     mine = ivs[rank * args.intervals:(rank + 1) * args.intervals]
     spec = SynthSpec(umis_per_locus=UMIS_PER_LOCUS, rpb=RPB, snv_every=1000, snv_vaf=0.01, indel_every=12000, indel_vaf=0.01)
     soa, refs, truth = make_panel_mp(mine, spec, seed=args.seed + 17 * rank)
     loci, bed_order = build_loci(mine, soa.chroms, refs)
+    if cache:
+        with open(cache, "wb") as fh:
+            pickle.dump((mine, soa, refs, loci, bed_order), fh, protocol=4)
     return mine, soa, refs, loci, bed_order
 
 

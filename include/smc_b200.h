@@ -70,7 +70,8 @@ typedef struct smc_reads_soa {
     const uint16_t *n_cigar;
     const uint64_t *umi;        /* injective 64-bit code of the barcode string  (BC, smCounter.py:323) */
     const uint32_t *frag_id;    /* id of (BC, readid) (smCounter.py:321), numbered by first appearance in BAM order:
-                                   ascending frag_id is the canonical fragment order inside a barcode */
+                                   ascending frag_id is the canonical fragment order inside a barcode; ids are dense
+                                   (every id < n_reads, checked: SMC_E_ARG otherwise) */
     const uint8_t  *seq;        /* BAM 4-bit bases, high nibble first, every read byte aligned */
     int64_t         seq_bytes;  /* < 4 GiB per batch */
     const uint8_t  *qual;       /* phred */

@@ -67,7 +67,7 @@ struct smc_ctx {
     // scratch
     DevBuf d_k0, d_k1, d_v0, d_v1, d_hist, d_scan, d_flags32a, d_flags32b, d_urank, d_frank, d_umi_of_urank, d_recs, d_ntiles,
         d_evoff, d_ek0, d_ek1, d_ev0, d_ev1, d_tile_off, d_unit_cnt, d_unit_off, d_small,
-        d_grec, d_ev_flags, d_unit_eb, d_unit_ee, d_unit_tile, d_unit_nfrag, d_codes, d_frag_first, d_umi_urank;
+        d_grec, d_ev_flags, d_unit_eb, d_unit_ee, d_unit_tile, d_unit_nfrag, d_codes, d_frag_first, d_umi_urank, d_umi_table;
     uint32_t code_mult = 1;                     // fragment-code storage per tile event (1, or 3 = worst case after GF_CODE_FULL)
     uint32_t n_units_cap = 0;
     // per-locus accumulators / outputs
@@ -84,7 +84,7 @@ struct smc_ctx {
     DevBuf d_list_idx, d_list_count, d_list_off, d_list_umi, d_list_first;
     DevBuf d_hp_bases, d_hp_meta, d_hp_flags;     // smc_hp_lowcomp
     smc_timings tm{};
-    uint32_t chunk = 256;       // tile events per warp unit (A/B on B200: 64 -> 4.39 ms, 256 -> 3.37, 384 -> 3.37, 2048 -> 4.0, 4096 -> 4.3)
+    uint32_t chunk = 128;       // tile events per warp unit (A/B on B200, whole step: 96 -> 4.42 ms, 128 -> 4.39, 160 -> 4.39, 256 -> 4.47, 384 -> 4.60)
     const uint32_t* ev_read_sorted = nullptr;   // tile-sorted event -> srank map (lives in d_ev0 or d_ev1)
     uint32_t n_tiles = 0; int64_t n_tile_events = 0;
 };
@@ -112,6 +112,26 @@ __global__ void k_init_pairs_frag(const uint32_t* frag, int64_t n, uint64_t* k, 
 __global__ void k_gather_umi_keys(const uint64_t* umi, const uint32_t* v, int64_t n, uint64_t* k) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) k[i] = umi[v[i]];
+}
+// Barcode slots: every distinct barcode code gets one slot of an open-addressing table (linear probing, atomicCAS); the slot
+// index stands in for the barcode in the read sort key, so that ONE sort on (slot, fragment id) groups the reads by barcode and
+// fragment.  Which slot a barcode lands in may differ from run to run; nothing downstream depends on the order of barcodes
+// (the PI sums are fixed point, every other accumulation is an integer).
+#define UMI_EMPTY 0xffffffffffffffffull
+__global__ void k_umi_slots(const uint64_t* __restrict__ umi, const uint32_t* __restrict__ frag, int64_t n, unsigned long long* __restrict__ table,
+                            uint32_t mask, int frag_bits, uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long u = umi[i];
+    uint32_t h = hash64to32(u) & mask;
+    for (;;) {
+        unsigned long long cur = table[h];
+        if (cur == UMI_EMPTY) cur = atomicCAS(&table[h], UMI_EMPTY, u);
+        if (cur == UMI_EMPTY || cur == u) break;
+        h = (h + 1) & mask;
+    }
+    key[i] = ((uint64_t)h << frag_bits) | (uint64_t)frag[i];
+    val[i] = (uint32_t)i;
 }
 __global__ void k_heads(const uint64_t* umi, const uint32_t* frag, const uint32_t* perm, int64_t n, uint32_t* uhead, uint32_t* fhead) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -248,6 +268,7 @@ extern "C" int smc_ctx_create(int device, const smc_params* params, smc_ctx** ou
         return fail("cudaFuncSetAttribute(k_gather)", e);
     if ((e = cudaFuncSetAttribute(k_gather_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KA_SMEM_BYTES(true))) != cudaSuccess)
         return fail("cudaFuncSetAttribute(k_gather list)", e);
+    if ((e = radix_sort_init()) != cudaSuccess) return fail("cudaFuncSetAttribute(k_radix_scatter)", e);
     if ((e = ctx->d_small.ensure(4096)) != cudaSuccess) return fail("cudaMalloc", e);
     *out = ctx;
     return SMC_OK;
@@ -271,7 +292,7 @@ extern "C" void smc_ctx_destroy(smc_ctx* ctx) {
                       &ctx->d_lk0, &ctx->d_lk1, &ctx->d_lv0, &ctx->d_lv1, &ctx->d_s_key, &ctx->d_s_cnt, &ctx->d_s_limb, &ctx->d_s_iskey,
                       &ctx->d_s_pi, &ctx->d_s_rep_read, &ctx->d_s_rep_qpos, &ctx->d_s_len, &ctx->d_dyn_first, &ctx->d_tasks,
                       &ctx->d_list_idx, &ctx->d_list_count, &ctx->d_list_off, &ctx->d_list_umi, &ctx->d_list_first,
-                      &ctx->d_hp_bases, &ctx->d_hp_meta, &ctx->d_hp_flags, &ctx->d_pipe_need};
+                      &ctx->d_hp_bases, &ctx->d_hp_meta, &ctx->d_hp_flags, &ctx->d_pipe_need, &ctx->d_umi_table};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_chunk) if (ev) cudaEventDestroy(ev);
@@ -404,31 +425,32 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
     uint32_t* small = ctx->d_small.as<uint32_t>();          // [0..1] u64 or/and  [4] NE  [5] gflags  [6] dyn count  [7] n_tasks  [8..9] u64 cvg sum
     CK(cudaEventRecord(ctx->ev[2], ctx->st));
     int64_t NE = 0;
+    int frag_bits_used = 32;
     if (n > 0 && nl > 0) {
-        // ---------------- K2a: order reads by (umi, frag_id, BAM index)
+        // ---------------- K2a: order reads by (barcode, frag_id, BAM index): one stable sort on (barcode slot, frag_id)
         CK(ctx->d_k0.ensure((size_t)n * 8)); CK(ctx->d_k1.ensure((size_t)n * 8));
         CK(ctx->d_v0.ensure((size_t)n * 4)); CK(ctx->d_v1.ensure((size_t)n * 4));
-        const uint32_t rs_blocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
-        CK(ctx->d_hist.ensure((size_t)256 * rs_blocks * 4 + 1024));
-        CK(ctx->d_scan.ensure((size_t)scan_scratch_words(std::max<int64_t>((int64_t)256 * rs_blocks, n + 1)) * 4 + 1024));
+        CK(ctx->d_hist.ensure(radix_hist_words(n) * 4 + 1024));
+        CK(ctx->d_scan.ensure((size_t)std::max<int64_t>(radix_scan_words(n), scan_scratch_words(n + 1)) * 4 + 1024));
         uint64_t* k0 = ctx->d_k0.as<uint64_t>(); uint64_t* k1 = ctx->d_k1.as<uint64_t>();
         uint32_t* v0 = ctx->d_v0.as<uint32_t>(); uint32_t* v1 = ctx->d_v1.as<uint32_t>();
-        unsigned long long orand[2];
-        auto sort_on = [&](uint64_t*& ka, uint32_t*& va, uint64_t*& kb, uint32_t*& vb) -> int {
+        int slot_bits = 4;                                             // table of >= 2n slots
+        while ((1ll << slot_bits) < 2 * n) ++slot_bits;
+        int frag_bits = 1;                                             // frag_id < 2^frag_bits; checked below (the contract says
+        while ((1ll << frag_bits) < n) ++frag_bits;                    // ids are dense, first-appearance numbers, hence < n_reads)
+        frag_bits_used = frag_bits;
+        CK(ctx->d_umi_table.ensure(((size_t)1 << slot_bits) * 8));
+        CK(cudaMemsetAsync(ctx->d_umi_table.p, 0xff, ((size_t)1 << slot_bits) * 8, ctx->st));
+        {
             unsigned long long init[2] = {0ull, ~0ull};
             CK(cudaMemcpyAsync(small, init, 16, cudaMemcpyHostToDevice, ctx->st));
-            LAUNCH(k_or_and_u64, std::min<unsigned>(nblk(n, 256), 1184u), 256, 0, ka, n, (unsigned long long*)small);
-            CK(cudaMemcpyAsync(orand, small, 16, cudaMemcpyDeviceToHost, ctx->st));
-            CK(cudaStreamSynchronize(ctx->st));
-            uint32_t bm = varying_byte_mask(orand[0], orand[1]);
-            int res = radix_sort_pairs(ka, va, kb, vb, n, bm, ctx->d_hist.as<uint32_t>(), ctx->d_scan.as<uint32_t>(), ctx->st);
-            if (res) { std::swap(ka, kb); std::swap(va, vb); }
-            return SMC_OK;
-        };
-        LAUNCH(k_init_pairs_frag, nblk(n, 256), 256, 0, ctx->d_frag.as<uint32_t>(), n, k0, v0);
-        { int rc = sort_on(k0, v0, k1, v1); if (rc) return rc; }
-        LAUNCH(k_gather_umi_keys, nblk(n, 256), 256, 0, ctx->d_umi.as<uint64_t>(), v0, n, k0);
-        { int rc = sort_on(k0, v0, k1, v1); if (rc) return rc; }
+            LAUNCH(k_or_and_u32, std::min<unsigned>(nblk(n, 256), 1184u), 256, 0, ctx->d_frag.as<uint32_t>(), n, (unsigned long long*)small);
+        }
+        LAUNCH(k_umi_slots, nblk(n, 256), 256, 0, ctx->d_umi.as<uint64_t>(), ctx->d_frag.as<uint32_t>(), n,
+               ctx->d_umi_table.as<unsigned long long>(), (uint32_t)((1u << slot_bits) - 1u), frag_bits, k0, v0);
+        if (radix_sort_bits(k0, v0, k1, v1, n, 0, slot_bits + frag_bits, ctx->d_hist.as<uint32_t>(), ctx->d_scan.as<uint32_t>(), ctx->st)) {
+            std::swap(k0, k1); std::swap(v0, v1);
+        }
         const uint32_t* perm = v0;
         // dense barcode / fragment ranks
         CK(ctx->d_flags32a.ensure((size_t)n * 4)); CK(ctx->d_flags32b.ensure((size_t)n * 4));
@@ -463,10 +485,13 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         LAUNCH(k_read_prep, nblk(n, 256), 256, 0, P);
         exclusive_scan_u32(ctx->d_ntiles.as<uint32_t>(), ctx->d_evoff.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + 4, ctx->st);
         uint32_t h[2], tot[3];
+        unsigned long long frag_or = 0;
+        CK(cudaMemcpyAsync(&frag_or, small, 8, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaMemcpyAsync(h, small + 4, 8, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaMemcpyAsync(tot, small + 40, 12, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         if (h[1] & GF_BAD_READ) { ctx->err = "a read has l_seq or clip length > 65535 (unsupported)"; return SMC_E_LIMIT; }
+        if (frag_or >> frag_bits_used) { ctx->err = "frag_id must be a dense id (< n_reads), numbered by first appearance"; return SMC_E_ARG; }
         if ((ctx->packed_seq && (int64_t)tot[0] != ctx->seq_bytes) || (ctx->packed_qual && (int64_t)tot[1] != ctx->qual_bytes) ||
             (ctx->packed_cigar && (int64_t)tot[2] != ctx->n_cigar_words)) {
             ctx->err = "packed payload (NULL offsets): seq_bytes / qual_bytes / n_cigar_words do not match the sums of (l_seq+1)/2, l_seq, n_cigar";
@@ -482,15 +507,14 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
     if (NE > 0) {
         CK(ctx->d_ek0.ensure((size_t)NE * 8)); CK(ctx->d_ek1.ensure((size_t)NE * 8));
         CK(ctx->d_ev0.ensure((size_t)NE * 4)); CK(ctx->d_ev1.ensure((size_t)NE * 4));
-        const uint32_t rs_blocks = (uint32_t)((NE + RS_TILE - 1) / RS_TILE);
-        CK(ctx->d_hist.ensure((size_t)256 * rs_blocks * 4 + 1024));
-        CK(ctx->d_scan.ensure((size_t)scan_scratch_words(std::max<int64_t>((int64_t)256 * rs_blocks, (int64_t)n_tiles + 2)) * 4 + 1024));
+        CK(ctx->d_hist.ensure(radix_hist_words(NE) * 4 + 1024));
+        CK(ctx->d_scan.ensure((size_t)std::max<int64_t>(radix_scan_words(NE), scan_scratch_words((int64_t)n_tiles + 2)) * 4 + 1024));
         LAUNCH(k_expand, nblk(n, 256), 256, 0, ctx->d_recs.as<ReadRec>(), ctx->d_evoff.as<uint32_t>(), n, ctx->d_ek0.as<uint64_t>(),
                ctx->d_ev0.as<uint32_t>());
-        uint32_t bm = 0;
-        for (int b = 0; b < 4; ++b) if (((uint64_t)(n_tiles - 1) >> (8 * b)) & 0xff) bm |= 1u << b;
-        int res = radix_sort_pairs(ctx->d_ek0.as<uint64_t>(), ctx->d_ev0.as<uint32_t>(), ctx->d_ek1.as<uint64_t>(), ctx->d_ev1.as<uint32_t>(),
-                                   NE, bm, ctx->d_hist.as<uint32_t>(), ctx->d_scan.as<uint32_t>(), ctx->st);
+        int tile_bits = 0;                                             // a panel batch of <= 2048 tiles is ONE pass
+        while (((uint64_t)(n_tiles - 1) >> tile_bits) != 0) ++tile_bits;
+        int res = radix_sort_bits(ctx->d_ek0.as<uint64_t>(), ctx->d_ev0.as<uint32_t>(), ctx->d_ek1.as<uint64_t>(), ctx->d_ev1.as<uint32_t>(),
+                                  NE, 0, tile_bits, ctx->d_hist.as<uint32_t>(), ctx->d_scan.as<uint32_t>(), ctx->st);
         ev_key_sorted = res ? ctx->d_ek1.as<uint64_t>() : ctx->d_ek0.as<uint64_t>();
         ev_read_sorted = res ? ctx->d_ev1.as<uint32_t>() : ctx->d_ev0.as<uint32_t>();
         LAUNCH(k_tile_offsets, nblk((int64_t)n_tiles + 1, 256), 256, 0, ev_key_sorted, NE, n_tiles, ctx->d_tile_off.as<uint32_t>());

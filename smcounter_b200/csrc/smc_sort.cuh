@@ -88,40 +88,49 @@ static void exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uin
 }
 
 // ---------------------------------------------------------------- radix sort --------------------------------
+// LSD passes over a bit field of the key: digit = (key >> shift) & (2^BITS - 1), BITS = 8 ... 11 chosen per sort so that
+// the varying bits are covered in as few passes as possible (e.g. a 9-bit tile index is ONE pass, a 45-bit
+// (barcode slot, fragment) key is five 9-bit passes).
 #define RS_WARPS   8
 #define RS_THREADS (RS_WARPS * 32)
 #define RS_ITEMS   8
 #define RS_TILE    (RS_THREADS * RS_ITEMS)
+#define RS_MAX_BITS 11
 
 // Element order inside a tile: warp w owns [w*256, w*256+256), iteration it covers 32 consecutive elements.
 __device__ __forceinline__ int64_t rs_index(int64_t tile_base, int w, int it, int lane) {
     return tile_base + (int64_t)w * (32 * RS_ITEMS) + it * 32 + lane;
 }
 
+template <int BITS>
 __global__ void __launch_bounds__(RS_THREADS)
 k_radix_hist(const uint64_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ hist, uint32_t nblocks) {
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
+    constexpr uint32_t ND = 1u << BITS;
+    __shared__ uint32_t h[ND];
+    for (uint32_t d = threadIdx.x; d < ND; d += RS_THREADS) h[d] = 0;
     __syncthreads();
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int64_t tb = (int64_t)blockIdx.x * RS_TILE;
 #pragma unroll
     for (int it = 0; it < RS_ITEMS; ++it) {
         int64_t i = rs_index(tb, w, it, lane);
-        if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+        if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & (ND - 1u)], 1u);
     }
     __syncthreads();
-    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+    for (uint32_t d = threadIdx.x; d < ND; d += RS_THREADS) hist[(size_t)d * nblocks + blockIdx.x] = h[d];
 }
 
+template <int BITS>
 __global__ void __launch_bounds__(RS_THREADS)
 k_radix_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t* __restrict__ keys_out,
                 uint32_t* __restrict__ vals_out, int64_t n, int shift, const uint32_t* __restrict__ hist_scanned,
                 uint32_t nblocks) {
-    __shared__ uint32_t wh[RS_WARPS][256];
+    constexpr uint32_t ND = 1u << BITS;
+    extern __shared__ uint32_t wh_s[];                  // [RS_WARPS][ND]
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wh[0][0])[i] = 0;
+    for (uint32_t i = threadIdx.x; i < RS_WARPS * ND; i += RS_THREADS) wh_s[i] = 0;
     __syncthreads();
+    uint32_t* wh = wh_s + (size_t)w * ND;
     int64_t tb = (int64_t)blockIdx.x * RS_TILE;
     uint64_t k[RS_ITEMS];
     uint32_t v[RS_ITEMS];
@@ -131,17 +140,17 @@ k_radix_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
         if (i < n) {
             k[it] = keys[i];
             v[it] = vals[i];
-            atomicAdd(&wh[w][(uint32_t)(k[it] >> shift) & 255u], 1u);
+            atomicAdd(&wh[(uint32_t)(k[it] >> shift) & (ND - 1u)], 1u);
         }
     }
     __syncthreads();
-    {   // per digit: global base of this block, then exclusive prefix over the warps
-        uint32_t d = threadIdx.x;
+    // per digit: global base of this block, then exclusive prefix over the warps
+    for (uint32_t d = threadIdx.x; d < ND; d += RS_THREADS) {
         uint32_t run = hist_scanned[(size_t)d * nblocks + blockIdx.x];
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ++ww) {
-            uint32_t t = wh[ww][d];
-            wh[ww][d] = run;
+            uint32_t t = wh_s[(size_t)ww * ND + d];
+            wh_s[(size_t)ww * ND + d] = run;
             run += t;
         }
     }
@@ -153,14 +162,14 @@ k_radix_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
         bool valid = i < n;
         uint32_t active = __ballot_sync(FULL_MASK, valid);
         if (valid) {
-            uint32_t d = (uint32_t)(k[it] >> shift) & 255u;
+            uint32_t d = (uint32_t)(k[it] >> shift) & (ND - 1u);
             uint32_t peers = __match_any_sync(active, d);
             uint32_t rank = __popc(peers & lt);
             int leader = __ffs(peers) - 1;
             uint32_t off = 0;
             if (lane == leader) {
-                off = wh[w][d];
-                wh[w][d] = off + __popc(peers);
+                off = wh[d];
+                wh[d] = off + __popc(peers);
             }
             off = __shfl_sync(peers, off, leader);
             keys_out[off + rank] = k[it];
@@ -170,22 +179,61 @@ k_radix_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
     }
 }
 
-// Stable sort of (keys, vals) on the key bytes selected by `byte_mask` (bit b set = byte b varies).
+// scratch sizes of a sort of n elements (any digit width up to RS_MAX_BITS)
+static inline size_t radix_hist_words(int64_t n) { return ((size_t)1 << RS_MAX_BITS) * (size_t)((n + RS_TILE - 1) / RS_TILE) + 256; }
+static inline int64_t radix_scan_words(int64_t n) { return scan_scratch_words((int64_t)radix_hist_words(n)); }
+
+template <int BITS>
+static void radix_pass(const uint64_t* ki, const uint32_t* vi, uint64_t* ko, uint32_t* vo, int64_t n, int shift, uint32_t* hist,
+                       uint32_t* scan_scratch, cudaStream_t st) {
+    const uint32_t nblocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+    constexpr size_t smem = (size_t)RS_WARPS * (1u << BITS) * 4;      // 11 bits: 64 KB, opted in per device by radix_sort_init()
+    k_radix_hist<BITS><<<nblocks, RS_THREADS, 0, st>>>(ki, n, shift, hist, nblocks);
+    ++g_launches;
+    exclusive_scan_u32(hist, hist, (int64_t)(1u << BITS) * nblocks, scan_scratch, nullptr, st);
+    k_radix_scatter<BITS><<<nblocks, RS_THREADS, smem, st>>>(ki, vi, ko, vo, n, shift, hist, nblocks);
+    ++g_launches;
+}
+
+// once per device: the 11-bit scatter needs more dynamic shared memory than the default limit
+static cudaError_t radix_sort_init() {
+    return cudaFuncSetAttribute(k_radix_scatter<RS_MAX_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_WARPS * (1 << RS_MAX_BITS) * 4);
+}
+
+// Stable sort of (keys, vals) on key bits [lo_bit, lo_bit + nbits), in ceil(nbits / 11) passes of equal digit width (>= 8).
 // Ping-pongs between (k0,v0) and (k1,v1); returns 0 if the result is in (k0,v0), 1 if in (k1,v1).
+static int radix_sort_bits(uint64_t* k0, uint32_t* v0, uint64_t* k1, uint32_t* v1, int64_t n, int lo_bit, int nbits, uint32_t* hist,
+                           uint32_t* scan_scratch, cudaStream_t st) {
+    if (n <= 1 || nbits <= 0) return 0;
+    const int npass = (nbits + RS_MAX_BITS - 1) / RS_MAX_BITS;
+    int width = (nbits + npass - 1) / npass;
+    if (width < 8) width = 8;
+    int cur = 0;
+    for (int done = 0; done < nbits; done += width) {
+        uint64_t* ki = cur ? k1 : k0; uint32_t* vi = cur ? v1 : v0;
+        uint64_t* ko = cur ? k0 : k1; uint32_t* vo = cur ? v0 : v1;
+        const int shift = lo_bit + done;
+        switch (width) {
+            case 8:  radix_pass<8>(ki, vi, ko, vo, n, shift, hist, scan_scratch, st); break;
+            case 9:  radix_pass<9>(ki, vi, ko, vo, n, shift, hist, scan_scratch, st); break;
+            case 10: radix_pass<10>(ki, vi, ko, vo, n, shift, hist, scan_scratch, st); break;
+            default: radix_pass<11>(ki, vi, ko, vo, n, shift, hist, scan_scratch, st); break;
+        }
+        cur ^= 1;
+    }
+    return cur;
+}
+
+// Stable sort of (keys, vals) on the key bytes selected by `byte_mask` (bit b set = byte b varies), 8 bits per pass.
 static int radix_sort_pairs(uint64_t* k0, uint32_t* v0, uint64_t* k1, uint32_t* v1, int64_t n, uint32_t byte_mask,
                             uint32_t* hist, uint32_t* scan_scratch, cudaStream_t st) {
     if (n <= 1) return 0;
-    uint32_t nblocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
     int cur = 0;
     for (int b = 0; b < 8; ++b) {
         if (!((byte_mask >> b) & 1u)) continue;
         uint64_t* ki = cur ? k1 : k0; uint32_t* vi = cur ? v1 : v0;
         uint64_t* ko = cur ? k0 : k1; uint32_t* vo = cur ? v0 : v1;
-        k_radix_hist<<<nblocks, RS_THREADS, 0, st>>>(ki, n, b * 8, hist, nblocks);
-        ++g_launches;
-        exclusive_scan_u32(hist, hist, (int64_t)256 * nblocks, scan_scratch, nullptr, st);
-        k_radix_scatter<<<nblocks, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n, b * 8, hist, nblocks);
-        ++g_launches;
+        radix_pass<8>(ki, vi, ko, vo, n, b * 8, hist, scan_scratch, st);
         cur ^= 1;
     }
     return cur;
@@ -212,4 +260,13 @@ static inline uint32_t varying_byte_mask(uint64_t orv, uint64_t andv) {
     for (int b = 0; b < 8; ++b)
         if ((diff >> (8 * b)) & 0xffull) m |= 1u << b;
     return m;
+}
+
+// bitwise OR of an array of u32 into out[0] (range check of the fragment ids)
+__global__ void k_or_and_u32(const uint32_t* __restrict__ a, int64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long o = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) o |= a[i];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) o |= __shfl_xor_sync(FULL_MASK, o, s);
+    if (lane_id() == 0 && o) atomicOr(&out[0], o);
 }

@@ -72,7 +72,9 @@ class ReadsSoA:
         return ReadsSoA(
             ref_id=self.ref_id[idx], pos=self.pos[idx], flag=self.flag[idx], mapq=self.mapq[idx], nm=self.nm[idx],
             l_seq=self.l_seq[idx], seq_off=new_seq_off, qual_off=new_qual_off, cigar_off=new_cig_off,
-            n_cigar=self.n_cigar[idx], umi=self.umi[idx], frag_id=self.frag_id[idx],
+            n_cigar=self.n_cigar[idx], umi=self.umi[idx],
+            # ids stay dense (< n reads, include/smc_b200.h) and keep their relative order = the fragment order inside a barcode
+            frag_id=np.unique(self.frag_id[idx], return_inverse=True)[1].astype(np.uint32) if len(idx) else self.frag_id[idx],
             seq=gather(self.seq, self.seq_off[idx], sb), qual=gather(self.qual, self.qual_off[idx], l_seq),
             cigar=gather(self.cigar, self.cigar_off[idx], nc), chroms=self.chroms, umi_names=self.umi_names, packed=True)
 

@@ -311,3 +311,22 @@ def test_packed_payload_without_offsets():
             c.call(soa, loci)
     finally:
         c.close()
+
+
+def test_fragment_ids_must_be_dense():
+    """frag_id is part of the read sort key ((barcode slot, frag_id) in one sort), sized from n_reads: ids that are not
+    dense first-appearance numbers (>= 2^ceil(log2 n_reads)) are refused instead of being sorted wrongly."""
+    import numpy as np
+    from smcounter_b200.caller import GpuCaller
+    from smcounter_b200.synth import make_panel
+    from smcounter_b200.targets import build_loci
+    ivs = [("chr1", 1000, 1040)]
+    soa, refs, _ = make_panel(ivs, SynthSpec(umis_per_locus=20, rpb=3.0), seed=71)
+    loci, _ = build_loci(ivs, soa.chroms, refs)
+    soa.frag_id = (soa.frag_id.astype(np.uint64) + np.uint64(4 * soa.n)).astype(np.uint32)
+    c = GpuCaller(VcParams(mtDepth=20, rpb=3.0), 0)
+    try:
+        with pytest.raises(RuntimeError, match="dense id"):
+            c.call(soa, loci)
+    finally:
+        c.close()
