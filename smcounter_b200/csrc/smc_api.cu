@@ -695,11 +695,12 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
         CK(cudaMemsetAsync(small + 6, 0, 4, ctx->st));
         LAUNCH(k_dyn_collect, nblk(ctx->dyn_cap, 256), 256, 0, ctx->d_dkey.as<unsigned long long>(), ctx->dyn_cap, ctx->d_lk0.as<uint64_t>(),
                ctx->d_lv0.as<uint32_t>(), small + 6);
-        const uint32_t rs_blocks = (uint32_t)((nd + RS_TILE - 1) / RS_TILE);
-        CK(ctx->d_hist.ensure((size_t)256 * rs_blocks * 4 + 1024));
-        CK(ctx->d_scan.ensure((size_t)scan_scratch_words((int64_t)256 * rs_blocks) * 4 + 1024));
-        int res = radix_sort_pairs(ctx->d_lk0.as<uint64_t>(), ctx->d_lv0.as<uint32_t>(), ctx->d_lk1.as<uint64_t>(), ctx->d_lv1.as<uint32_t>(), nd,
-                                   0xffu, ctx->d_hist.as<uint32_t>(), ctx->d_scan.as<uint32_t>(), ctx->st);
+        CK(ctx->d_hist.ensure(radix_hist_words(nd) * 4 + 1024));
+        CK(ctx->d_scan.ensure((size_t)radix_scan_words(nd) * 4 + 1024));
+        int locus_bits = 1;                                            // key = locus | kind | site | payload: only the locus bits in use
+        while ((1ll << locus_bits) < nl) ++locus_bits;
+        int res = radix_sort_bits(ctx->d_lk0.as<uint64_t>(), ctx->d_lv0.as<uint32_t>(), ctx->d_lk1.as<uint64_t>(), ctx->d_lv1.as<uint32_t>(), nd,
+                                  0, DYN_LOCUS_SHIFT + locus_bits, ctx->d_hist.as<uint32_t>(), ctx->d_scan.as<uint32_t>(), ctx->st);
         const uint64_t* lk = res ? ctx->d_lk1.as<uint64_t>() : ctx->d_lk0.as<uint64_t>();
         const uint32_t* lv = res ? ctx->d_lv1.as<uint32_t>() : ctx->d_lv0.as<uint32_t>();
         LAUNCH(k_dyn_gather, nblk(nd, 128), 128, 0, lk, lv, nd, ctx->d_dcnt.as<int32_t>(), ctx->d_dlimb.as<unsigned long long>(),

@@ -1,9 +1,10 @@
 // Hand-written device-wide exclusive scan and stable LSD radix sort (u64 key, u32 payload).
 //
-// K2 of the pipeline ("segmented radix sort"): reads are ordered by (barcode, fragment, BAM index) and the
+// K2 of the pipeline ("segmented radix sort"): reads are ordered by (barcode slot, fragment, BAM index) and the
 // (read x 32-locus tile) events by tile, so that every tile's events form one segment in which barcodes and
-// fragments are contiguous runs in BAM order.  Both sorts are LSD passes of 8 bits over only the bits that vary.
-// HBM-bound: each pass reads 12 B and writes 12 B per element; histogram, scan and scatter are separate kernels.
+// fragments are contiguous runs in BAM order.  Both sorts are LSD passes over exactly the key bits in use, with a digit
+// width of 8-11 bits chosen per sort.  Each pass reads 12 B and writes 12 B per element (the working sets of a panel batch
+// fit the 126 MB L2); histogram, scan and scatter are separate kernels.
 #pragma once
 #include "smc_common.cuh"
 
@@ -222,44 +223,6 @@ static int radix_sort_bits(uint64_t* k0, uint32_t* v0, uint64_t* k1, uint32_t* v
         cur ^= 1;
     }
     return cur;
-}
-
-// Stable sort of (keys, vals) on the key bytes selected by `byte_mask` (bit b set = byte b varies), 8 bits per pass.
-static int radix_sort_pairs(uint64_t* k0, uint32_t* v0, uint64_t* k1, uint32_t* v1, int64_t n, uint32_t byte_mask,
-                            uint32_t* hist, uint32_t* scan_scratch, cudaStream_t st) {
-    if (n <= 1) return 0;
-    int cur = 0;
-    for (int b = 0; b < 8; ++b) {
-        if (!((byte_mask >> b) & 1u)) continue;
-        uint64_t* ki = cur ? k1 : k0; uint32_t* vi = cur ? v1 : v0;
-        uint64_t* ko = cur ? k0 : k1; uint32_t* vo = cur ? v0 : v1;
-        radix_pass<8>(ki, vi, ko, vo, n, b * 8, hist, scan_scratch, st);
-        cur ^= 1;
-    }
-    return cur;
-}
-
-// bitwise OR / AND of an array of u64 (to find the key bytes that vary)
-__global__ void k_or_and_u64(const uint64_t* __restrict__ a, int64_t n, unsigned long long* __restrict__ out /* [2]: or, and */) {
-    unsigned long long o = 0, d = ~0ull;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        unsigned long long x = a[i];
-        o |= x; d &= x;
-    }
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-        o |= __shfl_xor_sync(FULL_MASK, o, s);
-        d &= __shfl_xor_sync(FULL_MASK, d, s);
-    }
-    if (lane_id() == 0) { atomicOr(&out[0], o); atomicAnd(&out[1], d); }
-}
-
-static inline uint32_t varying_byte_mask(uint64_t orv, uint64_t andv) {
-    uint64_t diff = orv ^ andv;   // bits that are not constant over the array
-    uint32_t m = 0;
-    for (int b = 0; b < 8; ++b)
-        if ((diff >> (8 * b)) & 0xffull) m |= 1u << b;
-    return m;
 }
 
 // bitwise OR of an array of u32 into out[0] (range check of the fragment ids)
