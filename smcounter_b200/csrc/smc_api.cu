@@ -21,18 +21,22 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// Device scratch, grown lazily.  Stream-ordered allocations from the device's default memory pool (its release threshold
+// is raised in smc_ctx_create): growing a buffer or destroying a context hands the memory back to the pool, not to the
+// driver, so the next batch / the next context of the process does not pay cudaMalloc / cudaFree again (measured: a fresh
+// context right after another one was destroyed spent 100-900 ms in cudaMalloc for a 0.3 M read batch).
 struct DevBuf {
-    void* p = nullptr; size_t cap = 0;
+    void* p = nullptr; size_t cap = 0; cudaStream_t st = nullptr;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, st);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
+        cudaError_t e = cudaMallocAsync(&p, want, st);
         if (e == cudaSuccess) cap = want;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -88,6 +92,23 @@ struct smc_ctx {
     const uint32_t* ev_read_sorted = nullptr;   // tile-sorted event -> srank map (lives in d_ev0 or d_ev1)
     uint32_t n_tiles = 0; int64_t n_tile_events = 0;
 };
+
+static std::vector<DevBuf*> all_bufs(smc_ctx* ctx) {
+    return {&ctx->d_ref_id, &ctx->d_pos, &ctx->d_flag, &ctx->d_mapq, &ctx->d_nm, &ctx->d_lseq, &ctx->d_seq_off, &ctx->d_qual_off,
+                      &ctx->d_cig_off, &ctx->d_ncig, &ctx->d_umi, &ctx->d_frag, &ctx->d_seq, &ctx->d_qual, &ctx->d_cigar, &ctx->d_loci_ref,
+                      &ctx->d_loci_pos, &ctx->d_loci_base, &ctx->d_loci_key, &ctx->d_keep_idx, &ctx->d_keep_off, &ctx->d_keep_umi,
+                      &ctx->d_bqtab, &ctx->d_pcrtab, &ctx->d_k0, &ctx->d_k1, &ctx->d_v0, &ctx->d_v1, &ctx->d_hist, &ctx->d_scan,
+                      &ctx->d_flags32a, &ctx->d_flags32b, &ctx->d_urank, &ctx->d_frank, &ctx->d_umi_of_urank, &ctx->d_recs, &ctx->d_ntiles,
+                      &ctx->d_evoff, &ctx->d_ek0, &ctx->d_ek1, &ctx->d_ev0, &ctx->d_ev1, &ctx->d_tile_off, &ctx->d_unit_cnt,
+                      &ctx->d_unit_off, &ctx->d_small, &ctx->d_grec, &ctx->d_ev_flags, &ctx->d_unit_eb, &ctx->d_unit_ee, &ctx->d_unit_tile,
+                      &ctx->d_unit_nfrag, &ctx->d_codes, &ctx->d_frag_first, &ctx->d_umi_urank, &ctx->d_loc, &ctx->d_cnt, &ctx->d_limb, &ctx->d_pi, &ctx->d_max, &ctx->d_second,
+                      &ctx->d_alt, &ctx->d_altpi, &ctx->d_secondpi, &ctx->d_fl1, &ctx->d_fl2, &ctx->d_bial, &ctx->d_fp, &ctx->d_for,
+                      &ctx->d_dkey, &ctx->d_drep_read, &ctx->d_drep_qpos, &ctx->d_dlen, &ctx->d_dcnt, &ctx->d_dlimb, &ctx->d_diskey,
+                      &ctx->d_lk0, &ctx->d_lk1, &ctx->d_lv0, &ctx->d_lv1, &ctx->d_s_key, &ctx->d_s_cnt, &ctx->d_s_limb, &ctx->d_s_iskey,
+                      &ctx->d_s_pi, &ctx->d_s_rep_read, &ctx->d_s_rep_qpos, &ctx->d_s_len, &ctx->d_dyn_first, &ctx->d_tasks,
+                      &ctx->d_list_idx, &ctx->d_list_count, &ctx->d_list_off, &ctx->d_list_umi, &ctx->d_list_first,
+                      &ctx->d_hp_bases, &ctx->d_hp_meta, &ctx->d_hp_flags, &ctx->d_pipe_need, &ctx->d_umi_table};
+}
 
 #define CK(call)                                                                                         \
     do {                                                                                                 \
@@ -241,6 +262,13 @@ extern "C" int smc_ctx_create(int device, const smc_params* params, smc_ctx** ou
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    for (DevBuf* b : all_bufs(ctx)) b->st = ctx->st;
+    {   // keep freed scratch in the pool for the next batch / context of this process
+        cudaMemPool_t pool;
+        unsigned long long keep = ~0ull;
+        if ((e = cudaDeviceGetDefaultMemPool(&pool, device)) != cudaSuccess) return fail("cudaDeviceGetDefaultMemPool", e);
+        if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return fail("cudaMemPoolSetAttribute", e);
+    }
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_scal, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -279,21 +307,8 @@ extern "C" void smc_ctx_destroy(smc_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->st_copy) cudaStreamSynchronize(ctx->st_copy);
     cudaStreamSynchronize(ctx->st);
-    DevBuf* bufs[] = {&ctx->d_ref_id, &ctx->d_pos, &ctx->d_flag, &ctx->d_mapq, &ctx->d_nm, &ctx->d_lseq, &ctx->d_seq_off, &ctx->d_qual_off,
-                      &ctx->d_cig_off, &ctx->d_ncig, &ctx->d_umi, &ctx->d_frag, &ctx->d_seq, &ctx->d_qual, &ctx->d_cigar, &ctx->d_loci_ref,
-                      &ctx->d_loci_pos, &ctx->d_loci_base, &ctx->d_loci_key, &ctx->d_keep_idx, &ctx->d_keep_off, &ctx->d_keep_umi,
-                      &ctx->d_bqtab, &ctx->d_pcrtab, &ctx->d_k0, &ctx->d_k1, &ctx->d_v0, &ctx->d_v1, &ctx->d_hist, &ctx->d_scan,
-                      &ctx->d_flags32a, &ctx->d_flags32b, &ctx->d_urank, &ctx->d_frank, &ctx->d_umi_of_urank, &ctx->d_recs, &ctx->d_ntiles,
-                      &ctx->d_evoff, &ctx->d_ek0, &ctx->d_ek1, &ctx->d_ev0, &ctx->d_ev1, &ctx->d_tile_off, &ctx->d_unit_cnt,
-                      &ctx->d_unit_off, &ctx->d_small, &ctx->d_grec, &ctx->d_ev_flags, &ctx->d_unit_eb, &ctx->d_unit_ee, &ctx->d_unit_tile,
-                      &ctx->d_unit_nfrag, &ctx->d_codes, &ctx->d_frag_first, &ctx->d_umi_urank, &ctx->d_loc, &ctx->d_cnt, &ctx->d_limb, &ctx->d_pi, &ctx->d_max, &ctx->d_second,
-                      &ctx->d_alt, &ctx->d_altpi, &ctx->d_secondpi, &ctx->d_fl1, &ctx->d_fl2, &ctx->d_bial, &ctx->d_fp, &ctx->d_for,
-                      &ctx->d_dkey, &ctx->d_drep_read, &ctx->d_drep_qpos, &ctx->d_dlen, &ctx->d_dcnt, &ctx->d_dlimb, &ctx->d_diskey,
-                      &ctx->d_lk0, &ctx->d_lk1, &ctx->d_lv0, &ctx->d_lv1, &ctx->d_s_key, &ctx->d_s_cnt, &ctx->d_s_limb, &ctx->d_s_iskey,
-                      &ctx->d_s_pi, &ctx->d_s_rep_read, &ctx->d_s_rep_qpos, &ctx->d_s_len, &ctx->d_dyn_first, &ctx->d_tasks,
-                      &ctx->d_list_idx, &ctx->d_list_count, &ctx->d_list_off, &ctx->d_list_umi, &ctx->d_list_first,
-                      &ctx->d_hp_bases, &ctx->d_hp_meta, &ctx->d_hp_flags, &ctx->d_pipe_need, &ctx->d_umi_table};
-    for (DevBuf* b : bufs) b->release();
+    for (DevBuf* b : all_bufs(ctx)) b->release();
+    cudaStreamSynchronize(ctx->st);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_chunk) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_scal) cudaEventDestroy(ctx->ev_scal);
@@ -362,14 +377,13 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
     if (ctx->has_keep) {
         UP(ctx->d_keep_off, K->off, K->n_loci + 1, int64_t);
         UP(ctx->d_keep_umi, K->umi, K->off[K->n_loci], uint64_t);
-        DevBuf tmp = ctx->d_k0;  // reuse: locus list staging
+        // d_k0 doubles as the staging buffer of the masked-locus list
         CK(ctx->d_k0.ensure((size_t)K->n_loci * 8));
         CK(cudaMemcpyAsync(ctx->d_k0.p, K->locus, (size_t)K->n_loci * 8, cudaMemcpyHostToDevice, ctx->st));
         bytes += K->n_loci * 8;
         CK(ctx->d_keep_idx.ensure((size_t)(nl ? nl : 1) * 4));
         LAUNCH(k_fill_i32, nblk(nl, 256), 256, 0, ctx->d_keep_idx.as<int32_t>(), nl, -1);
         LAUNCH(k_scatter_idx, nblk(K->n_loci, 256), 256, 0, ctx->d_k0.as<int64_t>(), K->n_loci, ctx->d_keep_idx.as<int32_t>());
-        (void)tmp;
         ctx->n_keep_loci = K->n_loci;
     }
 #undef UP
