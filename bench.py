@@ -58,7 +58,14 @@ def make_batch(args, rank, world):
             with open(cache, "rb") as fh:
                 return pickle.load(fh)
     ivs = panel_intervals_from_bed(PANEL_BED, limit=args.intervals * world, seed=args.seed)
-    mine = ivs[rank * args.intervals:(rank + 1) * args.intervals]
+    if world > 1:
+        # the product's own multi-GPU plan (shard.assign_intervals): BED intervals to ranks, balanced by estimated pileup
+        # events (uniform depth here, so ~ interval length + the read-length margin on both sides), not by interval count
+        from smcounter_b200.shard import assign_intervals
+        shard, _ = assign_intervals([float(e - s + 150) for (_, s, e) in ivs], world)
+        mine = [iv for iv, g in zip(ivs, shard) if g == rank]
+    else:
+        mine = ivs
     spec = SynthSpec(umis_per_locus=UMIS_PER_LOCUS, rpb=RPB, snv_every=1000, snv_vaf=0.01, indel_every=12000, indel_vaf=0.01)
     soa, refs, truth = make_panel_mp(mine, spec, seed=args.seed + 17 * rank)
     loci, bed_order = build_loci(mine, soa.chroms, refs)
@@ -282,6 +289,22 @@ def main():
     from smcounter_b200.caller import GpuCaller, LocusResults
 
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa = None
+    if world > 1 and all_cpus is not None:
+        # one process per GPU: run on the cores next to this GPU so that the pinned host buffers (first touch) live on its
+        # NUMA node and the uploads of the 8 ranks do not all cross the socket interconnect
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(local_rank)
+            words = nv.nvmlDeviceGetCpuAffinity(h, (max(all_cpus) + 64) // 64)
+            local = {64 * w + b for w, x in enumerate(words) for b in range(64) if (int(x) >> b) & 1} & set(all_cpus)
+            if local:
+                os.sched_setaffinity(0, local)
+                numa = len(local)
+        except Exception:
+            numa = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     mine, soa, refs, loci, bed_order = make_batch(args, rank, world)
@@ -386,7 +409,8 @@ def main():
                            "pileup_events_per_step": int(events_total), "tile_events_per_step_rank0": int(tms["n_tile_events"]),
                            "params": "mtDepth 3000 rpb 4.0 mtDrop 0 minBQ 20 minMQ 30",
                            "l2": "inputs larger than L2 (%.0f MB resident per GPU), no flush needed" % (soa.nbytes() / 1e6),
-                           "parallelism": "panel sharded by BED interval, no collective"},
+                           "parallelism": "panel sharded by BED interval (balanced by estimated events), no collective",
+                           "host_affinity": ("GPU-local cores (%d) while pinning and uploading" % numa) if numa else "unbound"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_tm["bytes_h2d"]),
                         "d2h_bytes_per_step": int(e2e_tm["bytes_d2h"]), "ms_per_step": 1000.0 * e2e_s_max / args.steps,
                         "ms_h2d": e2e_tm["ms_h2d"], "ms_device": e2e_tm["ms_total_device"], "ms_d2h": e2e_tm["ms_d2h"],
@@ -404,6 +428,8 @@ def main():
                 "clocks": sampler.summary(), "n_dyn_alleles_rank0": int(n_dyn), "n_fisher_rank0": int(tms["n_fisher"])}
     caller.close()
 
+    if all_cpus is not None and numa:
+        os.sched_setaffinity(0, all_cpus)          # the host-side legs below may use every core again
     if rank == 0 and args.pipeline_intervals > 0:
         try:
             line["pipeline"] = pipeline_leg(args, mine, soa, refs, local_rank)
