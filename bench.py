@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-loci", type=int, default=0, help="loci in the CPU-baseline sample (0 = 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--whole-reads", action="store_true", help="upload whole reads instead of the target windows (store_lo/store_len)")
     ap.add_argument("--pipeline-intervals", type=int, default=12,
                     help="intervals of the rank-0 batch run once through the whole CLI path (BAM decode -> files); 0 = skip")
     return ap.parse_args()
@@ -53,7 +54,7 @@ def make_batch(args, rank, world):
     from smcounter_b200.targets import build_loci
     cache = os.environ.get("SMC_BENCH_CACHE")           # tuning sessions: reuse the generated batch between runs
     if cache:
-        cache = "%s.%d_%d_%d_%d" % (cache, args.intervals, args.seed, rank, world)
+        cache = "%s.%d_%d_%d_%d_%d" % (cache, args.intervals, args.seed, rank, world, int(args.whole_reads))
         if os.path.exists(cache):
             with open(cache, "rb") as fh:
                 return pickle.load(fh)
@@ -68,11 +69,15 @@ def make_batch(args, rank, world):
         mine = ivs
     spec = SynthSpec(umis_per_locus=UMIS_PER_LOCUS, rpb=RPB, snv_every=1000, snv_vaf=0.01, indel_every=12000, indel_vaf=0.01)
     soa, refs, truth = make_panel_mp(mine, spec, seed=args.seed + 17 * rank)
+    full = soa                                          # whole reads: the CPU legs (oracle, BAM writer) need them
+    if not args.whole_reads:
+        # what the BAM decoder hands over: only the bases a pileup over the targets can see (store_lo / store_len), packed
+        soa = soa.trim_to_targets(mine)
     loci, bed_order = build_loci(mine, soa.chroms, refs)
     if cache:
         with open(cache, "wb") as fh:
-            pickle.dump((mine, soa, refs, loci, bed_order), fh, protocol=4)
-    return mine, soa, refs, loci, bed_order
+            pickle.dump((mine, soa, refs, loci, bed_order, full), fh, protocol=4)
+    return mine, soa, refs, loci, bed_order, full
 
 
 def vc_params():
@@ -257,7 +262,7 @@ def main():
         if rank != 0:
             return 0
         args.intervals = min(args.intervals, 16)     # the sample only needs the reads around its loci
-        mine, soa, refs, loci, bed_order = make_batch(args, 0, 1)
+        mine, _, refs, loci, bed_order, soa = make_batch(args, 0, 1)
         n_sample = args.cpu_loci or 48 * cores
         jobs, nrec = cpu_sample_setup(soa, refs, loci, n_sample)
         import multiprocessing as mp
@@ -307,7 +312,7 @@ def main():
             numa = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    mine, soa, refs, loci, bed_order = make_batch(args, rank, world)
+    mine, soa, refs, loci, bed_order, soa_full = make_batch(args, rank, world)
 
     # pinned host copies of every buffer that crosses the ABI
     def pin(a):
@@ -316,6 +321,9 @@ def main():
     for f in ("ref_id", "pos", "flag", "mapq", "nm", "l_seq", "seq_off", "qual_off", "cigar_off", "n_cigar", "umi", "frag_id", "seq",
               "qual", "cigar"):
         setattr(soa, f, pin(getattr(soa, f)))
+    for f in ("store_lo", "store_len"):
+        if getattr(soa, f) is not None:
+            setattr(soa, f, pin(getattr(soa, f)))
     for f in ("ref_id", "pos0", "ref_base"):
         setattr(loci, f, pin(getattr(loci, f)))
 
@@ -409,6 +417,8 @@ def main():
                            "pileup_events_per_step": int(events_total), "tile_events_per_step_rank0": int(tms["n_tile_events"]),
                            "params": "mtDepth 3000 rpb 4.0 mtDrop 0 minBQ 20 minMQ 30",
                            "l2": "inputs larger than L2 (%.0f MB resident per GPU), no flush needed" % (soa.nbytes() / 1e6),
+                           "reads": "whole reads" if soa.store_lo is None else "bases / qualities trimmed to each read's target window (store_lo / store_len), "
+                                    "%.0f of %d bases per read stored" % (float(soa.store_len.mean()), int(soa.l_seq.max())),
                            "parallelism": "panel sharded by BED interval (balanced by estimated events), no collective",
                            "host_affinity": ("GPU-local cores (%d) while pinning and uploading" % numa) if numa else "unbound"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_tm["bytes_h2d"]),
@@ -432,13 +442,13 @@ def main():
         os.sched_setaffinity(0, all_cpus)          # the host-side legs below may use every core again
     if rank == 0 and args.pipeline_intervals > 0:
         try:
-            line["pipeline"] = pipeline_leg(args, mine, soa, refs, local_rank)
+            line["pipeline"] = pipeline_leg(args, mine, soa_full, refs, local_rank)
         except Exception as e:          # the extra leg must never cost the bench line
             line["pipeline"] = {"error": repr(e)}
 
     if rank == 0 and not args.no_cpu_baseline:
         n_sample = args.cpu_loci or 160 * cores          # ~10-15 s of host work
-        jobs, nrec = cpu_sample_setup(soa, refs, loci, n_sample)
+        jobs, nrec = cpu_sample_setup(soa_full, refs, loci, n_sample)
         v, dt, ev = cpu_run(jobs, cores)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "%d consecutive loci of the rank-0 batch (%d reads, %d pileup events), oracle/smcounter_oracle.py "

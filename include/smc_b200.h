@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SMC_ABI_VERSION 1
+#define SMC_ABI_VERSION 2
 
 /* error codes */
 #define SMC_OK            0
@@ -78,6 +78,14 @@ typedef struct smc_reads_soa {
     int64_t         qual_bytes; /* < 4 GiB per batch */
     const uint32_t *cigar;      /* BAM cigar words: len<<4 | op (M0 I1 D2 N3 S4 H5 P6 =7 X8) */
     int64_t         n_cigar_words; /* < 2^32 per batch */
+    /* Optional stored window (both NULL = every read is stored whole).  A pileup over the target loci never looks at the
+     * bases of a read that hang off the target intervals, so a decoder may store only query bases
+     * [store_lo, store_lo + store_len) of a read in seq[] / qual[]: (store_len+1)/2 bytes and store_len bytes.  store_lo must
+     * be even; reads that are not one plain aligned run (indels, hard clips, several M runs) must be stored whole; every
+     * target base of the read must be inside the window (all checked on the device: SMC_E_ARG).  l_seq, nm, the CIGAR
+     * and all other scalars keep describing the whole read.  On amplicon panels this halves the bytes that cross PCIe. */
+    const int32_t  *store_lo;
+    const int32_t  *store_len;
 } smc_reads_soa;
 
 /* Target loci: unique, sorted by (ref_id, pos0).  At most 4 194 302 per batch. */

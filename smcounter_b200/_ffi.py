@@ -34,7 +34,7 @@ class smc_reads_soa(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("ref_id", _vp), ("pos", _vp), ("flag", _vp), ("mapq", _vp), ("nm", _vp),
                 ("l_seq", _vp), ("seq_off", _vp), ("qual_off", _vp), ("cigar_off", _vp), ("n_cigar", _vp), ("umi", _vp),
                 ("frag_id", _vp), ("seq", _vp), ("seq_bytes", C.c_int64), ("qual", _vp), ("qual_bytes", C.c_int64),
-                ("cigar", _vp), ("n_cigar_words", C.c_int64)]
+                ("cigar", _vp), ("n_cigar_words", C.c_int64), ("store_lo", _vp), ("store_len", _vp)]
 
 
 class smc_loci(C.Structure):

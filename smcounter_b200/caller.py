@@ -160,6 +160,7 @@ class GpuCaller:
         s.umi, s.frag_id = p(r.umi), p(r.frag_id)
         s.seq, s.seq_bytes, s.qual, s.qual_bytes = p(r.seq), r.seq.nbytes, p(r.qual), r.qual.nbytes
         s.cigar, s.n_cigar_words = p(r.cigar), r.cigar.shape[0]
+        s.store_lo, s.store_len = p(getattr(r, "store_lo", None)), p(getattr(r, "store_len", None))
         return s
 
     @staticmethod

@@ -62,7 +62,8 @@ struct smc_ctx {
     int64_t n_reads = 0, n_loci = 0, n_keep_loci = 0, n_keep_umi = 0;
     int64_t seq_bytes = 0, qual_bytes = 0, n_cigar_words = 0;
     DevBuf d_ref_id, d_pos, d_flag, d_mapq, d_nm, d_lseq, d_seq_off, d_qual_off, d_cig_off, d_ncig, d_umi, d_frag, d_seq, d_qual,
-        d_cigar;
+        d_cigar, d_store_lo, d_store_len;
+    bool has_store = false;                     // reads carry a stored window (smc_reads_soa::store_lo / store_len)
     DevBuf d_loci_ref, d_loci_pos, d_loci_base, d_loci_key;
     DevBuf d_keep_idx, d_keep_off, d_keep_umi;
     bool has_keep = false, uploaded = false, ran = false;
@@ -94,7 +95,7 @@ struct smc_ctx {
 };
 
 static std::vector<DevBuf*> all_bufs(smc_ctx* ctx) {
-    return {&ctx->d_ref_id, &ctx->d_pos, &ctx->d_flag, &ctx->d_mapq, &ctx->d_nm, &ctx->d_lseq, &ctx->d_seq_off, &ctx->d_qual_off,
+    return {&ctx->d_store_lo, &ctx->d_store_len, &ctx->d_ref_id, &ctx->d_pos, &ctx->d_flag, &ctx->d_mapq, &ctx->d_nm, &ctx->d_lseq, &ctx->d_seq_off, &ctx->d_qual_off,
                       &ctx->d_cig_off, &ctx->d_ncig, &ctx->d_umi, &ctx->d_frag, &ctx->d_seq, &ctx->d_qual, &ctx->d_cigar, &ctx->d_loci_ref,
                       &ctx->d_loci_pos, &ctx->d_loci_base, &ctx->d_loci_key, &ctx->d_keep_idx, &ctx->d_keep_off, &ctx->d_keep_umi,
                       &ctx->d_bqtab, &ctx->d_pcrtab, &ctx->d_k0, &ctx->d_k1, &ctx->d_v0, &ctx->d_v1, &ctx->d_hist, &ctx->d_scan,
@@ -354,6 +355,9 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
     UP(ctx->d_ref_id, R->ref_id, n, int32_t); UP(ctx->d_pos, R->pos, n, int32_t); UP(ctx->d_flag, R->flag, n, uint16_t);
     UP(ctx->d_mapq, R->mapq, n, uint8_t); UP(ctx->d_nm, R->nm, n, int32_t); UP(ctx->d_lseq, R->l_seq, n, int32_t);
     UP(ctx->d_ncig, R->n_cigar, n, uint16_t); UP(ctx->d_umi, R->umi, n, uint64_t); UP(ctx->d_frag, R->frag_id, n, uint32_t);
+    if ((R->store_lo == nullptr) != (R->store_len == nullptr)) { ctx->err = "smc_upload: store_lo and store_len must be given together"; return SMC_E_ARG; }
+    ctx->has_store = R->store_lo != nullptr;
+    if (ctx->has_store) { UP(ctx->d_store_lo, R->store_lo, n, int32_t); UP(ctx->d_store_len, R->store_len, n, int32_t); }
     // offsets: uploaded, or -- NULL = payload packed in read order -- computed here from l_seq / n_cigar (saves 24 B per read of PCIe)
     ctx->packed_seq = !R->seq_off; ctx->packed_qual = !R->qual_off; ctx->packed_cigar = !R->cigar_off;
     {
@@ -365,7 +369,8 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
             CK(dev_off[kind]->ensure((size_t)(n ? n : 1) * 8));
             CK(ctx->d_v0.ensure((size_t)(n ? n : 1) * 4));
             CK(ctx->d_scan.ensure((size_t)scan_scratch_words(n + 1) * 4 + 1024));
-            LAUNCH(k_pack_len, nblk(n, 256), 256, 0, ctx->d_lseq.as<int32_t>(), ctx->d_ncig.as<uint16_t>(), n, kind, ctx->d_v0.as<uint32_t>());
+            LAUNCH(k_pack_len, nblk(n, 256), 256, 0, ctx->d_lseq.as<int32_t>(), ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr,
+                   ctx->d_ncig.as<uint16_t>(), n, kind, ctx->d_v0.as<uint32_t>());
             exclusive_scan_u32(ctx->d_v0.as<uint32_t>(), ctx->d_v0.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + 40 + kind, ctx->st);
             LAUNCH(k_widen_u32, nblk(n, 256), 256, 0, ctx->d_v0.as<uint32_t>(), n, dev_off[kind]->as<int64_t>());
         }
@@ -488,6 +493,7 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         P.mapq = ctx->d_mapq.as<uint8_t>(); P.nm = ctx->d_nm.as<int32_t>(); P.l_seq = ctx->d_lseq.as<int32_t>();
         P.seq_off = ctx->d_seq_off.as<int64_t>(); P.qual_off = ctx->d_qual_off.as<int64_t>(); P.cigar_off = ctx->d_cig_off.as<int64_t>();
         P.n_cigar = ctx->d_ncig.as<uint16_t>(); P.cigar = ctx->d_cigar.as<uint32_t>();
+        if (ctx->has_store) { P.store_lo = ctx->d_store_lo.as<int32_t>(); P.store_len = ctx->d_store_len.as<int32_t>(); }
         P.loci_key = ctx->d_loci_key.as<uint64_t>(); P.n_loci = nl;
         P.minMQ = ctx->prm.minMQ; P.primerDist = ctx->prm.primerDist; P.mismatchThr = ctx->prm.mismatchThr;
         P.recs = ctx->d_recs.as<ReadRec>(); P.grec = ctx->d_grec.as<GRec>(); P.ntiles = ctx->d_ntiles.as<uint32_t>(); P.gflags = small + 5;
@@ -505,10 +511,15 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         CK(cudaMemcpyAsync(tot, small + 40, 12, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         if (h[1] & GF_BAD_READ) { ctx->err = "a read has l_seq or clip length > 65535 (unsupported)"; return SMC_E_LIMIT; }
+        if (h[1] & GF_BAD_STORE) {
+            ctx->err = "stored window: store_lo must be even and >= 0, store_lo + store_len <= l_seq, reads with indels / clips inside must be "
+                       "stored whole, and every target base of a read must lie inside its window";
+            return SMC_E_ARG;
+        }
         if (frag_or >> frag_bits_used) { ctx->err = "frag_id must be a dense id (< n_reads), numbered by first appearance"; return SMC_E_ARG; }
         if ((ctx->packed_seq && (int64_t)tot[0] != ctx->seq_bytes) || (ctx->packed_qual && (int64_t)tot[1] != ctx->qual_bytes) ||
             (ctx->packed_cigar && (int64_t)tot[2] != ctx->n_cigar_words)) {
-            ctx->err = "packed payload (NULL offsets): seq_bytes / qual_bytes / n_cigar_words do not match the sums of (l_seq+1)/2, l_seq, n_cigar";
+            ctx->err = "packed payload (NULL offsets): seq_bytes / qual_bytes / n_cigar_words do not match the sums of (len+1)/2, len, n_cigar (len = store_len or l_seq)";
             return SMC_E_ARG;
         }
         NE = h[0];

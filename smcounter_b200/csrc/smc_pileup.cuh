@@ -44,6 +44,7 @@ struct PrepArgs {
     const uint32_t* frank;
     const int32_t* ref_id; const int32_t* pos; const uint16_t* flag; const uint8_t* mapq; const int32_t* nm;
     const int32_t* l_seq; const int64_t* seq_off; const int64_t* qual_off; const int64_t* cigar_off;
+    const int32_t* store_lo; const int32_t* store_len;     // optional stored window of the read's bases / qualities (nullptr: whole read)
     const uint16_t* n_cigar; const uint32_t* cigar;
     const uint64_t* loci_key; int64_t n_loci;
     int minMQ; int primerDist; double mismatchThr;
@@ -54,6 +55,7 @@ struct PrepArgs {
 #define GF_DYN_FULL   1u
 #define GF_BAD_READ   2u     // l_seq / clip length beyond the 16-bit record fields
 #define GF_CODE_FULL  4u     // a unit ran out of fragment-code storage (host retries with the worst-case layout)
+#define GF_BAD_STORE  8u     // stored window (store_lo / store_len) malformed or not covering every target base of the read
 
 __global__ void __launch_bounds__(256) k_read_prep(PrepArgs A) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -97,7 +99,16 @@ __global__ void __launch_bounds__(256) k_read_prep(PrepArgs A) {
     rec.start = start; rec.lo = (int32_t)lo; rec.hi = (int32_t)hi;
     const bool rev = fl & 0x10u, r2 = fl & 0x80u;
     rec.meta = (ok ? RM_OK : 0u) | (rev ? RM_REVERSE : 0u) | (r2 ? RM_READ2 : 0u) | (simple ? RM_SIMPLE : 0u) | (ncig << 8);
-    rec.seq_off = (uint32_t)A.seq_off[r]; rec.qual_off = (uint32_t)A.qual_off[r]; rec.cigar_off = (uint32_t)co;
+    // Stored window: bases [slo, slo + slen) of the read are in seq[] / qual[] (slo even).  The record keeps the offset of the
+    // read's (virtual) base 0, so that every later access is offset + query position in wrapping 32-bit arithmetic.
+    const int32_t slo = A.store_lo ? A.store_lo[r] : 0, slen = A.store_len ? A.store_len[r] : lseq;
+    if (slo < 0 || (slo & 1) || slen < 0 || slo + slen > lseq || (!simple && (slo != 0 || slen != lseq))) { atomicOr(A.gflags, GF_BAD_STORE); lo = hi = 0; }
+    else if (simple && hi > lo) {          // every target base of the read must be stored: query position = p + leftSP - start
+        const int32_t q0 = (int32_t)(uint32_t)A.loci_key[lo] + leftSP - start, q1 = (int32_t)(uint32_t)A.loci_key[hi - 1] + leftSP - start;
+        if (q0 < slo || q1 >= slo + slen) { atomicOr(A.gflags, GF_BAD_STORE); lo = hi = 0; }
+    }
+    rec.seq_off = (uint32_t)A.seq_off[r] - (uint32_t)(slo >> 1); rec.qual_off = (uint32_t)A.qual_off[r] - (uint32_t)slo;
+    rec.cigar_off = (uint32_t)co;
     rec.urank = A.urank[s]; rec.frank = A.frank[s];
     rec.read_idx = r; rec.gspan = simple ? (uint32_t)(hi - lo) : 0u;
     rec.sp_aln = (uint32_t)leftSP | ((uint32_t)alnlen << 16);
@@ -128,9 +139,9 @@ __global__ void __launch_bounds__(256) k_read_prep(PrepArgs A) {
     A.ntiles[s] = hi > lo ? (uint32_t)(((hi - 1) >> 5) - (lo >> 5) + 1) : 0u;
     if (A.pipe_need) {                                         // last chunk that carries a byte of this read
         uint32_t c = 0;
-        if (lseq > 0) {
-            const uint32_t cs = (uint32_t)((rec.seq_off + ((uint32_t)lseq + 1u) / 2u - 1u) / A.pipe_seq_chunk);
-            const uint32_t cq = (uint32_t)((rec.qual_off + (uint32_t)lseq - 1u) / A.pipe_qual_chunk);
+        if (slen > 0) {
+            const uint32_t cs = (uint32_t)(((uint32_t)A.seq_off[r] + ((uint32_t)slen + 1u) / 2u - 1u) / A.pipe_seq_chunk);
+            const uint32_t cq = (uint32_t)(((uint32_t)A.qual_off[r] + (uint32_t)slen - 1u) / A.pipe_qual_chunk);
             c = min(max(cs, cq), A.pipe_n - 1u);
         }
         A.pipe_need[s] = (uint8_t)c;
@@ -214,10 +225,11 @@ k_pipe_unit_need(const uint32_t* __restrict__ unit_eb, const uint32_t* __restric
 }
 // Packed payloads (smc_reads_soa offsets passed as NULL): per-read byte / word counts, scanned into the offsets on the device
 __global__ void __launch_bounds__(256)
-k_pack_len(const int32_t* __restrict__ l_seq, const uint16_t* __restrict__ n_cigar, int64_t n, int kind, uint32_t* __restrict__ out) {
+k_pack_len(const int32_t* __restrict__ l_seq, const int32_t* __restrict__ store_len, const uint16_t* __restrict__ n_cigar, int64_t n, int kind,
+           uint32_t* __restrict__ out) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
-    const uint32_t l = kind == 2 ? 0u : (uint32_t)max(l_seq[r], 0);
+    const uint32_t l = kind == 2 ? 0u : (uint32_t)max(store_len ? store_len[r] : l_seq[r], 0);
     out[r] = kind == 0 ? (l + 1u) / 2u : kind == 1 ? l : (uint32_t)n_cigar[r];
 }
 __global__ void __launch_bounds__(256) k_widen_u32(const uint32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
@@ -346,9 +358,9 @@ struct KAArgs {
 
 // Tallies of one pileup event whose base is not A/C/G/T (N / IUPAC, smCounter.py:423-457 with that key): rare, so it goes
 // straight to the dynamic-allele row with atomics.  Returns the row | (nibble == N) << 31.
-__device__ __noinline__ uint32_t dyn_base_event(DynTab T, const uint8_t* seq_read, uint32_t locus, uint32_t read_idx, int qpos,
+__device__ __noinline__ uint32_t dyn_base_event(DynTab T, const uint8_t* seqp, uint32_t seq_off, uint32_t locus, uint32_t read_idx, int qpos,
                                                 uint32_t flags /* 1 fwd 2 lowq 4 inc 8 r2 16 le20 32 ple */) {
-    const uint32_t sb = __ldg(seq_read + (qpos >> 1));
+    const uint32_t sb = __ldg(seqp + (uint32_t)(seq_off + (uint32_t)(qpos >> 1)));     // wrapping: seq_off is the read's virtual base 0
     const uint32_t nib = (qpos & 1) ? (sb & 15u) : (sb >> 4);
     const uint32_t e = dyn_lookup(T, dyn_make_key(locus, SMC_K_BASE, nib, 0ull), read_idx, qpos, 0);
     int32_t* row = T.dcnt + (size_t)e * SMC_NCNT;
@@ -420,9 +432,9 @@ __device__ __noinline__ uint2 slow_event(DynTab T, const uint32_t* __restrict__ 
         const bool inc = (meta & RM_OK);                                       // bq = minBQ passes the quality gate
         return make_uint2(((uint32_t)minBQ & 255u) | EC_COVERED | (inc ? EC_INC : 0u), (uint32_t)SMC_A_DEL);
     }
-    const uint32_t sb = __ldg(seqp + ((size_t)seq_off + (size_t)(qpos >> 1)));
+    const uint32_t sb = __ldg(seqp + (uint32_t)(seq_off + (uint32_t)(qpos >> 1)));
     const uint32_t nib = (qpos & 1) ? (sb & 15u) : (sb >> 4);
-    const uint32_t bq = __ldg(qualp + ((size_t)qual_off + (size_t)qpos));
+    const uint32_t bq = __ldg(qualp + (uint32_t)(qual_off + (uint32_t)qpos));
     const bool lowq = (int)bq < minBQ;
     const bool inc = !lowq && (meta & RM_OK);                                  // :378,400,431
     uint32_t code = bq | (nib << EC_NIB_SH) | EC_COVERED | (inc ? EC_INC : 0u);
@@ -444,7 +456,7 @@ __device__ __noinline__ uint2 slow_event(DynTab T, const uint32_t* __restrict__ 
             unsigned long long nibs = 0;
             for (int t = 0; t < len; ++t) {
                 const int qq = qpos + 1 + t;
-                const uint32_t b2 = __ldg(seqp + ((size_t)seq_off + (size_t)(qq >> 1)));
+                const uint32_t b2 = __ldg(seqp + (uint32_t)(seq_off + (uint32_t)(qq >> 1)));
                 nibs |= (unsigned long long)((qq & 1) ? (b2 & 15u) : (b2 >> 4)) << (28 - 4 * t);
             }
             payload = ((unsigned long long)len << 32) | nibs;
@@ -452,7 +464,7 @@ __device__ __noinline__ uint2 slow_event(DynTab T, const uint32_t* __restrict__ 
             uint32_t hsh = 2166136261u ^ (uint32_t)len;
             for (int t = 0; t < len; ++t) {
                 const int qq = qpos + 1 + t;
-                const uint32_t b2 = __ldg(seqp + ((size_t)seq_off + (size_t)(qq >> 1)));
+                const uint32_t b2 = __ldg(seqp + (uint32_t)(seq_off + (uint32_t)(qq >> 1)));
                 hsh = (hsh ^ ((qq & 1) ? (b2 & 15u) : (b2 >> 4))) * 16777619u;
             }
             payload = (15ull << 32) | hsh;
@@ -701,7 +713,7 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
                     const bool ple = (uint32_t)(p - (int32_t)rw[7]) <= ((meta & GM_PLE_INF) ? WIN_INF : pspan);
                     const uint32_t dfl = ((meta & RM_REVERSE) ? 0u : 1u) | ((int)(cd & 255u) < minBQ ? 2u : 0u) | ((cd & EC_INC) ? 4u : 0u) |
                                          ((meta & RM_READ2) ? 8u : 0u) | (le20 ? 16u : 0u) | (ple ? 32u : 0u);
-                    const uint32_t e = dyn_base_event(A.T, seqp + rw[4], (uint32_t)Li, __ldg(&A.recs[srank_s[j]].read_idx), p + (int32_t)rw[2], dfl);
+                    const uint32_t e = dyn_base_event(A.T, seqp, rw[4], (uint32_t)Li, __ldg(&A.recs[srank_s[j]].read_idx), p + (int32_t)rw[2], dfl);
                     mid = NF + (e & 0x7fffffffu); isN = e >> 31;
                 }
             } else {                                                                 // rare: per-event CIGAR walk, out of line
@@ -720,7 +732,7 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
                         } else {
                             const uint32_t dfl = ((meta & RM_REVERSE) ? 0u : 1u) | (lowq ? 2u : 0u) | ((cd & EC_INC) ? 4u : 0u) |
                                                  ((meta & RM_READ2) ? 8u : 0u) | ((cd & EC_LE20) ? 16u : 0u) | ((cd & EC_PLE) ? 32u : 0u);
-                            const uint32_t e = dyn_base_event(A.T, seqp + __ldg(rw + 4), (uint32_t)Li, __ldg(rw + 10), (int)ev.y, dfl);
+                            const uint32_t e = dyn_base_event(A.T, seqp, __ldg(rw + 4), (uint32_t)Li, __ldg(rw + 10), (int)ev.y, dfl);
                             mid = NF + (e & 0x7fffffffu); isN = e >> 31;
                         }
                     } else if (mid == (uint32_t)SMC_A_DEL) {

@@ -103,6 +103,8 @@ class AlleleNamer:
 
     def _read_bases(self, r, q0, n):
         so = int(self.reads.seq_off[r])
+        if getattr(self.reads, "store_lo", None) is not None:      # stored window: seq holds the bases from store_lo on
+            q0 -= int(self.reads.store_lo[r])
         out = []
         for q in range(q0, q0 + n):
             b = int(self.reads.seq[so + (q >> 1)])

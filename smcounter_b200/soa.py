@@ -42,6 +42,8 @@ class ReadsSoA:
     chroms: list = field(default_factory=list)
     umi_names: dict | None = None   # optional code -> barcode string (host side only)
     packed: bool = False            # payloads stored back to back in read order: the offsets need not cross the ABI (NULL)
+    store_lo: np.ndarray | None = None    # int32, optional stored window (include/smc_b200.h): first stored query base (even) ...
+    store_len: np.ndarray | None = None   # int32  ... and number of stored bases; None = reads stored whole
 
     @property
     def n(self) -> int:
@@ -50,12 +52,16 @@ class ReadsSoA:
     def nbytes(self) -> int:
         return sum(getattr(self, f).nbytes for f in
                    ("ref_id", "pos", "flag", "mapq", "nm", "l_seq", "seq_off", "qual_off", "cigar_off", "n_cigar",
-                    "umi", "frag_id", "seq", "qual", "cigar"))
+                    "umi", "frag_id", "seq", "qual", "cigar")) + (0 if self.store_lo is None else self.store_lo.nbytes + self.store_len.nbytes)
+
+    def stored_len(self) -> np.ndarray:
+        """Stored bases per read (== l_seq unless the SoA was trimmed to its targets)."""
+        return (self.l_seq if self.store_len is None else self.store_len).astype(np.int64)
 
     def select(self, idx: np.ndarray) -> "ReadsSoA":
         """Sub-batch with the reads ``idx`` (ascending), variable-length payloads re-packed."""
         idx = np.asarray(idx, dtype=np.int64)
-        l_seq = self.l_seq[idx].astype(np.int64)
+        l_seq = self.stored_len()[idx]
         sb = (l_seq + 1) // 2
         nc = self.n_cigar[idx].astype(np.int64)
         new_seq_off = np.concatenate(([0], np.cumsum(sb)))[:-1]
@@ -76,12 +82,13 @@ class ReadsSoA:
             # ids stay dense (< n reads, include/smc_b200.h) and keep their relative order = the fragment order inside a barcode
             frag_id=np.unique(self.frag_id[idx], return_inverse=True)[1].astype(np.uint32) if len(idx) else self.frag_id[idx],
             seq=gather(self.seq, self.seq_off[idx], sb), qual=gather(self.qual, self.qual_off[idx], l_seq),
-            cigar=gather(self.cigar, self.cigar_off[idx], nc), chroms=self.chroms, umi_names=self.umi_names, packed=True)
+            cigar=gather(self.cigar, self.cigar_off[idx], nc), chroms=self.chroms, umi_names=self.umi_names, packed=True,
+            store_lo=None if self.store_lo is None else self.store_lo[idx], store_len=None if self.store_len is None else self.store_len[idx])
 
     def repack(self, block: int = 1 << 18) -> "ReadsSoA":
         """Same reads, with bases / qualities / CIGARs stored in read order (what a BAM decode produces).  libsmc_b200
         accepts any layout, but only a read-ordered payload lets smc_call_batch overlap the upload with the kernels."""
-        l_seq = self.l_seq.astype(np.int64)
+        l_seq = self.stored_len()
         sb = (l_seq + 1) // 2
         nc = self.n_cigar.astype(np.int64)
         out = {}
@@ -100,11 +107,74 @@ class ReadsSoA:
         return ReadsSoA(ref_id=self.ref_id, pos=self.pos, flag=self.flag, mapq=self.mapq, nm=self.nm, l_seq=self.l_seq,
                         seq_off=out["seq"][1], qual_off=out["qual"][1], cigar_off=out["cigar"][1], n_cigar=self.n_cigar, umi=self.umi,
                         frag_id=self.frag_id, seq=out["seq"][0], qual=out["qual"][0], cigar=out["cigar"][0], chroms=self.chroms,
-                        umi_names=self.umi_names, packed=True)
+                        umi_names=self.umi_names, packed=True, store_lo=self.store_lo, store_len=self.store_len)
+
+    def trim_to_targets(self, intervals, block: int = 1 << 18) -> "ReadsSoA":
+        """Same reads with only the bases a pileup over ``intervals`` can see kept in seq / qual (store_lo / store_len of
+        include/smc_b200.h): for a read that is one plain aligned run, the query bases from its first to its last target
+        position (start rounded down to an even base); every other read is kept whole.  Payload packed in read order."""
+        if self.store_lo is not None:
+            raise ValueError("already trimmed")
+        n = self.n
+        cidx = {c: i for i, c in enumerate(self.chroms)}
+        l_seq = self.l_seq.astype(np.int64)
+        ops = self.cigar & 0xF
+        first = self.cigar[np.minimum(self.cigar_off, max(len(self.cigar) - 1, 0))] if len(self.cigar) else np.zeros(n, np.uint32)
+        is_ref = np.isin(ops, (0, 7, 8))
+        bad = np.isin(ops, (1, 2, 3, 5, 6))
+        cs_ref = np.concatenate(([0], np.cumsum(is_ref)))
+        cs_bad = np.concatenate(([0], np.cumsum(bad)))
+        a, b = self.cigar_off, self.cigar_off + self.n_cigar.astype(np.int64)
+        simple = ((cs_ref[b] - cs_ref[a]) == 1) & ((cs_bad[b] - cs_bad[a]) == 0)
+        left_sp = np.where((self.n_cigar > 0) & ((first & 0xF) == 4), (first >> 4).astype(np.int64), 0)
+        start = self.pos.astype(np.int64)
+        end = self.ref_end()
+        # first / last target position inside [start, end) per read: over the sorted unique target positions of its contig
+        p_lo = np.full(n, -1, dtype=np.int64)
+        p_hi = np.full(n, -1, dtype=np.int64)
+        for c in set(iv[0] for iv in intervals):
+            if c not in cidx:
+                continue
+            pos = np.unique(np.concatenate([np.arange(s, e, dtype=np.int64) for (cc, s, e) in intervals if cc == c and e > s] or
+                                           [np.zeros(0, np.int64)]))
+            if not len(pos):
+                continue
+            m = np.flatnonzero(self.ref_id == cidx[c])
+            i0 = np.searchsorted(pos, start[m], side="left")
+            i1 = np.searchsorted(pos, end[m], side="left")
+            has = i1 > i0
+            p_lo[m[has]] = pos[i0[has]]
+            p_hi[m[has]] = pos[i1[has] - 1]
+        covered = p_lo >= 0
+        q_lo = np.where(simple & covered, (p_lo - start + left_sp) & ~1, 0)
+        q_hi = np.where(simple & covered, p_hi - start + left_sp + 1, np.where(simple, 0, l_seq))
+        q_lo = np.where(simple, q_lo, 0)
+        store_lo = q_lo.astype(np.int32)
+        store_len = np.maximum(q_hi - q_lo, 0).astype(np.int32)
+        # payloads: seq bytes [store_lo/2, ...), qual bytes [store_lo, ...)
+        sl = store_len.astype(np.int64)
+        out = {}
+        for name, src, offs, lens in (("seq", self.seq, self.seq_off + q_lo // 2, (sl + 1) // 2), ("qual", self.qual, self.qual_off + q_lo, sl),
+                                      ("cigar", self.cigar, self.cigar_off, self.n_cigar.astype(np.int64))):
+            new_off = np.concatenate(([0], np.cumsum(lens)))
+            dst = np.empty(int(new_off[-1]), dtype=src.dtype)
+            for x in range(0, n, block):
+                y = min(n, x + block)
+                ln = lens[x:y]
+                tot = int(ln.sum())
+                if tot:
+                    starts = np.repeat(offs[x:y] - (new_off[x:y] - new_off[x]), ln)
+                    dst[new_off[x]:new_off[y]] = src[starts + np.arange(tot, dtype=np.int64)]
+            out[name] = (dst, new_off[:-1].copy())
+        # an odd stored length leaves the low nibble of the last byte holding the next (unstored) base: harmless, never read
+        return ReadsSoA(ref_id=self.ref_id, pos=self.pos, flag=self.flag, mapq=self.mapq, nm=self.nm, l_seq=self.l_seq,
+                        seq_off=out["seq"][1], qual_off=out["qual"][1], cigar_off=out["cigar"][1], n_cigar=self.n_cigar, umi=self.umi,
+                        frag_id=self.frag_id, seq=out["seq"][0], qual=out["qual"][0], cigar=out["cigar"][0], chroms=self.chroms,
+                        umi_names=self.umi_names, packed=True, store_lo=store_lo, store_len=store_len)
 
     def is_packed(self) -> bool:
         """True when every payload is stored back to back in read order (checked, O(n))."""
-        l = self.l_seq.astype(np.int64)
+        l = self.stored_len()
         for off, lens, tot in ((self.seq_off, (l + 1) // 2, self.seq.shape[0]), (self.qual_off, l, self.qual.shape[0]),
                                (self.cigar_off, self.n_cigar.astype(np.int64), self.cigar.shape[0])):
             ends = np.cumsum(lens)
@@ -249,6 +319,8 @@ def soa_to_records(soa: ReadsSoA, record_type=None):
     ``F<frag_id>:<barcode>:x`` so that (barcode, readid) round-trips."""
     from collections import namedtuple
     R = record_type or namedtuple("Read", "qname chrom pos flag mapq nm cigar seq qual")
+    if soa.store_lo is not None:
+        raise ValueError("soa_to_records needs whole reads (this SoA was trimmed to its targets)")
     out = []
     for i in range(soa.n):
         L = int(soa.l_seq[i])

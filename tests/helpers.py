@@ -166,17 +166,20 @@ def keep_from_oracle(details, bed_order, soa):
     return UmiKeep(mapping) if mapping else None
 
 
-def run_case(intervals, spec: SynthSpec, prm: VcParams, seed: int, verbose=False, mutate=None):
+def run_case(intervals, spec: SynthSpec, prm: VcParams, seed: int, verbose=False, mutate=None, gpu_mutate=None):
+    """``mutate``: applied to the generated reads before both sides see them; ``gpu_mutate``: a different ENCODING of the same
+    reads for the CUDA path only (packed, trimmed to the targets, ...) -- the oracle keeps the plain one."""
     soa, refs, truth = make_panel(intervals, spec, seed=seed)
     if mutate is not None:
         soa = mutate(soa)
     o_rows, details = oracle_run(soa, intervals, refs, prm)
     _, bo = build_loci(intervals, soa.chroms, refs)
     keep = keep_from_oracle(details, bo, soa)
-    g_rows, res, loci, bed_order, tm = gpu_run(soa, intervals, refs, prm, keep)
-    problems, stats = diff_details(res, loci, bed_order, details, soa, refs)
+    gsoa = gpu_mutate(soa) if gpu_mutate is not None else soa
+    g_rows, res, loci, bed_order, tm = gpu_run(gsoa, intervals, refs, prm, keep)
+    problems, stats = diff_details(res, loci, bed_order, details, gsoa, refs)
     problems += diff_rows(g_rows, o_rows)
-    stats.update(n_downsampled=0 if keep is None else len(keep.locus), n_reads=soa.n, n_loci=loci.n, events=tm["n_pileup_events"], n_dyn=tm["n_dyn"], code_mult=tm["code_mult"], dyn_capacity=tm["dyn_capacity"], pipe_chunks=tm["pipe_chunks"], pipe_launches=tm["pipe_launches"], ms_device=tm["ms_total_device"],
+    stats.update(n_downsampled=0 if keep is None else len(keep.locus), n_reads=soa.n, payload_bytes=int(gsoa.seq.nbytes + gsoa.qual.nbytes), n_loci=loci.n, events=tm["n_pileup_events"], n_dyn=tm["n_dyn"], code_mult=tm["code_mult"], dyn_capacity=tm["dyn_capacity"], pipe_chunks=tm["pipe_chunks"], pipe_launches=tm["pipe_launches"], ms_device=tm["ms_total_device"],
                  ms_pileup=tm["ms_pileup"])
     if verbose:
         print(stats)

@@ -330,3 +330,50 @@ def test_fragment_ids_must_be_dense():
             c.call(soa, loci)
     finally:
         c.close()
+
+
+def test_reads_trimmed_to_their_targets():
+    """smc_reads_soa with a stored window per read (store_lo / store_len): only the query bases between a read's first and
+    last target position are in seq / qual.  The oracle sees the whole reads, the CUDA path the trimmed ones; every tally, PI,
+    allele string and row must match -- with soft clips, indels (kept whole), N bases, the chunked upload and the packed offsets."""
+    from helpers import run_case
+    ivs = [("chr1", 1000, 1060), ("chr1", 1200, 1203), ("chr2", 300, 420), ("chr3", 50, 51)]
+    spec = SynthSpec(umis_per_locus=60, rpb=3.0, snv_every=30, snv_vaf=0.1, indel_every=40, indel_vaf=0.1, n_frac=0.005, softclip_frac=0.4)
+    prm = VcParams(mtDepth=60, rpb=3.0)
+    for chunks in ("1", "4"):
+        problems, stats, (soa, *_rest) = _with_env("SMC_PIPE_CHUNKS", chunks, lambda: run_case(
+            ivs, spec, prm, seed=73, gpu_mutate=lambda s: s.trim_to_targets(ivs)))
+        print(stats)
+        assert stats["payload_bytes"] < 0.75 * (soa.seq.nbytes + soa.qual.nbytes)
+        assert not problems, "\n".join(problems)
+
+
+def test_malformed_stored_windows_are_refused():
+    import numpy as np
+    from smcounter_b200.caller import GpuCaller
+    from smcounter_b200.synth import make_panel
+    from smcounter_b200.targets import build_loci
+    ivs = [("chr1", 1000, 1040)]
+    prm = VcParams(mtDepth=20, rpb=3.0)
+    soa, refs, _ = make_panel(ivs, SynthSpec(umis_per_locus=20, rpb=3.0), seed=79)
+    loci, _ = build_loci(ivs, soa.chroms, refs)
+    good = soa.trim_to_targets(ivs)
+    k = int(np.flatnonzero((good.store_len > 8) & (good.store_len < good.l_seq))[0])
+
+    def broken(edit):
+        t = soa.trim_to_targets(ivs)
+        t.packed = False                      # keep the explicit offsets: only the window itself is wrong
+        edit(t)
+        return t
+
+    cases = (broken(lambda t: t.store_lo.__setitem__(k, t.store_lo[k] + 1)),                 # odd start
+             broken(lambda t: t.store_len.__setitem__(k, t.store_len[k] - 4)),               # last target bases not stored
+             broken(lambda t: t.store_len.__setitem__(k, t.l_seq[k] + 2)))                   # window longer than the read
+    c = GpuCaller(prm, 0)
+    try:
+        c.call(good, loci)                                                                    # the unbroken one is fine
+        for t in cases:
+            with pytest.raises(RuntimeError, match="stored window"):
+                c.call(t, loci)
+    finally:
+        c.close()

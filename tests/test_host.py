@@ -282,3 +282,37 @@ def test_repack_puts_payload_in_read_order():
     for f in ("seq_off", "qual_off", "cigar_off", ):
         assert (np.diff(getattr(merged, f)) >= 0).all()
     assert (np.diff(merged.ref_id.astype(np.int64) << 32 | merged.pos) >= 0).all()
+
+
+def test_trim_to_targets_keeps_exactly_the_target_window():
+    """ReadsSoA.trim_to_targets(): stored window = query bases from the first to the last target position of a plain read
+    (even start), whole read otherwise; stored bytes identical to the same window of the untrimmed payload."""
+    import numpy as np
+    from smcounter_b200.synth import SynthSpec, make_panel
+    ivs = [("chr1", 1000, 1100), ("chr2", 300, 380), ("chr1", 5000, 5060)]
+    soa, _, _ = make_panel(ivs, SynthSpec(umis_per_locus=30, rpb=3.0, indel_every=30, indel_vaf=0.1, softclip_frac=0.3), seed=5)
+    t = soa.trim_to_targets(ivs)
+    assert t.packed and t.is_packed() and t.seq.nbytes + t.qual.nbytes < 0.7 * (soa.seq.nbytes + soa.qual.nbytes)
+    ends = soa.ref_end()
+    cidx = {c: i for i, c in enumerate(soa.chroms)}
+    n_whole = 0
+    for r in range(soa.n):
+        lo, ln, L = int(t.store_lo[r]), int(t.store_len[r]), int(soa.l_seq[r])
+        assert lo % 2 == 0 and 0 <= lo and lo + ln <= L
+        assert (t.qual[t.qual_off[r]:t.qual_off[r] + ln] == soa.qual[soa.qual_off[r] + lo:soa.qual_off[r] + lo + ln]).all()
+        a = t.seq[t.seq_off[r]:t.seq_off[r] + (ln + 1) // 2]
+        b = soa.seq[soa.seq_off[r] + lo // 2:soa.seq_off[r] + lo // 2 + (ln + 1) // 2]
+        assert (a[:ln // 2] == b[:ln // 2]).all() and (ln % 2 == 0 or (a[-1] >> 4) == (b[-1] >> 4))
+        cig = soa.cigar[soa.cigar_off[r]:soa.cigar_off[r] + soa.n_cigar[r]]
+        plain = all((int(w) & 15) in (0, 4) for w in cig) and sum((int(w) & 15) == 0 for w in cig) == 1
+        if not plain:
+            assert lo == 0 and ln == L
+            n_whole += 1
+            continue
+        left_sp = int(cig[0]) >> 4 if (int(cig[0]) & 15) == 4 else 0
+        tp = [p for (c, s, e) in ivs if cidx[c] == soa.ref_id[r] for p in range(max(s, int(soa.pos[r])), min(e, int(ends[r])))]
+        if tp:
+            assert lo == ((min(tp) - int(soa.pos[r]) + left_sp) & ~1) and lo + ln == max(tp) - int(soa.pos[r]) + left_sp + 1
+        else:
+            assert ln == 0
+    assert n_whole > 0
