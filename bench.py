@@ -229,7 +229,7 @@ def pipeline_leg(args, mine, soa, refs, device):
         path = os.path.join(tmp, "reads.bam")
         bam.write_bam(path, sub, refs.lengths)
         t = [time.perf_counter()]
-        reads = bam.read_bam(path, ivs, threads=os.cpu_count() or 1)
+        reads = bam.read_bam(path, ivs, threads=os.cpu_count() or 1, trim=True)
         t.append(time.perf_counter())
         rows = call_loci(reads, ivs, refs, vc_params(), gpus=1, devices=[device], stage_times=(st := {}))
         t.append(time.perf_counter())

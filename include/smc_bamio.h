@@ -45,10 +45,15 @@ typedef struct smc_bam_reads {
     const uint32_t *cigar;
     int64_t         n_cigar_words;
     int64_t         n_dict_umis; /* barcodes that needed the dictionary (see smc_bam_dict_umi) */
+    const int32_t  *store_lo;   /* trim mode (smc_bam_set_trim): the stored window of smc_reads_soa, else NULL */
+    const int32_t  *store_len;
 } smc_bam_reads;
 
 int         smc_bam_open(const char *path, int threads, smc_bam **out);   /* read + inflate + parse the header */
 void        smc_bam_close(smc_bam *h);
+/* trim != 0: smc_bam_decode keeps, for every read that is one plain aligned run, only the query bases between its first and
+ * its last target position (store_lo / store_len of include/smc_b200.h); needs n_intervals > 0.  Default off. */
+void        smc_bam_set_trim(smc_bam *h, int trim);
 const char *smc_bam_last_error(smc_bam *h);                               /* h may be NULL: error of smc_bam_open */
 int         smc_bam_n_refs(smc_bam *h);
 const char *smc_bam_ref_name(smc_bam *h, int i);

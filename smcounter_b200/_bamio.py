@@ -10,7 +10,7 @@ from .soa import ReadsSoA, umi_strings_bulk
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmc_bamio.so")
-EXPORTS = ("smc_bam_open", "smc_bam_close", "smc_bam_last_error", "smc_bam_n_refs", "smc_bam_ref_name", "smc_bam_ref_length",
+EXPORTS = ("smc_bam_set_trim", "smc_bam_open", "smc_bam_close", "smc_bam_last_error", "smc_bam_n_refs", "smc_bam_ref_name", "smc_bam_ref_length",
            "smc_bam_decode", "smc_bam_dict_umi")
 _vp = C.c_void_p
 
@@ -19,7 +19,7 @@ class smc_bam_reads(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("ref_id", _vp), ("pos", _vp), ("flag", _vp), ("mapq", _vp), ("nm", _vp), ("l_seq", _vp),
                 ("seq_off", _vp), ("qual_off", _vp), ("cigar_off", _vp), ("n_cigar", _vp), ("umi", _vp), ("frag_id", _vp),
                 ("seq", _vp), ("seq_bytes", C.c_int64), ("qual", _vp), ("qual_bytes", C.c_int64), ("cigar", _vp),
-                ("n_cigar_words", C.c_int64), ("n_dict_umis", C.c_int64)]
+                ("n_cigar_words", C.c_int64), ("n_dict_umis", C.c_int64), ("store_lo", _vp), ("store_len", _vp)]
 
 
 _lib = None
@@ -36,6 +36,8 @@ def load():
     lib.smc_bam_open.restype = C.c_int
     lib.smc_bam_close.argtypes = [_vp]
     lib.smc_bam_close.restype = None
+    lib.smc_bam_set_trim.argtypes = [_vp, C.c_int]
+    lib.smc_bam_set_trim.restype = None
     lib.smc_bam_last_error.argtypes = [_vp]
     lib.smc_bam_last_error.restype = C.c_char_p
     lib.smc_bam_n_refs.argtypes = [_vp]
@@ -60,7 +62,7 @@ def _arr(ptr, n, dtype):
     return np.frombuffer(buf, dtype=dtype, count=n).copy()
 
 
-def read_bam_native(path: str, intervals=None, threads: int = 0) -> ReadsSoA:
+def read_bam_native(path: str, intervals=None, threads: int = 0, trim: bool = False) -> ReadsSoA:
     lib = load()
     h = _vp()
     rc = lib.smc_bam_open(os.fsencode(path), int(threads), C.byref(h))
@@ -78,6 +80,7 @@ def read_bam_native(path: str, intervals=None, threads: int = 0) -> ReadsSoA:
             n_iv, args = 1, (np.asarray([-1], np.int32), np.zeros(1, np.int32), np.zeros(1, np.int32))   # nothing can match
         else:
             n_iv, args = len(ivs), (iv_ref, iv_s, iv_e)
+        lib.smc_bam_set_trim(h, 1 if (trim and ivs) else 0)
         rc = lib.smc_bam_decode(h, n_iv, args[0].ctypes.data, args[1].ctypes.data, args[2].ctypes.data, C.byref(out))
         if rc != 0:
             raise ValueError(lib.smc_bam_last_error(h).decode())
@@ -95,6 +98,8 @@ def read_bam_native(path: str, intervals=None, threads: int = 0) -> ReadsSoA:
             seq_off=_arr(out.seq_off, n, np.int64), qual_off=_arr(out.qual_off, n, np.int64), cigar_off=_arr(out.cigar_off, n, np.int64),
             n_cigar=_arr(out.n_cigar, n, np.uint16), umi=umi, frag_id=_arr(out.frag_id, n, np.uint32),
             seq=_arr(out.seq, out.seq_bytes, np.uint8), qual=_arr(out.qual, out.qual_bytes, np.uint8),
-            cigar=_arr(out.cigar, out.n_cigar_words, np.uint32), chroms=chroms, umi_names=names, packed=True)
+            cigar=_arr(out.cigar, out.n_cigar_words, np.uint32), chroms=chroms, umi_names=names, packed=True,
+            store_lo=_arr(out.store_lo, n, np.int32) if out.store_lo else None,
+            store_len=_arr(out.store_len, n, np.int32) if out.store_len else None)
     finally:
         lib.smc_bam_close(h)

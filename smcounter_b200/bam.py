@@ -202,22 +202,24 @@ def _assemble(cols, seqs, quals, cigs, chroms, names):
         seq=cat(seqs, np.uint8), qual=cat(quals, np.uint8), cigar=cat(cigs, np.uint32), chroms=chroms, umi_names=names)
 
 
-def read_bam(path: str, intervals=None, native: bool | None = None, threads: int = 0) -> ReadsSoA:
+def read_bam(path: str, intervals=None, native: bool | None = None, threads: int = 0, trim: bool = False) -> ReadsSoA:
     """Decode ``path`` into a ReadsSoA (BAM order).  ``intervals`` = [(chrom, start, end)]: keep only reads whose
     reference span touches a target interval (the only reads a pileup over those targets can see).
 
-    ``native``: True = require libsmc_bamio.so, False = Python walker, None = native when built."""
+    ``native``: True = require libsmc_bamio.so, False = Python walker, None = native when built.
+    ``trim``: store only each read's target window (ReadsSoA.store_lo / store_len): what the calling path uploads."""
     if native is not False:
         try:
             from . import _bamio
-            return _bamio.read_bam_native(path, intervals, threads)
+            return _bamio.read_bam_native(path, intervals, threads, trim)
         except ImportError:
             if native:
                 raise
     with open(path, "rb") as fh:
         raw = bgzf_decompress(fh.read())
     _text, refs, first = parse_header(raw)
-    return decode_records_py(raw, first, [n for n, _ in refs], intervals)
+    soa = decode_records_py(raw, first, [n for n, _ in refs], intervals)
+    return soa.trim_to_targets(intervals) if (trim and intervals) else soa
 
 
 # ------------------------------------------------------------------------------------------------------------------

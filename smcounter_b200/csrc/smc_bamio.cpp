@@ -38,6 +38,8 @@ struct smc_bam {
     std::vector<uint64_t> umi;
     std::vector<uint32_t> frag_id, cigar;
     std::vector<std::string> dict_umis;
+    std::vector<int32_t> store_lo, store_len;   // stored window per read (trim mode)
+    int trim = 0;
 };
 
 static int inflate_all(const std::vector<uint8_t>& file, int threads, std::vector<uint8_t>& out, std::string& err) {
@@ -130,6 +132,7 @@ extern "C" int smc_bam_open(const char* path, int threads, smc_bam** out) {
 }
 
 extern "C" void smc_bam_close(smc_bam* h) { delete h; }
+extern "C" void smc_bam_set_trim(smc_bam* h, int trim) { if (h) h->trim = trim ? 1 : 0; }
 extern "C" const char* smc_bam_last_error(smc_bam* h) { return h ? h->err.c_str() : g_open_error.c_str(); }
 extern "C" int smc_bam_n_refs(smc_bam* h) { return h ? (int)h->ref_names.size() : 0; }
 extern "C" const char* smc_bam_ref_name(smc_bam* h, int i) { return (h && i >= 0 && i < (int)h->ref_names.size()) ? h->ref_names[i].c_str() : ""; }
@@ -184,6 +187,7 @@ static int32_t first_nm(const uint8_t* p, const uint8_t* end) {
 namespace {
 struct RecInfo {
     uint32_t keep;                 // 1 kept, 0 dropped
+    uint32_t store_lo, store_len;  // stored window of the bases / qualities (whole read unless trimming)
     uint32_t bc_off, bc_len;       // barcode bytes inside qname
     uint32_t rid_len;              // readid = qname[0, rid_len)
     uint64_t h1, h2;               // hash of (barcode, readid)
@@ -225,6 +229,20 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
         while (lo < hi) { size_t mid = (lo + hi) / 2; if (v[mid].first < e) lo = mid + 1; else hi = mid; }
         return lo > 0 && v[lo - 1].second > s;
     };
+    // trim mode: disjoint merged target intervals per reference, to find a read's first and last target position
+    const bool trim = h->trim && n_iv > 0;
+    std::vector<std::vector<std::pair<int64_t, int64_t>>> merged(trim ? nref : 0);
+    if (trim)
+        for (size_t rid = 0; rid < nref; ++rid) {
+            std::vector<std::pair<int64_t, int64_t>> v;
+            for (int64_t k = 0; k < n_iv; ++k)
+                if (iv_ref[k] == (int32_t)rid && iv_end[k] > iv_start[k]) v.push_back({iv_start[k], iv_end[k]});
+            std::sort(v.begin(), v.end());
+            for (auto& pr : v) {
+                if (!merged[rid].empty() && pr.first <= merged[rid].back().second) merged[rid].back().second = std::max(merged[rid].back().second, pr.second);
+                else merged[rid].push_back(pr);
+            }
+        }
     const std::vector<uint8_t>& r = h->raw;
     const int threads = std::max(1, h->threads);
     // ---- pass 1: record boundaries
@@ -261,13 +279,31 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
                 continue;
             }
             if ((flag & 0x4) || refID < 0 || (size_t)refID >= nref) continue;
+            R.store_lo = 0; R.store_len = (uint32_t)l_seq;
             if (n_iv > 0) {
                 int64_t reflen = 0;
+                int n_run = 0; bool plain = true;                      // one aligned run, nothing but soft clips around it
                 for (uint16_t k = 0; k < n_cig; ++k) {
                     const uint32_t cw = rd32(cig + 4 * k), op = cw & 15u;
                     if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) reflen += cw >> 4;
+                    if (op == 0 || op == 7 || op == 8) ++n_run; else if (op != 4) plain = false;
                 }
                 if (!touches(refID, pos, (int64_t)pos + reflen)) continue;
+                if (trim && plain && n_run == 1) {
+                    // query bases from the first to the last target position of the read (include/smc_b200.h: store_lo / store_len)
+                    const auto& mv = merged[refID];
+                    const int64_t s0 = pos, e0 = (int64_t)pos + reflen;
+                    size_t lo = 0, hi = mv.size();
+                    while (lo < hi) { size_t mid = (lo + hi) / 2; if (mv[mid].second <= s0) lo = mid + 1; else hi = mid; }      // first interval ending after s0
+                    size_t lo2 = 0, hi2 = mv.size();
+                    while (lo2 < hi2) { size_t mid = (lo2 + hi2) / 2; if (mv[mid].first < e0) lo2 = mid + 1; else hi2 = mid; }  // intervals starting before e0
+                    if (lo < mv.size() && lo2 > lo) {
+                        const int64_t p_lo = std::max(s0, mv[lo].first), p_hi = std::min(e0, mv[lo2 - 1].second) - 1;
+                        const int64_t left_sp = (n_cig > 0 && (rd32(cig) & 15u) == 4) ? (int64_t)(rd32(cig) >> 4) : 0;
+                        const int64_t q_lo = (p_lo - s0 + left_sp) & ~1ll, q_hi = p_hi - s0 + left_sp + 1;
+                        if (q_lo >= 0 && q_hi <= l_seq && q_hi >= q_lo) { R.store_lo = (uint32_t)q_lo; R.store_len = (uint32_t)(q_hi - q_lo); }
+                    }
+                }
             }
             // identity: BC = parts[-2], readid = ':'.join(parts[:-2])   (smCounter.py:319-325)
             const size_t qn = l_rn ? (size_t)l_rn - 1 : 0;
@@ -303,6 +339,7 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
     h->ref_id.resize(n); h->pos.resize(n); h->nm.resize(n); h->l_seq.resize(n); h->flag.resize(n); h->n_cigar.resize(n);
     h->mapq.resize(n); h->seq_off.resize(n); h->qual_off.resize(n); h->cigar_off.resize(n); h->umi.resize(n); h->frag_id.resize(n);
     h->dict_umis.clear();
+    h->store_lo.assign(trim ? n : 0, 0); h->store_len.assign(trim ? n : 0, 0);
     {
         size_t cap = 16;
         while (cap < 2 * n + 2) cap <<= 1;
@@ -325,7 +362,8 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
             const uint16_t n_cig = rd16(b + 12);
             slot[i] = (uint32_t)o;
             h->seq_off[o] = (int64_t)seq_tot; h->qual_off[o] = (int64_t)qual_tot; h->cigar_off[o] = (int64_t)cig_tot;
-            seq_tot += ((size_t)l_seq + 1) / 2; qual_tot += (size_t)l_seq; cig_tot += n_cig;
+            (void)l_seq;
+            seq_tot += ((size_t)R.store_len + 1) / 2; qual_tot += (size_t)R.store_len; cig_tot += n_cig;
             size_t k = (size_t)R.h1 & (cap - 1);
             for (;;) {
                 Ent& E = tab[k];
@@ -363,8 +401,11 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
             const uint8_t* ql = sq + sb;
             h->ref_id[o] = rdi32(b); h->pos[o] = rdi32(b + 4); h->flag[o] = rd16(b + 14); h->mapq[o] = b[9];
             h->nm[o] = first_nm(ql + l_seq, rec_end); h->l_seq[o] = l_seq; h->n_cigar[o] = n_cig;
-            if (sb) memcpy(&h->seq[(size_t)h->seq_off[o]], sq, sb);
-            if (l_seq) memcpy(&h->qual[(size_t)h->qual_off[o]], ql, (size_t)l_seq);
+            const size_t w_lo = info[i].store_lo, w_len = info[i].store_len;
+            if (trim) { h->store_lo[o] = (int32_t)w_lo; h->store_len[o] = (int32_t)w_len; }
+            (void)sb;
+            if (w_len) memcpy(&h->seq[(size_t)h->seq_off[o]], sq + w_lo / 2, (w_len + 1) / 2);
+            if (w_len) memcpy(&h->qual[(size_t)h->qual_off[o]], ql + w_lo, w_len);
             if (n_cig) memcpy(&h->cigar[(size_t)h->cigar_off[o]], cig, 4 * (size_t)n_cig);
         }
     });
@@ -374,5 +415,6 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
     out->cigar_off = h->cigar_off.data(); out->n_cigar = h->n_cigar.data(); out->umi = h->umi.data(); out->frag_id = h->frag_id.data();
     out->seq = h->seq.data(); out->seq_bytes = (int64_t)h->seq.size(); out->qual = h->qual.data(); out->qual_bytes = (int64_t)h->qual.size();
     out->cigar = h->cigar.data(); out->n_cigar_words = (int64_t)h->cigar.size(); out->n_dict_umis = (int64_t)h->dict_umis.size();
+    out->store_lo = trim ? h->store_lo.data() : nullptr; out->store_len = trim ? h->store_len.data() : nullptr;
     return 0;
 }

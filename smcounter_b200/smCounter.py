@@ -147,7 +147,7 @@ def main(args):
         bed_lines = fh.readlines()
     intervals = intervals_from_bed_lines(bed_lines)
     refs = FastaFile(args.refGenome)
-    reads = read_bam(args.bamFile, intervals, threads=max(1, args.nCPU))
+    reads = read_bam(args.bamFile, intervals, threads=max(1, args.nCPU), trim=True)      # only the target windows cross PCIe
     prm = VcParams(mtDepth=args.mtDepth, rpb=args.rpb, minBQ=args.minBQ, minMQ=args.minMQ, hpLen=args.hpLen,
                    mismatchThr=args.mismatchThr, mtDrop=args.mtDrop, maxMT=args.maxMT, primerDist=args.primerDist)
     try:

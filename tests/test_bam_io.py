@@ -104,3 +104,27 @@ def test_bgzf_multi_block_roundtrip():
     assert bam.bgzf_decompress(comp) == data
     with pytest.raises(ValueError):
         bam.bgzf_decompress(b"\x1f\x8b\x08\x00" + b"\x00" * 30)
+
+
+def test_native_decoder_trim_mode_matches_trim_to_targets(tmp_path):
+    """smc_bam_set_trim: the C++ decoder's stored windows and payload are exactly ReadsSoA.trim_to_targets() of the untrimmed
+    decode (both for overlapping / adjacent intervals and reads with soft clips and indels)."""
+    import numpy as np
+    from smcounter_b200 import bam
+    from smcounter_b200.synth import SynthSpec, make_panel
+    ivs = [("chr1", 1000, 1100), ("chr1", 1090, 1120), ("chr1", 1120, 1130), ("chr2", 300, 380), ("chr1", 5000, 5060)]
+    soa, refs, _ = make_panel(ivs, SynthSpec(umis_per_locus=30, rpb=3.0, indel_every=30, indel_vaf=0.1, softclip_frac=0.3), seed=9)
+    path = str(tmp_path / "t.bam")
+    bam.write_bam(path, soa, refs.lengths)
+    want = bam.read_bam(path, ivs, native=True).trim_to_targets(ivs)
+    got = bam.read_bam(path, ivs, native=True, trim=True)
+    assert got.packed and got.store_lo is not None and (got.store_len < got.l_seq).any()
+    for f in ("ref_id", "pos", "flag", "l_seq", "n_cigar", "umi", "frag_id", "store_lo", "store_len", "seq_off", "qual_off", "cigar_off", "qual", "cigar"):
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f
+    # seq: identical up to the unused low nibble after an odd-length window
+    assert got.seq.shape == want.seq.shape
+    last = (want.seq_off + (want.store_len.astype(np.int64) + 1) // 2 - 1)[want.store_len % 2 == 1]
+    mask = np.ones(len(want.seq), dtype=bool); mask[last] = False
+    assert np.array_equal(got.seq[mask], want.seq[mask]) and np.array_equal(got.seq[last] >> 4, want.seq[last] >> 4)
+    py = bam.read_bam(path, ivs, native=False, trim=True)
+    assert np.array_equal(py.store_lo, want.store_lo) and np.array_equal(py.qual, want.qual)

@@ -127,6 +127,13 @@ def test_cfg2_panel_batch_properties_sharding_and_oracle_sample():
         _check_properties(res, soa, loci)
         hp = device_hp_flags(caller, res, soa, loci, soa.chroms, refs, prm.hpLen)
         g_rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order, hp_flags=hp)
+        # the same reads trimmed to their target windows (what the BAM decoder delivers): identical bits from fewer bytes
+        trimmed = soa.trim_to_targets(ivs)
+        assert trimmed.seq.nbytes + trimmed.qual.nbytes < 0.7 * (soa.seq.nbytes + soa.qual.nbytes)
+        res_t = caller.call(trimmed, loci)
+        for f in ("loc", "cnt", "pi", "alt_allele", "alt_pi", "fl1", "fl2"):
+            assert np.array_equal(getattr(res, f), getattr(res_t, f)), f
+        res = caller.call(soa, loci)
         # idempotence: the resident batch run again, one launch instead of per-chunk launches -> identical bits
         caller.run()
         again = caller.download(None)
