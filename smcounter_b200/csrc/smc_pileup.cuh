@@ -1171,10 +1171,20 @@ __global__ void __launch_bounds__(KB_WARPS * 32, KB_MINBLOCKS) k_merge_t(const K
             const uint32_t e = __ldg(extp);
             if (aid == FC_AID_DYN) aid = NF + e;
         }
-        if (st == 3u) {
-            const double2 pq = pq_s[((cd >> 5) & 0x100u) | (cd & 0xffu)];            // smCounter.py:65-68
-            fragment_join(pq.x, pq.y, aid, lane, ucnt, uprod, S);
-        }
+        const double2 pq = pq_s[((cd >> 5) & 0x100u) | (cd & 0xffu)];                // smCounter.py:65-68 (a valid entry for any code)
+        const bool join = st == 3u;
+        // Nine rows out of ten no lane's barcode shows a second allele or a dynamic one: the fragment joins a single-allele
+        // barcode (fragment_join reduces to two products and a count), done without a divergent branch -- a fragment that
+        // is not in bcDict multiplies by exactly 1.0.
+        const uint32_t bit = 1u << (aid & 31u);
+        const bool rare = join && (aid >= NF || (S.exist & ~bit) != 0u);
+        if (!__any_sync(FULL_MASK, rare)) {
+            S.Q = __dmul_rn(S.Q, join ? pq.x : 1.0);
+            S.rightP = __dmul_rn(S.rightP, join ? pq.y : 1.0);                        // :77
+            S.n += join ? 1 : 0;
+            S.exist |= join ? bit : 0u;
+            S.last_aid = join ? aid : S.last_aid;
+        } else if (join) fragment_join(pq.x, pq.y, aid, lane, ucnt, uprod, S);
     }
     // ---- flush the lane's locus to the per-locus accumulators ([field][locus] layout: coalesced across lanes)
     if (lane_valid) {
