@@ -1,7 +1,9 @@
 // libsmc_b200.so -- C ABI (include/smc_b200.h) and pipeline orchestration.
 //
-//   H2D -> K1 read prep (CIGAR walk, QC gate, locus range)        smc_pileup.cuh
-//       -> K2 segmented radix sort: reads by (barcode, fragment), tile events by tile   smc_sort.cuh
+//   H2D (scalars first; bases / qualities in chunks on a second stream, overlapped with everything up to K3)
+//       -> K2a barcode slots (hash table) + one radix sort of the reads on (slot, fragment id)     smc_sort.cuh
+//       -> K1 read prep (CIGAR walk, QC gate, locus range, stored window)                         smc_pileup.cuh
+//       -> K2b (read x 32-locus tile) events, radix sort by tile                                  smc_sort.cuh
 //       -> K3a k_gather: lane = locus, base/quality gather, read tallies, fragment merge smc_pileup.cuh
 //       -> K3b k_merge: per-barcode posterior (calProb), prediction index, consensus    smc_pileup.cuh
 //       -> K4 FP64 statistics: PI, ALT, filters, Fisher                                smc_stats.cuh
@@ -127,14 +129,6 @@ __global__ void k_loci_keys(const int32_t* ref_id, const int32_t* pos0, int64_t 
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) key[i] = ((uint64_t)(uint32_t)ref_id[i] << 32) | (uint32_t)pos0[i];
 }
-__global__ void k_init_pairs_frag(const uint32_t* frag, int64_t n, uint64_t* k, uint32_t* v) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { k[i] = frag[i]; v[i] = (uint32_t)i; }
-}
-__global__ void k_gather_umi_keys(const uint64_t* umi, const uint32_t* v, int64_t n, uint64_t* k) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) k[i] = umi[v[i]];
-}
 // Barcode slots: every distinct barcode code gets one slot of an open-addressing table (linear probing, atomicCAS); the slot
 // index stands in for the barcode in the read sort key, so that ONE sort on (slot, fragment id) groups the reads by barcode and
 // fragment.  Which slot a barcode lands in may differ from run to run; nothing downstream depends on the order of barcodes
@@ -185,10 +179,6 @@ __global__ void k_unit_counts(const uint32_t* tile_off, uint32_t n_tiles, uint32
     if (t > n_tiles) return;
     uint32_t n = t < n_tiles ? tile_off[t + 1] - tile_off[t] : 0;
     cnt[t] = (n + chunk - 1) / chunk;
-}
-__global__ void k_fill_u64(unsigned long long* p, int64_t n, unsigned long long v) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
 }
 __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
