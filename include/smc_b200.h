@@ -152,7 +152,7 @@ typedef struct smc_umi_keep {
 
 #define SMC_ST_ZERO_COVERAGE   1u   /* usedMT == 0 (:492-494) */
 #define SMC_ST_NEED_DOWNSAMPLE 2u   /* len(bcDict) > ds and no mask given: tallies cover ALL barcodes; re-run with a mask */
-#define SMC_ST_UMI_OVERFLOW    4u   /* a barcode showed > 2 distinct non-ACGT/DEL alleles at this locus (unsupported) */
+#define SMC_ST_UMI_OVERFLOW    4u   /* a barcode showed > 6 distinct non-ACGT/DEL alleles at this locus (unsupported) */
 #define SMC_ST_BAD_MASK        8u   /* mask given but kept count != ds */
 
 /* dynamic allele kinds (dyn_kind) */

@@ -271,7 +271,8 @@ static inline uint64_t code_slots_total(uint64_t ne, uint64_t n_units, uint32_t 
 }
 
 #define NF SMC_NFIXED
-#define NSLOT 7            // per-barcode allele slots: 5 fixed + 2 dynamic
+#define NDYN 6             // distinct dynamic alleles (indel starts, N / IUPAC bases) one barcode may show at one locus
+#define NSLOT (NF + NDYN)  // per-barcode allele slots: 5 fixed + NDYN dynamic
 
 // The dynamic-allele table, passed BY VALUE to the out-of-line helpers.
 struct DynTab {
@@ -766,7 +767,8 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
 #define KB_LIMB_WORDS  (NF * 4 * 32)            // 128-bit fixed-point PI accumulator per fixed allele and lane
 #define KB_UCNT_WORDS  (NSLOT * 32)
 #define KB_UPROD_WORDS (NSLOT * 64)
-#define KB_WARP_WORDS  (KB_FC_WORDS + KB_LIMB_WORDS + KB_UCNT_WORDS + KB_UPROD_WORDS)
+#define KB_UDYN_WORDS  (NDYN * 32)              // dynamic-allele row of slot NF + k of the open barcode, per lane
+#define KB_WARP_WORDS  (KB_FC_WORDS + KB_LIMB_WORDS + KB_UCNT_WORDS + KB_UPROD_WORDS + KB_UDYN_WORDS)
 #define KB_TAB_BYTES   8192                     // {p, 1 - p} of a fragment, indexed by 'Paired' << 8 | quality (512 x double2)
 #define KB_SMEM_BYTES  (KB_TAB_BYTES + KB_WARPS * KB_WARP_WORDS * 4)
 
@@ -823,7 +825,7 @@ struct MergeState {
     unsigned long long pad_lo, pad_hi;      // PI terms that go to all of A, C, G, T (single-allele barcodes, see umi_finalize)
     uint32_t flags;                         // LF_*
     // barcode-level
-    int n; uint32_t exist; double Q, rightP; uint32_t last_aid; uint32_t udyn0, udyn1; int ndyn;
+    int n; uint32_t exist; double Q, rightP; uint32_t last_aid; int ndyn;      // the rows of the dynamic slots live in shared memory (UDYN)
     uint32_t first_read;                    // BAM index of the barcode's first passing read at this locus (listing only)
 };
 
@@ -831,6 +833,7 @@ struct MergeState {
 #define LIMB(a)     limb[(a) * 32 + lane]
 #define UCNT(s)     ucnt[(s) * 32 + lane]
 #define UPROD(s)    uprod[(s) * 32 + lane]
+#define UDYN(k)     (reinterpret_cast<uint32_t*>(uprod + NSLOT * 32)[(k) * 32 + lane])
 
 // MTCnt / strongMTCnt of an allele that may be dynamic; add = 1 (MTCnt) or 0x10001 (both)
 __device__ __forceinline__ void bump_mt(int32_t* dcnt, int* fc, int lane, uint32_t aid, uint32_t add) {
@@ -854,11 +857,13 @@ __device__ __forceinline__ void fragment_join(double p, double q1, uint32_t aid,
     int slot = (int)aid;
     if (aid >= NF) {
         const uint32_t e = aid - NF;
-        if (S.ndyn > 0 && S.udyn0 == e) slot = 5;
-        else if (S.ndyn > 1 && S.udyn1 == e) slot = 6;
-        else if (S.ndyn == 0) { S.udyn0 = e; S.ndyn = 1; slot = 5; }
-        else if (S.ndyn == 1) { S.udyn1 = e; S.ndyn = 2; slot = 6; }
-        else { S.status |= SMC_ST_UMI_OVERFLOW; slot = 5; }
+        int k = 0;
+        while (k < S.ndyn && UDYN(k) != e) ++k;
+        if (k == S.ndyn) {
+            if (k < NDYN) { UDYN(k) = e; S.ndyn = k + 1; }
+            else { S.status |= SMC_ST_UMI_OVERFLOW; k = 0; }
+        }
+        slot = NF + k;
     }
     const uint32_t bit = 1u << slot;
     if (S.exist == 0) S.exist = bit;
@@ -928,17 +933,20 @@ __device__ __forceinline__ double neg_log10_1m_small(double p) {
 // table holds (smCounter.py:26-98, 506-523) -- the general form; the per-barcode arrays are in shared memory.
 // Returns the finalDict keys it touched among the fixed alleles.
 __device__ __noinline__ uint32_t umi_general(DynTab T, const double* __restrict__ pcrtab, int pcr_nmax, double smt, int lane, int n,
-                                             uint32_t exist, double rightP, int ndyn, uint32_t udyn0, uint32_t udyn1, uint32_t last_aid,
+                                             uint32_t exist, double rightP, int ndyn, uint32_t last_aid,
                                              int* fc, ulonglong2* limb, int* ucnt, double* uprod) {
     uint32_t keymask = 0;
-    // canonical order of the dynamic slots = ascending allele key
-    if (ndyn == 2 && __ldcg(&T.dkey[udyn0]) > __ldcg(&T.dkey[udyn1])) {
-        uint32_t t = udyn0; udyn0 = udyn1; udyn1 = t;
-        int c5 = UCNT(5), c6 = UCNT(6); double p5 = UPROD(5), p6 = UPROD(6);
-        uint32_t b5 = (exist >> 5) & 1u, b6 = (exist >> 6) & 1u;
-        UCNT(5) = c6; UCNT(6) = c5; UPROD(5) = p6; UPROD(6) = p5;
-        exist = (exist & 0x1fu) | (b6 << 5) | (b5 << 6);
-    }
+    // canonical order of the dynamic slots = ascending allele key (insertion sort of the slot rows; a slot whose exist bit is
+    // clear -- its fragments were all deleted again -- travels with its bit)
+    for (int i = 1; i < ndyn; ++i)
+        for (int j = i; j > 0 && __ldcg(&T.dkey[UDYN(j - 1)]) > __ldcg(&T.dkey[UDYN(j)]); --j) {
+            const int a = NF + j - 1, b = NF + j;
+            const uint32_t tu = UDYN(j - 1); UDYN(j - 1) = UDYN(j); UDYN(j) = tu;
+            const int tc = UCNT(a); UCNT(a) = UCNT(b); UCNT(b) = tc;
+            const double tp = UPROD(a); UPROD(a) = UPROD(b); UPROD(b) = tp;
+            const uint32_t ba = (exist >> a) & 1u, bb = (exist >> b) & 1u;
+            exist = (exist & ~((1u << a) | (1u << b))) | (bb << a) | (ba << b);
+        }
     int k = __popc(exist);
     uint32_t pad = 0;                             // :49-54  pad with A, T, G, C until 4
     if (k < 4 && !((exist >> SMC_A_A) & 1u)) { pad |= 1u << SMC_A_A; ++k; }
@@ -994,7 +1002,7 @@ __device__ __noinline__ uint32_t umi_general(DynTab T, const double* __restrict_
             LIMB(s) = v;
             keymask |= 1u << s;
         } else {
-            const uint32_t e = s == 5 ? udyn0 : udyn1;
+            const uint32_t e = UDYN(s - NF);
             unsigned long long a0, a1, a2;
             split_limbs(lo, hi, a0, a1, a2);
             if (a0) atomicAdd(&T.dlimb[(size_t)e * 3 + 0], a0);
@@ -1006,7 +1014,7 @@ __device__ __noinline__ uint32_t umi_general(DynTab T, const double* __restrict_
         else if (l == best) nbest++;
     }
     if (nbest == 1) {                                             // :515-519
-        const uint32_t aid = cons < NF ? (uint32_t)cons : NF + (cons == 5 ? udyn0 : udyn1);
+        const uint32_t aid = cons < NF ? (uint32_t)cons : NF + UDYN(cons - NF);
         bump_mt(T.dcnt, fc, lane, aid, best > smt ? 0x10001u : 1u);
     } else if (n == 1) {                                          // :521-523
         bump_mt(T.dcnt, fc, lane, last_aid, 1u);
@@ -1094,7 +1102,7 @@ __device__ __forceinline__ void umi_finalize(const KBArgs& A, int lane, int ki, 
             else if (n == 1) FCW(a0) += 1;
         } else {
             if (!multi) umi_materialize(lane, ucnt, uprod, S.exist, n, S.rightP);
-            S.keymask |= umi_general(A.T, A.pcrtab, A.pcr_nmax, A.smt, lane, n, S.exist, S.rightP, S.ndyn, S.udyn0, S.udyn1,
+            S.keymask |= umi_general(A.T, A.pcrtab, A.pcr_nmax, A.smt, lane, n, S.exist, S.rightP, S.ndyn,
                                      S.last_aid, fc, limb, ucnt, uprod);
         }
     }
@@ -1138,7 +1146,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32, KB_MINBLOCKS) k_merge_t(const K
     S.allFrag = S.allMT = S.usedFrag = S.nBC = S.usedMT = S.mt3 = S.mt5 = S.mt7 = S.mt10 = 0;
     S.keymask = 0; S.status = 0; S.pad_lo = S.pad_hi = 0;
     S.flags = 0;
-    S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.last_aid = 0; S.udyn0 = S.udyn1 = 0; S.ndyn = 0;
+    S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.last_aid = 0; S.ndyn = 0;
     S.first_read = 0xffffffffu;
 
     uint32_t umi_slot = eb;                                        // warp uniform: umi_urank[] slot of the open barcode

@@ -377,3 +377,78 @@ def test_malformed_stored_windows_are_refused():
                 c.call(t, loci)
     finally:
         c.close()
+
+
+def _plant_ambiguity_codes(soa, chrom_idx, p, codes):
+    """Rewrite the base at reference position ``p`` in every fully matched read of the deepest barcode there: fragment k of
+    that barcode shows BAM nibble codes[k] (IUPAC ambiguity codes and N: each a distinct 'dynamic' allele), quality 37."""
+    import numpy as np
+    ends = soa.ref_end()
+    plain = (soa.n_cigar == 1) & ((soa.cigar[soa.cigar_off] & 15) == 0)
+    cover = np.flatnonzero((soa.ref_id == chrom_idx) & (soa.pos <= p) & (ends > p) & plain)
+    umis, counts = np.unique(soa.umi[cover], return_counts=True)
+    order = np.argsort(-counts)
+    for u in umis[order]:
+        reads = cover[soa.umi[cover] == u]
+        frags = list(dict.fromkeys(soa.frag_id[reads].tolist()))
+        if len(frags) >= len(codes):
+            break
+    else:
+        raise AssertionError("no barcode with %d fragments over the locus" % len(codes))
+    seq, qual = soa.seq.copy(), soa.qual.copy()
+    for k, f in enumerate(frags[:len(codes)]):
+        for r in reads[soa.frag_id[reads] == f]:
+            q = int(p - soa.pos[r])
+            b = int(soa.seq_off[r]) + (q >> 1)
+            seq[b] = (seq[b] & 0x0F) | (codes[k] << 4) if q % 2 == 0 else (seq[b] & 0xF0) | codes[k]
+            qual[int(soa.qual_off[r]) + q] = 37
+    soa.seq, soa.qual = seq, qual
+    return soa
+
+
+@pytest.mark.parametrize("codes", [(15, 3, 5), (3, 5, 9, 10, 6, 12)])
+def test_barcode_with_many_dynamic_alleles_at_one_locus(codes):
+    """One barcode showing three / six distinct non-ACGT alleles at one locus (N and IUPAC codes stand in for the distinct
+    insertion / deletion alleles a homopolymer collects): the per-barcode slots hold six dynamic alleles, canonical order =
+    ascending allele key.  calProb over 7 / 10 alleles must match the oracle."""
+    from helpers import run_case
+    ivs = [("chr1", 1000, 1040)]
+    spec = SynthSpec(umis_per_locus=25, rpb=9.0, snv_every=0, n_frac=0.0, softclip_frac=0.0, lowmapq_frac=0.0)
+    problems, stats, _ = run_case(ivs, spec, VcParams(mtDepth=25, rpb=9.0), seed=83,
+                                  mutate=lambda s: _plant_ambiguity_codes(s, 0, 1020, codes))
+    print(stats)
+    assert stats["n_dyn"] >= len(codes)
+    assert not problems, "\n".join(problems)
+
+
+@pytest.mark.parametrize("seed", list(range(101, 113)))
+def test_randomised_parameters_and_panels(seed):
+    """Differential fuzz: panel shape, read-error knobs and every vc() parameter drawn from a seeded generator; the CUDA path
+    (alternating plain / packed / target-trimmed encodings and chunked uploads) against the oracle, field by field."""
+    import numpy as np
+    from helpers import run_case
+    rng = np.random.default_rng(seed)
+    ivs, used = [], set()
+    for _ in range(int(rng.integers(1, 5))):
+        c = "chr%d" % int(rng.integers(1, 4))
+        s = int(rng.integers(200, 3000))
+        L = int(rng.choice([1, 2, 7, 31, 33, 64, 90, 150]))
+        if any(c == cc and s < ee + 400 and ss < s + L + 400 for (cc, ss, ee) in ivs):
+            continue
+        ivs.append((c, s, s + L))
+    rpb = float(rng.choice([1.1, 2.0, 3.5, 6.0]))
+    umis = int(rng.choice([8, 25, 60, 150]))
+    spec = SynthSpec(umis_per_locus=umis, rpb=rpb, snv_every=int(rng.choice([0, 20, 60])), snv_vaf=float(rng.choice([0.02, 0.2, 0.6])),
+                     indel_every=int(rng.choice([0, 45, 120])), indel_vaf=float(rng.choice([0.05, 0.3])),
+                     softclip_frac=float(rng.choice([0.0, 0.1, 0.5])), lowmapq_frac=float(rng.choice([0.0, 0.1, 0.4])),
+                     n_frac=float(rng.choice([0.0, 0.002])), pcr_err_per_frag=float(rng.choice([0.0, 0.01, 0.05])),
+                     q_values=(37, 30, 12) if rng.random() < 0.7 else (40, 22, 19), q_probs=(0.85, 0.10, 0.05) if rng.random() < 0.7 else (0.4, 0.3, 0.3))
+    prm = VcParams(mtDepth=int(rng.choice([umis, max(2, umis // 3)])), rpb=rpb, minBQ=int(rng.choice([0, 13, 20, 25, 31])),
+                   minMQ=int(rng.choice([0, 20, 30, 60])), hpLen=int(rng.choice([4, 8, 10])), mismatchThr=float(rng.choice([0.5, 2.0, 6.0, 100.0])),
+                   mtDrop=int(rng.choice([0, 0, 1, 2])), maxMT=int(rng.choice([0, 0, 12])), primerDist=int(rng.choice([0, 2, 10])))
+    enc = seed % 3
+    gpu_mutate = None if enc == 0 else (lambda s: s.repack()) if enc == 1 else (lambda s: s.trim_to_targets(ivs))
+    chunks = "1" if seed % 2 else "3"
+    problems, stats, _ = _with_env("SMC_PIPE_CHUNKS", chunks, lambda: run_case(ivs, spec, prm, seed=seed, gpu_mutate=gpu_mutate))
+    print(seed, ivs, spec, prm, stats)
+    assert not problems, "\n".join(problems)
