@@ -44,18 +44,83 @@ def assign_intervals(weights, n_shards: int):
     return shard, load
 
 
+class ReadLocator:
+    """Finds the reads whose reference span touches an interval.  For reads in BAM coordinate order (checked once) this is a
+    binary search per interval over each contig's start positions plus an exact end test on the few candidates; any other
+    order falls back to a full scan per interval."""
+
+    def __init__(self, reads: ReadsSoA, chroms):
+        self.reads = reads
+        self.cidx = {c: i for i, c in enumerate(chroms)}
+        self.starts = reads.pos.astype(np.int64)
+        self.ends = reads.ref_end()
+        key = (reads.ref_id.astype(np.int64) << 32) | self.starts
+        self.sorted = bool(reads.n == 0 or np.all(key[1:] >= key[:-1]))
+        self.max_span = int((self.ends - self.starts).max()) if reads.n else 0
+        self.block = {}
+        if self.sorted and reads.n:
+            rid = reads.ref_id
+            cuts = np.flatnonzero(np.diff(rid) != 0) + 1
+            for a, b in zip(np.concatenate(([0], cuts)), np.concatenate((cuts, [reads.n]))):
+                self.block[int(rid[a])] = (int(a), int(b))
+
+    def candidates(self, chrom, s, e):
+        """(lo, hi): index range that contains every read of ``chrom`` starting in [s - max_span, e)."""
+        r = self.cidx.get(chrom)
+        if r is None or e <= s or r not in self.block:
+            return 0, 0
+        a, b = self.block[r]
+        st = self.starts[a:b]
+        return a + int(np.searchsorted(st, s - self.max_span, side="left")), a + int(np.searchsorted(st, e, side="left"))
+
+    def count_upper(self, chrom, s, e) -> int:
+        lo, hi = self.candidates(chrom, s, e)
+        return hi - lo
+
+    def select(self, intervals) -> np.ndarray:
+        """Ascending indices of the reads that touch one of ``intervals`` (BAM order is kept)."""
+        n = self.reads.n
+        keep = np.zeros(n, dtype=bool)
+        if self.sorted:
+            for (c, s, e) in intervals:
+                lo, hi = self.candidates(c, s, e)
+                if hi > lo:
+                    keep[lo:hi] |= self.ends[lo:hi] > s
+        else:
+            for (c, s, e) in intervals:
+                r = self.cidx.get(c)
+                if r is None or e <= s:
+                    continue
+                keep |= (self.reads.ref_id == r) & (self.starts < e) & (self.ends > s)
+        return np.flatnonzero(keep)
+
+
 def reads_for_intervals(reads: ReadsSoA, intervals, chroms) -> np.ndarray:
     """Ascending indices of the reads whose reference span touches one of ``intervals`` (BAM order is kept)."""
-    cidx = {c: i for i, c in enumerate(chroms)}
-    ends = reads.ref_end()
-    starts = reads.pos.astype(np.int64)
-    keep = np.zeros(reads.n, dtype=bool)
-    for (c, s, e) in intervals:
-        r = cidx.get(c)
-        if r is None or e <= s:
-            continue
-        keep |= (reads.ref_id == r) & (starts < e) & (ends > s)
-    return np.flatnonzero(keep)
+    return ReadLocator(reads, chroms).select(intervals)
+
+
+def plan_batches(locator: ReadLocator, intervals, idxs, max_payload_bytes: int = 1 << 30, max_loci: int = 1 << 21,
+                 max_reads: int = 1 << 27):
+    """Cut the interval indices ``idxs`` (BED order) into consecutive batches that respect the per-batch limits of
+    libsmc_b200 (include/smc_b200.h: < 4 GiB of bases / qualities, < 2^31 reads, <= 4 194 302 loci) with a wide margin,
+    from an upper estimate of the reads per interval.  A whole panel or exome goes through one GPU as a stream of batches."""
+    reads = locator.reads
+    per_read = (float(reads.seq.nbytes + reads.qual.nbytes) / reads.n) if reads.n else 0.0
+    batches, cur, loci, nreads = [], [], 0, 0
+    for k in idxs:
+        c, s, e = intervals[k]
+        n_loci = max(0, e - s)
+        cnt = locator.count_upper(c, s, e) if locator.sorted else reads.n
+        if cur and (loci + n_loci > max_loci or (nreads + cnt) * per_read > max_payload_bytes or nreads + cnt > max_reads):
+            batches.append(cur)
+            cur, loci, nreads = [], 0, 0
+        cur.append(k)
+        loci += n_loci
+        nreads += cnt
+    if cur:
+        batches.append(cur)
+    return batches
 
 
 def subset_loci(loci: Loci, intervals, chroms):

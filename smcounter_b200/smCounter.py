@@ -30,7 +30,7 @@ from .caller import GpuCaller, UmiKeep, VcParams
 from .downsample import draw_keep_masks
 from .fasta import FastaFile
 from .rows import device_hp_flags, format_rows
-from .shard import interleave_rows, plan_shards, reads_for_intervals
+from .shard import ReadLocator, interleave_rows, plan_batches, plan_shards
 from .targets import build_loci, intervals_from_bed_lines
 
 parser = None
@@ -64,13 +64,16 @@ def argParseInit():
     parser.add_argument('--gpus', type=int, default=1, help='number of B200 GPUs to shard the target over (BED intervals, balanced by depth)')
 
 
-def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None, stage_times: dict | None = None):
+def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None, stage_times: dict | None = None,
+              batch_limits: dict | None = None):
     """The drop-in for the reference's per-locus fan-out: rows of vc() (45 tab-joined fields each, FILTER still in
     accumulator form) for every position of ``intervals`` in BED order.
 
     ``reads``: ReadsSoA of the BAM; ``refs``: object with fetch()/get_reference_length().  One host thread per GPU
     (ctypes drops the GIL); a failing shard fails the run like smCounter.py:690-694.  ``stage_times`` (optional dict)
-    receives the wall-clock ms of the device calls and of the row formatting, summed over shards."""
+    receives the wall-clock ms of the device calls and of the row formatting, summed over shards.  A shard larger than
+    the library's per-batch limits is streamed through its GPU in consecutive batches (``batch_limits``: keyword overrides
+    of shard.plan_batches, for tests)."""
     import time
     chroms = reads.chroms
     devices = list(devices) if devices is not None else list(range(max(1, gpus)))
@@ -78,37 +81,47 @@ def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None
     shard_rows = [None] * len(plan)
     errors = [None] * len(plan)
 
+    locator = ReadLocator(reads, chroms)
+
     def work(g):
         try:
-            ivs = [intervals[k] for k in plan[g][0]]
-            if not ivs:
+            idxs = plan[g][0]
+            if not idxs:
                 shard_rows[g] = []
                 return
-            sub = reads if len(plan) == 1 else reads.select(reads_for_intervals(reads, ivs, chroms))
-            loci, bed_order = build_loci(ivs, chroms, refs)
+            # a shard goes through its GPU as a stream of batches under the library's per-batch limits
+            batches = plan_batches(locator, intervals, idxs, **(batch_limits or {}))
             tc = time.perf_counter()
             caller = GpuCaller(prm, devices[g])
-            t0 = time.perf_counter()
+            rows = []
             try:
-                res = caller.call(sub, loci)
-                if stage_times is not None:
-                    tm = caller.timings()
-                    stage_times["ms_ctx_create"] = stage_times.get("ms_ctx_create", 0.0) + 1e3 * (t0 - tc)
-                    stage_times["ms_first_call"] = stage_times.get("ms_first_call", 0.0) + 1e3 * (time.perf_counter() - t0)
-                    for k in ("ms_h2d", "ms_total_device", "ms_d2h"):
-                        stage_times[k] = stage_times.get(k, 0.0) + float(tm[k])
-                keep = draw_keep_masks(caller, res, sub, loci, chroms, prm)        # smCounter.py:496-500
-                if keep is not None:
-                    res = caller.call(sub, loci, keep)
-                hp = device_hp_flags(caller, res, sub, loci, chroms, refs, prm.hpLen)   # isHPorLowComp, smCounter.py:122-177
+                for b in batches:
+                    ivs = [intervals[k] for k in b]
+                    whole = len(plan) == 1 and len(batches) == 1
+                    sub = reads if whole else reads.select(locator.select(ivs))
+                    loci, bed_order = build_loci(ivs, chroms, refs)
+                    t0 = time.perf_counter()
+                    res = caller.call(sub, loci)
+                    if stage_times is not None:
+                        tm = caller.timings()
+                        stage_times["ms_ctx_create"] = stage_times.get("ms_ctx_create", 0.0) + 1e3 * (t0 - tc)
+                        stage_times["ms_first_call"] = stage_times.get("ms_first_call", 0.0) + 1e3 * (time.perf_counter() - t0)
+                        for k in ("ms_h2d", "ms_total_device", "ms_d2h"):
+                            stage_times[k] = stage_times.get(k, 0.0) + float(tm[k])
+                    keep = draw_keep_masks(caller, res, sub, loci, chroms, prm)        # smCounter.py:496-500
+                    if keep is not None:
+                        res = caller.call(sub, loci, keep)
+                    hp = device_hp_flags(caller, res, sub, loci, chroms, refs, prm.hpLen)   # isHPorLowComp, smCounter.py:122-177
+                    t1 = time.perf_counter()
+                    rows.extend(format_rows(res, sub, loci, chroms, refs, prm.hpLen, bed_order, hp_flags=hp))
+                    if stage_times is not None:
+                        stage_times["ms_gpu_call"] = stage_times.get("ms_gpu_call", 0.0) + 1e3 * (t1 - t0)
+                        stage_times["ms_format_rows"] = stage_times.get("ms_format_rows", 0.0) + 1e3 * (time.perf_counter() - t1)
+                        stage_times["batches"] = stage_times.get("batches", 0) + 1
+                    tc = time.perf_counter()
             finally:
-                t1 = time.perf_counter()
                 caller.close()
-            t2 = time.perf_counter()
-            shard_rows[g] = format_rows(res, sub, loci, chroms, refs, prm.hpLen, bed_order, hp_flags=hp)
-            if stage_times is not None:
-                stage_times["ms_gpu_call"] = stage_times.get("ms_gpu_call", 0.0) + 1e3 * (t1 - t0)
-                stage_times["ms_format_rows"] = stage_times.get("ms_format_rows", 0.0) + 1e3 * (time.perf_counter() - t2)
+            shard_rows[g] = rows
         except BaseException as e:          # noqa: BLE001 -- re-raised on the main thread
             errors[g] = e
 

@@ -189,3 +189,7 @@ def test_cfg5_many_loci_many_contigs_shape():
         caller.close()
     _compare_with_oracle(g_rows, ivs, soa, refs, prm, truth, seed=9, n_random=40, n_truth=20)
     assert call_loci(soa, ivs, refs, prm, gpus=8, devices=[0] * 8) == g_rows
+    # one GPU, the target streamed through it in batches of at most 20 000 loci (the per-batch limits, scaled down)
+    st = {}
+    assert call_loci(soa, ivs, refs, prm, gpus=1, stage_times=st, batch_limits={"max_loci": 20000}) == g_rows
+    assert st["batches"] >= 12

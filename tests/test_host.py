@@ -316,3 +316,40 @@ def test_trim_to_targets_keeps_exactly_the_target_window():
         else:
             assert ln == 0
     assert n_whole > 0
+
+
+def test_read_locator_and_batch_plan():
+    """shard.ReadLocator.select() == brute-force overlap scan (coordinate-sorted and shuffled reads); plan_batches() cuts the
+    BED order into consecutive batches under the given limits and keeps every interval exactly once."""
+    import numpy as np
+    from smcounter_b200.shard import ReadLocator, plan_batches, reads_for_intervals
+    from smcounter_b200.synth import SynthSpec, make_panel
+    ivs = [("chr1", 1000, 1100), ("chr2", 300, 380), ("chr1", 5000, 5060), ("chr1", 1080, 1150), ("chr3", 10, 11), ("chr2", 900, 905)]
+    soa, _, _ = make_panel(ivs[:4], SynthSpec(umis_per_locus=30, rpb=3.0, indel_every=30, indel_vaf=0.1), seed=5)
+    chroms = soa.chroms + ["chr3"]
+    ends, starts = soa.ref_end(), soa.pos.astype(np.int64)
+
+    def brute(s_, sel):
+        keep = np.zeros(s_.n, dtype=bool)
+        e_, st_ = s_.ref_end(), s_.pos.astype(np.int64)
+        for (c, s, e) in sel:
+            if c in s_.chroms:
+                keep |= (s_.ref_id == s_.chroms.index(c)) & (st_ < e) & (e_ > s)
+        return np.flatnonzero(keep)
+
+    loc = ReadLocator(soa, chroms)
+    assert loc.sorted
+    for sel in (ivs, ivs[1:2], ivs[4:], [("chr1", 0, 10)], [("chr1", 1099, 1100)], []):
+        assert np.array_equal(loc.select(sel), brute(soa, sel))
+        assert np.array_equal(reads_for_intervals(soa, sel, chroms), brute(soa, sel))
+    shuffled = soa.select(np.random.default_rng(1).permutation(soa.n))
+    loc2 = ReadLocator(shuffled, chroms)
+    assert not loc2.sorted and np.array_equal(loc2.select(ivs), brute(shuffled, ivs))
+    idxs = list(range(len(ivs)))
+    one = plan_batches(loc, ivs, idxs)
+    assert one == [idxs]
+    small = plan_batches(loc, ivs, idxs, max_loci=120)
+    assert [k for b in small for k in b] == idxs and len(small) >= 3
+    assert all(sum(ivs[k][2] - ivs[k][1] for k in b) <= 120 or len(b) == 1 for b in small)
+    by_reads = plan_batches(loc, ivs, idxs, max_reads=loc.count_upper(*ivs[0]) + 1)
+    assert [k for b in by_reads for k in b] == idxs and len(by_reads) >= 2
