@@ -193,3 +193,20 @@ def test_cfg5_many_loci_many_contigs_shape():
     st = {}
     assert call_loci(soa, ivs, refs, prm, gpus=1, stage_times=st, batch_limits={"max_loci": 20000}) == g_rows
     assert st["batches"] >= 12
+
+
+def test_call_loci_across_all_visible_gpus():
+    """The CLI's multi-GPU path: one host thread and one context per visible GPU (up to 4), BED intervals sharded by
+    estimated depth, rows interleaved back into BED order -- identical to the single-GPU rows.  (On a one-GPU box this runs
+    two shards on the same device.)"""
+    import torch
+    from smcounter_b200.smCounter import call_loci
+    ndev = min(4, torch.cuda.device_count())
+    ivs = [("chr%d" % (1 + k % 3), 1000 + 400 * k, 1000 + 400 * k + 40 + 13 * (k % 5)) for k in range(14)]
+    spec = SynthSpec(umis_per_locus=80, rpb=3.0, snv_every=60, snv_vaf=0.1, indel_every=90, indel_vaf=0.1)
+    prm = VcParams(mtDepth=80, rpb=3.0)
+    soa, refs, _ = make_panel_mp(ivs, spec, seed=6, workers=2)
+    one = call_loci(soa, ivs, refs, prm, gpus=1)
+    devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    many = call_loci(soa.trim_to_targets(ivs), ivs, refs, prm, gpus=len(devices), devices=devices)
+    assert many == one and len(one) == sum(e - s for (_, s, e) in ivs)
