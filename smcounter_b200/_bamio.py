@@ -6,7 +6,7 @@ import os
 
 import numpy as np
 
-from .soa import ReadsSoA, umi_strings_bulk
+from .soa import ReadsSoA
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmc_bamio.so")
@@ -89,9 +89,7 @@ def read_bam_native(path: str, intervals=None, threads: int = 0, trim: bool = Fa
         names = {}
         for i in range(out.n_dict_umis):
             names[(1 << 63) | i] = lib.smc_bam_dict_umi(h, i).decode()
-        packed = np.unique(umi)
-        packed = packed[(packed >> np.uint64(63)) == 0]
-        names.update(zip(packed.tolist(), umi_strings_bulk(packed)))
+        # 2-bit packed codes decode to their barcode on demand (soa.umi_string); only the dictionary-coded ones need a name
         return ReadsSoA(
             ref_id=_arr(out.ref_id, n, np.int32), pos=_arr(out.pos, n, np.int32), flag=_arr(out.flag, n, np.uint16),
             mapq=_arr(out.mapq, n, np.uint8), nm=_arr(out.nm, n, np.int32), l_seq=_arr(out.l_seq, n, np.int32),

@@ -33,9 +33,25 @@ def py2round(x: float, nd: int) -> float:
     """Python-2.7 round(): correctly rounded, exact decimal ties away from zero (Py3 rounds them to even)."""
     r = round(x, nd)
     s = x * (2 * 10 ** nd)
-    if s == int(s):       # possibly an exact halfway case -> decide on the exact binary value
-        return float(Decimal(x).quantize(Decimal(1).scaleb(-nd), rounding=ROUND_HALF_UP))
+    if s == int(s) and int(s) & 1:       # x * 10^nd is an odd multiple of 1/2: possibly an exact halfway case -> decide on the
+        return float(Decimal(x).quantize(Decimal(1).scaleb(-nd), rounding=ROUND_HALF_UP))   # exact binary value
     return r
+
+
+def _f4(num: int, den: int) -> str:
+    """py2str(py2round(1.0 * num / den, 4)): the fraction columns (VAF, VMF, AF_*, UMF_*) of smCounter.py:575-600.  repr() of a
+    value rounded to <= 4 decimals is its Python-2 str() ('%.12g' with '.0' for integral values)."""
+    if num == 0:
+        return "0.0"
+    return repr(py2round(1.0 * num / den, 4))
+
+
+def _f2(x: float) -> str:
+    """py2str(py2round(x, 2)) for the prediction-index columns (below 1e10, so repr() == '%.12g' form)."""
+    if x == 0.0:
+        return "0.0"
+    r = py2round(x, 2)
+    return repr(r) if abs(r) < 1e10 else py2str(r)
 
 
 def py2str(v) -> str:
@@ -162,7 +178,7 @@ def _filter_string(bits, hp_lc):
 
 
 _POOL_JOB = None          # inputs of the forked formatting workers (inherited, never pickled)
-PARALLEL_MIN_ROWS = 4096
+PARALLEL_MIN_ROWS = 60000        # below this the fork + pickle overhead exceeds the ~10 us per row of the inline loop
 
 
 def _format_slice(bounds):
@@ -195,9 +211,8 @@ def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, workers
     import threading
     if workers > 1 and n_rows >= PARALLEL_MIN_ROWS and threading.current_thread() is threading.main_thread() and hasattr(os, "fork"):
         import multiprocessing as mp
-        import numpy as np
         order = np.arange(loci.n) if locus_order is None else np.asarray(locus_order)
-        nchunk = min(n_rows // 512, workers * 4)
+        nchunk = max(2, min(n_rows // 8192, workers * 2))
         cuts = [(n_rows * k) // nchunk for k in range(nchunk + 1)]
         _POOL_JOB = (res, reads, loci, chroms, refs, hpLen, order, hp_flags)
         try:
@@ -213,39 +228,43 @@ def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, workers
         return rows
     namer = AlleleNamer(res, reads, loci, chroms, refs)
     n = loci.n
-    order = range(n) if locus_order is None else locus_order
-    loc, cnt, pi = res.loc, res.cnt, res.pi
+    order = range(n) if locus_order is None else np.asarray(locus_order).tolist()
+    # plain Python lists: element access on numpy arrays costs more than the formatting itself
+    loc, cnt, pi = res.loc[:, :n].tolist(), res.cnt[:, :, :n].tolist(), res.pi[:, :n].tolist()
+    ref_id, pos0, ref_base = loci.ref_id.tolist(), loci.pos0.tolist(), loci.ref_base.tolist()
+    alt_allele, second_allele = res.alt_allele[:n].tolist(), res.second_allele[:n].tolist()
+    fl1, fl2, biallelic = res.fl1[:n].tolist(), res.fl2[:n].tolist(), res.biallelic[:n].tolist()
+    l_cvg, l_allfrag, l_allmt, l_usedfrag, l_usedmt, l_status = (loc[k] for k in (L_CVG, L_ALLFRAG, L_ALLMT, L_USEDFRAG, L_USEDMT, L_STATUS))
+    l_mt3, l_mt5, l_mt7, l_mt10 = (loc[k] for k in (L_MT3, L_MT5, L_MT7, L_MT10))
+    ATGC = (A_A, A_T, A_G, A_C)
+    c_allele = [cnt[a][C_ALLELE] for a in ATGC]
+    c_mt = [cnt[a][C_MT] for a in ATGC]
+    c_strong = [cnt[a][C_STRONG] for a in ATGC]
+    pi_atgc = [pi[a] for a in ATGC]
+    bad_status = ST_NEED_DOWNSAMPLE | ST_UMI_OVERFLOW | ST_BAD_MASK
+    zero_tail = "\t" * 42 + "Zero_Coverage"
     rows = []
     for i in order:
-        i = int(i)
-        chrom = chroms[int(loci.ref_id[i])]
-        pos = str(int(loci.pos0[i]) + 1)
-        origRef = chr(int(loci.ref_base[i]))
-        status = int(loc[L_STATUS, i])
-        if status & (ST_NEED_DOWNSAMPLE | ST_UMI_OVERFLOW | ST_BAD_MASK):
+        chrom = chroms[ref_id[i]]
+        pos = "%d" % (pos0[i] + 1)
+        origRef = chr(ref_base[i])
+        status = l_status[i]
+        if status & bad_status:
             raise RuntimeError("Exception thrown in vc() at location: %s (device status 0x%x)" % ((chrom, pos), status))
-        if status & ST_ZERO_COVERAGE:                                           # smCounter.py:492-494
-            rows.append("\t".join([chrom, pos, origRef] + [""] * 41 + ["Zero_Coverage"]))
+        if status & ST_ZERO_COVERAGE:                                           # smCounter.py:492-494: 3 fields + 41 blanks + tag
+            rows.append(chrom + "\t" + pos + "\t" + origRef + zero_tail)
             continue
-        d0 = int(res.dyn_first[i])
-
-        def C_(a, c):          # counter c of allele reference a
-            return int(cnt[a, c, i]) if a < SMC_NFIXED else int(res.dyn_cnt[a - SMC_NFIXED, c])
-
-        def PI_(a):
-            return float(pi[a, i]) if a < SMC_NFIXED else float(res.dyn_pi[a - SMC_NFIXED])
-
-        cvg, usedMT = int(loc[L_CVG, i]), int(loc[L_USEDMT, i])
-        a1 = int(res.alt_allele[i])
-        origAlt = namer.name(a1)
+        cvg, usedMT = l_cvg[i], l_usedmt[i]
+        a1 = alt_allele[i]
+        origAlt = FIXED_NAMES[a1] if a1 < SMC_NFIXED else namer.name(a1)
         ref, alt, vtype = convert_to_vcf(origRef, origAlt)
-        fltr = _filter_string(int(res.fl1[i]), hp_flags.get((i, 0)))
+        fltr = _filter_string(fl1[i], hp_flags.get((i, 0))) if fl1[i] & F_EVALUATED else ";"
         alt_ref = a1
-        if res.biallelic[i]:                                                    # smCounter.py:555-573
-            a2 = int(res.second_allele[i])
+        if biallelic[i]:                                                        # smCounter.py:555-573
+            a2 = second_allele[i]
             origAlt2 = namer.name(a2)
             ref2, alt2, vtype2 = convert_to_vcf(origRef, origAlt2)
-            fltr2 = _filter_string(int(res.fl2[i]), hp_flags.get((i, 1)))
+            fltr2 = _filter_string(fl2[i], hp_flags.get((i, 1)))
             if fltr == ";" and fltr2 == ";":
                 alt = alt + "," + alt2
                 vtype = vtype.lower() + "," + vtype2.lower()
@@ -253,20 +272,22 @@ def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, workers
                 alt = alt2
                 fltr = fltr2
                 alt_ref = a2
-        acnt = [int(cnt[a, C_ALLELE, i]) for a in (A_A, A_T, A_G, A_C)]
-        mt = [int(cnt[a, C_MT, i]) for a in (A_A, A_T, A_G, A_C)]
-        sm = [int(cnt[a, C_STRONG, i]) for a in (A_A, A_T, A_G, A_C)]
-        outvec = [chrom, pos, ref, alt, vtype, cvg, int(loc[L_ALLFRAG, i]), int(loc[L_ALLMT, i]), int(loc[L_USEDFRAG, i]), usedMT,
-                  py2round(PI_(alt_ref), 2), C_(alt_ref, C_ALLELE), py2round(1.0 * C_(alt_ref, C_ALLELE) / cvg, 4),
-                  C_(alt_ref, C_MT), py2round(1.0 * C_(alt_ref, C_MT) / usedMT, 4), C_(alt_ref, C_STRONG)]
-        outvec.extend(acnt)
-        outvec.extend(py2round(1.0 * c / cvg, 4) for c in acnt)
-        outvec.extend(int(loc[k, i]) for k in (L_MT3, L_MT5, L_MT7, L_MT10))
-        outvec.extend(mt)
-        outvec.extend(py2round(1.0 * m / usedMT, 4) for m in mt)
-        outvec.extend(sm)
-        outvec.extend(py2round(float(pi[a, i]), 2) for a in (A_A, A_T, A_G, A_C))
-        outvec.append(fltr)
-        rows.append("\t".join(py2str(x) for x in outvec))
-        del d0
+        if alt_ref < SMC_NFIXED:          # counters / PI of the reported allele (fixed slot or dynamic-allele row)
+            ca = cnt[alt_ref]
+            v_dp, v_mt, v_sm, v_pi = ca[C_ALLELE][i], ca[C_MT][i], ca[C_STRONG][i], pi[alt_ref][i]
+        else:
+            j = alt_ref - SMC_NFIXED
+            v_dp, v_mt, v_sm = (int(res.dyn_cnt[j, c]) for c in (C_ALLELE, C_MT, C_STRONG))
+            v_pi = float(res.dyn_pi[j])
+        a0, a1c, a2c, a3c = c_allele[0][i], c_allele[1][i], c_allele[2][i], c_allele[3][i]
+        m0, m1, m2, m3 = c_mt[0][i], c_mt[1][i], c_mt[2][i], c_mt[3][i]
+        rows.append("%s\t%s\t%s\t%s\t%s\t%d\t%d\t%d\t%d\t%d\t%s\t%d\t%s\t%d\t%s\t%d\t%d\t%d\t%d\t%d\t%s\t%s\t%s\t%s\t%d\t%d\t%d\t%d\t"
+                    "%d\t%d\t%d\t%d\t%s\t%s\t%s\t%s\t%d\t%d\t%d\t%d\t%s\t%s\t%s\t%s\t%s" % (
+                        chrom, pos, ref, alt, vtype, cvg, l_allfrag[i], l_allmt[i], l_usedfrag[i], usedMT,
+                        _f2(v_pi), v_dp, _f4(v_dp, cvg), v_mt, _f4(v_mt, usedMT), v_sm,
+                        a0, a1c, a2c, a3c, _f4(a0, cvg), _f4(a1c, cvg), _f4(a2c, cvg), _f4(a3c, cvg),
+                        l_mt3[i], l_mt5[i], l_mt7[i], l_mt10[i],
+                        m0, m1, m2, m3, _f4(m0, usedMT), _f4(m1, usedMT), _f4(m2, usedMT), _f4(m3, usedMT),
+                        c_strong[0][i], c_strong[1][i], c_strong[2][i], c_strong[3][i],
+                        _f2(pi_atgc[0][i]), _f2(pi_atgc[1][i]), _f2(pi_atgc[2][i]), _f2(pi_atgc[3][i]), fltr))
     return rows
