@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -21,11 +22,25 @@ inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v;
 inline int32_t rdi32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; }
 
 struct Block { size_t coff, clen; size_t uoff; uint32_t isize; };
+
+// the inflated stream: malloc'ed, NOT zero-filled (every byte is written by inflate before anything reads it)
+struct RawBuf {
+    uint8_t* p = nullptr; size_t n = 0;
+    ~RawBuf() { free(p); }
+    RawBuf() = default;
+    RawBuf(const RawBuf&) = delete;
+    RawBuf& operator=(const RawBuf&) = delete;
+    bool alloc(size_t bytes) { free(p); p = (uint8_t*)malloc(bytes ? bytes : 1); n = p ? bytes : 0; return p != nullptr; }
+    size_t size() const { return n; }
+    const uint8_t& operator[](size_t i) const { return p[i]; }
+    uint8_t& operator[](size_t i) { return p[i]; }
+    const uint8_t* data() const { return p; }
+};
 }  // namespace
 
 struct smc_bam {
     std::string err;
-    std::vector<uint8_t> raw;                 // inflated stream
+    RawBuf raw;                               // inflated stream
     std::vector<std::string> ref_names;
     std::vector<int64_t> ref_lens;
     size_t first_record = 0;
@@ -42,7 +57,7 @@ struct smc_bam {
     int trim = 0;
 };
 
-static int inflate_all(const std::vector<uint8_t>& file, int threads, std::vector<uint8_t>& out, std::string& err) {
+static int inflate_all(const std::vector<uint8_t>& file, int threads, RawBuf& out, std::string& err) {
     std::vector<Block> blocks;
     size_t off = 0, uoff = 0;
     const size_t n = file.size();
@@ -68,7 +83,7 @@ static int inflate_all(const std::vector<uint8_t>& file, int threads, std::vecto
         blocks.push_back(b);
         off += (size_t)bsize + 1;
     }
-    out.resize(uoff);
+    if (!out.alloc(uoff)) { err = "out of memory for the inflated BAM"; return -1; }
     std::atomic<size_t> next(0);
     std::atomic<int> bad(0);
     auto work = [&]() {
@@ -112,7 +127,7 @@ extern "C" int smc_bam_open(const char* path, int threads, smc_bam** out) {
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     h->threads = threads;
     if (inflate_all(file, threads, h->raw, g_open_error) != 0) { delete h; return -1; }
-    const std::vector<uint8_t>& r = h->raw;
+    const RawBuf& r = h->raw;
     if (r.size() < 12 || memcmp(r.data(), "BAM\1", 4) != 0) { g_open_error = "not a BAM file (bad magic)"; delete h; return -1; }
     size_t p = 8 + (size_t)rdi32(&r[4]);
     if (p + 4 > r.size()) { g_open_error = "truncated BAM header"; delete h; return -1; }
@@ -243,7 +258,7 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
                 else merged[rid].push_back(pr);
             }
         }
-    const std::vector<uint8_t>& r = h->raw;
+    const RawBuf& r = h->raw;
     const int threads = std::max(1, h->threads);
     // ---- pass 1: record boundaries
     std::vector<size_t> offs;
@@ -340,37 +355,58 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
     h->mapq.resize(n); h->seq_off.resize(n); h->qual_off.resize(n); h->cigar_off.resize(n); h->umi.resize(n); h->frag_id.resize(n);
     h->dict_umis.clear();
     h->store_lo.assign(trim ? n : 0, 0); h->store_len.assign(trim ? n : 0, 0);
+    // fragment ids = first-appearance numbers of the (barcode, readid) identities.  Threads own disjoint hash partitions:
+    // each walks the records in order, keeps its identities in its own open-addressing table and notes, per record, the
+    // FIRST record of that identity (hits verified on the name bytes).  A prefix sum over "is a first record" then numbers
+    // the identities in order of first appearance -- the same ids the sequential dictionary would hand out.
+    std::vector<uint32_t> first_rec(nrec);
     {
-        size_t cap = 16;
-        while (cap < 2 * n + 2) cap <<= 1;
-        struct Ent { uint64_t h1, h2; uint32_t rec, id; };
-        std::vector<Ent> tab(cap, Ent{0, 0, UINT32_MAX, 0});
-        std::unordered_map<std::string, uint64_t> umi_dict;
-        uint32_t next_id = 0;
-        size_t o = 0;
         auto same_identity = [&](size_t i, size_t j) {
             const RecInfo& A = info[i]; const RecInfo& B = info[j];
             if (A.bc_len != B.bc_len || A.rid_len != B.rid_len) return false;
             const uint8_t* qa = &r[offs[i] + 4 + 32]; const uint8_t* qb = &r[offs[j] + 4 + 32];
             return memcmp(qa + A.bc_off, qb + B.bc_off, A.bc_len) == 0 && memcmp(qa, qb, A.rid_len) == 0;
         };
+        const int P = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n / 65536 + 1));
+        auto part = [&](int t) {
+            struct Ent { uint64_t h1, h2; uint32_t rec; };
+            size_t mine = 0;
+            for (size_t i = 0; i < nrec; ++i) if (info[i].keep && (int)((info[i].h2 >> 40) % (uint64_t)P) == t) ++mine;
+            size_t cap = 16;
+            while (cap < 2 * mine + 2) cap <<= 1;
+            std::vector<Ent> tab(cap, Ent{0, 0, UINT32_MAX});
+            for (size_t i = 0; i < nrec; ++i) {
+                const RecInfo& R = info[i];
+                if (!R.keep || (int)((R.h2 >> 40) % (uint64_t)P) != t) continue;
+                size_t k = (size_t)R.h1 & (cap - 1);
+                for (;;) {
+                    Ent& E = tab[k];
+                    if (E.rec == UINT32_MAX) { E = Ent{R.h1, R.h2, (uint32_t)i}; first_rec[i] = (uint32_t)i; break; }
+                    if (E.h1 == R.h1 && E.h2 == R.h2 && same_identity(E.rec, i)) { first_rec[i] = E.rec; break; }
+                    k = (k + 1) & (cap - 1);
+                }
+            }
+        };
+        std::vector<std::thread> ts;
+        for (int t = 1; t < P; ++t) ts.emplace_back(part, t);
+        part(0);
+        for (auto& t : ts) t.join();
+    }
+    {
+        std::vector<uint32_t> id_of(nrec);                                       // id of the identity whose first record is i
+        std::unordered_map<std::string, uint64_t> umi_dict;
+        uint32_t next_id = 0;
+        size_t o = 0;
         for (size_t i = 0; i < nrec; ++i) {
             RecInfo& R = info[i];
             if (!R.keep) continue;
             const uint8_t* b = &r[offs[i] + 4];
-            const int32_t l_seq = rdi32(b + 16);
             const uint16_t n_cig = rd16(b + 12);
             slot[i] = (uint32_t)o;
             h->seq_off[o] = (int64_t)seq_tot; h->qual_off[o] = (int64_t)qual_tot; h->cigar_off[o] = (int64_t)cig_tot;
-            (void)l_seq;
             seq_tot += ((size_t)R.store_len + 1) / 2; qual_tot += (size_t)R.store_len; cig_tot += n_cig;
-            size_t k = (size_t)R.h1 & (cap - 1);
-            for (;;) {
-                Ent& E = tab[k];
-                if (E.rec == UINT32_MAX) { E = Ent{R.h1, R.h2, (uint32_t)i, next_id}; h->frag_id[o] = next_id++; break; }
-                if (E.h1 == R.h1 && E.h2 == R.h2 && same_identity(E.rec, i)) { h->frag_id[o] = E.id; break; }
-                k = (k + 1) & (cap - 1);
-            }
+            if (first_rec[i] == (uint32_t)i) id_of[i] = next_id++;
+            h->frag_id[o] = id_of[first_rec[i]];
             if (R.code == 0) {                                                  // barcode not packable: dictionary code
                 const std::string bc(reinterpret_cast<const char*>(b + 32) + R.bc_off, R.bc_len);
                 auto it = umi_dict.find(bc);
