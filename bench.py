@@ -434,6 +434,10 @@ def main():
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                              "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_event": ALGO_BYTES_PER_EVENT,
                              "ms_per_launch": 1000.0 * kp_avg_s, "traffic": traffic,
+                             "whole_step": {"what": "the same 35 B x pileup events over the WHOLE device step (read sort, prep, tile events, "
+                                                    "both pileup kernels, ALT / filters / Fisher) of rank 0",
+                                            "achieved": algo_bytes / ((dev_ms / args.steps) / 1000.0) / 1e9 if dev_ms > 0 else 0.0,
+                                            "frac": algo_bytes / ((dev_ms / args.steps) / 1000.0) / 1e9 / peak if dev_ms > 0 and peak else None},
                              "events_per_s": float(tms["n_pileup_events"]) / kp_avg_s if kp_avg_s > 0 else 0.0},
                 "clocks": sampler.summary(), "n_dyn_alleles_rank0": int(n_dyn), "n_fisher_rank0": int(tms["n_fisher"])}
     caller.close()

@@ -138,7 +138,7 @@ def subset_loci(loci: Loci, intervals, chroms):
 def plan_shards(reads: ReadsSoA, intervals, chroms, n_shards: int):
     """[(interval indices, estimated events)] per shard; intervals keep their BED order inside a shard."""
     if n_shards <= 1:
-        return [(list(range(len(intervals))), float(estimate_interval_events(reads, intervals, chroms).sum()))]
+        return [(list(range(len(intervals))), 0.0)]          # nothing to balance: skip the estimate
     w = estimate_interval_events(reads, intervals, chroms)
     shard, load = assign_intervals(w, n_shards)
     return [([int(k) for k in np.flatnonzero(shard == g)], float(load[g])) for g in range(n_shards)]

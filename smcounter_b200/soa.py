@@ -185,7 +185,14 @@ class ReadsSoA:
         return True
 
     def ref_end(self) -> np.ndarray:
-        """0-based exclusive reference end of every read (host-side helper for sharding)."""
+        """0-based exclusive reference end of every read (host-side helper for sharding); memoised per instance."""
+        cached = self.__dict__.get("_ref_end")
+        if cached is not None and len(cached) == self.n:
+            return cached
+        self.__dict__["_ref_end"] = out = self._ref_end_compute()
+        return out
+
+    def _ref_end_compute(self) -> np.ndarray:
         ops = self.cigar & 0xF
         lens = (self.cigar >> 4).astype(np.int64)
         consumes = np.isin(ops, (0, 2, 3, 7, 8))
