@@ -188,11 +188,35 @@ __global__ void k_scatter_idx(const int64_t* locus, int64_t n, int32_t* idx) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) idx[locus[i]] = (int32_t)i;
 }
-__global__ void k_dyn_collect(const unsigned long long* dkey, uint32_t cap, uint64_t* lk, uint32_t* lv, uint32_t* count) {
+// Dynamic-allele rows, grouped by locus and ordered by key inside a locus: count per locus, scan, place, and a tiny
+// insertion sort per locus (a locus has a handful of such alleles) -- 7 launches instead of a 6-pass radix sort of a few
+// thousand keys that was pure launch latency.
+__global__ void k_dyn_count(const unsigned long long* __restrict__ dkey, uint32_t cap, uint32_t* __restrict__ cnt) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cap) return;
     unsigned long long k = dkey[i];
-    if (k != DYN_EMPTY) { uint32_t o = atomicAdd(count, 1u); lk[o] = k; lv[o] = i; }
+    if (k != DYN_EMPTY) atomicAdd(&cnt[(uint32_t)(k >> DYN_LOCUS_SHIFT)], 1u);
+}
+__global__ void k_dyn_place(const unsigned long long* __restrict__ dkey, uint32_t cap, const uint32_t* __restrict__ first,
+                            uint32_t* __restrict__ cursor, uint64_t* __restrict__ lk, uint32_t* __restrict__ lv) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    unsigned long long k = dkey[i];
+    if (k == DYN_EMPTY) return;
+    const uint32_t L = (uint32_t)(k >> DYN_LOCUS_SHIFT);
+    const uint32_t o = first[L] + atomicAdd(&cursor[L], 1u);
+    lk[o] = k; lv[o] = i;
+}
+__global__ void k_dyn_sort_local(const uint32_t* __restrict__ first, int64_t n_loci, uint64_t* __restrict__ lk, uint32_t* __restrict__ lv) {
+    int64_t L = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (L >= n_loci) return;
+    const uint32_t a = first[L], b = first[L + 1];
+    for (uint32_t i = a + 1; i < b; ++i) {
+        const uint64_t k = lk[i]; const uint32_t v = lv[i];
+        uint32_t j = i;
+        while (j > a && lk[j - 1] > k) { lk[j] = lk[j - 1]; lv[j] = lv[j - 1]; --j; }
+        lk[j] = k; lv[j] = v;
+    }
 }
 __global__ void k_dyn_gather(const uint64_t* lk, const uint32_t* lv, int64_t n, const int32_t* dcnt, const unsigned long long* dlimb,
                              const uint8_t* diskey, const uint32_t* drep_read, const int32_t* drep_qpos, const int32_t* dlen,
@@ -207,11 +231,6 @@ __global__ void k_dyn_gather(const uint64_t* lk, const uint32_t* lv, int64_t n, 
     for (int t = 0; t < 3; ++t) s_limb[j * 3 + t] = dlimb[(size_t)e * 3 + t];
     s_iskey[j] = diskey[e];
     s_rep_read[j] = drep_read[e]; s_rep_qpos[j] = drep_qpos[e]; s_len[j] = dlen[e];
-}
-__global__ void k_dyn_first(const unsigned long long* s_key, int64_t n_dyn, int64_t n_loci, uint32_t* first) {
-    int64_t L = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (L > n_loci) return;
-    first[L] = (uint32_t)lower_bound_u64((const uint64_t*)s_key, n_dyn, (uint64_t)L << DYN_LOCUS_SHIFT);
 }
 __global__ void k_sum_cvg(const int32_t* cvg, int64_t n, unsigned long long* out) {
     unsigned long long s = 0;
@@ -705,25 +724,24 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
     CK(ctx->d_s_key.ensure(ndz * 8)); CK(ctx->d_s_cnt.ensure(ndz * SMC_NCNT * 4)); CK(ctx->d_s_limb.ensure(ndz * 24));
     CK(ctx->d_s_iskey.ensure(ndz)); CK(ctx->d_s_pi.ensure(ndz * 8)); CK(ctx->d_s_rep_read.ensure(ndz * 4));
     CK(ctx->d_s_rep_qpos.ensure(ndz * 4)); CK(ctx->d_s_len.ensure(ndz * 4));
+    CK(cudaMemsetAsync(ctx->d_dyn_first.p, 0, (nlz + 2) * 4, ctx->st));
     if (nd > 0) {
-        CK(ctx->d_lk0.ensure(ndz * 8)); CK(ctx->d_lk1.ensure(ndz * 8)); CK(ctx->d_lv0.ensure(ndz * 4)); CK(ctx->d_lv1.ensure(ndz * 4));
-        CK(cudaMemsetAsync(small + 6, 0, 4, ctx->st));
-        LAUNCH(k_dyn_collect, nblk(ctx->dyn_cap, 256), 256, 0, ctx->d_dkey.as<unsigned long long>(), ctx->dyn_cap, ctx->d_lk0.as<uint64_t>(),
-               ctx->d_lv0.as<uint32_t>(), small + 6);
-        CK(ctx->d_hist.ensure(radix_hist_words(nd) * 4 + 1024));
-        CK(ctx->d_scan.ensure((size_t)radix_scan_words(nd) * 4 + 1024));
-        int locus_bits = 1;                                            // key = locus | kind | site | payload: only the locus bits in use
-        while ((1ll << locus_bits) < nl) ++locus_bits;
-        int res = radix_sort_bits(ctx->d_lk0.as<uint64_t>(), ctx->d_lv0.as<uint32_t>(), ctx->d_lk1.as<uint64_t>(), ctx->d_lv1.as<uint32_t>(), nd,
-                                  0, DYN_LOCUS_SHIFT + locus_bits, ctx->d_hist.as<uint32_t>(), ctx->d_scan.as<uint32_t>(), ctx->st);
-        const uint64_t* lk = res ? ctx->d_lk1.as<uint64_t>() : ctx->d_lk0.as<uint64_t>();
-        const uint32_t* lv = res ? ctx->d_lv1.as<uint32_t>() : ctx->d_lv0.as<uint32_t>();
-        LAUNCH(k_dyn_gather, nblk(nd, 128), 128, 0, lk, lv, nd, ctx->d_dcnt.as<int32_t>(), ctx->d_dlimb.as<unsigned long long>(),
+        CK(ctx->d_lk0.ensure(ndz * 8)); CK(ctx->d_lv0.ensure(ndz * 4)); CK(ctx->d_lv1.ensure((nlz + 2) * 4));
+        CK(ctx->d_scan.ensure((size_t)scan_scratch_words((int64_t)nl + 2) * 4 + 1024));
+        uint32_t* first = ctx->d_dyn_first.as<uint32_t>();
+        uint32_t* cursor = ctx->d_lv1.as<uint32_t>();
+        CK(cudaMemsetAsync(cursor, 0, (nlz + 2) * 4, ctx->st));
+        LAUNCH(k_dyn_count, nblk(ctx->dyn_cap, 256), 256, 0, ctx->d_dkey.as<unsigned long long>(), ctx->dyn_cap, first);
+        exclusive_scan_u32(first, first, nl + 1, ctx->d_scan.as<uint32_t>(), nullptr, ctx->st);
+        LAUNCH(k_dyn_place, nblk(ctx->dyn_cap, 256), 256, 0, ctx->d_dkey.as<unsigned long long>(), ctx->dyn_cap, first, cursor,
+               ctx->d_lk0.as<uint64_t>(), ctx->d_lv0.as<uint32_t>());
+        LAUNCH(k_dyn_sort_local, nblk(nl, 256), 256, 0, first, nl, ctx->d_lk0.as<uint64_t>(), ctx->d_lv0.as<uint32_t>());
+        LAUNCH(k_dyn_gather, nblk(nd, 128), 128, 0, ctx->d_lk0.as<uint64_t>(), ctx->d_lv0.as<uint32_t>(), nd, ctx->d_dcnt.as<int32_t>(),
+               ctx->d_dlimb.as<unsigned long long>(),
                ctx->d_diskey.as<uint8_t>(), ctx->d_drep_read.as<uint32_t>(), ctx->d_drep_qpos.as<int32_t>(), ctx->d_dlen.as<int32_t>(),
                ctx->d_s_key.as<unsigned long long>(), ctx->d_s_cnt.as<int32_t>(), ctx->d_s_limb.as<unsigned long long>(),
                ctx->d_s_iskey.as<uint8_t>(), ctx->d_s_rep_read.as<uint32_t>(), ctx->d_s_rep_qpos.as<int32_t>(), ctx->d_s_len.as<int32_t>());
     }
-    LAUNCH(k_dyn_first, nblk(nl + 1, 256), 256, 0, ctx->d_s_key.as<unsigned long long>(), nd, nl, ctx->d_dyn_first.as<uint32_t>());
     // ---------------- K4
     uint32_t n_tasks_h = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
