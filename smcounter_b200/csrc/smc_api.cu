@@ -149,25 +149,27 @@ __global__ void k_umi_slots(const uint64_t* __restrict__ umi, const uint32_t* __
     key[i] = ((uint64_t)h << frag_bits) | (uint64_t)frag[i];
     val[i] = (uint32_t)i;
 }
-__global__ void k_heads(const uint64_t* umi, const uint32_t* frag, const uint32_t* perm, int64_t n, uint32_t* uhead, uint32_t* fhead) {
+// reads in sorted order: a new barcode starts where the slot part of the key changes, a new fragment where the key changes
+__global__ void k_heads(const uint64_t* __restrict__ key_sorted, int frag_bits, int64_t n, uint32_t* uhead, uint32_t* fhead) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    uint32_t r = perm[s];
     bool uh = true, fh = true;
     if (s > 0) {
-        uint32_t q = perm[s - 1];
-        uh = umi[r] != umi[q];
-        fh = uh || frag[r] != frag[q];
+        const uint64_t a = key_sorted[s], b = key_sorted[s - 1];
+        uh = (a >> frag_bits) != (b >> frag_bits);
+        fh = a != b;
     }
     uhead[s] = uh; fhead[s] = fh;
 }
 __global__ void k_ranks(const uint32_t* uhead, const uint32_t* fhead, const uint32_t* uex, const uint32_t* fex, const uint64_t* umi,
-                        const uint32_t* perm, int64_t n, uint32_t* urank, uint32_t* frank, uint64_t* umi_of_urank) {
+                        const uint32_t* perm, int64_t n, uint32_t* urank, uint32_t* frank, uint64_t* umi_of_urank, uint32_t* inv) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     uint32_t ur = uex[s] + uhead[s] - 1, fr = fex[s] + fhead[s] - 1;
     urank[s] = ur; frank[s] = fr;
-    if (uhead[s]) umi_of_urank[ur] = umi[perm[s]];
+    const uint32_t r = perm[s];
+    inv[r] = (uint32_t)s;                                   // sorted position of read r (k_read_prep runs in BAM order)
+    if (uhead[s]) umi_of_urank[ur] = umi[r];
 }
 __global__ void k_tile_offsets(const uint64_t* ev_key, int64_t ne, uint32_t n_tiles, uint32_t* tile_off) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -486,18 +488,18 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         CK(ctx->d_umi_of_urank.ensure((size_t)n * 8));
         uint32_t* uhead = ctx->d_flags32a.as<uint32_t>(); uint32_t* fhead = ctx->d_flags32b.as<uint32_t>();
         uint32_t* uex = ctx->d_urank.as<uint32_t>(); uint32_t* fex = ctx->d_frank.as<uint32_t>();
-        LAUNCH(k_heads, nblk(n, 256), 256, 0, ctx->d_umi.as<uint64_t>(), ctx->d_frag.as<uint32_t>(), perm, n, uhead, fhead);
+        LAUNCH(k_heads, nblk(n, 256), 256, 0, k0, frag_bits, n, uhead, fhead);
         exclusive_scan_u32(uhead, uex, n, ctx->d_scan.as<uint32_t>(), small + 10, ctx->st);
         exclusive_scan_u32(fhead, fex, n, ctx->d_scan.as<uint32_t>(), nullptr, ctx->st);
         LAUNCH(k_ranks, nblk(n, 256), 256, 0, uhead, fhead, uex, fex, ctx->d_umi.as<uint64_t>(), perm, n, uex, fex,
-               ctx->d_umi_of_urank.as<uint64_t>());
-        // ---------------- K1: per-read records in srank order
+               ctx->d_umi_of_urank.as<uint64_t>(), v1);
+        // ---------------- K1: per-read records, computed in BAM order (coalesced inputs) and stored at their sorted position
         CK(ctx->d_recs.ensure((size_t)n * sizeof(ReadRec))); CK(ctx->d_grec.ensure((size_t)n * sizeof(GRec)));
         CK(ctx->d_ntiles.ensure((size_t)(n + 1) * 4));
         CK(ctx->d_evoff.ensure((size_t)(n + 1) * 4));
         CK(cudaMemsetAsync(small + 4, 0, 32, ctx->st));
         PrepArgs P{};
-        P.n_reads = n; P.perm = perm; P.urank = uex; P.frank = fex;
+        P.n_reads = n; P.inv = v1; P.urank = uex; P.frank = fex;
         P.ref_id = ctx->d_ref_id.as<int32_t>(); P.pos = ctx->d_pos.as<int32_t>(); P.flag = ctx->d_flag.as<uint16_t>();
         P.mapq = ctx->d_mapq.as<uint8_t>(); P.nm = ctx->d_nm.as<int32_t>(); P.l_seq = ctx->d_lseq.as<int32_t>();
         P.seq_off = ctx->d_seq_off.as<int64_t>(); P.qual_off = ctx->d_qual_off.as<int64_t>(); P.cigar_off = ctx->d_cig_off.as<int64_t>();

@@ -16,7 +16,7 @@
 #include "smc_common.cuh"
 
 // ------------------------------------------------------------------------------------------------------------
-// K1: per-read preparation, in srank order (thread s handles read perm[s]).
+// K1: per-read preparation: thread r handles read r (inputs coalesced) and writes its records at the read's sorted position.
 // Restates smCounter.py:327-356 (mapq, NM, nIndel, leftSP, mismatchPer100b) and the htslib column membership
 // pos <= p < reference_end, once per read instead of once per pileup event.
 // ------------------------------------------------------------------------------------------------------------
@@ -39,7 +39,7 @@ static_assert(sizeof(GRec) == 32, "GRec must be 32 bytes");
 
 struct PrepArgs {
     int64_t n_reads;
-    const uint32_t* perm;         // srank -> read index
+    const uint32_t* inv;          // read index -> srank (sorted position)
     const uint32_t* urank;        // per srank
     const uint32_t* frank;
     const int32_t* ref_id; const int32_t* pos; const uint16_t* flag; const uint8_t* mapq; const int32_t* nm;
@@ -58,9 +58,9 @@ struct PrepArgs {
 #define GF_BAD_STORE  8u     // stored window (store_lo / store_len) malformed or not covering every target base of the read
 
 __global__ void __launch_bounds__(256) k_read_prep(PrepArgs A) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= A.n_reads) return;
-    uint32_t r = A.perm[s];
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // BAM order in (coalesced), sorted position out
+    if (r >= A.n_reads) return;
+    const int64_t s = A.inv[r];
     uint32_t ncig = A.n_cigar[r];
     int64_t co = A.cigar_off[r];
     int32_t lseq = A.l_seq[r];
