@@ -74,7 +74,7 @@ struct smc_ctx {
     // scratch
     DevBuf d_k0, d_k1, d_v0, d_v1, d_hist, d_scan, d_flags32a, d_flags32b, d_urank, d_frank, d_umi_of_urank, d_recs, d_ntiles,
         d_evoff, d_ek0, d_ek1, d_ev0, d_ev1, d_tile_off, d_unit_cnt, d_unit_off, d_small,
-        d_grec, d_ev_flags, d_unit_eb, d_unit_ee, d_unit_tile, d_unit_nfrag, d_codes, d_frag_first, d_umi_urank, d_umi_table;
+        d_grec, d_unit_eb, d_unit_ee, d_unit_tile, d_unit_nfrag, d_codes, d_frag_first, d_umi_urank, d_umi_table;
     uint32_t code_mult = 1;                     // fragment-code storage per tile event (1, or 3 = worst case after GF_CODE_FULL)
     uint32_t n_units_cap = 0;
     // per-locus accumulators / outputs
@@ -103,7 +103,7 @@ static std::vector<DevBuf*> all_bufs(smc_ctx* ctx) {
                       &ctx->d_bqtab, &ctx->d_pcrtab, &ctx->d_k0, &ctx->d_k1, &ctx->d_v0, &ctx->d_v1, &ctx->d_hist, &ctx->d_scan,
                       &ctx->d_flags32a, &ctx->d_flags32b, &ctx->d_urank, &ctx->d_frank, &ctx->d_umi_of_urank, &ctx->d_recs, &ctx->d_ntiles,
                       &ctx->d_evoff, &ctx->d_ek0, &ctx->d_ek1, &ctx->d_ev0, &ctx->d_ev1, &ctx->d_tile_off, &ctx->d_unit_cnt,
-                      &ctx->d_unit_off, &ctx->d_small, &ctx->d_grec, &ctx->d_ev_flags, &ctx->d_unit_eb, &ctx->d_unit_ee, &ctx->d_unit_tile,
+                      &ctx->d_unit_off, &ctx->d_small, &ctx->d_grec, &ctx->d_unit_eb, &ctx->d_unit_ee, &ctx->d_unit_tile,
                       &ctx->d_unit_nfrag, &ctx->d_codes, &ctx->d_frag_first, &ctx->d_umi_urank, &ctx->d_loc, &ctx->d_cnt, &ctx->d_limb, &ctx->d_pi, &ctx->d_max, &ctx->d_second,
                       &ctx->d_alt, &ctx->d_altpi, &ctx->d_secondpi, &ctx->d_fl1, &ctx->d_fl2, &ctx->d_bial, &ctx->d_fp, &ctx->d_for,
                       &ctx->d_dkey, &ctx->d_drep_read, &ctx->d_drep_qpos, &ctx->d_dlen, &ctx->d_dcnt, &ctx->d_dlimb, &ctx->d_diskey,
@@ -554,9 +554,6 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         ev_key_sorted = res ? ctx->d_ek1.as<uint64_t>() : ctx->d_ek0.as<uint64_t>();
         ev_read_sorted = res ? ctx->d_ev1.as<uint32_t>() : ctx->d_ev0.as<uint32_t>();
         LAUNCH(k_tile_offsets, nblk((int64_t)n_tiles + 1, 256), 256, 0, ev_key_sorted, NE, n_tiles, ctx->d_tile_off.as<uint32_t>());
-        CK(ctx->d_ev_flags.ensure((size_t)NE));
-        LAUNCH(k_event_flags, nblk(NE, 256), 256, 0, ev_key_sorted, ev_read_sorted, ctx->d_urank.as<uint32_t>(), ctx->d_frank.as<uint32_t>(),
-               ctx->d_grec.as<GRec>(), NE, ctx->d_ev_flags.as<uint8_t>());
     } else {
         CK(cudaMemsetAsync(ctx->d_tile_off.p, 0, (size_t)(n_tiles + 2) * 4, ctx->st));
         CK(ctx->d_scan.ensure((size_t)scan_scratch_words((int64_t)n_tiles + 2) * 4 + 1024));
@@ -571,7 +568,7 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         CK(ctx->d_unit_eb.ensure((size_t)max_units * 4)); CK(ctx->d_unit_ee.ensure((size_t)max_units * 4));
         CK(ctx->d_unit_tile.ensure((size_t)max_units * 4)); CK(ctx->d_unit_nfrag.ensure((size_t)max_units * 4));
         LAUNCH(k_unit_bounds, nblk(max_units, 256), 256, 0, ctx->d_tile_off.as<uint32_t>(), ctx->d_unit_off.as<uint32_t>(), n_tiles, ctx->chunk,
-               ctx->d_ev_flags.as<uint8_t>(), ctx->d_unit_eb.as<uint32_t>(), ctx->d_unit_ee.as<uint32_t>(), ctx->d_unit_tile.as<uint32_t>(),
+               ev_read_sorted, ctx->d_urank.as<uint32_t>(), ctx->d_unit_eb.as<uint32_t>(), ctx->d_unit_ee.as<uint32_t>(), ctx->d_unit_tile.as<uint32_t>(),
                ctx->n_units_cap);
     }
     ctx->tm.n_tile_events = NE;
@@ -623,7 +620,7 @@ static int ensure_code_storage(smc_ctx* ctx, bool list, bool need_uranks) {
 static void fill_kargs(smc_ctx* ctx, KAArgs& A, KBArgs& B, bool list, bool need_uranks) {
     A = KAArgs{}; B = KBArgs{};
     A.grec = ctx->d_grec.as<GRec>(); A.recs = ctx->d_recs.as<ReadRec>(); A.ev_read = ctx->ev_read_sorted;
-    A.ev_flags = ctx->d_ev_flags.as<uint8_t>(); A.urank_s = ctx->d_urank.as<uint32_t>();
+    A.urank_s = ctx->d_urank.as<uint32_t>(); A.frank_s = ctx->d_frank.as<uint32_t>();
     A.unit_eb = ctx->d_unit_eb.as<uint32_t>(); A.unit_ee = ctx->d_unit_ee.as<uint32_t>(); A.unit_tile = ctx->d_unit_tile.as<uint32_t>();
     A.n_units = ctx->n_units_cap; A.code_mult = ctx->code_mult;
     A.loci_pos = ctx->d_loci_pos.as<int32_t>(); A.n_loci = ctx->n_loci;

@@ -162,31 +162,16 @@ k_expand(const ReadRec* __restrict__ recs, const uint32_t* __restrict__ ev_off, 
     for (uint32_t t = t0; t <= t1; ++t, ++o) { ev_key[o] = t; ev_val[o] = (uint32_t)s; }
 }
 
-// Per tile event (tile-sorted): bit 0 a new fragment starts here, bit 1 a new barcode starts here (both set at the first
-// event of a tile), bit 2 the read is one plain aligned run.
+// Per tile event (tile-sorted), derived by k_gather while it stages a batch: bit 0 a new fragment starts here, bit 1 a new
+// barcode starts here (both set at the first event of a unit), bit 2 the read is one plain aligned run.
 #define EF_FRAG   1u
 #define EF_UMI    2u
 #define EF_SIMPLE 4u
-__global__ void __launch_bounds__(256)
-k_event_flags(const uint64_t* __restrict__ ev_key, const uint32_t* __restrict__ ev_read, const uint32_t* __restrict__ urank,
-              const uint32_t* __restrict__ frank, const GRec* __restrict__ grec, int64_t ne, uint8_t* __restrict__ flags) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= ne) return;
-    const uint32_t sr = ev_read[e];
-    bool ub = true, fb = true;
-    if (e > 0 && ev_key[e - 1] == ev_key[e]) {
-        const uint32_t pr = ev_read[e - 1];
-        ub = urank[sr] != urank[pr];
-        fb = ub || frank[sr] != frank[pr];
-    }
-    flags[e] = (uint8_t)((fb ? EF_FRAG : 0u) | (ub ? EF_UMI : 0u) | ((__ldg(&grec[sr].meta) & RM_SIMPLE) ? EF_SIMPLE : 0u));
-}
-
 // Units: a tile's events are cut every `chunk` events, moved forward to the next barcode boundary.  One warp per unit.
 __global__ void __launch_bounds__(256)
 k_unit_bounds(const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ unit_off, uint32_t n_tiles, uint32_t chunk,
-              const uint8_t* __restrict__ flags, uint32_t* __restrict__ unit_eb, uint32_t* __restrict__ unit_ee,
-              uint32_t* __restrict__ unit_tile, uint32_t n_units_cap) {
+              const uint32_t* __restrict__ ev_read, const uint32_t* __restrict__ urank, uint32_t* __restrict__ unit_eb,
+              uint32_t* __restrict__ unit_ee, uint32_t* __restrict__ unit_tile, uint32_t n_units_cap) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units_cap) return;
     if (u >= unit_off[n_tiles]) { unit_eb[u] = unit_ee[u] = 0; unit_tile[u] = 0; return; }
@@ -196,7 +181,7 @@ k_unit_bounds(const uint32_t* __restrict__ tile_off, const uint32_t* __restrict_
     auto boundary = [&](uint64_t x64) -> uint32_t {
         if (x64 >= te) return te;
         uint32_t x = (uint32_t)x64;
-        while (x < te && !(flags[x] & EF_UMI)) ++x;
+        while (x < te && urank[ev_read[x]] == urank[ev_read[x - 1]]) ++x;       // x > tb here: forward to the next barcode start
         return x;
     };
     const uint32_t eb = c == 0 ? tb : boundary((uint64_t)tb + (uint64_t)c * chunk);
@@ -343,7 +328,7 @@ __device__ __noinline__ uint32_t dyn_lookup(DynTab T, unsigned long long key, ui
 #define EC_PLE      (1u << 17)    // R2 and distance to the primer end <= primerDist
 
 struct KAArgs {
-    const GRec* grec; const ReadRec* recs; const uint32_t* ev_read; const uint8_t* ev_flags; const uint32_t* urank_s;
+    const GRec* grec; const ReadRec* recs; const uint32_t* ev_read; const uint32_t* urank_s; const uint32_t* frank_s;
     const uint32_t* unit_eb; const uint32_t* unit_ee; const uint32_t* unit_tile;
     uint32_t unit0, n_units;      // this launch covers units [unit0, n_units)
     uint32_t code_mult;
@@ -581,6 +566,7 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
     uint32_t fs = 0, f_mid = 0, f_bq = 0, f_first = 0xffffffffu;
     // warp-uniform
     uint32_t fcount = 0, ext = 0, umi_k = 0, since_flush = 0;
+    uint32_t carry_ur = 0xffffffffu, carry_fr = 0xffffffffu;          // ranks of the previous batch's last event
     bool open = false, umi_first = true, dead = false;
     uint16_t* const cst16 = reinterpret_cast<uint16_t*>(cst) + 2 * lane;
 
@@ -642,22 +628,30 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
     for (uint32_t base = eb; base < ee; base += 32) {
         const int nb = (int)min(32u, ee - base);
         // ---------------- stage
-        uint32_t fl8 = EF_SIMPLE;                                        // slots past the end: an empty simple read, no boundary
+        // boundaries from the dense barcode / fragment ranks of consecutive events (a unit always starts at a barcode start);
+        // slots past the end: an empty simple read, no boundary
+        bool ub = false, fb = false, simple = true;
         {
-            uint4 g0 = make_uint4(0u, 0u, 0u, 0u), g1 = g0; uint32_t sr = 0;
+            uint4 g0 = make_uint4(0u, 0u, 0u, 0u), g1 = g0; uint32_t sr = 0, ur = 0xffffffffu, fr = 0xffffffffu;
             if (lane < nb) {
                 sr = __ldg(&A.ev_read[base + lane]);
-                fl8 = __ldg(&A.ev_flags[base + lane]);
+                ur = __ldg(&A.urank_s[sr]); fr = __ldg(&A.frank_s[sr]);
                 const uint4* src = reinterpret_cast<const uint4*>(&A.grec[sr]);
                 g0 = __ldg(src); g1 = __ldg(src + 1);
+                simple = g0.w & RM_SIMPLE;
             }
+            uint32_t pur = __shfl_up_sync(FULL_MASK, ur, 1), pfr = __shfl_up_sync(FULL_MASK, fr, 1);
+            if (lane == 0) { pur = carry_ur; pfr = carry_fr; }
+            ub = lane < nb && ur != pur;
+            fb = lane < nb && (ub || fr != pfr);
+            carry_ur = __shfl_sync(FULL_MASK, ur, nb - 1); carry_fr = __shfl_sync(FULL_MASK, fr, nb - 1);
             uint4* dst = reinterpret_cast<uint4*>(ws + lane * 8);
             dst[0] = g0; dst[1] = g1;
             srank_s[lane] = sr;
         }
-        const uint32_t fragmask = __ballot_sync(FULL_MASK, fl8 & EF_FRAG);
-        const uint32_t umimask = __ballot_sync(FULL_MASK, fl8 & EF_UMI);
-        const uint32_t simplemask = __ballot_sync(FULL_MASK, fl8 & EF_SIMPLE);
+        const uint32_t fragmask = __ballot_sync(FULL_MASK, fb);
+        const uint32_t umimask = __ballot_sync(FULL_MASK, ub);
+        const uint32_t simplemask = __ballot_sync(FULL_MASK, simple);
         if (since_flush + 32u > 255u) { flush_gather_regs(A.cnt, nl, L, lane_valid, R); since_flush = 0; }
         since_flush += 32u;
         __syncwarp();
