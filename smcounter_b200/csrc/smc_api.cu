@@ -46,6 +46,19 @@ struct DevBuf {
 
 #define PCR_NMAX 192
 
+// words of the small device scratch block (smc_ctx::d_small) the kernels report through
+enum SmallWord {
+    SW_FRAG_OR = 0,          // u64: OR of all fragment ids (range check)
+    SW_N_TILE_EVENTS = 4,    // total of the tile-event scan
+    SW_GFLAGS = 5,           // GF_* bits raised by the kernels
+    SW_DYN_COUNT = 6,        // entries of the dynamic-allele table
+    SW_N_TASKS = 7,          // Fisher tasks emitted by k_call
+    SW_CVG_SUM = 8,          // u64: sum of cvg over the loci (= pileup read-events)
+    SW_N_UMI = 10,           // distinct barcodes
+    SW_PIPE_BLOCKED = 16,    // [SMC_PIPE_MAX]: first unit that has to wait for chunk c + 1
+    SW_PACK_TOTALS = 40      // [3]: bytes / words of packed bases, qualities, CIGARs
+};
+
 struct smc_ctx {
     int device = 0;
     smc_params prm{};
@@ -382,7 +395,7 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
             CK(ctx->d_scan.ensure((size_t)scan_scratch_words(n + 1) * 4 + 1024));
             LAUNCH(k_pack_len, nblk(n, 256), 256, 0, ctx->d_lseq.as<int32_t>(), ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr,
                    ctx->d_ncig.as<uint16_t>(), n, kind, ctx->d_v0.as<uint32_t>());
-            exclusive_scan_u32(ctx->d_v0.as<uint32_t>(), ctx->d_v0.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + 40 + kind, ctx->st);
+            exclusive_scan_u32(ctx->d_v0.as<uint32_t>(), ctx->d_v0.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + SW_PACK_TOTALS + kind, ctx->st);
             LAUNCH(k_widen_u32, nblk(n, 256), 256, 0, ctx->d_v0.as<uint32_t>(), n, dev_off[kind]->as<int64_t>());
         }
     }
@@ -473,8 +486,8 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         CK(cudaMemsetAsync(ctx->d_umi_table.p, 0xff, ((size_t)1 << slot_bits) * 8, ctx->st));
         {
             unsigned long long init[2] = {0ull, ~0ull};
-            CK(cudaMemcpyAsync(small, init, 16, cudaMemcpyHostToDevice, ctx->st));
-            LAUNCH(k_or_and_u32, std::min<unsigned>(nblk(n, 256), 1184u), 256, 0, ctx->d_frag.as<uint32_t>(), n, (unsigned long long*)small);
+            CK(cudaMemcpyAsync(small + SW_FRAG_OR, init, 16, cudaMemcpyHostToDevice, ctx->st));
+            LAUNCH(k_or_and_u32, std::min<unsigned>(nblk(n, 256), 1184u), 256, 0, ctx->d_frag.as<uint32_t>(), n, (unsigned long long*)(small + SW_FRAG_OR));
         }
         LAUNCH(k_umi_slots, nblk(n, 256), 256, 0, ctx->d_umi.as<uint64_t>(), ctx->d_frag.as<uint32_t>(), n,
                ctx->d_umi_table.as<unsigned long long>(), (uint32_t)((1u << slot_bits) - 1u), frag_bits, k0, v0);
@@ -489,7 +502,7 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         uint32_t* uhead = ctx->d_flags32a.as<uint32_t>(); uint32_t* fhead = ctx->d_flags32b.as<uint32_t>();
         uint32_t* uex = ctx->d_urank.as<uint32_t>(); uint32_t* fex = ctx->d_frank.as<uint32_t>();
         LAUNCH(k_heads, nblk(n, 256), 256, 0, k0, frag_bits, n, uhead, fhead);
-        exclusive_scan_u32(uhead, uex, n, ctx->d_scan.as<uint32_t>(), small + 10, ctx->st);
+        exclusive_scan_u32(uhead, uex, n, ctx->d_scan.as<uint32_t>(), small + SW_N_UMI, ctx->st);
         exclusive_scan_u32(fhead, fex, n, ctx->d_scan.as<uint32_t>(), nullptr, ctx->st);
         LAUNCH(k_ranks, nblk(n, 256), 256, 0, uhead, fhead, uex, fex, ctx->d_umi.as<uint64_t>(), perm, n, uex, fex,
                ctx->d_umi_of_urank.as<uint64_t>(), v1);
@@ -497,7 +510,7 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         CK(ctx->d_recs.ensure((size_t)n * sizeof(ReadRec))); CK(ctx->d_grec.ensure((size_t)n * sizeof(GRec)));
         CK(ctx->d_ntiles.ensure((size_t)(n + 1) * 4));
         CK(ctx->d_evoff.ensure((size_t)(n + 1) * 4));
-        CK(cudaMemsetAsync(small + 4, 0, 32, ctx->st));
+        CK(cudaMemsetAsync(small + SW_N_TILE_EVENTS, 0, 32, ctx->st));
         PrepArgs P{};
         P.n_reads = n; P.inv = v1; P.urank = uex; P.frank = fex;
         P.ref_id = ctx->d_ref_id.as<int32_t>(); P.pos = ctx->d_pos.as<int32_t>(); P.flag = ctx->d_flag.as<uint16_t>();
@@ -507,19 +520,19 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         if (ctx->has_store) { P.store_lo = ctx->d_store_lo.as<int32_t>(); P.store_len = ctx->d_store_len.as<int32_t>(); }
         P.loci_key = ctx->d_loci_key.as<uint64_t>(); P.n_loci = nl;
         P.minMQ = ctx->prm.minMQ; P.primerDist = ctx->prm.primerDist; P.mismatchThr = ctx->prm.mismatchThr;
-        P.recs = ctx->d_recs.as<ReadRec>(); P.grec = ctx->d_grec.as<GRec>(); P.ntiles = ctx->d_ntiles.as<uint32_t>(); P.gflags = small + 5;
+        P.recs = ctx->d_recs.as<ReadRec>(); P.grec = ctx->d_grec.as<GRec>(); P.ntiles = ctx->d_ntiles.as<uint32_t>(); P.gflags = small + SW_GFLAGS;
         if (ctx->pipe_n > 1) {
             CK(ctx->d_pipe_need.ensure((size_t)n));
             P.pipe_need = ctx->d_pipe_need.as<uint8_t>(); P.pipe_n = (uint32_t)ctx->pipe_n;
             P.pipe_seq_chunk = ctx->pipe_seq_chunk; P.pipe_qual_chunk = ctx->pipe_qual_chunk;
         }
         LAUNCH(k_read_prep, nblk(n, 256), 256, 0, P);
-        exclusive_scan_u32(ctx->d_ntiles.as<uint32_t>(), ctx->d_evoff.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + 4, ctx->st);
+        exclusive_scan_u32(ctx->d_ntiles.as<uint32_t>(), ctx->d_evoff.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + SW_N_TILE_EVENTS, ctx->st);
         uint32_t h[2], tot[3];
         unsigned long long frag_or = 0;
-        CK(cudaMemcpyAsync(&frag_or, small, 8, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaMemcpyAsync(h, small + 4, 8, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaMemcpyAsync(tot, small + 40, 12, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(&frag_or, small + SW_FRAG_OR, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(h, small + SW_N_TILE_EVENTS, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(tot, small + SW_PACK_TOTALS, 12, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         if (h[1] & GF_BAD_READ) { ctx->err = "a read has l_seq or clip length > 65535 (unsupported)"; return SMC_E_LIMIT; }
         if (h[1] & GF_BAD_STORE) {
@@ -580,7 +593,7 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         const int G = ctx->pipe_n;
         uint32_t init[SMC_PIPE_MAX];
         for (int c = 0; c < SMC_PIPE_MAX; ++c) init[c] = ctx->n_units_cap;
-        uint32_t* pd = small + 16;                      // first blocked unit per chunk
+        uint32_t* pd = small + SW_PIPE_BLOCKED;                      // first blocked unit per chunk
         CK(cudaMemcpyAsync(pd, init, sizeof(init), cudaMemcpyHostToDevice, ctx->st));
         LAUNCH(k_pipe_unit_need, nblk((int64_t)ctx->n_units_cap * 32, 256), 256, 0, ctx->d_unit_eb.as<uint32_t>(),
                ctx->d_unit_ee.as<uint32_t>(), ev_read_sorted, ctx->d_pipe_need.as<uint8_t>(), ctx->n_units_cap, pd);
@@ -603,7 +616,7 @@ static DynTab make_dyntab(smc_ctx* ctx) {
     DynTab T;
     T.dkey = ctx->d_dkey.as<unsigned long long>(); T.dmask = ctx->dyn_cap - 1; T.drep_read = ctx->d_drep_read.as<uint32_t>();
     T.drep_qpos = ctx->d_drep_qpos.as<int32_t>(); T.dlen = ctx->d_dlen.as<int32_t>(); T.dcnt = ctx->d_dcnt.as<int32_t>();
-    T.dlimb = ctx->d_dlimb.as<unsigned long long>(); T.diskey = ctx->d_diskey.as<uint8_t>(); T.dcount = small + 6; T.gflags = small + 5;
+    T.dlimb = ctx->d_dlimb.as<unsigned long long>(); T.diskey = ctx->d_diskey.as<uint8_t>(); T.dcount = small + SW_DYN_COUNT; T.gflags = small + SW_GFLAGS;
     return T;
 }
 
@@ -677,7 +690,7 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
         CK(cudaMemsetAsync(ctx->d_loc.p, 0, nlz * SMC_NLOC * 4, ctx->st));
         CK(cudaMemsetAsync(ctx->d_cnt.p, 0, nlz * SMC_NFIXED * SMC_NCNT * 4, ctx->st));
         CK(cudaMemsetAsync(ctx->d_limb.p, 0, nlz * SMC_NFIXED * 3 * 8, ctx->st));
-        CK(cudaMemsetAsync(small + 5, 0, 24, ctx->st));     // gflags, dyn count, n_tasks, cvg sum
+        CK(cudaMemsetAsync(small + SW_GFLAGS, 0, 24, ctx->st));     // gflags, dyn count, n_tasks, cvg sum
         if (NE > 0) {
             { int rc = ensure_code_storage(ctx, false, ctx->has_keep); if (rc) return rc; }
             KAArgs A; KBArgs B;
@@ -705,7 +718,7 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
             CK(cudaEventRecord(ctx->ev[10], ctx->st));
         }
         uint32_t h[3];
-        CK(cudaMemcpyAsync(h, small + 5, 12, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(h, small + SW_GFLAGS, 12, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         CK(cudaGetLastError());
         if (!(h[0] & (GF_DYN_FULL | GF_CODE_FULL))) { ctx->n_dyn = h[1]; break; }
@@ -746,7 +759,7 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (ctx->task_cap == 0) ctx->task_cap = 1u << 16;
         CK(ctx->d_tasks.ensure((size_t)ctx->task_cap * sizeof(FisherTask)));
-        CK(cudaMemsetAsync(small + 7, 0, 4, ctx->st));
+        CK(cudaMemsetAsync(small + SW_N_TASKS, 0, 4, ctx->st));
         K4Args B{};
         B.n_loci = nl; B.ref_base = ctx->d_loci_base.as<uint8_t>(); B.loc = ctx->d_loc.as<int32_t>(); B.cnt = ctx->d_cnt.as<int32_t>();
         B.limb = ctx->d_limb.as<unsigned long long>(); B.pi = ctx->d_pi.as<double>();
@@ -758,21 +771,21 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
         B.max_allele = ctx->d_max.as<int32_t>(); B.second_allele = ctx->d_second.as<int32_t>(); B.alt_allele = ctx->d_alt.as<int32_t>();
         B.alt_pi = ctx->d_altpi.as<double>(); B.second_pi = ctx->d_secondpi.as<double>(); B.fl1 = ctx->d_fl1.as<uint32_t>();
         B.fl2 = ctx->d_fl2.as<uint32_t>(); B.biallelic = ctx->d_bial.as<uint8_t>(); B.fisher_p = ctx->d_fp.as<double>();
-        B.fisher_or = ctx->d_for.as<double>(); B.tasks = ctx->d_tasks.as<FisherTask>(); B.n_tasks = small + 7; B.task_cap = ctx->task_cap;
+        B.fisher_or = ctx->d_for.as<double>(); B.tasks = ctx->d_tasks.as<FisherTask>(); B.n_tasks = small + SW_N_TASKS; B.task_cap = ctx->task_cap;
         LAUNCH(k_call, nblk(nl, 128), 128, 0, B);
-        CK(cudaMemcpyAsync(&n_tasks_h, small + 7, 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(&n_tasks_h, small + SW_N_TASKS, 4, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         if (n_tasks_h <= ctx->task_cap) break;
         ctx->task_cap = n_tasks_h + n_tasks_h / 4 + 1024;      // grow and redo the (cheap) call kernel
     }
     if (n_tasks_h > 0)
-        LAUNCH(k_fisher, nblk(n_tasks_h, 128), 128, 0, ctx->d_tasks.as<FisherTask>(), small + 7, ctx->task_cap, nl, ctx->d_fp.as<double>(),
+        LAUNCH(k_fisher, nblk(n_tasks_h, 128), 128, 0, ctx->d_tasks.as<FisherTask>(), small + SW_N_TASKS, ctx->task_cap, nl, ctx->d_fp.as<double>(),
                ctx->d_for.as<double>(), ctx->d_fl1.as<uint32_t>(), ctx->d_fl2.as<uint32_t>());
     LAUNCH(k_sum_cvg, std::min<unsigned>(nblk(nl, 256), 592u), 256, 0, ctx->d_loc.as<int32_t>() + (size_t)SMC_L_CVG * nl, nl,
-           (unsigned long long*)(small + 8));
+           (unsigned long long*)(small + SW_CVG_SUM));
     CK(cudaEventRecord(ctx->ev[6], ctx->st));
     unsigned long long cvgsum = 0;
-    CK(cudaMemcpyAsync(&cvgsum, small + 8, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&cvgsum, small + SW_CVG_SUM, 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     CK(cudaGetLastError());
     cudaEventElapsedTime(&ctx->tm.ms_prep, ctx->ev[2], ctx->ev[3]);
