@@ -60,10 +60,12 @@ def make_batch(args, rank, world):
                 return pickle.load(fh)
     ivs = panel_intervals_from_bed(PANEL_BED, limit=args.intervals * world, seed=args.seed)
     if world > 1:
-        # the product's own multi-GPU plan (shard.assign_intervals): BED intervals to ranks, balanced by estimated pileup
-        # events (uniform depth here, so ~ interval length + the read-length margin on both sides), not by interval count
+        # the product's own multi-GPU plan (shard.assign_intervals): BED intervals to ranks, balanced by estimated work
+        # (uniform depth here, so ~ interval length + a margin for the reads hanging over both ends), not by interval count.
+        # Margin measured at N=4 on B200: 150 -> 5.14 ms max step, 300 -> 4.88, 600 -> 4.84 (ideal 4.54)
         from smcounter_b200.shard import assign_intervals
-        shard, _ = assign_intervals([float(e - s + 150) for (_, s, e) in ivs], world)
+        margin = float(os.environ.get("SMC_BENCH_MARGIN", "500"))
+        shard, _ = assign_intervals([float(e - s) + margin for (_, s, e) in ivs], world)
         mine = [iv for iv, g in zip(ivs, shard) if g == rank]
     else:
         mine = ivs
