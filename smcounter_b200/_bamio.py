@@ -54,12 +54,32 @@ def load():
     return lib
 
 
-def _arr(ptr, n, dtype):
+class _Handle:
+    """Owns an smc_bam handle; closed when the last array that views its buffers is gone."""
+
+    def __init__(self, lib, h):
+        self.lib, self.h = lib, h
+
+    def close(self):
+        if self.h:
+            self.lib.smc_bam_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _arr(ptr, n, dtype, owner):
+    """numpy view of a decoder buffer (no copy): the ctypes buffer the array is based on keeps ``owner`` alive."""
     n = int(n)
     if n == 0 or not ptr:
         return np.zeros(0, dtype=dtype)
     buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
-    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+    buf._smc_owner = owner
+    return np.frombuffer(buf, dtype=dtype, count=n)
 
 
 def read_bam_native(path: str, intervals=None, threads: int = 0, trim: bool = False) -> ReadsSoA:
@@ -68,6 +88,8 @@ def read_bam_native(path: str, intervals=None, threads: int = 0, trim: bool = Fa
     rc = lib.smc_bam_open(os.fsencode(path), int(threads), C.byref(h))
     if rc != 0:
         raise ValueError(lib.smc_bam_last_error(None).decode())
+    owner = _Handle(lib, h)
+    ok = False
     try:
         chroms = [lib.smc_bam_ref_name(h, i).decode() for i in range(lib.smc_bam_n_refs(h))]
         cidx = {c: i for i, c in enumerate(chroms)}
@@ -85,19 +107,23 @@ def read_bam_native(path: str, intervals=None, threads: int = 0, trim: bool = Fa
         if rc != 0:
             raise ValueError(lib.smc_bam_last_error(h).decode())
         n = out.n_reads
-        umi = _arr(out.umi, n, np.uint64)
+        A = lambda ptr, count, dtype: _arr(ptr, count, dtype, owner)
+        umi = A(out.umi, n, np.uint64)
         names = {}
         for i in range(out.n_dict_umis):
             names[(1 << 63) | i] = lib.smc_bam_dict_umi(h, i).decode()
         # 2-bit packed codes decode to their barcode on demand (soa.umi_string); only the dictionary-coded ones need a name
-        return ReadsSoA(
-            ref_id=_arr(out.ref_id, n, np.int32), pos=_arr(out.pos, n, np.int32), flag=_arr(out.flag, n, np.uint16),
-            mapq=_arr(out.mapq, n, np.uint8), nm=_arr(out.nm, n, np.int32), l_seq=_arr(out.l_seq, n, np.int32),
-            seq_off=_arr(out.seq_off, n, np.int64), qual_off=_arr(out.qual_off, n, np.int64), cigar_off=_arr(out.cigar_off, n, np.int64),
-            n_cigar=_arr(out.n_cigar, n, np.uint16), umi=umi, frag_id=_arr(out.frag_id, n, np.uint32),
-            seq=_arr(out.seq, out.seq_bytes, np.uint8), qual=_arr(out.qual, out.qual_bytes, np.uint8),
-            cigar=_arr(out.cigar, out.n_cigar_words, np.uint32), chroms=chroms, umi_names=names, packed=True,
-            store_lo=_arr(out.store_lo, n, np.int32) if out.store_lo else None,
-            store_len=_arr(out.store_len, n, np.int32) if out.store_len else None)
+        soa = ReadsSoA(
+            ref_id=A(out.ref_id, n, np.int32), pos=A(out.pos, n, np.int32), flag=A(out.flag, n, np.uint16),
+            mapq=A(out.mapq, n, np.uint8), nm=A(out.nm, n, np.int32), l_seq=A(out.l_seq, n, np.int32),
+            seq_off=A(out.seq_off, n, np.int64), qual_off=A(out.qual_off, n, np.int64), cigar_off=A(out.cigar_off, n, np.int64),
+            n_cigar=A(out.n_cigar, n, np.uint16), umi=umi, frag_id=A(out.frag_id, n, np.uint32),
+            seq=A(out.seq, out.seq_bytes, np.uint8), qual=A(out.qual, out.qual_bytes, np.uint8),
+            cigar=A(out.cigar, out.n_cigar_words, np.uint32), chroms=chroms, umi_names=names, packed=True,
+            store_lo=A(out.store_lo, n, np.int32) if out.store_lo else None,
+            store_len=A(out.store_len, n, np.int32) if out.store_len else None)
+        ok = True
+        return soa
     finally:
-        lib.smc_bam_close(h)
+        if not ok:
+            owner.close()

@@ -3,6 +3,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -17,11 +18,39 @@
 namespace {
 thread_local std::string g_open_error;
 
+// SMC_BAM_TIMING=1: per-phase wall clock on stderr (tuning aid)
+struct PhaseTimer {
+    bool on = getenv("SMC_BAM_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[smc_bamio] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 inline uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
 inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 inline int32_t rdi32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; }
 
 struct Block { size_t coff, clen; size_t uoff; uint32_t isize; };
+
+// output arrays: malloc'ed and NOT zero-filled (std::vector::resize would touch every page once more, serially)
+template <class T> struct PodBuf {
+    T* p = nullptr; size_t n = 0;
+    PodBuf() = default;
+    PodBuf(const PodBuf&) = delete;
+    PodBuf& operator=(const PodBuf&) = delete;
+    ~PodBuf() { free(p); }
+    void resize(size_t count) { free(p); p = (T*)malloc((count ? count : 1) * sizeof(T)); n = p ? count : 0; }
+    void clear() { resize(0); }
+    void assign(size_t count, T v) { resize(count); for (size_t i = 0; i < n; ++i) p[i] = v; }
+    size_t size() const { return n; }
+    T* data() { return p; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+};
 
 // the inflated stream: malloc'ed, NOT zero-filled (every byte is written by inflate before anything reads it)
 struct RawBuf {
@@ -46,18 +75,19 @@ struct smc_bam {
     size_t first_record = 0;
     int threads = 1;
     // decoded buffers
-    std::vector<int32_t> ref_id, pos, nm, l_seq;
-    std::vector<uint16_t> flag, n_cigar;
-    std::vector<uint8_t> mapq, seq, qual;
-    std::vector<int64_t> seq_off, qual_off, cigar_off;
-    std::vector<uint64_t> umi;
-    std::vector<uint32_t> frag_id, cigar;
+    PodBuf<int32_t> ref_id, pos, nm, l_seq;
+    PodBuf<uint16_t> flag, n_cigar;
+    PodBuf<uint8_t> mapq, seq, qual;
+    PodBuf<int64_t> seq_off, qual_off, cigar_off;
+    PodBuf<uint64_t> umi;
+    PodBuf<uint32_t> frag_id, cigar;
     std::vector<std::string> dict_umis;
-    std::vector<int32_t> store_lo, store_len;   // stored window per read (trim mode)
+    PodBuf<int32_t> store_lo, store_len;        // stored window per read (trim mode)
     int trim = 0;
+    bool decoded = false;
 };
 
-static int inflate_all(const std::vector<uint8_t>& file, int threads, RawBuf& out, std::string& err) {
+static int inflate_all(const RawBuf& file, int threads, RawBuf& out, std::string& err) {
     std::vector<Block> blocks;
     size_t off = 0, uoff = 0;
     const size_t n = file.size();
@@ -115,18 +145,21 @@ extern "C" int smc_bam_open(const char* path, int threads, smc_bam** out) {
     if (!path || !out) { g_open_error = "smc_bam_open: null argument"; return -2; }
     FILE* fh = fopen(path, "rb");
     if (!fh) { g_open_error = std::string("smc_bam_open: cannot open ") + path; return -1; }
-    std::vector<uint8_t> file;
+    PhaseTimer pt;
+    RawBuf file;
     fseek(fh, 0, SEEK_END);
     const long sz = ftell(fh);
     fseek(fh, 0, SEEK_SET);
-    file.resize(sz > 0 ? (size_t)sz : 0);
-    const size_t got = file.empty() ? 0 : fread(file.data(), 1, file.size(), fh);
+    if (!file.alloc(sz > 0 ? (size_t)sz : 0)) { fclose(fh); g_open_error = "smc_bam_open: out of memory"; return -1; }
+    const size_t got = file.size() ? fread(file.p, 1, file.size(), fh) : 0;
     fclose(fh);
     if (got != file.size()) { g_open_error = "smc_bam_open: short read"; return -1; }
+    pt.lap("read file");
     smc_bam* h = new smc_bam();
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     h->threads = threads;
     if (inflate_all(file, threads, h->raw, g_open_error) != 0) { delete h; return -1; }
+    pt.lap("inflate");
     const RawBuf& r = h->raw;
     if (r.size() < 12 || memcmp(r.data(), "BAM\1", 4) != 0) { g_open_error = "not a BAM file (bad magic)"; delete h; return -1; }
     size_t p = 8 + (size_t)rdi32(&r[4]);
@@ -228,6 +261,7 @@ template <class F> void parallel_for(size_t n, int threads, F f) {          // f
 extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, const int32_t* iv_start, const int32_t* iv_end,
                               smc_bam_reads* out) {
     if (!h || !out || (n_iv > 0 && (!iv_ref || !iv_start || !iv_end))) { if (h) h->err = "smc_bam_decode: null argument"; return -2; }
+    if (h->decoded) { h->err = "smc_bam_decode: a handle decodes once (the inflated stream is released afterwards); open the file again"; return -2; }
     // per reference: interval starts (sorted) and the running maximum of their ends
     const size_t nref = h->ref_names.size();
     std::vector<std::vector<std::pair<int64_t, int64_t>>> iv(nref);
@@ -260,6 +294,7 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
         }
     const RawBuf& r = h->raw;
     const int threads = std::max(1, h->threads);
+    PhaseTimer pt;
     // ---- pass 1: record boundaries
     std::vector<size_t> offs;
     offs.reserve(r.size() / 200 + 16);
@@ -270,6 +305,7 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
         p += 4 + (size_t)bs;
     }
     const size_t nrec = offs.size();
+    pt.lap("pass 1 boundaries");
     // ---- pass 2: fields, filter, identity hash
     std::vector<RecInfo> info(nrec);
     std::atomic<size_t> bad_rec(SIZE_MAX);
@@ -345,6 +381,7 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
             R.keep = 1;
         }
     });
+    pt.lap("pass 2 fields + hash");
     if (bad_rec.load() != SIZE_MAX) { h->err = "malformed BAM record (field lengths exceed block_size)"; return -1; }
     // ---- pass 3: output slots, payload offsets, fragment ids, barcode dictionary
     std::vector<uint32_t> slot(nrec);
@@ -359,6 +396,7 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
     // each walks the records in order, keeps its identities in its own open-addressing table and notes, per record, the
     // FIRST record of that identity (hits verified on the name bytes).  A prefix sum over "is a first record" then numbers
     // the identities in order of first appearance -- the same ids the sequential dictionary would hand out.
+    pt.lap("alloc outputs");
     std::vector<uint32_t> first_rec(nrec);
     {
         auto same_identity = [&](size_t i, size_t j) {
@@ -392,6 +430,7 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
         part(0);
         for (auto& t : ts) t.join();
     }
+    pt.lap("fragment identities");
     {
         std::vector<uint32_t> id_of(nrec);                                       // id of the identity whose first record is i
         std::unordered_map<std::string, uint64_t> umi_dict;
@@ -420,7 +459,9 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
             ++o;
         }
     }
+    pt.lap("pass 3 numbering + offsets");
     h->seq.resize(seq_tot); h->qual.resize(qual_tot); h->cigar.resize(cig_tot);
+    pt.lap("alloc payload");
     // ---- pass 4: scalars and payloads
     parallel_for(nrec, threads, [&](size_t a, size_t e, int) {
         for (size_t i = a; i < e; ++i) {
@@ -445,6 +486,7 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
             if (n_cig) memcpy(&h->cigar[(size_t)h->cigar_off[o]], cig, 4 * (size_t)n_cig);
         }
     });
+    pt.lap("pass 4 copy");
     out->n_reads = (int64_t)n;
     out->ref_id = h->ref_id.data(); out->pos = h->pos.data(); out->flag = h->flag.data(); out->mapq = h->mapq.data();
     out->nm = h->nm.data(); out->l_seq = h->l_seq.data(); out->seq_off = h->seq_off.data(); out->qual_off = h->qual_off.data();
@@ -452,5 +494,7 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
     out->seq = h->seq.data(); out->seq_bytes = (int64_t)h->seq.size(); out->qual = h->qual.data(); out->qual_bytes = (int64_t)h->qual.size();
     out->cigar = h->cigar.data(); out->n_cigar_words = (int64_t)h->cigar.size(); out->n_dict_umis = (int64_t)h->dict_umis.size();
     out->store_lo = trim ? h->store_lo.data() : nullptr; out->store_len = trim ? h->store_len.data() : nullptr;
+    h->raw.alloc(0);                               // the inflated stream is not needed any more (one decode per handle)
+    h->decoded = true;
     return 0;
 }
