@@ -210,3 +210,51 @@ def test_call_loci_across_all_visible_gpus():
     devices = list(range(ndev)) if ndev > 1 else [0, 0]
     many = call_loci(soa.trim_to_targets(ivs), ivs, refs, prm, gpus=len(devices), devices=devices)
     assert many == one and len(one) == sum(e - s for (_, s, e) in ivs)
+
+
+def test_cfg4_indel_and_repeat_heavy_panel_through_the_cli(tmp_path):
+    """BASELINE config 4 shape, scaled: panel intervals on three contigs, 5 % of the molecules carry a 1-4 bp indel every 40 bp,
+    synthetic simpleRepeat (3-column) and RepeatMasker (4-column: Simple_repeat / Low_complexity / Satellite / other) tracks
+    over ~10 % of the target, all filters active.  smCounter.main() from BAM + BED + FASTA + the two repeat BEDs to the three
+    output files, byte-identical to the oracle's restatement of main() (smCounter.py:645-909)."""
+    import os
+    from oracle import smcounter_oracle as orc
+    from smcounter_b200 import bam, smCounter
+    from smcounter_b200.soa import soa_to_records
+    bed_path = os.path.join(os.path.dirname(__file__), "golden", "n0030_panel.bed")
+    ivs = panel_intervals_from_bed(bed_path, limit=9, seed=21)
+    spec = SynthSpec(umis_per_locus=120, rpb=4.0, snv_every=150, snv_vaf=0.05, indel_every=40, indel_vaf=0.05, softclip_frac=0.1)
+    soa, refs, _ = make_panel_mp(ivs, spec, seed=21, workers=4)
+    fa = tmp_path / "ref.fa"
+    with open(fa, "w") as fh:
+        for c in soa.chroms:
+            s = refs.fetch(c, 0, refs.get_reference_length(c))
+            fh.write(">%s\n" % c)
+            for i in range(0, len(s), 60):
+                fh.write(s[i:i + 60] + "\n")
+    bed = tmp_path / "target.bed"
+    bed_lines = ["%s\t%d\t%d\n" % iv for iv in ivs]
+    bed.write_text("".join(bed_lines))
+    # repeat tracks: every third interval gets a tandem repeat over its first 30 bp and a RepeatMasker element over the next 25
+    kinds = ("Simple_repeat", "Low_complexity", "Satellite", "L1")
+    trf_rows, rm_rows = [], []
+    for k, (c, s, e) in enumerate(sorted(ivs)):
+        if k % 3 == 0:
+            trf_rows.append((c, str(s), str(min(e, s + 30))))
+            rm_rows.append((c, str(s + 20), str(min(e, s + 55)), kinds[(k // 3) % 4]))
+    trf = tmp_path / "simpleRepeat.bed"; trf.write_text("".join("\t".join(r) + "\n" for r in trf_rows))
+    rm = tmp_path / "SR_LC_SL.bed"; rm.write_text("".join("\t".join(r) + "\n" for r in rm_rows))
+    bam_path = tmp_path / "reads.bam"
+    bam.write_bam(str(bam_path), soa, refs.lengths)
+    prefix = str(tmp_path / "out")
+    smCounter.argParseInit()
+    thr = smCounter.main({"outPrefix": prefix, "bamFile": str(bam_path), "bedTarget": str(bed), "mtDepth": 120, "rpb": 4.0, "nCPU": 4,
+                          "refGenome": str(fa), "bedTandemRepeats": str(trf), "bedRepeatMaskerSubset": str(rm)})
+    want_thr, all_txt, cut_txt, cut_vcf = orc.run(soa_to_records(soa, orc.Read), bed_lines, refs, mtDepth=120, rpb=4.0, threshold=0,
+                                                   outPrefix=prefix, trf_rows=trf_rows, rm_rows=rm_rows)
+    assert thr == want_thr
+    got_all = open(prefix + ".smCounter.all.txt").read()
+    assert got_all == all_txt
+    assert open(prefix + ".smCounter.cut.txt").read() == cut_txt
+    assert open(prefix + ".smCounter.cut.vcf").read() == cut_vcf
+    assert "RepT" in all_txt and any(t in all_txt for t in ("RepS", "LowC", "SL", "Other_Repeat")) and "INDEL" in all_txt
