@@ -360,8 +360,8 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
     if (!R || !Lc) { ctx->err = "smc_upload: null reads/loci"; return SMC_E_ARG; }
     if (R->n_reads < 0 || Lc->n_loci < 0) { ctx->err = "smc_upload: negative size"; return SMC_E_ARG; }
     if (Lc->n_loci > SMC_MAX_LOCI) { ctx->err = "smc_upload: more than 4194302 loci in one batch"; return SMC_E_LIMIT; }
-    if (R->n_reads >= (1ll << 31) || R->seq_bytes >= (1ll << 32) || R->qual_bytes >= (1ll << 32) || R->n_cigar_words >= (1ll << 32)) {
-        ctx->err = "smc_upload: batch exceeds 2^31 reads or 4 GiB of bases/qualities/cigar; split the batch"; return SMC_E_LIMIT;
+    if (R->n_reads > (1ll << 30) || R->seq_bytes >= (1ll << 32) || R->qual_bytes >= (1ll << 32) || R->n_cigar_words >= (1ll << 32)) {
+        ctx->err = "smc_upload: batch exceeds 2^30 reads or 4 GiB of bases/qualities/cigar; split the batch"; return SMC_E_LIMIT;
     }
     CK(cudaSetDevice(ctx->device));
     ctx->uploaded = false; ctx->ran = false;

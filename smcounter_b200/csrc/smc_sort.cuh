@@ -66,7 +66,7 @@ static inline int64_t scan_scratch_words(int64_t n) {
     return w + 2;
 }
 
-static int g_launches = 0;   // kernel launch counter (reported through smc_timings)
+static thread_local int g_launches = 0;   // kernel launch counter of the calling host thread (one thread drives one context)
 
 static void exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* scratch, uint32_t* total,
                                cudaStream_t st) {

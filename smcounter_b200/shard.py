@@ -103,7 +103,7 @@ def reads_for_intervals(reads: ReadsSoA, intervals, chroms) -> np.ndarray:
 def plan_batches(locator: ReadLocator, intervals, idxs, max_payload_bytes: int = 1 << 30, max_loci: int = 1 << 21,
                  max_reads: int = 1 << 27):
     """Cut the interval indices ``idxs`` (BED order) into consecutive batches that respect the per-batch limits of
-    libsmc_b200 (include/smc_b200.h: < 4 GiB of bases / qualities, < 2^31 reads, <= 4 194 302 loci) with a wide margin,
+    libsmc_b200 (include/smc_b200.h: < 4 GiB of bases / qualities, <= 2^30 reads, <= 4 194 302 loci) with a wide margin,
     from an upper estimate of the reads per interval.  A whole panel or exome goes through one GPU as a stream of batches."""
     reads = locator.reads
     per_read = (float(reads.seq.nbytes + reads.qual.nbytes) / reads.n) if reads.n else 0.0
