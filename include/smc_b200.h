@@ -56,7 +56,7 @@ typedef struct smc_params {
  * pysam per pileup read at smCounter.py:319-365, 372-375, 424-425.
  */
 typedef struct smc_reads_soa {
-    int64_t         n_reads;
+    int64_t         n_reads;    /* <= 2^30 per batch */
     const int32_t  *ref_id;     /* contig index */
     const int32_t  *pos;        /* 0-based leftmost reference position */
     const uint16_t *flag;       /* BAM flag: 0x4 unmapped (skipped), 0x10 reverse, 0x40 read1, 0x80 read2 */
