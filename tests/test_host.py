@@ -353,3 +353,31 @@ def test_read_locator_and_batch_plan():
     assert all(sum(ivs[k][2] - ivs[k][1] for k in b) <= 120 or len(b) == 1 for b in small)
     by_reads = plan_batches(loc, ivs, idxs, max_reads=loc.count_upper(*ivs[0]) + 1)
     assert [k for b in by_reads for k in b] == idxs and len(by_reads) >= 2
+
+
+def test_bench_rank_batches_partition_the_panel(monkeypatch):
+    """bench.make_batch(): at N ranks the seeded panel subset is split into disjoint interval groups that cover it (the product's
+    shard.assign_intervals), every rank's reads are packed and trimmed to its own targets, and N=1 keeps the plain subset."""
+    import importlib.util
+    import os
+    import types
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(bench, "UMIS_PER_LOCUS", 6)
+    args = types.SimpleNamespace(intervals=3, seed=1, whole_reads=False)
+    from smcounter_b200.synth import panel_intervals_from_bed
+    world = 3
+    want = panel_intervals_from_bed(bench.PANEL_BED, limit=args.intervals * world, seed=args.seed)
+    got, loci_total = [], 0
+    for rank in range(world):
+        mine, soa, refs, loci, bed_order, full = bench.make_batch(args, rank, world)
+        assert mine and soa.packed and soa.store_lo is not None and full.store_lo is None and full.n == soa.n
+        assert soa.seq.nbytes + soa.qual.nbytes < full.seq.nbytes + full.qual.nbytes
+        assert loci.n == len(set((c, p) for (c, s, e) in mine for p in range(s, e)))
+        got += mine
+        loci_total += loci.n
+    assert sorted(got) == sorted(want) and len(got) == len(set(got))
+    one = bench.make_batch(args, 0, 1)[0]
+    assert one == panel_intervals_from_bed(bench.PANEL_BED, limit=args.intervals, seed=args.seed)
