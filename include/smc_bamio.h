@@ -7,8 +7,9 @@
  * (BC = qname.split(':')[-2], readid = ':'.join(parts[:-2])), NM follows :329-334 (first NM tag, else 0).
  * Unmapped records are dropped (htslib never piles them up); nothing else is filtered (stepper='nofilter').
  *
- * BGZF blocks are inflated by `threads` host threads (zlib); the record decode runs on the same number of threads (only the
- * numbering of fragments by first appearance is a sequential pass).
+ * BGZF blocks are inflated by `threads` host threads (zlib) and every pass of the record decode runs on the same number of
+ * threads (record boundaries per byte range with a verified speculative start, fields + identity hashes, fragment numbering by
+ * hash partition, prefix sums, payload copy); results are identical for any thread count.
  * All returned pointers stay valid until smc_bam_close().  Functions return 0 or a negative code; message via
  * smc_bam_last_error().
  */

@@ -295,14 +295,81 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
     const RawBuf& r = h->raw;
     const int threads = std::max(1, h->threads);
     PhaseTimer pt;
-    // ---- pass 1: record boundaries
+    // ---- pass 1: record boundaries.  The block_size chain is a serial pointer chase (one cache miss per record), so the stream
+    // is cut into byte ranges that are walked in parallel: a range that does not start the stream finds its first record by
+    // testing candidates for plausibility (three consistent records in a row), and the result is accepted only if every
+    // range's walk ends exactly where the next range started -- by induction from the known first record the chain is then
+    // the true one.  Anything else (including a malformed record) falls back to the plain serial walk and its error report.
     std::vector<size_t> offs;
-    offs.reserve(r.size() / 200 + 16);
-    for (size_t p = h->first_record; p + 4 <= r.size();) {
-        const int32_t bs = rdi32(&r[p]);
-        if (bs < 32 || p + 4 + (size_t)bs > r.size()) { h->err = "truncated BAM record at offset " + std::to_string(p); return -1; }
-        offs.push_back(p);
-        p += 4 + (size_t)bs;
+    {
+        const size_t begin = h->first_record, size = r.size();
+        auto plausible = [&](size_t p) -> size_t {                // 0 = no; else offset of the next record
+            if (p + 36 > size) return 0;
+            const int32_t bs = rdi32(&r[p]);
+            if (bs < 32 || p + 4 + (size_t)bs > size) return 0;
+            const uint8_t* b = &r[p + 4];
+            const int32_t refID = rdi32(b), pos = rdi32(b + 4), l_seq = rdi32(b + 16), nref_id = rdi32(b + 20), npos = rdi32(b + 24);
+            const uint32_t l_rn = b[8], n_cig = rd16(b + 12);
+            if (refID < -1 || refID >= (int32_t)nref || pos < -1 || nref_id < -1 || nref_id >= (int32_t)nref || npos < -1) return 0;
+            if (l_rn < 1 || l_seq < 0) return 0;
+            const size_t need = 32 + (size_t)l_rn + 4 * (size_t)n_cig + ((size_t)l_seq + 1) / 2 + (size_t)l_seq;
+            if (need > (size_t)bs || b[32 + l_rn - 1] != 0) return 0;
+            return p + 4 + (size_t)bs;
+        };
+        const size_t span = size > begin ? size - begin : 0;
+        const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, span / (4u << 20)));
+        bool ok = T > 1;
+        if (ok) {
+            std::vector<std::vector<size_t>> part(T);
+            std::vector<size_t> first(T, SIZE_MAX), last(T, SIZE_MAX);
+            std::vector<char> good(T, 1);
+            auto work = [&](int t) {
+                const size_t lo = begin + span * (size_t)t / T, hi = t + 1 == T ? size : begin + span * (size_t)(t + 1) / T;
+                size_t p = lo;
+                if (t > 0) {                                         // first plausible chain of three at or after lo
+                    for (;; ++p) {
+                        if (p + 4 > hi + (1u << 20) || p + 4 > size) { good[t] = 0; return; }
+                        size_t q = plausible(p);
+                        if (!q) continue;
+                        size_t q2 = q + 4 <= size ? plausible(q) : (q == size ? q : 0);
+                        if (!q2) continue;
+                        if (q2 != size && q2 + 4 <= size && !plausible(q2)) continue;
+                        break;
+                    }
+                }
+                first[t] = p;
+                part[t].reserve((hi - lo) / 200 + 16);
+                while (p + 4 <= size && p < hi) {
+                    const int32_t bs = rdi32(&r[p]);
+                    if (bs < 32 || p + 4 + (size_t)bs > size) { good[t] = 0; return; }
+                    part[t].push_back(p);
+                    p += 4 + (size_t)bs;
+                }
+                last[t] = p;
+            };
+            std::vector<std::thread> ts;
+            for (int t = 1; t < T; ++t) ts.emplace_back(work, t);
+            work(0);
+            for (auto& th : ts) th.join();
+            for (int t = 0; t < T && ok; ++t) ok = good[t] && (t + 1 == T || last[t] == first[t + 1]);
+            if (ok && last[T - 1] + 4 <= size) ok = false;          // trailing bytes that are not a record: let the serial walk judge
+            if (ok) {
+                size_t tot = 0;
+                for (auto& v : part) tot += v.size();
+                offs.reserve(tot);
+                for (auto& v : part) offs.insert(offs.end(), v.begin(), v.end());
+            }
+        }
+        if (!ok) {
+            offs.clear();
+            offs.reserve(size / 200 + 16);
+            for (size_t p = begin; p + 4 <= size;) {
+                const int32_t bs = rdi32(&r[p]);
+                if (bs < 32 || p + 4 + (size_t)bs > size) { h->err = "truncated BAM record at offset " + std::to_string(p); return -1; }
+                offs.push_back(p);
+                p += 4 + (size_t)bs;
+            }
+        }
     }
     const size_t nrec = offs.size();
     pt.lap("pass 1 boundaries");
@@ -432,32 +499,68 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
     }
     pt.lap("fragment identities");
     {
+        // exclusive prefix sums over the records (kept reads, identities, payload sizes): per-range totals in parallel, a scan of
+        // the few totals, then every range fills its own slice
+        struct Tot { size_t o, id, seq, qual, cig; };
+        const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, nrec / 65536 + 1));
+        std::vector<Tot> base(T + 1, Tot{0, 0, 0, 0, 0});
+        auto range = [&](int t, size_t& a, size_t& e) { a = nrec * (size_t)t / T; e = nrec * (size_t)(t + 1) / T; };
+        auto run = [&](auto&& f) {
+            std::vector<std::thread> ts;
+            for (int t = 1; t < T; ++t) ts.emplace_back(f, t);
+            f(0);
+            for (auto& th : ts) th.join();
+        };
+        run([&](int t) {
+            size_t a, e; range(t, a, e);
+            Tot s{0, 0, 0, 0, 0};
+            for (size_t i = a; i < e; ++i) {
+                const RecInfo& R = info[i];
+                if (!R.keep) continue;
+                ++s.o; s.id += first_rec[i] == (uint32_t)i;
+                s.seq += ((size_t)R.store_len + 1) / 2; s.qual += (size_t)R.store_len; s.cig += rd16(&r[offs[i] + 4 + 12]);
+            }
+            base[t + 1] = s;
+        });
+        for (int t = 0; t < T; ++t) {
+            base[t + 1].o += base[t].o; base[t + 1].id += base[t].id; base[t + 1].seq += base[t].seq;
+            base[t + 1].qual += base[t].qual; base[t + 1].cig += base[t].cig;
+        }
+        seq_tot = base[T].seq; qual_tot = base[T].qual; cig_tot = base[T].cig;
         std::vector<uint32_t> id_of(nrec);                                       // id of the identity whose first record is i
+        run([&](int t) {
+            size_t a, e; range(t, a, e);
+            Tot s = base[t];
+            for (size_t i = a; i < e; ++i) {
+                const RecInfo& R = info[i];
+                if (!R.keep) continue;
+                slot[i] = (uint32_t)s.o;
+                h->seq_off[s.o] = (int64_t)s.seq; h->qual_off[s.o] = (int64_t)s.qual; h->cigar_off[s.o] = (int64_t)s.cig;
+                if (first_rec[i] == (uint32_t)i) id_of[i] = (uint32_t)s.id++;
+                ++s.o; s.seq += ((size_t)R.store_len + 1) / 2; s.qual += (size_t)R.store_len; s.cig += rd16(&r[offs[i] + 4 + 12]);
+            }
+        });
+        // barcodes that do not pack into 64 bits get dictionary codes in order of first appearance (rare: sequential)
         std::unordered_map<std::string, uint64_t> umi_dict;
-        uint32_t next_id = 0;
-        size_t o = 0;
         for (size_t i = 0; i < nrec; ++i) {
             RecInfo& R = info[i];
-            if (!R.keep) continue;
-            const uint8_t* b = &r[offs[i] + 4];
-            const uint16_t n_cig = rd16(b + 12);
-            slot[i] = (uint32_t)o;
-            h->seq_off[o] = (int64_t)seq_tot; h->qual_off[o] = (int64_t)qual_tot; h->cigar_off[o] = (int64_t)cig_tot;
-            seq_tot += ((size_t)R.store_len + 1) / 2; qual_tot += (size_t)R.store_len; cig_tot += n_cig;
-            if (first_rec[i] == (uint32_t)i) id_of[i] = next_id++;
-            h->frag_id[o] = id_of[first_rec[i]];
-            if (R.code == 0) {                                                  // barcode not packable: dictionary code
-                const std::string bc(reinterpret_cast<const char*>(b + 32) + R.bc_off, R.bc_len);
-                auto it = umi_dict.find(bc);
-                if (it == umi_dict.end()) {
-                    R.code = (1ull << 63) | (uint64_t)umi_dict.size();
-                    umi_dict.emplace(bc, R.code);
-                    h->dict_umis.push_back(bc);
-                } else R.code = it->second;
-            }
-            h->umi[o] = R.code;
-            ++o;
+            if (!R.keep || R.code != 0) continue;
+            const std::string bc(reinterpret_cast<const char*>(&r[offs[i] + 4 + 32]) + R.bc_off, R.bc_len);
+            auto it = umi_dict.find(bc);
+            if (it == umi_dict.end()) {
+                R.code = (1ull << 63) | (uint64_t)umi_dict.size();
+                umi_dict.emplace(bc, R.code);
+                h->dict_umis.push_back(bc);
+            } else R.code = it->second;
         }
+        run([&](int t) {
+            size_t a, e; range(t, a, e);
+            for (size_t i = a; i < e; ++i) {
+                if (!info[i].keep) continue;
+                h->frag_id[slot[i]] = id_of[first_rec[i]];
+                h->umi[slot[i]] = info[i].code;
+            }
+        });
     }
     pt.lap("pass 3 numbering + offsets");
     h->seq.resize(seq_tot); h->qual.resize(qual_tot); h->cigar.resize(cig_tot);
