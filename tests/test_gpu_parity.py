@@ -421,7 +421,17 @@ def test_barcode_with_many_dynamic_alleles_at_one_locus(codes):
     assert not problems, "\n".join(problems)
 
 
-@pytest.mark.parametrize("seed", list(range(101, 113)))
+def _fuzz_seeds():
+    """Seeds of the differential fuzz; SMC_FUZZ_SEEDS=a:b runs a wider sweep by hand (e.g. 200:300)."""
+    import os
+    spec = os.environ.get("SMC_FUZZ_SEEDS")
+    if spec:
+        a, b = spec.split(":")
+        return list(range(int(a), int(b)))
+    return list(range(101, 113))
+
+
+@pytest.mark.parametrize("seed", _fuzz_seeds())
 def test_randomised_parameters_and_panels(seed):
     """Differential fuzz: panel shape, read-error knobs and every vc() parameter drawn from a seeded generator; the CUDA path
     (alternating plain / packed / target-trimmed encodings and chunked uploads) against the oracle, field by field."""
