@@ -52,6 +52,8 @@ def test_downsampling_drawn_by_the_product_matches_oracle_py2_sampler():
     assert sum(1 for d in details if d.get("nBC", 0) > d.get("ds", 1 << 30)) > 10
     g_rows = call_loci(soa, ivs, refs, prm, gpus=1)
     assert g_rows == o_rows
+    # the same through the trimmed + packed encoding (listing kernels, mask re-run) and as two shards
+    assert call_loci(soa.trim_to_targets(ivs), ivs, refs, prm, gpus=2, devices=[0, 0]) == o_rows
 
 
 def test_cli_end_to_end_files(tmp_path):
