@@ -353,7 +353,7 @@ static int pipe_chunks_for(const smc_reads_soa* R) {
 }
 
 // pipelined = false: everything on ctx->st, synchronised on return (smc_upload).
-// pipelined = true : scalars / CIGAR / loci on ctx->st; bases and qualities in ctx->pipe.n chunks of consecutive reads on
+// pipelined = true : scalars / CIGAR / loci on ctx->st; bases and qualities in ctx->pipe_n chunks of equal byte size on
 //                    ctx->st_copy, one event per chunk; returns without waiting (smc_call_batch synchronises both streams).
 static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc, const smc_umi_keep* K, bool pipelined) {
     if (!ctx) return SMC_E_ARG;
@@ -465,7 +465,7 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
     g_launches = 0;
     const int64_t n = ctx->n_reads, nl = ctx->n_loci;
     const uint32_t n_tiles = (uint32_t)((nl + 31) / 32);
-    uint32_t* small = ctx->d_small.as<uint32_t>();          // [0..1] u64 or/and  [4] NE  [5] gflags  [6] dyn count  [7] n_tasks  [8..9] u64 cvg sum
+    uint32_t* small = ctx->d_small.as<uint32_t>();          // words: enum SmallWord
     CK(cudaEventRecord(ctx->ev[2], ctx->st));
     int64_t NE = 0;
     int frag_bits_used = 32;
