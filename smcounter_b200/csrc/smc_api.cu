@@ -756,6 +756,7 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
     }
     // ---------------- K4
     uint32_t n_tasks_h = 0;
+    unsigned long long cvgsum = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (ctx->task_cap == 0) ctx->task_cap = 1u << 16;
         CK(ctx->d_tasks.ensure((size_t)ctx->task_cap * sizeof(FisherTask)));
@@ -773,21 +774,22 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
         B.fl2 = ctx->d_fl2.as<uint32_t>(); B.biallelic = ctx->d_bial.as<uint8_t>(); B.fisher_p = ctx->d_fp.as<double>();
         B.fisher_or = ctx->d_for.as<double>(); B.tasks = ctx->d_tasks.as<FisherTask>(); B.n_tasks = small + SW_N_TASKS; B.task_cap = ctx->task_cap;
         LAUNCH(k_call, nblk(nl, 128), 128, 0, B);
+        // k_fisher reads the task count on the device: launched for the whole task buffer (idle threads leave at once), so
+        // that no host round trip sits between the two kernels; an overflowing task list is noticed at the final sync
+        LAUNCH(k_fisher, nblk(ctx->task_cap, 128), 128, 0, ctx->d_tasks.as<FisherTask>(), small + SW_N_TASKS, ctx->task_cap, nl,
+               ctx->d_fp.as<double>(), ctx->d_for.as<double>(), ctx->d_fl1.as<uint32_t>(), ctx->d_fl2.as<uint32_t>());
+        CK(cudaMemsetAsync(small + SW_CVG_SUM, 0, 8, ctx->st));
+        LAUNCH(k_sum_cvg, std::min<unsigned>(nblk(nl, 256), 592u), 256, 0, ctx->d_loc.as<int32_t>() + (size_t)SMC_L_CVG * nl, nl,
+               (unsigned long long*)(small + SW_CVG_SUM));
+        CK(cudaEventRecord(ctx->ev[6], ctx->st));
         CK(cudaMemcpyAsync(&n_tasks_h, small + SW_N_TASKS, 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(&cvgsum, small + SW_CVG_SUM, 8, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
+        CK(cudaGetLastError());
         if (n_tasks_h <= ctx->task_cap) break;
+        if (attempt == 1) { ctx->err = "Fisher task list overflow"; return SMC_E_OVERFLOW; }
         ctx->task_cap = n_tasks_h + n_tasks_h / 4 + 1024;      // grow and redo the (cheap) call kernel
     }
-    if (n_tasks_h > 0)
-        LAUNCH(k_fisher, nblk(n_tasks_h, 128), 128, 0, ctx->d_tasks.as<FisherTask>(), small + SW_N_TASKS, ctx->task_cap, nl, ctx->d_fp.as<double>(),
-               ctx->d_for.as<double>(), ctx->d_fl1.as<uint32_t>(), ctx->d_fl2.as<uint32_t>());
-    LAUNCH(k_sum_cvg, std::min<unsigned>(nblk(nl, 256), 592u), 256, 0, ctx->d_loc.as<int32_t>() + (size_t)SMC_L_CVG * nl, nl,
-           (unsigned long long*)(small + SW_CVG_SUM));
-    CK(cudaEventRecord(ctx->ev[6], ctx->st));
-    unsigned long long cvgsum = 0;
-    CK(cudaMemcpyAsync(&cvgsum, small + SW_CVG_SUM, 8, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
-    CK(cudaGetLastError());
     cudaEventElapsedTime(&ctx->tm.ms_prep, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&ctx->tm.ms_sort, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&ctx->tm.ms_pileup, ctx->ev[4], ctx->ev[5]);
