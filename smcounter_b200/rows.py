@@ -177,19 +177,66 @@ def _filter_string(bits, hp_lc):
     return f
 
 
+_F4_TABLE = None
+
+
+def _f4_table():
+    """str of every value k / 10000 for k = 0 .. 10000: the fraction columns after rounding to 4 decimals."""
+    global _F4_TABLE
+    if _F4_TABLE is None:
+        _F4_TABLE = [repr(k / 10000.0) for k in range(10001)]
+    return _F4_TABLE
+
+
+def _f4_column(num, den):
+    """[_f4(n, d)] for integer arrays, vectorised: k = round(n / d * 1e4) is exact whenever the scaled value is not within
+    1e-6 of a half (the double rounding of the scaling is ~1e-12); the few near-ties go through py2round()."""
+    num = np.asarray(num, dtype=np.float64)
+    den = np.asarray(den, dtype=np.float64)
+    ok = den > 0
+    y = np.where(ok, num / np.where(ok, den, 1.0), 0.0) * 1e4
+    k = np.rint(y)
+    near = ok & (np.abs(y - np.floor(y) - 0.5) < 1e-6)
+    tab = _f4_table()
+    out = [tab[j] for j in np.clip(k, 0, 10000).astype(np.int64).tolist()]
+    for i in np.flatnonzero(near | (k > 10000) | (k < 0)).tolist():
+        out[i] = _f4(int(num[i]), int(den[i])) if den[i] > 0 else "0.0"
+    return out
+
+
+def _f2_column(x):
+    """[_f2(v)] for a float array (prediction indices), vectorised the same way."""
+    x = np.asarray(x, dtype=np.float64)
+    y = x * 100.0
+    k = np.rint(y)
+    near = (np.abs(y - np.floor(y) - 0.5) < 1e-6) | ~(np.abs(x) < 1e9)
+    out = [repr(v) for v in (k / 100.0).tolist()]
+    for i in np.flatnonzero(near).tolist():
+        out[i] = _f2(float(x[i]))
+    return out
+
+
+def _float_columns(res, n):
+    """The twelve per-base float columns (AF_*, UMF_*, PI_* in A, T, G, C order) as ready strings for every locus of the batch."""
+    atgc = (A_A, A_T, A_G, A_C)
+    return ([_f4_column(res.cnt[a, C_ALLELE, :n], res.loc[L_CVG, :n]) for a in atgc],
+            [_f4_column(res.cnt[a, C_MT, :n], res.loc[L_USEDMT, :n]) for a in atgc],
+            [_f2_column(res.pi[a, :n]) for a in atgc])
+
+
 _POOL_JOB = None          # inputs of the forked formatting workers (inherited, never pickled)
 PARALLEL_MIN_ROWS = 60000        # below this the fork + pickle overhead exceeds the ~10 us per row of the inline loop
 
 
 def _format_slice(bounds):
-    res, reads, loci, chroms, refs, hpLen, order, hp_flags = _POOL_JOB
+    res, reads, loci, chroms, refs, hpLen, order, hp_flags, cols = _POOL_JOB
     try:
-        return format_rows(res, reads, loci, chroms, refs, hpLen, order[bounds[0]:bounds[1]], workers=1, hp_flags=hp_flags)
+        return format_rows(res, reads, loci, chroms, refs, hpLen, order[bounds[0]:bounds[1]], workers=1, hp_flags=hp_flags, _cols=cols)
     except RuntimeError as e:                  # plain message: survives pickling back to the parent
         return e
 
 
-def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, workers=None, hp_flags=None):
+def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, workers=None, hp_flags=None, _cols=None):
     """The 45-field rows of vc() (smCounter.py:575-600) for ``locus_order`` (indices into loci; default all, in order).
 
     Row formatting is per-locus string work, as independent as the reference's per-locus workers (smCounter.py:683-685):
@@ -214,7 +261,7 @@ def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, workers
         order = np.arange(loci.n) if locus_order is None else np.asarray(locus_order)
         nchunk = max(2, min(n_rows // 8192, workers * 2))
         cuts = [(n_rows * k) // nchunk for k in range(nchunk + 1)]
-        _POOL_JOB = (res, reads, loci, chroms, refs, hpLen, order, hp_flags)
+        _POOL_JOB = (res, reads, loci, chroms, refs, hpLen, order, hp_flags, _float_columns(res, loci.n))   # columns once, inherited
         try:
             with mp.get_context("fork").Pool(min(workers, nchunk)) as pool:
                 parts = pool.map(_format_slice, list(zip(cuts[:-1], cuts[1:])), chunksize=1)
@@ -240,7 +287,7 @@ def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, workers
     c_allele = [cnt[a][C_ALLELE] for a in ATGC]
     c_mt = [cnt[a][C_MT] for a in ATGC]
     c_strong = [cnt[a][C_STRONG] for a in ATGC]
-    pi_atgc = [pi[a] for a in ATGC]
+    af_s, umf_s, pi_s = _cols if _cols is not None else _float_columns(res, n)
     bad_status = ST_NEED_DOWNSAMPLE | ST_UMI_OVERFLOW | ST_BAD_MASK
     zero_tail = "\t" * 42 + "Zero_Coverage"
     rows = []
@@ -285,9 +332,9 @@ def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, workers
                     "%d\t%d\t%d\t%d\t%s\t%s\t%s\t%s\t%d\t%d\t%d\t%d\t%s\t%s\t%s\t%s\t%s" % (
                         chrom, pos, ref, alt, vtype, cvg, l_allfrag[i], l_allmt[i], l_usedfrag[i], usedMT,
                         _f2(v_pi), v_dp, _f4(v_dp, cvg), v_mt, _f4(v_mt, usedMT), v_sm,
-                        a0, a1c, a2c, a3c, _f4(a0, cvg), _f4(a1c, cvg), _f4(a2c, cvg), _f4(a3c, cvg),
+                        a0, a1c, a2c, a3c, af_s[0][i], af_s[1][i], af_s[2][i], af_s[3][i],
                         l_mt3[i], l_mt5[i], l_mt7[i], l_mt10[i],
-                        m0, m1, m2, m3, _f4(m0, usedMT), _f4(m1, usedMT), _f4(m2, usedMT), _f4(m3, usedMT),
+                        m0, m1, m2, m3, umf_s[0][i], umf_s[1][i], umf_s[2][i], umf_s[3][i],
                         c_strong[0][i], c_strong[1][i], c_strong[2][i], c_strong[3][i],
-                        _f2(pi_atgc[0][i]), _f2(pi_atgc[1][i]), _f2(pi_atgc[2][i]), _f2(pi_atgc[3][i]), fltr))
+                        pi_s[0][i], pi_s[1][i], pi_s[2][i], pi_s[3][i], fltr))
     return rows

@@ -381,3 +381,23 @@ def test_bench_rank_batches_partition_the_panel(monkeypatch):
     assert sorted(got) == sorted(want) and len(got) == len(set(got))
     one = bench.make_batch(args, 0, 1)[0]
     assert one == panel_intervals_from_bed(bench.PANEL_BED, limit=args.intervals, seed=args.seed)
+
+
+def test_vectorised_float_columns_equal_the_scalar_py2_formatting():
+    """rows._f4_column / _f2_column (numpy, table lookup) against the scalar py2round + repr path, including exact decimal
+    ties (multiples of 1/32, odd multiples of 1/20000 and 1/200) where Python-2 rounds half away from zero."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    den = rng.integers(1, 40000, size=60000)
+    num = (rng.random(60000) * den).astype(np.int64)
+    num[:2000] = np.arange(2000); den[:2000] = 32
+    num[2000:4000] = np.arange(1, 4001, 2)[:2000]; den[2000:4000] = 20000
+    num[4000:4010] = 0; den[4010:4020] = 0; num[4010:4020] = 0
+    got = rows._f4_column(num, den)
+    want = [rows._f4(int(a), int(b)) if b > 0 else "0.0" for a, b in zip(num, den)]
+    assert got == want and "0.0313" in got and "1.0" in got
+    x = np.concatenate([rng.random(40000) * 300, rng.random(20000) * 1e5, np.arange(0, 2000) / 8.0, np.arange(1, 4001, 2) / 200.0,
+                        [0.0, 0.005, 0.015, 16.0, 1e9, 2.5e10]])
+    assert rows._f2_column(x) == [rows._f2(float(v)) for v in x]
+    for v in (0.125, 2.675, 1.005, 0.5, 105.585):
+        assert rows._f2(v) == py2compat.py2str(py2compat.py2round(v, 2))
