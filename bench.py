@@ -158,12 +158,25 @@ class ClockSampler(threading.Thread):
 # CPU baseline: the oracle port of the reference's vc() on the host cores (bounded sample of the same workload)
 # --------------------------------------------------------------------------------------------------------------
 _G = {}
+CPU_WHAT = {"reference": "the reference's own vc_wrapper() (oracle/_ref = /root/reference/smCounter.py via oracle/ref_build.py; pysam stand-in over "
+                         "in-memory reads, plain dict/set containers)",
+            "port": "oracle/smcounter_oracle.py (Python-3 port; oracle/_ref not built)"}
+
+
+def cpu_kind():
+    """'reference': oracle/_ref (the reference's own smCounter.py made runnable by oracle/ref_build.py, plain containers,
+    pysam stand-in) is present; 'port': only the oracle restatement is."""
+    from oracle import ref_build
+    return "reference" if ref_build.available() else "port"
 
 
 def _cpu_worker(job):
     from oracle import smcounter_oracle as orc
     chrom, pos = job
     p = _G["prm"]
+    if _G.get("ref") is not None:          # the reference's vc_wrapper(), exactly as its Pool calls it (smCounter.py:684)
+        return _G["ref"].vc_wrapper("bench.bam", chrom, pos, p.minBQ, p.minMQ, p.mtDepth, p.rpb, p.hpLen, p.mismatchThr, p.mtDrop,
+                                    p.maxMT, p.primerDist, "bench.fa")
     return orc.vc(_G["index"], chrom, pos, p.minBQ, p.minMQ, p.mtDepth, p.rpb, p.hpLen, p.mismatchThr, p.mtDrop, p.maxMT,
                   p.primerDist, _G["refs"])
 
@@ -189,6 +202,12 @@ def cpu_sample_setup(soa, refs, loci, n_loci_sample):
     _G["index"] = orc.ReadIndex(recs)
     _G["refs"] = refs
     _G["prm"] = vc_params()
+    _G["ref"] = None
+    if cpu_kind() == "reference":
+        from oracle import ref_build, ref_shims
+        _G["ref"] = ref_build.load("native", inline_pool=False)
+        ref_shims.register_bam("bench.bam", _G["index"])
+        ref_shims.register_fasta("bench.fa", refs)
     jobs = [(soa.chroms[int(loci.ref_id[i])], str(int(loci.pos0[i]) + 1)) for i in sel]
     return jobs, len(recs)
 
@@ -283,8 +302,8 @@ def main():
                 "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
                 "config": {"workload": "cfg2 synthetic N0030 194-gene panel, 3000 UMIs/locus, rpb 4, 2x150bp",
                            "sample": "%d consecutive loci, %d reads, %d pileup events per step" % (len(jobs), nrec, ev)},
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": "%d loci per step x %d steps (oracle/smcounter_oracle.py, multiprocessing.Pool)" % (len(jobs), args.steps)},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
+                                 "sample": "%d loci per step x %d steps (%s, multiprocessing.Pool(%d))" % (len(jobs), args.steps, CPU_WHAT[cpu_kind()], cores)},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -456,9 +475,9 @@ def main():
         n_sample = args.cpu_loci or 160 * cores          # ~10-15 s of host work
         jobs, nrec = cpu_sample_setup(soa_full, refs, loci, n_sample)
         v, dt, ev = cpu_run(jobs, cores)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "%d consecutive loci of the rank-0 batch (%d reads, %d pileup events), oracle/smcounter_oracle.py "
-                                          "with multiprocessing.Pool(%d), %.1f s" % (len(jobs), nrec, ev, cores, dt),
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
+                                "sample": "%d consecutive loci of the rank-0 batch (%d reads, %d pileup events), %s "
+                                          "with multiprocessing.Pool(%d), %.1f s" % (len(jobs), nrec, ev, CPU_WHAT[cpu_kind()], cores, dt),
                                 "archived_reference": "4.15 loci/s on 10 processes at DP~58k (example run log, 2017 hardware)"}
     if rank == 0:
         print(json.dumps(line))
