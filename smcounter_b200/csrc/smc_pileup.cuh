@@ -318,7 +318,9 @@ __device__ __noinline__ uint32_t dyn_lookup(DynTab T, unsigned long long key, ui
 #define KA_WARP_WORDS(LIST) (256 + 32 + 512 + 128 + ((LIST) ? 256 : 0))   // GRec stage | srank | event codes | fragment-code staging | first-read staging
 #define KA_SMEM_BYTES(LIST) (64 + KA_WARPS * KA_WARP_WORDS(LIST) * 4)
 
-// slow-path event code (internal to k_gather)
+// event code (internal to k_gather).  Staged codes of plain aligned reads: quality in bits 0-7, allele slot (A0 C1 T3 G4,
+// 7 = N / IUPAC) in bits 8-10 like the fragment code; codes returned by slow_event: BAM nibble in bits 8-11
+#define SC_AID_SH   8u
 #define EC_NIB_SH   8u
 #define EC_COVERED  (1u << 12)
 #define EC_DYN      (1u << 13)    // regular base that is not A/C/G/T (N / IUPAC): dynamic allele row
@@ -568,6 +570,7 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
     uint32_t fcount = 0, ext = 0, umi_k = 0, since_flush = 0;
     uint32_t carry_ur = 0xffffffffu, carry_fr = 0xffffffffu;          // ranks of the previous batch's last event
     bool open = false, umi_first = true, dead = false;
+    uint32_t simplemask_cur = 0;                                      // "plain aligned run" bits of the staged batch
     uint16_t* const cst16 = reinterpret_cast<uint16_t*>(cst) + 2 * lane;
 
     auto flush_codes = [&](uint32_t f0) {
@@ -599,15 +602,6 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
         if ((fcount & 7u) == 0u) flush_codes(fcount - 8u);
         fs = 0; f_first = 0xffffffffu; umi_first = false;
     };
-    // warp-uniform bookkeeping at the first event of a fragment
-    auto boundary = [&](bool umi_start, int j) {
-        if (open) emit();
-        if (umi_start) {
-            umi_first = true;
-            if (A.umi_urank) { if (lane == 0) A.umi_urank[eb + umi_k] = __ldg(&A.urank_s[srank_s[j]]); ++umi_k; }
-        }
-        open = true;
-    };
     // fragment merge of an event that passed incCond (smCounter.py:467-479); `one` = register field of an A/C/G/T base, else 0
     auto merge = [&](uint32_t mid, uint32_t bq, bool isN, uint32_t one, int j) {
         if (LIST) f_first = min(f_first, __ldg(&A.recs[srank_s[j]].read_idx));
@@ -625,14 +619,61 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
         }
     };
 
-    for (uint32_t base = eb; base < ee; base += 32) {
+    // one pileup event of the ordered (generic) pass: the staged event code of a plain aligned read, or the per-event CIGAR
+    // walk of any other read (out of line); then the fragment merge
+    auto gen_event = [&](int e) {
+        uint32_t cd, mid, one; bool isN = false;
+        if ((simplemask_cur >> e) & 1u) {
+            cd = evc[e * 32 + lane];
+            mid = (cd >> SC_AID_SH) & 7u;
+            one = 1u << (((mid * 3u + 1u) << 1) & 0x18u);                            // register field of A0 C1 T3 G4
+            if (cd & EC_DYN) {                                                   // rare: N / IUPAC base -> dynamic allele row
+                const uint32_t* rw = ws + e * 8;
+                const uint32_t meta = rw[3];
+                const bool le20 = (uint32_t)(p - (int32_t)rw[6]) <= ((meta & GM_LE_INF) ? WIN_INF : 20u);
+                const bool ple = (uint32_t)(p - (int32_t)rw[7]) <= ((meta & GM_PLE_INF) ? WIN_INF : pspan);
+                const uint32_t dfl = ((meta & RM_REVERSE) ? 0u : 1u) | ((int)(cd & 255u) < minBQ ? 2u : 0u) | ((cd & EC_INC) ? 4u : 0u) |
+                                     ((meta & RM_READ2) ? 8u : 0u) | (le20 ? 16u : 0u) | (ple ? 32u : 0u);
+                const uint32_t en = dyn_base_event(A.T, seqp, rw[4], (uint32_t)Li, __ldg(&A.recs[srank_s[e]].read_idx), p + (int32_t)rw[2], dfl);
+                mid = NF + (en & 0x7fffffffu); isN = en >> 31; one = 0;
+            }
+        } else {                                                             // rare: per-event CIGAR walk, out of line
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&A.recs[srank_s[e]]);
+            const uint2 ev = slow_event(A.T, rw, A.cigar, seqp, qualp, p, Li, minBQ, A.primerDist);
+            cd = ev.x; mid = ev.y; one = 0;
+            if (cd & EC_COVERED) {
+                const uint32_t meta = __ldg(rw + 3);
+                const bool lowq = (int)(cd & 255u) < minBQ;
+                cvg++;
+                if (cd & EC_REGULAR) {
+                    if (!(cd & EC_DYN)) {
+                        const uint32_t lv = lut[(cd >> EC_NIB_SH) & 15u];
+                        one = lv & 0x0fffffffu; mid = lv >> 28;
+                        tally_regular(R, one, (cd & EC_INC) ? one : 0u, meta & RM_REVERSE, meta & RM_READ2, lowq, cd & EC_LE20, cd & EC_PLE);
+                    } else {
+                        const uint32_t dfl = ((meta & RM_REVERSE) ? 0u : 1u) | (lowq ? 2u : 0u) | ((cd & EC_INC) ? 4u : 0u) |
+                                             ((meta & RM_READ2) ? 8u : 0u) | ((cd & EC_LE20) ? 16u : 0u) | ((cd & EC_PLE) ? 32u : 0u);
+                        const uint32_t en = dyn_base_event(A.T, seqp, __ldg(rw + 4), (uint32_t)Li, __ldg(rw + 10), (int)ev.y, dfl);
+                        mid = NF + (en & 0x7fffffffu); isN = en >> 31;
+                    }
+                } else if (mid == (uint32_t)SMC_A_DEL) {
+                    atomicAdd(&A.cnt[((size_t)SMC_A_DEL * SMC_NCNT + SMC_C_ALLELE) * nl + L], 1);   // alleleCnt only (:416-421, :459)
+                }
+            }
+        }
+        if (cd & EC_COVERED) fs |= FS_SEEN;                                  // :463-464
+        if (cd & EC_INC) merge(mid, cd & 255u, isN, one, e);                 // :467-479
+    };
+
+    for (uint32_t base = eb; base < ee;) {
         const int nb = (int)min(32u, ee - base);
         // ---------------- stage
         // boundaries from the dense barcode / fragment ranks of consecutive events (a unit always starts at a barcode start);
         // slots past the end: an empty simple read, no boundary
         bool ub = false, fb = false, simple = true;
+        uint32_t ur = 0xffffffffu, fr = 0xffffffffu;
         {
-            uint4 g0 = make_uint4(0u, 0u, 0u, 0u), g1 = g0; uint32_t sr = 0, ur = 0xffffffffu, fr = 0xffffffffu;
+            uint4 g0 = make_uint4(0u, 0u, 0u, 0u), g1 = g0; uint32_t sr = 0;
             if (lane < nb) {
                 sr = __ldg(&A.ev_read[base + lane]);
                 ur = __ldg(&A.urank_s[sr]); fr = __ldg(&A.frank_s[sr]);
@@ -644,7 +685,6 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
             if (lane == 0) { pur = carry_ur; pfr = carry_fr; }
             ub = lane < nb && ur != pur;
             fb = lane < nb && (ub || fr != pfr);
-            carry_ur = __shfl_sync(FULL_MASK, ur, nb - 1); carry_fr = __shfl_sync(FULL_MASK, fr, nb - 1);
             uint4* dst = reinterpret_cast<uint4*>(ws + lane * 8);
             dst[0] = g0; dst[1] = g1;
             srank_s[lane] = sr;
@@ -652,20 +692,31 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
         const uint32_t fragmask = __ballot_sync(FULL_MASK, fb);
         const uint32_t umimask = __ballot_sync(FULL_MASK, ub);
         const uint32_t simplemask = __ballot_sync(FULL_MASK, simple);
+        simplemask_cur = simplemask;
+        // Events consumed from this batch: when more events follow, stop before the last fragment start, so that a fragment
+        // that starts in a batch also ends in it (a fragment of 32+ events is carried across batches by the ordered pass).
+        int ncons = nb;
+        bool tail_open = false;
+        if (base + (uint32_t)nb < ee) {
+            const int last = 31 - __clz((int)(fragmask | 1u));
+            if (last > 0) ncons = last; else tail_open = true;
+        }
+        carry_ur = __shfl_sync(FULL_MASK, ur, ncons - 1); carry_fr = __shfl_sync(FULL_MASK, fr, ncons - 1);
         if (since_flush + 32u > 255u) { flush_gather_regs(A.cnt, nl, L, lane_valid, R); since_flush = 0; }
-        since_flush += 32u;
+        since_flush += (uint32_t)ncons;
         __syncwarp();
-        // ---------------- gather + tally (order independent), KA_GATHER reads at a time; what the ordered pass needs goes to
-        // shared memory as a 16-bit event code
+        // ---------------- gather + tally (order independent) of the plain aligned reads, KA_GATHER reads at a time; what the
+        // fragment pass needs goes to shared memory as a 16-bit event code (bits as in the fragment code: quality, allele slot)
+        uint32_t odd = 0;                                                        // events where this lane sees an N / IUPAC base
 #pragma unroll 1
-        for (int g = 0; g < nb; g += KA_GATHER) {
+        for (int g = 0; g < ncons; g += KA_GATHER) {
             uint32_t sbv[KA_GATHER], bqv[KA_GATHER], fl[KA_GATHER];
 #pragma unroll
             for (int u = 0; u < KA_GATHER; ++u) {
                 const uint32_t* rw = ws + (g + u) * 8;
                 const uint4 qa = *reinterpret_cast<const uint4*>(rw);        // lo gspan qk meta
                 const uint4 qb = *reinterpret_cast<const uint4*>(rw + 4);    // seq_off qual_off le_lo ple_lo
-                const bool cov = (uint32_t)(Li - (int32_t)qa.x) < qa.y;
+                const bool cov = (g + u < ncons) && (uint32_t)(Li - (int32_t)qa.x) < qa.y;
                 const uint32_t qpos = (uint32_t)(p + (int32_t)qa.z);
                 sbv[u] = 0; bqv[u] = 0;
                 if (cov) {
@@ -683,65 +734,105 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
                 const bool cov = f & 16u;
                 const uint32_t nib = (f & 128u) ? (sbv[u] & 15u) : (sbv[u] >> 4);   // 0 when not covered
                 const uint32_t bq = bqv[u];
-                const uint32_t one = lut[nib] & 0x0fffffffu;                         // 0 when not covered or not A/C/G/T
+                const uint32_t lv = lut[nib];
+                const uint32_t one = lv & 0x0fffffffu;                               // 0 when not covered or not A/C/G/T
                 const bool lowq = (int)bq < minBQ;
                 const bool inc = cov && !lowq && (f & RM_OK);                        // :431
+                const bool dynb = cov && !one;
                 cvg += cov ? 1 : 0;                                                  // :368
                 tally_regular(R, one, inc ? one : 0u, f & RM_REVERSE, f & RM_READ2, lowq, f & 32u, f & 64u);
-                evc[(g + u) * 32 + lane] = (uint16_t)(bq | (nib << EC_NIB_SH) | (cov ? EC_COVERED : 0u) | ((cov && !one) ? EC_DYN : 0u) |
+                odd |= (dynb ? 1u : 0u) << (g + u);
+                evc[(g + u) * 32 + lane] = (uint16_t)(bq | ((dynb ? 7u : (lv >> 28)) << SC_AID_SH) | (cov ? EC_COVERED : 0u) | (dynb ? EC_DYN : 0u) |
                                                       (inc ? EC_INC : 0u));
             }
         }
-        // ---------------- ordered pass: fragment boundaries, fragment merge (smCounter.py:467-479), the rare events
+        const uint32_t oddmask = __reduce_or_sync(FULL_MASK, odd);
+        // fragment structure of the batch, one event per lane: which fragments are complete runs of one or two plain
+        // aligned reads without an N / IUPAC base in any lane (fast path), and which of those have two reads
+        uint32_t fastmask, twomask;
+        {
+            const uint32_t restk = __funnelshift_rc(fragmask, 0u, (uint32_t)lane + 1u);      // fragmask >> (lane + 1)
+            int endk = restk ? lane + __ffs((int)restk) : 32;
+            endk = min(endk, ncons);
+            const int nk = endk - lane;
+            const uint32_t m2 = nk == 2 ? 3u : 1u;
+            const bool fastk = !LIST && lane < ncons && ((fragmask >> lane) & 1u) && (endk < ncons || !tail_open) && nk <= 2 &&
+                               (((simplemask & ~oddmask) >> lane) & m2) == m2;
+            fastmask = __ballot_sync(FULL_MASK, fastk);
+            twomask = __ballot_sync(FULL_MASK, fastk && nk == 2);
+        }
+        int j = 0;
 #pragma unroll 1
-        for (int j = 0; j < nb; ++j) {
-            if ((fragmask >> j) & 1u) boundary((umimask >> j) & 1u, j);              // warp uniform
-            uint32_t cd, mid, one; bool isN = false;
-            if ((simplemask >> j) & 1u) {
-                cd = evc[j * 32 + lane];
-                const uint32_t lv = lut[(cd >> EC_NIB_SH) & 15u];
-                one = lv & 0x0fffffffu; mid = lv >> 28;
-                if (cd & EC_DYN) {                                                   // rare: N / IUPAC base -> dynamic allele row
-                    const uint32_t* rw = ws + j * 8;
-                    const uint32_t meta = rw[3];
-                    const bool le20 = (uint32_t)(p - (int32_t)rw[6]) <= ((meta & GM_LE_INF) ? WIN_INF : 20u);
-                    const bool ple = (uint32_t)(p - (int32_t)rw[7]) <= ((meta & GM_PLE_INF) ? WIN_INF : pspan);
-                    const uint32_t dfl = ((meta & RM_REVERSE) ? 0u : 1u) | ((int)(cd & 255u) < minBQ ? 2u : 0u) | ((cd & EC_INC) ? 4u : 0u) |
-                                         ((meta & RM_READ2) ? 8u : 0u) | (le20 ? 16u : 0u) | (ple ? 32u : 0u);
-                    const uint32_t e = dyn_base_event(A.T, seqp, rw[4], (uint32_t)Li, __ldg(&A.recs[srank_s[j]].read_idx), p + (int32_t)rw[2], dfl);
-                    mid = NF + (e & 0x7fffffffu); isN = e >> 31;
+        while (j < ncons) {
+            if ((fastmask >> j) & 1u) {
+                // ---------------- fast path: complete fragments of one or two plain aligned reads, two fragments at a time:
+                // the fragment merge of (at most) two reads in BAM order (smCounter.py:467-479) in closed form
+                if (open) { emit(); open = false; }                                     // a carried fragment ends here
+                const int n = 1 + (int)((twomask >> j) & 1u);
+                const int j2 = j + n;
+                const int n2 = (__funnelshift_rc(fastmask, 0u, (uint32_t)j2) & 1u) ? 1 + (int)(__funnelshift_rc(twomask, 0u, (uint32_t)j2) & 1u) : 0;
+                const uint16_t* ev = evc + lane;
+                uint32_t c[4];
+                c[0] = ev[j * 32];
+                c[1] = n == 2 ? ev[(j + 1) * 32] : 0u;
+                c[2] = n2 ? ev[j2 * 32] : 0u;
+                c[3] = n2 == 2 ? ev[(j2 + 1) * 32] : 0u;
+                uint32_t codes2[2];
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    const uint32_t c0 = c[2 * f], c1 = c[2 * f + 1];
+                    const bool i0 = c0 & EC_INC, i1 = c1 & EC_INC;
+                    const bool both = i0 && i1;
+                    const bool same = ((c0 ^ c1) & (7u << SC_AID_SH)) == 0u;
+                    const uint32_t one1 = 1u << (((((c1 >> SC_AID_SH) & 7u) * 3u + 1u) << 1) & 0x18u);
+                    if (both) { if (same) R.conc += one1; else R.disc += one1; }        // keyed by the later read's base
+                    const uint32_t sel = i0 ? c0 : c1;
+                    const uint32_t bqf = both ? min(c0 & 255u, c1 & 255u) : (sel & 255u);
+                    const bool exists = both ? same : (i0 || i1);
+                    const uint32_t st = exists ? 3u : (i0 || i1) ? 2u : ((c0 | c1) & EC_COVERED) ? 1u : 0u;
+                    codes2[f] = (st << FC_ST_SH) | ((both && same) ? FC_PAIRED : 0u) | (sel & (7u << FC_AID_SH)) | bqf;
                 }
-            } else {                                                                 // rare: per-event CIGAR walk, out of line
-                const uint32_t* rw = reinterpret_cast<const uint32_t*>(&A.recs[srank_s[j]]);
-                const uint2 ev = slow_event(A.T, rw, A.cigar, seqp, qualp, p, Li, minBQ, A.primerDist);
-                cd = ev.x; mid = ev.y; one = 0;
-                if (cd & EC_COVERED) {
-                    const uint32_t meta = __ldg(rw + 3);
-                    const bool lowq = (int)(cd & 255u) < minBQ;
-                    cvg++;
-                    if (cd & EC_REGULAR) {
-                        if (!(cd & EC_DYN)) {
-                            const uint32_t lv = lut[(cd >> EC_NIB_SH) & 15u];
-                            one = lv & 0x0fffffffu; mid = lv >> 28;
-                            tally_regular(R, one, (cd & EC_INC) ? one : 0u, meta & RM_REVERSE, meta & RM_READ2, lowq, cd & EC_LE20, cd & EC_PLE);
-                        } else {
-                            const uint32_t dfl = ((meta & RM_REVERSE) ? 0u : 1u) | (lowq ? 2u : 0u) | ((cd & EC_INC) ? 4u : 0u) |
-                                                 ((meta & RM_READ2) ? 8u : 0u) | ((cd & EC_LE20) ? 16u : 0u) | ((cd & EC_PLE) ? 32u : 0u);
-                            const uint32_t e = dyn_base_event(A.T, seqp, __ldg(rw + 4), (uint32_t)Li, __ldg(rw + 10), (int)ev.y, dfl);
-                            mid = NF + (e & 0x7fffffffu); isN = e >> 31;
-                        }
-                    } else if (mid == (uint32_t)SMC_A_DEL) {
-                        atomicAdd(&A.cnt[((size_t)SMC_A_DEL * SMC_NCNT + SMC_C_ALLELE) * nl + L], 1);   // alleleCnt only (:416-421, :459)
-                    }
+                {
+                    const bool ustart = (umimask >> j) & 1u;
+                    if (ustart && A.umi_urank) { if (lane == 0) A.umi_urank[eb + umi_k] = __ldg(&A.urank_s[srank_s[j]]); ++umi_k; }
+                    const uint32_t k = fcount & 7u;
+                    cst16[((k >> 1) << 6) + (k & 1u)] = (uint16_t)(codes2[0] | (ustart ? FC_UMIFIRST : 0u));
+                    ++fcount;
+                    if ((fcount & 7u) == 0u) flush_codes(fcount - 8u);
                 }
+                if (n2) {
+                    const bool ustart = (umimask >> j2) & 1u;
+                    if (ustart && A.umi_urank) { if (lane == 0) A.umi_urank[eb + umi_k] = __ldg(&A.urank_s[srank_s[j2]]); ++umi_k; }
+                    const uint32_t k = fcount & 7u;
+                    cst16[((k >> 1) << 6) + (k & 1u)] = (uint16_t)(codes2[1] | (ustart ? FC_UMIFIRST : 0u));
+                    ++fcount;
+                    if ((fcount & 7u) == 0u) flush_codes(fcount - 8u);
+                }
+                umi_first = false;
+                j = j2 + n2;
+                continue;
             }
-            if (cd & EC_COVERED) fs |= FS_SEEN;                                      // :463-464
-            if (cd & EC_INC) merge(mid, cd & 255u, isN, one, j);                     // :467-479
+            // ---------------- ordered pass over the segment: fragment boundary, per-event merge, the rare events
+            const uint32_t rest = __funnelshift_rc(fragmask, 0u, (uint32_t)j + 1u);
+            int n = rest ? __ffs((int)rest) : 32;                              // the segment that starts at event j: up to the next fragment start
+            n = min(n, ncons - j);
+            if ((fragmask >> j) & 1u) {
+                if (open) emit();
+                const bool ustart = (umimask >> j) & 1u;
+                umi_first = ustart;
+                if (ustart && A.umi_urank) { if (lane == 0) A.umi_urank[eb + umi_k] = __ldg(&A.urank_s[srank_s[j]]); ++umi_k; }
+                open = true;
+            }
+#pragma unroll 1
+            for (int e = j; e < j + n; ++e) gen_event(e);
+            if ((j + n < ncons) || !tail_open) { emit(); open = false; }        // the fragment is complete
+            j += n;
         }
         __syncwarp();
+        base += (uint32_t)ncons;
     }
-    // ---- close the last fragment, write the partial group, flush the tallies
-    emit();
+    // ---- close a fragment that is still open, write the partial group, flush the tallies
+    if (open) emit();
     if (fcount & 7u) flush_codes(fcount & ~7u);
     if (lane == 0) A.unit_nfrag[unit] = dead ? 0u : fcount;
     flush_gather_regs(A.cnt, nl, L, lane_valid, R);

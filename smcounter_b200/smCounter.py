@@ -139,6 +139,19 @@ def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None
     return interleave_rows(plan, intervals, shard_rows)
 
 
+def _read_track(path, flag, ncol):
+    """A repeat track of main() (smCounter.py:699-710).  The reference hands the path to bedtools under check_call, so a
+    missing file aborts the run; silently skipping it would report variants inside repeats as PASS.  Opting out is explicit:
+    pass an empty string or 'none'."""
+    if path is None or str(path).strip().lower() in ("", "none"):
+        print("warning: %s disabled; its repeat filters (%s) are not applied" % (flag, "RepT" if ncol == 3 else "RepS/LowC/SL"))
+        return []
+    if not os.path.exists(path):
+        raise IOError("%s: no such file: %r (the reference's bedtools call fails on a missing track; pass %s=none to run "
+                      "without this filter)" % (flag, path, flag))
+    return repeats.read_bed_rows(path, ncol) if ncol == 4 else repeats.read_bed_rows(path)
+
+
 def main(args):
     timeStart = datetime.datetime.now()
     print("smCounter started at " + str(timeStart))
@@ -171,10 +184,8 @@ def main(args):
 
     print("begin variant filtering and output")                           # :697
     target_rows = [tuple(l.strip().split('\t')[0:3]) for l in bed_lines if not l.startswith("track ") and l.strip()]
-    trf_rows = repeats.read_bed_rows(args.bedTandemRepeats) if args.bedTandemRepeats and os.path.exists(args.bedTandemRepeats) else []
-    rm_rows = repeats.read_bed_rows(args.bedRepeatMaskerSubset, 4) if args.bedRepeatMaskerSubset and os.path.exists(args.bedRepeatMaskerSubset) else []
-    if not trf_rows and not rm_rows:
-        print("warning: repeat tracks not found; RepT/RepS/LowC/SL filters are not applied")
+    trf_rows = _read_track(args.bedTandemRepeats, "--bedTandemRepeats", 3)
+    rm_rows = _read_track(args.bedRepeatMaskerSubset, "--bedRepeatMaskerSubset", 4)
     trf, rm = repeats.build_repeat_regions(target_rows, trf_rows, rm_rows)
     output = repeats.apply_repeat_filters(output, trf, rm)
     threshold = writers.write_outputs(output, args.outPrefix, args.mtDepth, args.threshold)

@@ -21,6 +21,78 @@ def test_parity_case(name):
     assert stats["events"] > 0
 
 
+def _ref_rows_fixture():
+    import json, os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "ref_rows.json")) as fh:
+        return json.load(fh)["cases"]
+
+
+@pytest.mark.parametrize("name", sorted(_ref_rows_fixture()))
+def test_product_rows_equal_the_reference_codes_rows(name):
+    """tests/golden/ref_rows.json holds the rows the REFERENCE'S OWN vc() printed (smCounter.py run through oracle/ref_build.py with
+    Python-2 container order; made by tests/golden/make_ref_rows.py).  The product path -- call_loci(): C-ABI, CUDA kernels,
+    its own Py2 down-sampling emulation, host row formatting -- must print the same bytes."""
+    from fuzz import case_inputs
+    from smcounter_b200.smCounter import call_loci
+    from smcounter_b200.synth import make_panel
+    want = _ref_rows_fixture()[name]
+    if name.startswith("fuzz"):
+        seed = int(name[4:])
+        ivs, spec, prm = fuzz_case(seed)
+    else:
+        ivs, spec, prm, seed = case_inputs(name)
+    soa, refs, _ = make_panel(ivs, spec, seed=seed)
+    got = call_loci(soa, ivs, refs, prm, gpus=1)
+    assert len(got) == len(want)
+    bad = [(g, w) for g, w in zip(got, want) if g != w]
+    assert not bad, "%d rows differ, first: %r vs %r" % (len(bad), bad[0][0], bad[0][1])
+
+
+def test_cli_files_equal_the_files_of_the_references_main(tmp_path):
+    """The reference's main() (oracle/_ref: BED -> vc per locus -> bedtools repeat filters -> three files) against the product
+    CLI on the same BAM / BED / FASTA / repeat tracks: all three output files byte-identical."""
+    from oracle import ref_build, ref_shims
+    from oracle import smcounter_oracle as orc
+    if not ref_build.available():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    from smcounter_b200 import bam, smCounter
+    from smcounter_b200.soa import soa_to_records
+    from smcounter_b200.synth import make_panel
+    ivs = [("chr1", 1000, 1150), ("chr2", 600, 640), ("chr1", 1100, 1120)]
+    spec = SynthSpec(umis_per_locus=80, rpb=3.0, snv_every=40, snv_vaf=0.2, indel_every=60, indel_vaf=0.15)
+    soa, refs, _ = make_panel(ivs, spec, seed=31)
+    fa = tmp_path / "ref.fa"
+    with open(fa, "w") as fh:
+        for c in soa.chroms:
+            s = refs.fetch(c, 0, refs.get_reference_length(c))
+            fh.write(">%s\n" % c)
+            for i in range(0, len(s), 60):
+                fh.write(s[i:i + 60] + "\n")
+    bed = tmp_path / "target.bed"
+    bed.write_text("track name=t\n" + "".join("%s\t%d\t%d\n" % iv for iv in ivs))
+    trf = tmp_path / "trf.bed"; trf.write_text("chr1\t1010\t1040\nchr2\t0\t700\n")
+    rm = tmp_path / "rm.bed"
+    rm.write_text("chr1\t1030\t1060\tSimple_repeat\nchr1\t1055\t1100\tLow_complexity\nchr1\t1101\t1105\tSatellite\nchr2\t610\t620\tL1\n")
+    bam_path = tmp_path / "reads.bam"
+    bam.write_bam(str(bam_path), soa, refs.lengths)
+    common = {"bedTarget": str(bed), "mtDepth": 80, "rpb": 3.0, "bedTandemRepeats": str(trf), "bedRepeatMaskerSubset": str(rm), "threshold": 20}
+    smCounter.argParseInit()
+    thr = smCounter.main(dict(common, outPrefix=str(tmp_path / "gpu"), bamFile=str(bam_path), refGenome=str(fa)))
+    ref = ref_build.load("py2")
+    ref.parser = None
+    rbam = ref_shims.register_bam("mem:cli.bam", soa_to_records(soa, orc.Read))
+    rfa = ref_shims.register_fasta("mem:cli.fa", refs)
+    thr_ref = ref.main(dict(common, outPrefix=str(tmp_path / "ref"), bamFile=rbam, refGenome=rfa, bedtoolsPath="/nowhere/"))
+    ref_shims.clear_registries()
+    assert thr == thr_ref == 20
+    for ext in (".smCounter.all.txt", ".smCounter.cut.txt", ".smCounter.cut.vcf"):
+        a = open(str(tmp_path / "gpu") + ext).read(); b = open(str(tmp_path / "ref") + ext).read()
+        if ext.endswith(".vcf"):        # the sample column is named after outPrefix (smCounter.py:817)
+            a = a.replace(str(tmp_path / "gpu"), "X"); b = b.replace(str(tmp_path / "ref"), "X")
+        assert a == b, ext
+    assert open(str(tmp_path / "gpu") + ".smCounter.cut.txt").read().count("\n") > 3
+
+
 def test_downsampling_mask_from_oracle():
     """mtDepth far below the real depth: ds = 2*mtDepth fires on most loci; the CUDA path applies the read-selection mask
     the oracle produced (north_star) and must agree on everything downstream of it."""

@@ -401,3 +401,18 @@ def test_vectorised_float_columns_equal_the_scalar_py2_formatting():
     assert rows._f2_column(x) == [rows._f2(float(v)) for v in x]
     for v in (0.125, 2.675, 1.005, 0.5, 105.585):
         assert rows._f2(v) == py2compat.py2str(py2compat.py2round(v, 2))
+
+
+def test_missing_repeat_track_aborts_like_the_reference(tmp_path, capsys):
+    """smCounter.py:700-710 runs bedtools on both tracks under check_call: a missing file aborts the run.  The product must
+    not write PASS rows for variants inside repeats because a path was mistyped; opting out is explicit ('none')."""
+    from smcounter_b200 import smCounter
+    with pytest.raises(IOError, match="bedTandemRepeats"):
+        smCounter._read_track(str(tmp_path / "nope.bed"), "--bedTandemRepeats", 3)
+    with pytest.raises(IOError, match="bedRepeatMaskerSubset"):
+        smCounter._read_track("/qgen/home/xuc/UCSC/SR_LC_SL.nochr.bed", "--bedRepeatMaskerSubset", 4)
+    assert smCounter._read_track("none", "--bedTandemRepeats", 3) == []
+    assert smCounter._read_track("", "--bedRepeatMaskerSubset", 4) == []
+    assert "disabled" in capsys.readouterr().out
+    (tmp_path / "rm.bed").write_text("chr1\t5\t9\tSimple_repeat\textra\nchr2 1 2 Satellite\n")
+    assert smCounter._read_track(str(tmp_path / "rm.bed"), "--bedRepeatMaskerSubset", 4) == [("chr1", "5", "9", "Simple_repeat"), ("chr2", "1", "2", "Satellite")]
