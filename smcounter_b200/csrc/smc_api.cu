@@ -321,6 +321,11 @@ extern "C" int smc_ctx_create(int device, const smc_params* params, smc_ctx** ou
         return fail("cudaFuncSetAttribute(k_gather)", e);
     if ((e = cudaFuncSetAttribute(k_gather_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KA_SMEM_BYTES(true))) != cudaSuccess)
         return fail("cudaFuncSetAttribute(k_gather list)", e);
+    // both pileup kernels want the shared-memory side of the L1 / shared split (their global loads are streamed once)
+    cudaFuncSetAttribute(k_gather_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_gather_t<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_merge_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_merge_t<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if ((e = radix_sort_init()) != cudaSuccess) return fail("cudaFuncSetAttribute(k_radix_scatter)", e);
     if ((e = ctx->d_small.ensure(4096)) != cudaSuccess) return fail("cudaMalloc", e);
     *out = ctx;

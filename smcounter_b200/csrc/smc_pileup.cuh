@@ -21,21 +21,24 @@
 // pos <= p < reference_end, once per read instead of once per pileup event.
 // ------------------------------------------------------------------------------------------------------------
 
-// The 32 bytes of a read the gather loop needs (the 64-byte ReadRec keeps everything, for the rare paths).
+// The 32 bytes of a read the gather loop needs (the 64-byte ReadRec keeps everything, for the rare paths).  Everything that is
+// the same for all 32 loci of a tile is resolved here, once per read: the byte offsets of query position 0 folded into the
+// payload offsets, and the two "distance to an end" windows of smCounter.py:432-452 as ranges of covered-locus indices.
 struct __align__(16) GRec {
     int32_t  lo;         // first covered locus index
-    uint32_t gspan;      // simple reads: hi - lo; other reads: 0 (the gather loop never covers them)
-    uint32_t qk;         // leftSP - start: the query position of reference position p is p + qk
-    uint32_t meta;       // RM_* bits 0-3, GM_LE_INF, GM_PLE_INF
-    uint32_t seq_off, qual_off;
-    uint32_t le_lo;      // p is within 20 of the barcode end iff (uint32)(p - le_lo) <= (GM_LE_INF ? 2^31-1 : 20)        (:432-452)
-    uint32_t ple_lo;     // R2: p is within primerDist of the primer end iff (uint32)(p - ple_lo) <= (GM_PLE_INF ? 2^31-1 : primerDist)
+    uint32_t gspan_fl;   // bits 0-15: simple reads hi - lo, other reads 0 (the gather loop never covers them); bits 16.. GR_* flags
+    uint32_t seq_base;   // the base of reference position p is nibble (p + b) & 1 of seq[seq_base + ((p + b) >> 1)], b = GR_ODD
+    uint32_t qual_base;  // its quality is qual[qual_base + p]                                   (all wrapping 32-bit arithmetic)
+    uint32_t le;         // covered loci [lo + (le & 0xffff), lo + (le >> 16)) are within 20 of the barcode end    (:432-452)
+    uint32_t ple;        // R2: the same for "within primerDist of the primer end"; empty for R1
+    uint32_t urank, frank;
 };
 static_assert(sizeof(GRec) == 32, "GRec must be 32 bytes");
-#define GM_LE_INF  16u
-#define GM_PLE_INF 32u
-#define WIN_EMPTY  0x7fffffffu
-#define WIN_INF    0x7fffffffu
+#define GR_OK      (1u << 16)    // passes the MQ + mismatch gate
+#define GR_REVERSE (1u << 17)
+#define GR_READ2   (1u << 18)
+#define GR_SIMPLE  (1u << 19)
+#define GR_ODD     (1u << 20)    // b: parity of leftSP - start
 
 struct PrepArgs {
     int64_t n_reads;
@@ -114,18 +117,34 @@ __global__ void __launch_bounds__(256) k_read_prep(PrepArgs A) {
     rec.sp_aln = (uint32_t)leftSP | ((uint32_t)alnlen << 16);
     rec.cig[0] = c4[0]; rec.cig[1] = c4[1]; rec.cig[2] = c4[2]; rec.cig[3] = c4[3];
     GRec g;
-    g.lo = (int32_t)lo; g.gspan = rec.gspan; g.qk = (uint32_t)(leftSP - start); g.meta = rec.meta & 15u;
-    g.seq_off = rec.seq_off; g.qual_off = rec.qual_off; g.le_lo = WIN_EMPTY; g.ple_lo = WIN_EMPTY;
-    if (simple) {
-        // One aligned run: d = p - start is the distance from the alignment start, alnlen - d from its end.
+    g.lo = (int32_t)lo;
+    g.gspan_fl = rec.gspan | (ok ? GR_OK : 0u) | (rev ? GR_REVERSE : 0u) | (r2 ? GR_READ2 : 0u) | (simple ? GR_SIMPLE : 0u);
+    g.seq_base = rec.seq_off; g.qual_base = rec.qual_off; g.le = 0u; g.ple = 0u;
+    g.urank = rec.urank; g.frank = rec.frank;
+    if (simple && hi > lo) {
+        // One aligned run: the query position of reference position p is p + qk, qk = leftSP - start.
+        const int32_t qk = leftSP - start;
+        g.seq_base = rec.seq_off + (uint32_t)(qk >> 1); g.qual_base = rec.qual_off + (uint32_t)qk;
+        if (qk & 1) g.gspan_fl |= GR_ODD;
+        // d = p - start is the distance from the alignment start, alnlen - d from its end.
         //   R1: distToBcEnd = rev ? alnlen - d : d;   R2: distToBcEnd = rev ? d : alnlen - d, distToPrimerEnd = rev ? alnlen - d : d
-        // "<= X from the start" is the window [start, start + X], "<= X from the end" is [start + alnlen - X, inf).
+        // "<= X from the start" is the position window [start, start + X], "<= X from the end" is [start + alnlen - X, inf);
+        // as ranges of the covered loci [lo, hi): count of loci below a position (loci of one interval are consecutive positions)
+        const int32_t n = (int32_t)(hi - lo);
+        const int32_t p_first = (int32_t)(uint32_t)A.loci_key[lo];
+        const bool contiguous = (int32_t)(uint32_t)A.loci_key[hi - 1] - p_first == n - 1;
+        auto below = [&](int64_t x) -> uint32_t {              // number of covered loci at positions < x
+            if (contiguous) { const int64_t c = x - (int64_t)p_first; return (uint32_t)(c < 0 ? 0 : c > n ? n : c); }
+            int32_t a0 = 0, b0 = n;
+            while (a0 < b0) { const int32_t mid = (a0 + b0) >> 1; if ((int64_t)(int32_t)(uint32_t)A.loci_key[lo + mid] < x) a0 = mid + 1; else b0 = mid; }
+            return (uint32_t)a0;
+        };
         const bool bc_at_start = (r2 == rev);                 // R1 fwd / R2 rev measure the barcode end from the start
-        if (bc_at_start) g.le_lo = (uint32_t)start;
-        else { g.le_lo = (uint32_t)(start + alnlen - 20); g.meta |= GM_LE_INF; }
+        if (bc_at_start) g.le = below((int64_t)start) | (below((int64_t)start + 21) << 16);
+        else g.le = below((int64_t)start + alnlen - 20) | ((uint32_t)n << 16);
         if (r2) {
-            if (rev) { g.ple_lo = (uint32_t)(start + alnlen - A.primerDist); g.meta |= GM_PLE_INF; }
-            else if (A.primerDist >= 0) g.ple_lo = (uint32_t)start;
+            if (rev) g.ple = below((int64_t)start + alnlen - A.primerDist) | ((uint32_t)n << 16);
+            else if (A.primerDist >= 0) g.ple = below((int64_t)start) | (below((int64_t)start + A.primerDist + 1) << 16);
         }
     }
     {
@@ -294,14 +313,19 @@ __device__ __noinline__ uint32_t dyn_lookup(DynTab T, unsigned long long key, ui
 // ============================================================================================================
 // K3a: k_gather
 //
-// A warp owns one unit; it works in batches of 32 tile events:
-//   stage  : 32 GRec (32 B each, gathered through ev_read[]) -> shared memory; boundary / "simple read" flags of the
-//            batch become warp-uniform bit masks (one byte load + three ballots);
-//   gather : KA_GATHER reads at a time every lane computes the query position of ITS locus and loads the base nibble
-//            and the quality (the loads of a group are independent: ILP + occupancy hide the latency);
-//   apply  : in event order, the read-level tallies (cvg, alleleCnt, strand, lowQ, R1/R2 end distances: registers, 4 x 8-bit
-//            fields A C T G per word) and the fragment merge; at every fragment boundary the lane's fragment code goes to a
-//            shared-memory staging row, eight rows are written out as one 128-bit word per lane.
+// A warp owns one unit (a run of tile events of one 32-locus tile, cut at barcode starts), LANE = LOCUS.  It works in batches
+// of up to 32 tile events and always stops a batch at a fragment start, so that a fragment begins and ends in one batch:
+//   stage    : lane k loads the GRec of event k and turns everything that is the same for all 32 loci into three 32-bit LANE
+//              MASKS (covered / within 20 of the barcode end / within primerDist of the primer end) and a tally class; barcode
+//              and fragment boundaries of the batch become warp-uniform bit masks (ranks of neighbouring events, ballots);
+//   gather   : KA_GATHER events at a time every lane loads the base nibble and the quality of ITS locus (independent loads:
+//              ILP + occupancy hide the latency), adds the event to a per-lane CLASS HISTOGRAM in shared memory (one
+//              fire-and-forget shared atomic: 16 classes = strand x {lowQ, not included, R1 x le20, R2 x le20 x ple}, the four
+//              bases as 8-bit fields of one word) and leaves a 16-bit event code (quality, allele slot, covered / included);
+//   fragments: complete fragments of one or two plain aligned reads -- nearly all of them -- get the reference's fragment merge
+//              (smCounter.py:467-479) in closed form from their event codes, two fragments per iteration, branch free; anything
+//              else (3+ reads, indel / clipped reads, N / IUPAC bases) takes the ordered per-event state machine;
+//   emit     : the lane's fragment code goes to a shared-memory staging row; eight rows leave as one 128-bit word per lane.
 // Everything rare is out of line: reads with indels / hard clips / several aligned runs (per-event CIGAR walk),
 // non-ACGT bases, pairs on a deletion or a dynamic allele.
 // ============================================================================================================
@@ -314,12 +338,20 @@ __device__ __noinline__ uint32_t dyn_lookup(DynTab T, unsigned long long key, ui
 #ifndef KA_GATHER
 #define KA_GATHER 4
 #endif
-#define KA_REG_FLUSH 224u                       // tile events between register -> global flushes (8-bit fields)
-#define KA_WARP_WORDS(LIST) (256 + 32 + 512 + 128 + ((LIST) ? 256 : 0))   // GRec stage | srank | event codes | fragment-code staging | first-read staging
+// per-warp shared memory (words): event masks 32 x uint4 | payload bases 32 x uint2 | srank | event codes 32 x 32 x u16 |
+// fragment-code staging | class histogram 16 x 32 | (LIST) first-read staging
+#define KA_OFF_BASE  128
+#define KA_OFF_SRANK (KA_OFF_BASE + 64)
+#define KA_OFF_EVC   (KA_OFF_SRANK + 32)
+#define KA_OFF_CST   (KA_OFF_EVC + 512)
+#define KA_OFF_HIST  (KA_OFF_CST + 128)
+#define KA_OFF_FST   (KA_OFF_HIST + 512)
+#define KA_WARP_WORDS(LIST) (KA_OFF_FST + ((LIST) ? 256 : 0))
 #define KA_SMEM_BYTES(LIST) (64 + KA_WARPS * KA_WARP_WORDS(LIST) * 4)
 
-// event code (internal to k_gather).  Staged codes of plain aligned reads: quality in bits 0-7, allele slot (A0 C1 T3 G4,
-// 7 = N / IUPAC) in bits 8-10 like the fragment code; codes returned by slow_event: BAM nibble in bits 8-11
+// event code (internal to k_gather).  Staged codes of plain aligned reads: quality in bits 0-7, bits 8-11 the allele slot
+// (A0 C1 T3 G4, as in the fragment code) or, with EC_DYN, the BAM nibble of an N / IUPAC base; codes returned by slow_event:
+// BAM nibble in bits 8-11
 #define SC_AID_SH   8u
 #define EC_NIB_SH   8u
 #define EC_COVERED  (1u << 12)
@@ -328,6 +360,10 @@ __device__ __noinline__ uint32_t dyn_lookup(DynTab T, unsigned long long key, ui
 #define EC_REGULAR  (1u << 15)    // a plain base, not an indel start / in-deletion event
 #define EC_LE20     (1u << 16)    // distance to the barcode end <= 20
 #define EC_PLE      (1u << 17)    // R2 and distance to the primer end <= primerDist
+
+// tally classes of a regular A/C/G/T event (smCounter.py:423-459): bit 3 reverse strand; low bits 0 low quality, 1 not
+// included (MQ / mismatch gate), 2 + le20 included R1, 4 + le20 + 2 ple included R2
+#define TC_REVERSE 8u
 
 struct KAArgs {
     const GRec* grec; const ReadRec* recs; const uint32_t* ev_read; const uint32_t* urank_s; const uint32_t* frank_s;
@@ -346,10 +382,8 @@ struct KAArgs {
 
 // Tallies of one pileup event whose base is not A/C/G/T (N / IUPAC, smCounter.py:423-457 with that key): rare, so it goes
 // straight to the dynamic-allele row with atomics.  Returns the row | (nibble == N) << 31.
-__device__ __noinline__ uint32_t dyn_base_event(DynTab T, const uint8_t* seqp, uint32_t seq_off, uint32_t locus, uint32_t read_idx, int qpos,
+__device__ __noinline__ uint32_t dyn_base_event(DynTab T, uint32_t nib, uint32_t locus, uint32_t read_idx, int qpos,
                                                 uint32_t flags /* 1 fwd 2 lowq 4 inc 8 r2 16 le20 32 ple */) {
-    const uint32_t sb = __ldg(seqp + (uint32_t)(seq_off + (uint32_t)(qpos >> 1)));     // wrapping: seq_off is the read's virtual base 0
-    const uint32_t nib = (qpos & 1) ? (sb & 15u) : (sb >> 4);
     const uint32_t e = dyn_lookup(T, dyn_make_key(locus, SMC_K_BASE, nib, 0ull), read_idx, qpos, 0);
     int32_t* row = T.dcnt + (size_t)e * SMC_NCNT;
     atomicAdd(&row[SMC_C_ALLELE], 1);
@@ -480,23 +514,36 @@ __device__ __noinline__ void pair_bump_global(int32_t* cnt, size_t nl, int64_t L
 #define FS_EXISTS 4u      // the fragment is in bcDict
 #define FS_PAIRED 8u
 
-struct GatherRegs {          // 4 x 8-bit fields (A, C, T, G) per word
-    uint32_t allele, fwd, lowq, r1tot, r1le, r2tot, r2le, r2ple, conc, disc;
-};
+// lanes [a, b) of a warp as a bit mask (a, b any integers)
+__device__ __forceinline__ uint32_t lane_range_mask(int a, int b) {
+    a = max(a, 0); b = min(b, 32);
+    return b > a ? ((0xffffffffu >> (32 - (b - a))) << a) : 0u;
+}
 
-// registers -> the per-locus global accumulators ([field][locus]: coalesced across lanes)
-__device__ __forceinline__ void flush_gather_regs(int32_t* cnt, size_t nl, int64_t L, bool lane_valid, GatherRegs& R) {
-    if (lane_valid) {
+// The lane's class histogram (shared memory, word [class][lane], 4 x 8-bit fields A C T G) and its concordant / discordant
+// pair counters (registers, same fields) -> the per-locus global accumulators ([field][locus]: coalesced across lanes)
+__device__ __forceinline__ void flush_tallies(int32_t* cnt, size_t nl, int64_t L, bool lane_valid, uint32_t* hist_lane, uint32_t& conc, uint32_t& disc) {
+    uint32_t h[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) { h[t] = hist_lane[t * 32]; hist_lane[t * 32] = 0u; }
+    // no field can overflow: an event adds 1 to one class of one base, and at most 255 events lie between two flushes
+    const uint32_t r1le = h[3] + h[11], r1tot = h[2] + h[10] + r1le;
+    const uint32_t r2le = h[5] + h[7] + h[13] + h[15], r2ple = h[6] + h[7] + h[14] + h[15];
+    const uint32_t r2tot = h[4] + h[5] + h[6] + h[7] + h[12] + h[13] + h[14] + h[15];
+    const uint32_t lowq = h[0] + h[8];
+    const uint32_t fwd = h[0] + h[1] + h[2] + h[3] + h[4] + h[5] + h[6] + h[7];
+    const uint32_t allele = fwd + h[8] + h[9] + h[10] + h[11] + h[12] + h[13] + h[14] + h[15];
+    if (lane_valid && (allele | conc | disc)) {
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
             const int a = f + (f >> 1);                                     // A0 C1 T3 G4
             int32_t* base = cnt + (size_t)a * SMC_NCNT * nl + L;
-            const uint32_t al = (R.allele >> (8 * f)) & 255u;
+            const uint32_t al = (allele >> (8 * f)) & 255u;
+            const uint32_t cc = (conc >> (8 * f)) & 255u, dc = (disc >> (8 * f)) & 255u;
             if (al) {
-                const uint32_t fw = (R.fwd >> (8 * f)) & 255u, lq = (R.lowq >> (8 * f)) & 255u;
-                const uint32_t t1 = (R.r1tot >> (8 * f)) & 255u, l1 = (R.r1le >> (8 * f)) & 255u;
-                const uint32_t t2 = (R.r2tot >> (8 * f)) & 255u, l2 = (R.r2le >> (8 * f)) & 255u, pl = (R.r2ple >> (8 * f)) & 255u;
-                const uint32_t cc = (R.conc >> (8 * f)) & 255u, dc = (R.disc >> (8 * f)) & 255u;
+                const uint32_t fw = (fwd >> (8 * f)) & 255u, lq = (lowq >> (8 * f)) & 255u;
+                const uint32_t t1 = (r1tot >> (8 * f)) & 255u, l1 = (r1le >> (8 * f)) & 255u;
+                const uint32_t t2 = (r2tot >> (8 * f)) & 255u, l2 = (r2le >> (8 * f)) & 255u, pl = (r2ple >> (8 * f)) & 255u;
                 atomicAdd(base + (size_t)SMC_C_ALLELE * nl, (int)al);
                 if (fw) atomicAdd(base + (size_t)SMC_C_FWD * nl, (int)fw);
                 if (al - fw) atomicAdd(base + (size_t)SMC_C_REV * nl, (int)(al - fw));
@@ -506,25 +553,16 @@ __device__ __forceinline__ void flush_gather_regs(int32_t* cnt, size_t nl, int64
                 if (t2) atomicAdd(base + (size_t)SMC_C_R2TOT * nl, (int)t2);
                 if (l2) atomicAdd(base + (size_t)SMC_C_R2LE * nl, (int)l2);
                 if (pl) atomicAdd(base + (size_t)SMC_C_R2PLE * nl, (int)pl);
-                if (cc) atomicAdd(base + (size_t)SMC_C_CONCORD * nl, (int)cc);
-                if (dc) atomicAdd(base + (size_t)SMC_C_DISCORD * nl, (int)dc);
             }
+            if (cc) atomicAdd(base + (size_t)SMC_C_CONCORD * nl, (int)cc);
+            if (dc) atomicAdd(base + (size_t)SMC_C_DISCORD * nl, (int)dc);
         }
     }
-    R.allele = R.fwd = R.lowq = R.r1tot = R.r1le = R.r2tot = R.r2le = R.r2ple = R.conc = R.disc = 0;
+    conc = disc = 0u;
 }
 
-// order-independent tallies of a regular A/C/G/T event (smCounter.py:423-459) into the register counters;
-// `one` = the field increment of the base (0 when the event does not count), `onei` = the same if it passes incCond
-__device__ __forceinline__ void tally_regular(GatherRegs& R, uint32_t one, uint32_t onei, bool reverse, bool read2, bool lowq, bool le20, bool ple) {
-    R.allele += one;                                               // :459
-    if (!reverse) R.fwd += one;                                    // :454-457
-    if (lowq) R.lowq += one;                                       // :428-429
-    const uint32_t onel = le20 ? onei : 0u;
-    if (!read2) { R.r1tot += onei; R.r1le += onel; }               // :432-441
-    else { R.r2tot += onei; R.r2le += onel; }                      // :442-452
-    if (ple) R.r2ple += onei;                                      // the primer window of an R1 read is empty
-}
+// register field increment (1 << 8 * field) of allele slot A0 C1 T3 G4
+__device__ __forceinline__ uint32_t slot_field_one(uint32_t aid) { return 1u << (((aid * 3u + 1u) << 1) & 0x18u); }
 
 template <bool LIST>
 __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const KAArgs A) {
@@ -535,13 +573,18 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
         const uint32_t f = nib_field(n);
         lut[n] = nib_is_acgt(n) ? ((1u << (8u * f)) | ((f + (f >> 1)) << 28)) : 0u;
     }
-    __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* ws = smem + 16 + (size_t)w * KA_WARP_WORDS(LIST);     // 32 GRec
-    uint32_t* srank_s = ws + 256;
-    uint16_t* evc = reinterpret_cast<uint16_t*>(ws + 256 + 32);       // 32 x 32 event codes of the batch
-    uint32_t* cst = ws + 256 + 32 + 512;                              // fragment-code staging: word [k >> 1][lane], half k & 1
-    uint32_t* fst = ws + 256 + 32 + 512 + 128;                        // LIST: [k][lane]
+    uint32_t* ws = smem + 16 + (size_t)w * KA_WARP_WORDS(LIST);
+    uint4* smask = reinterpret_cast<uint4*>(ws);                      // per event: covered / le20 / ple lane masks, class + flags
+    uint2* sbase = reinterpret_cast<uint2*>(ws + KA_OFF_BASE);        // per event: seq_base, qual_base
+    uint32_t* srank_s = ws + KA_OFF_SRANK;
+    uint16_t* evc = reinterpret_cast<uint16_t*>(ws + KA_OFF_EVC);     // 32 x 32 event codes of the batch
+    uint32_t* cst = ws + KA_OFF_CST;                                  // fragment-code staging: word [k >> 1][lane], half k & 1
+    uint32_t* hist_lane = ws + KA_OFF_HIST + lane;                    // class histogram: word [class][lane]
+    uint32_t* fst = ws + KA_OFF_FST;                                  // LIST: [k][lane]
+#pragma unroll
+    for (int t = 0; t < 16; ++t) hist_lane[t * 32] = 0u;
+    __syncthreads();
 
     const uint32_t unit = A.unit0 + blockIdx.x * KA_WARPS + w;
     if (unit >= A.n_units) return;
@@ -553,16 +596,18 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
 
     const int64_t L = (int64_t)tile * 32 + lane;
     const bool lane_valid = L < A.n_loci;
+    const uint32_t validmask = __ballot_sync(FULL_MASK, lane_valid);
     const int32_t p = lane_valid ? A.loci_pos[L] : 0;
     const int32_t Li = lane_valid ? (int32_t)L : -1;                  // -1 is never inside a read's [lo, hi)
+    const uint32_t ph0 = (uint32_t)p >> 1, ph1 = ((uint32_t)p + 1u) >> 1, ppar = (uint32_t)p & 1u;
+    const uint32_t lanebit = 1u << lane;
+    const int32_t tile0 = (int32_t)(tile * 32u);
     const size_t nl = (size_t)A.n_loci;
     const int minBQ = A.minBQ;
-    const uint32_t pspan = A.primerDist > 0 ? (uint32_t)A.primerDist : 0u;
     const uint8_t* __restrict__ seqp = A.seq;
     const uint8_t* __restrict__ qualp = A.qual;
 
-    GatherRegs R;
-    R.allele = R.fwd = R.lowq = R.r1tot = R.r1le = R.r2tot = R.r2le = R.r2ple = R.conc = R.disc = 0;
+    uint32_t conc = 0, disc = 0;                                      // 4 x 8-bit fields (A, C, T, G)
     int cvg = 0;
     // open fragment of this lane: FS_* bits, allele (slot, or NF + dynamic row), effective quality
     uint32_t fs = 0, f_mid = 0, f_bq = 0, f_first = 0xffffffffu;
@@ -583,24 +628,32 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
             for (int k = 0; k < 8; ++k) A.frag_first[(so + f0 + k) * 32 + lane] = fst[k * 32 + lane];
         }
     };
-    // close the open fragment: its code goes to the staging rows, eight rows are written out as one 128-bit word per lane
+    // a finished fragment code goes to the staging rows; eight rows are written out as one 128-bit word per lane
+    auto put_code = [&](uint32_t code) {
+        const uint32_t k = fcount & 7u;
+        cst16[((k >> 1) << 6) + (k & 1u)] = (uint16_t)code;
+        ++fcount;
+        if ((fcount & 7u) == 0u) flush_codes(fcount - 8u);
+    };
+    // close the open fragment of the ordered pass
     auto emit = [&]() {
         const bool dynl = (fs & FS_EXISTS) && f_mid >= NF;
         const bool any_dyn = __any_sync(FULL_MASK, dynl);
         const uint32_t st = (fs & FS_EXISTS) ? 3u : ((fs & 3u) - ((fs >> 1) & 1u));
         const uint32_t code = (st << FC_ST_SH) | ((fs & FS_PAIRED) ? FC_PAIRED : 0u) | (any_dyn ? FC_EXT : 0u) | (umi_first ? FC_UMIFIRST : 0u) |
                               ((f_mid < NF ? f_mid : FC_AID_DYN) << FC_AID_SH) | f_bq;
-        const uint32_t k = fcount & 7u;
-        cst16[((k >> 1) << 6) + (k & 1u)] = (uint16_t)code;
-        if (LIST) fst[k * 32 + lane] = f_first;
+        if (LIST) fst[(fcount & 7u) * 32 + lane] = f_first;
         if (any_dyn) {                                                   // extension row: the dynamic-allele rows of this fragment
             if (8u * ((fcount >> 3) + 1u) + 2u * (ext + 1u) > cap) { if (!dead && lane == 0) atomicOr(A.T.gflags, GF_CODE_FULL); dead = true; }
             if (!dead) reinterpret_cast<uint32_t*>(A.codes)[(so + cap - 2u * (ext + 1u)) * 16 + lane] = dynl ? f_mid - NF : 0u;
             ++ext;
         }
-        ++fcount;
-        if ((fcount & 7u) == 0u) flush_codes(fcount - 8u);
+        put_code(code);
         fs = 0; f_first = 0xffffffffu; umi_first = false;
+    };
+    // warp-uniform bookkeeping at the first fragment of a barcode
+    auto umi_begin = [&](int j) {
+        if (A.umi_urank) { if (lane == 0) A.umi_urank[eb + umi_k] = __ldg(&A.urank_s[srank_s[j]]); ++umi_k; }
     };
     // fragment merge of an event that passed incCond (smCounter.py:467-479); `one` = register field of an A/C/G/T base, else 0
     auto merge = [&](uint32_t mid, uint32_t bq, bool isN, uint32_t one, int j) {
@@ -609,32 +662,30 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
         else if (mid == f_mid || isN) {
             f_bq = min(f_bq, bq); fs |= FS_PAIRED;
             if (mid == f_mid) {
-                if (one) R.conc += one;
+                if (one) conc += one;
                 else pair_bump_global(A.cnt, nl, L, A.T.dcnt, mid, SMC_C_CONCORD);
             }
         } else {
             fs &= ~FS_EXISTS;
-            if (one) R.disc += one;
+            if (one) disc += one;
             else pair_bump_global(A.cnt, nl, L, A.T.dcnt, mid, SMC_C_DISCORD);
         }
     };
-
-    // one pileup event of the ordered (generic) pass: the staged event code of a plain aligned read, or the per-event CIGAR
-    // walk of any other read (out of line); then the fragment merge
+    // one pileup event of the ordered pass: the staged event code of a plain aligned read, or the per-event CIGAR walk of any
+    // other read (out of line); then the fragment merge
     auto gen_event = [&](int e) {
         uint32_t cd, mid, one; bool isN = false;
         if ((simplemask_cur >> e) & 1u) {
             cd = evc[e * 32 + lane];
-            mid = (cd >> SC_AID_SH) & 7u;
-            one = 1u << (((mid * 3u + 1u) << 1) & 0x18u);                            // register field of A0 C1 T3 G4
+            mid = (cd >> SC_AID_SH) & 15u;
+            one = slot_field_one(mid);
             if (cd & EC_DYN) {                                                   // rare: N / IUPAC base -> dynamic allele row
-                const uint32_t* rw = ws + e * 8;
-                const uint32_t meta = rw[3];
-                const bool le20 = (uint32_t)(p - (int32_t)rw[6]) <= ((meta & GM_LE_INF) ? WIN_INF : 20u);
-                const bool ple = (uint32_t)(p - (int32_t)rw[7]) <= ((meta & GM_PLE_INF) ? WIN_INF : pspan);
-                const uint32_t dfl = ((meta & RM_REVERSE) ? 0u : 1u) | ((int)(cd & 255u) < minBQ ? 2u : 0u) | ((cd & EC_INC) ? 4u : 0u) |
-                                     ((meta & RM_READ2) ? 8u : 0u) | (le20 ? 16u : 0u) | (ple ? 32u : 0u);
-                const uint32_t en = dyn_base_event(A.T, seqp, rw[4], (uint32_t)Li, __ldg(&A.recs[srank_s[e]].read_idx), p + (int32_t)rw[2], dfl);
+                const uint4 m = smask[e];
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(&A.recs[srank_s[e]]);
+                const int qpos = p - (int32_t)__ldg(rw + 6) + (int)(__ldg(rw + 2) & 0xffffu);       // p - start + leftSP
+                const uint32_t dfl = ((m.w & TC_REVERSE) ? 0u : 1u) | ((int)(cd & 255u) < minBQ ? 2u : 0u) | ((cd & EC_INC) ? 4u : 0u) |
+                                     ((m.w & 4u) ? 8u : 0u) | ((m.y & lanebit) ? 16u : 0u) | ((m.z & lanebit) ? 32u : 0u);
+                const uint32_t en = dyn_base_event(A.T, mid, (uint32_t)Li, __ldg(rw + 10), qpos, dfl);
                 mid = NF + (en & 0x7fffffffu); isN = en >> 31; one = 0;
             }
         } else {                                                             // rare: per-event CIGAR walk, out of line
@@ -649,11 +700,14 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
                     if (!(cd & EC_DYN)) {
                         const uint32_t lv = lut[(cd >> EC_NIB_SH) & 15u];
                         one = lv & 0x0fffffffu; mid = lv >> 28;
-                        tally_regular(R, one, (cd & EC_INC) ? one : 0u, meta & RM_REVERSE, meta & RM_READ2, lowq, cd & EC_LE20, cd & EC_PLE);
+                        const uint32_t cls = ((meta & RM_REVERSE) ? TC_REVERSE : 0u) |
+                                             (lowq ? 0u : !(cd & EC_INC) ? 1u : (meta & RM_READ2) ? 4u + ((cd & EC_LE20) ? 1u : 0u) + ((cd & EC_PLE) ? 2u : 0u)
+                                                                                                   : 2u + ((cd & EC_LE20) ? 1u : 0u));
+                        atomicAdd(&hist_lane[cls * 32], one);
                     } else {
                         const uint32_t dfl = ((meta & RM_REVERSE) ? 0u : 1u) | (lowq ? 2u : 0u) | ((cd & EC_INC) ? 4u : 0u) |
                                              ((meta & RM_READ2) ? 8u : 0u) | ((cd & EC_LE20) ? 16u : 0u) | ((cd & EC_PLE) ? 32u : 0u);
-                        const uint32_t en = dyn_base_event(A.T, seqp, __ldg(rw + 4), (uint32_t)Li, __ldg(rw + 10), (int)ev.y, dfl);
+                        const uint32_t en = dyn_base_event(A.T, (cd >> EC_NIB_SH) & 15u, (uint32_t)Li, __ldg(rw + 10), (int)ev.y, dfl);
                         mid = NF + (en & 0x7fffffffu); isN = en >> 31;
                     }
                 } else if (mid == (uint32_t)SMC_A_DEL) {
@@ -667,31 +721,23 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
 
     for (uint32_t base = eb; base < ee;) {
         const int nb = (int)min(32u, ee - base);
-        // ---------------- stage
+        // ---------------- stage: lane k owns event k
         // boundaries from the dense barcode / fragment ranks of consecutive events (a unit always starts at a barcode start);
         // slots past the end: an empty simple read, no boundary
-        bool ub = false, fb = false, simple = true;
-        uint32_t ur = 0xffffffffu, fr = 0xffffffffu;
-        {
-            uint4 g0 = make_uint4(0u, 0u, 0u, 0u), g1 = g0; uint32_t sr = 0;
-            if (lane < nb) {
-                sr = __ldg(&A.ev_read[base + lane]);
-                ur = __ldg(&A.urank_s[sr]); fr = __ldg(&A.frank_s[sr]);
-                const uint4* src = reinterpret_cast<const uint4*>(&A.grec[sr]);
-                g0 = __ldg(src); g1 = __ldg(src + 1);
-                simple = g0.w & RM_SIMPLE;
-            }
-            uint32_t pur = __shfl_up_sync(FULL_MASK, ur, 1), pfr = __shfl_up_sync(FULL_MASK, fr, 1);
-            if (lane == 0) { pur = carry_ur; pfr = carry_fr; }
-            ub = lane < nb && ur != pur;
-            fb = lane < nb && (ub || fr != pfr);
-            uint4* dst = reinterpret_cast<uint4*>(ws + lane * 8);
-            dst[0] = g0; dst[1] = g1;
-            srank_s[lane] = sr;
+        uint4 g0 = make_uint4(0u, GR_SIMPLE, 0u, 0u), g1 = make_uint4(0u, 0u, 0xffffffffu, 0xffffffffu);
+        uint32_t sr = 0;
+        if (lane < nb) {
+            sr = __ldg(&A.ev_read[base + lane]);
+            const uint4* src = reinterpret_cast<const uint4*>(&A.grec[sr]);
+            g0 = __ldg(src); g1 = __ldg(src + 1);                            // lo gspan|flags seq_base qual_base | le ple urank frank
         }
+        uint32_t pur = __shfl_up_sync(FULL_MASK, g1.z, 1), pfr = __shfl_up_sync(FULL_MASK, g1.w, 1);
+        if (lane == 0) { pur = carry_ur; pfr = carry_fr; }
+        const bool ub = lane < nb && g1.z != pur;
+        const bool fb = lane < nb && (ub || g1.w != pfr);
         const uint32_t fragmask = __ballot_sync(FULL_MASK, fb);
         const uint32_t umimask = __ballot_sync(FULL_MASK, ub);
-        const uint32_t simplemask = __ballot_sync(FULL_MASK, simple);
+        const uint32_t simplemask = __ballot_sync(FULL_MASK, (g0.y & GR_SIMPLE) != 0u);
         simplemask_cur = simplemask;
         // Events consumed from this batch: when more events follow, stop before the last fragment start, so that a fragment
         // that starts in a batch also ends in it (a fragment of 32+ events is carried across batches by the ordered pass).
@@ -701,54 +747,62 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
             const int last = 31 - __clz((int)(fragmask | 1u));
             if (last > 0) ncons = last; else tail_open = true;
         }
-        carry_ur = __shfl_sync(FULL_MASK, ur, ncons - 1); carry_fr = __shfl_sync(FULL_MASK, fr, ncons - 1);
-        if (since_flush + 32u > 255u) { flush_gather_regs(A.cnt, nl, L, lane_valid, R); since_flush = 0; }
+        carry_ur = __shfl_sync(FULL_MASK, g1.z, ncons - 1); carry_fr = __shfl_sync(FULL_MASK, g1.w, ncons - 1);
+        {
+            // what is the same for all 32 loci, as lane masks: covered loci [lo, lo + gspan), the two end-distance windows
+            // (only ever needed for included reads); tally class of the read; parity of its query offset
+            const int rel = (int32_t)g0.x - tile0;
+            const bool live = lane < ncons;
+            const uint32_t okm = (g0.y & GR_OK) ? 0xffffffffu : 0u;
+            const uint32_t cov = live ? lane_range_mask(rel, rel + (int)(g0.y & 0xffffu)) & validmask : 0u;
+            const uint32_t le = cov & okm & lane_range_mask(rel + (int)(g1.x & 0xffffu), rel + (int)(g1.x >> 16));
+            const uint32_t ple = cov & okm & lane_range_mask(rel + (int)(g1.y & 0xffffu), rel + (int)(g1.y >> 16));
+            const uint32_t cls = ((g0.y & GR_REVERSE) ? TC_REVERSE : 0u) | (!(g0.y & GR_OK) ? 1u : (g0.y & GR_READ2) ? 4u : 2u);
+            smask[lane] = make_uint4(cov, le, ple, cls | ((g0.y & GR_ODD) ? 16u : 0u) | ((g0.y & GR_OK) ? 32u : 0u));
+            sbase[lane] = make_uint2(g0.z, g0.w);
+            srank_s[lane] = sr;
+        }
+        if (since_flush + 32u > 255u) { flush_tallies(A.cnt, nl, L, lane_valid, hist_lane, conc, disc); since_flush = 0; }
         since_flush += (uint32_t)ncons;
         __syncwarp();
-        // ---------------- gather + tally (order independent) of the plain aligned reads, KA_GATHER reads at a time; what the
-        // fragment pass needs goes to shared memory as a 16-bit event code (bits as in the fragment code: quality, allele slot)
-        uint32_t odd = 0;                                                        // events where this lane sees an N / IUPAC base
+        // ---------------- gather + tally (order independent) of the plain aligned reads, KA_GATHER events at a time
 #pragma unroll 1
         for (int g = 0; g < ncons; g += KA_GATHER) {
-            uint32_t sbv[KA_GATHER], bqv[KA_GATHER], fl[KA_GATHER];
+            uint32_t sbv[KA_GATHER], bqv[KA_GATHER];
+            uint4 mk[KA_GATHER];
 #pragma unroll
             for (int u = 0; u < KA_GATHER; ++u) {
-                const uint32_t* rw = ws + (g + u) * 8;
-                const uint4 qa = *reinterpret_cast<const uint4*>(rw);        // lo gspan qk meta
-                const uint4 qb = *reinterpret_cast<const uint4*>(rw + 4);    // seq_off qual_off le_lo ple_lo
-                const bool cov = (g + u < ncons) && (uint32_t)(Li - (int32_t)qa.x) < qa.y;
-                const uint32_t qpos = (uint32_t)(p + (int32_t)qa.z);
+                mk[u] = smask[g + u];
+                const uint2 bs = sbase[g + u];
                 sbv[u] = 0; bqv[u] = 0;
-                if (cov) {
-                    sbv[u] = __ldg(seqp + (qb.x + (qpos >> 1)));
-                    bqv[u] = __ldg(qualp + (qb.y + qpos));
+                if (mk[u].x & lanebit) {
+                    sbv[u] = __ldg(seqp + (bs.x + ((mk[u].w & 16u) ? ph1 : ph0)));
+                    bqv[u] = __ldg(qualp + (bs.y + (uint32_t)p));
                 }
-                const bool le20 = (uint32_t)(p - (int32_t)qb.z) <= ((qa.w & GM_LE_INF) ? WIN_INF : 20u);
-                const bool ple = (uint32_t)(p - (int32_t)qb.w) <= ((qa.w & GM_PLE_INF) ? WIN_INF : pspan);
-                // bits 0-3 RM_*, 4 covered, 5 le20, 6 ple, 7 odd query position
-                fl[u] = (qa.w & 15u) | (cov ? 16u : 0u) | (le20 ? 32u : 0u) | (ple ? 64u : 0u) | ((qpos & 1u) << 7);
             }
 #pragma unroll
             for (int u = 0; u < KA_GATHER; ++u) {
-                const uint32_t f = fl[u];
-                const bool cov = f & 16u;
-                const uint32_t nib = (f & 128u) ? (sbv[u] & 15u) : (sbv[u] >> 4);   // 0 when not covered
+                const uint32_t fw = mk[u].w;
+                const bool cov = mk[u].x & lanebit;
+                const uint32_t nib = ((ppar ^ (fw >> 4)) & 1u) ? (sbv[u] & 15u) : (sbv[u] >> 4);   // 0 when not covered
                 const uint32_t bq = bqv[u];
                 const uint32_t lv = lut[nib];
                 const uint32_t one = lv & 0x0fffffffu;                               // 0 when not covered or not A/C/G/T
                 const bool lowq = (int)bq < minBQ;
-                const bool inc = cov && !lowq && (f & RM_OK);                        // :431
+                const bool inc = cov && !lowq && (fw & 32u);                         // :431
                 const bool dynb = cov && !one;
                 cvg += cov ? 1 : 0;                                                  // :368
-                tally_regular(R, one, inc ? one : 0u, f & RM_REVERSE, f & RM_READ2, lowq, f & 32u, f & 64u);
-                odd |= (dynb ? 1u : 0u) << (g + u);
-                evc[(g + u) * 32 + lane] = (uint16_t)(bq | ((dynb ? 7u : (lv >> 28)) << SC_AID_SH) | (cov ? EC_COVERED : 0u) | (dynb ? EC_DYN : 0u) |
+                uint32_t cls = fw & 15u;                                             // :428-459, as one class count
+                if (mk[u].y & lanebit) cls += 1u;
+                if (mk[u].z & lanebit) cls += 2u;
+                if (lowq) cls = fw & TC_REVERSE;
+                atomicAdd(&hist_lane[cls * 32], one);                                // fire and forget; adds 0 for a lane the read does not cover
+                evc[(g + u) * 32 + lane] = (uint16_t)(bq | ((dynb ? nib : (lv >> 28)) << SC_AID_SH) | (cov ? EC_COVERED : 0u) | (dynb ? EC_DYN : 0u) |
                                                       (inc ? EC_INC : 0u));
             }
         }
-        const uint32_t oddmask = __reduce_or_sync(FULL_MASK, odd);
         // fragment structure of the batch, one event per lane: which fragments are complete runs of one or two plain
-        // aligned reads without an N / IUPAC base in any lane (fast path), and which of those have two reads
+        // aligned reads (fast path), and which of those have two reads
         uint32_t fastmask, twomask;
         {
             const uint32_t restk = __funnelshift_rc(fragmask, 0u, (uint32_t)lane + 1u);      // fragmask >> (lane + 1)
@@ -757,7 +811,7 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
             const int nk = endk - lane;
             const uint32_t m2 = nk == 2 ? 3u : 1u;
             const bool fastk = !LIST && lane < ncons && ((fragmask >> lane) & 1u) && (endk < ncons || !tail_open) && nk <= 2 &&
-                               (((simplemask & ~oddmask) >> lane) & m2) == m2;
+                               ((simplemask >> lane) & m2) == m2;
             fastmask = __ballot_sync(FULL_MASK, fastk);
             twomask = __ballot_sync(FULL_MASK, fastk && nk == 2);
         }
@@ -767,7 +821,6 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
             if ((fastmask >> j) & 1u) {
                 // ---------------- fast path: complete fragments of one or two plain aligned reads, two fragments at a time:
                 // the fragment merge of (at most) two reads in BAM order (smCounter.py:467-479) in closed form
-                if (open) { emit(); open = false; }                                     // a carried fragment ends here
                 const int n = 1 + (int)((twomask >> j) & 1u);
                 const int j2 = j + n;
                 const int n2 = (__funnelshift_rc(fastmask, 0u, (uint32_t)j2) & 1u) ? 1 + (int)(__funnelshift_rc(twomask, 0u, (uint32_t)j2) & 1u) : 0;
@@ -777,40 +830,36 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
                 c[1] = n == 2 ? ev[(j + 1) * 32] : 0u;
                 c[2] = n2 ? ev[j2 * 32] : 0u;
                 c[3] = n2 == 2 ? ev[(j2 + 1) * 32] : 0u;
-                uint32_t codes2[2];
+                if (!__any_sync(FULL_MASK, ((c[0] | c[1] | c[2] | c[3]) & EC_DYN) != 0u)) {
+                    if (open) { emit(); open = false; }                                 // a carried fragment ends here
+                    uint32_t codes2[2];
 #pragma unroll
-                for (int f = 0; f < 2; ++f) {
-                    const uint32_t c0 = c[2 * f], c1 = c[2 * f + 1];
-                    const bool i0 = c0 & EC_INC, i1 = c1 & EC_INC;
-                    const bool both = i0 && i1;
-                    const bool same = ((c0 ^ c1) & (7u << SC_AID_SH)) == 0u;
-                    const uint32_t one1 = 1u << (((((c1 >> SC_AID_SH) & 7u) * 3u + 1u) << 1) & 0x18u);
-                    if (both) { if (same) R.conc += one1; else R.disc += one1; }        // keyed by the later read's base
-                    const uint32_t sel = i0 ? c0 : c1;
-                    const uint32_t bqf = both ? min(c0 & 255u, c1 & 255u) : (sel & 255u);
-                    const bool exists = both ? same : (i0 || i1);
-                    const uint32_t st = exists ? 3u : (i0 || i1) ? 2u : ((c0 | c1) & EC_COVERED) ? 1u : 0u;
-                    codes2[f] = (st << FC_ST_SH) | ((both && same) ? FC_PAIRED : 0u) | (sel & (7u << FC_AID_SH)) | bqf;
+                    for (int f = 0; f < 2; ++f) {
+                        const uint32_t c0 = c[2 * f], c1 = c[2 * f + 1];
+                        const uint32_t i0 = (c0 >> 14) & 1u, i1 = (c1 >> 14) & 1u;        // included
+                        const uint32_t both = i0 & i1;
+                        const uint32_t same = ((c0 ^ c1) & (15u << SC_AID_SH)) == 0u ? 1u : 0u;
+                        const uint32_t one1 = slot_field_one((c1 >> SC_AID_SH) & 15u);
+                        conc += (both & same) ? one1 : 0u;                              // keyed by the later read's base
+                        disc += (both & (same ^ 1u)) ? one1 : 0u;
+                        const uint32_t sel = i0 ? c0 : c1;
+                        const uint32_t bqf = both ? min(c0 & 255u, c1 & 255u) : (sel & 255u);
+                        const uint32_t exists = both ? same : (i0 | i1);
+                        const uint32_t st = exists ? 3u : (i0 | i1) ? 2u : (((c0 | c1) >> 12) & 1u);
+                        codes2[f] = (st << FC_ST_SH) | ((both & same) << 13) | (sel & (7u << FC_AID_SH)) | bqf;
+                    }
+                    const bool us1 = (umimask >> j) & 1u;
+                    if (us1) umi_begin(j);
+                    put_code(codes2[0] | (us1 ? FC_UMIFIRST : 0u));
+                    if (n2) {
+                        const bool us2 = (umimask >> j2) & 1u;
+                        if (us2) umi_begin(j2);
+                        put_code(codes2[1] | (us2 ? FC_UMIFIRST : 0u));
+                    }
+                    j = j2 + n2;
+                    continue;
                 }
-                {
-                    const bool ustart = (umimask >> j) & 1u;
-                    if (ustart && A.umi_urank) { if (lane == 0) A.umi_urank[eb + umi_k] = __ldg(&A.urank_s[srank_s[j]]); ++umi_k; }
-                    const uint32_t k = fcount & 7u;
-                    cst16[((k >> 1) << 6) + (k & 1u)] = (uint16_t)(codes2[0] | (ustart ? FC_UMIFIRST : 0u));
-                    ++fcount;
-                    if ((fcount & 7u) == 0u) flush_codes(fcount - 8u);
-                }
-                if (n2) {
-                    const bool ustart = (umimask >> j2) & 1u;
-                    if (ustart && A.umi_urank) { if (lane == 0) A.umi_urank[eb + umi_k] = __ldg(&A.urank_s[srank_s[j2]]); ++umi_k; }
-                    const uint32_t k = fcount & 7u;
-                    cst16[((k >> 1) << 6) + (k & 1u)] = (uint16_t)(codes2[1] | (ustart ? FC_UMIFIRST : 0u));
-                    ++fcount;
-                    if ((fcount & 7u) == 0u) flush_codes(fcount - 8u);
-                }
-                umi_first = false;
-                j = j2 + n2;
-                continue;
+                // a lane sees an N / IUPAC base in one of these reads: fragment A takes the ordered pass below
             }
             // ---------------- ordered pass over the segment: fragment boundary, per-event merge, the rare events
             const uint32_t rest = __funnelshift_rc(fragmask, 0u, (uint32_t)j + 1u);
@@ -818,9 +867,8 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
             n = min(n, ncons - j);
             if ((fragmask >> j) & 1u) {
                 if (open) emit();
-                const bool ustart = (umimask >> j) & 1u;
-                umi_first = ustart;
-                if (ustart && A.umi_urank) { if (lane == 0) A.umi_urank[eb + umi_k] = __ldg(&A.urank_s[srank_s[j]]); ++umi_k; }
+                umi_first = (umimask >> j) & 1u;
+                if (umi_first) umi_begin(j);
                 open = true;
             }
 #pragma unroll 1
@@ -835,7 +883,7 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
     if (open) emit();
     if (fcount & 7u) flush_codes(fcount & ~7u);
     if (lane == 0) A.unit_nfrag[unit] = dead ? 0u : fcount;
-    flush_gather_regs(A.cnt, nl, L, lane_valid, R);
+    flush_tallies(A.cnt, nl, L, lane_valid, hist_lane, conc, disc);
     if (lane_valid && cvg) atomicAdd(&A.loc[(size_t)SMC_L_CVG * nl + L], cvg);
 }
 
