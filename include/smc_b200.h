@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SMC_ABI_VERSION 2
+#define SMC_ABI_VERSION 3
 
 /* error codes */
 #define SMC_OK            0
@@ -48,6 +48,11 @@ typedef struct smc_params {
     int32_t primerDist;   /* --primerDist  (:632) */
     double  rpb;          /* --rpb         (:624)  strong-MT bar 2/3/4, :303-308 */
     double  mismatchThr;  /* --mismatchThr (:629) */
+    int32_t fisherLegacy; /* which scipy.stats.fisher_exact the run is to match (smCounter.py:215,238,248,260; scipy is unpinned in the
+                             reference): 0 = scipy >= 1.7 (two-sided p sums every outcome with pmf <= pmf(observed) * (1 + 1e-7 ... 1e-14);
+                             the installed scipy the oracle calls), 1 = the scipy of the reference's day (<= 1.6: epsilon = 1 - 1e-4, i.e.
+                             p = 1 when pmf(observed) is within 1e-4 of the mode's, outcomes up to pmf(observed) / (1 - 1e-4) are summed) */
+    int32_t reserved0;
 } smc_params;
 
 /*
@@ -287,6 +292,14 @@ typedef struct smc_hp_batch {
 #define SMC_HP_LOWCOMP     2u
 
 int smc_hp_lowcomp(smc_ctx *ctx, const smc_hp_batch *batch, uint8_t *flags_out);
+
+/*
+ * The Fisher exact test kernel on caller-supplied 2x2 tables (what filterVariants() asks scipy for at smCounter.py:215, 238,
+ * 248, 260): tables[4*i .. 4*i+3] = a, b, c, d of [[a, b], [c, d]]; p_out[i] = two-sided p, or_out[i] = sample odds ratio
+ * (inf / nan as scipy returns them).  Uses the context's fisherLegacy setting.  A utility for validating the device
+ * arithmetic against scipy on tables of the caller's choosing; smc_call_batch does not need it.
+ */
+int smc_fisher_exact(smc_ctx *ctx, int64_t n, const int32_t *tables, double *p_out, double *or_out);
 
 #ifdef __cplusplus
 }

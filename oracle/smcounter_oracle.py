@@ -348,6 +348,74 @@ def fisher_exact(table):
     return float(res[0]), float(res[1])
 
 
+def fisher_exact_legacy(table):
+    """``scipy.stats.fisher_exact(table)`` (two-sided) as scipy <= 1.6 computed it -- the scipy of the reference's day (the
+    reference pins no version): ``epsilon = 1 - 1e-4`` in the "pexact is the mode" shortcut and in the search for the
+    opposite tail.  Restated from scipy/stats/stats.py of that era over today's hypergeom pmf / cdf / sf."""
+    import numpy as np
+    from scipy.stats import hypergeom
+    c = np.asarray(table, dtype=np.int64)
+    if 0 in c.sum(axis=0) or 0 in c.sum(axis=1):
+        return float("nan"), 1.0
+    oddsratio = c[0, 0] * c[1, 1] / float(c[1, 0] * c[0, 1]) if c[1, 0] > 0 and c[0, 1] > 0 else float("inf")
+    n1, n2, n = int(c[0, 0] + c[0, 1]), int(c[1, 0] + c[1, 1]), int(c[0, 0] + c[1, 0])
+    a = int(c[0, 0])
+    pmf = lambda x: float(hypergeom.pmf(x, n1 + n2, n1, n))
+
+    def binary_search(side):
+        if side == "upper":
+            minval, maxval = mode, n
+        else:
+            minval, maxval = 0, mode
+        guess = -1
+        while maxval - minval > 1:
+            if maxval == minval + 1 and guess == minval:
+                guess = maxval
+            else:
+                guess = (maxval + minval) // 2
+            pguess = pmf(guess)
+            ng = guess - 1 if side == "upper" else guess + 1
+            if pguess <= pexact < pmf(ng):
+                break
+            elif pguess < pexact:
+                maxval = guess
+            else:
+                minval = guess
+        if guess == -1:
+            guess = minval
+        if side == "upper":
+            while guess > 0 and pmf(guess) < pexact * epsilon:
+                guess -= 1
+            while pmf(guess) > pexact / epsilon:
+                guess += 1
+        else:
+            while pmf(guess) < pexact * epsilon:
+                guess += 1
+            while guess > 0 and pmf(guess) > pexact / epsilon:
+                guess -= 1
+        return guess
+
+    mode = int(float((n + 1) * (n1 + 1)) / (n1 + n2 + 2))
+    pexact = pmf(a)
+    pmode = pmf(mode)
+    epsilon = 1 - 1e-4
+    if abs(pexact - pmode) / max(pexact, pmode) <= 1 - epsilon:
+        return oddsratio, 1.0
+    elif a < mode:
+        plower = float(hypergeom.cdf(a, n1 + n2, n1, n))
+        if pmf(n) > pexact / epsilon:
+            return oddsratio, plower
+        guess = binary_search("upper")
+        pvalue = plower + float(hypergeom.sf(guess - 1, n1 + n2, n1, n))
+    else:
+        pupper = float(hypergeom.sf(a - 1, n1 + n2, n1, n))
+        if pmf(0) > pexact / epsilon:
+            return oddsratio, pupper
+        guess = binary_search("lower")
+        pvalue = pupper + float(hypergeom.cdf(guess, n1 + n2, n1, n))
+    return oddsratio, min(pvalue, 1.0)
+
+
 def filter_variants(ref, alt, vtype, origAlt, origRef, usedMT, strongMTCnt, chrom, pos, hpLen, refs, MTCnt,
                     alleleCnt, cvg, discordPairCnt, concordPairCnt, reverseCnt, forwardCnt, lowQReads,
                     r1BcEndPos, r2BcEndPos, r2PrimerEndPos, primerDist, dbg=None):

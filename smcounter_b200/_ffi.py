@@ -27,7 +27,8 @@ _vp = C.c_void_p
 
 class smc_params(C.Structure):
     _fields_ = [("minBQ", C.c_int32), ("minMQ", C.c_int32), ("mtDepth", C.c_int32), ("mtDrop", C.c_int32),
-                ("maxMT", C.c_int32), ("primerDist", C.c_int32), ("rpb", C.c_double), ("mismatchThr", C.c_double)]
+                ("maxMT", C.c_int32), ("primerDist", C.c_int32), ("rpb", C.c_double), ("mismatchThr", C.c_double),
+                ("fisherLegacy", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class smc_reads_soa(C.Structure):
@@ -70,7 +71,7 @@ class smc_hp_batch(C.Structure):
 HP_HOMOPOLYMER, HP_LOWCOMP = 1, 2
 
 EXPORTS = ("smc_version", "smc_ctx_create", "smc_ctx_destroy", "smc_last_error", "smc_call_batch", "smc_upload",
-           "smc_run_resident", "smc_download", "smc_get_timings", "smc_list_barcodes", "smc_hp_lowcomp")
+           "smc_run_resident", "smc_download", "smc_get_timings", "smc_list_barcodes", "smc_hp_lowcomp", "smc_fisher_exact")
 
 _lib = None
 
@@ -100,6 +101,8 @@ def load():
     lib.smc_run_resident.restype = C.c_int
     lib.smc_download.argtypes = [_vp, C.POINTER(smc_out)]
     lib.smc_download.restype = C.c_int
+    lib.smc_fisher_exact.argtypes = [_vp, C.c_int64, _vp, _vp, _vp]
+    lib.smc_fisher_exact.restype = C.c_int
     lib.smc_get_timings.argtypes = [_vp, C.POINTER(smc_timings)]
     lib.smc_get_timings.restype = C.c_int
     lib.smc_list_barcodes.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64]

@@ -27,6 +27,7 @@ class VcParams:
     mtDrop: int = 0
     maxMT: int = 0
     primerDist: int = 2
+    fisherLegacy: int = 0      # 0: scipy >= 1.7 fisher_exact semantics (what the oracle's scipy does); 1: scipy <= 1.6 (epsilon = 1 - 1e-4)
 
     @property
     def ds(self) -> int:
@@ -119,7 +120,7 @@ class GpuCaller:
         self.lib = _ffi.load()
         self.params = params
         p = _ffi.smc_params(params.minBQ, params.minMQ, params.mtDepth, params.mtDrop, params.maxMT, params.primerDist,
-                            float(params.rpb), float(params.mismatchThr))
+                            float(params.rpb), float(params.mismatchThr), int(params.fisherLegacy), 0)
         h = C.c_void_p()
         rc = self.lib.smc_ctx_create(int(device), C.byref(p), C.byref(h))
         if rc != 0:
@@ -257,6 +258,15 @@ class GpuCaller:
         if rc != 0:
             raise self._err("smc_hp_lowcomp", rc)
         return flags[:n]
+
+    def fisher_exact(self, tables):
+        """scipy.stats.fisher_exact (two-sided) for an (n, 4) int array of [[a, b], [c, d]] tables on the device: (p, odds)."""
+        t = np.ascontiguousarray(tables, dtype=np.int32).reshape(-1, 4)
+        p = np.empty(len(t), np.float64); o = np.empty(len(t), np.float64)
+        rc = self.lib.smc_fisher_exact(self.h, len(t), t.ctypes.data, p.ctypes.data, o.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("smc_fisher_exact failed (%d): %s" % (rc, self.lib.smc_last_error(self.h).decode()))
+        return p, o
 
     def timings(self) -> dict:
         t = _ffi.smc_timings()

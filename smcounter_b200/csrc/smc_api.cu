@@ -622,6 +622,7 @@ static DynTab make_dyntab(smc_ctx* ctx) {
     T.dkey = ctx->d_dkey.as<unsigned long long>(); T.dmask = ctx->dyn_cap - 1; T.drep_read = ctx->d_drep_read.as<uint32_t>();
     T.drep_qpos = ctx->d_drep_qpos.as<int32_t>(); T.dlen = ctx->d_dlen.as<int32_t>(); T.dcnt = ctx->d_dcnt.as<int32_t>();
     T.dlimb = ctx->d_dlimb.as<unsigned long long>(); T.diskey = ctx->d_diskey.as<uint8_t>(); T.dcount = small + SW_DYN_COUNT; T.gflags = small + SW_GFLAGS;
+    T.seq = ctx->d_seq.as<uint8_t>(); T.seq_off = ctx->d_seq_off.as<int64_t>();
     return T;
 }
 
@@ -689,6 +690,7 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
         CK(ctx->d_dlen.ensure((size_t)cap * 4)); CK(ctx->d_dcnt.ensure((size_t)cap * SMC_NCNT * 4)); CK(ctx->d_dlimb.ensure((size_t)cap * 24));
         CK(ctx->d_diskey.ensure(cap));
         CK(cudaMemsetAsync(ctx->d_dkey.p, 0xff, (size_t)cap * 8, ctx->st));
+        CK(cudaMemsetAsync(ctx->d_drep_read.p, 0xff, (size_t)cap * 4, ctx->st));      // "not published yet" (dyn_lookup_long_ins)
         CK(cudaMemsetAsync(ctx->d_dcnt.p, 0, (size_t)cap * SMC_NCNT * 4, ctx->st));
         CK(cudaMemsetAsync(ctx->d_dlimb.p, 0, (size_t)cap * 24, ctx->st));
         CK(cudaMemsetAsync(ctx->d_diskey.p, 0, cap, ctx->st));
@@ -781,7 +783,7 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
         LAUNCH(k_call, nblk(nl, 128), 128, 0, B);
         // k_fisher reads the task count on the device: launched for the whole task buffer (idle threads leave at once), so
         // that no host round trip sits between the two kernels; an overflowing task list is noticed at the final sync
-        LAUNCH(k_fisher, nblk(ctx->task_cap, 128), 128, 0, ctx->d_tasks.as<FisherTask>(), small + SW_N_TASKS, ctx->task_cap, nl,
+        LAUNCH(k_fisher, nblk(ctx->task_cap, 128), 128, 0, ctx->d_tasks.as<FisherTask>(), small + SW_N_TASKS, ctx->task_cap, nl, (int)ctx->prm.fisherLegacy,
                ctx->d_fp.as<double>(), ctx->d_for.as<double>(), ctx->d_fl1.as<uint32_t>(), ctx->d_fl2.as<uint32_t>());
         CK(cudaMemsetAsync(small + SW_CVG_SUM, 0, 8, ctx->st));
         LAUNCH(k_sum_cvg, std::min<unsigned>(nblk(nl, 256), 592u), 256, 0, ctx->d_loc.as<int32_t>() + (size_t)SMC_L_CVG * nl, nl,
@@ -925,6 +927,23 @@ extern "C" int smc_list_barcodes(smc_ctx* ctx, int64_t n, const int64_t* locus, 
     LAUNCH(k_merge_t<true>, nblk(ctx->n_units_cap, KB_WARPS), KB_WARPS * 32, KB_SMEM_BYTES, B);
     CK(cudaMemcpyAsync(umi_out, ctx->d_list_umi.p, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(first_read_out, ctx->d_list_first.p, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaGetLastError());
+    return SMC_OK;
+}
+
+extern "C" int smc_fisher_exact(smc_ctx* ctx, int64_t n, const int32_t* tables, double* p_out, double* or_out) {
+    if (!ctx) return SMC_E_ARG;
+    if (n < 0 || (n > 0 && (!tables || !p_out || !or_out))) { ctx->err = "smc_fisher_exact: bad arguments"; return SMC_E_ARG; }
+    if (n == 0) return SMC_OK;
+    for (int64_t i = 0; i < 4 * n; ++i) if (tables[i] < 0) { ctx->err = "smc_fisher_exact: negative cell"; return SMC_E_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_hp_bases.ensure((size_t)n * 16)); CK(ctx->d_hp_meta.ensure((size_t)n * 16));      // the candidate buffers double as scratch
+    CK(cudaMemcpyAsync(ctx->d_hp_bases.p, tables, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->st));
+    double* dp = ctx->d_hp_meta.as<double>();
+    k_fisher_tables<<<nblk(n, 128), 128, 0, ctx->st>>>(ctx->d_hp_bases.as<int32_t>(), n, (int)ctx->prm.fisherLegacy, dp, dp + n);
+    CK(cudaMemcpyAsync(p_out, dp, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(or_out, dp + n, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     CK(cudaGetLastError());
     return SMC_OK;

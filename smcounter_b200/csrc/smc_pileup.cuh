@@ -282,6 +282,7 @@ static inline uint64_t code_slots_total(uint64_t ne, uint64_t n_units, uint32_t 
 struct DynTab {
     unsigned long long* dkey; uint32_t dmask; uint32_t* drep_read; int32_t* drep_qpos; int32_t* dlen;
     int32_t* dcnt; unsigned long long* dlimb; uint8_t* diskey; uint32_t* dcount; uint32_t* gflags;
+    const uint8_t* seq; const int64_t* seq_off;      // bases of every read (caller's SoA order): long insertions are compared base by base
 };
 
 // BAM nibble of A, C, G, T (1, 2, 4, 8) -> field A0 C1 T2 G3 of the packed register counters / allele slot A0 C1 T3 G4
@@ -303,6 +304,47 @@ __device__ __noinline__ uint32_t dyn_lookup(DynTab T, unsigned long long key, ui
                 return h;
             }
             if (prev == key) return h;
+        }
+        h = (h + 1) & T.dmask;
+    }
+    atomicOr(T.gflags, GF_DYN_FULL);
+    return 0;
+}
+
+// Insertions longer than 8 bases do not fit the 64-bit key: the key carries a 32-bit hash of the inserted bases and every hit is
+// verified base by base against the entry's representative read (drep_read / drep_qpos); two different insertions with
+// equal hashes chain to separate entries, so alleles are never merged (collision free, like the short ones).
+// `my_seq0`: offset of this read's query position 0 in seq[]; the representative's comes from seq_off[] (reads with an
+// insertion are always stored whole).  drep_read doubles as the "entry published" flag (0xffffffff until the creator is done).
+__device__ __noinline__ uint32_t dyn_lookup_long_ins(DynTab T, unsigned long long key, uint32_t rep_read, int rep_qpos, int len, uint32_t my_seq0) {
+    uint32_t h = hash64to32(key) & T.dmask;
+    for (uint32_t probe = 0; probe <= T.dmask; ++probe) {
+        unsigned long long cur = __ldcg(&T.dkey[h]);
+        if (cur == DYN_EMPTY) {
+            const unsigned long long prev = atomicCAS(&T.dkey[h], DYN_EMPTY, key);
+            if (prev == DYN_EMPTY) {
+                T.drep_qpos[h] = rep_qpos; T.dlen[h] = len;
+                __threadfence();
+                atomicExch(&T.drep_read[h], rep_read);
+                uint32_t c = atomicAdd(T.dcount, 1u);
+                if (2ull * (c + 1ull) > (unsigned long long)T.dmask + 1ull) atomicOr(T.gflags, GF_DYN_FULL);
+                return h;
+            }
+            cur = prev;
+        }
+        if (cur == key) {
+            uint32_t rr;
+            while ((rr = *reinterpret_cast<volatile uint32_t*>(&T.drep_read[h])) == 0xffffffffu) { }
+            __threadfence();
+            const int rq = *reinterpret_cast<volatile int32_t*>(&T.drep_qpos[h]);
+            const uint32_t rs0 = (uint32_t)T.seq_off[rr];
+            bool eq = true;
+            for (int t = 1; t <= len && eq; ++t) {
+                const int qa = rep_qpos + t, qb = rq + t;
+                const uint32_t ba = __ldg(T.seq + (uint32_t)(my_seq0 + (uint32_t)(qa >> 1))), bb = __ldg(T.seq + (uint32_t)(rs0 + (uint32_t)(qb >> 1)));
+                eq = ((qa & 1) ? (ba & 15u) : (ba >> 4)) == ((qb & 1) ? (bb & 15u) : (bb >> 4));
+            }
+            if (eq) return h;
         }
         h = (h + 1) & T.dmask;
     }
@@ -496,7 +538,7 @@ __device__ __noinline__ uint2 slow_event(DynTab T, const uint32_t* __restrict__ 
         len = -indel;
         key = dyn_make_key((uint32_t)Li, SMC_K_DEL, nib, (unsigned long long)len);
     }
-    const uint32_t e = dyn_lookup(T, key, __ldg(rw + 10), qpos, len);
+    const uint32_t e = (indel > 8) ? dyn_lookup_long_ins(T, key, __ldg(rw + 10), qpos, len, seq_off) : dyn_lookup(T, key, __ldg(rw + 10), qpos, len);
     atomicAdd(&T.dcnt[(size_t)e * SMC_NCNT + SMC_C_ALLELE], 1);
     if (!reverse) atomicAdd(&T.dcnt[(size_t)e * SMC_NCNT + SMC_C_FWD], 1);
     return make_uint2(code, NF + e);

@@ -62,6 +62,7 @@ def argParseInit():
     parser.add_argument('--logFile', default=None, help='log file')
     parser.add_argument('--paramFile', default=None, help='optional parameter file that contains the above paramters. if specified, this must be the only parameter, except for --logFile.')
     parser.add_argument('--gpus', type=int, default=1, help='number of B200 GPUs to shard the target over (BED intervals, balanced by depth)')
+    parser.add_argument('--fisherLegacy', type=int, default=0, help='1: two-sided Fisher p-values as scipy <= 1.6 computed them (epsilon = 1 - 1e-4, the scipy of the 2017 reference run); 0 (default): scipy >= 1.7')
 
 
 def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None, stage_times: dict | None = None,
@@ -175,7 +176,8 @@ def main(args):
     refs = FastaFile(args.refGenome)
     reads = read_bam(args.bamFile, intervals, threads=max(1, args.nCPU), trim=True)      # only the target windows cross PCIe
     prm = VcParams(mtDepth=args.mtDepth, rpb=args.rpb, minBQ=args.minBQ, minMQ=args.minMQ, hpLen=args.hpLen,
-                   mismatchThr=args.mismatchThr, mtDrop=args.mtDrop, maxMT=args.maxMT, primerDist=args.primerDist)
+                   mismatchThr=args.mismatchThr, mtDrop=args.mtDrop, maxMT=args.maxMT, primerDist=args.primerDist,
+                   fisherLegacy=args.fisherLegacy)
     try:
         output = call_loci(reads, intervals, refs, prm, gpus=args.gpus)
     except Exception as e:

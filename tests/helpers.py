@@ -186,3 +186,25 @@ def run_case(intervals, spec: SynthSpec, prm: VcParams, seed: int, verbose=False
         for p in problems:
             print("  ", p)
     return problems, stats, (soa, refs, o_rows, g_rows, res, details)
+
+
+def run_records(records, intervals, refs, prm: VcParams, chroms=None, verbose=False):
+    """Hand-made reads (oracle.Read records in BAM order) through the CUDA path and the oracle: (problems, stats, extras)."""
+    from smcounter_b200.soa import records_to_soa
+    soa = records_to_soa(records, chroms)
+    index = orc.ReadIndex(records)
+    o_rows, details = [], []
+    for (chrom, pos) in loc_list(intervals):
+        d = {}
+        o_rows.append(orc.vc(index, chrom, pos, prm.minBQ, prm.minMQ, prm.mtDepth, prm.rpb, prm.hpLen, prm.mismatchThr, prm.mtDrop,
+                             prm.maxMT, prm.primerDist, refs, detail=d))
+        details.append(d)
+    g_rows, res, loci, bed_order, tm = gpu_run(soa, intervals, refs, prm)
+    problems, stats = diff_details(res, loci, bed_order, details, soa, refs)
+    problems += diff_rows(g_rows, o_rows)
+    stats.update(n_dyn=tm["n_dyn"], events=tm["n_pileup_events"])
+    if verbose:
+        print(stats)
+        for p in problems:
+            print("  ", p)
+    return problems, stats, (soa, o_rows, g_rows, res, details)

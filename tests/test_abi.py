@@ -31,7 +31,7 @@ def test_exports_every_declared_symbol(lib):
     assert set(names) == set(_ffi.EXPORTS), (names, _ffi.EXPORTS)
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.smc_version() == 2
+    assert lib.smc_version() == 3
     out = subprocess.run(["nm", "-D", "--defined-only", _ffi.LIB_PATH], capture_output=True, text=True).stdout
     for n in names:
         assert re.search(r"\bT %s\b" % n, out), n

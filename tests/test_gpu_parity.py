@@ -488,6 +488,153 @@ def test_barcode_with_many_dynamic_alleles_at_one_locus(codes):
     assert not problems, "\n".join(problems)
 
 
+def _hand_reads(ref_seq, site, families, read_len=70):
+    """Paired reads over one amplicon of ``ref_seq`` (chrom 'c1'): ``families`` = [(barcode, n_fragments, inserted bases or '')];
+    every read starts at 0, R1 forward / R2 reverse, the insertion (if any) follows reference position ``site`` (0-based)."""
+    from oracle import smcounter_oracle as orc
+    recs = []
+    fid = 0
+    for (bc, nfrag, ins) in families:
+        for _ in range(nfrag):
+            fid += 1
+            for flag in (0x40, 0x80 | 0x10):
+                if ins:
+                    seq = ref_seq[:site + 1] + ins + ref_seq[site + 1:read_len]
+                    cigar = [(0, site + 1), (1, len(ins)), (0, read_len - site - 1)]
+                    nm = len(ins)
+                else:
+                    seq = ref_seq[:read_len]; cigar = [(0, read_len)]; nm = 0
+                recs.append(orc.Read("M%d:%s:x" % (fid, bc), "c1", 0, flag, 60, nm, cigar, seq, [37] * len(seq)))
+    return recs
+
+
+def test_long_insertions_with_equal_hashes_stay_separate_alleles():
+    """Insertions longer than 8 bases are keyed by a 32-bit hash of the inserted bases plus a base-by-base check against the entry's
+    representative read.  TGCATGTACCCG and TTGACGGACAGA have the SAME hash (found by exhaustive search over all 12-mers): before
+    the check they were merged into one allele.  A third, 20-base insertion rides along."""
+    import random
+    from helpers import run_records
+    from oracle import smcounter_oracle as orc
+    rng = random.Random(5)
+    ref_seq = "".join(rng.choice("ACGT") for _ in range(120))
+    refs = orc.DictFasta({"c1": ref_seq})
+    x, y, z = "TGCATGTACCCG", "TTGACGGACAGA", "ACGTTGCAACGTTGCAACGT"
+    fam = []
+    for k, ins in enumerate([x] * 5 + [y] * 4 + [z] * 2 + [""] * 3):       # unequal support: no exact PI tie between the insertions
+        bc = "".join(rng.choice("ACGT") for _ in range(12))
+        fam.append((bc, 3, ins))
+    recs = _hand_reads(ref_seq, 33, fam)
+    problems, stats, (soa, o_rows, g_rows, res, details) = run_records(recs, [("c1", 30, 38)], refs, VcParams(mtDepth=14, rpb=3.0), chroms=["c1"])
+    print(stats)
+    d = details[3]                                        # locus 34 (1-based) = site 33: the insertion start
+    site = ref_seq[33]
+    for ins, nbc in ((x, 5), (y, 4), (z, 2)):
+        assert d["alleleCnt"]["INS|%s|%s%s" % (site, site, ins)] == 6 * nbc
+    assert stats["n_dyn"] >= 3
+    assert not problems, "\n".join(problems)
+
+
+def _fisher_tables(n, seed, scales=(6, 60, 3000, 100000), near_sym_scale=30000):
+    """Random 2x2 tables at smCounter's scales: tiny, panel-sized, 1e5-cell, exactly symmetric margins (mirrored outcomes tie with
+    the observed one), near-symmetric ones, and degenerate rows / columns."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out = []
+    for scale in scales:
+        t = rng.integers(0, scale, size=(n // 8, 4))
+        out.append(t)
+        u = rng.integers(0, scale, size=(n // 16, 4))                      # a strongly skewed second row: the SB / R1CP shape
+        u[:, 2:] = rng.integers(0, max(2, scale // 50), size=(len(u), 2))
+        out.append(u)
+    sym = rng.integers(0, 400, size=(n // 8, 4))
+    sym[:, 3] = np.maximum(sym[:, 0] + sym[:, 2] - sym[:, 1], 0)           # a + c == b + d when possible
+    out.append(sym)
+    sym2 = rng.integers(0, near_sym_scale, size=(n // 16, 4))
+    sym2[:, 1] = sym2[:, 0] + rng.integers(-2, 3, size=len(sym2)); sym2[:, 3] = sym2[:, 2] + rng.integers(-2, 3, size=len(sym2))
+    out.append(np.maximum(sym2, 0))
+    deg = rng.integers(0, 50, size=(n // 16, 4))
+    deg[np.arange(len(deg)), rng.integers(0, 4, size=len(deg))] = 0
+    deg[::3, :2] = 0; deg[1::7, [0, 2]] = 0
+    out.append(deg)
+    out.append(np.array([[3, 0, 0, 3], [0, 5, 5, 0], [7, 0, 3, 0], [0, 0, 3, 4], [10, 20, 25, 15], [30000, 30100, 150, 50], [1, 1, 1, 1],
+                         [0, 0, 0, 0], [45000, 44000, 12, 90], [2, 99999, 99999, 2]]))
+    return np.concatenate(out).astype(np.int32)
+
+
+def _scipy_fisher(t):
+    import scipy.stats
+    r = scipy.stats.fisher_exact([[int(t[0]), int(t[1])], [int(t[2]), int(t[3])]])
+    return float(r[0]), float(r[1])
+
+
+def _legacy_fisher(t):
+    from oracle import smcounter_oracle as orc
+    return orc.fisher_exact_legacy([[int(t[0]), int(t[1])], [int(t[2]), int(t[3])]])
+
+
+P_FLOOR = 1e-280     # below this the recurrence weights underflow relative to the mode: only "p is that small" is asserted
+
+
+def _fisher_diff(tables, got_p, got_or, want, p_rtol):
+    import math
+    from helpers import rel_err
+    bad, worst, n_tiny = [], 0.0, 0
+    for t, gp, go, (wo, wp) in zip(tables, got_p, got_or, want):
+        same_or = (math.isnan(go) and math.isnan(wo)) or go == wo or rel_err(float(go), wo) <= 1e-12
+        if wp < P_FLOOR:
+            n_tiny += 1
+            ok_p = float(gp) < 1e-270
+        else:
+            e = rel_err(float(gp), wp)
+            worst = max(worst, e if math.isfinite(e) else 1.0)
+            ok_p = e <= p_rtol
+        if not ok_p or not same_or:
+            bad.append((t.tolist(), float(gp), wp, float(go), wo))
+    return bad, worst, n_tiny
+
+
+def test_fisher_kernel_against_scipy_on_100k_tables():
+    """k_fisher's arithmetic (smc_fisher_exact: the same device function smc_call_batch uses for SB / R1CP / R2CP / PrimerCP,
+    smCounter.py:215-266) against scipy.stats.fisher_exact on 100 000 tables: p within 1e-9 relative, odds ratio identical
+    (inf / nan included).  The pipeline itself only exercises a few dozen tables per parity case.  For p < 1e-280 -- 275 orders of
+    magnitude below the filters' cut-offs (1e-3, 1e-5) -- only the smallness is asserted: the mode-relative weights underflow there."""
+    import multiprocessing
+    import os
+    from smcounter_b200.caller import GpuCaller
+    tables = _fisher_tables(100000, seed=1)
+    assert len(tables) >= 90000
+    c = GpuCaller(VcParams(mtDepth=100, rpb=3.0), 0)
+    p, o = c.fisher_exact(tables)
+    c.close()
+    with multiprocessing.get_context("fork").Pool(min(os.cpu_count() or 1, 32)) as pool:
+        want = pool.map(_scipy_fisher, tables, chunksize=512)
+    bad, worst, n_tiny = _fisher_diff(tables, p, o, want, 1e-9)
+    print("fisher: %d tables (%d with p < %g), worst relative p error above that %.2e, %d failures" % (len(tables), n_tiny, P_FLOOR, worst, len(bad)))
+    assert not bad, bad[:5]
+
+
+def test_fisher_kernel_legacy_scipy_semantics():
+    """fisherLegacy = 1: the two-sided p of scipy <= 1.6 (epsilon = 1 - 1e-4), against the oracle's literal restatement of that
+    algorithm; includes near-symmetric tables where the two eras differ by one mirrored outcome."""
+    import multiprocessing
+    import os
+    from smcounter_b200.caller import GpuCaller
+    tables = _fisher_tables(2400, seed=2, scales=(6, 60, 1500), near_sym_scale=4000)     # (the old algorithm is slow on huge tables)
+    c = GpuCaller(VcParams(mtDepth=100, rpb=3.0, fisherLegacy=1), 0)
+    p, o = c.fisher_exact(tables)
+    c.close()
+    c0 = GpuCaller(VcParams(mtDepth=100, rpb=3.0), 0)
+    p0, _ = c0.fisher_exact(tables)
+    c0.close()
+    with multiprocessing.get_context("fork").Pool(min(os.cpu_count() or 1, 32)) as pool:
+        want = pool.map(_legacy_fisher, tables, chunksize=128)
+    bad, worst, _ = _fisher_diff(tables, p, o, want, 1e-9)
+    n_era = int((abs(p - p0) > 1e-12 * abs(p0)).sum())
+    print("legacy fisher: %d tables, worst relative p error %.2e, %d outside 1e-9; %d tables where the two scipy eras differ" % (len(tables), worst, len(bad), n_era))
+    assert not bad, bad[:5]
+    assert n_era > 0
+
+
 def _fuzz_seeds():
     """Seeds of the differential fuzz; SMC_FUZZ_SEEDS=a:b runs a wider sweep by hand (e.g. 200:300)."""
     import os

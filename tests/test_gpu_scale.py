@@ -65,18 +65,45 @@ def _check_properties(res, soa, loci):
     assert np.isfinite(res.pi).all() and (res.pi >= 0).all()
 
 
+_ORC = {}
+
+
+def _oracle_one(cp):
+    from oracle import smcounter_oracle as orc
+    prm = _ORC["prm"]
+    c, p = cp
+    return orc.vc(_ORC["index"], c, str(p + 1), prm.minBQ, prm.minMQ, prm.mtDepth, prm.rpb, prm.hpLen, prm.mismatchThr, prm.mtDrop,
+                  prm.maxMT, prm.primerDist, _ORC["refs"])
+
+
 def _oracle_rows_for(soa, refs, prm, positions):
-    """Oracle rows for [(chrom, pos0)] using only the reads that overlap them."""
+    """Oracle rows for [(chrom, pos0)] using only the reads that overlap them; one forked worker per host core (the oracle
+    is the reference's per-locus Python: ~0.1 - 1 s per locus at these depths)."""
+    import multiprocessing
+    import os
     from oracle import smcounter_oracle as orc
     from smcounter_b200.soa import soa_to_records
     cidx = {c: i for i, c in enumerate(soa.chroms)}
     ends = soa.ref_end()
     mask = np.zeros(soa.n, dtype=bool)
+    by_chrom = {}
     for (c, p) in positions:
-        mask |= (soa.ref_id == cidx[c]) & (soa.pos <= p) & (ends > p)
-    index = orc.ReadIndex(soa_to_records(soa.select(np.flatnonzero(mask)), orc.Read))
-    return [orc.vc(index, c, str(p + 1), prm.minBQ, prm.minMQ, prm.mtDepth, prm.rpb, prm.hpLen, prm.mismatchThr, prm.mtDrop,
-                   prm.maxMT, prm.primerDist, refs) for (c, p) in positions]
+        by_chrom.setdefault(c, []).append(p)
+    for c, ps in by_chrom.items():
+        ps = np.sort(np.asarray(ps))
+        on = soa.ref_id == cidx[c]
+        # a read is needed iff some requested position lies in [pos, end)
+        nxt = np.searchsorted(ps, soa.pos[on], side="left")
+        hit = np.zeros(int(on.sum()), dtype=bool)
+        ok = nxt < len(ps)
+        hit[ok] = ps[nxt[ok]] < ends[on][ok]
+        mask[np.flatnonzero(on)[hit]] = True
+    _ORC.update(index=orc.ReadIndex(soa_to_records(soa.select(np.flatnonzero(mask)), orc.Read)), refs=refs, prm=prm)
+    workers = min(os.cpu_count() or 1, 32, max(1, len(positions)))
+    if workers == 1:
+        return [_oracle_one(cp) for cp in positions]
+    with multiprocessing.get_context("fork").Pool(workers) as pool:
+        return pool.map(_oracle_one, positions, chunksize=1)
 
 
 def _sample_positions(intervals, truth, rng, n_random, n_truth):
@@ -141,16 +168,43 @@ def test_cfg2_panel_batch_properties_sharding_and_oracle_sample():
             assert np.array_equal(getattr(res, f), getattr(again, f)), f
     finally:
         caller.close()
-    n = _compare_with_oracle(g_rows, ivs, soa, refs, prm, truth, seed=3, n_random=10, n_truth=6)
-    assert n >= 10
+    n = _compare_with_oracle(g_rows, ivs, soa, refs, prm, truth, seed=3, n_random=200, n_truth=24)
+    assert n >= 200
     # the same panel as three shards (three contexts, depth-balanced interval groups): rows identical to the single batch
     assert call_loci(soa, ivs, refs, prm, gpus=3, devices=[0, 0, 0]) == g_rows
+
+
+@pytest.mark.parametrize("umis", [5500, 10400])
+def test_cfg1_example_shaped_every_locus_against_the_oracle(umis):
+    """BASELINE config 1 in its synthetic form (example.bam is not distributed): the parameters of
+    /root/reference/example/run.example.sh:4-24 (mtDepth 3612, rpb 8.6, mtDrop 1, hpLen 8, minBQ 20, minMQ 30, mismatchThr 6.0,
+    primerDist 2) on an example-shaped amplicon -- ~4 100 barcodes per locus at 9.8 fragments per barcode (the example: 4 162),
+    and a deep variant at ~7 800 barcodes where ds = 2 * 3612 = 7 224 fires and the product draws the Python-2
+    random.sample() mask itself.  EVERY locus is compared with the oracle, row for row."""
+    from helpers import diff_rows
+    from smcounter_b200.smCounter import call_loci
+    ivs = [("chr17", 41243700, 41243800)]
+    spec = SynthSpec(umis_per_locus=umis, rpb=9.8, snv_every=25, snv_vaf=0.01, indel_every=60, indel_vaf=0.02)
+    prm = VcParams(mtDepth=3612, rpb=8.6, minBQ=20, minMQ=30, hpLen=8, mismatchThr=6.0, mtDrop=1, maxMT=0, primerDist=2)
+    soa, refs, truth = make_panel_mp(ivs, spec, seed=20170410)
+    g_rows = call_loci(soa, ivs, refs, prm, gpus=1)
+    picks = [(c, p) for (c, s, e) in ivs for p in range(s, e)]
+    want = _oracle_rows_for(soa, refs, prm, picks)
+    umt = [int(r.split("\t")[9]) for r in want]
+    mt = [int(r.split("\t")[7]) for r in want]
+    print("cfg1-shaped: %d loci, MT %d..%d, UMT %d..%d, DP %s..%s" % (len(want), min(mt), max(mt), min(umt), max(umt), want[0].split("\t")[5], want[-1].split("\t")[5]))
+    if umis > 7224:
+        assert max(umt) == 7224 and sum(1 for u in umt if u == 7224) > 50        # down-sampling fired (smCounter.py:486-500)
+    else:
+        assert max(umt) < 7224 and min(mt) > 2000
+    problems = diff_rows(g_rows, want)
+    assert not problems, "\n".join(problems)
 
 
 def test_cfg3_deep_low_vaf_shape():
     """BASELINE config 3 shape: 20 000 barcodes per locus (E ~ 1e5 reads per locus, hundreds of units per tile), 0.5 % VAF
     spike-ins, mtDepth 20000 (ds = 40 000: no down-sampling)."""
-    ivs = [("chr7", 55000, 55048)]
+    ivs = [("chr7", 55000, 55200)]
     spec = SynthSpec(umis_per_locus=20000, rpb=4.0, snv_every=12, snv_vaf=0.005)
     prm = VcParams(mtDepth=20000, rpb=4.0)
     soa, refs, truth = make_panel_mp(ivs, spec, seed=2)
@@ -162,7 +216,8 @@ def test_cfg3_deep_low_vaf_shape():
         g_rows = format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order, hp_flags=hp)
     finally:
         caller.close()
-    _compare_with_oracle(g_rows, ivs, soa, refs, prm, truth, seed=5, n_random=2, n_truth=2)
+    n = _compare_with_oracle(g_rows, ivs, soa, refs, prm, truth, seed=5, n_random=200, n_truth=16)      # every locus of the batch
+    assert n >= 200
 
 
 def test_cfg5_many_loci_many_contigs_shape():
@@ -187,7 +242,8 @@ def test_cfg5_many_loci_many_contigs_shape():
         assert format_rows(res, soa, loci, soa.chroms, refs, prm.hpLen, bed_order[:20000], workers=1, hp_flags=hp) == g_rows[:20000]
     finally:
         caller.close()
-    _compare_with_oracle(g_rows, ivs, soa, refs, prm, truth, seed=9, n_random=40, n_truth=20)
+    n = _compare_with_oracle(g_rows, ivs, soa, refs, prm, truth, seed=9, n_random=200, n_truth=40)
+    assert n >= 200
     assert call_loci(soa, ivs, refs, prm, gpus=8, devices=[0] * 8) == g_rows
     # one GPU, the target streamed through it in batches of at most 20 000 loci (the per-batch limits, scaled down)
     st = {}
@@ -258,3 +314,46 @@ def test_cfg4_indel_and_repeat_heavy_panel_through_the_cli(tmp_path):
     assert open(prefix + ".smCounter.cut.txt").read() == cut_txt
     assert open(prefix + ".smCounter.cut.vcf").read() == cut_vcf
     assert "RepT" in all_txt and any(t in all_txt for t in ("RepS", "LowC", "SL", "Other_Repeat")) and "INDEL" in all_txt
+
+
+def test_example_bam_against_the_committed_golden_output(tmp_path):
+    """BASELINE config 1 proper: /root/reference/example/run.example.sh on the real example.bam, diffed against the committed
+    example.smCounter.all.txt / .cut.txt / .cut.vcf.  The BAM (76 MB) and hg19 are not distributed with the reference and there
+    is no network here, so this runs only where they are supplied:
+
+        SMC_EXAMPLE_BAM=/path/example.bam  SMC_HG19=/path/ucsc.hg19.fasta  [SMC_TRF_BED=simpleRepeat.bed  SMC_RM_BED=SR_LC_SL.nochr.bed]
+
+    Expected: every integer column identical; PI columns equal as printed except for last-digit effects of the summation order
+    (DESIGN.md section 5); the 8 rows at UMT = 7224 depend on the Python-2 random.sample emulation."""
+    import os
+    bam_path, fa = os.environ.get("SMC_EXAMPLE_BAM"), os.environ.get("SMC_HG19")
+    if not bam_path or not fa:
+        pytest.skip("set SMC_EXAMPLE_BAM and SMC_HG19 to run the reference's example (files not distributed with the reference)")
+    from smcounter_b200 import smCounter
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    prefix = str(tmp_path / "example")
+    smCounter.argParseInit()
+    thr = smCounter.main({"outPrefix": prefix, "bamFile": bam_path, "bedTarget": os.path.join(gold, "example.bed"), "mtDepth": 3612, "rpb": 8.6,
+                          "nCPU": os.cpu_count() or 1, "minBQ": 20, "minMQ": 30, "hpLen": 8, "mismatchThr": 6.0, "mtDrop": 1, "maxMT": 0,
+                          "primerDist": 2, "threshold": 0, "refGenome": fa, "bedTandemRepeats": os.environ.get("SMC_TRF_BED", "none"),
+                          "bedRepeatMaskerSubset": os.environ.get("SMC_RM_BED", "none")})
+    assert thr == 58                                                       # ceil(14 + 0.012 * 3612), example.smCounter.cut.txt
+    got = open(prefix + ".smCounter.all.txt").read().split("\n")
+    want = open(os.path.join(gold, "example.smCounter.all.txt")).read().split("\n")
+    assert got[0] == want[0] and len(got) == len(want)
+    int_cols = [5, 6, 7, 8, 9, 11, 13, 15] + list(range(16, 20)) + list(range(24, 32)) + list(range(36, 40))
+    bad_int, bad_any = [], []
+    for g, w in zip(got[1:], want[1:]):
+        if g == w:
+            continue
+        gf, wf = g.split("\t"), w.split("\t")
+        bad_any.append((wf[1], [(i, gf[i], wf[i]) for i in range(min(len(gf), len(wf))) if gf[i] != wf[i]][:6]))
+        if wf[9] != "7224" and any(gf[i] != wf[i] for i in int_cols):
+            bad_int.append(bad_any[-1])
+    print("example.bam: %d rows, %d differ in any column, %d differ in an integer column outside the down-sampled rows" % (len(want) - 2, len(bad_any), len(bad_int)))
+    for b in bad_any[:40]:
+        print("  ", b)
+    if "SMC_TRF_BED" not in os.environ:
+        bad_any = [b for b in bad_any if not all(i == 44 for (i, _, _) in b[1])]       # FILTER column carries RepT in the golden run
+    assert not bad_int, bad_int[:10]
+    assert len(bad_any) <= 40
