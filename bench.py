@@ -1,15 +1,17 @@
 #!/usr/bin/env python
-"""bench.py -- target loci called / s on the synthetic N0030 panel (BASELINE.json config 2), one process per GPU.
+"""bench.py -- target loci called / s (BASELINE.json metric) on synthetic UMI-tagged panel reads, one process per GPU.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...   # the reference's algorithm on the host CPU (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's own vc() on the host CPU (oracle/_ref)
 
-A "step" is one pass of the hot path (K1 prep -> K2 sorts -> K3 tile pileup -> K4 statistics) over one batch:
-``--intervals`` seeded intervals of the N0030 panel BED per GPU, ~3 000 barcodes per locus, ~4 read pairs per
-barcode, 2 x 150 bp.  ``value`` is measured with the batch resident in HBM, ``e2e`` through
-``GpuCaller.call()`` with pinned host buffers (H2D + kernels + D2H inside the timed region).  The panel is sharded
-across GPUs by BED interval (weak scaling: every rank gets its own ``--intervals`` intervals); loci are independent,
-so there is no data-path collective -- torch.distributed is used for the barrier and the max-over-ranks only.
+Workload (``--workload``, default cfg2 = BASELINE.json configs[1]): seeded intervals of the N0030 panel BED, ~3 000 barcodes
+per locus, ~4 read pairs per barcode, 2 x 150 bp.  A "step" is one pass of the hot path over one slice of the panel per GPU:
+``--batches`` DISTINCT library batches of ``--intervals`` panel intervals each (every batch has its own reads and its own
+pinned host buffers), streamed through the GPU one after the other -- so a timed region of K steps runs K x batches different
+device calls, not the same batch K times.  ``value`` is measured with the batches resident in HBM (one context per batch),
+``e2e`` through ``GpuCaller.call()`` + the device HP / LowC pass from pinned host buffers (H2D + kernels + D2H inside the timed
+region, every step).  The panel is sharded across GPUs by BED interval (weak scaling: every rank gets its own slice); loci are
+independent, so there is no data-path collective -- torch.distributed is used for the barrier and the max-over-ranks only.
 """
 from __future__ import annotations
 
@@ -31,61 +33,134 @@ UNIT = "loci/s"
 ALGO_BYTES_PER_EVENT = 35.0     # reads in once (2.7 B/event) + every 16-byte event written once and read once
 UMIS_PER_LOCUS, RPB = 3000, 4.0
 
+# BASELINE.json configs as bench workloads: (description, SynthSpec keywords, VcParams keywords, default intervals per batch)
+WORKLOADS = {
+    "cfg2": ("cfg2 synthetic N0030 194-gene panel (primers...coding.bed geometry), 3000 UMIs/locus, rpb 4, 2x150bp",
+             dict(umis_per_locus=3000, rpb=4.0, snv_every=1000, snv_vaf=0.01, indel_every=12000, indel_vaf=0.01),
+             dict(mtDepth=3000, rpb=4.0, minBQ=20, minMQ=30, hpLen=10, mismatchThr=6.0, mtDrop=0, maxMT=0, primerDist=2), 96),
+    "cfg1": ("cfg1 example-shaped (run.example.sh parameters): BRCA1 amplicon chr17:41243700-41245700 in 100-locus intervals, ~4100 UMIs/locus, 9.8 fragments/UMI",
+             dict(umis_per_locus=5500, rpb=9.8, snv_every=250, snv_vaf=0.01, indel_every=600, indel_vaf=0.02),
+             dict(mtDepth=3612, rpb=8.6, minBQ=20, minMQ=30, hpLen=8, mismatchThr=6.0, mtDrop=1, maxMT=0, primerDist=2), 5),
+    "cfg3": ("cfg3 synthetic deep low-VAF panel: 150-bp amplicons, 20000 UMIs/locus, rpb 4, 0.5% VAF spike-ins every 50 bp",
+             dict(umis_per_locus=20000, rpb=4.0, snv_every=50, snv_vaf=0.005),
+             dict(mtDepth=20000, rpb=4.0, minBQ=20, minMQ=30, hpLen=10, mismatchThr=6.0, mtDrop=0, maxMT=0, primerDist=2), 8),
+    "cfg5": ("cfg5 exome-scale shape: 200-bp intervals over 24 contigs, 1000 UMIs/locus, rpb 4, log-normal depth per interval (sigma 0.5)",
+             dict(umis_per_locus=1000, rpb=4.0, snv_every=1000, snv_vaf=0.05, depth_sigma=0.5),
+             dict(mtDepth=1000, rpb=4.0, minBQ=20, minMQ=30, hpLen=10, mismatchThr=6.0, mtDrop=0, maxMT=4000, primerDist=2), 320),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
-    ap.add_argument("--intervals", type=int, default=96, help="panel intervals per GPU in one batch")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--intervals", type=int, default=0, help="target intervals per library batch (0 = the workload's default; cfg2: 96)")
+    ap.add_argument("--batches", type=int, default=4, help="distinct batches streamed per step and GPU")
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--cpu-loci", type=int, default=0, help="loci in the CPU-baseline sample (0 = 2 per core)")
+    ap.add_argument("--cpu-loci", type=int, default=0, help="loci in the CPU-baseline sample (0 = 24 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--whole-reads", action="store_true", help="upload whole reads instead of the target windows (store_lo/store_len)")
+    ap.add_argument("--no-compact", action="store_true", help="upload one byte per quality and 32-bit scalars instead of the compact ABI v3 encodings")
     ap.add_argument("--pipeline-intervals", type=int, default=12,
-                    help="intervals of the rank-0 batch run once through the whole CLI path (BAM decode -> files); 0 = skip")
-    return ap.parse_args()
+                    help="intervals of the rank-0 batch run through the whole CLI path (BAM decode -> files); 0 = skip")
+    ap.add_argument("--pipeline-repeats", type=int, default=5)
+    a = ap.parse_args()
+    if a.intervals <= 0:
+        a.intervals = WORKLOADS[a.workload][3]
+    return a
 
 
-def make_batch(args, rank, world):
-    import pickle
-    from smcounter_b200.synth import SynthSpec, make_panel_mp, panel_intervals_from_bed
-    from smcounter_b200.targets import build_loci
-    cache = os.environ.get("SMC_BENCH_CACHE")           # tuning sessions: reuse the generated batch between runs
-    if cache:
-        cache = "%s.%d_%d_%d_%d_%d" % (cache, args.intervals, args.seed, rank, world, int(args.whole_reads))
-        if os.path.exists(cache):
-            with open(cache, "rb") as fh:
-                return pickle.load(fh)
-    ivs = panel_intervals_from_bed(PANEL_BED, limit=args.intervals * world, seed=args.seed)
+def workload_intervals(args, world):
+    """The intervals of the whole job: ``world * batches * intervals`` of them, in BED order."""
+    from smcounter_b200.synth import panel_intervals_from_bed
+    need = args.intervals * args.batches * world
+    if args.workload == "cfg2":
+        return panel_intervals_from_bed(PANEL_BED, limit=need, seed=args.seed)
+    if args.workload == "cfg1":
+        return [("chr17", 41243700 + 100 * k, 41243700 + 100 * (k + 1)) for k in range(need)]
+    if args.workload == "cfg3":
+        return [("chr%d" % (1 + k % 22), 100000 + 1000 * (k // 22), 100000 + 1000 * (k // 22) + 150) for k in range(need)]
+    return [("chr%d" % (1 + k % 24), 100000 + 700 * (k // 24), 100000 + 700 * (k // 24) + 200) for k in range(need)]
+
+
+def rank_batches(args, rank, world):
+    """[intervals of batch 0, batch 1, ...] of this rank: the job's intervals go to ranks by the product's own multi-GPU plan
+    (shard.assign_intervals: balanced by estimated work = interval length + a margin for the reads hanging over both ends; margin
+    measured at N=4 on B200: 150 -> 5.14 ms max step, 300 -> 4.88, 600 -> 4.84), then to the rank's batches in BED order."""
+    ivs = workload_intervals(args, world)
     if world > 1:
-        # the product's own multi-GPU plan (shard.assign_intervals): BED intervals to ranks, balanced by estimated work
-        # (uniform depth here, so ~ interval length + a margin for the reads hanging over both ends), not by interval count.
-        # Margin measured at N=4 on B200: 150 -> 5.14 ms max step, 300 -> 4.88, 600 -> 4.84 (ideal 4.54)
         from smcounter_b200.shard import assign_intervals
         margin = float(os.environ.get("SMC_BENCH_MARGIN", "500"))
         shard, _ = assign_intervals([float(e - s) + margin for (_, s, e) in ivs], world)
-        mine = [iv for iv, g in zip(ivs, shard) if g == rank]
+        ivs = [iv for iv, g in zip(ivs, shard) if g == rank]
+    nb = args.batches
+    cuts = [(len(ivs) * k) // nb for k in range(nb + 1)]
+    return [ivs[cuts[k]:cuts[k + 1]] for k in range(nb)]
+
+
+def _gen_batch(job):
+    """One batch in a worker process: synthetic reads, trimmed to the targets and compacted (what the BAM decoder delivers)."""
+    (ivs, spec_kw, seed, whole, no_compact, workers, keep_full) = job
+    from smcounter_b200.synth import SynthSpec, make_panel_mp
+    from smcounter_b200.targets import build_loci
+    soa, refs, truth = make_panel_mp(ivs, SynthSpec(**spec_kw), seed=seed, workers=workers)
+    full = soa
+    if not whole:
+        soa = soa.trim_to_targets(ivs)
+        if not no_compact:
+            soa = soa.compact()                         # 16-bit scalars, 2- / 4-bit quality codes + codebook (expanded on the device)
+    loci, bed_order = build_loci(ivs, soa.chroms, refs)
+    return ivs, soa, refs, loci, bed_order, (full if keep_full else None)
+
+
+def make_batches(args, rank, world, only_first=False):
+    """[(intervals, upload SoA, refs, loci, bed_order, whole-read SoA or None)] of this rank; generated by one worker process per
+    batch (each with its share of the host cores)."""
+    import pickle
+    from concurrent.futures import ProcessPoolExecutor
+    cache = os.environ.get("SMC_BENCH_CACHE")           # tuning sessions: reuse the generated batches between runs
+    if cache:
+        cache = "%s.%s_%d_%d_%d_%d_%d_%d%d%d" % (cache, args.workload, args.intervals, args.batches, args.seed, rank, world, int(args.whole_reads),
+                                              int(args.no_compact), int(only_first))
+        if os.path.exists(cache):
+            with open(cache, "rb") as fh:
+                return pickle.load(fh)
+    groups = rank_batches(args, rank, world)
+    if only_first:
+        groups = groups[:1]
+    spec_kw = WORKLOADS[args.workload][1]
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per = max(1, min(16, cores // max(1, len(groups))))
+    jobs = [(g, spec_kw, args.seed + 17 * rank + 1009 * k, args.whole_reads, args.no_compact, per, k == 0 and rank == 0) for k, g in enumerate(groups)]
+    if len(jobs) == 1:
+        out = [_gen_batch(jobs[0])]
     else:
-        mine = ivs
-    spec = SynthSpec(umis_per_locus=UMIS_PER_LOCUS, rpb=RPB, snv_every=1000, snv_vaf=0.01, indel_every=12000, indel_vaf=0.01)
-    soa, refs, truth = make_panel_mp(mine, spec, seed=args.seed + 17 * rank)
-    full = soa                                          # whole reads: the CPU legs (oracle, BAM writer) need them
-    if not args.whole_reads:
-        # what the BAM decoder hands over: only the bases a pileup over the targets can see (store_lo / store_len), packed
-        soa = soa.trim_to_targets(mine)
-    loci, bed_order = build_loci(mine, soa.chroms, refs)
+        with ProcessPoolExecutor(max_workers=len(jobs)) as ex:
+            out = list(ex.map(_gen_batch, jobs))
     if cache:
         with open(cache, "wb") as fh:
-            pickle.dump((mine, soa, refs, loci, bed_order, full), fh, protocol=4)
-    return mine, soa, refs, loci, bed_order, full
+            pickle.dump(out, fh, protocol=4)
+    return out
 
 
-def vc_params():
+def vc_params(args=None):
     from smcounter_b200.caller import VcParams
-    # --mtDepth 3000 --rpb 4.0 --mtDrop 0 --minBQ 20 --minMQ 30 --hpLen 10 (ds = 6000: no down-sampling)
-    return VcParams(mtDepth=3000, rpb=4.0, minBQ=20, minMQ=30, hpLen=10, mismatchThr=6.0, mtDrop=0, maxMT=0, primerDist=2)
+    # cfg2 = SURVEY.md 8(d): --mtDepth 3000 --rpb 4.0 --mtDrop 0 --minBQ 20 --minMQ 30 --hpLen 10 (ds = 6000: no down-sampling)
+    return VcParams(**WORKLOADS[args.workload if args is not None else "cfg2"][2])
+
+
+def config_dict(args, world):
+    """The ``config`` of the JSON line: identical for the CUDA arm and the reference arm (same workload, same loci)."""
+    ivs = workload_intervals(args, world)
+    p = WORKLOADS[args.workload][2]
+    return {"workload": WORKLOADS[args.workload][0] + "; one step = %d distinct batches of %d intervals per GPU" % (args.batches, args.intervals),
+            "intervals_per_batch": args.intervals, "batches_per_step": args.batches, "loci_per_step": int(sum(e - s for (_, s, e) in ivs)),
+            "params": " ".join("%s %s" % kv for kv in p.items()), "seed": args.seed,
+            "l2": "every step streams %d distinct batches (hundreds of MB each): inputs larger than L2, no flush needed" % args.batches,
+            "parallelism": "panel sharded by BED interval (balanced by estimated events), no collective"}
 
 
 class ClockSampler(threading.Thread):
@@ -181,7 +256,7 @@ def _cpu_worker(job):
                   p.primerDist, _G["refs"])
 
 
-def cpu_sample_setup(soa, refs, loci, n_loci_sample):
+def cpu_sample_setup(soa, refs, loci, n_loci_sample, args=None):
     """Pick consecutive loci from the middle of the batch and the reads that overlap them (host objects for the oracle)."""
     import numpy as np
     from oracle import smcounter_oracle as orc
@@ -201,7 +276,7 @@ def cpu_sample_setup(soa, refs, loci, n_loci_sample):
     recs = soa_to_records(soa.select(np.flatnonzero(mask)), orc.Read)
     _G["index"] = orc.ReadIndex(recs)
     _G["refs"] = refs
-    _G["prm"] = vc_params()
+    _G["prm"] = vc_params(args)
     _G["ref"] = None
     if cpu_kind() == "reference":
         from oracle import ref_build, ref_shims
@@ -233,39 +308,53 @@ def cpu_run(jobs, cores, pool=None):
 
 
 def pipeline_leg(args, mine, soa, refs, device):
-    """The whole reference-facing path once, stage by stage, on the first ``--pipeline-intervals`` intervals of the rank-0
-    batch: BAM file -> libsmc_bamio decode -> SoA -> smc_call_batch -> 45-column rows -> repeat filters -> the three output
-    files (what smCounter.main() does, smCounter.py:645-909).  north_star asks for the end-to-end figure including the
-    BAM decode beside the kernel-only one; the BAM itself is written outside the timed stages."""
+    """The whole reference-facing path, stage by stage, on the first ``--pipeline-intervals`` intervals of the rank-0 batch: BAM
+    file -> libsmc_bamio decode -> SoA -> smc_call_batch -> native output stage (rows, repeat filters, called variants) -> the
+    three output files (what smCounter.main() does, smCounter.py:645-909).  north_star asks for the end-to-end figure including the
+    BAM decode beside the kernel-only one.  One warm-up pass, then ``--pipeline-repeats`` timed passes (median); the BAM itself is
+    written outside the timed stages."""
     import shutil
     import tempfile
-    import numpy as np
     from smcounter_b200 import bam, repeats, writers
+    from smcounter_b200.rows import headerAll, headerVariants
     from smcounter_b200.shard import reads_for_intervals
-    from smcounter_b200.smCounter import call_loci
+    from smcounter_b200.smCounter import call_loci_text
     ivs = mine[:args.pipeline_intervals]
     sub = soa.select(reads_for_intervals(soa, ivs, soa.chroms))
     tmp = tempfile.mkdtemp(prefix="smc_pipe_")
+    prm = vc_params(args)
     try:
         path = os.path.join(tmp, "reads.bam")
         bam.write_bam(path, sub, refs.lengths)
-        t = [time.perf_counter()]
-        reads = bam.read_bam(path, ivs, threads=os.cpu_count() or 1, trim=True)
-        t.append(time.perf_counter())
-        rows = call_loci(reads, ivs, refs, vc_params(), gpus=1, devices=[device], stage_times=(st := {}))
-        t.append(time.perf_counter())
         target_rows = [(c, str(s), str(e)) for (c, s, e) in ivs]
-        trf, rm = repeats.build_repeat_regions(target_rows, [], [])
-        rows = repeats.apply_repeat_filters(rows, trf, rm)
-        writers.write_outputs(rows, os.path.join(tmp, "out"), 3000, 0)
-        t.append(time.perf_counter())
         n_loci = sum(e - s for (_, s, e) in ivs)
-        return {"value": n_loci / (t[3] - t[0]), "unit": UNIT, "loci": n_loci, "reads": int(reads.n), "intervals": len(ivs),
-                "bam_mb": os.path.getsize(path) / 1e6, "ms_bam_decode": 1e3 * (t[1] - t[0]), "ms_call_loci": 1e3 * (t[2] - t[1]),
-                "ms_gpu_call": st.get("ms_gpu_call"), "ms_format_rows": st.get("ms_format_rows"), "gpu_call_detail": {k: v for k, v in st.items() if k not in ("ms_gpu_call", "ms_format_rows")},
-                "ms_filters_and_writers": 1e3 * (t[3] - t[2]),
-                "what": "BAM decode (libsmc_bamio, all host threads) + smc_call_batch + row formatting + repeat filters + the three "
-                        "output files, once, on a sub-batch of the rank-0 panel batch"}
+        runs = []
+        for rep in range(1 + max(1, args.pipeline_repeats)):
+            t = [time.perf_counter()]
+            reads = bam.read_bam(path, ivs, threads=os.cpu_count() or 1, trim=True)
+            t.append(time.perf_counter())
+            trf, rm = repeats.build_repeat_regions(target_rows, [], [])
+            thr = writers.pi_threshold(prm.mtDepth, 0)
+            a, c, v = call_loci_text(reads, ivs, refs, prm, thr, trf, rm, gpus=1, devices=[device], stage_times=(st := {}))
+            t.append(time.perf_counter())
+            with open(os.path.join(tmp, "out.smCounter.all.txt"), "wb") as fh:
+                fh.write(("\t".join(headerAll) + "\n").encode()); fh.write(a)
+            with open(os.path.join(tmp, "out.smCounter.cut.txt"), "wb") as fh:
+                fh.write(("\t".join(headerVariants) + "\n").encode()); fh.write(c)
+            with open(os.path.join(tmp, "out.smCounter.cut.vcf"), "wb") as fh:
+                fh.write(writers.vcf_header("out").encode()); fh.write(v)
+            t.append(time.perf_counter())
+            if rep > 0:
+                runs.append((t[3] - t[0], t[1] - t[0], t[2] - t[1], t[3] - t[2], dict(st), int(reads.n)))
+        runs.sort(key=lambda r: r[0])
+        tot, dec, call, wr, st, nreads = runs[len(runs) // 2]
+        return {"value": n_loci / tot, "unit": UNIT, "loci": n_loci, "reads": nreads, "intervals": len(ivs), "repeats": len(runs), "warmup": 1,
+                "bam_mb": os.path.getsize(path) / 1e6, "ms_total": 1e3 * tot, "ms_bam_decode": 1e3 * dec, "ms_call_loci_text": 1e3 * call,
+                "ms_gpu_call": st.get("ms_gpu_call"), "ms_rows_filters_calls_native": st.get("ms_format_rows"), "ms_write_files": 1e3 * wr,
+                "gpu_call_detail": {k: v for k, v in st.items() if k not in ("ms_gpu_call", "ms_format_rows")},
+                "all_runs_ms": [round(1e3 * r[0], 2) for r in runs],
+                "what": "median of %d passes after 1 warm-up: BAM decode (libsmc_bamio, all host threads, trimmed on the fly) + context + smc_call_batch + "
+                        "device HP/LowC + native rows / repeat filters / called-variant lines (libsmc_bamio: smc_rows_emit) + the three files" % len(runs)}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -278,32 +367,32 @@ def main():
     cores = os.cpu_count() or 1
 
     if args.impl == "reference":
-        # The Python-2 reference cannot run (no python2 / pysam); its algorithm is timed through the oracle port, on
-        # rank 0 only, with all host cores.  Each step is a bounded sample of the same workload.
+        # The reference arm: the reference's own per-locus code (oracle/_ref: /root/reference/smCounter.py made runnable by
+        # oracle/ref_build.py; the oracle port if that is not built) behind a multiprocessing.Pool over all host cores, exactly as
+        # smCounter.py:683-685 fans it out.  Rank 0 only.  Same workload and config as the CUDA arm; each step is a bounded
+        # sample of it (consecutive loci of the first batch), sized so that the run ends within minutes.
         if rank != 0:
             return 0
-        args.intervals = min(args.intervals, 16)     # the sample only needs the reads around its loci
-        mine, _, refs, loci, bed_order, soa = make_batch(args, 0, 1)
-        n_sample = args.cpu_loci or 48 * cores
-        jobs, nrec = cpu_sample_setup(soa, refs, loci, n_sample)
+        ivs0, _, refs, loci, bed_order, soa = make_batches(args, 0, 1, only_first=True)[0]
+        n_sample = args.cpu_loci or 16 * cores
+        jobs, nrec = cpu_sample_setup(soa, refs, loci, n_sample, args)
         import multiprocessing as mp
         pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
         for _ in range(min(args.warmup, 1)):
             cpu_run(jobs[:max(1, 2 * cores)], cores, pool)
-        vals, times, ev = [], [], 0
+        times, ev = [], 0
         for _ in range(args.steps):
             v, dt, ev = cpu_run(jobs, cores, pool)
-            vals.append(v); times.append(dt)
+            times.append(dt)
         if pool is not None:
             pool.close(); pool.join()
         value = len(jobs) * len(times) / sum(times)
+        sample = "%d consecutive loci of batch 0 per step (%d reads, %d pileup events) x %d steps; %s; multiprocessing.Pool(%d)" % (
+            len(jobs), nrec, ev, args.steps, CPU_WHAT[cpu_kind()], cores)
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-                "config": {"workload": "cfg2 synthetic N0030 194-gene panel, 3000 UMIs/locus, rpb 4, 2x150bp",
-                           "sample": "%d consecutive loci, %d reads, %d pileup events per step" % (len(jobs), nrec, ev)},
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
-                                 "sample": "%d loci per step x %d steps (%s, multiprocessing.Pool(%d))" % (len(jobs), args.steps, CPU_WHAT[cpu_kind()], cores)},
+                "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic", "config": config_dict(args, max(1, args.gpus)),
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": cpu_kind(), "sample": sample},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -313,6 +402,7 @@ def main():
     import torch
     import torch.distributed as dist
     from smcounter_b200.caller import GpuCaller, LocusResults
+    from smcounter_b200.rows import device_hp_flags
 
     torch.cuda.set_device(local_rank)
     all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
@@ -333,81 +423,113 @@ def main():
             numa = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    mine, soa, refs, loci, bed_order, soa_full = make_batch(args, rank, world)
+    batches = make_batches(args, rank, world)
+    prm = vc_params(args)
+    NB = len(batches)
 
     # pinned host copies of every buffer that crosses the ABI
     def pin(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t.numpy()
-    for f in ("ref_id", "pos", "flag", "mapq", "nm", "l_seq", "seq_off", "qual_off", "cigar_off", "n_cigar", "umi", "frag_id", "seq",
-              "qual", "cigar"):
-        setattr(soa, f, pin(getattr(soa, f)))
-    for f in ("store_lo", "store_len"):
-        if getattr(soa, f) is not None:
+    for (_, soa, _, loci, _, _) in batches:
+        for f in ("ref_id", "pos", "flag", "mapq", "nm", "l_seq", "n_cigar", "umi", "frag_id", "seq", "qual", "cigar"):
             setattr(soa, f, pin(getattr(soa, f)))
-    for f in ("ref_id", "pos0", "ref_base"):
-        setattr(loci, f, pin(getattr(loci, f)))
-
-    caller = GpuCaller(vc_params(), device=local_rank)
+        if not soa.packed:
+            for f in ("seq_off", "qual_off", "cigar_off"):
+                setattr(soa, f, pin(getattr(soa, f)))
+        for f in ("store_lo", "store_len", "qual_lut"):
+            if getattr(soa, f) is not None:
+                setattr(soa, f, pin(getattr(soa, f)))
+        for f in ("ref_id", "pos0", "ref_base"):
+            setattr(loci, f, pin(getattr(loci, f)))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- kernel-only: batch resident in HBM
-    caller.upload(soa, loci)
+    # ---------------- kernel-only: every batch resident in HBM (one context per batch)
+    res_callers = []
+    for (_, soa, _, loci, _, _) in batches:
+        c = GpuCaller(prm, device=local_rank)
+        c.upload(soa, loci)
+        res_callers.append(c)
     for _ in range(args.warmup):
-        caller.run()
+        for c in res_callers:
+            c.run()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     t0 = time.perf_counter()
-    dev_ms, kp_ms, launches, tms = 0.0, 0.0, 0, None
+    dev_ms, launches = 0.0, 0
+    stage = {}
+    tms0 = None
     for _ in range(args.steps):
-        caller.run()
-        tms = caller.timings()
-        dev_ms += tms["ms_total_device"]; kp_ms += tms["ms_k_pileup"]; launches += tms["kernel_launches"]
+        for k, c in enumerate(res_callers):
+            c.run()
+            tm = c.timings()
+            dev_ms += tm["ms_total_device"]; launches += tm["kernel_launches"]
+            for key in ("ms_prep", "ms_sort", "ms_pileup", "ms_stats", "ms_k_pileup", "ms_k_gather", "ms_k_merge", "ms_read_sort", "ms_k_read_prep", "ms_event_sort"):
+                stage[key] = stage.get(key, 0.0) + tm[key]
+            if k == 0:
+                tms0 = tm
     barrier()
     wall_s = time.perf_counter() - t0
-    out = caller.download(LocusResults(loci.n, max(int(tms["n_dyn"]), 16), pinned=True))
-    n_dyn = out.n_dyn
+    events_rank = reads_rank = tile_events_rank = 0
+    prep_bytes = 0
+    outs = []
+    for c, (_, soa, _, loci, _, _) in zip(res_callers, batches):
+        tm = c.timings()
+        events_rank += int(tm["n_pileup_events"]); reads_rank += int(tm["n_reads"]); tile_events_rank += int(tm["n_tile_events"])
+        prep_bytes += int(tm["read_prep_bytes"])
+        outs.append(c.download(LocusResults(loci.n, max(int(tm["n_dyn"]), 16), pinned=True)))
+        c.close()
+    n_dyn = sum(o.n_dyn for o in outs)
 
-    # ---------------- end to end: host buffers in, host buffers out, every step
+    # ---------------- end to end: host buffers in, host buffers out, every step: smc_call_batch (pipelined upload, kernels,
+    # download) and the device HP / LowC pass over the candidates of the batch (smc_hp_lowcomp)
+    caller = GpuCaller(prm, device=local_rank)
+
+    def e2e_pass():
+        h2d = d2h = 0
+        last = None
+        for (_, soa, refs, loci, _, _), out in zip(batches, outs):
+            res = caller.call(soa, loci, out=out)
+            last = caller.timings()
+            h2d += int(last["bytes_h2d"]); d2h += int(last["bytes_d2h"])
+            device_hp_flags(caller, res, soa, loci, soa.chroms, refs, prm.hpLen)
+        return h2d, d2h, last
     for _ in range(min(args.warmup, 2)):
-        caller.call(soa, loci, out=out)
+        e2e_pass()
     barrier()
     t1 = time.perf_counter()
     for _ in range(args.steps):
-        caller.call(soa, loci, out=out)
-        e2e_tm = caller.timings()
+        h2d_b, d2h_b, e2e_tm = e2e_pass()
     barrier()
     e2e_s = time.perf_counter() - t1
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    caller.close()
 
-    def allmax(x):
+    def allred(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
+    allmax = lambda x: allred(x, dist.ReduceOp.MAX)
+    allsum = lambda x: allred(x, dist.ReduceOp.SUM)
 
-    def allsum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
+    loci_rank = float(sum(b[3].n for b in batches))
     dev_s_max = allmax(dev_ms / 1000.0)
     wall_s_max = allmax(wall_s)
     e2e_s_max = allmax(e2e_s)
-    loci_total = allsum(float(loci.n))
-    events_total = allsum(float(tms["n_pileup_events"]))
-    reads_total = allsum(float(soa.n))
-    # device time is what the CUDA events on the library's launch stream bracket for each step (it contains the
-    # few host round-trips a step needs); wall clock is reported beside it.
+    e2e_s_min = -allmax(-e2e_s)
+    loci_total = allsum(loci_rank)
+    events_total = allsum(float(events_rank))
+    reads_total = allsum(float(reads_rank))
+    # device time is what the CUDA events on the library's launch stream bracket for each batch run (it contains the host
+    # round-trips a run needs); wall clock is reported beside it.
     value = loci_total * args.steps / dev_s_max
     e2e_value = loci_total * args.steps / e2e_s_max
 
@@ -419,64 +541,79 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        algo_bytes = ALGO_BYTES_PER_EVENT * float(tms["n_pileup_events"])
-        kp_avg_s = (kp_ms / args.steps) / 1000.0
-        traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one k_pileup launch (ncu --set full, same batch)
+        nrun = args.steps * NB                                   # batch runs in the timed region of this rank
+        algo_bytes = ALGO_BYTES_PER_EVENT * float(events_rank) / NB          # per launch pair (one batch), averaged over the rank's batches
+        kp_avg_s = stage["ms_k_pileup"] / nrun / 1000.0
+        traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one k_gather + k_merge launch pair (ncu --set full, batch 0)
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "k_pileup_traffic.json")))
-            if int(tr["pileup_events"]) == int(tms["n_pileup_events"]):
+            if int(tr["pileup_events"]) == int(tms0["n_pileup_events"]):
                 traffic = int(tr["dram_bytes_read"]) + int(tr["dram_bytes_write"])
         except Exception:
             pass
         achieved = algo_bytes / kp_avg_s / 1e9 if kp_avg_s > 0 else 0.0
+        step_s = (dev_ms / nrun) / 1000.0
+        soa0 = batches[0][1]
+        gbs = lambda b, ms: (b / (ms / 1000.0) / 1e9) if ms > 0 else None
+        n_r, n_te = reads_rank / NB, tile_events_rank / NB
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1000.0 * dev_s_max / args.steps, "wall_ms_per_step": 1000.0 * wall_s_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-                "config": {"workload": "cfg2 synthetic N0030 194-gene panel (primers...coding.bed geometry), 3000 UMIs/locus, rpb 4, "
-                                       "2x150bp; one batch = %d seeded panel intervals per GPU" % args.intervals,
-                           "intervals_per_gpu": args.intervals, "loci_total": int(loci_total), "reads_total": int(reads_total),
-                           "pileup_events_per_step": int(events_total), "tile_events_per_step_rank0": int(tms["n_tile_events"]),
-                           "params": "mtDepth 3000 rpb 4.0 mtDrop 0 minBQ 20 minMQ 30",
-                           "l2": "inputs larger than L2 (%.0f MB resident per GPU), no flush needed" % (soa.nbytes() / 1e6),
-                           "reads": "whole reads" if soa.store_lo is None else "bases / qualities trimmed to each read's target window (store_lo / store_len), "
-                                    "%.0f of %d bases per read stored" % (float(soa.store_len.mean()), int(soa.l_seq.max())),
-                           "parallelism": "panel sharded by BED interval (balanced by estimated events), no collective",
-                           "host_affinity": ("GPU-local cores (%d) while pinning and uploading" % numa) if numa else "unbound"},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_tm["bytes_h2d"]),
-                        "d2h_bytes_per_step": int(e2e_tm["bytes_d2h"]), "ms_per_step": 1000.0 * e2e_s_max / args.steps,
-                        "ms_h2d": e2e_tm["ms_h2d"], "ms_device": e2e_tm["ms_total_device"], "ms_d2h": e2e_tm["ms_d2h"],
-                        "h2d_gbs": e2e_tm["bytes_h2d"] / e2e_tm["ms_h2d"] / 1e6 if e2e_tm["ms_h2d"] > 0 else None,
-                        "upload": "pipelined: scalars first, bases/qualities in %d chunks on a copy stream, %d pileup launch pairs as they "
-                                  "arrive (ms_device overlaps ms_h2d)" % (e2e_tm["pipe_chunks"], e2e_tm["pipe_launches"])},
+                "config": config_dict(args, world),
+                "workload_stats": {"loci_total": int(loci_total), "reads_total": int(reads_total), "pileup_events_per_step": int(events_total),
+                                   "tile_events_per_step_rank0": int(tile_events_rank), "resident_mb_rank0": sum(b[1].nbytes() for b in batches) / 1e6,
+                                   "reads": "whole reads" if soa0.store_lo is None else "bases / qualities trimmed to each read's target window (store_lo / store_len), "
+                                            "%.0f of %d bases per read stored" % (float(soa0.store_len.mean()), int(soa0.l_seq.max())) +
+                                            ("; compact upload: %d-bit scalars, %d-bit quality codes" % (soa0.scalar_bits, soa0.qual_bits)
+                                             if soa0.scalar_bits != 32 or soa0.qual_bits != 8 else ""),
+                                   "host_affinity": ("GPU-local cores (%d) while pinning and uploading" % numa) if numa else "unbound"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
+                        "ms_per_step": 1000.0 * e2e_s_max / args.steps, "ms_per_step_fastest_rank": 1000.0 * e2e_s_min / args.steps,
+                        "last_batch": {"ms_h2d": e2e_tm["ms_h2d"], "ms_device": e2e_tm["ms_total_device"], "ms_d2h": e2e_tm["ms_d2h"],
+                                       "h2d_gbs": e2e_tm["bytes_h2d"] / e2e_tm["ms_h2d"] / 1e6 if e2e_tm["ms_h2d"] > 0 else None},
+                        "what": "per step and GPU: %d x (smc_call_batch from pinned host buffers -- scalars first, bases / qualities in %d chunks on a copy "
+                                "stream, %d pileup launch pairs as they arrive -- + download + smc_hp_lowcomp over the batch's candidates)"
+                                % (NB, e2e_tm["pipe_chunks"], e2e_tm["pipe_launches"])},
                 "gpu_launches": int(launches),
-                "stage_ms_rank0": {k: tms[k] for k in ("ms_prep", "ms_sort", "ms_pileup", "ms_stats", "ms_k_pileup", "ms_k_gather", "ms_k_merge")},
-                "roofline": {"bound": "hbm", "kernel": "k_gather + k_merge (K3: tile pileup = event expansion + fragment merge, then calProb / PI / consensus)",
+                "stage_ms_per_batch_rank0": {k: v / nrun for k, v in stage.items()},
+                "roofline": {"bound": "hbm", "limited_by": "instruction issue (ncu, profiles/r02_k_gather_*_summary.txt: issue slots 70 % busy, DRAM 6 %): the tile "
+                                                          "design never materialises the per-(read, locus) events the 35 B / event figure charges for",
+                             "kernel": "k_gather + k_merge (K3: tile pileup = event expansion + fragment merge, then calProb / PI / consensus)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                              "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_event": ALGO_BYTES_PER_EVENT,
                              "ms_per_launch": 1000.0 * kp_avg_s, "traffic": traffic,
-                             "whole_step": {"what": "the same 35 B x pileup events over the WHOLE device step (read sort, prep, tile events, "
-                                                    "both pileup kernels, ALT / filters / Fisher) of rank 0",
-                                            "achieved": algo_bytes / ((dev_ms / args.steps) / 1000.0) / 1e9 if dev_ms > 0 else 0.0,
-                                            "frac": algo_bytes / ((dev_ms / args.steps) / 1000.0) / 1e9 / peak if dev_ms > 0 and peak else None},
-                             "events_per_s": float(tms["n_pileup_events"]) / kp_avg_s if kp_avg_s > 0 else 0.0},
-                "clocks": sampler.summary(), "n_dyn_alleles_rank0": int(n_dyn), "n_fisher_rank0": int(tms["n_fisher"])}
-    caller.close()
+                             "whole_step": {"what": "the same 35 B x pileup events over the WHOLE device run of a batch (read sort, prep, tile events, "
+                                                    "both pileup kernels, ALT / filters / Fisher), rank 0",
+                                            "achieved": algo_bytes / step_s / 1e9 if step_s > 0 else 0.0,
+                                            "frac": algo_bytes / step_s / 1e9 / peak if step_s > 0 and peak else None},
+                             "other_kernels": {
+                                 "k_read_prep": {"ms": stage["ms_k_read_prep"] / nrun, "algorithmic_bytes": prep_bytes / NB,
+                                                 "achieved_gbs": gbs(prep_bytes / NB, stage["ms_k_read_prep"] / nrun)},
+                                 "read_sort": {"ms": stage["ms_read_sort"] / nrun, "passes": int(tms0["read_sort_passes"]),
+                                               "algorithmic_bytes": 24.0 * n_r * int(tms0["read_sort_passes"]),
+                                               "achieved_gbs": gbs(24.0 * n_r * int(tms0["read_sort_passes"]), stage["ms_read_sort"] / nrun),
+                                               "what": "per pass 12 B read + 12 B written per read (u64 key + u32 index); histogram, scan and scatter kernels"},
+                                 "tile_event_sort": {"ms": stage["ms_event_sort"] / nrun, "algorithmic_bytes": 24.0 * n_te,
+                                                     "achieved_gbs": gbs(24.0 * n_te, stage["ms_event_sort"] / nrun)}},
+                             "events_per_s": float(events_rank) / NB / kp_avg_s if kp_avg_s > 0 else 0.0},
+                "clocks": sampler.summary(), "n_dyn_alleles_rank0": int(n_dyn), "n_fisher_rank0": int(tms0["n_fisher"])}
 
     if all_cpus is not None and numa:
         os.sched_setaffinity(0, all_cpus)          # the host-side legs below may use every core again
-    if rank == 0 and args.pipeline_intervals > 0:
+    ivs0, _, refs0, loci0, _, full0 = batches[0]
+    if rank == 0 and args.pipeline_intervals > 0 and full0 is not None:
         try:
-            line["pipeline"] = pipeline_leg(args, mine, soa_full, refs, local_rank)
+            line["pipeline"] = pipeline_leg(args, ivs0, full0, refs0, local_rank)
         except Exception as e:          # the extra leg must never cost the bench line
             line["pipeline"] = {"error": repr(e)}
 
-    if rank == 0 and not args.no_cpu_baseline:
-        n_sample = args.cpu_loci or 160 * cores          # ~10-15 s of host work
-        jobs, nrec = cpu_sample_setup(soa_full, refs, loci, n_sample)
+    if rank == 0 and not args.no_cpu_baseline and full0 is not None:
+        n_sample = args.cpu_loci or 24 * cores          # ~10-30 s of host work
+        jobs, nrec = cpu_sample_setup(full0, refs0, loci0, n_sample, args)
         v, dt, ev = cpu_run(jobs, cores)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
-                                "sample": "%d consecutive loci of the rank-0 batch (%d reads, %d pileup events), %s "
+                                "sample": "%d consecutive loci of the rank-0 batch 0 (%d reads, %d pileup events), %s "
                                           "with multiprocessing.Pool(%d), %.1f s" % (len(jobs), nrec, ev, CPU_WHAT[cpu_kind()], cores, dt),
                                 "archived_reference": "4.15 loci/s on 10 processes at DP~58k (example run log, 2017 hardware)"}
     if rank == 0:

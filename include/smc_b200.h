@@ -91,6 +91,15 @@ typedef struct smc_reads_soa {
      * and all other scalars keep describing the whole read.  On amplicon panels this halves the bytes that cross PCIe. */
     const int32_t  *store_lo;
     const int32_t  *store_len;
+    /* Optional compact encodings (ABI v3): fewer bytes over PCIe, expanded on the device in one pass.  All zero / NULL = off.
+     *   scalar_bits 16: l_seq, nm, store_lo and store_len point to uint16 arrays (every value < 65536) instead of int32.
+     *   qual_bits 4 or 2: qual[] holds one qual_bits-wide code per stored base, low bits first, every read starting on a byte
+     *     boundary ((stored bases * qual_bits + 7) / 8 bytes per read, qual_bytes = their sum); the phred value of code c is
+     *     qual_lut[c] (16 or 4 entries).  Sequencers that bin qualities (4 - 8 distinct values) fit 2 or 4 bits.  Requires the
+     *     packed layout (qual_off == NULL). */
+    int32_t         scalar_bits;
+    int32_t         qual_bits;
+    const uint8_t  *qual_lut;
 } smc_reads_soa;
 
 /* Target loci: unique, sorted by (ref_id, pos0).  At most 4 194 302 per batch. */
@@ -232,6 +241,12 @@ typedef struct smc_timings {
     int32_t dyn_capacity;  /* capacity of the dynamic-allele table in the last run (grows x4 on overflow) */
     int32_t pipe_chunks;   /* smc_call_batch: chunks the bases / qualities were uploaded in (1 = no overlap, small batch) */
     int32_t pipe_launches; /* smc_call_batch: (k_gather, k_merge) launch pairs issued as the chunks arrived */
+    /* ABI v3: CUDA-event times of the kernels north_star names besides the pileup pair, and what they move */
+    float   ms_read_sort;  /* the radix passes over the reads on (barcode slot, fragment id): histogram + scan + scatter per pass */
+    float   ms_k_read_prep;/* k_read_prep alone */
+    float   ms_event_sort; /* (read x tile) events: k_expand_scan + the radix pass by tile */
+    int32_t read_sort_passes;
+    int64_t read_prep_bytes; /* read SoA bytes in + the two per-read records out */
 } smc_timings;
 
 typedef struct smc_ctx smc_ctx;

@@ -11,7 +11,7 @@ from .soa import ReadsSoA
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmc_bamio.so")
 EXPORTS = ("smc_bam_set_trim", "smc_bam_open", "smc_bam_close", "smc_bam_last_error", "smc_bam_n_refs", "smc_bam_ref_name", "smc_bam_ref_length",
-           "smc_bam_decode", "smc_bam_dict_umi")
+           "smc_bam_decode", "smc_bam_dict_umi", "smc_rows_emit", "smc_rows_free")
 _vp = C.c_void_p
 
 
@@ -20,6 +20,20 @@ class smc_bam_reads(C.Structure):
                 ("seq_off", _vp), ("qual_off", _vp), ("cigar_off", _vp), ("n_cigar", _vp), ("umi", _vp), ("frag_id", _vp),
                 ("seq", _vp), ("seq_bytes", C.c_int64), ("qual", _vp), ("qual_bytes", C.c_int64), ("cigar", _vp),
                 ("n_cigar_words", C.c_int64), ("n_dict_umis", C.c_int64), ("store_lo", _vp), ("store_len", _vp)]
+
+
+class smc_rows_in(C.Structure):               # include/smc_rows.h
+    _fields_ = [("n_loci", C.c_int64), ("n_rows", C.c_int64), ("order", _vp), ("ref_id", _vp), ("pos0", _vp), ("ref_base", _vp),
+                ("n_chroms", C.c_int32), ("chroms", C.POINTER(C.c_char_p)), ("loc", _vp), ("cnt", _vp), ("pi", _vp), ("alt_allele", _vp),
+                ("second_allele", _vp), ("fl1", _vp), ("fl2", _vp), ("biallelic", _vp), ("n_dyn", C.c_int64), ("dyn_cnt", _vp), ("dyn_pi", _vp),
+                ("dyn_names", _vp), ("dyn_name_off", _vp), ("hp1", _vp), ("hp2", _vp), ("finalize", C.c_int32), ("threshold", C.c_int32),
+                ("n_trf", C.c_int64), ("trf_chrom", _vp), ("trf_lo", _vp), ("trf_hi", _vp), ("n_rm", C.c_int64), ("rm_chrom", _vp),
+                ("rm_lo", _vp), ("rm_hi", _vp), ("rm_tags", _vp), ("rm_tag_off", _vp), ("threads", C.c_int32), ("reserved0", C.c_int32)]
+
+
+class smc_rows_out(C.Structure):
+    _fields_ = [("all", _vp), ("all_off", _vp), ("cut", _vp), ("cut_off", _vp), ("vcf", _vp), ("vcf_off", _vp), ("bad_row", C.c_int64),
+                ("bad_status", C.c_uint32)]
 
 
 _lib = None
@@ -50,6 +64,10 @@ def load():
     lib.smc_bam_decode.restype = C.c_int
     lib.smc_bam_dict_umi.argtypes = [_vp, C.c_int64]
     lib.smc_bam_dict_umi.restype = C.c_char_p
+    lib.smc_rows_emit.argtypes = [C.POINTER(smc_rows_in), C.POINTER(smc_rows_out)]
+    lib.smc_rows_emit.restype = C.c_int
+    lib.smc_rows_free.argtypes = [C.POINTER(smc_rows_out)]
+    lib.smc_rows_free.restype = None
     _lib = lib
     return lib
 

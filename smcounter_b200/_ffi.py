@@ -35,7 +35,8 @@ class smc_reads_soa(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("ref_id", _vp), ("pos", _vp), ("flag", _vp), ("mapq", _vp), ("nm", _vp),
                 ("l_seq", _vp), ("seq_off", _vp), ("qual_off", _vp), ("cigar_off", _vp), ("n_cigar", _vp), ("umi", _vp),
                 ("frag_id", _vp), ("seq", _vp), ("seq_bytes", C.c_int64), ("qual", _vp), ("qual_bytes", C.c_int64),
-                ("cigar", _vp), ("n_cigar_words", C.c_int64), ("store_lo", _vp), ("store_len", _vp)]
+                ("cigar", _vp), ("n_cigar_words", C.c_int64), ("store_lo", _vp), ("store_len", _vp),
+                ("scalar_bits", C.c_int32), ("qual_bits", C.c_int32), ("qual_lut", _vp)]
 
 
 class smc_loci(C.Structure):
@@ -60,7 +61,9 @@ class smc_timings(C.Structure):
                 ("n_reads", C.c_int64), ("n_loci", C.c_int64), ("n_tile_events", C.c_int64), ("n_pileup_events", C.c_int64),
                 ("n_umi_groups", C.c_int64), ("n_dyn", C.c_int64), ("n_fisher", C.c_int64), ("bytes_h2d", C.c_int64),
                 ("bytes_d2h", C.c_int64), ("kernel_launches", C.c_int32), ("ms_k_gather", C.c_float), ("ms_k_merge", C.c_float), ("code_mult", C.c_int32),
-                ("dyn_capacity", C.c_int32), ("pipe_chunks", C.c_int32), ("pipe_launches", C.c_int32)]
+                ("dyn_capacity", C.c_int32), ("pipe_chunks", C.c_int32), ("pipe_launches", C.c_int32),
+                ("ms_read_sort", C.c_float), ("ms_k_read_prep", C.c_float), ("ms_event_sort", C.c_float), ("read_sort_passes", C.c_int32),
+                ("read_prep_bytes", C.c_int64)]
 
 
 class smc_hp_batch(C.Structure):

@@ -162,6 +162,10 @@ class GpuCaller:
         s.seq, s.seq_bytes, s.qual, s.qual_bytes = p(r.seq), r.seq.nbytes, p(r.qual), r.qual.nbytes
         s.cigar, s.n_cigar_words = p(r.cigar), r.cigar.shape[0]
         s.store_lo, s.store_len = p(getattr(r, "store_lo", None)), p(getattr(r, "store_len", None))
+        s.scalar_bits, s.qual_bits = int(getattr(r, "scalar_bits", 32)), int(getattr(r, "qual_bits", 8))
+        s.qual_lut = p(getattr(r, "qual_lut", None))
+        if s.qual_bits != 8 and not getattr(r, "packed", False):
+            raise ValueError("compact qualities need the packed layout")
         return s
 
     @staticmethod

@@ -64,7 +64,7 @@ struct smc_ctx {
     smc_params prm{};
     std::string err;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev[12]{};
+    cudaEvent_t ev[18]{};
     // pipelined upload of smc_call_batch: bases / qualities arrive in chunks on st_copy while st already computes
     cudaStream_t st_copy = nullptr;
     cudaEvent_t ev_scal = nullptr, ev_chunk[SMC_PIPE_MAX]{};
@@ -79,6 +79,9 @@ struct smc_ctx {
     DevBuf d_ref_id, d_pos, d_flag, d_mapq, d_nm, d_lseq, d_seq_off, d_qual_off, d_cig_off, d_ncig, d_umi, d_frag, d_seq, d_qual,
         d_cigar, d_store_lo, d_store_len;
     bool has_store = false;                     // reads carry a stored window (smc_reads_soa::store_lo / store_len)
+    int qual_bits = 8;                          // 4 / 2: compact qualities were uploaded (d_qual_packed) and are expanded into d_qual
+    DevBuf d_qual_packed, d_qual_poff, d_qual_lut, d_stage16;
+    const uint32_t* inv_ptr = nullptr;          // read index -> sorted position (lives in d_v0 or d_v1 after the read sort)
     DevBuf d_loci_ref, d_loci_pos, d_loci_base, d_loci_key;
     DevBuf d_keep_idx, d_keep_off, d_keep_umi;
     bool has_keep = false, uploaded = false, ran = false;
@@ -107,6 +110,7 @@ struct smc_ctx {
     uint32_t chunk = 128;       // tile events per warp unit (A/B on B200, whole step: 96 -> 4.42 ms, 128 -> 4.39, 160 -> 4.39, 256 -> 4.47, 384 -> 4.60)
     const uint32_t* ev_read_sorted = nullptr;   // tile-sorted event -> srank map (lives in d_ev0 or d_ev1)
     uint32_t n_tiles = 0; int64_t n_tile_events = 0;
+    int64_t ne_cap = 0;                         // capacity of the tile-event buffers (grow only)
 };
 
 static std::vector<DevBuf*> all_bufs(smc_ctx* ctx) {
@@ -123,7 +127,8 @@ static std::vector<DevBuf*> all_bufs(smc_ctx* ctx) {
                       &ctx->d_lk0, &ctx->d_lk1, &ctx->d_lv0, &ctx->d_lv1, &ctx->d_s_key, &ctx->d_s_cnt, &ctx->d_s_limb, &ctx->d_s_iskey,
                       &ctx->d_s_pi, &ctx->d_s_rep_read, &ctx->d_s_rep_qpos, &ctx->d_s_len, &ctx->d_dyn_first, &ctx->d_tasks,
                       &ctx->d_list_idx, &ctx->d_list_count, &ctx->d_list_off, &ctx->d_list_umi, &ctx->d_list_first,
-                      &ctx->d_hp_bases, &ctx->d_hp_meta, &ctx->d_hp_flags, &ctx->d_pipe_need, &ctx->d_umi_table};
+                      &ctx->d_hp_bases, &ctx->d_hp_meta, &ctx->d_hp_flags, &ctx->d_pipe_need, &ctx->d_umi_table,
+                      &ctx->d_qual_packed, &ctx->d_qual_poff, &ctx->d_qual_lut, &ctx->d_stage16};
 }
 
 #define CK(call)                                                                                         \
@@ -148,52 +153,149 @@ __global__ void k_loci_keys(const int32_t* ref_id, const int32_t* pos0, int64_t 
 // (the PI sums are fixed point, every other accumulation is an integer).
 #define UMI_EMPTY 0xffffffffffffffffull
 __global__ void k_umi_slots(const uint64_t* __restrict__ umi, const uint32_t* __restrict__ frag, int64_t n, unsigned long long* __restrict__ table,
-                            uint32_t mask, int frag_bits, uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+                            uint32_t mask, int frag_bits, uint64_t* __restrict__ key, uint32_t* __restrict__ val, unsigned long long* __restrict__ frag_or) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long u = umi[i];
-    uint32_t h = hash64to32(u) & mask;
-    for (;;) {
-        unsigned long long cur = table[h];
-        if (cur == UMI_EMPTY) cur = atomicCAS(&table[h], UMI_EMPTY, u);
-        if (cur == UMI_EMPTY || cur == u) break;
-        h = (h + 1) & mask;
+    uint32_t f = 0;
+    if (i < n) {
+        const unsigned long long u = umi[i];
+        f = frag[i];
+        uint32_t h = hash64to32(u) & mask;
+        for (;;) {
+            unsigned long long cur = table[h];
+            if (cur == UMI_EMPTY) cur = atomicCAS(&table[h], UMI_EMPTY, u);
+            if (cur == UMI_EMPTY || cur == u) break;
+            h = (h + 1) & mask;
+        }
+        key[i] = ((uint64_t)h << frag_bits) | (uint64_t)f;
+        val[i] = (uint32_t)i;
     }
-    key[i] = ((uint64_t)h << frag_bits) | (uint64_t)frag[i];
-    val[i] = (uint32_t)i;
+    // OR of all fragment ids (range check on the host: ids must be < 2^frag_bits)
+    f = __reduce_or_sync(FULL_MASK, f);
+    if ((threadIdx.x & 31) == 0 && (f >> frag_bits)) atomicOr(frag_or, (unsigned long long)f);
 }
-// reads in sorted order: a new barcode starts where the slot part of the key changes, a new fragment where the key changes
-__global__ void k_heads(const uint64_t* __restrict__ key_sorted, int frag_bits, int64_t n, uint32_t* uhead, uint32_t* fhead) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    bool uh = true, fh = true;
-    if (s > 0) {
-        const uint64_t a = key_sorted[s], b = key_sorted[s - 1];
-        uh = (a >> frag_bits) != (b >> frag_bits);
-        fh = a != b;
+// Reads in sorted order: a new barcode starts where the slot part of the key changes, a new fragment where the key changes.
+// ONE single-pass scan (decoupled look-back, smc_sort.cuh) over both head flags at once (two 31-bit counts in one word) turns
+// them into the dense barcode / fragment ranks, and writes the inverse permutation and the barcode of every rank.
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_rank_scan(const uint64_t* __restrict__ key_sorted, int frag_bits, int64_t n, const uint64_t* __restrict__ umi, const uint32_t* __restrict__ perm,
+            uint32_t* __restrict__ urank, uint32_t* __restrict__ frank, uint64_t* __restrict__ umi_of_urank, uint32_t* __restrict__ inv,
+            unsigned long long* desc, uint32_t* counter, uint32_t* n_umi_out) {
+    __shared__ unsigned long long warp_tot[SCAN_THREADS / 32];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    unsigned long long v[SCAN_ITEMS], tsum = 0;
+    uint64_t prev = (base > 0 && base <= n) ? key_sorted[base - 1] : 0ull;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = 0;
+        if (base + i < n) {
+            const uint64_t k = key_sorted[base + i];
+            const bool first = base + i == 0;
+            const unsigned long long uh = (first || (k >> frag_bits) != (prev >> frag_bits)) ? 1ull : 0ull;
+            const unsigned long long fh = (first || k != prev) ? 1ull : 0ull;
+            v[i] = (uh << 31) | fh;
+            prev = k;
+        }
+        tsum += v[i];
     }
-    uhead[s] = uh; fhead[s] = fh;
+    unsigned long long incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long t = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane_id() >= (uint32_t)d) incl += t;
+    }
+    const int w = threadIdx.x >> 5;
+    if (lane_id() == 31) warp_tot[w] = incl;
+    __syncthreads();
+    unsigned long long woff = 0, blk = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_THREADS / 32; ++i) {
+        unsigned long long t = warp_tot[i];
+        if (i < w) woff += t;
+        blk += t;
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long prefix = lb_resolve(desc, tile, blk);
+        s_prefix = prefix;
+        if (tile == gridDim.x - 1) *n_umi_out = (uint32_t)((prefix + blk) >> 31);
+    }
+    __syncthreads();
+    unsigned long long run = s_prefix + woff + incl - tsum;            // exclusive counts before the thread's first read
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) {
+            run += v[i];
+            const uint32_t ur = (uint32_t)(run >> 31) - 1u, fr = (uint32_t)(run & 0x7fffffffull) - 1u;
+            urank[base + i] = ur; frank[base + i] = fr;
+            const uint32_t r = perm[base + i];
+            inv[r] = (uint32_t)(base + i);                                // sorted position of read r (k_read_prep runs in BAM order)
+            if (v[i] >> 31) umi_of_urank[ur] = umi[r];
+        }
+    }
 }
-__global__ void k_ranks(const uint32_t* uhead, const uint32_t* fhead, const uint32_t* uex, const uint32_t* fex, const uint64_t* umi,
-                        const uint32_t* perm, int64_t n, uint32_t* urank, uint32_t* frank, uint64_t* umi_of_urank, uint32_t* inv) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    uint32_t ur = uex[s] + uhead[s] - 1, fr = fex[s] + fhead[s] - 1;
-    urank[s] = ur; frank[s] = fr;
-    const uint32_t r = perm[s];
-    inv[r] = (uint32_t)s;                                   // sorted position of read r (k_read_prep runs in BAM order)
-    if (uhead[s]) umi_of_urank[ur] = umi[r];
+// (read x 32-locus tile) events: the number of tiles each read covers is scanned (single pass, look-back) and the events are
+// written in the same kernel -- the only "event" that is ever materialised: one 12-byte row per (read x tile).  Events beyond
+// `cap` are not written; the total always is (the host grows the buffers and launches again).
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_expand_scan(const ReadRec* __restrict__ recs, int64_t n, uint64_t* __restrict__ ev_key, uint32_t* __restrict__ ev_val, uint32_t cap,
+              unsigned long long* desc, uint32_t* counter, uint32_t* total) {
+    __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+    __shared__ uint32_t s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t t0[SCAN_ITEMS], cnt[SCAN_ITEMS], tsum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        t0[i] = 0; cnt[i] = 0;
+        if (base + i < n) {
+            const int32_t lo = recs[base + i].lo, hi = recs[base + i].hi;
+            if (hi > lo) { t0[i] = (uint32_t)lo >> 5; cnt[i] = ((uint32_t)(hi - 1) >> 5) - t0[i] + 1u; }
+        }
+        tsum += cnt[i];
+    }
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane_id() >= (uint32_t)d) incl += t;
+    }
+    const int w = threadIdx.x >> 5;
+    if (lane_id() == 31) warp_tot[w] = incl;
+    __syncthreads();
+    uint32_t woff = 0, blk = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_THREADS / 32; ++i) {
+        uint32_t t = warp_tot[i];
+        if (i < w) woff += t;
+        blk += t;
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t prefix = (uint32_t)lb_resolve(desc, tile, blk);
+        s_prefix = prefix;
+        if (tile == gridDim.x - 1) *total = prefix + blk;
+    }
+    __syncthreads();
+    uint32_t o = s_prefix + woff + incl - tsum;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        for (uint32_t t = 0; t < cnt[i]; ++t, ++o)
+            if (o < cap) { ev_key[o] = t0[i] + t; ev_val[o] = (uint32_t)(base + i); }
 }
-__global__ void k_tile_offsets(const uint64_t* ev_key, int64_t ne, uint32_t n_tiles, uint32_t* tile_off) {
+// first event of every tile in the tile-sorted event list, and the number of warp units of the tile
+__global__ void k_tile_offsets(const uint64_t* ev_key, int64_t ne, uint32_t n_tiles, uint32_t chunk, uint32_t* tile_off, uint32_t* unit_cnt) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > n_tiles) return;
-    tile_off[t] = (uint32_t)lower_bound_u64(ev_key, ne, (uint64_t)t);
-}
-__global__ void k_unit_counts(const uint32_t* tile_off, uint32_t n_tiles, uint32_t chunk, uint32_t* cnt) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > n_tiles) return;
-    uint32_t n = t < n_tiles ? tile_off[t + 1] - tile_off[t] : 0;
-    cnt[t] = (n + chunk - 1) / chunk;
+    const uint32_t a = ne > 0 ? (uint32_t)lower_bound_u64(ev_key, ne, (uint64_t)t) : 0u;
+    tile_off[t] = a;
+    uint32_t nev = 0;
+    if (t < n_tiles) nev = (ne > 0 ? (uint32_t)lower_bound_u64(ev_key, ne, (uint64_t)t + 1ull) : 0u) - a;
+    unit_cnt[t] = (nev + chunk - 1) / chunk;
 }
 __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -381,12 +483,32 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
         CK((buf).ensure(b__ ? b__ : 16));                                                                        \
         if (b__) { CK(cudaMemcpyAsync((buf).p, (src), b__, cudaMemcpyHostToDevice, ctx->st)); bytes += b__; }     \
     } while (0)
+    if (R->scalar_bits != 0 && R->scalar_bits != 32 && R->scalar_bits != 16) { ctx->err = "smc_upload: scalar_bits must be 0, 16 or 32"; return SMC_E_ARG; }
+    if (R->qual_bits != 0 && R->qual_bits != 8 && R->qual_bits != 4 && R->qual_bits != 2) { ctx->err = "smc_upload: qual_bits must be 0, 2, 4 or 8"; return SMC_E_ARG; }
+    const bool s16 = R->scalar_bits == 16;
+    const int qbits = (R->qual_bits == 4 || R->qual_bits == 2) ? R->qual_bits : 8;
+    if (qbits != 8 && (R->qual_off || !R->qual_lut)) { ctx->err = "smc_upload: compact qualities need the packed layout (qual_off == NULL) and a qual_lut"; return SMC_E_ARG; }
     UP(ctx->d_ref_id, R->ref_id, n, int32_t); UP(ctx->d_pos, R->pos, n, int32_t); UP(ctx->d_flag, R->flag, n, uint16_t);
-    UP(ctx->d_mapq, R->mapq, n, uint8_t); UP(ctx->d_nm, R->nm, n, int32_t); UP(ctx->d_lseq, R->l_seq, n, int32_t);
+    UP(ctx->d_mapq, R->mapq, n, uint8_t);
     UP(ctx->d_ncig, R->n_cigar, n, uint16_t); UP(ctx->d_umi, R->umi, n, uint64_t); UP(ctx->d_frag, R->frag_id, n, uint32_t);
     if ((R->store_lo == nullptr) != (R->store_len == nullptr)) { ctx->err = "smc_upload: store_lo and store_len must be given together"; return SMC_E_ARG; }
     ctx->has_store = R->store_lo != nullptr;
-    if (ctx->has_store) { UP(ctx->d_store_lo, R->store_lo, n, int32_t); UP(ctx->d_store_len, R->store_len, n, int32_t); }
+    if (!s16) {
+        UP(ctx->d_nm, R->nm, n, int32_t); UP(ctx->d_lseq, R->l_seq, n, int32_t);
+        if (ctx->has_store) { UP(ctx->d_store_lo, R->store_lo, n, int32_t); UP(ctx->d_store_len, R->store_len, n, int32_t); }
+    } else {
+        // 16-bit scalars: four arrays staged back to back, widened on the device
+        const void* src16[4] = {R->nm, R->l_seq, R->store_lo, R->store_len};
+        DevBuf* dst32[4] = {&ctx->d_nm, &ctx->d_lseq, &ctx->d_store_lo, &ctx->d_store_len};
+        CK(ctx->d_stage16.ensure((size_t)(n ? n : 1) * 2 * 4));
+        for (int k = 0; k < (ctx->has_store ? 4 : 2); ++k) {
+            uint16_t* st16 = ctx->d_stage16.as<uint16_t>() + (size_t)k * n;
+            CK(dst32[k]->ensure((size_t)(n ? n : 1) * 4));
+            if (n) { CK(cudaMemcpyAsync(st16, src16[k], (size_t)n * 2, cudaMemcpyHostToDevice, ctx->st)); bytes += n * 2; }
+            LAUNCH(k_widen_u16, nblk(n, 256), 256, 0, st16, n, dst32[k]->as<int32_t>());
+        }
+    }
+    ctx->qual_bits = qbits;
     // offsets: uploaded, or -- NULL = payload packed in read order -- computed here from l_seq / n_cigar (saves 24 B per read of PCIe)
     ctx->packed_seq = !R->seq_off; ctx->packed_qual = !R->qual_off; ctx->packed_cigar = !R->cigar_off;
     {
@@ -399,12 +521,31 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
             CK(ctx->d_v0.ensure((size_t)(n ? n : 1) * 4));
             CK(ctx->d_scan.ensure((size_t)scan_scratch_words(n + 1) * 4 + 1024));
             LAUNCH(k_pack_len, nblk(n, 256), 256, 0, ctx->d_lseq.as<int32_t>(), ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr,
-                   ctx->d_ncig.as<uint16_t>(), n, kind, ctx->d_v0.as<uint32_t>());
+                   ctx->d_ncig.as<uint16_t>(), n, kind, 8, ctx->d_v0.as<uint32_t>());
             exclusive_scan_u32(ctx->d_v0.as<uint32_t>(), ctx->d_v0.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + SW_PACK_TOTALS + kind, ctx->st);
             LAUNCH(k_widen_u32, nblk(n, 256), 256, 0, ctx->d_v0.as<uint32_t>(), n, dev_off[kind]->as<int64_t>());
         }
+        if (qbits != 8) {          // byte offsets of the compact qualities inside the uploaded array
+            CK(ctx->d_qual_poff.ensure((size_t)(n ? n : 1) * 4));
+            CK(ctx->d_scan.ensure((size_t)scan_scratch_words(n + 1) * 4 + 1024));
+            LAUNCH(k_pack_len, nblk(n, 256), 256, 0, ctx->d_lseq.as<int32_t>(), ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr,
+                   ctx->d_ncig.as<uint16_t>(), n, 3, qbits, ctx->d_qual_poff.as<uint32_t>());
+            exclusive_scan_u32(ctx->d_qual_poff.as<uint32_t>(), ctx->d_qual_poff.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + SW_PACK_TOTALS + 3, ctx->st);
+            CK(ctx->d_qual_lut.ensure(16));
+            CK(cudaMemcpyAsync(ctx->d_qual_lut.p, R->qual_lut, qbits == 4 ? 16 : 4, cudaMemcpyHostToDevice, ctx->st));
+        }
     }
-    if (G == 1) { UP(ctx->d_seq, R->seq, R->seq_bytes, uint8_t); UP(ctx->d_qual, R->qual, R->qual_bytes, uint8_t); }
+    // expanded qualities never exceed two per byte of bases (a read stores (len + 1) / 2 bytes of bases)
+    const int64_t qual_dev_bytes = qbits == 8 ? R->qual_bytes : 2 * R->seq_bytes + 16;
+    DevBuf& qual_up = qbits == 8 ? ctx->d_qual : ctx->d_qual_packed;           // where the caller's qual[] bytes land
+    if (qbits != 8) CK(ctx->d_qual.ensure((size_t)qual_dev_bytes + 16));
+    if (G == 1) {
+        UP(ctx->d_seq, R->seq, R->seq_bytes, uint8_t); UP(qual_up, R->qual, R->qual_bytes, uint8_t);
+        if (qbits != 8)
+            LAUNCH(k_unpack_qual, nblk(n * 32, 256), 256, 0, n, ctx->d_qual_poff.as<uint32_t>(), ctx->d_qual_off.as<int64_t>(), ctx->d_lseq.as<int32_t>(),
+                   ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr, qbits, ctx->d_qual_lut.as<uint8_t>(), ctx->d_qual_packed.as<uint8_t>(),
+                   ctx->d_qual.as<uint8_t>(), nullptr, nullptr, 0u);
+    }
     UP(ctx->d_cigar, R->cigar, R->n_cigar_words, uint32_t);
     UP(ctx->d_loci_ref, Lc->ref_id, nl, int32_t); UP(ctx->d_loci_pos, Lc->pos0, nl, int32_t); UP(ctx->d_loci_base, Lc->ref_base, nl, uint8_t);
     ctx->has_keep = K && K->n_loci > 0;
@@ -435,7 +576,7 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
         }
     } else {
         // the chunks follow the scalars on the link; everything up to the first pileup launch needs the scalars only
-        CK(ctx->d_seq.ensure((size_t)R->seq_bytes + 16)); CK(ctx->d_qual.ensure((size_t)R->qual_bytes + 16));
+        CK(ctx->d_seq.ensure((size_t)R->seq_bytes + 16)); CK(qual_up.ensure((size_t)R->qual_bytes + 16));
         auto chunk_bytes = [&](int64_t total) { int64_t c = (total + G - 1) / G; c = (c + 255) & ~255ll; return (uint32_t)std::max<int64_t>(c, 256); };
         ctx->pipe_seq_chunk = chunk_bytes(R->seq_bytes); ctx->pipe_qual_chunk = chunk_bytes(R->qual_bytes);
         CK(cudaEventRecord(ctx->ev_scal, ctx->st));
@@ -444,7 +585,7 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
             const int64_t s0 = std::min<int64_t>(R->seq_bytes, (int64_t)c * ctx->pipe_seq_chunk), s1 = std::min<int64_t>(R->seq_bytes, (int64_t)(c + 1) * ctx->pipe_seq_chunk);
             const int64_t q0 = std::min<int64_t>(R->qual_bytes, (int64_t)c * ctx->pipe_qual_chunk), q1 = std::min<int64_t>(R->qual_bytes, (int64_t)(c + 1) * ctx->pipe_qual_chunk);
             if (s1 > s0) CK(cudaMemcpyAsync(ctx->d_seq.as<uint8_t>() + s0, R->seq + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, ctx->st_copy));
-            if (q1 > q0) CK(cudaMemcpyAsync(ctx->d_qual.as<uint8_t>() + q0, R->qual + q0, (size_t)(q1 - q0), cudaMemcpyHostToDevice, ctx->st_copy));
+            if (q1 > q0) CK(cudaMemcpyAsync(qual_up.as<uint8_t>() + q0, R->qual + q0, (size_t)(q1 - q0), cudaMemcpyHostToDevice, ctx->st_copy));
             CK(cudaEventRecord(ctx->ev_chunk[c], ctx->st_copy));
             bytes += (s1 - s0) + (q1 - q0);
         }
@@ -482,41 +623,41 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         CK(ctx->d_scan.ensure((size_t)std::max<int64_t>(radix_scan_words(n), scan_scratch_words(n + 1)) * 4 + 1024));
         uint64_t* k0 = ctx->d_k0.as<uint64_t>(); uint64_t* k1 = ctx->d_k1.as<uint64_t>();
         uint32_t* v0 = ctx->d_v0.as<uint32_t>(); uint32_t* v1 = ctx->d_v1.as<uint32_t>();
-        int slot_bits = 4;                                             // table of >= 2n slots
-        while ((1ll << slot_bits) < 2 * n) ++slot_bits;
+        // barcode table of >= 1.34 n slots (a batch has far fewer distinct barcodes than reads) and dense fragment ids < n:
+        // a 2.9 M read panel batch sorts on 22 + 22 = 44 key bits = four 11-bit passes
+        int slot_bits = 4;
+        while ((double)(1ll << slot_bits) < 1.34 * (double)n) ++slot_bits;
         int frag_bits = 1;                                             // frag_id < 2^frag_bits; checked below (the contract says
         while ((1ll << frag_bits) < n) ++frag_bits;                    // ids are dense, first-appearance numbers, hence < n_reads)
         frag_bits_used = frag_bits;
         CK(ctx->d_umi_table.ensure(((size_t)1 << slot_bits) * 8));
         CK(cudaMemsetAsync(ctx->d_umi_table.p, 0xff, ((size_t)1 << slot_bits) * 8, ctx->st));
-        {
-            unsigned long long init[2] = {0ull, ~0ull};
-            CK(cudaMemcpyAsync(small + SW_FRAG_OR, init, 16, cudaMemcpyHostToDevice, ctx->st));
-            LAUNCH(k_or_and_u32, std::min<unsigned>(nblk(n, 256), 1184u), 256, 0, ctx->d_frag.as<uint32_t>(), n, (unsigned long long*)(small + SW_FRAG_OR));
-        }
+        CK(cudaMemsetAsync(small + SW_FRAG_OR, 0, 8, ctx->st));
         LAUNCH(k_umi_slots, nblk(n, 256), 256, 0, ctx->d_umi.as<uint64_t>(), ctx->d_frag.as<uint32_t>(), n,
-               ctx->d_umi_table.as<unsigned long long>(), (uint32_t)((1u << slot_bits) - 1u), frag_bits, k0, v0);
+               ctx->d_umi_table.as<unsigned long long>(), (uint32_t)((1u << slot_bits) - 1u), frag_bits, k0, v0, (unsigned long long*)(small + SW_FRAG_OR));
+        CK(cudaEventRecord(ctx->ev[11], ctx->st));
         if (radix_sort_bits(k0, v0, k1, v1, n, 0, slot_bits + frag_bits, ctx->d_hist.as<uint32_t>(), ctx->d_scan.as<uint32_t>(), ctx->st)) {
             std::swap(k0, k1); std::swap(v0, v1);
         }
+        CK(cudaEventRecord(ctx->ev[12], ctx->st));
+        ctx->tm.read_sort_passes = (slot_bits + frag_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
         const uint32_t* perm = v0;
-        // dense barcode / fragment ranks
-        CK(ctx->d_flags32a.ensure((size_t)n * 4)); CK(ctx->d_flags32b.ensure((size_t)n * 4));
+        // dense barcode / fragment ranks, inverse permutation, barcode of every rank: one single-pass scan
         CK(ctx->d_urank.ensure((size_t)n * 4)); CK(ctx->d_frank.ensure((size_t)n * 4));
         CK(ctx->d_umi_of_urank.ensure((size_t)n * 8));
-        uint32_t* uhead = ctx->d_flags32a.as<uint32_t>(); uint32_t* fhead = ctx->d_flags32b.as<uint32_t>();
         uint32_t* uex = ctx->d_urank.as<uint32_t>(); uint32_t* fex = ctx->d_frank.as<uint32_t>();
-        LAUNCH(k_heads, nblk(n, 256), 256, 0, k0, frag_bits, n, uhead, fhead);
-        exclusive_scan_u32(uhead, uex, n, ctx->d_scan.as<uint32_t>(), small + SW_N_UMI, ctx->st);
-        exclusive_scan_u32(fhead, fex, n, ctx->d_scan.as<uint32_t>(), nullptr, ctx->st);
-        LAUNCH(k_ranks, nblk(n, 256), 256, 0, uhead, fhead, uex, fex, ctx->d_umi.as<uint64_t>(), perm, n, uex, fex,
-               ctx->d_umi_of_urank.as<uint64_t>(), v1);
+        {
+            const int64_t nbt = (n + SCAN_TILE - 1) / SCAN_TILE;
+            uint32_t* scr = ctx->d_scan.as<uint32_t>();
+            CK(cudaMemsetAsync(scr, 0, (size_t)(2 * nbt + 8) * 4, ctx->st));
+            LAUNCH(k_rank_scan, (unsigned)nbt, SCAN_THREADS, 0, k0, frag_bits, n, ctx->d_umi.as<uint64_t>(), perm, uex, fex,
+                   ctx->d_umi_of_urank.as<uint64_t>(), v1, reinterpret_cast<unsigned long long*>(scr + 2), scr, small + SW_N_UMI);
+        }
         // ---------------- K1: per-read records, computed in BAM order (coalesced inputs) and stored at their sorted position
         CK(ctx->d_recs.ensure((size_t)n * sizeof(ReadRec))); CK(ctx->d_grec.ensure((size_t)n * sizeof(GRec)));
-        CK(ctx->d_ntiles.ensure((size_t)(n + 1) * 4));
-        CK(ctx->d_evoff.ensure((size_t)(n + 1) * 4));
         CK(cudaMemsetAsync(small + SW_N_TILE_EVENTS, 0, 32, ctx->st));
         PrepArgs P{};
+        ctx->inv_ptr = v1;
         P.n_reads = n; P.inv = v1; P.urank = uex; P.frank = fex;
         P.ref_id = ctx->d_ref_id.as<int32_t>(); P.pos = ctx->d_pos.as<int32_t>(); P.flag = ctx->d_flag.as<uint16_t>();
         P.mapq = ctx->d_mapq.as<uint8_t>(); P.nm = ctx->d_nm.as<int32_t>(); P.l_seq = ctx->d_lseq.as<int32_t>();
@@ -525,19 +666,34 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         if (ctx->has_store) { P.store_lo = ctx->d_store_lo.as<int32_t>(); P.store_len = ctx->d_store_len.as<int32_t>(); }
         P.loci_key = ctx->d_loci_key.as<uint64_t>(); P.n_loci = nl;
         P.minMQ = ctx->prm.minMQ; P.primerDist = ctx->prm.primerDist; P.mismatchThr = ctx->prm.mismatchThr;
-        P.recs = ctx->d_recs.as<ReadRec>(); P.grec = ctx->d_grec.as<GRec>(); P.ntiles = ctx->d_ntiles.as<uint32_t>(); P.gflags = small + SW_GFLAGS;
+        P.recs = ctx->d_recs.as<ReadRec>(); P.grec = ctx->d_grec.as<GRec>(); P.gflags = small + SW_GFLAGS;
         if (ctx->pipe_n > 1) {
             CK(ctx->d_pipe_need.ensure((size_t)n));
             P.pipe_need = ctx->d_pipe_need.as<uint8_t>(); P.pipe_n = (uint32_t)ctx->pipe_n;
             P.pipe_seq_chunk = ctx->pipe_seq_chunk; P.pipe_qual_chunk = ctx->pipe_qual_chunk;
+            if (ctx->qual_bits != 8) { P.qual_poff = ctx->d_qual_poff.as<uint32_t>(); P.qual_bits = ctx->qual_bits; }
         }
+        CK(cudaEventRecord(ctx->ev[13], ctx->st));
         LAUNCH(k_read_prep, nblk(n, 256), 256, 0, P);
-        exclusive_scan_u32(ctx->d_ntiles.as<uint32_t>(), ctx->d_evoff.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + SW_N_TILE_EVENTS, ctx->st);
-        uint32_t h[2], tot[3];
+        CK(cudaEventRecord(ctx->ev[14], ctx->st));
+        ctx->tm.read_prep_bytes = n * (int64_t)(4 + 4 + 2 + 1 + 4 + 4 + 8 + 8 + 8 + 2 + (ctx->has_store ? 8 : 0) + 4 + sizeof(ReadRec) + sizeof(GRec)) + 4 * ctx->n_cigar_words;
+        // ---------------- K2b (first half): the (read x tile) events, scanned and written by one kernel into buffers sized from the
+        // previous batch (or 4 per read); the exact count comes back with the checks below
+        if (ctx->ne_cap < 4 * n + 4096) ctx->ne_cap = 4 * n + 4096;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            if (ctx->ne_cap > 0xfffffff0ll) ctx->ne_cap = 0xfffffff0ll;
+            CK(ctx->d_ek0.ensure((size_t)ctx->ne_cap * 8)); CK(ctx->d_ev0.ensure((size_t)ctx->ne_cap * 4));
+            const int64_t nbt = (n + SCAN_TILE - 1) / SCAN_TILE;
+            uint32_t* scr = ctx->d_scan.as<uint32_t>();
+            CK(cudaMemsetAsync(scr, 0, (size_t)(2 * nbt + 8) * 4, ctx->st));
+            LAUNCH(k_expand_scan, (unsigned)nbt, SCAN_THREADS, 0, ctx->d_recs.as<ReadRec>(), n, ctx->d_ek0.as<uint64_t>(), ctx->d_ev0.as<uint32_t>(),
+                   (uint32_t)ctx->ne_cap, reinterpret_cast<unsigned long long*>(scr + 2), scr, small + SW_N_TILE_EVENTS);
+            if (attempt == 1) break;
+        uint32_t h[2], tot[4];
         unsigned long long frag_or = 0;
         CK(cudaMemcpyAsync(&frag_or, small + SW_FRAG_OR, 8, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaMemcpyAsync(h, small + SW_N_TILE_EVENTS, 8, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaMemcpyAsync(tot, small + SW_PACK_TOTALS, 12, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(tot, small + SW_PACK_TOTALS, 16, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         if (h[1] & GF_BAD_READ) { ctx->err = "a read has l_seq or clip length > 65535 (unsupported)"; return SMC_E_LIMIT; }
         if (h[1] & GF_BAD_STORE) {
@@ -546,37 +702,37 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
             return SMC_E_ARG;
         }
         if (frag_or >> frag_bits_used) { ctx->err = "frag_id must be a dense id (< n_reads), numbered by first appearance"; return SMC_E_ARG; }
-        if ((ctx->packed_seq && (int64_t)tot[0] != ctx->seq_bytes) || (ctx->packed_qual && (int64_t)tot[1] != ctx->qual_bytes) ||
+        if ((ctx->packed_seq && (int64_t)tot[0] != ctx->seq_bytes) || (ctx->packed_qual && (int64_t)tot[ctx->qual_bits != 8 ? 3 : 1] != ctx->qual_bytes) ||
             (ctx->packed_cigar && (int64_t)tot[2] != ctx->n_cigar_words)) {
             ctx->err = "packed payload (NULL offsets): seq_bytes / qual_bytes / n_cigar_words do not match the sums of (len+1)/2, len, n_cigar (len = store_len or l_seq)";
             return SMC_E_ARG;
         }
-        NE = h[0];
+            NE = h[0];
+            if (NE <= ctx->ne_cap) break;
+            ctx->ne_cap = NE + NE / 8 + 4096;                 // first batch of this shape: grow and write the events again
+        }
     }
     CK(cudaEventRecord(ctx->ev[3], ctx->st));
+    CK(cudaEventRecord(ctx->ev[15], ctx->st));
     // ---------------- K2b: (read x tile) events, stable sort by tile
     const uint64_t* ev_key_sorted = nullptr; const uint32_t* ev_read_sorted = nullptr;
     CK(ctx->d_tile_off.ensure((size_t)(n_tiles + 2) * 4)); CK(ctx->d_unit_cnt.ensure((size_t)(n_tiles + 2) * 4));
     CK(ctx->d_unit_off.ensure((size_t)(n_tiles + 2) * 4));
     if (NE > 0) {
-        CK(ctx->d_ek0.ensure((size_t)NE * 8)); CK(ctx->d_ek1.ensure((size_t)NE * 8));
-        CK(ctx->d_ev0.ensure((size_t)NE * 4)); CK(ctx->d_ev1.ensure((size_t)NE * 4));
+        CK(ctx->d_ek1.ensure((size_t)NE * 8)); CK(ctx->d_ev1.ensure((size_t)NE * 4));
         CK(ctx->d_hist.ensure(radix_hist_words(NE) * 4 + 1024));
         CK(ctx->d_scan.ensure((size_t)std::max<int64_t>(radix_scan_words(NE), scan_scratch_words((int64_t)n_tiles + 2)) * 4 + 1024));
-        LAUNCH(k_expand, nblk(n, 256), 256, 0, ctx->d_recs.as<ReadRec>(), ctx->d_evoff.as<uint32_t>(), n, ctx->d_ek0.as<uint64_t>(),
-               ctx->d_ev0.as<uint32_t>());
         int tile_bits = 0;                                             // a panel batch of <= 2048 tiles is ONE pass
         while (((uint64_t)(n_tiles - 1) >> tile_bits) != 0) ++tile_bits;
         int res = radix_sort_bits(ctx->d_ek0.as<uint64_t>(), ctx->d_ev0.as<uint32_t>(), ctx->d_ek1.as<uint64_t>(), ctx->d_ev1.as<uint32_t>(),
                                   NE, 0, tile_bits, ctx->d_hist.as<uint32_t>(), ctx->d_scan.as<uint32_t>(), ctx->st);
         ev_key_sorted = res ? ctx->d_ek1.as<uint64_t>() : ctx->d_ek0.as<uint64_t>();
         ev_read_sorted = res ? ctx->d_ev1.as<uint32_t>() : ctx->d_ev0.as<uint32_t>();
-        LAUNCH(k_tile_offsets, nblk((int64_t)n_tiles + 1, 256), 256, 0, ev_key_sorted, NE, n_tiles, ctx->d_tile_off.as<uint32_t>());
     } else {
-        CK(cudaMemsetAsync(ctx->d_tile_off.p, 0, (size_t)(n_tiles + 2) * 4, ctx->st));
         CK(ctx->d_scan.ensure((size_t)scan_scratch_words((int64_t)n_tiles + 2) * 4 + 1024));
     }
-    LAUNCH(k_unit_counts, nblk((int64_t)n_tiles + 1, 256), 256, 0, ctx->d_tile_off.as<uint32_t>(), n_tiles, ctx->chunk,
+    CK(cudaEventRecord(ctx->ev[16], ctx->st));
+    LAUNCH(k_tile_offsets, nblk((int64_t)n_tiles + 1, 256), 256, 0, ev_key_sorted, NE, n_tiles, ctx->chunk, ctx->d_tile_off.as<uint32_t>(),
            ctx->d_unit_cnt.as<uint32_t>());
     exclusive_scan_u32(ctx->d_unit_cnt.as<uint32_t>(), ctx->d_unit_off.as<uint32_t>(), (int64_t)n_tiles + 1, ctx->d_scan.as<uint32_t>(),
                        nullptr, ctx->st);
@@ -709,6 +865,10 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
                 ctx->tm.pipe_launches = 0;
                 for (int c = 0; c < ctx->pipe_n; ++c) {
                     CK(cudaStreamWaitEvent(ctx->st, ctx->ev_chunk[c], 0));
+                    if (ctx->qual_bits != 8 && attempt == 0)        // the reads completed by this chunk: compact qualities -> bytes
+                        LAUNCH(k_unpack_qual, nblk(ctx->n_reads * 32, 256), 256, 0, ctx->n_reads, ctx->d_qual_poff.as<uint32_t>(), ctx->d_qual_off.as<int64_t>(),
+                               ctx->d_lseq.as<int32_t>(), ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr, ctx->qual_bits, ctx->d_qual_lut.as<uint8_t>(),
+                               ctx->d_qual_packed.as<uint8_t>(), ctx->d_qual.as<uint8_t>(), ctx->inv_ptr, ctx->d_pipe_need.as<uint8_t>(), (uint32_t)c);
                     const uint32_t u1 = ctx->pipe_end[c];
                     if (u1 <= u0) continue;
                     A.unit0 = B.unit0 = u0; A.n_units = B.n_units = u1;
@@ -802,6 +962,12 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
     cudaEventElapsedTime(&ctx->tm.ms_pileup, ctx->ev[4], ctx->ev[5]);
     cudaEventElapsedTime(&ctx->tm.ms_stats, ctx->ev[5], ctx->ev[6]);
     cudaEventElapsedTime(&ctx->tm.ms_total_device, ctx->ev[2], ctx->ev[6]);
+    ctx->tm.ms_read_sort = ctx->tm.ms_k_read_prep = ctx->tm.ms_event_sort = 0.f;
+    if (ctx->n_reads > 0 && nl > 0) {
+        cudaEventElapsedTime(&ctx->tm.ms_read_sort, ctx->ev[11], ctx->ev[12]);
+        cudaEventElapsedTime(&ctx->tm.ms_k_read_prep, ctx->ev[13], ctx->ev[14]);
+    }
+    cudaEventElapsedTime(&ctx->tm.ms_event_sort, ctx->ev[15], ctx->ev[16]);
     ctx->tm.ms_k_pileup = ctx->tm.ms_k_gather = ctx->tm.ms_k_merge = 0.f;
     if (NE > 0) {
         cudaEventElapsedTime(&ctx->tm.ms_k_pileup, ctx->ev[8], ctx->ev[10]);

@@ -51,8 +51,9 @@ struct PrepArgs {
     const uint16_t* n_cigar; const uint32_t* cigar;
     const uint64_t* loci_key; int64_t n_loci;
     int minMQ; int primerDist; double mismatchThr;
-    ReadRec* recs; GRec* grec; uint32_t* ntiles; uint32_t* gflags;
+    ReadRec* recs; GRec* grec; uint32_t* gflags;
     uint8_t* pipe_need; uint32_t pipe_n, pipe_seq_chunk, pipe_qual_chunk;     // pipelined upload only (else pipe_need == nullptr)
+    const uint32_t* qual_poff; int qual_bits;                                 // compact qualities: their byte offsets in the uploaded array
 };
 
 #define GF_DYN_FULL   1u
@@ -155,30 +156,16 @@ __global__ void __launch_bounds__(256) k_read_prep(PrepArgs A) {
         uint4* gd = reinterpret_cast<uint4*>(&A.grec[s]);
         gd[0] = gs[0]; gd[1] = gs[1];
     }
-    A.ntiles[s] = hi > lo ? (uint32_t)(((hi - 1) >> 5) - (lo >> 5) + 1) : 0u;
     if (A.pipe_need) {                                         // last chunk that carries a byte of this read
         uint32_t c = 0;
         if (slen > 0) {
             const uint32_t cs = (uint32_t)(((uint32_t)A.seq_off[r] + ((uint32_t)slen + 1u) / 2u - 1u) / A.pipe_seq_chunk);
-            const uint32_t cq = (uint32_t)(((uint32_t)A.qual_off[r] + (uint32_t)slen - 1u) / A.pipe_qual_chunk);
+            const uint32_t cq = A.qual_poff ? (uint32_t)((A.qual_poff[r] + ((uint32_t)slen * (uint32_t)A.qual_bits + 7u) / 8u - 1u) / A.pipe_qual_chunk)
+                                            : (uint32_t)(((uint32_t)A.qual_off[r] + (uint32_t)slen - 1u) / A.pipe_qual_chunk);
             c = min(max(cs, cq), A.pipe_n - 1u);
         }
         A.pipe_need[s] = (uint8_t)c;
     }
-}
-
-// Expansion of reads into (tile, read) events -- the only "event" that is ever materialised: one 12-byte row per
-// (read x 32-locus tile) instead of one per (read x locus).
-__global__ void __launch_bounds__(256)
-k_expand(const ReadRec* __restrict__ recs, const uint32_t* __restrict__ ev_off, int64_t n_reads,
-         uint64_t* __restrict__ ev_key, uint32_t* __restrict__ ev_val) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_reads) return;
-    int32_t lo = recs[s].lo, hi = recs[s].hi;
-    if (hi <= lo) return;
-    uint32_t t0 = (uint32_t)lo >> 5, t1 = (uint32_t)(hi - 1) >> 5;
-    uint32_t o = ev_off[s];
-    for (uint32_t t = t0; t <= t1; ++t, ++o) { ev_key[o] = t; ev_val[o] = (uint32_t)s; }
 }
 
 // Per tile event (tile-sorted), derived by k_gather while it stages a batch: bit 0 a new fragment starts here, bit 1 a new
@@ -227,14 +214,39 @@ k_pipe_unit_need(const uint32_t* __restrict__ unit_eb, const uint32_t* __restric
     for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(FULL_MASK, m, d));
     if (lane == 0 && eb < ee && m > 0) atomicMin(&first_blocked[m - 1], u);
 }
-// Packed payloads (smc_reads_soa offsets passed as NULL): per-read byte / word counts, scanned into the offsets on the device
+// Packed payloads (smc_reads_soa offsets passed as NULL): per-read byte / word counts, scanned into the offsets on the device.
+// kind 0 bytes of bases, 1 bytes of (expanded) qualities, 2 CIGAR words, 3 bytes of compact qualities (qbits per base)
 __global__ void __launch_bounds__(256)
 k_pack_len(const int32_t* __restrict__ l_seq, const int32_t* __restrict__ store_len, const uint16_t* __restrict__ n_cigar, int64_t n, int kind,
-           uint32_t* __restrict__ out) {
+           int qbits, uint32_t* __restrict__ out) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const uint32_t l = kind == 2 ? 0u : (uint32_t)max(store_len ? store_len[r] : l_seq[r], 0);
-    out[r] = kind == 0 ? (l + 1u) / 2u : kind == 1 ? l : (uint32_t)n_cigar[r];
+    out[r] = kind == 0 ? (l + 1u) / 2u : kind == 1 ? l : kind == 2 ? (uint32_t)n_cigar[r] : (l * (uint32_t)qbits + 7u) / 8u;
+}
+// compact scalars (smc_reads_soa::scalar_bits == 16)
+__global__ void __launch_bounds__(256) k_widen_u16(const uint16_t* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) out[r] = (int32_t)in[r];
+}
+// compact qualities (smc_reads_soa::qual_bits 4 / 2) -> one phred byte per stored base, one warp per read.  `need` / `inv` /
+// `chunk` (pipelined upload): only the reads whose last byte arrives with chunk `chunk`.
+__global__ void __launch_bounds__(256)
+k_unpack_qual(int64_t n, const uint32_t* __restrict__ poff, const int64_t* __restrict__ uoff, const int32_t* __restrict__ l_seq,
+              const int32_t* __restrict__ store_len, int qbits, const uint8_t* __restrict__ lut16, const uint8_t* __restrict__ packed,
+              uint8_t* __restrict__ out, const uint32_t* __restrict__ inv, const uint8_t* __restrict__ need, uint32_t chunk) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    if (need && need[inv[r]] != chunk) return;
+    const int len = max(store_len ? store_len[r] : l_seq[r], 0);
+    const uint8_t* src = packed + poff[r];
+    uint8_t* dst = out + uoff[r];
+    const uint32_t mask = (1u << qbits) - 1u;
+    for (int i = lane; i < len; i += 32) {
+        const uint32_t bit = (uint32_t)i * (uint32_t)qbits;
+        dst[i] = __ldg(&lut16[(__ldg(&src[bit >> 3]) >> (bit & 7u)) & mask]);
+    }
 }
 __global__ void __launch_bounds__(256) k_widen_u32(const uint32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -50,20 +50,79 @@ k_scan_tile(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* sums) {   //
     if (threadIdx.x == 0 && sums) sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_add(uint32_t* __restrict__ out, int64_t n, const uint32_t* __restrict__ offs) {
-    uint32_t o = offs[blockIdx.x];
-    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i)
-        if (base + i < n) out[base + i] += o;
+// Single-pass scan (decoupled look-back): tiles take their number from an atomic counter (so a tile only ever waits for tiles
+// that already run), publish their aggregate, and thread 0 walks back over the descriptors of the preceding tiles until it
+// meets an inclusive prefix.  One launch instead of three (tile scan, scan of the tile sums, add).
+// Descriptor: bits 62-63 status (0 empty, 1 aggregate, 2 inclusive prefix), low bits the value.
+#define LB_AGG  (1ull << 62)
+#define LB_INCL (2ull << 62)
+#define LB_VAL  ((1ull << 62) - 1ull)
+
+__device__ __forceinline__ unsigned long long lb_resolve(unsigned long long* desc, uint32_t tile, unsigned long long agg) {
+    // called by one thread of the tile; returns the exclusive prefix of the tile and publishes its inclusive prefix
+    unsigned long long prefix = 0;
+    if (tile > 0) {
+        atomicExch(&desc[tile], LB_AGG | agg);
+        for (int64_t t = (int64_t)tile - 1;; --t) {
+            unsigned long long d;
+            do { d = *reinterpret_cast<volatile unsigned long long*>(&desc[t]); } while ((d >> 62) == 0ull);
+            prefix += d & LB_VAL;
+            if ((d >> 62) == 2ull) break;
+        }
+    }
+    atomicExch(&desc[tile], LB_INCL | (prefix + agg));
+    return prefix;
 }
 
-// scratch must hold at least scan_scratch_words(n) uint32.  If total != nullptr the grand total is stored there.
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_lb(const uint32_t* in, uint32_t* out, int64_t n, unsigned long long* desc, uint32_t* counter, uint32_t* total) {   // in == out allowed
+    __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+    __shared__ uint32_t s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0u;
+        tsum += v[i];
+    }
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane_id() >= (uint32_t)d) incl += t;
+    }
+    const int w = threadIdx.x >> 5;
+    if (lane_id() == 31) warp_tot[w] = incl;
+    __syncthreads();
+    uint32_t woff = 0, blk = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_THREADS / 32; ++i) {
+        uint32_t t = warp_tot[i];
+        if (i < w) woff += t;
+        blk += t;
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t prefix = (uint32_t)lb_resolve(desc, tile, blk);
+        s_prefix = prefix;
+        if (total && tile == gridDim.x - 1) *total = prefix + blk;
+    }
+    __syncthreads();
+    uint32_t run = s_prefix + woff + incl - tsum;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+    }
+}
+
+// scratch must hold at least scan_scratch_words(n) uint32 (look-back descriptors + the tile counter).  If total != nullptr the
+// grand total is stored there.
 static inline int64_t scan_scratch_words(int64_t n) {
-    int64_t w = 0;
-    while (n > 1) { n = (n + SCAN_TILE - 1) / SCAN_TILE; w += n + 1; }
-    return w + 2;
+    return 2 * ((n + SCAN_TILE - 1) / SCAN_TILE) + 8;
 }
 
 static thread_local int g_launches = 0;   // kernel launch counter of the calling host thread (one thread drives one context)
@@ -74,17 +133,14 @@ static void exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uin
         if (total) cudaMemsetAsync(total, 0, sizeof(uint32_t), st);
         return;
     }
-    int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    const int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (nb == 1) {
         k_scan_tile<<<1, SCAN_THREADS, 0, st>>>(in, out, n, total);
         ++g_launches;
         return;
     }
-    uint32_t* sums = scratch;
-    k_scan_tile<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, sums);
-    ++g_launches;
-    exclusive_scan_u32(sums, sums, nb, scratch + nb + 1, total, st);
-    k_scan_add<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(out, n, sums);
+    cudaMemsetAsync(scratch, 0, (size_t)(2 * nb + 8) * 4, st);          // [0, 1] tile counter, descriptors from word 2 (8-byte aligned)
+    k_scan_lb<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, reinterpret_cast<unsigned long long*>(scratch + 2), scratch, total);
     ++g_launches;
 }
 

@@ -338,3 +338,120 @@ def format_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, workers
                         c_strong[0][i], c_strong[1][i], c_strong[2][i], c_strong[3][i],
                         pi_s[0][i], pi_s[1][i], pi_s[2][i], pi_s[3][i], fltr))
     return rows
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# native output stage (libsmc_bamio.so: csrc/smc_rows.cpp, include/smc_rows.h)
+# ----------------------------------------------------------------------------------------------------------------------
+class EmittedRows:
+    """Text produced by smc_rows_emit for one batch: ``all`` (45-column rows) and, when finalised, ``cut`` / ``vcf`` (the rows of the
+    called variants), each as bytes plus per-row offsets so that rows can be regrouped by BED interval without re-parsing."""
+
+    def __init__(self, all_b, all_off, cut_b, cut_off, vcf_b, vcf_off):
+        self.all, self.all_off, self.cut, self.cut_off, self.vcf, self.vcf_off = all_b, all_off, cut_b, cut_off, vcf_b, vcf_off
+
+    def rows(self):
+        """The rows as a list of str (without the trailing newline) -- the form format_rows() returns."""
+        s = self.all.decode()
+        return s.split("\n")[:-1] if s else []
+
+    def slices(self, r0, r1):
+        """(all, cut, vcf) bytes of rows [r0, r1)."""
+        return (self.all[self.all_off[r0]:self.all_off[r1]], self.cut[self.cut_off[r0]:self.cut_off[r1]], self.vcf[self.vcf_off[r0]:self.vcf_off[r1]])
+
+
+def _needed_dyn_names(res, n, namer):
+    """Names of the dynamic-allele rows that are an ALT candidate of some locus (the only ones a row can mention)."""
+    need = set()
+    a1 = res.alt_allele[:n]
+    need.update(int(a) - SMC_NFIXED for a in a1[a1 >= SMC_NFIXED].tolist())
+    bi = res.biallelic[:n] != 0
+    a2 = res.second_allele[:n][bi]
+    need.update(int(a) - SMC_NFIXED for a in a2[a2 >= SMC_NFIXED].tolist())
+    nd = int(res.n_dyn)
+    off = np.zeros(nd + 1, dtype=np.int64)
+    parts = []
+    for j in sorted(need):
+        s = namer.name(SMC_NFIXED + j).encode()
+        parts.append((j, s))
+    lens = np.zeros(nd, dtype=np.int64)
+    for j, s in parts:
+        lens[j] = len(s)
+    off[1:] = np.cumsum(lens)
+    return b"".join(s for _, s in parts), off
+
+
+def emit_rows(res, reads, loci, chroms, refs, hpLen, locus_order=None, hp_flags=None, finalize=False, threshold=0, trf=None, rm=None,
+              threads=0) -> EmittedRows:
+    """The rows of a batch through the native output stage: what format_rows() produces (finalize=False), or -- finalize=True --
+    what format_rows() + repeats.apply_repeat_filters() + writers.called_lines() produce, in one threaded pass over the device
+    results.  ``trf`` / ``rm``: the dicts of repeats.build_repeat_regions()."""
+    import ctypes as C
+    from . import _bamio
+    lib = _bamio.load()
+    n = loci.n
+    namer = AlleleNamer(res, reads, loci, chroms, refs)
+    names, name_off = _needed_dyn_names(res, n, namer)
+    hp1 = np.zeros(max(n, 1), np.uint8); hp2 = np.zeros(max(n, 1), np.uint8)
+    for (i, cand), (hp, lc) in (hp_flags or {}).items():
+        (hp1 if cand == 0 else hp2)[i] = 128 | (1 if hp else 0) | (2 if lc else 0)
+    order = None if locus_order is None else np.ascontiguousarray(locus_order, dtype=np.int64)
+    cidx = {c: k for k, c in enumerate(chroms)}
+
+    def flat(regions):
+        ch, lo, hi, tags = [], [], [], []
+        for c in chroms:
+            for (a, b, t) in (regions or {}).get(c, ()):
+                ch.append(cidx[c]); lo.append(a); hi.append(b); tags.append(t.encode())
+        toff = np.zeros(len(tags) + 1, dtype=np.int64)
+        if tags:
+            toff[1:] = np.cumsum([len(t) for t in tags])
+        return np.asarray(ch, np.int32), np.asarray(lo, np.int64), np.asarray(hi, np.int64), b"".join(tags), toff
+
+    t_ch, t_lo, t_hi, _, _ = flat(trf)
+    r_ch, r_lo, r_hi, r_tags, r_toff = flat(rm)
+    a = smc = _bamio.smc_rows_in()
+    p = lambda x: None if x is None else x.ctypes.data
+    keep = [np.ascontiguousarray(x) for x in (loci.ref_id, loci.pos0, loci.ref_base, res.loc, res.cnt, res.pi, res.alt_allele, res.second_allele,
+                                              res.fl1, res.fl2, res.biallelic, res.dyn_cnt, res.dyn_pi)]
+    # the 2-D result arrays are allocated for max(n, 1) loci: the stride is their second dimension
+    stride = res.loc.shape[1]
+    a.n_loci, a.n_rows, a.order = stride, (n if order is None else len(order)), p(order)
+    a.ref_id, a.pos0, a.ref_base = p(keep[0]), p(keep[1]), p(keep[2])
+    carr = (C.c_char_p * max(len(chroms), 1))(*[c.encode() for c in chroms])
+    a.n_chroms, a.chroms = len(chroms), carr
+    a.loc, a.cnt, a.pi, a.alt_allele, a.second_allele, a.fl1, a.fl2, a.biallelic = (p(k) for k in keep[3:11])
+    a.n_dyn, a.dyn_cnt, a.dyn_pi = int(res.n_dyn), p(keep[11]), p(keep[12])
+    names_buf = C.create_string_buffer(names, len(names) + 1)
+    a.dyn_names, a.dyn_name_off = C.addressof(names_buf), p(name_off)
+    a.hp1, a.hp2 = p(hp1), p(hp2)
+    a.finalize, a.threshold = int(bool(finalize)), int(threshold)
+    a.n_trf, a.trf_chrom, a.trf_lo, a.trf_hi = len(t_ch), p(t_ch), p(t_lo), p(t_hi)
+    tags_buf = C.create_string_buffer(r_tags, len(r_tags) + 1)
+    a.n_rm, a.rm_chrom, a.rm_lo, a.rm_hi, a.rm_tags, a.rm_tag_off = len(r_ch), p(r_ch), p(r_lo), p(r_hi), C.addressof(tags_buf), p(r_toff)
+    a.threads = int(threads)
+    if loci.ref_id.shape[0] < stride and n > 0:
+        raise ValueError("emit_rows: loci arrays shorter than the result stride")
+    out = _bamio.smc_rows_out()
+    rc = lib.smc_rows_emit(C.byref(a), C.byref(out))
+    if rc != 0:
+        k = int(out.bad_row)
+        i = int(k if order is None or k < 0 else order[k])
+        where = (chroms[int(loci.ref_id[i])], "%d" % (int(loci.pos0[i]) + 1)) if 0 <= i < n else "?"
+        if rc == -2:
+            raise RuntimeError("Exception thrown in vc() at location: %s (device status 0x%x)" % (where, int(out.bad_status)))
+        if rc == -3:
+            raise RuntimeError("format_rows: no device HP/LowC flags for a candidate that needs them (pass hp_flags=device_hp_flags(...))")
+        raise RuntimeError("smc_rows_emit failed (%d) at %s" % (rc, where))
+    try:
+        nr = a.n_rows
+
+        def take(buf, off):
+            o = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_int64)), shape=(nr + 1,)).copy()
+            return C.string_at(buf, int(o[-1])), o
+        all_b, all_off = take(out.all, out.all_off)
+        cut_b, cut_off = take(out.cut, out.cut_off)
+        vcf_b, vcf_off = take(out.vcf, out.vcf_off)
+    finally:
+        lib.smc_rows_free(C.byref(out))
+    return EmittedRows(all_b, all_off, cut_b, cut_off, vcf_b, vcf_off)

@@ -29,8 +29,8 @@ from .bam import read_bam
 from .caller import GpuCaller, UmiKeep, VcParams
 from .downsample import draw_keep_masks
 from .fasta import FastaFile
-from .rows import device_hp_flags, format_rows
-from .shard import ReadLocator, interleave_rows, plan_batches, plan_shards
+from .rows import device_hp_flags, emit_rows, headerAll, headerVariants
+from .shard import ReadLocator, plan_batches, plan_shards
 from .targets import build_loci, intervals_from_bed_lines
 
 parser = None
@@ -65,36 +65,27 @@ def argParseInit():
     parser.add_argument('--fisherLegacy', type=int, default=0, help='1: two-sided Fisher p-values as scipy <= 1.6 computed them (epsilon = 1 - 1e-4, the scipy of the 2017 reference run); 0 (default): scipy >= 1.7')
 
 
-def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None, stage_times: dict | None = None,
-              batch_limits: dict | None = None):
-    """The drop-in for the reference's per-locus fan-out: rows of vc() (45 tab-joined fields each, FILTER still in
-    accumulator form) for every position of ``intervals`` in BED order.
-
-    ``reads``: ReadsSoA of the BAM; ``refs``: object with fetch()/get_reference_length().  One host thread per GPU
-    (ctypes drops the GIL); a failing shard fails the run like smCounter.py:690-694.  ``stage_times`` (optional dict)
-    receives the wall-clock ms of the device calls and of the row formatting, summed over shards.  A shard larger than
-    the library's per-batch limits is streamed through its GPU in consecutive batches (``batch_limits``: keyword overrides
-    of shard.plan_batches, for tests)."""
+def _run_shards(reads, intervals, refs, prm: VcParams, gpus, devices, stage_times, batch_limits, emit_kw):
+    """Shards the BED intervals over the GPUs, streams every shard through its GPU in batches, and turns each batch's device
+    results into text with the native output stage (rows.emit_rows).  Returns {interval index: (EmittedRows, first row, end row)}."""
     import time
     chroms = reads.chroms
     devices = list(devices) if devices is not None else list(range(max(1, gpus)))
     plan = plan_shards(reads, intervals, chroms, len(devices))
-    shard_rows = [None] * len(plan)
+    per_interval = {}
     errors = [None] * len(plan)
-
     locator = ReadLocator(reads, chroms)
+    lock = threading.Lock()
 
     def work(g):
         try:
             idxs = plan[g][0]
             if not idxs:
-                shard_rows[g] = []
                 return
             # a shard goes through its GPU as a stream of batches under the library's per-batch limits
             batches = plan_batches(locator, intervals, idxs, **(batch_limits or {}))
             tc = time.perf_counter()
             caller = GpuCaller(prm, devices[g])
-            rows = []
             try:
                 for b in batches:
                     ivs = [intervals[k] for k in b]
@@ -114,7 +105,13 @@ def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None
                         res = caller.call(sub, loci, keep)
                     hp = device_hp_flags(caller, res, sub, loci, chroms, refs, prm.hpLen)   # isHPorLowComp, smCounter.py:122-177
                     t1 = time.perf_counter()
-                    rows.extend(format_rows(res, sub, loci, chroms, refs, prm.hpLen, bed_order, hp_flags=hp))
+                    em = emit_rows(res, sub, loci, chroms, refs, prm.hpLen, bed_order, hp_flags=hp, **emit_kw)
+                    o = 0
+                    with lock:
+                        for k in b:
+                            nrow = max(0, intervals[k][2] - intervals[k][1])
+                            per_interval[k] = (em, o, o + nrow)
+                            o += nrow
                     if stage_times is not None:
                         stage_times["ms_gpu_call"] = stage_times.get("ms_gpu_call", 0.0) + 1e3 * (t1 - t0)
                         stage_times["ms_format_rows"] = stage_times.get("ms_format_rows", 0.0) + 1e3 * (time.perf_counter() - t1)
@@ -122,7 +119,6 @@ def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None
                     tc = time.perf_counter()
             finally:
                 caller.close()
-            shard_rows[g] = rows
         except BaseException as e:          # noqa: BLE001 -- re-raised on the main thread
             errors[g] = e
 
@@ -137,7 +133,45 @@ def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None
     for e in errors:
         if e is not None:
             raise e
-    return interleave_rows(plan, intervals, shard_rows)
+    return per_interval
+
+
+def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None, stage_times: dict | None = None,
+              batch_limits: dict | None = None):
+    """The drop-in for the reference's per-locus fan-out: rows of vc() (45 tab-joined fields each, FILTER still in
+    accumulator form) for every position of ``intervals`` in BED order.
+
+    ``reads``: ReadsSoA of the BAM; ``refs``: object with fetch()/get_reference_length().  One host thread per GPU
+    (ctypes drops the GIL); a failing shard fails the run like smCounter.py:690-694.  ``stage_times`` (optional dict)
+    receives the wall-clock ms of the device calls and of the row formatting, summed over shards.  A shard larger than
+    the library's per-batch limits is streamed through its GPU in consecutive batches (``batch_limits``: keyword overrides
+    of shard.plan_batches, for tests)."""
+    per_interval = _run_shards(reads, intervals, refs, prm, gpus, devices, stage_times, batch_limits, {})
+    cache, out = {}, []
+    for k in range(len(intervals)):                    # BED order, like the reference's in-order p.get() (smCounter.py:685)
+        if k in per_interval:
+            em, r0, r1 = per_interval[k]
+            rows = cache.get(id(em))
+            if rows is None:
+                rows = cache[id(em)] = em.rows()
+            out.extend(rows[r0:r1])
+    return out
+
+
+def call_loci_text(reads, intervals, refs, prm: VcParams, threshold: int, trf=None, rm=None, gpus: int = 1, devices=None,
+                   stage_times: dict | None = None, batch_limits: dict | None = None):
+    """call_loci() + main()'s post-processing (repeat filters smCounter.py:751-785, PASS / strip, the called-variant rows of
+    :832-891) in the native output stage: returns the bodies of the three output files (bytes, without their headers) in BED
+    order: (all_txt, cut_txt, cut_vcf)."""
+    per_interval = _run_shards(reads, intervals, refs, prm, gpus, devices, stage_times, batch_limits,
+                               dict(finalize=True, threshold=threshold, trf=trf, rm=rm))
+    parts = ([], [], [])
+    for k in range(len(intervals)):
+        if k in per_interval:
+            em, r0, r1 = per_interval[k]
+            for dst, piece in zip(parts, em.slices(r0, r1)):
+                dst.append(piece)
+    return tuple(b"".join(p) for p in parts)
 
 
 def _read_track(path, flag, ncol):
@@ -178,19 +212,25 @@ def main(args):
     prm = VcParams(mtDepth=args.mtDepth, rpb=args.rpb, minBQ=args.minBQ, minMQ=args.minMQ, hpLen=args.hpLen,
                    mismatchThr=args.mismatchThr, mtDrop=args.mtDrop, maxMT=args.maxMT, primerDist=args.primerDist,
                    fisherLegacy=args.fisherLegacy)
-    try:
-        output = call_loci(reads, intervals, refs, prm, gpus=args.gpus)
-    except Exception as e:
-        print(str(e))
-        raise
-
-    print("begin variant filtering and output")                           # :697
     target_rows = [tuple(l.strip().split('\t')[0:3]) for l in bed_lines if not l.startswith("track ") and l.strip()]
     trf_rows = _read_track(args.bedTandemRepeats, "--bedTandemRepeats", 3)
     rm_rows = _read_track(args.bedRepeatMaskerSubset, "--bedRepeatMaskerSubset", 4)
-    trf, rm = repeats.build_repeat_regions(target_rows, trf_rows, rm_rows)
-    output = repeats.apply_repeat_filters(output, trf, rm)
-    threshold = writers.write_outputs(output, args.outPrefix, args.mtDepth, args.threshold)
+    trf, rm = repeats.build_repeat_regions(target_rows, trf_rows, rm_rows)                # smCounter.py:699-734
+    threshold = writers.pi_threshold(args.mtDepth, args.threshold)                         # :820
+    try:
+        # per-locus calling on the GPUs, then -- per batch, in the native output stage -- the rows, the repeat filters
+        # (:751-785) and the called-variant lines (:832-891)
+        all_txt, cut_txt, cut_vcf = call_loci_text(reads, intervals, refs, prm, threshold, trf, rm, gpus=args.gpus)
+    except Exception as e:
+        print(str(e))
+        raise
+    print("begin variant filtering and output")                           # :697
+    with open(args.outPrefix + '.smCounter.all.txt', 'wb') as fh:          # :823-901
+        fh.write(('\t'.join(headerAll) + '\n').encode()); fh.write(all_txt)
+    with open(args.outPrefix + '.smCounter.cut.txt', 'wb') as fh:
+        fh.write(('\t'.join(headerVariants) + '\n').encode()); fh.write(cut_txt)
+    with open(args.outPrefix + '.smCounter.cut.vcf', 'wb') as fh:
+        fh.write(writers.vcf_header(args.outPrefix).encode()); fh.write(cut_vcf)
 
     timeEnd = datetime.datetime.now()
     print("smCounter completed running at " + str(timeEnd))

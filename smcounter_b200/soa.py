@@ -44,6 +44,10 @@ class ReadsSoA:
     packed: bool = False            # payloads stored back to back in read order: the offsets need not cross the ABI (NULL)
     store_lo: np.ndarray | None = None    # int32, optional stored window (include/smc_b200.h): first stored query base (even) ...
     store_len: np.ndarray | None = None   # int32  ... and number of stored bases; None = reads stored whole
+    # compact wire encodings (include/smc_b200.h, ABI v3); a compacted SoA is an upload format, not a working one
+    scalar_bits: int = 32                 # 16: nm / l_seq / store_lo / store_len are uint16 arrays
+    qual_bits: int = 8                    # 4 / 2: ``qual`` holds qual_bits-wide codes (low bits first, reads byte aligned) ...
+    qual_lut: np.ndarray | None = None    # ... and this is the phred value of each code
 
     @property
     def n(self) -> int:
@@ -60,6 +64,8 @@ class ReadsSoA:
 
     def select(self, idx: np.ndarray) -> "ReadsSoA":
         """Sub-batch with the reads ``idx`` (ascending), variable-length payloads re-packed."""
+        if self.qual_bits != 8 or self.scalar_bits != 32:
+            raise ValueError("a compacted SoA is an upload format: select / trim before compact()")
         idx = np.asarray(idx, dtype=np.int64)
         l_seq = self.stored_len()[idx]
         sb = (l_seq + 1) // 2
@@ -171,6 +177,52 @@ class ReadsSoA:
                         seq_off=out["seq"][1], qual_off=out["qual"][1], cigar_off=out["cigar"][1], n_cigar=self.n_cigar, umi=self.umi,
                         frag_id=self.frag_id, seq=out["seq"][0], qual=out["qual"][0], cigar=out["cigar"][0], chroms=self.chroms,
                         umi_names=self.umi_names, packed=True, store_lo=store_lo, store_len=store_len)
+
+    def compact(self, block: int = 1 << 18) -> "ReadsSoA":
+        """The same reads in the compact upload encodings of include/smc_b200.h (ABI v3): 16-bit nm / l_seq / store_lo /
+        store_len when every value fits, and 2- or 4-bit quality codes when the batch shows at most 4 / 16 distinct
+        qualities (sequencers that bin qualities; a batch with more keeps one byte per base).  Needs a packed layout
+        (repack() / trim_to_targets() / select()).  On the cfg-2 panel batch: 157 -> 92 bytes per read over PCIe."""
+        if self.qual_bits != 8 or self.scalar_bits != 32:
+            raise ValueError("already compact")
+        src = self if self.packed else self.repack()
+        kw = {f: getattr(src, f) for f in ("ref_id", "pos", "flag", "mapq", "seq_off", "qual_off", "cigar_off", "n_cigar", "umi", "frag_id",
+                                            "seq", "cigar", "chroms", "umi_names")}
+        scal = {"nm": src.nm, "l_seq": src.l_seq, "store_lo": src.store_lo, "store_len": src.store_len}
+        fits = all(a is None or (len(a) == 0 or (int(a.min()) >= 0 and int(a.max()) < 65536)) for a in scal.values())
+        scalar_bits = 16 if fits else 32
+        if fits:
+            scal = {k: (None if a is None else a.astype(np.uint16)) for k, a in scal.items()}
+        present = np.flatnonzero(np.bincount(src.qual, minlength=256)) if len(src.qual) else np.zeros(0, np.int64)
+        bits = 2 if len(present) <= 4 else 4 if len(present) <= 16 else 8
+        qual, lut = src.qual, None
+        if bits != 8:
+            lut = np.zeros(1 << bits, np.uint8)
+            lut[:len(present)] = present
+            code_of = np.zeros(256, np.uint8)
+            code_of[present] = np.arange(len(present), dtype=np.uint8)
+            per = 8 // bits                                     # codes per byte
+            lens = src.stored_len()
+            nbytes = (lens * bits + 7) // 8
+            poff = np.concatenate(([0], np.cumsum(nbytes)))
+            qual = np.zeros(int(poff[-1]), np.uint8)
+            uoff = np.concatenate(([0], np.cumsum(lens)))
+            for a in range(0, src.n, block):                     # pad every read to whole bytes, then fold `per` codes into one byte
+                b = min(src.n, a + block)
+                codes = code_of[src.qual[uoff[a]:uoff[b]]]
+                padded = np.zeros(int(poff[b] - poff[a]) * per, np.uint8)
+                ln = lens[a:b]
+                tot = int(ln.sum())
+                if tot:
+                    dst = np.repeat((poff[a:b] - poff[a]) * per - (uoff[a:b] - uoff[a]), ln) + np.arange(tot, dtype=np.int64)
+                    padded[dst] = codes
+                    m = padded.reshape(-1, per)
+                    acc = np.zeros(len(m), np.uint8)
+                    for k in range(per):
+                        acc |= m[:, k] << np.uint8(k * bits)
+                    qual[poff[a]:poff[b]] = acc
+        return ReadsSoA(nm=scal["nm"], l_seq=scal["l_seq"], store_lo=scal["store_lo"], store_len=scal["store_len"], qual=qual, packed=True,
+                        scalar_bits=scalar_bits, qual_bits=bits, qual_lut=lut, **kw)
 
     def is_packed(self) -> bool:
         """True when every payload is stored back to back in read order (checked, O(n))."""

@@ -108,7 +108,8 @@ def test_bamio_library_exports_and_layout(tmp_path):
     build.build_bamio()
     lib = _bamio.load()
     src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "smc_bamio.h")).read(), flags=re.S)
-    names = sorted(set(re.findall(r"\b(smc_bam_[a-z_]+)\s*\(", src)))
+    src += re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "smc_rows.h")).read(), flags=re.S)      # same library
+    names = sorted(set(re.findall(r"\b(smc_(?:bam|rows)_[a-z_]+)\s*\(", src)))
     assert set(names) == set(_bamio.EXPORTS)
     for n in names:
         assert getattr(lib, n) is not None
@@ -124,6 +125,17 @@ def test_bamio_library_exports_and_layout(tmp_path):
     assert int(got["size"]) == C.sizeof(cls)
     for f, _ in cls._fields_:
         assert int(got[f]) == getattr(cls, f).offset, f
+    for cname, cls2 in (("smc_rows_in", _bamio.smc_rows_in), ("smc_rows_out", _bamio.smc_rows_out)):                # include/smc_rows.h
+        lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "smc_rows.h"', 'int main(void){', 'printf("size %%zu\\n", sizeof(%s));' % cname]
+        for f, _ in cls2._fields_:
+            lines.append('printf("%s %%zu\\n", offsetof(%s, %s));' % (f, cname, f))
+        lines.append('return 0;}')
+        (tmp_path / "r.c").write_text("\n".join(lines))
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(tmp_path / "r"), str(tmp_path / "r.c")])
+        got = dict(l.split() for l in subprocess.check_output([str(tmp_path / "r")], text=True).splitlines())
+        assert int(got["size"]) == C.sizeof(cls2), cname
+        for f, _ in cls2._fields_:
+            assert int(got[f]) == getattr(cls2, f).offset, (cname, f)
     h = C.c_void_p()
     assert lib.smc_bam_open(str(tmp_path / "missing.bam").encode(), 1, C.byref(h)) != 0
     assert b"cannot open" in lib.smc_bam_last_error(None)

@@ -488,6 +488,39 @@ def test_barcode_with_many_dynamic_alleles_at_one_locus(codes):
     assert not problems, "\n".join(problems)
 
 
+@pytest.mark.parametrize("nq,chunks", [(3, "1"), (3, "4"), (7, "1"), (7, "5"), (20, "3")])
+def test_compact_upload_encodings_give_identical_bits(nq, chunks):
+    """ABI v3 compact encodings (16-bit scalars; 2- / 4-bit quality codes + codebook, expanded on the device -- per upload chunk
+    when smc_call_batch pipelines): every output identical to the plain encoding of the same reads, and to the oracle.
+    nq distinct base qualities: 3 (+ the N quality) -> 2-bit codes, 7 -> 4-bit, 20 -> stays at one byte per base."""
+    import numpy as np
+    from helpers import run_case
+    from smcounter_b200.caller import GpuCaller
+    from smcounter_b200.synth import make_panel
+    from smcounter_b200.targets import build_loci
+    qv = tuple(int(q) for q in np.linspace(40, 3, nq).round())
+    spec = SynthSpec(**dict(PIPE_SPEC, q_values=qv, q_probs=tuple([1.0 / nq] * nq)))
+    prm = VcParams(mtDepth=50, rpb=3.0, minBQ=15)
+    seen = {}
+
+    def enc(s):
+        c = s.trim_to_targets(PIPE_IVS).compact()
+        seen["bits"], seen["sbits"], seen["bytes"] = c.qual_bits, c.scalar_bits, (s.nbytes(), c.nbytes())
+        return c
+    problems, stats, (soa, refs, o_rows, g_rows, res, details) = _with_env("SMC_PIPE_CHUNKS", chunks, lambda: run_case(PIPE_IVS, spec, prm, seed=67, gpu_mutate=enc))
+    print(nq, chunks, seen, stats["pipe_chunks"])
+    assert seen["bits"] == (2 if nq == 3 else 4 if nq == 7 else 8) and seen["sbits"] == 16
+    assert not problems, "\n".join(problems)
+    # bit-identical to the plain encoding, resident path
+    loci, _ = build_loci(PIPE_IVS, soa.chroms, refs)
+    c = GpuCaller(prm, 0)
+    c.upload(soa, loci); c.run(); a = c.download(None)
+    c.upload(soa.trim_to_targets(PIPE_IVS).compact(), loci); c.run(); b = c.download(None)
+    c.close()
+    for f in ("loc", "cnt", "pi", "alt_allele", "alt_pi", "fl1", "fl2", "max_allele", "second_allele"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+
+
 def _hand_reads(ref_seq, site, families, read_len=70):
     """Paired reads over one amplicon of ``ref_seq`` (chrom 'c1'): ``families`` = [(barcode, n_fragments, inserted bases or '')];
     every read starts at 0, R1 forward / R2 reverse, the insertion (if any) follows reference position ``site`` (0-based)."""
@@ -651,8 +684,8 @@ def test_randomised_parameters_and_panels(seed):
     (alternating plain / packed / target-trimmed encodings and chunked uploads) against the oracle, field by field."""
     from helpers import run_case
     ivs, spec, prm = fuzz_case(seed)
-    enc = seed % 3
-    gpu_mutate = None if enc == 0 else (lambda s: s.repack()) if enc == 1 else (lambda s: s.trim_to_targets(ivs))
+    enc = seed % 4
+    gpu_mutate = (None, lambda s: s.repack(), lambda s: s.trim_to_targets(ivs), lambda s: s.trim_to_targets(ivs).compact())[enc]
     chunks = "1" if seed % 2 else "3"
     problems, stats, _ = _with_env("SMC_PIPE_CHUNKS", chunks, lambda: run_case(ivs, spec, prm, seed=seed, gpu_mutate=gpu_mutate))
     print(seed, ivs, spec, prm, stats)

@@ -355,32 +355,35 @@ def test_read_locator_and_batch_plan():
     assert [k for b in by_reads for k in b] == idxs and len(by_reads) >= 2
 
 
-def test_bench_rank_batches_partition_the_panel(monkeypatch):
-    """bench.make_batch(): at N ranks the seeded panel subset is split into disjoint interval groups that cover it (the product's
-    shard.assign_intervals), every rank's reads are packed and trimmed to its own targets, and N=1 keeps the plain subset."""
+def test_bench_rank_batches_partition_the_panel():
+    """bench.rank_batches(): at N ranks the seeded panel subset is split into disjoint interval groups that cover it (the product's
+    shard.assign_intervals), every rank's share is cut into its distinct batches in BED order, and the reference arm and the CUDA
+    arm print the same ``config``."""
     import importlib.util
     import os
     import types
-    import numpy as np
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    monkeypatch.setattr(bench, "UMIS_PER_LOCUS", 6)
-    args = types.SimpleNamespace(intervals=3, seed=1, whole_reads=False)
-    from smcounter_b200.synth import panel_intervals_from_bed
+    args = types.SimpleNamespace(intervals=3, batches=2, seed=1, whole_reads=False, no_compact=False, workload="cfg2", gpus=3)
     world = 3
-    want = panel_intervals_from_bed(bench.PANEL_BED, limit=args.intervals * world, seed=args.seed)
-    got, loci_total = [], 0
-    for rank in range(world):
-        mine, soa, refs, loci, bed_order, full = bench.make_batch(args, rank, world)
-        assert mine and soa.packed and soa.store_lo is not None and full.store_lo is None and full.n == soa.n
-        assert soa.seq.nbytes + soa.qual.nbytes < full.seq.nbytes + full.qual.nbytes
-        assert loci.n == len(set((c, p) for (c, s, e) in mine for p in range(s, e)))
-        got += mine
-        loci_total += loci.n
+    want = bench.workload_intervals(args, world)
+    assert len(want) == 3 * 2 * 3 and want == sorted(want, key=want.index)
+    got = []
+    for r in range(world):
+        groups = bench.rank_batches(args, r, world)
+        assert len(groups) == args.batches and all(groups)
+        for g in groups:
+            got.extend(g)
     assert sorted(got) == sorted(want) and len(got) == len(set(got))
-    one = bench.make_batch(args, 0, 1)[0]
-    assert one == panel_intervals_from_bed(bench.PANEL_BED, limit=args.intervals, seed=args.seed)
+    assert [iv for g in bench.rank_batches(args, 0, 1) for iv in g] == bench.workload_intervals(args, 1)
+    cfg = bench.config_dict(args, world)
+    assert cfg["loci_per_step"] == sum(e - s for (_, s, e) in want) and cfg["batches_per_step"] == 2
+    for wl in bench.WORKLOADS:
+        a2 = types.SimpleNamespace(intervals=bench.WORKLOADS[wl][3], batches=2, seed=1, workload=wl)
+        ivs = bench.workload_intervals(a2, 2)
+        assert len(ivs) == a2.intervals * 4 and len(set(ivs)) == len(ivs)
+        assert bench.vc_params(a2).mtDepth == bench.WORKLOADS[wl][2]["mtDepth"]
 
 
 def test_vectorised_float_columns_equal_the_scalar_py2_formatting():
@@ -416,3 +419,97 @@ def test_missing_repeat_track_aborts_like_the_reference(tmp_path, capsys):
     assert "disabled" in capsys.readouterr().out
     (tmp_path / "rm.bed").write_text("chr1\t5\t9\tSimple_repeat\textra\nchr2 1 2 Satellite\n")
     assert smCounter._read_track(str(tmp_path / "rm.bed"), "--bedRepeatMaskerSubset", 4) == [("chr1", "5", "9", "Simple_repeat"), ("chr2", "1", "2", "Satellite")]
+
+
+def _fabricated_results(n, seed):
+    """Random per-locus device results (no GPU): every code path of the row formatter -- zero coverage, bi-allelic pairs, dynamic
+    alleles, all FILTER bits, exact decimal ties in the rounded columns."""
+    from smcounter_b200 import _ffi
+    from smcounter_b200.caller import LocusResults
+    rng = np.random.default_rng(seed)
+    chroms = ["chr1", "chr2", "chrY"]
+    ref_id = np.sort(rng.integers(0, 3, n)).astype(np.int32)
+    pos0 = np.zeros(n, np.int32)
+    for c in range(3):
+        m = ref_id == c
+        pos0[m] = np.sort(rng.choice(100000, int(m.sum()), replace=False))
+    loci = soa.Loci(ref_id, pos0, np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)].copy())
+    res = LocusResults(n, 64)
+    res.loc[:] = 0
+    cvg = rng.integers(1, 120000, n)
+    used = rng.integers(1, 8000, n)
+    res.loc[_ffi.L_CVG], res.loc[_ffi.L_USEDMT] = cvg, used
+    res.loc[_ffi.L_ALLFRAG], res.loc[_ffi.L_ALLMT], res.loc[_ffi.L_USEDFRAG] = rng.integers(0, 90000, n), rng.integers(1, 9000, n), rng.integers(0, 9000, n)
+    for k in (_ffi.L_MT3, _ffi.L_MT5, _ffi.L_MT7, _ffi.L_MT10):
+        res.loc[k] = rng.integers(0, 5000, n)
+    res.loc[_ffi.L_STATUS] = np.where(rng.random(n) < 0.02, 1, 0)
+    for a in range(5):
+        res.cnt[a, _ffi.C_ALLELE] = (cvg * rng.random(n) * rng.choice([0, 0.001, 0.3, 1], n)).astype(np.int32)
+        res.cnt[a, _ffi.C_MT] = (used * rng.random(n) * rng.choice([0, 0.01, 0.5, 1], n)).astype(np.int32)
+        res.cnt[a, _ffi.C_STRONG] = rng.integers(0, 50, n)
+        res.pi[a] = np.where(rng.random(n) < 0.3, 0.0, rng.random(n) * rng.choice([0.01, 1, 30, 20000], n))
+    res.pi[0, :50] = np.arange(50) * 0.125 + 0.005                    # x.xx5 values that are exact in binary: round-half-away cases
+    res.pi[1, :50] = np.arange(50) / 8.0 + 0.625
+    res.cnt[0, _ffi.C_ALLELE, :64] = np.arange(64)                     # k / 32 fractions: exact ties at 4 decimals (1/32 = 0.03125)
+    res.loc[_ffi.L_CVG, :64] = 32 * np.arange(1, 65)
+    res.loc[_ffi.L_STATUS, :64] = 0
+    nd = 40
+    res.n_dyn = nd
+    res.dyn_cnt[:nd] = rng.integers(0, 300, (nd, 13))
+    res.dyn_pi[:nd] = rng.random(nd) * 80
+    res.alt_allele[:] = rng.choice([0, 1, 2, 3, 4], n)
+    res.second_allele[:] = rng.choice([0, 1, 3, 4], n)
+    dynloc = rng.choice(n, nd, replace=False)
+    res.alt_allele[dynloc] = 5 + np.arange(nd)
+    res.biallelic[:] = (rng.random(n) < 0.1).astype(np.uint8)
+    res.second_allele[dynloc[:10]] = 5 + np.arange(10)[::-1]
+    res.biallelic[dynloc[:10]] = 1
+    bits = [_ffi.F_LM, _ffi.F_LSM, _ffi.F_DP, _ffi.F_SB, _ffi.F_LOWQ, _ffi.F_R1CP, _ffi.F_R2CP, _ffi.F_PRIMERCP, _ffi.F_HPGATE]
+
+    def rbits():
+        f = np.zeros(n, np.uint32)
+        for b in bits:
+            f |= np.where(rng.random(n) < 0.15, b, 0).astype(np.uint32)
+        return np.where(rng.random(n) < 0.5, f | _ffi.F_EVALUATED, 0).astype(np.uint32)
+    res.fl1[:], res.fl2[:] = rbits(), rbits()
+    hp = {}
+    for i in range(n):
+        for cand, fl in ((0, res.fl1), (1, res.fl2)):
+            if fl[i] & _ffi.F_HPGATE:
+                hp[(i, cand)] = (bool(rng.random() < 0.5), bool(rng.random() < 0.5))
+    return chroms, loci, res, hp, rng
+
+
+def test_native_output_stage_equals_the_python_rows_filters_and_writers(monkeypatch):
+    """csrc/smc_rows.cpp (the product's output stage) against the Python restatement kept for this purpose: format_rows(),
+    repeats.apply_repeat_filters() and writers.render_outputs() -- rows, repeat tags, PASS / strip, cut.txt and VCF lines, byte
+    for byte, on fabricated device results."""
+    from smcounter_b200 import _ffi
+    chroms, loci, res, hp, rng = _fabricated_results(12000, seed=5)
+    names = ["N", "INS|A|ATT", "DEL|ACG|A", "R", "INS|C|CGGGGGGGGGGGG"]
+    monkeypatch.setattr(rows.AlleleNamer, "name", lambda self, a: _ffi.FIXED_NAMES[a] if a < 5 else names[(a - 5) % 5])
+    refs = SparseRef({c: 200000 for c in chroms})
+    order = rng.permutation(loci.n)[:9000]
+    want = rows.format_rows(res, None, loci, chroms, refs, 10, order, workers=1, hp_flags=hp)
+    got = rows.emit_rows(res, None, loci, chroms, refs, 10, order, hp_flags=hp)
+    assert got.rows() == want
+    assert rows.emit_rows(res, None, loci, chroms, refs, 10, order, hp_flags=hp, threads=1).all == got.all
+    assert sum(1 for r in want if r.endswith("Zero_Coverage")) > 50 and sum(1 for r in want if "," in r.split("\t")[3]) > 20
+    trf_rows = [("chr1", str(s), str(s + int(rng.integers(5, 400)))) for s in sorted(rng.integers(0, 100000, 300).tolist())]
+    rm_rows = sorted([("chr%d" % rng.integers(1, 3), str(s), str(s + int(rng.integers(5, 300))), str(rng.choice(["Simple_repeat", "Low_complexity", "Satellite", "L1"])))
+                      for s in rng.integers(0, 100000, 500).tolist()], key=lambda r: (r[0], int(r[1])))
+    trf, rm = repeats.build_repeat_regions([(c, "0", "100000") for c in chroms], trf_rows, rm_rows)
+    fin = repeats.apply_repeat_filters(want, trf, rm)
+    thr, a, c, v = writers.render_outputs(fin, "pfx", 3000, 0)
+    em = rows.emit_rows(res, None, loci, chroms, refs, 10, order, hp_flags=hp, finalize=True, threshold=thr, trf=trf, rm=rm)
+    assert "\t".join(rows.headerAll) + "\n" + em.all.decode() == a
+    assert "\t".join(rows.headerVariants) + "\n" + em.cut.decode() == c
+    assert writers.vcf_header("pfx") + em.vcf.decode() == v
+    assert c.count("\n") > 500 and "RepT" in a and "RepS" in a and "1/2" in v and "1/1" in v
+    # regrouping by row ranges (what the CLI does per BED interval)
+    x = em.slices(100, 200)
+    assert x[0] == "".join(l + "\n" for l in fin[100:200]).encode()
+    # a locus that needs a down-sampling mask has no row: same error as the Python formatter
+    res.loc[_ffi.L_STATUS, int(order[7])] = _ffi.ST_NEED_DOWNSAMPLE
+    with pytest.raises(RuntimeError, match="Exception thrown in vc"):
+        rows.emit_rows(res, None, loci, chroms, refs, 10, order, hp_flags=hp)
