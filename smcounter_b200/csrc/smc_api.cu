@@ -14,12 +14,20 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only: ranges show up under nsys / ncu --nvtx, cost nothing otherwise
+
 #include "smc_common.cuh"
 #include "smc_sort.cuh"
 #include "smc_pileup.cuh"
 #include "smc_stats.cuh"
 
 namespace {
+
+// NVTX range over one pipeline stage (tracing)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 thread_local std::string g_create_error;
 
@@ -56,7 +64,8 @@ enum SmallWord {
     SW_CVG_SUM = 8,          // u64: sum of cvg over the loci (= pileup read-events)
     SW_N_UMI = 10,           // distinct barcodes
     SW_PIPE_BLOCKED = 16,    // [SMC_PIPE_MAX]: first unit that has to wait for chunk c + 1
-    SW_PACK_TOTALS = 40      // [3]: bytes / words of packed bases, qualities, CIGARs
+    SW_PACK_TOTALS = 40,     // [4]: bytes / words of packed bases, qualities, CIGARs, compact qualities
+    SW_SPILL_COUNT = 48      // k_merge spill records handed out
 };
 
 struct smc_ctx {
@@ -80,7 +89,8 @@ struct smc_ctx {
         d_cigar, d_store_lo, d_store_len;
     bool has_store = false;                     // reads carry a stored window (smc_reads_soa::store_lo / store_len)
     int qual_bits = 8;                          // 4 / 2: compact qualities were uploaded (d_qual_packed) and are expanded into d_qual
-    DevBuf d_qual_packed, d_qual_poff, d_qual_lut, d_stage16;
+    DevBuf d_qual_packed, d_qual_poff, d_qual_lut, d_stage16, d_spill;
+    uint32_t spill_cap = 0;                     // records in the k_merge spill pool (grows x4 on GF_SPILL_FULL)
     const uint32_t* inv_ptr = nullptr;          // read index -> sorted position (lives in d_v0 or d_v1 after the read sort)
     DevBuf d_loci_ref, d_loci_pos, d_loci_base, d_loci_key;
     DevBuf d_keep_idx, d_keep_off, d_keep_umi;
@@ -128,7 +138,7 @@ static std::vector<DevBuf*> all_bufs(smc_ctx* ctx) {
                       &ctx->d_s_pi, &ctx->d_s_rep_read, &ctx->d_s_rep_qpos, &ctx->d_s_len, &ctx->d_dyn_first, &ctx->d_tasks,
                       &ctx->d_list_idx, &ctx->d_list_count, &ctx->d_list_off, &ctx->d_list_umi, &ctx->d_list_first,
                       &ctx->d_hp_bases, &ctx->d_hp_meta, &ctx->d_hp_flags, &ctx->d_pipe_need, &ctx->d_umi_table,
-                      &ctx->d_qual_packed, &ctx->d_qual_poff, &ctx->d_qual_lut, &ctx->d_stage16};
+                      &ctx->d_qual_packed, &ctx->d_qual_poff, &ctx->d_qual_lut, &ctx->d_stage16, &ctx->d_spill};
 }
 
 #define CK(call)                                                                                         \
@@ -464,6 +474,7 @@ static int pipe_chunks_for(const smc_reads_soa* R) {
 //                    ctx->st_copy, one event per chunk; returns without waiting (smc_call_batch synchronises both streams).
 static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc, const smc_umi_keep* K, bool pipelined) {
     if (!ctx) return SMC_E_ARG;
+    NvtxRange nvtx_r("smc:upload");
     if (!R || !Lc) { ctx->err = "smc_upload: null reads/loci"; return SMC_E_ARG; }
     if (R->n_reads < 0 || Lc->n_loci < 0) { ctx->err = "smc_upload: negative size"; return SMC_E_ARG; }
     if (Lc->n_loci > SMC_MAX_LOCI) { ctx->err = "smc_upload: more than 4194302 loci in one batch"; return SMC_E_LIMIT; }
@@ -609,6 +620,7 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
     if (!ctx->uploaded) { ctx->err = "smc_run_resident: nothing uploaded"; return SMC_E_STATE; }
     CK(cudaSetDevice(ctx->device));
     g_launches = 0;
+    NvtxRange nvtx_r("smc:read_sort+prep+tile_events");
     const int64_t n = ctx->n_reads, nl = ctx->n_loci;
     const uint32_t n_tiles = (uint32_t)((nl + 31) / 32);
     uint32_t* small = ctx->d_small.as<uint32_t>();          // words: enum SmallWord
@@ -779,6 +791,7 @@ static DynTab make_dyntab(smc_ctx* ctx) {
     T.drep_qpos = ctx->d_drep_qpos.as<int32_t>(); T.dlen = ctx->d_dlen.as<int32_t>(); T.dcnt = ctx->d_dcnt.as<int32_t>();
     T.dlimb = ctx->d_dlimb.as<unsigned long long>(); T.diskey = ctx->d_diskey.as<uint8_t>(); T.dcount = small + SW_DYN_COUNT; T.gflags = small + SW_GFLAGS;
     T.seq = ctx->d_seq.as<uint8_t>(); T.seq_off = ctx->d_seq_off.as<int64_t>();
+    T.spill = ctx->d_spill.as<SpillRec>(); T.spill_cap = ctx->spill_cap; T.spill_count = small + SW_SPILL_COUNT;
     return T;
 }
 
@@ -822,6 +835,7 @@ static void fill_kargs(smc_ctx* ctx, KAArgs& A, KBArgs& B, bool list, bool need_
 }
 
 static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
+    NvtxRange nvtx_r("smc:pileup+stats");
     const int64_t nl = ctx->n_loci;
     uint32_t* small = ctx->d_small.as<uint32_t>();
     const size_t nlz = (size_t)(nl ? nl : 1);
@@ -854,6 +868,12 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
         CK(cudaMemsetAsync(ctx->d_cnt.p, 0, nlz * SMC_NFIXED * SMC_NCNT * 4, ctx->st));
         CK(cudaMemsetAsync(ctx->d_limb.p, 0, nlz * SMC_NFIXED * 3 * 8, ctx->st));
         CK(cudaMemsetAsync(small + SW_GFLAGS, 0, 24, ctx->st));     // gflags, dyn count, n_tasks, cvg sum
+        if (ctx->spill_cap == 0) {
+            ctx->spill_cap = 1024;
+            if (const char* ev = getenv("SMC_SPILL_CAP0")) { long v = atol(ev); if (v >= 1 && v <= (1l << 24)) ctx->spill_cap = (uint32_t)v; }   // test hook
+        }
+        CK(ctx->d_spill.ensure((size_t)ctx->spill_cap * sizeof(SpillRec)));
+        CK(cudaMemsetAsync(small + SW_SPILL_COUNT, 0, 4, ctx->st));
         if (NE > 0) {
             { int rc = ensure_code_storage(ctx, false, ctx->has_keep); if (rc) return rc; }
             KAArgs A; KBArgs B;
@@ -888,7 +908,8 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
         CK(cudaMemcpyAsync(h, small + SW_GFLAGS, 12, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         CK(cudaGetLastError());
-        if (!(h[0] & (GF_DYN_FULL | GF_CODE_FULL))) { ctx->n_dyn = h[1]; break; }
+        if (!(h[0] & (GF_DYN_FULL | GF_CODE_FULL | GF_SPILL_FULL))) { ctx->n_dyn = h[1]; break; }
+        if (h[0] & GF_SPILL_FULL) ctx->spill_cap = ctx->spill_cap >= (1u << 24) ? ctx->spill_cap : ctx->spill_cap * 4;
         if (attempt == 5) { ctx->err = "dynamic allele table / fragment code storage overflow"; return SMC_E_OVERFLOW; }
         if (h[0] & GF_CODE_FULL) ctx->code_mult = 3;             // worst-case layout: always fits
         if (h[0] & GF_DYN_FULL) {
@@ -897,6 +918,7 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
         }
     }
     CK(cudaEventRecord(ctx->ev[5], ctx->st));
+    NvtxRange nvtx_s("smc:dyn_rows+call+fisher");
     // ---------------- dynamic alleles -> sorted rows
     const int64_t nd = ctx->n_dyn;
     const size_t ndz = (size_t)(nd ? nd : 1);
@@ -991,6 +1013,7 @@ extern "C" int smc_download(smc_ctx* ctx, smc_out* out) {
     const int64_t nd = ctx->n_dyn;
     out->n_dyn = nd;
     if (nd > out->dyn_capacity) { ctx->err = "smc_download: dyn_capacity too small (n_dyn reported in smc_out.n_dyn)"; return SMC_E_LIMIT; }
+    NvtxRange nvtx_r("smc:download");
     int64_t bytes = 0;
     CK(cudaEventRecord(ctx->ev[0], ctx->st));
 #define DOWN(dst, buf, count, T)                                                                                \

@@ -60,6 +60,7 @@ struct PrepArgs {
 #define GF_BAD_READ   2u     // l_seq / clip length beyond the 16-bit record fields
 #define GF_CODE_FULL  4u     // a unit ran out of fragment-code storage (host retries with the worst-case layout)
 #define GF_BAD_STORE  8u     // stored window (store_lo / store_len) malformed or not covering every target base of the read
+#define GF_SPILL_FULL 16u    // k_merge ran out of spill records (host retries with a larger pool)
 
 __global__ void __launch_bounds__(256) k_read_prep(PrepArgs A) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // BAM order in (coalesced), sorted position out
@@ -287,14 +288,18 @@ static inline uint64_t code_slots_total(uint64_t ne, uint64_t n_units, uint32_t 
 }
 
 #define NF SMC_NFIXED
-#define NDYN 6             // distinct dynamic alleles (indel starts, N / IUPAC bases) one barcode may show at one locus
-#define NSLOT (NF + NDYN)  // per-barcode allele slots: 5 fixed + NDYN dynamic
+#define NDYN 6             // dynamic alleles (indel starts, N / IUPAC bases) of one barcode at one locus that live in shared memory
+#define NSLOT (NF + NDYN)  // per-barcode allele slots in shared memory: 5 fixed + NDYN dynamic
+#define NSPILL 21          // further dynamic alleles of the barcode live in a spill record in global memory (5 + 6 + 21 = the 32
+                           // slots of the lane's allele bit mask; a barcode beyond that raises SMC_ST_UMI_OVERFLOW)
+struct SpillRec { uint32_t e[NSPILL]; int32_t cnt[NSPILL]; double prod[NSPILL]; };
 
 // The dynamic-allele table, passed BY VALUE to the out-of-line helpers.
 struct DynTab {
     unsigned long long* dkey; uint32_t dmask; uint32_t* drep_read; int32_t* drep_qpos; int32_t* dlen;
     int32_t* dcnt; unsigned long long* dlimb; uint8_t* diskey; uint32_t* dcount; uint32_t* gflags;
     const uint8_t* seq; const int64_t* seq_off;      // bases of every read (caller's SoA order): long insertions are compared base by base
+    SpillRec* spill; uint32_t spill_cap; uint32_t* spill_count;      // k_merge: pool of spill records (one per overflowing lane and barcode)
 };
 
 // BAM nibble of A, C, G, T (1, 2, 4, 8) -> field A0 C1 T2 G3 of the packed register counters / allele slot A0 C1 T3 G4
@@ -1012,7 +1017,8 @@ struct MergeState {
     unsigned long long pad_lo, pad_hi;      // PI terms that go to all of A, C, G, T (single-allele barcodes, see umi_finalize)
     uint32_t flags;                         // LF_*
     // barcode-level
-    int n; uint32_t exist; double Q, rightP; uint32_t last_aid; int ndyn;      // the rows of the dynamic slots live in shared memory (UDYN)
+    int n; uint32_t exist; double Q, rightP; uint32_t last_aid; int ndyn;      // the rows of the dynamic slots live in shared memory (UDYN) ...
+    SpillRec* sp;                           // ... and, from the 7th dynamic allele of the barcode on, in this spill record (else nullptr)
     uint32_t first_read;                    // BAM index of the barcode's first passing read at this locus (listing only)
 };
 
@@ -1021,6 +1027,10 @@ struct MergeState {
 #define UCNT(s)     ucnt[(s) * 32 + lane]
 #define UPROD(s)    uprod[(s) * 32 + lane]
 #define UDYN(k)     (reinterpret_cast<uint32_t*>(uprod + NSLOT * 32)[(k) * 32 + lane])
+// the same three per-slot arrays with the spill record behind them (`sp` in scope; never touched for slots in shared memory)
+#define XCNT(s)     (*((s) < NSLOT ? &UCNT(s) : &sp->cnt[(s) - NSLOT]))
+#define XPROD(s)    (*((s) < NSLOT ? &UPROD(s) : &sp->prod[(s) - NSLOT]))
+#define XDYN(k)     (*((k) < NDYN ? &UDYN(k) : &sp->e[(k) - NDYN]))
 
 // MTCnt / strongMTCnt of an allele that may be dynamic; add = 1 (MTCnt) or 0x10001 (both)
 __device__ __forceinline__ void bump_mt(int32_t* dcnt, int* fc, int lane, uint32_t aid, uint32_t add) {
@@ -1040,14 +1050,20 @@ __device__ __forceinline__ void umi_materialize(int lane, int* ucnt, double* upr
 }
 
 // one fragment of bcDict joins the open barcode (the per-fragment part of calProb, smCounter.py:56-77)
-__device__ __forceinline__ void fragment_join(double p, double q1, uint32_t aid, int lane, int* ucnt, double* uprod, MergeState& S) {
+__device__ __forceinline__ void fragment_join(DynTab T, double p, double q1, uint32_t aid, int lane, int* ucnt, double* uprod, MergeState& S) {
     int slot = (int)aid;
+    SpillRec* sp = S.sp;
     if (aid >= NF) {
         const uint32_t e = aid - NF;
         int k = 0;
-        while (k < S.ndyn && UDYN(k) != e) ++k;
+        while (k < S.ndyn && XDYN(k) != e) ++k;
         if (k == S.ndyn) {
-            if (k < NDYN) { UDYN(k) = e; S.ndyn = k + 1; }
+            if (k >= NDYN && !sp) {                                   // 7th dynamic allele of this barcode: take a spill record
+                const uint32_t r = atomicAdd(T.spill_count, 1u);
+                if (r >= T.spill_cap) atomicOr(T.gflags, GF_SPILL_FULL);
+                sp = S.sp = T.spill + (r < T.spill_cap ? r : 0u);
+            }
+            if (k < NDYN + NSPILL) { XDYN(k) = e; S.ndyn = k + 1; }
             else { S.status |= SMC_ST_UMI_OVERFLOW; k = 0; }
         }
         slot = NF + k;
@@ -1058,13 +1074,13 @@ __device__ __forceinline__ void fragment_join(double p, double q1, uint32_t aid,
         const bool multi = (S.exist & (S.exist - 1u)) != 0u;
         if (multi || S.exist != bit) {
             if (!multi) umi_materialize(lane, ucnt, uprod, S.exist, S.n, S.rightP);
-            if (!(S.exist & bit)) { S.exist |= bit; UCNT(slot) = 0; UPROD(slot) = S.Q; }
+            if (!(S.exist & bit)) { S.exist |= bit; XCNT(slot) = 0; XPROD(slot) = S.Q; }
             uint32_t m = S.exist;
             while (m) {                                                  // :70-74
                 int s = __ffs(m) - 1; m &= m - 1;
-                UPROD(s) = __dmul_rn(UPROD(s), s == slot ? q1 : p);
+                XPROD(s) = __dmul_rn(XPROD(s), s == slot ? q1 : p);
             }
-            UCNT(slot) += 1;
+            XCNT(slot) += 1;
         }
     }
     S.Q = __dmul_rn(S.Q, p);
@@ -1072,6 +1088,7 @@ __device__ __forceinline__ void fragment_join(double p, double q1, uint32_t aid,
     S.n += 1;
     S.last_aid = aid;
 }
+
 
 // PCR prior outside the host-built table (barcodes with > pcr_nmax fragments or > 6 distinct alleles): device pow()
 __device__ __noinline__ double pcr_slow(int cnt, double denom) {
@@ -1121,16 +1138,16 @@ __device__ __forceinline__ double neg_log10_1m_small(double p) {
 // Returns the finalDict keys it touched among the fixed alleles.
 __device__ __noinline__ uint32_t umi_general(DynTab T, const double* __restrict__ pcrtab, int pcr_nmax, double smt, int lane, int n,
                                              uint32_t exist, double rightP, int ndyn, uint32_t last_aid,
-                                             int* fc, ulonglong2* limb, int* ucnt, double* uprod) {
+                                             int* fc, ulonglong2* limb, int* ucnt, double* uprod, SpillRec* sp) {
     uint32_t keymask = 0;
     // canonical order of the dynamic slots = ascending allele key (insertion sort of the slot rows; a slot whose exist bit is
     // clear -- its fragments were all deleted again -- travels with its bit)
     for (int i = 1; i < ndyn; ++i)
-        for (int j = i; j > 0 && __ldcg(&T.dkey[UDYN(j - 1)]) > __ldcg(&T.dkey[UDYN(j)]); --j) {
+        for (int j = i; j > 0 && __ldcg(&T.dkey[XDYN(j - 1)]) > __ldcg(&T.dkey[XDYN(j)]); --j) {
             const int a = NF + j - 1, b = NF + j;
-            const uint32_t tu = UDYN(j - 1); UDYN(j - 1) = UDYN(j); UDYN(j) = tu;
-            const int tc = UCNT(a); UCNT(a) = UCNT(b); UCNT(b) = tc;
-            const double tp = UPROD(a); UPROD(a) = UPROD(b); UPROD(b) = tp;
+            const uint32_t tu = XDYN(j - 1); XDYN(j - 1) = XDYN(j); XDYN(j) = tu;
+            const int tc = XCNT(a); XCNT(a) = XCNT(b); XCNT(b) = tc;
+            const double tp = XPROD(a); XPROD(a) = XPROD(b); XPROD(b) = tp;
             const uint32_t ba = (exist >> a) & 1u, bb = (exist >> b) & 1u;
             exist = (exist & ~((1u << a) | (1u << b))) | (bb << a) | (ba << b);
         }
@@ -1151,7 +1168,7 @@ __device__ __noinline__ uint32_t umi_general(DynTab T, const double* __restrict_
     double tpad = rightP;                                         // :88-91
     for (uint32_t m = exist; m; m &= m - 1) {
         const int s = __ffs(m) - 1;
-        const int c = UCNT(s);
+        const int c = XCNT(s);
         const double v = tab ? __ldg(trow + c) : pcr_slow(c, denom);
         tpad = __dmul_rn(tpad, v);
         if (v < m1) { m2 = m1; m1 = v; arg1 = s; } else if (v < m2) m2 = v;
@@ -1161,12 +1178,12 @@ __device__ __noinline__ uint32_t umi_general(DynTab T, const double* __restrict_
     for (uint32_t m = exist; m; m &= m - 1) {
         const int s = __ffs(m) - 1;
         const double minp = (s == arg1) ? m2 : m1;                // min over the OTHER members of uniq
-        UPROD(s) = __dadd_rn(__dmul_rn(PCR_NO_ERROR, UPROD(s)), __dmul_rn(rightP, minp));
+        XPROD(s) = __dadd_rn(__dmul_rn(PCR_NO_ERROR, XPROD(s)), __dmul_rn(rightP, minp));
     }
     double sumP = 0.0;                                            // :93, in canonical slot order
     for (uint32_t m = uniq; m; m &= m - 1) {
         const int s = __ffs(m) - 1;
-        sumP = __dadd_rn(sumP, ((exist >> s) & 1u) ? UPROD(s) : tpad);
+        sumP = __dadd_rn(sumP, ((exist >> s) & 1u) ? XPROD(s) : tpad);
     }
     // ---- posterior -> -log10(1-p) (:96, :509-510), PI accumulation (:512), consensus (:514-523).
     // One loop over the members of uniq in slot order; the pads share one value (computed at the first pad).
@@ -1179,7 +1196,7 @@ __device__ __noinline__ uint32_t umi_general(DynTab T, const double* __restrict_
         double l; unsigned long long lo, hi;
         if (is_pad && have_pad) { l = l_pad; lo = plo; hi = phi; }
         else {
-            l = neg_log10_1m(sumP <= 0.0 ? 0.0 : (is_pad ? tpad : UPROD(s)) / sumP);
+            l = neg_log10_1m(sumP <= 0.0 ? 0.0 : (is_pad ? tpad : XPROD(s)) / sumP);
             pi_fixed128(l, lo, hi);
             if (is_pad) { have_pad = true; l_pad = l; plo = lo; phi = hi; }
         }
@@ -1189,7 +1206,7 @@ __device__ __noinline__ uint32_t umi_general(DynTab T, const double* __restrict_
             LIMB(s) = v;
             keymask |= 1u << s;
         } else {
-            const uint32_t e = UDYN(s - NF);
+            const uint32_t e = XDYN(s - NF);
             unsigned long long a0, a1, a2;
             split_limbs(lo, hi, a0, a1, a2);
             if (a0) atomicAdd(&T.dlimb[(size_t)e * 3 + 0], a0);
@@ -1201,7 +1218,7 @@ __device__ __noinline__ uint32_t umi_general(DynTab T, const double* __restrict_
         else if (l == best) nbest++;
     }
     if (nbest == 1) {                                             // :515-519
-        const uint32_t aid = cons < NF ? (uint32_t)cons : NF + UDYN(cons - NF);
+        const uint32_t aid = cons < NF ? (uint32_t)cons : NF + XDYN(cons - NF);
         bump_mt(T.dcnt, fc, lane, aid, best > smt ? 0x10001u : 1u);
     } else if (n == 1) {                                          // :521-523
         bump_mt(T.dcnt, fc, lane, last_aid, 1u);
@@ -1290,10 +1307,10 @@ __device__ __forceinline__ void umi_finalize(const KBArgs& A, int lane, int ki, 
         } else {
             if (!multi) umi_materialize(lane, ucnt, uprod, S.exist, n, S.rightP);
             S.keymask |= umi_general(A.T, A.pcrtab, A.pcr_nmax, A.smt, lane, n, S.exist, S.rightP, S.ndyn,
-                                     S.last_aid, fc, limb, ucnt, uprod);
+                                     S.last_aid, fc, limb, ucnt, uprod, S.sp);
         }
     }
-    S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.ndyn = 0; S.flags = 0; S.first_read = 0xffffffffu;
+    S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.ndyn = 0; S.flags = 0; S.first_read = 0xffffffffu; S.sp = nullptr;
 }
 
 template <bool LIST>
@@ -1333,7 +1350,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32, KB_MINBLOCKS) k_merge_t(const K
     S.allFrag = S.allMT = S.usedFrag = S.nBC = S.usedMT = S.mt3 = S.mt5 = S.mt7 = S.mt10 = 0;
     S.keymask = 0; S.status = 0; S.pad_lo = S.pad_hi = 0;
     S.flags = 0;
-    S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.last_aid = 0; S.ndyn = 0;
+    S.n = 0; S.exist = 0; S.Q = 1.0; S.rightP = 1.0; S.last_aid = 0; S.ndyn = 0; S.sp = nullptr;
     S.first_read = 0xffffffffu;
 
     uint32_t umi_slot = eb;                                        // warp uniform: umi_urank[] slot of the open barcode
@@ -1379,7 +1396,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32, KB_MINBLOCKS) k_merge_t(const K
             S.n += join ? 1 : 0;
             S.exist |= join ? bit : 0u;
             S.last_aid = join ? aid : S.last_aid;
-        } else if (join) fragment_join(pq.x, pq.y, aid, lane, ucnt, uprod, S);
+        } else if (join) fragment_join(A.T, pq.x, pq.y, aid, lane, ucnt, uprod, S);
     }
     // ---- flush the lane's locus to the per-locus accumulators ([field][locus] layout: coalesced across lanes)
     if (lane_valid) {
