@@ -65,7 +65,8 @@ enum SmallWord {
     SW_N_UMI = 10,           // distinct barcodes
     SW_PIPE_BLOCKED = 16,    // [SMC_PIPE_MAX]: first unit that has to wait for chunk c + 1
     SW_PACK_TOTALS = 40,     // [4]: bytes / words of packed bases, qualities, CIGARs, compact qualities
-    SW_SPILL_COUNT = 48      // k_merge spill records handed out
+    SW_SPILL_COUNT = 48,     // k_merge spill records handed out
+    SW_CHUNK_READS = 64      // [SMC_PIPE_MAX + 2]: first read completed by each upload chunk (compact qualities)
 };
 
 struct smc_ctx {
@@ -552,10 +553,14 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
     if (qbits != 8) CK(ctx->d_qual.ensure((size_t)qual_dev_bytes + 16));
     if (G == 1) {
         UP(ctx->d_seq, R->seq, R->seq_bytes, uint8_t); UP(qual_up, R->qual, R->qual_bytes, uint8_t);
-        if (qbits != 8)
-            LAUNCH(k_unpack_qual, nblk(n * 32, 256), 256, 0, n, ctx->d_qual_poff.as<uint32_t>(), ctx->d_qual_off.as<int64_t>(), ctx->d_lseq.as<int32_t>(),
+        if (qbits != 8) {
+            const uint32_t whole[2] = {0u, (uint32_t)n};
+            CK(cudaMemcpyAsync(ctx->d_small.as<uint32_t>() + SW_CHUNK_READS, whole, 8, cudaMemcpyHostToDevice, ctx->st));
+            LAUNCH(k_unpack_qual, std::min<unsigned>(nblk(n * 32, 256), 148u * 16u), 256, 0, ctx->d_small.as<uint32_t>() + SW_CHUNK_READS,
+                   ctx->d_qual_poff.as<uint32_t>(), ctx->d_qual_off.as<int64_t>(), ctx->d_lseq.as<int32_t>(),
                    ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr, qbits, ctx->d_qual_lut.as<uint8_t>(), ctx->d_qual_packed.as<uint8_t>(),
-                   ctx->d_qual.as<uint8_t>(), nullptr, nullptr, 0u);
+                   ctx->d_qual.as<uint8_t>());
+        }
     }
     UP(ctx->d_cigar, R->cigar, R->n_cigar_words, uint32_t);
     UP(ctx->d_loci_ref, Lc->ref_id, nl, int32_t); UP(ctx->d_loci_pos, Lc->pos0, nl, int32_t); UP(ctx->d_loci_base, Lc->ref_base, nl, uint8_t);
@@ -590,6 +595,9 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
         CK(ctx->d_seq.ensure((size_t)R->seq_bytes + 16)); CK(qual_up.ensure((size_t)R->qual_bytes + 16));
         auto chunk_bytes = [&](int64_t total) { int64_t c = (total + G - 1) / G; c = (c + 255) & ~255ll; return (uint32_t)std::max<int64_t>(c, 256); };
         ctx->pipe_seq_chunk = chunk_bytes(R->seq_bytes); ctx->pipe_qual_chunk = chunk_bytes(R->qual_bytes);
+        if (qbits != 8)            // which reads each chunk completes (the compact payload is in read order)
+            LAUNCH(k_chunk_reads, 1, 32, 0, ctx->d_qual_poff.as<uint32_t>(), n, (uint32_t)R->qual_bytes, ctx->pipe_qual_chunk, G,
+                   ctx->d_small.as<uint32_t>() + SW_CHUNK_READS);
         CK(cudaEventRecord(ctx->ev_scal, ctx->st));
         CK(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_scal, 0));
         for (int c = 0; c < G; ++c) {
@@ -886,9 +894,9 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
                 for (int c = 0; c < ctx->pipe_n; ++c) {
                     CK(cudaStreamWaitEvent(ctx->st, ctx->ev_chunk[c], 0));
                     if (ctx->qual_bits != 8 && attempt == 0)        // the reads completed by this chunk: compact qualities -> bytes
-                        LAUNCH(k_unpack_qual, nblk(ctx->n_reads * 32, 256), 256, 0, ctx->n_reads, ctx->d_qual_poff.as<uint32_t>(), ctx->d_qual_off.as<int64_t>(),
+                        LAUNCH(k_unpack_qual, 148u * 8u, 256, 0, small + SW_CHUNK_READS + c, ctx->d_qual_poff.as<uint32_t>(), ctx->d_qual_off.as<int64_t>(),
                                ctx->d_lseq.as<int32_t>(), ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr, ctx->qual_bits, ctx->d_qual_lut.as<uint8_t>(),
-                               ctx->d_qual_packed.as<uint8_t>(), ctx->d_qual.as<uint8_t>(), ctx->inv_ptr, ctx->d_pipe_need.as<uint8_t>(), (uint32_t)c);
+                               ctx->d_qual_packed.as<uint8_t>(), ctx->d_qual.as<uint8_t>());
                     const uint32_t u1 = ctx->pipe_end[c];
                     if (u1 <= u0) continue;
                     A.unit0 = B.unit0 = u0; A.n_units = B.n_units = u1;

@@ -230,23 +230,40 @@ __global__ void __launch_bounds__(256) k_widen_u16(const uint16_t* __restrict__ 
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r < n) out[r] = (int32_t)in[r];
 }
-// compact qualities (smc_reads_soa::qual_bits 4 / 2) -> one phred byte per stored base, one warp per read.  `need` / `inv` /
-// `chunk` (pipelined upload): only the reads whose last byte arrives with chunk `chunk`.
+// compact qualities (smc_reads_soa::qual_bits 4 / 2) -> one phred byte per stored base, one warp per read over the reads
+// [range[0], range[1]) (grid-stride).  Pipelined upload: the compact payload is stored in read order, so the reads whose last
+// byte arrives with chunk c are a contiguous range; k_chunk_reads finds the range borders by binary search over the offsets.
+__global__ void k_chunk_reads(const uint32_t* __restrict__ poff, int64_t n, uint32_t total_bytes, uint32_t chunk_bytes, int n_chunks,
+                              uint32_t* __restrict__ first) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_chunks) return;
+    // first[c] = first read whose LAST byte lies in chunk >= c, i.e. whose end offset exceeds c * chunk_bytes
+    // (end offset of read r = poff[r + 1], or total_bytes for the last read); first[n_chunks] = n
+    int64_t lo = 0, hi = n;
+    const uint64_t lim = (uint64_t)c * chunk_bytes;
+    if (c == n_chunks) lo = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const uint64_t end = mid + 1 < n ? poff[mid + 1] : total_bytes;
+        if (end <= lim) lo = mid + 1; else hi = mid;
+    }
+    first[c] = (uint32_t)lo;
+}
 __global__ void __launch_bounds__(256)
-k_unpack_qual(int64_t n, const uint32_t* __restrict__ poff, const int64_t* __restrict__ uoff, const int32_t* __restrict__ l_seq,
+k_unpack_qual(const uint32_t* __restrict__ range, const uint32_t* __restrict__ poff, const int64_t* __restrict__ uoff, const int32_t* __restrict__ l_seq,
               const int32_t* __restrict__ store_len, int qbits, const uint8_t* __restrict__ lut16, const uint8_t* __restrict__ packed,
-              uint8_t* __restrict__ out, const uint32_t* __restrict__ inv, const uint8_t* __restrict__ need, uint32_t chunk) {
-    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+              uint8_t* __restrict__ out) {
     const int lane = threadIdx.x & 31;
-    if (r >= n) return;
-    if (need && need[inv[r]] != chunk) return;
-    const int len = max(store_len ? store_len[r] : l_seq[r], 0);
-    const uint8_t* src = packed + poff[r];
-    uint8_t* dst = out + uoff[r];
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t mask = (1u << qbits) - 1u;
-    for (int i = lane; i < len; i += 32) {
-        const uint32_t bit = (uint32_t)i * (uint32_t)qbits;
-        dst[i] = __ldg(&lut16[(__ldg(&src[bit >> 3]) >> (bit & 7u)) & mask]);
+    for (int64_t r = (int64_t)range[0] + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < (int64_t)range[1]; r += warps) {
+        const int len = max(store_len ? store_len[r] : l_seq[r], 0);
+        const uint8_t* src = packed + poff[r];
+        uint8_t* dst = out + uoff[r];
+        for (int i = lane; i < len; i += 32) {
+            const uint32_t bit = (uint32_t)i * (uint32_t)qbits;
+            dst[i] = __ldg(&lut16[(__ldg(&src[bit >> 3]) >> (bit & 7u)) & mask]);
+        }
     }
 }
 __global__ void __launch_bounds__(256) k_widen_u32(const uint32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {

@@ -123,6 +123,38 @@ def plan_batches(locator: ReadLocator, intervals, idxs, max_payload_bytes: int =
     return batches
 
 
+def split_long_intervals(intervals, locator: ReadLocator | None = None, max_loci: int = 1 << 20, max_payload_bytes: int = 1 << 30,
+                         max_reads: int = 1 << 27):
+    """BED intervals no single one of which exceeds the per-batch limits: an interval with more positions than ``max_loci`` (a
+    whole-chromosome line), or -- when a ``locator`` over coordinate-sorted reads is given -- with more overlapping reads than
+    a batch may carry, is cut into consecutive sub-intervals (halved until each piece fits or is one position wide).  The
+    reference takes any interval size (it works per position, smCounter.py:675-680); rows are per position, so the pieces'
+    rows concatenate to the interval's."""
+    per_read = 0.0
+    if locator is not None and locator.reads.n:
+        per_read = float(locator.reads.seq.nbytes + locator.reads.qual.nbytes) / locator.reads.n
+
+    def too_big(c, s, e):
+        if e - s > max_loci:
+            return True
+        if locator is None or not locator.sorted or e - s <= 1:
+            return False
+        cnt = locator.count_upper(c, s, e)
+        return cnt > max_reads or cnt * per_read > max_payload_bytes
+
+    out = []
+    stack = list(reversed([tuple(iv) for iv in intervals]))
+    while stack:
+        c, s, e = stack.pop()
+        if e - s > 1 and too_big(c, s, e):
+            m = (s + e) // 2
+            stack.append((c, m, e))
+            stack.append((c, s, m))
+        else:
+            out.append((c, s, e))
+    return out
+
+
 def subset_loci(loci: Loci, intervals, chroms):
     """Indices (into ``loci``) of the unique loci that fall inside ``intervals``."""
     cidx = {c: i for i, c in enumerate(chroms)}

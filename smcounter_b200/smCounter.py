@@ -30,7 +30,7 @@ from .caller import GpuCaller, UmiKeep, VcParams
 from .downsample import draw_keep_masks
 from .fasta import FastaFile
 from .rows import device_hp_flags, emit_rows, headerAll, headerVariants
-from .shard import ReadLocator, plan_batches, plan_shards
+from .shard import ReadLocator, plan_batches, plan_shards, split_long_intervals
 from .targets import build_loci, intervals_from_bed_lines
 
 parser = None
@@ -71,10 +71,18 @@ def _run_shards(reads, intervals, refs, prm: VcParams, gpus, devices, stage_time
     import time
     chroms = reads.chroms
     devices = list(devices) if devices is not None else list(range(max(1, gpus)))
+    locator = ReadLocator(reads, chroms)
+    # an interval above the library's per-batch limits (a whole-chromosome BED line, a very deep amplicon) is processed as
+    # consecutive sub-intervals; the callers below see one entry per ORIGINAL interval again
+    lim = dict(batch_limits or {})
+    pieces = split_long_intervals(intervals, locator, max_loci=lim.get("max_loci", 1 << 20), max_payload_bytes=lim.get("max_payload_bytes", 1 << 30),
+                                  max_reads=lim.get("max_reads", 1 << 27))
+    if len(pieces) != len(intervals):
+        sub = _run_shards(reads, pieces, refs, prm, gpus, devices, stage_times, batch_limits, emit_kw)
+        return _regroup_pieces(intervals, pieces, sub)
     plan = plan_shards(reads, intervals, chroms, len(devices))
     per_interval = {}
     errors = [None] * len(plan)
-    locator = ReadLocator(reads, chroms)
     lock = threading.Lock()
 
     def work(g):
@@ -134,6 +142,47 @@ def _run_shards(reads, intervals, refs, prm: VcParams, gpus, devices, stage_time
         if e is not None:
             raise e
     return per_interval
+
+
+class _Joined:
+    """Rows of several consecutive pieces of one BED interval, presented like one EmittedRows."""
+
+    def __init__(self, parts):
+        self.parts = parts                                   # [(EmittedRows, r0, r1)]
+
+    def rows(self):
+        out = []
+        for em, r0, r1 in self.parts:
+            out.extend(em.rows()[r0:r1])
+        return out
+
+    def slices(self, r0, r1):
+        assert r0 == 0
+        cols = ([], [], [])
+        for em, a, b in self.parts:
+            for dst, piece in zip(cols, em.slices(a, b)):
+                dst.append(piece)
+        return tuple(b"".join(c) for c in cols)
+
+
+def _regroup_pieces(intervals, pieces, sub):
+    """{piece index: rows} -> {original interval index: rows}: the pieces of an interval are consecutive and tile it."""
+    out, j = {}, 0
+    for k, (c, s, e) in enumerate(intervals):
+        parts, pos = [], s
+        while j < len(pieces) and pieces[j][0] == c and pieces[j][1] == pos and pieces[j][2] <= e and pos < e:
+            if j in sub:
+                parts.append(sub[j])
+            pos = pieces[j][2]
+            j += 1
+        if e <= s and j < len(pieces) and pieces[j] == (c, s, e):
+            j += 1
+        if len(parts) == 1:
+            out[k] = parts[0]
+        elif parts:
+            n = sum(r1 - r0 for (_, r0, r1) in parts)
+            out[k] = (_Joined(parts), 0, n)
+    return out
 
 
 def call_loci(reads, intervals, refs, prm: VcParams, gpus: int = 1, devices=None, stage_times: dict | None = None,

@@ -266,6 +266,11 @@ def test_call_loci_across_all_visible_gpus():
     devices = list(range(ndev)) if ndev > 1 else [0, 0]
     many = call_loci(soa.trim_to_targets(ivs), ivs, refs, prm, gpus=len(devices), devices=devices)
     assert many == one and len(one) == sum(e - s for (_, s, e) in ivs)
+    # intervals larger than the per-batch limits (here: 25 loci; in production a whole-chromosome BED line or a very deep
+    # amplicon) are cut into consecutive sub-intervals and streamed; rows unchanged
+    st = {}
+    assert call_loci(soa, ivs, refs, prm, gpus=1, batch_limits={"max_loci": 25}, stage_times=st) == one
+    assert st["batches"] > len(ivs)
 
 
 def test_cfg4_indel_and_repeat_heavy_panel_through_the_cli(tmp_path):
