@@ -229,10 +229,12 @@ k_rank_scan(const uint64_t* __restrict__ key_sorted, int frag_bits, int64_t n, c
         if (i < w) woff += t;
         blk += t;
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         const unsigned long long prefix = lb_resolve(desc, tile, blk);
-        s_prefix = prefix;
-        if (tile == gridDim.x - 1) *n_umi_out = (uint32_t)((prefix + blk) >> 31);
+        if (threadIdx.x == 0) {
+            s_prefix = prefix;
+            if (tile == gridDim.x - 1) *n_umi_out = (uint32_t)((prefix + blk) >> 31);
+        }
     }
     __syncthreads();
     unsigned long long run = s_prefix + woff + incl - tsum;            // exclusive counts before the thread's first read
@@ -259,25 +261,30 @@ k_expand_scan(const ReadRec* __restrict__ recs, int64_t n, uint64_t* __restrict_
     if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-    uint32_t t0[SCAN_ITEMS], cnt[SCAN_ITEMS], tsum = 0;
+    const int w = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    // a warp owns 256 consecutive reads as SCAN_ITEMS rows of 32: lanes hold consecutive reads, so that the event writes of a row
+    // land next to each other
+    const int64_t wbase = (int64_t)tile * SCAN_TILE + (int64_t)w * (32 * SCAN_ITEMS);
+    uint32_t t0[SCAN_ITEMS], cnt[SCAN_ITEMS], off[SCAN_ITEMS], run = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
+        const int64_t r = wbase + i * 32 + lane;
         t0[i] = 0; cnt[i] = 0;
-        if (base + i < n) {
-            const int32_t lo = recs[base + i].lo, hi = recs[base + i].hi;
+        if (r < n) {
+            const int32_t lo = recs[r].lo, hi = recs[r].hi;
             if (hi > lo) { t0[i] = (uint32_t)lo >> 5; cnt[i] = ((uint32_t)(hi - 1) >> 5) - t0[i] + 1u; }
         }
-        tsum += cnt[i];
-    }
-    uint32_t incl = tsum;
+        uint32_t incl = cnt[i];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(FULL_MASK, incl, d);
-        if (lane_id() >= (uint32_t)d) incl += t;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
+        }
+        off[i] = run + incl - cnt[i];                         // exclusive offset inside the warp's 256 reads
+        run += __shfl_sync(FULL_MASK, incl, 31);
     }
-    const int w = threadIdx.x >> 5;
-    if (lane_id() == 31) warp_tot[w] = incl;
+    if (lane == 0) warp_tot[w] = run;
     __syncthreads();
     uint32_t woff = 0, blk = 0;
 #pragma unroll
@@ -286,17 +293,22 @@ k_expand_scan(const ReadRec* __restrict__ recs, int64_t n, uint64_t* __restrict_
         if (i < w) woff += t;
         blk += t;
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         const uint32_t prefix = (uint32_t)lb_resolve(desc, tile, blk);
-        s_prefix = prefix;
-        if (tile == gridDim.x - 1) *total = prefix + blk;
+        if (threadIdx.x == 0) {
+            s_prefix = prefix;
+            if (tile == gridDim.x - 1) *total = prefix + blk;
+        }
     }
     __syncthreads();
-    uint32_t o = s_prefix + woff + incl - tsum;
+    const uint32_t base_o = s_prefix + woff;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i)
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        uint32_t o = base_o + off[i];
+        const uint32_t sidx = (uint32_t)(wbase + i * 32 + lane);
         for (uint32_t t = 0; t < cnt[i]; ++t, ++o)
-            if (o < cap) { ev_key[o] = t0[i] + t; ev_val[o] = (uint32_t)(base + i); }
+            if (o < cap) { ev_key[o] = t0[i] + t; ev_val[o] = sidx; }
+    }
 }
 // first event of every tile in the tile-sorted event list, and the number of warp units of the tile
 __global__ void k_tile_offsets(const uint64_t* ev_key, int64_t ne, uint32_t n_tiles, uint32_t chunk, uint32_t* tile_off, uint32_t* unit_cnt) {
@@ -643,10 +655,10 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
         CK(ctx->d_scan.ensure((size_t)std::max<int64_t>(radix_scan_words(n), scan_scratch_words(n + 1)) * 4 + 1024));
         uint64_t* k0 = ctx->d_k0.as<uint64_t>(); uint64_t* k1 = ctx->d_k1.as<uint64_t>();
         uint32_t* v0 = ctx->d_v0.as<uint32_t>(); uint32_t* v1 = ctx->d_v1.as<uint32_t>();
-        // barcode table of >= 1.34 n slots (a batch has far fewer distinct barcodes than reads) and dense fragment ids < n:
+        // barcode table of >= 1.1 n slots (a batch has far fewer distinct barcodes than reads) and dense fragment ids < n:
         // a 2.9 M read panel batch sorts on 22 + 22 = 44 key bits = four 11-bit passes
         int slot_bits = 4;
-        while ((double)(1ll << slot_bits) < 1.34 * (double)n) ++slot_bits;
+        while ((double)(1ll << slot_bits) < 1.1 * (double)n) ++slot_bits;
         int frag_bits = 1;                                             // frag_id < 2^frag_bits; checked below (the contract says
         while ((1ll << frag_bits) < n) ++frag_bits;                    // ids are dense, first-appearance numbers, hence < n_reads)
         frag_bits_used = frag_bits;
@@ -955,7 +967,7 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
     uint32_t n_tasks_h = 0;
     unsigned long long cvgsum = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        if (ctx->task_cap == 0) ctx->task_cap = 1u << 16;
+        if (ctx->task_cap == 0) ctx->task_cap = 1u << 13;
         CK(ctx->d_tasks.ensure((size_t)ctx->task_cap * sizeof(FisherTask)));
         CK(cudaMemsetAsync(small + SW_N_TASKS, 0, 4, ctx->st));
         K4Args B{};
@@ -973,7 +985,7 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
         LAUNCH(k_call, nblk(nl, 128), 128, 0, B);
         // k_fisher reads the task count on the device: launched for the whole task buffer (idle threads leave at once), so
         // that no host round trip sits between the two kernels; an overflowing task list is noticed at the final sync
-        LAUNCH(k_fisher, nblk(ctx->task_cap, 128), 128, 0, ctx->d_tasks.as<FisherTask>(), small + SW_N_TASKS, ctx->task_cap, nl, (int)ctx->prm.fisherLegacy,
+        LAUNCH(k_fisher, nblk((int64_t)ctx->task_cap * 32, 128), 128, 0, ctx->d_tasks.as<FisherTask>(), small + SW_N_TASKS, ctx->task_cap, nl, (int)ctx->prm.fisherLegacy,
                ctx->d_fp.as<double>(), ctx->d_for.as<double>(), ctx->d_fl1.as<uint32_t>(), ctx->d_fl2.as<uint32_t>());
         CK(cudaMemsetAsync(small + SW_CVG_SUM, 0, 8, ctx->st));
         LAUNCH(k_sum_cvg, std::min<unsigned>(nblk(nl, 256), 592u), 256, 0, ctx->d_loc.as<int32_t>() + (size_t)SMC_L_CVG * nl, nl,
@@ -1138,7 +1150,7 @@ extern "C" int smc_fisher_exact(smc_ctx* ctx, int64_t n, const int32_t* tables, 
     CK(ctx->d_hp_bases.ensure((size_t)n * 16)); CK(ctx->d_hp_meta.ensure((size_t)n * 16));      // the candidate buffers double as scratch
     CK(cudaMemcpyAsync(ctx->d_hp_bases.p, tables, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->st));
     double* dp = ctx->d_hp_meta.as<double>();
-    k_fisher_tables<<<nblk(n, 128), 128, 0, ctx->st>>>(ctx->d_hp_bases.as<int32_t>(), n, (int)ctx->prm.fisherLegacy, dp, dp + n);
+    k_fisher_tables<<<nblk(n * 32, 128), 128, 0, ctx->st>>>(ctx->d_hp_bases.as<int32_t>(), n, (int)ctx->prm.fisherLegacy, dp, dp + n);
     CK(cudaMemcpyAsync(p_out, dp, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(or_out, dp + n, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));

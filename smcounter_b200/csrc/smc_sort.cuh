@@ -59,18 +59,28 @@ k_scan_tile(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* sums) {   //
 #define LB_VAL  ((1ull << 62) - 1ull)
 
 __device__ __forceinline__ unsigned long long lb_resolve(unsigned long long* desc, uint32_t tile, unsigned long long agg) {
-    // called by one thread of the tile; returns the exclusive prefix of the tile and publishes its inclusive prefix
+    // called by ALL 32 lanes of one warp of the tile (converged); returns the exclusive prefix of the tile (same value in every lane)
+    // and publishes its inclusive prefix.  The warp looks back 32 descriptors at a time: lane k reads tile - 1 - k (- 32 per round).
+    const uint32_t lane = lane_id();
     unsigned long long prefix = 0;
     if (tile > 0) {
-        atomicExch(&desc[tile], LB_AGG | agg);
-        for (int64_t t = (int64_t)tile - 1;; --t) {
-            unsigned long long d;
-            do { d = *reinterpret_cast<volatile unsigned long long*>(&desc[t]); } while ((d >> 62) == 0ull);
-            prefix += d & LB_VAL;
-            if ((d >> 62) == 2ull) break;
+        if (lane == 0) atomicExch(&desc[tile], LB_AGG | agg);
+        int64_t t0 = (int64_t)tile - 1;
+        for (;;) {
+            const int64_t t = t0 - lane;
+            unsigned long long d = LB_INCL;                                  // before tile 0: an inclusive prefix of 0
+            if (t >= 0) { do { d = *reinterpret_cast<volatile unsigned long long*>(&desc[t]); } while ((d >> 62) == 0ull); }
+            const uint32_t incl = __ballot_sync(FULL_MASK, (d >> 62) == 2ull);
+            const int stop = incl ? __ffs((int)incl) - 1 : 31;               // nearest descriptor that already holds a prefix
+            unsigned long long v = (int)lane <= stop ? (d & LB_VAL) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+            prefix += v;
+            if (incl) break;
+            t0 -= 32;
         }
     }
-    atomicExch(&desc[tile], LB_INCL | (prefix + agg));
+    if (lane == 0) atomicExch(&desc[tile], LB_INCL | (prefix + agg));
     return prefix;
 }
 
@@ -105,10 +115,12 @@ k_scan_lb(const uint32_t* in, uint32_t* out, int64_t n, unsigned long long* desc
         if (i < w) woff += t;
         blk += t;
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         const uint32_t prefix = (uint32_t)lb_resolve(desc, tile, blk);
-        s_prefix = prefix;
-        if (total && tile == gridDim.x - 1) *total = prefix + blk;
+        if (threadIdx.x == 0) {
+            s_prefix = prefix;
+            if (total && tile == gridDim.x - 1) *total = prefix + blk;
+        }
     }
     __syncthreads();
     uint32_t run = s_prefix + woff + incl - tsum;
