@@ -489,15 +489,21 @@ def main():
     # ---------------- end to end: host buffers in, host buffers out, every step: smc_call_batch (pipelined upload, kernels,
     # download) and the device HP / LowC pass over the candidates of the batch (smc_hp_lowcomp)
     caller = GpuCaller(prm, device=local_rank)
+    hp_caller = GpuCaller(prm, device=local_rank)      # as in smCounter._run_shards: the HP / LowC pass of batch k runs on a worker
+    from concurrent.futures import ThreadPoolExecutor   # thread (own context) while the main thread already uploads batch k + 1
+    post = ThreadPoolExecutor(max_workers=1)
 
     def e2e_pass():
         h2d = d2h = 0
         last = None
+        pending = []
         for (_, soa, refs, loci, _, _), out in zip(batches, outs):
             res = caller.call(soa, loci, out=out)
             last = caller.timings()
             h2d += int(last["bytes_h2d"]); d2h += int(last["bytes_d2h"])
-            device_hp_flags(caller, res, soa, loci, soa.chroms, refs, prm.hpLen)
+            pending.append(post.submit(device_hp_flags, hp_caller, res, soa, loci, soa.chroms, refs, prm.hpLen))
+        for f in pending:
+            f.result()
         return h2d, d2h, last
     for _ in range(min(args.warmup, 2)):
         e2e_pass()
@@ -509,7 +515,9 @@ def main():
     e2e_s = time.perf_counter() - t1
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    post.shutdown(wait=True)
     caller.close()
+    hp_caller.close()
 
     def allred(x, op):
         if world == 1:
@@ -572,7 +580,7 @@ def main():
                         "last_batch": {"ms_h2d": e2e_tm["ms_h2d"], "ms_device": e2e_tm["ms_total_device"], "ms_d2h": e2e_tm["ms_d2h"],
                                        "h2d_gbs": e2e_tm["bytes_h2d"] / e2e_tm["ms_h2d"] / 1e6 if e2e_tm["ms_h2d"] > 0 else None},
                         "what": "per step and GPU: %d x (smc_call_batch from pinned host buffers -- scalars first, bases / qualities in %d chunks on a copy "
-                                "stream, %d pileup launch pairs as they arrive -- + download + smc_hp_lowcomp over the batch's candidates)"
+                                "stream, %d pileup launch pairs as they arrive -- + download; smc_hp_lowcomp over the batch's candidates on a worker thread beside the next call)"
                                 % (NB, e2e_tm["pipe_chunks"], e2e_tm["pipe_launches"])},
                 "gpu_launches": int(launches),
                 "stage_ms_per_batch_rank0": {k: v / nrun for k, v in stage.items()},
