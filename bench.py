@@ -50,7 +50,7 @@ WORKLOADS = {
 }
 
 
-def parse_args():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -67,7 +67,7 @@ def parse_args():
     ap.add_argument("--pipeline-intervals", type=int, default=12,
                     help="intervals of the rank-0 batch run through the whole CLI path (BAM decode -> files); 0 = skip")
     ap.add_argument("--pipeline-repeats", type=int, default=5)
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     if a.intervals <= 0:
         a.intervals = WORKLOADS[a.workload][3]
     return a
@@ -111,7 +111,8 @@ def _gen_batch(job):
     if not whole:
         soa = soa.trim_to_targets(ivs)
         if not no_compact:
-            soa = soa.compact()                         # 16-bit scalars, 2- / 4-bit quality codes + codebook (expanded on the device)
+            # 16-bit scalars, 2- / 4-bit quality codes + codebook, 2-bit bases + exception list (expanded on the device)
+            soa = soa.compact(seq_bits_wanted=int(os.environ.get("SMC_BENCH_SEQ_BITS", "2")))
     loci, bed_order = build_loci(ivs, soa.chroms, refs)
     return ivs, soa, refs, loci, bed_order, (full if keep_full else None)
 
@@ -440,6 +441,8 @@ def main():
         for f in ("store_lo", "store_len", "qual_lut"):
             if getattr(soa, f) is not None:
                 setattr(soa, f, pin(getattr(soa, f)))
+        if soa.seq_exc is not None:
+            soa.seq_exc = tuple(pin(a) for a in soa.seq_exc)
         for f in ("ref_id", "pos0", "ref_base"):
             setattr(loci, f, pin(getattr(loci, f)))
 
@@ -488,36 +491,56 @@ def main():
 
     # ---------------- end to end: host buffers in, host buffers out, every step: smc_call_batch (pipelined upload, kernels,
     # download) and the device HP / LowC pass over the candidates of the batch (smc_hp_lowcomp)
-    caller = GpuCaller(prm, device=local_rank)
-    hp_caller = GpuCaller(prm, device=local_rank)      # as in smCounter._run_shards: the HP / LowC pass of batch k runs on a worker
-    from concurrent.futures import ThreadPoolExecutor   # thread (own context) while the main thread already uploads batch k + 1
-    post = ThreadPoolExecutor(max_workers=1)
+    # As smCounter._run_shards does: two contexts and two host threads per GPU, so that one batch uploads while the previous one
+    # computes and downloads (ctypes drops the GIL inside the library).
+    import queue
+    from concurrent.futures import ThreadPoolExecutor
+    n_ctx = min(int(os.environ.get("SMC_CTX_PER_GPU", "2")), NB)
+    callers = [GpuCaller(prm, device=local_rank) for _ in range(n_ctx)]
+    free = queue.SimpleQueue()
+    for i in range(n_ctx):
+        free.put(i)
+    pool = ThreadPoolExecutor(max_workers=n_ctx)
 
-    def e2e_pass():
-        h2d = d2h = 0
-        last = None
-        pending = []
-        for (_, soa, refs, loci, _, _), out in zip(batches, outs):
-            res = caller.call(soa, loci, out=out)
-            last = caller.timings()
-            h2d += int(last["bytes_h2d"]); d2h += int(last["bytes_d2h"])
-            pending.append(post.submit(device_hp_flags, hp_caller, res, soa, loci, soa.chroms, refs, prm.hpLen))
-        for f in pending:
-            f.result()
-        return h2d, d2h, last
-    for _ in range(min(args.warmup, 2)):
-        e2e_pass()
+    host_tl = [] if os.environ.get("SMC_TIMELINE") else None      # debugging: host-side stamps of every e2e batch
+
+    def e2e_batch(k):
+        (_, soa, refs, loci, _, _), out = batches[k], outs[k]
+        t_a = time.perf_counter()
+        i = free.get()
+        try:
+            t_b = time.perf_counter()
+            res = callers[i].call(soa, loci, out=out)
+            t_c = time.perf_counter()
+            tm = callers[i].timings()
+            device_hp_flags(callers[i], res, soa, loci, soa.chroms, refs, prm.hpLen)
+            if host_tl is not None:
+                host_tl.append((k, i, t_a, t_b, t_c, time.perf_counter()))
+            return tm
+        finally:
+            free.put(i)
+
+    def e2e_pass(steps):
+        # the batches of all the steps go through the two contexts as one stream, the way a long job's shards do
+        # (smCounter._run_shards): no barrier between steps, so a batch uploads while the one before it computes
+        tms = list(pool.map(e2e_batch, [k % NB for k in range(steps * NB)]))
+        last = tms[-NB:]
+        return sum(int(t["bytes_h2d"]) for t in last), sum(int(t["bytes_d2h"]) for t in last), tms[-1]
+    e2e_pass(min(args.warmup, 2))
     barrier()
     t1 = time.perf_counter()
-    for _ in range(args.steps):
-        h2d_b, d2h_b, e2e_tm = e2e_pass()
+    h2d_b, d2h_b, e2e_tm = e2e_pass(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t1
+    if host_tl:
+        for (k, i, t_a, t_b, t_c, t_d) in host_tl[-3 * NB:]:
+            print("[bench timeline] batch %d ctx %d: task %.2f got ctx %.2f call done %.2f hp flags done %.2f (ms since the timed region began)"
+                  % (k, i, 1e3 * (t_a - t1), 1e3 * (t_b - t1), 1e3 * (t_c - t1), 1e3 * (t_d - t1)), file=sys.stderr)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    post.shutdown(wait=True)
-    caller.close()
-    hp_caller.close()
+    pool.shutdown(wait=True)
+    for c in callers:
+        c.close()
 
     def allred(x, op):
         if world == 1:
@@ -572,7 +595,7 @@ def main():
                                    "tile_events_per_step_rank0": int(tile_events_rank), "resident_mb_rank0": sum(b[1].nbytes() for b in batches) / 1e6,
                                    "reads": "whole reads" if soa0.store_lo is None else "bases / qualities trimmed to each read's target window (store_lo / store_len), "
                                             "%.0f of %d bases per read stored" % (float(soa0.store_len.mean()), int(soa0.l_seq.max())) +
-                                            ("; compact upload: %d-bit scalars, %d-bit quality codes" % (soa0.scalar_bits, soa0.qual_bits)
+                                            ("; compact upload: %d-bit scalars, %d-bit quality codes, %d-bit bases" % (soa0.scalar_bits, soa0.qual_bits, soa0.seq_bits)
                                              if soa0.scalar_bits != 32 or soa0.qual_bits != 8 else ""),
                                    "host_affinity": ("GPU-local cores (%d) while pinning and uploading" % numa) if numa else "unbound"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
@@ -580,7 +603,7 @@ def main():
                         "last_batch": {"ms_h2d": e2e_tm["ms_h2d"], "ms_device": e2e_tm["ms_total_device"], "ms_d2h": e2e_tm["ms_d2h"],
                                        "h2d_gbs": e2e_tm["bytes_h2d"] / e2e_tm["ms_h2d"] / 1e6 if e2e_tm["ms_h2d"] > 0 else None},
                         "what": "per step and GPU: %d x (smc_call_batch from pinned host buffers -- scalars first, bases / qualities in %d chunks on a copy "
-                                "stream, %d pileup launch pairs as they arrive -- + download; smc_hp_lowcomp over the batch's candidates on a worker thread beside the next call)"
+                                "stream, %d pileup launch pairs as they arrive -- + download + smc_hp_lowcomp over the batch's candidates); two contexts / host threads, so the next batch uploads while this one computes"
                                 % (NB, e2e_tm["pipe_chunks"], e2e_tm["pipe_launches"])},
                 "gpu_launches": int(launches),
                 "stage_ms_per_batch_rank0": {k: v / nrun for k, v in stage.items()},

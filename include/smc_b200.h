@@ -100,6 +100,16 @@ typedef struct smc_reads_soa {
     int32_t         scalar_bits;
     int32_t         qual_bits;
     const uint8_t  *qual_lut;
+    /*   seq_bits 2: seq[] holds 2-bit base codes A0 C1 G2 T3, four bases per byte, low bits first, every read starting on a byte
+     *     boundary ((stored bases + 3) / 4 bytes per read, seq_bytes = their sum).  A base that is not A/C/G/T carries code 0 and
+     *     is listed in the exception arrays (ascending read index; position = index of the base inside the read's stored
+     *     window; its BAM nibble).  Requires the packed layout (seq_off == NULL).  0 or 4 = BAM nibbles as above. */
+    int32_t         seq_bits;
+    int32_t         reserved1;
+    int64_t         n_seq_exc;
+    const uint32_t *seq_exc_read;
+    const uint32_t *seq_exc_pos;
+    const uint8_t  *seq_exc_nib;
 } smc_reads_soa;
 
 /* Target loci: unique, sorted by (ref_id, pos0).  At most 4 194 302 per batch. */

@@ -36,7 +36,9 @@ class smc_reads_soa(C.Structure):
                 ("l_seq", _vp), ("seq_off", _vp), ("qual_off", _vp), ("cigar_off", _vp), ("n_cigar", _vp), ("umi", _vp),
                 ("frag_id", _vp), ("seq", _vp), ("seq_bytes", C.c_int64), ("qual", _vp), ("qual_bytes", C.c_int64),
                 ("cigar", _vp), ("n_cigar_words", C.c_int64), ("store_lo", _vp), ("store_len", _vp),
-                ("scalar_bits", C.c_int32), ("qual_bits", C.c_int32), ("qual_lut", _vp)]
+                ("scalar_bits", C.c_int32), ("qual_bits", C.c_int32), ("qual_lut", _vp),
+                ("seq_bits", C.c_int32), ("reserved1", C.c_int32), ("n_seq_exc", C.c_int64), ("seq_exc_read", _vp), ("seq_exc_pos", _vp),
+                ("seq_exc_nib", _vp)]
 
 
 class smc_loci(C.Structure):

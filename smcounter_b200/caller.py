@@ -164,8 +164,12 @@ class GpuCaller:
         s.store_lo, s.store_len = p(getattr(r, "store_lo", None)), p(getattr(r, "store_len", None))
         s.scalar_bits, s.qual_bits = int(getattr(r, "scalar_bits", 32)), int(getattr(r, "qual_bits", 8))
         s.qual_lut = p(getattr(r, "qual_lut", None))
-        if s.qual_bits != 8 and not getattr(r, "packed", False):
-            raise ValueError("compact qualities need the packed layout")
+        s.seq_bits = int(getattr(r, "seq_bits", 4))
+        exc = getattr(r, "seq_exc", None)
+        if s.seq_bits == 2 and exc is not None and len(exc[0]):
+            s.n_seq_exc, s.seq_exc_read, s.seq_exc_pos, s.seq_exc_nib = len(exc[0]), p(exc[0]), p(exc[1]), p(exc[2])
+        if (s.qual_bits != 8 or s.seq_bits != 4) and not getattr(r, "packed", False):
+            raise ValueError("compact qualities / bases need the packed layout")
         return s
 
     @staticmethod

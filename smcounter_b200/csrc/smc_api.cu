@@ -8,9 +8,12 @@
 //       -> K3b k_merge: per-barcode posterior (calProb), prediction index, consensus    smc_pileup.cuh
 //       -> K4 FP64 statistics: PI, ALT, filters, Fisher                                smc_stats.cuh
 //   -> D2H
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <new>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -30,6 +33,13 @@ struct NvtxRange {
 };
 
 thread_local std::string g_create_error;
+// Contexts of one process that upload to the same GPU take turns on the host link: the chunked copies of a batch start
+// after those of the batch enqueued before it (an event at the tail of each context's copies).  Two copy streams running
+// side by side would each get half the link, finish together and leave the GPU idle until then; in turns, the first
+// batch's kernels start while the second one is still arriving.  SMC_LINK_TURNS=0 switches it off.
+static std::mutex g_link_mu;
+static cudaEvent_t g_link_tail[64] = {};
+static smc_ctx* g_link_owner[64] = {};
 
 // Device scratch, grown lazily.  Stream-ordered allocations from the device's default memory pool (its release threshold
 // is raised in smc_ctx_create): growing a buffer or destroying a context hands the memory back to the pool, not to the
@@ -66,7 +76,8 @@ enum SmallWord {
     SW_PIPE_BLOCKED = 16,    // [SMC_PIPE_MAX]: first unit that has to wait for chunk c + 1
     SW_PACK_TOTALS = 40,     // [4]: bytes / words of packed bases, qualities, CIGARs, compact qualities
     SW_SPILL_COUNT = 48,     // k_merge spill records handed out
-    SW_CHUNK_READS = 64      // [SMC_PIPE_MAX + 2]: first read completed by each upload chunk (compact qualities)
+    SW_CHUNK_READS = 64,     // [SMC_PIPE_MAX + 2]: first read completed by each upload chunk (compact qualities)
+    SW_CHUNK_READS_SEQ = 96  // the same for the compact bases
 };
 
 struct smc_ctx {
@@ -77,7 +88,7 @@ struct smc_ctx {
     cudaEvent_t ev[18]{};
     // pipelined upload of smc_call_batch: bases / qualities arrive in chunks on st_copy while st already computes
     cudaStream_t st_copy = nullptr;
-    cudaEvent_t ev_scal = nullptr, ev_chunk[SMC_PIPE_MAX]{};
+    cudaEvent_t ev_scal = nullptr, ev_link = nullptr, ev_tmp = nullptr, ev_tmp2 = nullptr, ev_chunk[SMC_PIPE_MAX]{};
     int pipe_n = 0;                             // > 1: the chunk events of the current batch are pending / recorded
     uint32_t pipe_seq_chunk = 0, pipe_qual_chunk = 0;   // bytes of bases / qualities per chunk
     DevBuf d_pipe_need;
@@ -90,7 +101,8 @@ struct smc_ctx {
         d_cigar, d_store_lo, d_store_len;
     bool has_store = false;                     // reads carry a stored window (smc_reads_soa::store_lo / store_len)
     int qual_bits = 8;                          // 4 / 2: compact qualities were uploaded (d_qual_packed) and are expanded into d_qual
-    DevBuf d_qual_packed, d_qual_poff, d_qual_lut, d_stage16, d_spill;
+    DevBuf d_qual_packed, d_qual_poff, d_qual_lut, d_stage16, d_spill, d_seq_packed, d_seq_poff, d_exc_read, d_exc_pos, d_exc_nib;
+    int seq_bits = 4; int64_t n_seq_exc = 0;    // 2: compact bases were uploaded (d_seq_packed) and are expanded into d_seq
     uint32_t spill_cap = 0;                     // records in the k_merge spill pool (grows x4 on GF_SPILL_FULL)
     const uint32_t* inv_ptr = nullptr;          // read index -> sorted position (lives in d_v0 or d_v1 after the read sort)
     DevBuf d_loci_ref, d_loci_pos, d_loci_base, d_loci_key;
@@ -139,7 +151,8 @@ static std::vector<DevBuf*> all_bufs(smc_ctx* ctx) {
                       &ctx->d_s_pi, &ctx->d_s_rep_read, &ctx->d_s_rep_qpos, &ctx->d_s_len, &ctx->d_dyn_first, &ctx->d_tasks,
                       &ctx->d_list_idx, &ctx->d_list_count, &ctx->d_list_off, &ctx->d_list_umi, &ctx->d_list_first,
                       &ctx->d_hp_bases, &ctx->d_hp_meta, &ctx->d_hp_flags, &ctx->d_pipe_need, &ctx->d_umi_table,
-                      &ctx->d_qual_packed, &ctx->d_qual_poff, &ctx->d_qual_lut, &ctx->d_stage16, &ctx->d_spill};
+                      &ctx->d_qual_packed, &ctx->d_qual_poff, &ctx->d_qual_lut, &ctx->d_stage16, &ctx->d_spill,
+                      &ctx->d_seq_packed, &ctx->d_seq_poff, &ctx->d_exc_read, &ctx->d_exc_pos, &ctx->d_exc_nib};
 }
 
 #define CK(call)                                                                                         \
@@ -422,6 +435,9 @@ extern "C" int smc_ctx_create(int device, const smc_params* params, smc_ctx** ou
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_scal, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_link, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_tmp, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_tmp2, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     for (auto& ev : ctx->ev_chunk) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     // host-computed tables (glibc pow, the same libm CPython calls): 10^(-bq/10) and the PCR prior
     std::vector<double> bq(256);
@@ -467,6 +483,13 @@ extern "C" void smc_ctx_destroy(smc_ctx* ctx) {
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_chunk) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_scal) cudaEventDestroy(ctx->ev_scal);
+    if (ctx->ev_tmp) cudaEventDestroy(ctx->ev_tmp);
+    if (ctx->ev_tmp2) cudaEventDestroy(ctx->ev_tmp2);
+    if (ctx->ev_link) {
+        std::lock_guard<std::mutex> lk(g_link_mu);
+        if (ctx->device >= 0 && ctx->device < 64 && g_link_owner[ctx->device] == ctx) { g_link_owner[ctx->device] = nullptr; g_link_tail[ctx->device] = nullptr; }
+        cudaEventDestroy(ctx->ev_link);
+    }
     if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
@@ -499,19 +522,47 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
     const int64_t n = R->n_reads, nl = Lc->n_loci;
     const int G = pipelined ? pipe_chunks_for(R) : 1;
     ctx->pipe_n = 0;
-    CK(cudaEventRecord(ctx->ev[0], ctx->st));
+    // A chunked batch sends EVERYTHING over the copy stream, in the order the kernels need it (scalars, CIGARs, loci, then
+    // the chunks of bases / qualities): no copy waits for a kernel, so the link stays busy however long this context's --
+    // or another context's -- kernels queue on the GPU.  The compute stream waits for what it consumes (SYNC_UP).
+    const bool split = pipelined && G > 1;
+    cudaStream_t up_st = split ? ctx->st_copy : ctx->st;
+    static const bool link_turns = [] { const char* ev = getenv("SMC_LINK_TURNS"); return !(ev && atoi(ev) == 0); }();
+    std::unique_lock<std::mutex> link_lock(g_link_mu, std::defer_lock);
+    const int dv = ctx->device;
+    if (split && link_turns && dv >= 0 && dv < 64) {
+        link_lock.lock();
+        if (g_link_tail[dv] && g_link_owner[dv] != ctx) CK(cudaStreamWaitEvent(ctx->st_copy, g_link_tail[dv], 0));
+    }
+    CK(cudaEventRecord(ctx->ev[0], up_st));
     int64_t bytes = 0;
+    bool grew = false;                      // a buffer was (re)allocated on ctx->st since the copy stream last waited for it
+#define ALLOC_SYNC()                                                                                             \
+    do {                                                                                                         \
+        if (split && grew) { CK(cudaEventRecord(ctx->ev_tmp, ctx->st)); CK(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_tmp, 0)); grew = false; } \
+    } while (0)
+#define ENSURE(buf, nbytes)                                                                                      \
+    do { void* before__ = (buf).p; CK((buf).ensure(nbytes)); if ((buf).p != before__) grew = true; } while (0)
+#define SYNC_UP()                                                                                                \
+    do {                                                                                                         \
+        if (split) { CK(cudaEventRecord(ctx->ev_tmp2, ctx->st_copy)); CK(cudaStreamWaitEvent(ctx->st, ctx->ev_tmp2, 0)); } \
+    } while (0)
 #define UP(buf, src, count, T)                                                                                   \
     do {                                                                                                         \
         size_t b__ = (size_t)(count) * sizeof(T);                                                                \
-        CK((buf).ensure(b__ ? b__ : 16));                                                                        \
-        if (b__) { CK(cudaMemcpyAsync((buf).p, (src), b__, cudaMemcpyHostToDevice, ctx->st)); bytes += b__; }     \
+        ENSURE(buf, b__ ? b__ : 16);                                                                             \
+        if (b__) { ALLOC_SYNC(); CK(cudaMemcpyAsync((buf).p, (src), b__, cudaMemcpyHostToDevice, up_st)); bytes += b__; } \
     } while (0)
     if (R->scalar_bits != 0 && R->scalar_bits != 32 && R->scalar_bits != 16) { ctx->err = "smc_upload: scalar_bits must be 0, 16 or 32"; return SMC_E_ARG; }
     if (R->qual_bits != 0 && R->qual_bits != 8 && R->qual_bits != 4 && R->qual_bits != 2) { ctx->err = "smc_upload: qual_bits must be 0, 2, 4 or 8"; return SMC_E_ARG; }
     const bool s16 = R->scalar_bits == 16;
     const int qbits = (R->qual_bits == 4 || R->qual_bits == 2) ? R->qual_bits : 8;
     if (qbits != 8 && (R->qual_off || !R->qual_lut)) { ctx->err = "smc_upload: compact qualities need the packed layout (qual_off == NULL) and a qual_lut"; return SMC_E_ARG; }
+    if (R->seq_bits != 0 && R->seq_bits != 4 && R->seq_bits != 2) { ctx->err = "smc_upload: seq_bits must be 0, 2 or 4"; return SMC_E_ARG; }
+    const int sbits = R->seq_bits == 2 ? 2 : 4;
+    if (sbits == 2 && (R->seq_off || R->n_seq_exc < 0 || (R->n_seq_exc > 0 && (!R->seq_exc_read || !R->seq_exc_pos || !R->seq_exc_nib)))) {
+        ctx->err = "smc_upload: compact bases need the packed layout (seq_off == NULL) and consistent exception arrays"; return SMC_E_ARG;
+    }
     UP(ctx->d_ref_id, R->ref_id, n, int32_t); UP(ctx->d_pos, R->pos, n, int32_t); UP(ctx->d_flag, R->flag, n, uint16_t);
     UP(ctx->d_mapq, R->mapq, n, uint8_t);
     UP(ctx->d_ncig, R->n_cigar, n, uint16_t); UP(ctx->d_umi, R->umi, n, uint64_t); UP(ctx->d_frag, R->frag_id, n, uint32_t);
@@ -524,15 +575,18 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
         // 16-bit scalars: four arrays staged back to back, widened on the device
         const void* src16[4] = {R->nm, R->l_seq, R->store_lo, R->store_len};
         DevBuf* dst32[4] = {&ctx->d_nm, &ctx->d_lseq, &ctx->d_store_lo, &ctx->d_store_len};
-        CK(ctx->d_stage16.ensure((size_t)(n ? n : 1) * 2 * 4));
+        ENSURE(ctx->d_stage16, (size_t)(n ? n : 1) * 2 * 4);
         for (int k = 0; k < (ctx->has_store ? 4 : 2); ++k) {
             uint16_t* st16 = ctx->d_stage16.as<uint16_t>() + (size_t)k * n;
             CK(dst32[k]->ensure((size_t)(n ? n : 1) * 4));
-            if (n) { CK(cudaMemcpyAsync(st16, src16[k], (size_t)n * 2, cudaMemcpyHostToDevice, ctx->st)); bytes += n * 2; }
-            LAUNCH(k_widen_u16, nblk(n, 256), 256, 0, st16, n, dst32[k]->as<int32_t>());
+            if (n) { ALLOC_SYNC(); CK(cudaMemcpyAsync(st16, src16[k], (size_t)n * 2, cudaMemcpyHostToDevice, up_st)); bytes += n * 2; }
         }
+        SYNC_UP();
+        for (int k = 0; k < (ctx->has_store ? 4 : 2); ++k)
+            LAUNCH(k_widen_u16, nblk(n, 256), 256, 0, ctx->d_stage16.as<uint16_t>() + (size_t)k * n, n, dst32[k]->as<int32_t>());
     }
-    ctx->qual_bits = qbits;
+    SYNC_UP();                              // the offsets below are computed from the scalars
+    ctx->qual_bits = qbits; ctx->seq_bits = sbits; ctx->n_seq_exc = sbits == 2 ? R->n_seq_exc : 0;
     // offsets: uploaded, or -- NULL = payload packed in read order -- computed here from l_seq / n_cigar (saves 24 B per read of PCIe)
     ctx->packed_seq = !R->seq_off; ctx->packed_qual = !R->qual_off; ctx->packed_cigar = !R->cigar_off;
     {
@@ -544,8 +598,10 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
             CK(dev_off[kind]->ensure((size_t)(n ? n : 1) * 8));
             CK(ctx->d_v0.ensure((size_t)(n ? n : 1) * 4));
             CK(ctx->d_scan.ensure((size_t)scan_scratch_words(n + 1) * 4 + 1024));
+            // compact payloads are expanded into a device-only layout with every read on a word boundary (k_unpack)
+            const int layout = (kind == 0 && sbits == 2) ? 5 : (kind == 1 && qbits != 8) ? 6 : kind;
             LAUNCH(k_pack_len, nblk(n, 256), 256, 0, ctx->d_lseq.as<int32_t>(), ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr,
-                   ctx->d_ncig.as<uint16_t>(), n, kind, 8, ctx->d_v0.as<uint32_t>());
+                   ctx->d_ncig.as<uint16_t>(), n, layout, 8, ctx->d_v0.as<uint32_t>());
             exclusive_scan_u32(ctx->d_v0.as<uint32_t>(), ctx->d_v0.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + SW_PACK_TOTALS + kind, ctx->st);
             LAUNCH(k_widen_u32, nblk(n, 256), 256, 0, ctx->d_v0.as<uint32_t>(), n, dev_off[kind]->as<int64_t>());
         }
@@ -558,22 +614,54 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
             CK(ctx->d_qual_lut.ensure(16));
             CK(cudaMemcpyAsync(ctx->d_qual_lut.p, R->qual_lut, qbits == 4 ? 16 : 4, cudaMemcpyHostToDevice, ctx->st));
         }
+        if (sbits == 2) {          // byte offsets of the compact bases inside the uploaded array, and their exceptions
+            CK(ctx->d_seq_poff.ensure((size_t)(n ? n : 1) * 4));
+            CK(ctx->d_scan.ensure((size_t)scan_scratch_words(n + 1) * 4 + 1024));
+            LAUNCH(k_pack_len, nblk(n, 256), 256, 0, ctx->d_lseq.as<int32_t>(), ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr,
+                   ctx->d_ncig.as<uint16_t>(), n, 4, 2, ctx->d_seq_poff.as<uint32_t>());
+            exclusive_scan_u32(ctx->d_seq_poff.as<uint32_t>(), ctx->d_seq_poff.as<uint32_t>(), n, ctx->d_scan.as<uint32_t>(), small + SW_PACK_TOTALS + 4, ctx->st);
+            UP(ctx->d_exc_read, R->seq_exc_read, R->n_seq_exc, uint32_t); UP(ctx->d_exc_pos, R->seq_exc_pos, R->n_seq_exc, uint32_t);
+            UP(ctx->d_exc_nib, R->seq_exc_nib, R->n_seq_exc, uint8_t);
+        }
     }
-    // expanded qualities never exceed two per byte of bases (a read stores (len + 1) / 2 bytes of bases)
-    const int64_t qual_dev_bytes = qbits == 8 ? R->qual_bytes : 2 * R->seq_bytes + 16;
+    // expanded payloads: a read stores (len + 1) / 2 bytes of 4-bit bases for (len + 3) / 4 bytes of 2-bit ones, and never more
+    // qualities than two per byte of 4-bit bases; up to 3 bytes of padding per read
+    const int64_t seq_dev_bytes = sbits == 4 ? R->seq_bytes : 2 * R->seq_bytes + 4 * n + 16;
+    const int64_t qual_dev_bytes = qbits == 8 ? R->qual_bytes : 2 * (sbits == 4 ? R->seq_bytes : 2 * R->seq_bytes) + 4 * n + 16;
+    if (seq_dev_bytes >= (1ll << 32) || qual_dev_bytes >= (1ll << 32)) {
+        ctx->err = "smc_upload: the expanded bases / qualities of the batch exceed 4 GiB; split the batch"; return SMC_E_LIMIT;
+    }
+    DevBuf& seq_up = sbits == 4 ? ctx->d_seq : ctx->d_seq_packed;              // where the caller's seq[] bytes land
+    if (sbits == 2) CK(ctx->d_seq.ensure((size_t)seq_dev_bytes + 16));
     DevBuf& qual_up = qbits == 8 ? ctx->d_qual : ctx->d_qual_packed;           // where the caller's qual[] bytes land
     if (qbits != 8) CK(ctx->d_qual.ensure((size_t)qual_dev_bytes + 16));
     if (G == 1) {
-        UP(ctx->d_seq, R->seq, R->seq_bytes, uint8_t); UP(qual_up, R->qual, R->qual_bytes, uint8_t);
+        UP(seq_up, R->seq, R->seq_bytes, uint8_t); UP(qual_up, R->qual, R->qual_bytes, uint8_t);
+        if (sbits == 2) {
+            const uint32_t whole[2] = {0u, (uint32_t)n};
+            CK(cudaMemcpyAsync(ctx->d_small.as<uint32_t>() + SW_CHUNK_READS_SEQ, whole, 8, cudaMemcpyHostToDevice, ctx->st));
+            LAUNCH(k_unpack<2>, std::min<unsigned>(nblk(n, 256) + 1u, 148u * 8u), 256, 0, ctx->d_small.as<uint32_t>() + SW_CHUNK_READS_SEQ,
+                   ctx->d_seq_poff.as<uint32_t>(), ctx->d_seq_off.as<int64_t>(), ctx->d_lseq.as<int32_t>(),
+                   ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr, nullptr, ctx->d_seq_packed.as<uint8_t>(), ctx->d_seq.as<uint8_t>());
+            LAUNCH(k_patch_seq, nblk(ctx->n_seq_exc, 256), 256, 0, ctx->d_small.as<uint32_t>() + SW_CHUNK_READS_SEQ, ctx->n_seq_exc,
+                   ctx->d_exc_read.as<uint32_t>(), ctx->d_exc_pos.as<uint32_t>(), ctx->d_exc_nib.as<uint8_t>(), ctx->d_seq_off.as<int64_t>(),
+                   ctx->d_seq.as<uint8_t>());
+        }
         if (qbits != 8) {
             const uint32_t whole[2] = {0u, (uint32_t)n};
             CK(cudaMemcpyAsync(ctx->d_small.as<uint32_t>() + SW_CHUNK_READS, whole, 8, cudaMemcpyHostToDevice, ctx->st));
-            LAUNCH(k_unpack_qual, std::min<unsigned>(nblk(n * 32, 256), 148u * 16u), 256, 0, ctx->d_small.as<uint32_t>() + SW_CHUNK_READS,
-                   ctx->d_qual_poff.as<uint32_t>(), ctx->d_qual_off.as<int64_t>(), ctx->d_lseq.as<int32_t>(),
-                   ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr, qbits, ctx->d_qual_lut.as<uint8_t>(), ctx->d_qual_packed.as<uint8_t>(),
-                   ctx->d_qual.as<uint8_t>());
+            const unsigned ug = std::min<unsigned>(nblk(n, 256) + 1u, 148u * 8u);
+            if (qbits == 2)
+                LAUNCH(k_unpack<0>, ug, 256, 0, ctx->d_small.as<uint32_t>() + SW_CHUNK_READS, ctx->d_qual_poff.as<uint32_t>(), ctx->d_qual_off.as<int64_t>(),
+                       ctx->d_lseq.as<int32_t>(), ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr, ctx->d_qual_lut.as<uint8_t>(),
+                       ctx->d_qual_packed.as<uint8_t>(), ctx->d_qual.as<uint8_t>());
+            else
+                LAUNCH(k_unpack<1>, ug, 256, 0, ctx->d_small.as<uint32_t>() + SW_CHUNK_READS, ctx->d_qual_poff.as<uint32_t>(), ctx->d_qual_off.as<int64_t>(),
+                       ctx->d_lseq.as<int32_t>(), ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr, ctx->d_qual_lut.as<uint8_t>(),
+                       ctx->d_qual_packed.as<uint8_t>(), ctx->d_qual.as<uint8_t>());
         }
     }
+    if (G == 1) SYNC_UP();
     UP(ctx->d_cigar, R->cigar, R->n_cigar_words, uint32_t);
     UP(ctx->d_loci_ref, Lc->ref_id, nl, int32_t); UP(ctx->d_loci_pos, Lc->pos0, nl, int32_t); UP(ctx->d_loci_base, Lc->ref_base, nl, uint8_t);
     ctx->has_keep = K && K->n_loci > 0;
@@ -581,15 +669,17 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
         UP(ctx->d_keep_off, K->off, K->n_loci + 1, int64_t);
         UP(ctx->d_keep_umi, K->umi, K->off[K->n_loci], uint64_t);
         // d_k0 doubles as the staging buffer of the masked-locus list
-        CK(ctx->d_k0.ensure((size_t)K->n_loci * 8));
-        CK(cudaMemcpyAsync(ctx->d_k0.p, K->locus, (size_t)K->n_loci * 8, cudaMemcpyHostToDevice, ctx->st));
+        ENSURE(ctx->d_k0, (size_t)K->n_loci * 8);
+        ALLOC_SYNC();
+        CK(cudaMemcpyAsync(ctx->d_k0.p, K->locus, (size_t)K->n_loci * 8, cudaMemcpyHostToDevice, up_st));
         bytes += K->n_loci * 8;
+        SYNC_UP();
         CK(ctx->d_keep_idx.ensure((size_t)(nl ? nl : 1) * 4));
         LAUNCH(k_fill_i32, nblk(nl, 256), 256, 0, ctx->d_keep_idx.as<int32_t>(), nl, -1);
         LAUNCH(k_scatter_idx, nblk(K->n_loci, 256), 256, 0, ctx->d_k0.as<int64_t>(), K->n_loci, ctx->d_keep_idx.as<int32_t>());
         ctx->n_keep_loci = K->n_loci;
     }
-#undef UP
+    SYNC_UP();
     CK(ctx->d_loci_key.ensure((size_t)(nl ? nl : 1) * 8));
     LAUNCH(k_loci_keys, nblk(nl, 256), 256, 0, ctx->d_loci_ref.as<int32_t>(), ctx->d_loci_pos.as<int32_t>(), nl, ctx->d_loci_key.as<uint64_t>());
     ctx->n_reads = n; ctx->n_loci = nl;
@@ -604,25 +694,36 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
         }
     } else {
         // the chunks follow the scalars on the link; everything up to the first pileup launch needs the scalars only
-        CK(ctx->d_seq.ensure((size_t)R->seq_bytes + 16)); CK(qual_up.ensure((size_t)R->qual_bytes + 16));
+        ENSURE(seq_up, (size_t)R->seq_bytes + 16); ENSURE(qual_up, (size_t)R->qual_bytes + 16);
         auto chunk_bytes = [&](int64_t total) { int64_t c = (total + G - 1) / G; c = (c + 255) & ~255ll; return (uint32_t)std::max<int64_t>(c, 256); };
         ctx->pipe_seq_chunk = chunk_bytes(R->seq_bytes); ctx->pipe_qual_chunk = chunk_bytes(R->qual_bytes);
         if (qbits != 8)            // which reads each chunk completes (the compact payload is in read order)
             LAUNCH(k_chunk_reads, 1, 32, 0, ctx->d_qual_poff.as<uint32_t>(), n, (uint32_t)R->qual_bytes, ctx->pipe_qual_chunk, G,
                    ctx->d_small.as<uint32_t>() + SW_CHUNK_READS);
-        CK(cudaEventRecord(ctx->ev_scal, ctx->st));
-        CK(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_scal, 0));
+        if (sbits == 2)
+            LAUNCH(k_chunk_reads, 1, 32, 0, ctx->d_seq_poff.as<uint32_t>(), n, (uint32_t)R->seq_bytes, ctx->pipe_seq_chunk, G,
+                   ctx->d_small.as<uint32_t>() + SW_CHUNK_READS_SEQ);
+        grew = true;                        // d_seq / d_qual (the expanded payloads) may have been reallocated above as well
+        ALLOC_SYNC();
         for (int c = 0; c < G; ++c) {
             const int64_t s0 = std::min<int64_t>(R->seq_bytes, (int64_t)c * ctx->pipe_seq_chunk), s1 = std::min<int64_t>(R->seq_bytes, (int64_t)(c + 1) * ctx->pipe_seq_chunk);
             const int64_t q0 = std::min<int64_t>(R->qual_bytes, (int64_t)c * ctx->pipe_qual_chunk), q1 = std::min<int64_t>(R->qual_bytes, (int64_t)(c + 1) * ctx->pipe_qual_chunk);
-            if (s1 > s0) CK(cudaMemcpyAsync(ctx->d_seq.as<uint8_t>() + s0, R->seq + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, ctx->st_copy));
+            if (s1 > s0) CK(cudaMemcpyAsync(seq_up.as<uint8_t>() + s0, R->seq + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, ctx->st_copy));
             if (q1 > q0) CK(cudaMemcpyAsync(qual_up.as<uint8_t>() + q0, R->qual + q0, (size_t)(q1 - q0), cudaMemcpyHostToDevice, ctx->st_copy));
             CK(cudaEventRecord(ctx->ev_chunk[c], ctx->st_copy));
             bytes += (s1 - s0) + (q1 - q0);
         }
         CK(cudaEventRecord(ctx->ev[1], ctx->st_copy));
+        if (link_lock.owns_lock()) {
+            CK(cudaEventRecord(ctx->ev_link, ctx->st_copy));
+            g_link_tail[dv] = ctx->ev_link; g_link_owner[dv] = ctx;
+        }
         ctx->pipe_n = G;
     }
+#undef UP
+#undef SYNC_UP
+#undef ENSURE
+#undef ALLOC_SYNC
     ctx->tm.pipe_chunks = pipelined ? G : 0;
     ctx->tm.bytes_h2d = bytes;
     ctx->uploaded = true;
@@ -704,6 +805,7 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
             P.pipe_need = ctx->d_pipe_need.as<uint8_t>(); P.pipe_n = (uint32_t)ctx->pipe_n;
             P.pipe_seq_chunk = ctx->pipe_seq_chunk; P.pipe_qual_chunk = ctx->pipe_qual_chunk;
             if (ctx->qual_bits != 8) { P.qual_poff = ctx->d_qual_poff.as<uint32_t>(); P.qual_bits = ctx->qual_bits; }
+            if (ctx->seq_bits == 2) P.seq_poff = ctx->d_seq_poff.as<uint32_t>();
         }
         CK(cudaEventRecord(ctx->ev[13], ctx->st));
         LAUNCH(k_read_prep, nblk(n, 256), 256, 0, P);
@@ -721,11 +823,11 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
             LAUNCH(k_expand_scan, (unsigned)nbt, SCAN_THREADS, 0, ctx->d_recs.as<ReadRec>(), n, ctx->d_ek0.as<uint64_t>(), ctx->d_ev0.as<uint32_t>(),
                    (uint32_t)ctx->ne_cap, reinterpret_cast<unsigned long long*>(scr + 2), scr, small + SW_N_TILE_EVENTS);
             if (attempt == 1) break;
-        uint32_t h[2], tot[4];
+        uint32_t h[2], tot[5];
         unsigned long long frag_or = 0;
         CK(cudaMemcpyAsync(&frag_or, small + SW_FRAG_OR, 8, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaMemcpyAsync(h, small + SW_N_TILE_EVENTS, 8, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaMemcpyAsync(tot, small + SW_PACK_TOTALS, 16, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(tot, small + SW_PACK_TOTALS, 20, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         if (h[1] & GF_BAD_READ) { ctx->err = "a read has l_seq or clip length > 65535 (unsupported)"; return SMC_E_LIMIT; }
         if (h[1] & GF_BAD_STORE) {
@@ -734,7 +836,7 @@ extern "C" int smc_run_resident(smc_ctx* ctx) {
             return SMC_E_ARG;
         }
         if (frag_or >> frag_bits_used) { ctx->err = "frag_id must be a dense id (< n_reads), numbered by first appearance"; return SMC_E_ARG; }
-        if ((ctx->packed_seq && (int64_t)tot[0] != ctx->seq_bytes) || (ctx->packed_qual && (int64_t)tot[ctx->qual_bits != 8 ? 3 : 1] != ctx->qual_bytes) ||
+        if ((ctx->packed_seq && (int64_t)tot[ctx->seq_bits == 2 ? 4 : 0] != ctx->seq_bytes) || (ctx->packed_qual && (int64_t)tot[ctx->qual_bits != 8 ? 3 : 1] != ctx->qual_bytes) ||
             (ctx->packed_cigar && (int64_t)tot[2] != ctx->n_cigar_words)) {
             ctx->err = "packed payload (NULL offsets): seq_bytes / qual_bytes / n_cigar_words do not match the sums of (len+1)/2, len, n_cigar (len = store_len or l_seq)";
             return SMC_E_ARG;
@@ -905,10 +1007,23 @@ static int run_pileup_and_stats(smc_ctx* ctx, uint32_t n_tiles, int64_t NE) {
                 ctx->tm.pipe_launches = 0;
                 for (int c = 0; c < ctx->pipe_n; ++c) {
                     CK(cudaStreamWaitEvent(ctx->st, ctx->ev_chunk[c], 0));
-                    if (ctx->qual_bits != 8 && attempt == 0)        // the reads completed by this chunk: compact qualities -> bytes
-                        LAUNCH(k_unpack_qual, 148u * 8u, 256, 0, small + SW_CHUNK_READS + c, ctx->d_qual_poff.as<uint32_t>(), ctx->d_qual_off.as<int64_t>(),
-                               ctx->d_lseq.as<int32_t>(), ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr, ctx->qual_bits, ctx->d_qual_lut.as<uint8_t>(),
-                               ctx->d_qual_packed.as<uint8_t>(), ctx->d_qual.as<uint8_t>());
+                    if (ctx->seq_bits == 2 && attempt == 0) {       // the reads completed by this chunk: compact bases -> nibbles, exceptions
+                        LAUNCH(k_unpack<2>, 148u * 8u, 256, 0, small + SW_CHUNK_READS_SEQ + c, ctx->d_seq_poff.as<uint32_t>(), ctx->d_seq_off.as<int64_t>(),
+                               ctx->d_lseq.as<int32_t>(), ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr, nullptr, ctx->d_seq_packed.as<uint8_t>(),
+                               ctx->d_seq.as<uint8_t>());
+                        LAUNCH(k_patch_seq, nblk(ctx->n_seq_exc, 256), 256, 0, small + SW_CHUNK_READS_SEQ + c, ctx->n_seq_exc, ctx->d_exc_read.as<uint32_t>(),
+                               ctx->d_exc_pos.as<uint32_t>(), ctx->d_exc_nib.as<uint8_t>(), ctx->d_seq_off.as<int64_t>(), ctx->d_seq.as<uint8_t>());
+                    }
+                    if (ctx->qual_bits != 8 && attempt == 0) {      // the reads completed by this chunk: compact qualities -> bytes
+                        if (ctx->qual_bits == 2)
+                            LAUNCH(k_unpack<0>, 148u * 8u, 256, 0, small + SW_CHUNK_READS + c, ctx->d_qual_poff.as<uint32_t>(), ctx->d_qual_off.as<int64_t>(),
+                                   ctx->d_lseq.as<int32_t>(), ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr, ctx->d_qual_lut.as<uint8_t>(),
+                                   ctx->d_qual_packed.as<uint8_t>(), ctx->d_qual.as<uint8_t>());
+                        else
+                            LAUNCH(k_unpack<1>, 148u * 8u, 256, 0, small + SW_CHUNK_READS + c, ctx->d_qual_poff.as<uint32_t>(), ctx->d_qual_off.as<int64_t>(),
+                                   ctx->d_lseq.as<int32_t>(), ctx->has_store ? ctx->d_store_len.as<int32_t>() : nullptr, ctx->d_qual_lut.as<uint8_t>(),
+                                   ctx->d_qual_packed.as<uint8_t>(), ctx->d_qual.as<uint8_t>());
+                    }
                     const uint32_t u1 = ctx->pipe_end[c];
                     if (u1 <= u0) continue;
                     A.unit0 = B.unit0 = u0; A.n_units = B.n_units = u1;
@@ -1070,7 +1185,30 @@ extern "C" int smc_download(smc_ctx* ctx, smc_out* out) {
     return SMC_OK;
 }
 
+// SMC_TIMELINE=1: one stderr line per smc_call_batch with the host enter / exit times and the device times of the stage
+// events, all in ms since the first call of the process (how the calls of several contexts interleave on one GPU).
+static std::mutex g_tl_mu;
+static cudaEvent_t g_tl_base = nullptr;
+static std::chrono::steady_clock::time_point g_tl_t0;
+static double tl_host_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_tl_t0).count(); }
+
 extern "C" int smc_call_batch(smc_ctx* ctx, const smc_reads_soa* reads, const smc_loci* loci, const smc_umi_keep* keep, smc_out* out) {
+    static const bool timeline = [] { const char* ev = getenv("SMC_TIMELINE"); return ev && atoi(ev) != 0; }();
+    double tl_enter = 0;
+    if (timeline && ctx) {
+        std::lock_guard<std::mutex> lk(g_tl_mu);
+        if (!g_tl_base) {
+            cudaSetDevice(ctx->device);
+            cudaEventCreate(&g_tl_base); cudaEventRecord(g_tl_base, ctx->st); cudaEventSynchronize(g_tl_base);
+            g_tl_t0 = std::chrono::steady_clock::now();
+        }
+        tl_enter = tl_host_ms();
+    }
+    struct TlExit {
+        smc_ctx* c; bool on; double enter; float dev[8];
+        ~TlExit() { if (on) fprintf(stderr, "[smc timeline] ctx %p host %.2f .. %.2f | dev: scalars %.2f chunks_done %.2f run %.2f prep_done %.2f sort_done %.2f pileup_done %.2f "
+                                            "stats_done %.2f\n", (void*)c, enter, tl_host_ms(), dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6]); }
+    } tl{ctx, false, tl_enter, {}};
     // Bases and qualities (3/4 of the bytes) are uploaded in chunks on a second stream while the kernels that only need the
     // per-read scalars already run; the pileup kernels are launched per chunk as the data arrives (upload_impl,
     // smc_run_resident).  Whatever happens, no copy may still read the caller's buffers when this returns.
@@ -1082,6 +1220,10 @@ extern "C" int smc_call_batch(smc_ctx* ctx, const smc_reads_soa* reads, const sm
             ctx->err = std::string("smc_call_batch: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2); rc = SMC_E_CUDA;
         }
         if (rc == SMC_OK && ctx->uploaded) cudaEventElapsedTime(&ctx->tm.ms_h2d, ctx->ev[0], ctx->ev[1]);
+        if (timeline && rc == SMC_OK) {
+            for (int i = 0; i < 7; ++i) if (cudaEventElapsedTime(&tl.dev[i], g_tl_base, ctx->ev[i]) != cudaSuccess) { tl.dev[i] = -1.f; cudaGetLastError(); }
+            tl.on = true;
+        }
         ctx->pipe_n = 0;                                 // the batch is resident now: later smc_run_resident calls run it in one go
     }
     if (rc) return rc;

@@ -118,12 +118,15 @@ class AlleleNamer:
         self._cache = {}
 
     def _read_bases(self, r, q0, n):
-        so = int(self.reads.seq_off[r])
-        if getattr(self.reads, "store_lo", None) is not None:      # stored window: seq holds the bases from store_lo on
-            q0 -= int(self.reads.store_lo[r])
+        rd = self.reads
+        if getattr(rd, "store_lo", None) is not None:              # stored window: seq holds the bases from store_lo on
+            q0 -= int(rd.store_lo[r])
+        if getattr(rd, "seq_bits", 4) == 2:                         # compact bases: 2-bit codes + the list of non-ACGT bases
+            return "".join(NT16[v] for v in rd.compact_bases(r, q0, n))
+        so = int(rd.seq_off[r])
         out = []
         for q in range(q0, q0 + n):
-            b = int(self.reads.seq[so + (q >> 1)])
+            b = int(rd.seq[so + (q >> 1)])
             out.append(NT16[(b & 15) if (q & 1) else (b >> 4)])
         return "".join(out)
 

@@ -20,6 +20,7 @@ from __future__ import annotations
 import argparse
 import datetime
 import os
+import queue
 import threading
 from concurrent.futures import ThreadPoolExecutor
 
@@ -93,56 +94,60 @@ def _run_shards(reads, intervals, refs, prm: VcParams, gpus, devices, stage_time
                 return
             # a shard goes through its GPU as a stream of batches under the library's per-batch limits
             batches = plan_batches(locator, intervals, idxs, **(batch_limits or {}))
-            tc = time.perf_counter()
-            caller = GpuCaller(prm, devices[g])
-            hp_caller = GpuCaller(prm, devices[g])        # the HP / LowC pass of a finished batch runs beside the next batch's call
-            post = ThreadPoolExecutor(max_workers=1)
-            pending = []
-
-            def finish(res, sub, loci, bed_order, b):
-                """Post-processing of one batch (device HP / LowC pass, native output stage) on the shard's worker thread: the
-                main thread is already uploading the next batch (ctypes drops the GIL for both)."""
-                t1 = time.perf_counter()
-                hp = device_hp_flags(hp_caller, res, sub, loci, chroms, refs, prm.hpLen)   # isHPorLowComp, smCounter.py:122-177
-                em = emit_rows(res, sub, loci, chroms, refs, prm.hpLen, bed_order, hp_flags=hp, **emit_kw)
-                o = 0
+            # Two contexts per GPU, two host threads: while one batch computes and downloads, the next one is already uploading
+            # (ctypes drops the GIL inside the library), so the PCIe link and the SMs are both kept busy across batches.
+            n_ctx = max(1, min(int(os.environ.get("SMC_CTX_PER_GPU", "2")), len(batches)))
+            t_create = time.perf_counter()
+            callers = [GpuCaller(prm, devices[g]) for _ in range(n_ctx)]
+            free = queue.SimpleQueue()
+            for i in range(n_ctx):
+                free.put(i)
+            if stage_times is not None:
                 with lock:
-                    for k in b:
-                        nrow = max(0, intervals[k][2] - intervals[k][1])
-                        per_interval[k] = (em, o, o + nrow)
-                        o += nrow
-                    if stage_times is not None:
-                        stage_times["ms_format_rows"] = stage_times.get("ms_format_rows", 0.0) + 1e3 * (time.perf_counter() - t1)
-                        stage_times["batches"] = stage_times.get("batches", 0) + 1
-            try:
-                for b in batches:
+                    stage_times["ms_ctx_create"] = stage_times.get("ms_ctx_create", 0.0) + 1e3 * (time.perf_counter() - t_create)
+
+            def do_batch(b):
+                i = free.get()
+                try:
+                    caller = callers[i]
                     ivs = [intervals[k] for k in b]
                     whole = len(plan) == 1 and len(batches) == 1
                     sub = reads if whole else reads.select(locator.select(ivs))
                     loci, bed_order = build_loci(ivs, chroms, refs)
                     t0 = time.perf_counter()
                     res = caller.call(sub, loci)
-                    if stage_times is not None:
-                        tm = caller.timings()
-                        with lock:
-                            stage_times["ms_ctx_create"] = stage_times.get("ms_ctx_create", 0.0) + 1e3 * (t0 - tc)
-                            stage_times["ms_first_call"] = stage_times.get("ms_first_call", 0.0) + 1e3 * (time.perf_counter() - t0)
-                            for k in ("ms_h2d", "ms_total_device", "ms_d2h"):
-                                stage_times[k] = stage_times.get(k, 0.0) + float(tm[k])
+                    tm = caller.timings()
                     keep = draw_keep_masks(caller, res, sub, loci, chroms, prm)        # smCounter.py:496-500
                     if keep is not None:
                         res = caller.call(sub, loci, keep)
-                    if stage_times is not None:
-                        with lock:
-                            stage_times["ms_gpu_call"] = stage_times.get("ms_gpu_call", 0.0) + 1e3 * (time.perf_counter() - t0)
-                    pending.append(post.submit(finish, res, sub, loci, bed_order, b))
-                    tc = time.perf_counter()
-                for f in pending:
-                    f.result()
+                    hp = device_hp_flags(caller, res, sub, loci, chroms, refs, prm.hpLen)   # isHPorLowComp, smCounter.py:122-177
+                    t1 = time.perf_counter()
+                    em = emit_rows(res, sub, loci, chroms, refs, prm.hpLen, bed_order, hp_flags=hp, **emit_kw)
+                    o = 0
+                    with lock:
+                        for k in b:
+                            nrow = max(0, intervals[k][2] - intervals[k][1])
+                            per_interval[k] = (em, o, o + nrow)
+                            o += nrow
+                        if stage_times is not None:
+                            for key in ("ms_h2d", "ms_total_device", "ms_d2h"):
+                                stage_times[key] = stage_times.get(key, 0.0) + float(tm[key])
+                            stage_times["ms_gpu_call"] = stage_times.get("ms_gpu_call", 0.0) + 1e3 * (t1 - t0)
+                            stage_times["ms_format_rows"] = stage_times.get("ms_format_rows", 0.0) + 1e3 * (time.perf_counter() - t1)
+                            stage_times["batches"] = stage_times.get("batches", 0) + 1
+                finally:
+                    free.put(i)
+            try:
+                if n_ctx == 1:
+                    for b in batches:
+                        do_batch(b)
+                else:
+                    with ThreadPoolExecutor(max_workers=n_ctx) as ex:
+                        for f in [ex.submit(do_batch, b) for b in batches]:
+                            f.result()
             finally:
-                post.shutdown(wait=True)
-                caller.close()
-                hp_caller.close()
+                for c in callers:
+                    c.close()
         except BaseException as e:          # noqa: BLE001 -- re-raised on the main thread
             errors[g] = e
 

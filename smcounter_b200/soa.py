@@ -48,6 +48,8 @@ class ReadsSoA:
     scalar_bits: int = 32                 # 16: nm / l_seq / store_lo / store_len are uint16 arrays
     qual_bits: int = 8                    # 4 / 2: ``qual`` holds qual_bits-wide codes (low bits first, reads byte aligned) ...
     qual_lut: np.ndarray | None = None    # ... and this is the phred value of each code
+    seq_bits: int = 4                     # 2: ``seq`` holds A C G T = 0..3 (low bits first, reads byte aligned) ...
+    seq_exc: tuple | None = None          # ... and (read u32, base index u32, BAM nibble u8) of every other base
 
     @property
     def n(self) -> int:
@@ -56,7 +58,8 @@ class ReadsSoA:
     def nbytes(self) -> int:
         return sum(getattr(self, f).nbytes for f in
                    ("ref_id", "pos", "flag", "mapq", "nm", "l_seq", "seq_off", "qual_off", "cigar_off", "n_cigar",
-                    "umi", "frag_id", "seq", "qual", "cigar")) + (0 if self.store_lo is None else self.store_lo.nbytes + self.store_len.nbytes)
+                    "umi", "frag_id", "seq", "qual", "cigar")) + (0 if self.store_lo is None else self.store_lo.nbytes + self.store_len.nbytes) \
+            + (0 if self.seq_exc is None else sum(a.nbytes for a in self.seq_exc))
 
     def stored_len(self) -> np.ndarray:
         """Stored bases per read (== l_seq unless the SoA was trimmed to its targets)."""
@@ -64,7 +67,7 @@ class ReadsSoA:
 
     def select(self, idx: np.ndarray) -> "ReadsSoA":
         """Sub-batch with the reads ``idx`` (ascending), variable-length payloads re-packed."""
-        if self.qual_bits != 8 or self.scalar_bits != 32:
+        if self.qual_bits != 8 or self.scalar_bits != 32 or self.seq_bits != 4:
             raise ValueError("a compacted SoA is an upload format: select / trim before compact()")
         idx = np.asarray(idx, dtype=np.int64)
         l_seq = self.stored_len()[idx]
@@ -178,12 +181,13 @@ class ReadsSoA:
                         frag_id=self.frag_id, seq=out["seq"][0], qual=out["qual"][0], cigar=out["cigar"][0], chroms=self.chroms,
                         umi_names=self.umi_names, packed=True, store_lo=store_lo, store_len=store_len)
 
-    def compact(self, block: int = 1 << 18) -> "ReadsSoA":
+    def compact(self, block: int = 1 << 18, seq_bits_wanted: int = 2) -> "ReadsSoA":
         """The same reads in the compact upload encodings of include/smc_b200.h (ABI v3): 16-bit nm / l_seq / store_lo /
         store_len when every value fits, and 2- or 4-bit quality codes when the batch shows at most 4 / 16 distinct
-        qualities (sequencers that bin qualities; a batch with more keeps one byte per base).  Needs a packed layout
-        (repack() / trim_to_targets() / select()).  On the cfg-2 panel batch: 157 -> 92 bytes per read over PCIe."""
-        if self.qual_bits != 8 or self.scalar_bits != 32:
+        qualities (sequencers that bin qualities; a batch with more keeps one byte per base), 2-bit bases with a side list for
+        the non-ACGT ones (`seq_bits_wanted=4` keeps BAM's nibbles).  Needs a packed layout (repack() / trim_to_targets() /
+        select()).  On the cfg-2 panel batch: 157 -> 72 bytes per read over PCIe."""
+        if self.qual_bits != 8 or self.scalar_bits != 32 or self.seq_bits != 4:
             raise ValueError("already compact")
         src = self if self.packed else self.repack()
         kw = {f: getattr(src, f) for f in ("ref_id", "pos", "flag", "mapq", "seq_off", "qual_off", "cigar_off", "n_cigar", "umi", "frag_id",
@@ -195,34 +199,73 @@ class ReadsSoA:
             scal = {k: (None if a is None else a.astype(np.uint16)) for k, a in scal.items()}
         present = np.flatnonzero(np.bincount(src.qual, minlength=256)) if len(src.qual) else np.zeros(0, np.int64)
         bits = 2 if len(present) <= 4 else 4 if len(present) <= 16 else 8
+        lens = src.stored_len()
+        uoff = np.concatenate(([0], np.cumsum(lens)))
         qual, lut = src.qual, None
         if bits != 8:
             lut = np.zeros(1 << bits, np.uint8)
             lut[:len(present)] = present
             code_of = np.zeros(256, np.uint8)
             code_of[present] = np.arange(len(present), dtype=np.uint8)
-            per = 8 // bits                                     # codes per byte
-            lens = src.stored_len()
-            nbytes = (lens * bits + 7) // 8
-            poff = np.concatenate(([0], np.cumsum(nbytes)))
-            qual = np.zeros(int(poff[-1]), np.uint8)
-            uoff = np.concatenate(([0], np.cumsum(lens)))
-            for a in range(0, src.n, block):                     # pad every read to whole bytes, then fold `per` codes into one byte
-                b = min(src.n, a + block)
-                codes = code_of[src.qual[uoff[a]:uoff[b]]]
-                padded = np.zeros(int(poff[b] - poff[a]) * per, np.uint8)
+            qual = _pack_codes(lambda a, b: code_of[src.qual[uoff[a]:uoff[b]]], lens, bits, block)
+        # bases: 2 bits each (A C G T = 0 1 2 3); everything else (N, IUPAC codes, '=') goes to a side list of
+        # (read, base index, 4-bit code) and travels as code 0
+        seq, seq_bits, exc = src.seq, 4, None
+        if seq_bits_wanted == 2:
+            soff = np.concatenate(([0], np.cumsum((lens + 1) // 2)))
+            code2 = np.zeros(16, np.uint8)
+            code2[[1, 2, 4, 8]] = (0, 1, 2, 3)
+            plain = np.zeros(16, bool)
+            plain[[1, 2, 4, 8]] = True
+            exc_read, exc_pos, exc_nib = [], [], []
+
+            def base_codes(a, b):
+                by = src.seq[soff[a]:soff[b]]
+                nib = np.empty(2 * len(by), np.uint8)
+                nib[0::2] = by >> 4
+                nib[1::2] = by & 15
                 ln = lens[a:b]
                 tot = int(ln.sum())
-                if tot:
-                    dst = np.repeat((poff[a:b] - poff[a]) * per - (uoff[a:b] - uoff[a]), ln) + np.arange(tot, dtype=np.int64)
-                    padded[dst] = codes
-                    m = padded.reshape(-1, per)
-                    acc = np.zeros(len(m), np.uint8)
-                    for k in range(per):
-                        acc |= m[:, k] << np.uint8(k * bits)
-                    qual[poff[a]:poff[b]] = acc
-        return ReadsSoA(nm=scal["nm"], l_seq=scal["l_seq"], store_lo=scal["store_lo"], store_len=scal["store_len"], qual=qual, packed=True,
-                        scalar_bits=scalar_bits, qual_bits=bits, qual_lut=lut, **kw)
+                # nibble index of base i of read r inside this block: 2 * (soff[r] - soff[a]) + i
+                rel = np.repeat(2 * (soff[a:b] - soff[a]) - (uoff[a:b] - uoff[a]), ln) + np.arange(tot, dtype=np.int64)
+                nb = nib[rel]
+                odd = np.flatnonzero(~plain[nb])
+                if len(odd):
+                    rd = np.searchsorted(uoff[a:b + 1] - uoff[a], odd, side="right") - 1
+                    exc_read.append((rd + a).astype(np.uint32))
+                    exc_pos.append((odd - (uoff[a:b] - uoff[a])[rd]).astype(np.uint32))
+                    exc_nib.append(nb[odd])
+                return code2[nb]
+            seq = _pack_codes(base_codes, lens, 2, block)
+            seq_bits = 2
+            cat = lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(0, dt)
+            exc = (cat(exc_read, np.uint32), cat(exc_pos, np.uint32), cat(exc_nib, np.uint8))
+        kw["seq"] = seq
+        out = ReadsSoA(nm=scal["nm"], l_seq=scal["l_seq"], store_lo=scal["store_lo"], store_len=scal["store_len"], qual=qual, packed=True,
+                        scalar_bits=scalar_bits, qual_bits=bits, qual_lut=lut, seq_bits=seq_bits, seq_exc=exc, **kw)
+        if seq_bits == 2:            # what compact_bases() looks reads up with (allele names of insertions), made here once
+            out.__dict__["_compact_memo"] = (np.concatenate(([0], np.cumsum((lens + 3) // 4))),
+                                             (exc[0].astype(np.uint64) << np.uint64(32)) | exc[1].astype(np.uint64))
+        return out
+
+    def compact_bases(self, r: int, q0: int, n: int) -> list:
+        """BAM nibble codes of stored bases [q0, q0 + n) of read r of a seq_bits == 2 SoA (the offsets and the sorted
+        exception keys are memoised per instance: one cumsum over the reads the first time)."""
+        memo = self.__dict__.get("_compact_memo")
+        if memo is None:
+            poff = np.concatenate(([0], np.cumsum((self.stored_len() + 3) // 4)))
+            e = self.seq_exc
+            keys = np.zeros(0, np.uint64) if e is None else (e[0].astype(np.uint64) << np.uint64(32)) | e[1].astype(np.uint64)
+            self.__dict__["_compact_memo"] = memo = (poff, keys)
+        poff, keys = memo
+        so = int(poff[r])
+        out = [1 << ((int(self.seq[so + (q >> 2)]) >> ((q & 3) * 2)) & 3) for q in range(q0, q0 + n)]
+        if len(keys):
+            lo = int(np.searchsorted(keys, np.uint64((r << 32) | max(q0, 0))))
+            while lo < len(keys) and int(keys[lo]) < ((r << 32) | (q0 + n)):
+                out[int(keys[lo]) - ((r << 32) | q0)] = int(self.seq_exc[2][lo])
+                lo += 1
+        return out
 
     def is_packed(self) -> bool:
         """True when every payload is stored back to back in read order (checked, O(n))."""
@@ -253,6 +296,32 @@ class ReadsSoA:
         a = self.cigar_off
         b = self.cigar_off + self.n_cigar.astype(np.int64)
         return (self.pos.astype(np.int64) + cs[b] - cs[a]).astype(np.int64)
+
+
+def _pack_codes(codes_of, lens: np.ndarray, bits: int, block: int) -> np.ndarray:
+    """Fold per-base codes of `bits` bits into bytes, every read padded to whole bytes (first base in the low bits).
+    codes_of(a, b) returns the codes of reads [a, b) back to back."""
+    per = 8 // bits
+    n = len(lens)
+    poff = np.concatenate(([0], np.cumsum((lens * bits + 7) // 8)))
+    uoff = np.concatenate(([0], np.cumsum(lens)))
+    out = np.zeros(int(poff[-1]), np.uint8)
+    for a in range(0, n, block):
+        b = min(n, a + block)
+        codes = codes_of(a, b)
+        ln = lens[a:b]
+        tot = int(ln.sum())
+        if not tot:
+            continue
+        padded = np.zeros(int(poff[b] - poff[a]) * per, np.uint8)
+        dst = np.repeat((poff[a:b] - poff[a]) * per - (uoff[a:b] - uoff[a]), ln) + np.arange(tot, dtype=np.int64)
+        padded[dst] = codes
+        m = padded.reshape(-1, per)
+        acc = np.zeros(len(m), np.uint8)
+        for k in range(per):
+            acc |= m[:, k] << np.uint8(k * bits)
+        out[poff[a]:poff[b]] = acc
+    return out
 
 
 @dataclass

@@ -380,6 +380,32 @@ def test_packed_payload_without_offsets():
         c.close()
 
 
+@pytest.mark.parametrize("nq,seq_bits", [(3, 2), (7, 2), (20, 2), (3, 4)])
+def test_compact_upload_encodings_give_identical_bits(nq, seq_bits):
+    """ABI v3 wire encodings (16-bit scalars, 2- / 4-bit quality codes behind a LUT, 2-bit bases with the non-ACGT ones in a
+    side list) are expanded on the device into the same arrays the plain upload makes: every count, PI and row must equal
+    the oracle's on the plain reads, through the single-shot and the chunked upload.  The synthetic reads carry 'N's and
+    insertion sites, so allele names are read back from the compact bases too."""
+    import numpy as np
+    from helpers import run_case
+    qs = tuple(int(q) for q in np.linspace(40, 8, nq).round())
+    spec = SynthSpec(**dict(PIPE_SPEC, q_values=qs, q_probs=tuple([1.0 / nq] * nq)))
+    prm = VcParams(mtDepth=50, rpb=3.0)
+    seen = {}
+
+    def enc(soa):
+        out = soa.trim_to_targets(PIPE_IVS).compact(seq_bits_wanted=seq_bits)
+        seen.update(qual_bits=out.qual_bits, seq_bits=out.seq_bits, n_exc=0 if out.seq_exc is None else len(out.seq_exc[0]), scalar_bits=out.scalar_bits)
+        return out
+
+    for chunks in ("1", "5"):
+        problems, stats, _ = _with_env("SMC_PIPE_CHUNKS", chunks, lambda: run_case(PIPE_IVS, spec, prm, seed=71, gpu_mutate=enc))
+        print(stats, seen)
+        assert not problems, "\n".join(problems)
+    assert seen["qual_bits"] == (2 if nq + 1 <= 4 else 4 if nq + 1 <= 16 else 8) and seen["scalar_bits"] == 16   # + quality 2 of the 'N's
+    assert seen["seq_bits"] == seq_bits and (seq_bits == 4 or seen["n_exc"] > 0)
+
+
 def test_fragment_ids_must_be_dense():
     """frag_id is part of the read sort key ((barcode slot, frag_id) in one sort), sized from n_reads: ids that are not
     dense first-appearance numbers (>= 2^ceil(log2 n_reads)) are refused instead of being sorted wrongly."""
