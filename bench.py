@@ -58,10 +58,11 @@ def parse_args(argv=None):
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--intervals", type=int, default=0, help="target intervals per library batch (0 = the workload's default; cfg2: 96)")
-    ap.add_argument("--batches", type=int, default=4, help="distinct batches streamed per step and GPU")
+    ap.add_argument("--batches", type=int, default=8, help="distinct batches streamed per step and GPU")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-loci", type=int, default=0, help="loci in the CPU-baseline sample (0 = 24 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (call_loci(gpus=N) on one fixed panel)")
     ap.add_argument("--whole-reads", action="store_true", help="upload whole reads instead of the target windows (store_lo/store_len)")
     ap.add_argument("--no-compact", action="store_true", help="upload one byte per quality and 32-bit scalars instead of the compact ABI v3 encodings")
     ap.add_argument("--pipeline-intervals", type=int, default=12,
@@ -347,6 +348,15 @@ def pipeline_leg(args, mine, soa, refs, device):
             t.append(time.perf_counter())
             if rep > 0:
                 runs.append((t[3] - t[0], t[1] - t[0], t[2] - t[1], t[3] - t[2], dict(st), int(reads.n)))
+        if os.environ.get("SMC_PROFILE_PIPELINE"):          # where the host time of one pass goes (stderr)
+            import cProfile
+            import pstats
+            pr = cProfile.Profile()
+            pr.enable()
+            reads = bam.read_bam(path, ivs, threads=os.cpu_count() or 1, trim=True)
+            call_loci_text(reads, ivs, refs, prm, thr, trf, rm, gpus=1, devices=[device])
+            pr.disable()
+            pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(25)
         runs.sort(key=lambda r: r[0])
         tot, dec, call, wr, st, nreads = runs[len(runs) // 2]
         return {"value": n_loci / tot, "unit": UNIT, "loci": n_loci, "reads": nreads, "intervals": len(ivs), "repeats": len(runs), "warmup": 1,
@@ -358,6 +368,40 @@ def pipeline_leg(args, mine, soa, refs, device):
                         "device HP/LowC + native rows / repeat filters / called-variant lines (libsmc_bamio: smc_rows_emit) + the three files" % len(runs)}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def strong_leg(args, ivs, soa, refs, n_gpus):
+    """Strong scaling of the product path: ONE fixed panel (the rank-0 batch 0: its intervals and all their reads, trimmed
+    as the BAM decoder delivers them) through ``smCounter.call_loci(gpus=N)`` from ONE process -- the drop-in for the
+    reference's Pool fan-out (smCounter.py:683-685): shards by BED interval, one host thread and two contexts per GPU,
+    rows formatted by the native output stage.  Median of 5 calls after one warm-up."""
+    from smcounter_b200.smCounter import call_loci
+    prm = vc_params(args)
+    reads = soa.trim_to_targets(ivs)
+    n_loci = sum(e - s for (_, s, e) in ivs)
+    runs = []
+    for rep in range(6):
+        t0 = time.perf_counter()
+        rows = call_loci(reads, ivs, refs, prm, gpus=n_gpus, devices=list(range(n_gpus)), stage_times=(st := {}))
+        dt = time.perf_counter() - t0
+        assert len(rows) == n_loci
+        if rep:
+            runs.append((dt, dict(st)))
+    if os.environ.get("SMC_PROFILE_STRONG"):            # where the host time of one call goes (stderr)
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        call_loci(reads, ivs, refs, prm, gpus=n_gpus, devices=list(range(n_gpus)))
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(35)
+    runs.sort(key=lambda r: r[0])
+    dt, st = runs[len(runs) // 2]
+    return {"value": n_loci / dt, "unit": UNIT, "gpus": n_gpus, "loci": n_loci, "reads": int(reads.n), "intervals": len(ivs), "ms": 1e3 * dt,
+            "all_runs_ms": [round(1e3 * r[0], 2) for r in runs], "ms_gpu_call_sum": st.get("ms_gpu_call"), "ms_format_rows_sum": st.get("ms_format_rows"),
+            "batches": st.get("batches"),
+            "what": "smCounter.call_loci(reads, intervals, gpus=%d) on one fixed panel from one process (plan_shards by BED interval, one thread and "
+                    "two contexts per GPU, pageable host arrays, rows through smc_rows_emit); total work fixed as N grows" % n_gpus}
 
 
 def main():
@@ -424,6 +468,7 @@ def main():
             numa = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_group = dist.new_group(backend="gloo")          # waits that must not park a kernel on the GPU
     batches = make_batches(args, rank, world)
     prm = vc_params(args)
     NB = len(batches)
@@ -557,6 +602,17 @@ def main():
     e2e_s_max = allmax(e2e_s)
     e2e_s_min = -allmax(-e2e_s)
     loci_total = allsum(loci_rank)
+    # who is the straggler: every rank's own e2e / device time per step and the H2D of its last batch
+    mine_stats = [float(rank), 1000.0 * e2e_s / args.steps, 1000.0 * (dev_ms / 1000.0) / args.steps, float(e2e_tm["ms_h2d"]),
+                  float(e2e_tm["bytes_h2d"]) / float(e2e_tm["ms_h2d"]) / 1e6 if e2e_tm["ms_h2d"] > 0 else 0.0, float(e2e_tm["ms_total_device"])]
+    if world > 1:
+        tl = [torch.zeros(len(mine_stats), dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(tl, torch.tensor(mine_stats, dtype=torch.float64, device="cuda"))
+        all_stats = [t.tolist() for t in tl]
+    else:
+        all_stats = [mine_stats]
+    per_rank = [{"rank": int(a[0]), "e2e_ms_per_step": a[1], "resident_ms_per_step": a[2], "last_batch_ms_h2d": a[3], "last_batch_h2d_gbs": a[4],
+                 "last_batch_ms_device": a[5]} for a in all_stats]
     events_total = allsum(float(events_rank))
     reads_total = allsum(float(reads_rank))
     # device time is what the CUDA events on the library's launch stream bracket for each batch run (it contains the host
@@ -605,6 +661,7 @@ def main():
                         "what": "per step and GPU: %d x (smc_call_batch from pinned host buffers -- scalars first, bases / qualities in %d chunks on a copy "
                                 "stream, %d pileup launch pairs as they arrive -- + download + smc_hp_lowcomp over the batch's candidates); two contexts / host threads, so the next batch uploads while this one computes"
                                 % (NB, e2e_tm["pipe_chunks"], e2e_tm["pipe_launches"])},
+                "per_rank": per_rank,
                 "gpu_launches": int(launches),
                 "stage_ms_per_batch_rank0": {k: v / nrun for k, v in stage.items()},
                 "roofline": {"bound": "hbm", "limited_by": "instruction issue (ncu, profiles/r02_k_gather_*_summary.txt: issue slots 70 % busy, DRAM 6 %): the tile "
@@ -639,6 +696,14 @@ def main():
         except Exception as e:          # the extra leg must never cost the bench line
             line["pipeline"] = {"error": repr(e)}
 
+    if world > 1:
+        dist.barrier()                      # every rank has finished its timed legs and closed its contexts: the GPUs are idle
+    if rank == 0 and not args.no_strong and full0 is not None:
+        try:
+            line["strong"] = strong_leg(args, ivs0, full0, refs0, world)
+        except Exception as e:
+            line["strong"] = {"error": repr(e)}
+
     if rank == 0 and not args.no_cpu_baseline and full0 is not None:
         n_sample = args.cpu_loci or 24 * cores          # ~10-30 s of host work
         jobs, nrec = cpu_sample_setup(full0, refs0, loci0, n_sample, args)
@@ -650,7 +715,7 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=host_group)
         dist.destroy_process_group()
     return 0
 

@@ -326,6 +326,11 @@ int smc_hp_lowcomp(smc_ctx *ctx, const smc_hp_batch *batch, uint8_t *flags_out);
  */
 int smc_fisher_exact(smc_ctx *ctx, int64_t n, const int32_t *tables, double *p_out, double *or_out);
 
+/* Page-locked host memory for the buffers of smc_reads_soa / smc_out: copies from / to it run as one DMA and overlap the
+ * kernels (pageable memory is staged by the driver at a fraction of the link rate).  Not tied to a context. */
+int  smc_host_alloc(int64_t bytes, void **out);
+void smc_host_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,8 @@ from .soa import ReadsSoA
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmc_bamio.so")
 EXPORTS = ("smc_bam_set_trim", "smc_bam_open", "smc_bam_close", "smc_bam_last_error", "smc_bam_n_refs", "smc_bam_ref_name", "smc_bam_ref_length",
-           "smc_bam_decode", "smc_bam_dict_umi", "smc_rows_emit", "smc_rows_free")
+           "smc_bam_decode", "smc_bam_dict_umi", "smc_rows_emit", "smc_rows_free", "smc_soa_qual_hist", "smc_soa_ref_end", "smc_soa_pack_begin", "smc_soa_pack_fill",
+           "smc_soa_pack_end")
 _vp = C.c_void_p
 
 
@@ -34,6 +35,29 @@ class smc_rows_in(C.Structure):               # include/smc_rows.h
 class smc_rows_out(C.Structure):
     _fields_ = [("all", _vp), ("all_off", _vp), ("cut", _vp), ("cut_off", _vp), ("vcf", _vp), ("vcf_off", _vp), ("bad_row", C.c_int64),
                 ("bad_status", C.c_uint32)]
+
+
+class smc_soa_view(C.Structure):             # include/smc_soa.h
+    _fields_ = [("n_reads", C.c_int64), ("ref_id", _vp), ("pos", _vp), ("flag", _vp), ("mapq", _vp), ("nm", _vp), ("l_seq", _vp),
+                ("seq_off", _vp), ("qual_off", _vp), ("cigar_off", _vp), ("n_cigar", _vp), ("umi", _vp), ("frag_id", _vp),
+                ("seq", _vp), ("qual", _vp), ("cigar", _vp), ("store_lo", _vp), ("store_len", _vp)]
+
+
+class smc_soa_pack_opts(C.Structure):
+    _fields_ = [("scalar_bits", C.c_int32), ("qual_bits", C.c_int32), ("seq_bits", C.c_int32), ("threads", C.c_int32), ("code_of", C.c_uint8 * 256)]
+
+
+class smc_soa_pack_sizes(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("seq_bytes", C.c_int64), ("qual_bytes", C.c_int64), ("n_cigar_words", C.c_int64)]
+
+
+class smc_soa_pack_bufs(C.Structure):
+    _fields_ = [("ref_id", _vp), ("pos", _vp), ("flag", _vp), ("mapq", _vp), ("nm", _vp), ("l_seq", _vp), ("store_lo", _vp), ("store_len", _vp),
+                ("n_cigar", _vp), ("umi", _vp), ("frag_id", _vp), ("seq", _vp), ("qual", _vp), ("cigar", _vp), ("seq_poff", _vp)]
+
+
+class smc_soa_pack_exc(C.Structure):
+    _fields_ = [("n", C.c_int64), ("read", _vp), ("pos", _vp), ("nib", _vp)]
 
 
 _lib = None
@@ -68,6 +92,16 @@ def load():
     lib.smc_rows_emit.restype = C.c_int
     lib.smc_rows_free.argtypes = [C.POINTER(smc_rows_out)]
     lib.smc_rows_free.restype = None
+    lib.smc_soa_qual_hist.argtypes = [C.POINTER(smc_soa_view), C.c_int, _vp]
+    lib.smc_soa_qual_hist.restype = C.c_int
+    lib.smc_soa_ref_end.argtypes = [C.POINTER(smc_soa_view), C.c_int, _vp]
+    lib.smc_soa_ref_end.restype = C.c_int
+    lib.smc_soa_pack_begin.argtypes = [C.POINTER(smc_soa_view), _vp, C.c_int64, C.POINTER(smc_soa_pack_opts), C.POINTER(_vp), C.POINTER(smc_soa_pack_sizes)]
+    lib.smc_soa_pack_begin.restype = C.c_int
+    lib.smc_soa_pack_fill.argtypes = [_vp, C.POINTER(smc_soa_pack_bufs), C.POINTER(smc_soa_pack_exc)]
+    lib.smc_soa_pack_fill.restype = C.c_int
+    lib.smc_soa_pack_end.argtypes = [_vp]
+    lib.smc_soa_pack_end.restype = None
     _lib = lib
     return lib
 
@@ -145,3 +179,112 @@ def read_bam_native(path: str, intervals=None, threads: int = 0, trim: bool = Fa
     finally:
         if not ok:
             owner.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# include/smc_soa.h: the reads of a batch, gathered and written in the compact wire encodings in one native pass
+def _view(r: ReadsSoA) -> smc_soa_view:
+    v = smc_soa_view()
+    v.n_reads = r.n
+    for f in ("ref_id", "pos", "flag", "mapq", "nm", "l_seq", "seq_off", "qual_off", "cigar_off", "n_cigar", "umi", "frag_id", "seq", "qual", "cigar"):
+        a = getattr(r, f)
+        assert a.flags["C_CONTIGUOUS"]
+        setattr(v, f, a.ctypes.data)
+    if r.store_lo is not None:
+        v.store_lo, v.store_len = r.store_lo.ctypes.data, r.store_len.ctypes.data
+    return v
+
+
+def ref_end_native(reads: ReadsSoA, threads: int = 0) -> np.ndarray:
+    """ReadsSoA.ref_end() by one threaded native pass over the CIGARs."""
+    out = np.empty(reads.n, np.int64)
+    v = _view(reads)
+    rc = load().smc_soa_ref_end(C.byref(v), threads, out.ctypes.data)
+    if rc:
+        raise RuntimeError("smc_soa_ref_end failed (%d)" % rc)
+    return out
+
+
+def upload_codebook(reads: ReadsSoA, threads: int = 0) -> dict:
+    """What every batch of ``reads`` is packed with (memoised on the SoA): 16-bit scalars when every value fits, the
+    quality codebook (2 / 4 bits when at most 4 / 16 distinct phred values occur in the whole file)."""
+    memo = reads.__dict__.get("_upload_codebook")
+    if memo is not None:
+        return memo
+    lib = load()
+    hist = np.zeros(256, np.uint64)
+    v = _view(reads)
+    rc = lib.smc_soa_qual_hist(C.byref(v), threads, hist.ctypes.data)
+    if rc:
+        raise RuntimeError("smc_soa_qual_hist failed (%d)" % rc)
+    present = np.flatnonzero(hist)
+    bits = 2 if len(present) <= 4 else 4 if len(present) <= 16 else 8
+    lut = code_of = None
+    if bits != 8:
+        lut = np.zeros(1 << bits, np.uint8)
+        lut[:len(present)] = present
+        code_of = np.full(256, 0xFF, np.uint8)
+        code_of[present] = np.arange(len(present), dtype=np.uint8)
+    scal = [reads.nm, reads.l_seq] + ([] if reads.store_lo is None else [reads.store_lo, reads.store_len])
+    fits = all(len(a) == 0 or (int(a.min()) >= 0 and int(a.max()) < 65536) for a in scal)
+    memo = dict(scalar_bits=16 if fits else 32, qual_bits=bits, qual_lut=lut, code_of=code_of)
+    reads.__dict__["_upload_codebook"] = memo
+    return memo
+
+
+def pack_upload(reads: ReadsSoA, idx=None, alloc=None, seq_bits: int = 2, threads: int = 0) -> ReadsSoA:
+    """The reads ``idx`` (ascending; None = all) of a plain SoA as a compact upload SoA (ReadsSoA.compact() of
+    ReadsSoA.select(idx), bit for bit) made by one threaded native pass.  ``alloc(nbytes) -> uint8 array`` supplies the
+    output buffers (a pinned arena: caller.PinnedArena.take); default: ordinary numpy memory."""
+    if reads.qual_bits != 8 or reads.scalar_bits != 32 or reads.seq_bits != 4:
+        raise ValueError("pack_upload needs a plain SoA")
+    lib = load()
+    cb = upload_codebook(reads, threads)
+    alloc = alloc or (lambda nbytes: np.empty(nbytes, np.uint8))
+    take = lambda count, dt: alloc(max(int(count), 1) * np.dtype(dt).itemsize).view(dt)[:int(count)]
+    o = smc_soa_pack_opts()
+    o.scalar_bits, o.qual_bits, o.seq_bits, o.threads = cb["scalar_bits"], cb["qual_bits"], seq_bits, threads
+    if cb["code_of"] is not None:
+        C.memmove(o.code_of, cb["code_of"].ctypes.data, 256)
+    v = _view(reads)
+    if idx is not None:
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+    h, sz = _vp(), smc_soa_pack_sizes()
+    rc = lib.smc_soa_pack_begin(C.byref(v), None if idx is None else idx.ctypes.data, 0 if idx is None else len(idx), C.byref(o), C.byref(h), C.byref(sz))
+    if rc:
+        raise RuntimeError("smc_soa_pack_begin failed (%d)" % rc)
+    try:
+        n = int(sz.n_reads)
+        sdt = np.uint16 if cb["scalar_bits"] == 16 else np.int32
+        out = dict(ref_id=take(n, np.int32), pos=take(n, np.int32), flag=take(n, np.uint16), mapq=take(n, np.uint8), nm=take(n, sdt),
+                   l_seq=take(n, sdt), n_cigar=take(n, np.uint16), umi=take(n, np.uint64), frag_id=take(n, np.uint32),
+                   seq=take(sz.seq_bytes, np.uint8), qual=take(sz.qual_bytes, np.uint8), cigar=take(sz.n_cigar_words, np.uint32))
+        if reads.store_lo is not None:
+            out["store_lo"], out["store_len"] = take(n, sdt), take(n, sdt)
+        poff = np.empty(n + 1, np.int64)
+        b = smc_soa_pack_bufs()
+        for f, a in out.items():
+            setattr(b, f, a.ctypes.data)
+        b.seq_poff = poff.ctypes.data
+        ex = smc_soa_pack_exc()
+        rc = lib.smc_soa_pack_fill(h, C.byref(b), C.byref(ex))
+        if rc:
+            raise RuntimeError("smc_soa_pack_fill failed (%d): a scalar above 65535 or a quality outside the codebook" % rc)
+        exc = None
+        if seq_bits == 2:
+            ne = int(ex.n)
+            exc = (take(ne, np.uint32), take(ne, np.uint32), take(ne, np.uint8))
+            if ne:
+                C.memmove(exc[0].ctypes.data, ex.read, 4 * ne); C.memmove(exc[1].ctypes.data, ex.pos, 4 * ne); C.memmove(exc[2].ctypes.data, ex.nib, ne)
+    finally:
+        lib.smc_soa_pack_end(h)
+    zero = np.zeros(0, np.int64)
+    res = ReadsSoA(seq_off=zero, qual_off=zero, cigar_off=zero, chroms=reads.chroms, umi_names=reads.umi_names, packed=True,
+                   scalar_bits=cb["scalar_bits"], qual_bits=cb["qual_bits"], qual_lut=cb["qual_lut"], seq_bits=seq_bits, seq_exc=exc,
+                   store_lo=out.get("store_lo"), store_len=out.get("store_len"),
+                   **{f: out[f] for f in ("ref_id", "pos", "flag", "mapq", "nm", "l_seq", "n_cigar", "umi", "frag_id", "seq", "qual", "cigar")})
+    if seq_bits == 2:
+        res.__dict__["_compact_memo"] = (poff, (exc[0].astype(np.uint64) << np.uint64(32)) | exc[1].astype(np.uint64))
+    else:
+        res.seq_off = poff[:-1]
+    return res

@@ -76,7 +76,8 @@ class smc_hp_batch(C.Structure):
 HP_HOMOPOLYMER, HP_LOWCOMP = 1, 2
 
 EXPORTS = ("smc_version", "smc_ctx_create", "smc_ctx_destroy", "smc_last_error", "smc_call_batch", "smc_upload",
-           "smc_run_resident", "smc_download", "smc_get_timings", "smc_list_barcodes", "smc_hp_lowcomp", "smc_fisher_exact")
+           "smc_run_resident", "smc_download", "smc_get_timings", "smc_list_barcodes", "smc_hp_lowcomp", "smc_fisher_exact", "smc_host_alloc",
+           "smc_host_free")
 
 _lib = None
 
@@ -108,6 +109,10 @@ def load():
     lib.smc_download.restype = C.c_int
     lib.smc_fisher_exact.argtypes = [_vp, C.c_int64, _vp, _vp, _vp]
     lib.smc_fisher_exact.restype = C.c_int
+    lib.smc_host_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
+    lib.smc_host_alloc.restype = C.c_int
+    lib.smc_host_free.argtypes = [C.c_void_p]
+    lib.smc_host_free.restype = None
     lib.smc_get_timings.argtypes = [_vp, C.POINTER(smc_timings)]
     lib.smc_get_timings.restype = C.c_int
     lib.smc_list_barcodes.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64]

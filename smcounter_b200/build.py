@@ -27,13 +27,15 @@ BAMIO_SRC = os.path.join(CSRC, "smc_bamio.cpp")
 ROWS_SRC = os.path.join(CSRC, "smc_rows.cpp")            # host-side output stage (include/smc_rows.h), same library
 BAMIO_HDR = os.path.join(HERE, "..", "include", "smc_bamio.h")
 ROWS_HDR = os.path.join(HERE, "..", "include", "smc_rows.h")
+SOA_SRC = os.path.join(CSRC, "smc_soa.cpp")              # host-side batch packer (include/smc_soa.h), same library
+SOA_HDR = os.path.join(HERE, "..", "include", "smc_soa.h")
 
 
 def build_bamio(force: bool = False) -> str:
     """Host-side BAM decoder (C++17, zlib, threads) -> libsmc_bamio.so."""
-    if not force and os.path.exists(BAMIO_OUT) and os.path.getmtime(BAMIO_OUT) >= max(os.path.getmtime(f) for f in (BAMIO_SRC, BAMIO_HDR, ROWS_SRC, ROWS_HDR)):
+    if not force and os.path.exists(BAMIO_OUT) and os.path.getmtime(BAMIO_OUT) >= max(os.path.getmtime(f) for f in (BAMIO_SRC, BAMIO_HDR, ROWS_SRC, ROWS_HDR, SOA_SRC, SOA_HDR)):
         return BAMIO_OUT
-    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", BAMIO_OUT, BAMIO_SRC, ROWS_SRC, "-lz"]
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", BAMIO_OUT, BAMIO_SRC, ROWS_SRC, SOA_SRC, "-lz"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

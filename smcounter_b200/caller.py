@@ -43,6 +43,56 @@ def _alloc(shape, dtype, pinned):
     return np.empty(shape, dtype=dtype)
 
 
+class PinnedArena:
+    """Page-locked host memory (smc_host_alloc) handed out in 256-byte aligned pieces and recycled batch after batch:
+    ``take(nbytes)`` until ``reset()``.  What _bamio.pack_upload writes a batch into, so that smc_call_batch's copies
+    run as DMA at the link rate.  Slabs only grow; ``close()`` frees them."""
+
+    def __init__(self, first_bytes: int = 64 << 20):
+        self.lib = _ffi.load()
+        self.slabs = []             # (address, size, uint8 view)
+        self.cur, self.off = 0, 0
+        self.first = int(first_bytes)
+
+    def _new_slab(self, nbytes):
+        p = C.c_void_p()
+        rc = self.lib.smc_host_alloc(nbytes, C.byref(p))
+        if rc != 0 or not p.value:
+            raise MemoryError("smc_host_alloc(%d) failed (%d)" % (nbytes, rc))
+        view = np.frombuffer((C.c_uint8 * nbytes).from_address(p.value), dtype=np.uint8)
+        self.slabs.append((p.value, nbytes, view))
+
+    def take(self, nbytes: int) -> np.ndarray:
+        nbytes = max(int(nbytes), 1)
+        need = (nbytes + 255) & ~255
+        while True:
+            if self.cur < len(self.slabs):
+                _, size, view = self.slabs[self.cur]
+                if self.off + need <= size:
+                    out = view[self.off:self.off + nbytes]
+                    self.off += need
+                    return out
+                self.cur, self.off = self.cur + 1, 0
+                continue
+            last = self.slabs[-1][1] if self.slabs else self.first // 2
+            self._new_slab(max(2 * last, need))
+
+    def reset(self):
+        self.cur, self.off = 0, 0
+
+    def close(self):
+        for (addr, _, _) in self.slabs:
+            self.lib.smc_host_free(addr)
+        self.slabs = []
+        self.reset()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class LocusResults:
     """Per-locus outputs of the device path (include/smc_b200.h: smc_out)."""
 

@@ -1230,6 +1230,16 @@ extern "C" int smc_call_batch(smc_ctx* ctx, const smc_reads_soa* reads, const sm
     return smc_download(ctx, out);
 }
 
+extern "C" int smc_host_alloc(int64_t bytes, void** out) {
+    if (!out || bytes < 0) return SMC_E_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, (size_t)(bytes ? bytes : 1), cudaHostAllocPortable);
+    if (e != cudaSuccess) { g_create_error = std::string("smc_host_alloc: ") + cudaGetErrorString(e); cudaGetLastError(); *out = nullptr; return SMC_E_CUDA; }
+    return SMC_OK;
+}
+
+extern "C" void smc_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 extern "C" int smc_get_timings(smc_ctx* ctx, smc_timings* t) {
     if (!ctx || !t) return SMC_E_ARG;
     *t = ctx->tm;

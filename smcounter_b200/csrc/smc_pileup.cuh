@@ -1052,7 +1052,7 @@ __global__ void __launch_bounds__(KA_WARPS * 32, KA_MINBLOCKS) k_gather_t(const 
 #define KB_UPROD_WORDS (NSLOT * 64)
 #define KB_UDYN_WORDS  (NDYN * 32)              // dynamic-allele row of slot NF + k of the open barcode, per lane
 #define KB_WARP_WORDS  (KB_FC_WORDS + KB_LIMB_WORDS + KB_UCNT_WORDS + KB_UPROD_WORDS + KB_UDYN_WORDS)
-#define KB_TAB_BYTES   8192                     // {p, 1 - p} of a fragment, indexed by 'Paired' << 8 | quality (512 x double2)
+#define KB_TAB_BYTES   4128                     // {p, 1 - p} of a fragment: entry 0 = not 'Paired' (0.1), entry 1 + quality = 'Paired' (257 x double2)
 #define KB_SMEM_BYTES  (KB_TAB_BYTES + KB_WARPS * KB_WARP_WORDS * 4)
 
 struct KBArgs {
@@ -1408,8 +1408,8 @@ template <bool LIST>
 __global__ void __launch_bounds__(KB_WARPS * 32, KB_MINBLOCKS) k_merge_t(const KBArgs A) {
     extern __shared__ __align__(16) uint32_t smem[];
     double2* pq_s = reinterpret_cast<double2*>(smem);        // fragment probability (smCounter.py:65-68) and its complement (:72, :77)
-    for (int i = threadIdx.x; i < 512; i += KB_WARPS * 32) {
-        const double pf = i < 256 ? 0.1 : __ldg(&A.bqtab[i - 256]);
+    for (int i = threadIdx.x; i < 257; i += KB_WARPS * 32) {
+        const double pf = i == 0 ? 0.1 : __ldg(&A.bqtab[i - 1]);
         pq_s[i] = make_double2(pf, 1.0 - pf);
     }
     __syncthreads();
@@ -1474,7 +1474,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32, KB_MINBLOCKS) k_merge_t(const K
             const uint32_t e = __ldg(extp);
             if (aid == FC_AID_DYN) aid = NF + e;
         }
-        const double2 pq = pq_s[((cd >> 5) & 0x100u) | (cd & 0xffu)];                // smCounter.py:65-68 (a valid entry for any code)
+        const double2 pq = pq_s[((cd >> 13) & 1u) * ((cd & 0xffu) + 1u)];                // smCounter.py:65-68 (a valid entry for any code)
         const bool join = st == 3u;
         // Nine rows out of ten no lane's barcode shows a second allele or a dynamic one: the fragment joins a single-allele
         // barcode (fragment_join reduces to two products and a count), done without a divergent branch -- a fragment that

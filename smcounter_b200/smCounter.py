@@ -28,7 +28,8 @@ import numpy as np
 
 from . import repeats, writers
 from .bam import read_bam
-from .caller import GpuCaller, UmiKeep, VcParams
+from ._bamio import pack_upload
+from .caller import GpuCaller, PinnedArena, UmiKeep, VcParams
 from .downsample import draw_keep_masks
 from .fasta import FastaFile
 from .rows import device_hp_flags, emit_rows, headerAll, headerVariants
@@ -67,6 +68,27 @@ def argParseInit():
     parser.add_argument('--fisherLegacy', type=int, default=0, help='1: two-sided Fisher p-values as scipy <= 1.6 computed them (epsilon = 1 - 1e-4, the scipy of the 2017 reference run); 0 (default): scipy >= 1.7')
 
 
+# Page-locked upload buffers are expensive to create (the driver pins every page): they are kept for the life of the process
+# and handed from one call_loci() to the next.
+_ARENAS: "queue.SimpleQueue[PinnedArena]" = queue.SimpleQueue()
+
+
+def _take_arena() -> PinnedArena:
+    try:
+        return _ARENAS.get_nowait()
+    except queue.Empty:
+        return PinnedArena()
+
+
+def release_host_buffers():
+    """Frees the pinned upload buffers kept between calls."""
+    while True:
+        try:
+            _ARENAS.get_nowait().close()
+        except queue.Empty:
+            return
+
+
 def _run_shards(reads, intervals, refs, prm: VcParams, gpus, devices, stage_times, batch_limits, emit_kw):
     """Shards the BED intervals over the GPUs, streams every shard through its GPU in batches, and turns each batch's device
     results into text with the native output stage (rows.emit_rows).  Returns {interval index: (EmittedRows, first row, end row)}."""
@@ -83,6 +105,7 @@ def _run_shards(reads, intervals, refs, prm: VcParams, gpus, devices, stage_time
         sub = _run_shards(reads, pieces, refs, prm, gpus, devices, stage_times, batch_limits, emit_kw)
         return _regroup_pieces(intervals, pieces, sub)
     plan = plan_shards(reads, intervals, chroms, len(devices))
+    compactable = reads.qual_bits == 8 and reads.scalar_bits == 32 and reads.seq_bits == 4 and os.environ.get("SMC_NATIVE_PACK", "1") != "0"
     per_interval = {}
     errors = [None] * len(plan)
     lock = threading.Lock()
@@ -99,6 +122,7 @@ def _run_shards(reads, intervals, refs, prm: VcParams, gpus, devices, stage_time
             n_ctx = max(1, min(int(os.environ.get("SMC_CTX_PER_GPU", "2")), len(batches)))
             t_create = time.perf_counter()
             callers = [GpuCaller(prm, devices[g]) for _ in range(n_ctx)]
+            arenas = [_take_arena() for _ in range(n_ctx)]      # the upload buffers of each context, recycled batch after batch
             free = queue.SimpleQueue()
             for i in range(n_ctx):
                 free.put(i)
@@ -112,7 +136,12 @@ def _run_shards(reads, intervals, refs, prm: VcParams, gpus, devices, stage_time
                     caller = callers[i]
                     ivs = [intervals[k] for k in b]
                     whole = len(plan) == 1 and len(batches) == 1
-                    sub = reads if whole else reads.select(locator.select(ivs))
+                    # the batch's reads, gathered and written in the compact wire encodings by one native pass (include/smc_soa.h)
+                    arenas[i].reset()
+                    if compactable:
+                        sub = pack_upload(reads, None if whole else locator.select(ivs), alloc=arenas[i].take)
+                    else:
+                        sub = reads if whole else reads.select(locator.select(ivs))
                     loci, bed_order = build_loci(ivs, chroms, refs)
                     t0 = time.perf_counter()
                     res = caller.call(sub, loci)
@@ -148,6 +177,8 @@ def _run_shards(reads, intervals, refs, prm: VcParams, gpus, devices, stage_time
             finally:
                 for c in callers:
                     c.close()
+                for a in arenas:
+                    _ARENAS.put(a)
         except BaseException as e:          # noqa: BLE001 -- re-raised on the main thread
             errors[g] = e
 

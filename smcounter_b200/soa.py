@@ -288,6 +288,12 @@ class ReadsSoA:
         return out
 
     def _ref_end_compute(self) -> np.ndarray:
+        if self.qual_bits == 8 and self.scalar_bits == 32 and self.seq_bits == 4 and self.n > (1 << 16):
+            try:                                    # big plain SoAs: the threaded native pass (include/smc_soa.h)
+                from ._bamio import ref_end_native
+                return ref_end_native(self)
+            except ImportError:
+                pass
         ops = self.cigar & 0xF
         lens = (self.cigar >> 4).astype(np.int64)
         consumes = np.isin(ops, (0, 2, 3, 7, 8))

@@ -109,7 +109,8 @@ def test_bamio_library_exports_and_layout(tmp_path):
     lib = _bamio.load()
     src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "smc_bamio.h")).read(), flags=re.S)
     src += re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "smc_rows.h")).read(), flags=re.S)      # same library
-    names = sorted(set(re.findall(r"\b(smc_(?:bam|rows)_[a-z_]+)\s*\(", src)))
+    src += re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "smc_soa.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(smc_(?:bam|rows|soa)_[a-z_]+)\s*\(", src)))
     assert set(names) == set(_bamio.EXPORTS)
     for n in names:
         assert getattr(lib, n) is not None
@@ -125,8 +126,12 @@ def test_bamio_library_exports_and_layout(tmp_path):
     assert int(got["size"]) == C.sizeof(cls)
     for f, _ in cls._fields_:
         assert int(got[f]) == getattr(cls, f).offset, f
-    for cname, cls2 in (("smc_rows_in", _bamio.smc_rows_in), ("smc_rows_out", _bamio.smc_rows_out)):                # include/smc_rows.h
-        lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "smc_rows.h"', 'int main(void){', 'printf("size %%zu\\n", sizeof(%s));' % cname]
+    for cname, cls2 in (("smc_rows_in", _bamio.smc_rows_in), ("smc_rows_out", _bamio.smc_rows_out),                 # include/smc_rows.h
+                        ("smc_soa_view", _bamio.smc_soa_view), ("smc_soa_pack_opts", _bamio.smc_soa_pack_opts),     # include/smc_soa.h
+                        ("smc_soa_pack_sizes", _bamio.smc_soa_pack_sizes), ("smc_soa_pack_bufs", _bamio.smc_soa_pack_bufs),
+                        ("smc_soa_pack_exc", _bamio.smc_soa_pack_exc)):
+        lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "smc_rows.h"', '#include "smc_soa.h"', 'int main(void){',
+                 'printf("size %%zu\\n", sizeof(%s));' % cname]
         for f, _ in cls2._fields_:
             lines.append('printf("%s %%zu\\n", offsetof(%s, %s));' % (f, cname, f))
         lines.append('return 0;}')

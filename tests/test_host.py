@@ -513,3 +513,43 @@ def test_native_output_stage_equals_the_python_rows_filters_and_writers(monkeypa
     res.loc[_ffi.L_STATUS, int(order[7])] = _ffi.ST_NEED_DOWNSAMPLE
     with pytest.raises(RuntimeError, match="Exception thrown in vc"):
         rows.emit_rows(res, None, loci, chroms, refs, 10, order, hp_flags=hp)
+
+
+def test_native_batch_packer_equals_select_plus_compact():
+    """smc_soa_pack (include/smc_soa.h): the reads of a batch gathered and written in the compact wire encodings by one
+    native pass == ReadsSoA.select(idx).compact() made with numpy, array for array; any thread count; plain encodings too."""
+    import numpy as np
+    from smcounter_b200 import _bamio
+    from smcounter_b200.synth import SynthSpec, make_panel
+    ivs = [("chr1", 1000, 1400), ("chr2", 500, 800)]
+    soa, _, _ = make_panel(ivs, SynthSpec(umis_per_locus=25, rpb=2.5, n_frac=0.01, indel_every=60, indel_vaf=0.2), seed=9)
+    rng = np.random.default_rng(3)
+    for plain in (soa.repack(), soa.trim_to_targets(ivs)):
+        for idx in (None, np.flatnonzero(rng.random(plain.n) < 0.6), np.zeros(0, np.int64)):
+            want = (plain if idx is None else plain.select(idx)).compact()
+            for threads in (1, 5):
+                got = _bamio.pack_upload(plain, idx, threads=threads)
+                assert (got.scalar_bits, got.qual_bits, got.seq_bits) == (want.scalar_bits, want.qual_bits, want.seq_bits) == (16, 2, 2)
+                for f in ("ref_id", "pos", "flag", "mapq", "nm", "l_seq", "n_cigar", "umi", "frag_id", "seq", "qual", "cigar", "qual_lut"):
+                    a, b = getattr(got, f), getattr(want, f)
+                    if f == "qual_lut" and got.n == 0:
+                        continue                        # the codebook is the whole file's, whatever the batch holds
+                    assert a.dtype == b.dtype and np.array_equal(a, b), f
+                if plain.store_lo is not None:
+                    assert np.array_equal(got.store_lo, want.store_lo) and np.array_equal(got.store_len, want.store_len)
+                for a, b in zip(got.seq_exc, want.seq_exc):
+                    assert a.dtype == b.dtype and np.array_equal(a, b)
+                if got.n:
+                    r = got.n // 2
+                    L = int(got.stored_len()[r])
+                    assert got.compact_bases(r, 0, L) == want.compact_bases(r, 0, L)
+    # 4-bit bases and a codebook that does not fit 4 bits
+    soa2, _, _ = make_panel(ivs[:1], SynthSpec(umis_per_locus=10, rpb=2.0, q_values=tuple(range(10, 30)), q_probs=tuple([0.05] * 20)), seed=4)
+    plain = soa2.repack()
+    got, want = _bamio.pack_upload(plain, None, seq_bits=4), plain.compact(seq_bits_wanted=4)
+    assert got.qual_bits == want.qual_bits == 8 and got.seq_bits == 4
+    assert np.array_equal(got.seq, want.seq) and np.array_equal(got.qual, want.qual) and np.array_equal(got.seq_off, plain.seq_off)
+    # a read index out of order is refused
+    import pytest
+    with pytest.raises(RuntimeError):
+        _bamio.pack_upload(plain, np.array([3, 2], np.int64))
