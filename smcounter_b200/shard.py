@@ -10,23 +10,24 @@ import numpy as np
 from .soa import Loci, ReadsSoA
 
 
-def estimate_interval_events(reads: ReadsSoA, intervals, chroms) -> np.ndarray:
-    """Estimated pileup read-events per interval = sum over reads of the overlap length with the interval."""
-    cidx = {c: i for i, c in enumerate(chroms)}
-    ends = reads.ref_end()
-    starts = reads.pos.astype(np.int64)
+def estimate_interval_events(reads: ReadsSoA, intervals, chroms, locator: "ReadLocator | None" = None) -> np.ndarray:
+    """Estimated pileup read-events per interval = sum over reads of the overlap length with the interval.  Reads in BAM
+    coordinate order: only the reads that can reach the interval are looked at (ReadLocator.candidates)."""
+    loc = locator if locator is not None else ReadLocator(reads, chroms)
     out = np.zeros(len(intervals), dtype=np.float64)
-    order_by_ref = {}
-    for r in np.unique(reads.ref_id):
-        m = np.flatnonzero(reads.ref_id == r)
-        order_by_ref[int(r)] = (starts[m], ends[m])
+    if loc.sorted:
+        for k, (c, s, e) in enumerate(intervals):
+            lo, hi = loc.candidates(c, s, e)
+            if hi > lo:
+                ov = np.minimum(loc.ends[lo:hi], e) - np.maximum(loc.starts[lo:hi], s)
+                out[k] = float(ov[ov > 0].sum())
+        return out
     for k, (c, s, e) in enumerate(intervals):
-        t = order_by_ref.get(cidx.get(c, -1))
-        if t is None or e <= s:
+        r = loc.cidx.get(c)
+        if r is None or e <= s:
             continue
-        st, en = t
-        lo = np.searchsorted(st, e, side="left")          # reads starting before the interval end (st is sorted: BAM order)
-        ov = np.minimum(en[:lo], e) - np.maximum(st[:lo], s)
+        m = reads.ref_id == r
+        ov = np.minimum(loc.ends[m], e) - np.maximum(loc.starts[m], s)
         out[k] = float(ov[ov > 0].sum())
     return out
 
@@ -167,11 +168,11 @@ def subset_loci(loci: Loci, intervals, chroms):
     return np.flatnonzero(keep)
 
 
-def plan_shards(reads: ReadsSoA, intervals, chroms, n_shards: int):
+def plan_shards(reads: ReadsSoA, intervals, chroms, n_shards: int, locator: "ReadLocator | None" = None):
     """[(interval indices, estimated events)] per shard; intervals keep their BED order inside a shard."""
     if n_shards <= 1:
         return [(list(range(len(intervals))), 0.0)]          # nothing to balance: skip the estimate
-    w = estimate_interval_events(reads, intervals, chroms)
+    w = estimate_interval_events(reads, intervals, chroms, locator)
     shard, load = assign_intervals(w, n_shards)
     return [([int(k) for k in np.flatnonzero(shard == g)], float(load[g])) for g in range(n_shards)]
 

@@ -95,6 +95,7 @@ def _run_shards(reads, intervals, refs, prm: VcParams, gpus, devices, stage_time
     import time
     chroms = reads.chroms
     devices = list(devices) if devices is not None else list(range(max(1, gpus)))
+    t_plan = time.perf_counter()
     locator = ReadLocator(reads, chroms)
     # an interval above the library's per-batch limits (a whole-chromosome BED line, a very deep amplicon) is processed as
     # consecutive sub-intervals; the callers below see one entry per ORIGINAL interval again
@@ -104,11 +105,14 @@ def _run_shards(reads, intervals, refs, prm: VcParams, gpus, devices, stage_time
     if len(pieces) != len(intervals):
         sub = _run_shards(reads, pieces, refs, prm, gpus, devices, stage_times, batch_limits, emit_kw)
         return _regroup_pieces(intervals, pieces, sub)
-    plan = plan_shards(reads, intervals, chroms, len(devices))
+    plan = plan_shards(reads, intervals, chroms, len(devices), locator)
+    pack_threads = max(2, (os.cpu_count() or 2) // max(1, len(devices)))       # the shards of all GPUs pack side by side
     compactable = reads.qual_bits == 8 and reads.scalar_bits == 32 and reads.seq_bits == 4 and os.environ.get("SMC_NATIVE_PACK", "1") != "0"
     per_interval = {}
     errors = [None] * len(plan)
     lock = threading.Lock()
+    if stage_times is not None:
+        stage_times["ms_plan"] = stage_times.get("ms_plan", 0.0) + 1e3 * (time.perf_counter() - t_plan)
 
     def work(g):
         try:
@@ -138,12 +142,16 @@ def _run_shards(reads, intervals, refs, prm: VcParams, gpus, devices, stage_time
                     whole = len(plan) == 1 and len(batches) == 1
                     # the batch's reads, gathered and written in the compact wire encodings by one native pass (include/smc_soa.h)
                     arenas[i].reset()
+                    t_pack = time.perf_counter()
                     if compactable:
-                        sub = pack_upload(reads, None if whole else locator.select(ivs), alloc=arenas[i].take)
+                        sub = pack_upload(reads, None if whole else locator.select(ivs), alloc=arenas[i].take, threads=pack_threads)
                     else:
                         sub = reads if whole else reads.select(locator.select(ivs))
                     loci, bed_order = build_loci(ivs, chroms, refs)
                     t0 = time.perf_counter()
+                    if stage_times is not None:
+                        with lock:
+                            stage_times["ms_select_pack"] = stage_times.get("ms_select_pack", 0.0) + 1e3 * (t0 - t_pack)
                     res = caller.call(sub, loci)
                     tm = caller.timings()
                     keep = draw_keep_masks(caller, res, sub, loci, chroms, prm)        # smCounter.py:496-500
