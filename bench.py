@@ -650,7 +650,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
                 "config": config_dict(args, world),
                 "workload_stats": {"loci_total": int(loci_total), "reads_total": int(reads_total), "pileup_events_per_step": int(events_total),
-                                   "tile_events_per_step_rank0": int(tile_events_rank), "resident_mb_rank0": sum(b[1].nbytes() for b in batches) / 1e6,
+                                   "tile_events_per_step_rank0": int(tile_events_rank), "pileup_events_batch0_rank0": int(tms0["n_pileup_events"]), "resident_mb_rank0": sum(b[1].nbytes() for b in batches) / 1e6,
                                    "reads": "whole reads" if soa0.store_lo is None else "bases / qualities trimmed to each read's target window (store_lo / store_len), "
                                             "%.0f of %d bases per read stored" % (float(soa0.store_len.mean()), int(soa0.l_seq.max())) +
                                             ("; compact upload: %d-bit scalars, %d-bit quality codes, %d-bit bases" % (soa0.scalar_bits, soa0.qual_bits, soa0.seq_bits)

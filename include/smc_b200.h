@@ -105,11 +105,13 @@ typedef struct smc_reads_soa {
      *     is listed in the exception arrays (ascending read index; position = index of the base inside the read's stored
      *     window; its BAM nibble).  Requires the packed layout (seq_off == NULL).  0 or 4 = BAM nibbles as above. */
     int32_t         seq_bits;
-    int32_t         reserved1;
+    int32_t         ref_id_bits;    /* 8: ref_id points to a uint8 array (every reference index < 256); 0 or 32: int32 */
     int64_t         n_seq_exc;
     const uint32_t *seq_exc_read;
     const uint32_t *seq_exc_pos;
     const uint8_t  *seq_exc_nib;
+    int32_t         umi_bits;       /* 32: umi points to a uint32 array (every barcode code < 2^32: barcodes of <= 15 nt); 0 or 64: uint64 */
+    int32_t         reserved2;
 } smc_reads_soa;
 
 /* Target loci: unique, sorted by (ref_id, pos0).  At most 4 194 302 per batch. */

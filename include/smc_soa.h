@@ -52,6 +52,8 @@ typedef struct smc_soa_pack_opts {
     int32_t  qual_bits;             /* 2, 4 or 8 */
     int32_t  seq_bits;              /* 2 or 4 */
     int32_t  threads;               /* <= 0: all */
+    int32_t  ref_id_bits;           /* 8 (every ref_id < 256: checked) or 32 */
+    int32_t  umi_bits;              /* 32 (every barcode code < 2^32: checked) or 64 */
     uint8_t  code_of[256];          /* qual_bits != 8: code of every phred value that occurs (others must not occur: checked) */
 } smc_soa_pack_opts;
 
@@ -66,7 +68,7 @@ typedef struct smc_soa_pack_sizes {
  * by scalar_bits; store_lo / store_len may be NULL when the view has none), seq / qual / cigar the byte / word counts.
  * seq_poff (optional, n_reads + 1 entries) receives the byte offset of every read inside seq (host-side look-ups only). */
 typedef struct smc_soa_pack_bufs {
-    int32_t  *ref_id;
+    void     *ref_id;               /* uint8 or int32 by ref_id_bits */
     int32_t  *pos;
     uint16_t *flag;
     uint8_t  *mapq;
@@ -75,7 +77,7 @@ typedef struct smc_soa_pack_bufs {
     void     *store_lo;
     void     *store_len;
     uint16_t *n_cigar;
-    uint64_t *umi;
+    void     *umi;                  /* uint32 or uint64 by umi_bits */
     uint32_t *frag_id;
     uint8_t  *seq;
     uint8_t  *qual;

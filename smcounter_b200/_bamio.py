@@ -44,7 +44,8 @@ class smc_soa_view(C.Structure):             # include/smc_soa.h
 
 
 class smc_soa_pack_opts(C.Structure):
-    _fields_ = [("scalar_bits", C.c_int32), ("qual_bits", C.c_int32), ("seq_bits", C.c_int32), ("threads", C.c_int32), ("code_of", C.c_uint8 * 256)]
+    _fields_ = [("scalar_bits", C.c_int32), ("qual_bits", C.c_int32), ("seq_bits", C.c_int32), ("threads", C.c_int32), ("ref_id_bits", C.c_int32),
+                ("umi_bits", C.c_int32), ("code_of", C.c_uint8 * 256)]
 
 
 class smc_soa_pack_sizes(C.Structure):
@@ -227,7 +228,9 @@ def upload_codebook(reads: ReadsSoA, threads: int = 0) -> dict:
         code_of[present] = np.arange(len(present), dtype=np.uint8)
     scal = [reads.nm, reads.l_seq] + ([] if reads.store_lo is None else [reads.store_lo, reads.store_len])
     fits = all(len(a) == 0 or (int(a.min()) >= 0 and int(a.max()) < 65536) for a in scal)
-    memo = dict(scalar_bits=16 if fits else 32, qual_bits=bits, qual_lut=lut, code_of=code_of)
+    ref8 = bool(reads.n) and int(reads.ref_id.min()) >= 0 and int(reads.ref_id.max()) < 256
+    umi32 = bool(reads.n) and int(reads.umi.max()) < (1 << 32)
+    memo = dict(scalar_bits=16 if fits else 32, qual_bits=bits, qual_lut=lut, code_of=code_of, ref_id_bits=8 if ref8 else 32, umi_bits=32 if umi32 else 64)
     reads.__dict__["_upload_codebook"] = memo
     return memo
 
@@ -244,6 +247,7 @@ def pack_upload(reads: ReadsSoA, idx=None, alloc=None, seq_bits: int = 2, thread
     take = lambda count, dt: alloc(max(int(count), 1) * np.dtype(dt).itemsize).view(dt)[:int(count)]
     o = smc_soa_pack_opts()
     o.scalar_bits, o.qual_bits, o.seq_bits, o.threads = cb["scalar_bits"], cb["qual_bits"], seq_bits, threads
+    o.ref_id_bits, o.umi_bits = cb["ref_id_bits"], cb["umi_bits"]
     if cb["code_of"] is not None:
         C.memmove(o.code_of, cb["code_of"].ctypes.data, 256)
     v = _view(reads)
@@ -256,8 +260,9 @@ def pack_upload(reads: ReadsSoA, idx=None, alloc=None, seq_bits: int = 2, thread
     try:
         n = int(sz.n_reads)
         sdt = np.uint16 if cb["scalar_bits"] == 16 else np.int32
-        out = dict(ref_id=take(n, np.int32), pos=take(n, np.int32), flag=take(n, np.uint16), mapq=take(n, np.uint8), nm=take(n, sdt),
-                   l_seq=take(n, sdt), n_cigar=take(n, np.uint16), umi=take(n, np.uint64), frag_id=take(n, np.uint32),
+        out = dict(ref_id=take(n, np.uint8 if cb["ref_id_bits"] == 8 else np.int32), pos=take(n, np.int32), flag=take(n, np.uint16),
+                   mapq=take(n, np.uint8), nm=take(n, sdt), l_seq=take(n, sdt), n_cigar=take(n, np.uint16),
+                   umi=take(n, np.uint32 if cb["umi_bits"] == 32 else np.uint64), frag_id=take(n, np.uint32),
                    seq=take(sz.seq_bytes, np.uint8), qual=take(sz.qual_bytes, np.uint8), cigar=take(sz.n_cigar_words, np.uint32))
         if reads.store_lo is not None:
             out["store_lo"], out["store_len"] = take(n, sdt), take(n, sdt)

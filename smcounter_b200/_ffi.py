@@ -37,8 +37,8 @@ class smc_reads_soa(C.Structure):
                 ("frag_id", _vp), ("seq", _vp), ("seq_bytes", C.c_int64), ("qual", _vp), ("qual_bytes", C.c_int64),
                 ("cigar", _vp), ("n_cigar_words", C.c_int64), ("store_lo", _vp), ("store_len", _vp),
                 ("scalar_bits", C.c_int32), ("qual_bits", C.c_int32), ("qual_lut", _vp),
-                ("seq_bits", C.c_int32), ("reserved1", C.c_int32), ("n_seq_exc", C.c_int64), ("seq_exc_read", _vp), ("seq_exc_pos", _vp),
-                ("seq_exc_nib", _vp)]
+                ("seq_bits", C.c_int32), ("ref_id_bits", C.c_int32), ("n_seq_exc", C.c_int64), ("seq_exc_read", _vp), ("seq_exc_pos", _vp),
+                ("seq_exc_nib", _vp), ("umi_bits", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class smc_loci(C.Structure):

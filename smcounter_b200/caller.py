@@ -215,6 +215,8 @@ class GpuCaller:
         s.scalar_bits, s.qual_bits = int(getattr(r, "scalar_bits", 32)), int(getattr(r, "qual_bits", 8))
         s.qual_lut = p(getattr(r, "qual_lut", None))
         s.seq_bits = int(getattr(r, "seq_bits", 4))
+        s.ref_id_bits = 8 if r.ref_id.dtype == np.uint8 else 32
+        s.umi_bits = 32 if r.umi.dtype == np.uint32 else 64
         exc = getattr(r, "seq_exc", None)
         if s.seq_bits == 2 and exc is not None and len(exc[0]):
             s.n_seq_exc, s.seq_exc_read, s.seq_exc_pos, s.seq_exc_nib = len(exc[0]), p(exc[0]), p(exc[1]), p(exc[2])

@@ -101,7 +101,7 @@ struct smc_ctx {
         d_cigar, d_store_lo, d_store_len;
     bool has_store = false;                     // reads carry a stored window (smc_reads_soa::store_lo / store_len)
     int qual_bits = 8;                          // 4 / 2: compact qualities were uploaded (d_qual_packed) and are expanded into d_qual
-    DevBuf d_qual_packed, d_qual_poff, d_qual_lut, d_stage16, d_spill, d_seq_packed, d_seq_poff, d_exc_read, d_exc_pos, d_exc_nib;
+    DevBuf d_qual_packed, d_qual_poff, d_qual_lut, d_stage16, d_stage_ids, d_spill, d_seq_packed, d_seq_poff, d_exc_read, d_exc_pos, d_exc_nib;
     int seq_bits = 4; int64_t n_seq_exc = 0;    // 2: compact bases were uploaded (d_seq_packed) and are expanded into d_seq
     uint32_t spill_cap = 0;                     // records in the k_merge spill pool (grows x4 on GF_SPILL_FULL)
     const uint32_t* inv_ptr = nullptr;          // read index -> sorted position (lives in d_v0 or d_v1 after the read sort)
@@ -151,7 +151,7 @@ static std::vector<DevBuf*> all_bufs(smc_ctx* ctx) {
                       &ctx->d_s_pi, &ctx->d_s_rep_read, &ctx->d_s_rep_qpos, &ctx->d_s_len, &ctx->d_dyn_first, &ctx->d_tasks,
                       &ctx->d_list_idx, &ctx->d_list_count, &ctx->d_list_off, &ctx->d_list_umi, &ctx->d_list_first,
                       &ctx->d_hp_bases, &ctx->d_hp_meta, &ctx->d_hp_flags, &ctx->d_pipe_need, &ctx->d_umi_table,
-                      &ctx->d_qual_packed, &ctx->d_qual_poff, &ctx->d_qual_lut, &ctx->d_stage16, &ctx->d_spill,
+                      &ctx->d_qual_packed, &ctx->d_qual_poff, &ctx->d_qual_lut, &ctx->d_stage16, &ctx->d_stage_ids, &ctx->d_spill,
                       &ctx->d_seq_packed, &ctx->d_seq_poff, &ctx->d_exc_read, &ctx->d_exc_pos, &ctx->d_exc_nib};
 }
 
@@ -501,7 +501,9 @@ static int pipe_chunks_for(const smc_reads_soa* R) {
     if (const char* ev = getenv("SMC_PIPE_CHUNKS")) { long v = atol(ev); if (v >= 1 && v <= SMC_PIPE_MAX) return (int)v; }
     const int64_t payload = R->seq_bytes + R->qual_bytes;
     if (R->n_reads < 65536 || payload < (96ll << 20)) return 1;
-    const int64_t g = payload / (24ll << 20);          // A/B on B200 (320 MB payload): 6 chunks 9.79 ms, 8: 9.70, 12: 9.57, 16: 9.59
+    // A/B on B200, two contexts per GPU, 145 MB compact payload: 3 chunks 23.99 ms per 4 batches, 4: 24.11, 6: 24.49, 9: 24.51
+    // (one context, 320 MB plain payload, round 1: 6 chunks 9.79 ms, 12: 9.57)
+    const int64_t g = payload / (48ll << 20);
     return (int)(g < 2 ? 2 : g > 12 ? 12 : g);
 }
 
@@ -563,9 +565,26 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
     if (sbits == 2 && (R->seq_off || R->n_seq_exc < 0 || (R->n_seq_exc > 0 && (!R->seq_exc_read || !R->seq_exc_pos || !R->seq_exc_nib)))) {
         ctx->err = "smc_upload: compact bases need the packed layout (seq_off == NULL) and consistent exception arrays"; return SMC_E_ARG;
     }
-    UP(ctx->d_ref_id, R->ref_id, n, int32_t); UP(ctx->d_pos, R->pos, n, int32_t); UP(ctx->d_flag, R->flag, n, uint16_t);
+    if ((R->ref_id_bits != 0 && R->ref_id_bits != 32 && R->ref_id_bits != 8) || (R->umi_bits != 0 && R->umi_bits != 64 && R->umi_bits != 32)) {
+        ctx->err = "smc_upload: ref_id_bits must be 0, 8 or 32 and umi_bits 0, 32 or 64"; return SMC_E_ARG;
+    }
+    const bool ref8 = R->ref_id_bits == 8, umi32 = R->umi_bits == 32;
+    if (!ref8) UP(ctx->d_ref_id, R->ref_id, n, int32_t);
+    UP(ctx->d_pos, R->pos, n, int32_t); UP(ctx->d_flag, R->flag, n, uint16_t);
     UP(ctx->d_mapq, R->mapq, n, uint8_t);
-    UP(ctx->d_ncig, R->n_cigar, n, uint16_t); UP(ctx->d_umi, R->umi, n, uint64_t); UP(ctx->d_frag, R->frag_id, n, uint32_t);
+    UP(ctx->d_ncig, R->n_cigar, n, uint16_t); UP(ctx->d_frag, R->frag_id, n, uint32_t);
+    if (!umi32) UP(ctx->d_umi, R->umi, n, uint64_t);
+    if (ref8 || umi32) {
+        // narrow reference indices / barcode codes: staged back to back (u32 codes first), widened on the device
+        ENSURE(ctx->d_stage_ids, (size_t)(n ? n : 1) * 5);
+        uint32_t* st32 = ctx->d_stage_ids.as<uint32_t>();
+        uint8_t* st8 = ctx->d_stage_ids.as<uint8_t>() + (size_t)n * 4;
+        if (umi32) { CK(ctx->d_umi.ensure((size_t)(n ? n : 1) * 8)); if (n) { ALLOC_SYNC(); CK(cudaMemcpyAsync(st32, R->umi, (size_t)n * 4, cudaMemcpyHostToDevice, up_st)); bytes += n * 4; } }
+        if (ref8) { CK(ctx->d_ref_id.ensure((size_t)(n ? n : 1) * 4)); if (n) { ALLOC_SYNC(); CK(cudaMemcpyAsync(st8, R->ref_id, (size_t)n, cudaMemcpyHostToDevice, up_st)); bytes += n; } }
+        SYNC_UP();
+        if (umi32) LAUNCH(k_widen_u32, nblk(n, 256), 256, 0, st32, n, ctx->d_umi.as<int64_t>());
+        if (ref8) LAUNCH(k_widen_u8, nblk(n, 256), 256, 0, st8, n, ctx->d_ref_id.as<int32_t>());
+    }
     if ((R->store_lo == nullptr) != (R->store_len == nullptr)) { ctx->err = "smc_upload: store_lo and store_len must be given together"; return SMC_E_ARG; }
     ctx->has_store = R->store_lo != nullptr;
     if (!s16) {

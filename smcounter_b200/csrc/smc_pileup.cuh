@@ -235,6 +235,10 @@ __global__ void __launch_bounds__(256) k_widen_u16(const uint16_t* __restrict__ 
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r < n) out[r] = (int32_t)in[r];
 }
+__global__ void __launch_bounds__(256) k_widen_u8(const uint8_t* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) out[r] = (int32_t)in[r];
+}
 // compact qualities (smc_reads_soa::qual_bits 4 / 2) -> one phred byte per stored base, one warp per read over the reads
 // [range[0], range[1]) (grid-stride).  Pipelined upload: the compact payload is stored in read order, so the reads whose last
 // byte arrives with chunk c are a contiguous range; k_chunk_reads finds the range borders by binary search over the offsets.

@@ -107,7 +107,8 @@ extern "C" int smc_soa_pack_begin(const smc_soa_view* v, const int64_t* idx, int
                                   smc_soa_pack** out, smc_soa_pack_sizes* sizes) {
     if (!v || !opts || !out || !sizes || v->n_reads < 0 || (idx && n_idx < 0)) return SMC_SOA_E_ARG;
     if ((opts->scalar_bits != 16 && opts->scalar_bits != 32) || (opts->qual_bits != 2 && opts->qual_bits != 4 && opts->qual_bits != 8) ||
-        (opts->seq_bits != 2 && opts->seq_bits != 4) || ((v->store_lo == nullptr) != (v->store_len == nullptr)))
+        (opts->seq_bits != 2 && opts->seq_bits != 4) || (opts->ref_id_bits != 8 && opts->ref_id_bits != 32) ||
+        (opts->umi_bits != 32 && opts->umi_bits != 64) || ((v->store_lo == nullptr) != (v->store_len == nullptr)))
         return SMC_SOA_E_ARG;
     smc_soa_pack* h = new (std::nothrow) smc_soa_pack();
     if (!h) return SMC_SOA_E_MEM;
@@ -139,6 +140,7 @@ extern "C" int smc_soa_pack_begin(const smc_soa_view* v, const int64_t* idx, int
                                 (!v->store_lo || ((uint32_t)v->store_lo[r] < 65536u && (uint32_t)v->store_len[r] < 65536u));
                 if (!ok) { bad[(size_t)t] = 1; return; }
             }
+            if ((opts->ref_id_bits == 8 && (uint32_t)v->ref_id[r] >= 256u) || (opts->umi_bits == 32 && (v->umi[r] >> 32) != 0)) { bad[(size_t)t] = 1; return; }
             lo = std::min(lo, v->frag_id[r]); hi = std::max(hi, v->frag_id[r]);
         }
         fmin[(size_t)t] = lo; fmax[(size_t)t] = hi;
@@ -195,7 +197,7 @@ extern "C" int smc_soa_pack_fill(smc_soa_pack* h, const smc_soa_pack_bufs* B, sm
                   (h->cig_off[(size_t)n] && !B->cigar)))
         return SMC_SOA_E_ARG;
     const int T = h->threads, qb = h->o.qual_bits, sb = h->o.seq_bits;
-    const bool s16 = h->o.scalar_bits == 16;
+    const bool s16 = h->o.scalar_bits == 16, ref8 = h->o.ref_id_bits == 8, umi32 = h->o.umi_bits == 32;
     // BAM nibble -> 2-bit code (A 1, C 2, G 4, T 8); everything else travels as code 0 plus an exception
     uint8_t code2[16], plain[16];
     for (int i = 0; i < 16; ++i) { code2[i] = 0; plain[i] = 0; }
@@ -207,8 +209,10 @@ extern "C" int smc_soa_pack_fill(smc_soa_pack* h, const smc_soa_pack_bufs* B, sm
         std::vector<Exc>& ex = excs[(size_t)t];
         for (size_t k = a; k < e; ++k) {
             const int64_t r = h->src((int64_t)k);
-            B->ref_id[k] = v.ref_id[r]; B->pos[k] = v.pos[r]; B->flag[k] = v.flag[r]; B->mapq[k] = v.mapq[r];
-            B->n_cigar[k] = v.n_cigar[r]; B->umi[k] = v.umi[r];
+            if (ref8) ((uint8_t*)B->ref_id)[k] = (uint8_t)v.ref_id[r]; else ((int32_t*)B->ref_id)[k] = v.ref_id[r];
+            if (umi32) ((uint32_t*)B->umi)[k] = (uint32_t)v.umi[r]; else ((uint64_t*)B->umi)[k] = v.umi[r];
+            B->pos[k] = v.pos[r]; B->flag[k] = v.flag[r]; B->mapq[k] = v.mapq[r];
+            B->n_cigar[k] = v.n_cigar[r];
             B->frag_id[k] = h->frag_rank[v.frag_id[r] - h->frag_lo];
             if (s16) {
                 ((uint16_t*)B->nm)[k] = (uint16_t)v.nm[r]; ((uint16_t*)B->l_seq)[k] = (uint16_t)v.l_seq[r];

@@ -187,7 +187,7 @@ class ReadsSoA:
         qualities (sequencers that bin qualities; a batch with more keeps one byte per base), 2-bit bases with a side list for
         the non-ACGT ones (`seq_bits_wanted=4` keeps BAM's nibbles).  Needs a packed layout (repack() / trim_to_targets() /
         select()).  On the cfg-2 panel batch: 157 -> 72 bytes per read over PCIe."""
-        if self.qual_bits != 8 or self.scalar_bits != 32 or self.seq_bits != 4:
+        if self.qual_bits != 8 or self.scalar_bits != 32 or self.seq_bits != 4 or self.ref_id.dtype != np.int32 or self.umi.dtype != np.uint64:
             raise ValueError("already compact")
         src = self if self.packed else self.repack()
         kw = {f: getattr(src, f) for f in ("ref_id", "pos", "flag", "mapq", "seq_off", "qual_off", "cigar_off", "n_cigar", "umi", "frag_id",
@@ -241,6 +241,11 @@ class ReadsSoA:
             cat = lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(0, dt)
             exc = (cat(exc_read, np.uint32), cat(exc_pos, np.uint32), cat(exc_nib, np.uint8))
         kw["seq"] = seq
+        # reference indices below 256 travel as bytes, barcode codes below 2^32 (barcodes of <= 15 nt) as 32-bit words
+        if src.n and int(src.ref_id.min()) >= 0 and int(src.ref_id.max()) < 256:
+            kw["ref_id"] = src.ref_id.astype(np.uint8)
+        if src.n and int(src.umi.max()) < (1 << 32):
+            kw["umi"] = src.umi.astype(np.uint32)
         out = ReadsSoA(nm=scal["nm"], l_seq=scal["l_seq"], store_lo=scal["store_lo"], store_len=scal["store_len"], qual=qual, packed=True,
                         scalar_bits=scalar_bits, qual_bits=bits, qual_lut=lut, seq_bits=seq_bits, seq_exc=exc, **kw)
         if seq_bits == 2:            # what compact_bases() looks reads up with (allele names of insertions), made here once

@@ -395,13 +395,20 @@ def test_compact_upload_encodings_give_identical_bits(nq, seq_bits):
 
     def enc(soa):
         out = soa.trim_to_targets(PIPE_IVS).compact(seq_bits_wanted=seq_bits)
-        seen.update(qual_bits=out.qual_bits, seq_bits=out.seq_bits, n_exc=0 if out.seq_exc is None else len(out.seq_exc[0]), scalar_bits=out.scalar_bits)
+        seen.update(qual_bits=out.qual_bits, seq_bits=out.seq_bits, n_exc=0 if out.seq_exc is None else len(out.seq_exc[0]), scalar_bits=out.scalar_bits,
+                    umi=str(out.umi.dtype), ref_id=str(out.ref_id.dtype))
         return out
 
-    for chunks in ("1", "5"):
-        problems, stats, _ = _with_env("SMC_PIPE_CHUNKS", chunks, lambda: run_case(PIPE_IVS, spec, prm, seed=71, gpu_mutate=enc))
+    def twelve_nt(soa):                 # the synthetic barcodes are 16-mers (33-bit codes); QIAseq's are 12-mers: 25-bit codes, sent as uint32
+        soa.umi = (np.uint64(1) << np.uint64(24)) | (soa.umi & np.uint64(0xFFFFFF))
+        return soa
+
+    for chunks, short in (("1", False), ("5", False), ("5", True)):
+        problems, stats, _ = _with_env("SMC_PIPE_CHUNKS", chunks, lambda: run_case(PIPE_IVS, spec, prm, seed=71, mutate=twelve_nt if short else None,
+                                                                                   gpu_mutate=enc))
         print(stats, seen)
         assert not problems, "\n".join(problems)
+        assert seen["umi"] == ("uint32" if short else "uint64") and seen["ref_id"] == "uint8"
     assert seen["qual_bits"] == (2 if nq + 1 <= 4 else 4 if nq + 1 <= 16 else 8) and seen["scalar_bits"] == 16   # + quality 2 of the 'N's
     assert seen["seq_bits"] == seq_bits and (seq_bits == 4 or seen["n_exc"] > 0)
 
