@@ -373,7 +373,7 @@ def pipeline_leg(args, mine, soa, refs, device):
 def strong_leg(args, ivs, soa, refs, n_gpus):
     """Strong scaling of the product path: ONE fixed panel (the rank-0 batch 0: its intervals and all their reads, trimmed
     as the BAM decoder delivers them) through ``smCounter.call_loci(gpus=N)`` from ONE process -- the drop-in for the
-    reference's Pool fan-out (smCounter.py:683-685): shards by BED interval, one host thread and two contexts per GPU,
+    reference's Pool fan-out (smCounter.py:683-685): shards by BED interval, one host thread and up to three contexts per GPU,
     rows formatted by the native output stage.  Median of 5 calls after one warm-up."""
     from smcounter_b200.smCounter import call_loci
     prm = vc_params(args)
@@ -402,7 +402,7 @@ def strong_leg(args, ivs, soa, refs, n_gpus):
             "ms_gpu_call_sum": st.get("ms_gpu_call"), "ms_format_rows_sum": st.get("ms_format_rows"),
             "batches": st.get("batches"),
             "what": "smCounter.call_loci(reads, intervals, gpus=%d) on one fixed panel from one process (plan_shards by BED interval, one thread and "
-                    "two contexts per GPU, each batch packed natively into pinned buffers, rows through smc_rows_emit); total work fixed as N grows" % n_gpus}
+                    "up to three contexts per GPU, each batch packed natively into pinned buffers, rows through smc_rows_emit); total work fixed as N grows" % n_gpus}
 
 
 def main():
@@ -537,11 +537,11 @@ def main():
 
     # ---------------- end to end: host buffers in, host buffers out, every step: smc_call_batch (pipelined upload, kernels,
     # download) and the device HP / LowC pass over the candidates of the batch (smc_hp_lowcomp)
-    # As smCounter._run_shards does: two contexts and two host threads per GPU, so that one batch uploads while the previous one
+    # As smCounter._run_shards does: three contexts and three host threads per GPU, so that one batch uploads while the previous ones
     # computes and downloads (ctypes drops the GIL inside the library).
     import queue
     from concurrent.futures import ThreadPoolExecutor
-    n_ctx = min(int(os.environ.get("SMC_CTX_PER_GPU", "2")), NB)
+    n_ctx = min(int(os.environ.get("SMC_CTX_PER_GPU", "3")), NB)
     callers = [GpuCaller(prm, device=local_rank) for _ in range(n_ctx)]
     free = queue.SimpleQueue()
     for i in range(n_ctx):
@@ -567,11 +567,15 @@ def main():
             free.put(i)
 
     def e2e_pass(steps):
-        # the batches of all the steps go through the two contexts as one stream, the way a long job's shards do
+        # the batches of all the steps go through the contexts as one stream, the way a long job's shards do
         # (smCounter._run_shards): no barrier between steps, so a batch uploads while the one before it computes
         tms = list(pool.map(e2e_batch, [k % NB for k in range(steps * NB)]))
         last = tms[-NB:]
         return sum(int(t["bytes_h2d"]) for t in last), sum(int(t["bytes_d2h"]) for t in last), tms[-1]
+    # warm-up: every context meets every batch once (its device buffers grow to the largest one), then the streamed passes
+    for i in range(len(callers)):
+        for k in range(NB):
+            callers[i].call(batches[k][1], batches[k][3], out=outs[k])
     e2e_pass(min(args.warmup, 2))
     barrier()
     t1 = time.perf_counter()
@@ -661,8 +665,8 @@ def main():
                         "last_batch": {"ms_h2d": e2e_tm["ms_h2d"], "ms_device": e2e_tm["ms_total_device"], "ms_d2h": e2e_tm["ms_d2h"],
                                        "h2d_gbs": e2e_tm["bytes_h2d"] / e2e_tm["ms_h2d"] / 1e6 if e2e_tm["ms_h2d"] > 0 else None},
                         "what": "per step and GPU: %d x (smc_call_batch from pinned host buffers -- scalars first, bases / qualities in %d chunks on a copy "
-                                "stream, %d pileup launch pairs as they arrive -- + download + smc_hp_lowcomp over the batch's candidates); two contexts / host threads, so the next batch uploads while this one computes"
-                                % (NB, e2e_tm["pipe_chunks"], e2e_tm["pipe_launches"])},
+                                "stream, %d pileup launch pairs as they arrive -- + download + smc_hp_lowcomp over the batch's candidates); %d contexts / host threads per GPU taking turns on the link, so the next batch uploads while the previous ones compute and download"
+                                % (NB, e2e_tm["pipe_chunks"], e2e_tm["pipe_launches"], n_ctx)},
                 "per_rank": per_rank,
                 "gpu_launches": int(launches),
                 "stage_ms_per_batch_rank0": {k: v / nrun for k, v in stage.items()},

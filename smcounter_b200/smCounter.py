@@ -121,9 +121,9 @@ def _run_shards(reads, intervals, refs, prm: VcParams, gpus, devices, stage_time
                 return
             # a shard goes through its GPU as a stream of batches under the library's per-batch limits
             batches = plan_batches(locator, intervals, idxs, **(batch_limits or {}))
-            # Two contexts per GPU, two host threads: while one batch computes and downloads, the next one is already uploading
+            # Up to three contexts and host threads per GPU: while one batch computes and another downloads, the next one is already uploading
             # (ctypes drops the GIL inside the library), so the PCIe link and the SMs are both kept busy across batches.
-            n_ctx = max(1, min(int(os.environ.get("SMC_CTX_PER_GPU", "2")), len(batches)))
+            n_ctx = max(1, min(int(os.environ.get("SMC_CTX_PER_GPU", "3")), len(batches)))
             t_create = time.perf_counter()
             callers = [GpuCaller(prm, devices[g]) for _ in range(n_ctx)]
             arenas = [_take_arena() for _ in range(n_ctx)]      # the upload buffers of each context, recycled batch after batch
