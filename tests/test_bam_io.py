@@ -162,3 +162,49 @@ def test_native_decoder_parallel_passes_equal_single_thread(tmp_path):
         fh.write(bam.bgzf_compress(raw[:len(raw) - 1000], 1))
     with pytest.raises(ValueError, match="truncated BAM record"):
         bam.read_bam(cut, ivs, native=True, threads=4)
+
+
+@pytest.mark.parametrize("native", _decoders())
+def test_bgzf_streams_as_other_writers_make_them(tmp_path, native):
+    """BGZF as written by tools other than ours: blocks of irregular sizes that cut records (and even the 4-byte block_size
+    field) in two, every deflate flavour (stored blocks, fixed Huffman, dynamic Huffman at levels 1 and 9), an extra gzip
+    subfield before the BC one, an empty block in the middle of the file and the standard EOF marker at the end."""
+    import zlib
+    s, refs, ivs = _panel(seed=11)
+    path = str(tmp_path / "a.bam")
+    bam.write_bam(path, s, refs.lengths)
+    want = bam.read_bam(path, native=native)
+    raw = bam.bgzf_decompress(open(path, "rb").read())
+    rng = np.random.default_rng(7)
+    flavours = [(0, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED), (1, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_HUFFMAN_ONLY)]
+    out, p, k = [], 0, 0
+
+    def block(chunk, level, strategy, extra_subfield):
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+        c = co.compress(chunk) + co.flush()
+        extra = (b"XY\x03\x00abc" if extra_subfield else b"") + b"BC\x02\x00"
+        xlen = len(extra) + 2
+        bsize = 12 + xlen + len(c) + 8 - 1
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", xlen) + extra + struct.pack("<H", bsize) + c +
+                struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+    while p < len(raw):
+        n = int(rng.choice([1, 3, 37, 501, 4099, 30011]))
+        chunk = raw[p:p + n]
+        level, strategy = flavours[k % len(flavours)]
+        out.append(block(chunk, level, strategy, k % 3 == 1))
+        if k == 5:
+            out.append(block(b"", 6, zlib.Z_DEFAULT_STRATEGY, False))          # an empty block inside the file
+        p += n
+        k += 1
+    out.append(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))   # the EOF marker of the SAM specification
+    path2 = str(tmp_path / "b.bam")
+    with open(path2, "wb") as fh:
+        fh.write(b"".join(out))
+    got = bam.read_bam(path2, native=native)
+    assert got.n == want.n > 0
+    for f in FIELDS:
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f
+    got_t = bam.read_bam(path2, intervals=ivs, native=native, threads=3) if native else bam.read_bam(path2, intervals=ivs, native=native)
+    want_t = bam.read_bam(path, intervals=ivs, native=native)
+    for f in FIELDS:
+        assert np.array_equal(getattr(got_t, f), getattr(want_t, f)), f
