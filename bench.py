@@ -65,7 +65,7 @@ def parse_args(argv=None):
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (call_loci(gpus=N) on one fixed panel)")
     ap.add_argument("--whole-reads", action="store_true", help="upload whole reads instead of the target windows (store_lo/store_len)")
     ap.add_argument("--no-compact", action="store_true", help="upload one byte per quality and 32-bit scalars instead of the compact ABI v3 encodings")
-    ap.add_argument("--pipeline-intervals", type=int, default=12,
+    ap.add_argument("--pipeline-intervals", type=int, default=96,
                     help="intervals of the rank-0 batch run through the whole CLI path (BAM decode -> files); 0 = skip")
     ap.add_argument("--pipeline-repeats", type=int, default=5)
     a = ap.parse_args(argv)

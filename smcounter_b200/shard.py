@@ -81,18 +81,22 @@ class ReadLocator:
     def select(self, intervals) -> np.ndarray:
         """Ascending indices of the reads that touch one of ``intervals`` (BAM order is kept)."""
         n = self.reads.n
-        keep = np.zeros(n, dtype=bool)
         if self.sorted:
-            for (c, s, e) in intervals:
-                lo, hi = self.candidates(c, s, e)
-                if hi > lo:
-                    keep[lo:hi] |= self.ends[lo:hi] > s
-        else:
-            for (c, s, e) in intervals:
-                r = self.cidx.get(c)
-                if r is None or e <= s:
-                    continue
-                keep |= (self.reads.ref_id == r) & (self.starts < e) & (self.ends > s)
+            # only the index span the candidates of these intervals cover is looked at (a shard of a big file is a small part of it)
+            spans = [(lo, hi, s) for (lo, hi), s in ((self.candidates(c, s, e), s) for (c, s, e) in intervals) if hi > lo]
+            if not spans:
+                return np.zeros(0, dtype=np.int64)
+            base, top = min(t[0] for t in spans), max(t[1] for t in spans)
+            keep = np.zeros(top - base, dtype=bool)
+            for (lo, hi, s) in spans:
+                keep[lo - base:hi - base] |= self.ends[lo:hi] > s
+            return np.flatnonzero(keep) + base
+        keep = np.zeros(n, dtype=bool)
+        for (c, s, e) in intervals:
+            r = self.cidx.get(c)
+            if r is None or e <= s:
+                continue
+            keep |= (self.reads.ref_id == r) & (self.starts < e) & (self.ends > s)
         return np.flatnonzero(keep)
 
 
