@@ -30,7 +30,8 @@ from oracle import ref_build, ref_shims
 from oracle import smcounter_oracle as orc
 from fuzz import CASES, case_inputs, fuzz_case
 from smcounter_b200.soa import soa_to_records
-from smcounter_b200.synth import make_panel
+from smcounter_b200.caller import VcParams
+from smcounter_b200.synth import SynthSpec, make_panel
 from smcounter_b200.targets import loc_list
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -334,3 +335,37 @@ def test_oracle_reproduces_the_committed_reference_rows():
         assert got == want, name
         n += len(got)
     assert n > 1000
+
+
+# ---------------------------------------------------------------------------------------------- vc() at the depths of BASELINE.json's configs
+DEEP_TASKS = [  # (name, SynthSpec keywords, VcParams keywords, interval, seed)
+    ("cfg2", dict(umis_per_locus=3000, rpb=4.0, snv_every=7, snv_vaf=0.01), dict(mtDepth=3000, rpb=4.0), ("chr1", 5000 + 40 * k, 5008 + 40 * k), 900 + k)
+    for k in range(4)] + [
+    ("cfg1", dict(umis_per_locus=4000, rpb=9.8, snv_every=5, snv_vaf=0.02, indel_every=9, indel_vaf=0.02), dict(mtDepth=3612, rpb=8.6, mtDrop=1, hpLen=8),
+     ("chr17", 41243700 + 30 * k, 41243705 + 30 * k), 910 + k) for k in range(2)] + [
+    ("cfg3", dict(umis_per_locus=20000, rpb=4.0, snv_every=3, snv_vaf=0.005), dict(mtDepth=20000, rpb=4.0), ("chr2", 7000 + 50 * k, 7002 + 50 * k), 920 + k)
+    for k in range(2)]
+
+
+def _deep_worker(task):
+    name, spec_kw, prm_kw, iv, seed = task
+    rows = both_rows([iv], SynthSpec(**spec_kw), VcParams(**prm_kw), seed)
+    return name, len(rows), [(name, seed) + c for c in (classify(a, b, d) for (a, b, d) in rows) if c is not None], \
+        max(d.get("nBC", 0) for (_, _, d) in rows)
+
+
+@needs_ref
+def test_reference_vc_equals_oracle_at_benchmark_depth():
+    """The same comparison at the depths the BASELINE.json configurations run at (3 000 / 4 000 / 20 000 barcodes per locus,
+    rpb 4 / 9.8): thousands of barcodes go through the Python-2 dict models and calProb per locus, PI sums run over thousands
+    of terms in dict order on the reference side and exactly here."""
+    ref_build.load("py2")
+    ctx = multiprocessing.get_context("fork")
+    with ctx.Pool(min(os.cpu_count() or 1, len(DEEP_TASKS))) as pool:
+        res = pool.map(_deep_worker, DEEP_TASKS, chunksize=1)
+    n = sum(r[1] for r in res)
+    diffs = [d for r in res for d in r[2]]
+    print("reference vc() vs oracle at depth: %d loci, deepest %s barcodes, differences: %s" % (n, max(r[3] for r in res), diffs))
+    assert n == sum(t[3][2] - t[3][1] for t in DEEP_TASKS)
+    assert not [d for d in diffs if d[2] == "BAD"], diffs[:5]
+    assert max(r[3] for r in res if r[0] == "cfg3") > 12000 and max(r[3] for r in res if r[0] == "cfg2") > 2000
