@@ -46,6 +46,16 @@ CASES = {
 }
 
 
+# the depths of BASELINE.json's configurations, a few loci each: part of the committed reference-rows fixture
+# (tests/golden/ref_rows.json), i.e. the GPU path is held against rows the reference's own code printed at these depths
+DEEP_CASES = {
+    "deep_cfg2": (dict(umis_per_locus=3000, rpb=4.0, snv_every=5, snv_vaf=0.01), dict(mtDepth=3000, rpb=4.0), [("chr1", 5000, 5010)], 31),
+    "deep_cfg1": (dict(umis_per_locus=4000, rpb=9.8, snv_every=4, snv_vaf=0.02, indel_every=7, indel_vaf=0.02), dict(mtDepth=3612, rpb=8.6, mtDrop=1, hpLen=8),
+                  [("chr17", 41243700, 41243706)], 32),
+    "deep_cfg3": (dict(umis_per_locus=20000, rpb=4.0, snv_every=2, snv_vaf=0.005), dict(mtDepth=20000, rpb=4.0), [("chr2", 7000, 7003)], 33),
+}
+
+
 def case_inputs(name):
-    spec_kw, prm_kw, intervals, seed = CASES[name]
+    spec_kw, prm_kw, intervals, seed = CASES[name] if name in CASES else DEEP_CASES[name]
     return intervals, SynthSpec(**spec_kw), VcParams(**prm_kw), seed

@@ -1,6 +1,6 @@
 """Generates tests/golden/ref_rows.json: the 45-column rows printed by the REFERENCE'S OWN vc() (/root/reference/smCounter.py,
-run through oracle/ref_build.py + oracle/ref_shims.py with Python-2 container order) on the hand-written parity cases and
-a few cases of the fuzz corpus.  Run in the build container (the GPU box has no /root/reference):
+run through oracle/ref_build.py + oracle/ref_shims.py with Python-2 container order) on the hand-written parity cases, a few
+loci at the depths of the BASELINE.json configurations and a few cases of the fuzz corpus.  Run in the build container (the GPU box has no /root/reference):
 
     python tests/golden/make_ref_rows.py
 """
@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-from fuzz import CASES, case_inputs, fuzz_case                 # noqa: E402
+from fuzz import CASES, DEEP_CASES, case_inputs, fuzz_case     # noqa: E402
 from oracle import ref_build, ref_shims                         # noqa: E402
 from oracle import smcounter_oracle as orc                      # noqa: E402
 from smcounter_b200.soa import soa_to_records                   # noqa: E402
@@ -26,7 +26,7 @@ FUZZ = (101, 104, 107, 110)
 def main():
     ref = ref_build.load("py2")
     cases = {}
-    todo = [(n,) + case_inputs(n) for n in sorted(CASES)]
+    todo = [(n,) + case_inputs(n) for n in sorted(CASES) + sorted(DEEP_CASES)]
     for seed in FUZZ:
         ivs, spec, prm = fuzz_case(seed)
         todo.append(("fuzz%d" % seed, ivs, spec, prm, seed))
