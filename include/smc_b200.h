@@ -92,7 +92,8 @@ typedef struct smc_reads_soa {
     const int32_t  *store_lo;
     const int32_t  *store_len;
     /* Optional compact encodings (ABI v3): fewer bytes over PCIe, expanded on the device in one pass.  All zero / NULL = off.
-     *   scalar_bits 16: l_seq, nm, store_lo and store_len point to uint16 arrays (every value < 65536) instead of int32.
+     *   scalar_bits 16 / 8: l_seq, nm, store_lo and store_len point to uint16 / uint8 arrays (every value < 65536 / < 256:
+     *     reads of up to 255 bases) instead of int32.
      *   qual_bits 4 or 2: qual[] holds one qual_bits-wide code per stored base, low bits first, every read starting on a byte
      *     boundary ((stored bases * qual_bits + 7) / 8 bytes per read, qual_bytes = their sum); the phred value of code c is
      *     qual_lut[c] (16 or 4 entries).  Sequencers that bin qualities (4 - 8 distinct values) fit 2 or 4 bits.  Requires the

@@ -48,7 +48,7 @@ typedef struct smc_soa_view {
 } smc_soa_view;
 
 typedef struct smc_soa_pack_opts {
-    int32_t  scalar_bits;           /* 16 or 32 (16 needs every nm / l_seq / store_lo / store_len < 65536: checked) */
+    int32_t  scalar_bits;           /* 8, 16 or 32 (8 / 16 need every nm / l_seq / store_lo / store_len < 256 / < 65536: checked) */
     int32_t  qual_bits;             /* 2, 4 or 8 */
     int32_t  seq_bits;              /* 2 or 4 */
     int32_t  threads;               /* <= 0: all */
@@ -64,7 +64,7 @@ typedef struct smc_soa_pack_sizes {
     int64_t n_cigar_words;
 } smc_soa_pack_sizes;
 
-/* Output buffers, sized from smc_soa_pack_sizes: per-read arrays hold n_reads entries (nm .. store_len: uint16 or int32
+/* Output buffers, sized from smc_soa_pack_sizes: per-read arrays hold n_reads entries (nm .. store_len: uint8, uint16 or int32
  * by scalar_bits; store_lo / store_len may be NULL when the view has none), seq / qual / cigar the byte / word counts.
  * seq_poff (optional, n_reads + 1 entries) receives the byte offset of every read inside seq (host-side look-ups only). */
 typedef struct smc_soa_pack_bufs {

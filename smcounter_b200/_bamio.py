@@ -227,10 +227,12 @@ def upload_codebook(reads: ReadsSoA, threads: int = 0) -> dict:
         code_of = np.full(256, 0xFF, np.uint8)
         code_of[present] = np.arange(len(present), dtype=np.uint8)
     scal = [reads.nm, reads.l_seq] + ([] if reads.store_lo is None else [reads.store_lo, reads.store_len])
-    fits = all(len(a) == 0 or (int(a.min()) >= 0 and int(a.max()) < 65536) for a in scal)
+    top = max([0] + [int(a.max()) for a in scal if len(a)])
+    low = min([0] + [int(a.min()) for a in scal if len(a)])
+    sbits = 32 if (low < 0 or top >= 65536) else 16 if top >= 256 else 8
     ref8 = bool(reads.n) and int(reads.ref_id.min()) >= 0 and int(reads.ref_id.max()) < 256
     umi32 = bool(reads.n) and int(reads.umi.max()) < (1 << 32)
-    memo = dict(scalar_bits=16 if fits else 32, qual_bits=bits, qual_lut=lut, code_of=code_of, ref_id_bits=8 if ref8 else 32, umi_bits=32 if umi32 else 64)
+    memo = dict(scalar_bits=sbits, qual_bits=bits, qual_lut=lut, code_of=code_of, ref_id_bits=8 if ref8 else 32, umi_bits=32 if umi32 else 64)
     reads.__dict__["_upload_codebook"] = memo
     return memo
 
@@ -259,7 +261,7 @@ def pack_upload(reads: ReadsSoA, idx=None, alloc=None, seq_bits: int = 2, thread
         raise RuntimeError("smc_soa_pack_begin failed (%d)" % rc)
     try:
         n = int(sz.n_reads)
-        sdt = np.uint16 if cb["scalar_bits"] == 16 else np.int32
+        sdt = {8: np.uint8, 16: np.uint16, 32: np.int32}[cb["scalar_bits"]]
         out = dict(ref_id=take(n, np.uint8 if cb["ref_id_bits"] == 8 else np.int32), pos=take(n, np.int32), flag=take(n, np.uint16),
                    mapq=take(n, np.uint8), nm=take(n, sdt), l_seq=take(n, sdt), n_cigar=take(n, np.uint16),
                    umi=take(n, np.uint32 if cb["umi_bits"] == 32 else np.uint64), frag_id=take(n, np.uint32),

@@ -555,9 +555,10 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
         ENSURE(buf, b__ ? b__ : 16);                                                                             \
         if (b__) { ALLOC_SYNC(); CK(cudaMemcpyAsync((buf).p, (src), b__, cudaMemcpyHostToDevice, up_st)); bytes += b__; } \
     } while (0)
-    if (R->scalar_bits != 0 && R->scalar_bits != 32 && R->scalar_bits != 16) { ctx->err = "smc_upload: scalar_bits must be 0, 16 or 32"; return SMC_E_ARG; }
+    if (R->scalar_bits != 0 && R->scalar_bits != 32 && R->scalar_bits != 16 && R->scalar_bits != 8) { ctx->err = "smc_upload: scalar_bits must be 0, 8, 16 or 32"; return SMC_E_ARG; }
     if (R->qual_bits != 0 && R->qual_bits != 8 && R->qual_bits != 4 && R->qual_bits != 2) { ctx->err = "smc_upload: qual_bits must be 0, 2, 4 or 8"; return SMC_E_ARG; }
-    const bool s16 = R->scalar_bits == 16;
+    const bool s16 = R->scalar_bits == 16 || R->scalar_bits == 8;       // narrow scalars: staged, widened on the device
+    const size_t sw = R->scalar_bits == 8 ? 1 : 2;                      // bytes per narrow scalar
     const int qbits = (R->qual_bits == 4 || R->qual_bits == 2) ? R->qual_bits : 8;
     if (qbits != 8 && (R->qual_off || !R->qual_lut)) { ctx->err = "smc_upload: compact qualities need the packed layout (qual_off == NULL) and a qual_lut"; return SMC_E_ARG; }
     if (R->seq_bits != 0 && R->seq_bits != 4 && R->seq_bits != 2) { ctx->err = "smc_upload: seq_bits must be 0, 2 or 4"; return SMC_E_ARG; }
@@ -591,18 +592,21 @@ static int upload_impl(smc_ctx* ctx, const smc_reads_soa* R, const smc_loci* Lc,
         UP(ctx->d_nm, R->nm, n, int32_t); UP(ctx->d_lseq, R->l_seq, n, int32_t);
         if (ctx->has_store) { UP(ctx->d_store_lo, R->store_lo, n, int32_t); UP(ctx->d_store_len, R->store_len, n, int32_t); }
     } else {
-        // 16-bit scalars: four arrays staged back to back, widened on the device
+        // 8- / 16-bit scalars: four arrays staged back to back, widened on the device
         const void* src16[4] = {R->nm, R->l_seq, R->store_lo, R->store_len};
         DevBuf* dst32[4] = {&ctx->d_nm, &ctx->d_lseq, &ctx->d_store_lo, &ctx->d_store_len};
         ENSURE(ctx->d_stage16, (size_t)(n ? n : 1) * 2 * 4);
         for (int k = 0; k < (ctx->has_store ? 4 : 2); ++k) {
-            uint16_t* st16 = ctx->d_stage16.as<uint16_t>() + (size_t)k * n;
+            uint8_t* stg = ctx->d_stage16.as<uint8_t>() + (size_t)k * n * 2;
             CK(dst32[k]->ensure((size_t)(n ? n : 1) * 4));
-            if (n) { ALLOC_SYNC(); CK(cudaMemcpyAsync(st16, src16[k], (size_t)n * 2, cudaMemcpyHostToDevice, up_st)); bytes += n * 2; }
+            if (n) { ALLOC_SYNC(); CK(cudaMemcpyAsync(stg, src16[k], (size_t)n * sw, cudaMemcpyHostToDevice, up_st)); bytes += n * (int64_t)sw; }
         }
         SYNC_UP();
-        for (int k = 0; k < (ctx->has_store ? 4 : 2); ++k)
-            LAUNCH(k_widen_u16, nblk(n, 256), 256, 0, ctx->d_stage16.as<uint16_t>() + (size_t)k * n, n, dst32[k]->as<int32_t>());
+        for (int k = 0; k < (ctx->has_store ? 4 : 2); ++k) {
+            uint8_t* stg = ctx->d_stage16.as<uint8_t>() + (size_t)k * n * 2;
+            if (sw == 2) LAUNCH(k_widen_u16, nblk(n, 256), 256, 0, reinterpret_cast<uint16_t*>(stg), n, dst32[k]->as<int32_t>());
+            else LAUNCH(k_widen_u8, nblk(n, 256), 256, 0, stg, n, dst32[k]->as<int32_t>());
+        }
     }
     SYNC_UP();                              // the offsets below are computed from the scalars
     ctx->qual_bits = qbits; ctx->seq_bits = sbits; ctx->n_seq_exc = sbits == 2 ? R->n_seq_exc : 0;

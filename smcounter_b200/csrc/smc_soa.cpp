@@ -106,7 +106,7 @@ extern "C" int smc_soa_ref_end(const smc_soa_view* v, int threads, int64_t* ref_
 extern "C" int smc_soa_pack_begin(const smc_soa_view* v, const int64_t* idx, int64_t n_idx, const smc_soa_pack_opts* opts,
                                   smc_soa_pack** out, smc_soa_pack_sizes* sizes) {
     if (!v || !opts || !out || !sizes || v->n_reads < 0 || (idx && n_idx < 0)) return SMC_SOA_E_ARG;
-    if ((opts->scalar_bits != 16 && opts->scalar_bits != 32) || (opts->qual_bits != 2 && opts->qual_bits != 4 && opts->qual_bits != 8) ||
+    if ((opts->scalar_bits != 8 && opts->scalar_bits != 16 && opts->scalar_bits != 32) || (opts->qual_bits != 2 && opts->qual_bits != 4 && opts->qual_bits != 8) ||
         (opts->seq_bits != 2 && opts->seq_bits != 4) || (opts->ref_id_bits != 8 && opts->ref_id_bits != 32) ||
         (opts->umi_bits != 32 && opts->umi_bits != 64) || ((v->store_lo == nullptr) != (v->store_len == nullptr)))
         return SMC_SOA_E_ARG;
@@ -135,9 +135,10 @@ extern "C" int smc_soa_pack_begin(const smc_soa_view* v, const int64_t* idx, int
             h->seq_off[k + 1] = sb == 2 ? (l + 3) / 4 : (l + 1) / 2;
             h->qual_off[k + 1] = qb == 8 ? l : (l * qb + 7) / 8;
             h->cig_off[k + 1] = v->n_cigar[r];
-            if (opts->scalar_bits == 16) {
-                const bool ok = (uint32_t)v->nm[r] < 65536u && (uint32_t)v->l_seq[r] < 65536u &&
-                                (!v->store_lo || ((uint32_t)v->store_lo[r] < 65536u && (uint32_t)v->store_len[r] < 65536u));
+            if (opts->scalar_bits != 32) {
+                const uint32_t lim = opts->scalar_bits == 16 ? 65536u : 256u;
+                const bool ok = (uint32_t)v->nm[r] < lim && (uint32_t)v->l_seq[r] < lim &&
+                                (!v->store_lo || ((uint32_t)v->store_lo[r] < lim && (uint32_t)v->store_len[r] < lim));
                 if (!ok) { bad[(size_t)t] = 1; return; }
             }
             if ((opts->ref_id_bits == 8 && (uint32_t)v->ref_id[r] >= 256u) || (opts->umi_bits == 32 && (v->umi[r] >> 32) != 0)) { bad[(size_t)t] = 1; return; }
@@ -197,7 +198,7 @@ extern "C" int smc_soa_pack_fill(smc_soa_pack* h, const smc_soa_pack_bufs* B, sm
                   (h->cig_off[(size_t)n] && !B->cigar)))
         return SMC_SOA_E_ARG;
     const int T = h->threads, qb = h->o.qual_bits, sb = h->o.seq_bits;
-    const bool s16 = h->o.scalar_bits == 16, ref8 = h->o.ref_id_bits == 8, umi32 = h->o.umi_bits == 32;
+    const bool s16 = h->o.scalar_bits == 16, s8 = h->o.scalar_bits == 8, ref8 = h->o.ref_id_bits == 8, umi32 = h->o.umi_bits == 32;
     // BAM nibble -> 2-bit code (A 1, C 2, G 4, T 8); everything else travels as code 0 plus an exception
     uint8_t code2[16], plain[16];
     for (int i = 0; i < 16; ++i) { code2[i] = 0; plain[i] = 0; }
@@ -214,7 +215,10 @@ extern "C" int smc_soa_pack_fill(smc_soa_pack* h, const smc_soa_pack_bufs* B, sm
             B->pos[k] = v.pos[r]; B->flag[k] = v.flag[r]; B->mapq[k] = v.mapq[r];
             B->n_cigar[k] = v.n_cigar[r];
             B->frag_id[k] = h->frag_rank[v.frag_id[r] - h->frag_lo];
-            if (s16) {
+            if (s8) {
+                ((uint8_t*)B->nm)[k] = (uint8_t)v.nm[r]; ((uint8_t*)B->l_seq)[k] = (uint8_t)v.l_seq[r];
+                if (has_store) { ((uint8_t*)B->store_lo)[k] = (uint8_t)v.store_lo[r]; ((uint8_t*)B->store_len)[k] = (uint8_t)v.store_len[r]; }
+            } else if (s16) {
                 ((uint16_t*)B->nm)[k] = (uint16_t)v.nm[r]; ((uint16_t*)B->l_seq)[k] = (uint16_t)v.l_seq[r];
                 if (has_store) { ((uint16_t*)B->store_lo)[k] = (uint16_t)v.store_lo[r]; ((uint16_t*)B->store_len)[k] = (uint16_t)v.store_len[r]; }
             } else {

@@ -45,7 +45,7 @@ class ReadsSoA:
     store_lo: np.ndarray | None = None    # int32, optional stored window (include/smc_b200.h): first stored query base (even) ...
     store_len: np.ndarray | None = None   # int32  ... and number of stored bases; None = reads stored whole
     # compact wire encodings (include/smc_b200.h, ABI v3); a compacted SoA is an upload format, not a working one
-    scalar_bits: int = 32                 # 16: nm / l_seq / store_lo / store_len are uint16 arrays
+    scalar_bits: int = 32                 # 16 / 8: nm / l_seq / store_lo / store_len are uint16 / uint8 arrays
     qual_bits: int = 8                    # 4 / 2: ``qual`` holds qual_bits-wide codes (low bits first, reads byte aligned) ...
     qual_lut: np.ndarray | None = None    # ... and this is the phred value of each code
     seq_bits: int = 4                     # 2: ``seq`` holds A C G T = 0..3 (low bits first, reads byte aligned) ...
@@ -181,8 +181,8 @@ class ReadsSoA:
                         frag_id=self.frag_id, seq=out["seq"][0], qual=out["qual"][0], cigar=out["cigar"][0], chroms=self.chroms,
                         umi_names=self.umi_names, packed=True, store_lo=store_lo, store_len=store_len)
 
-    def compact(self, block: int = 1 << 18, seq_bits_wanted: int = 2) -> "ReadsSoA":
-        """The same reads in the compact upload encodings of include/smc_b200.h (ABI v3): 16-bit nm / l_seq / store_lo /
+    def compact(self, block: int = 1 << 18, seq_bits_wanted: int = 2, scalar_bits_min: int = 8) -> "ReadsSoA":
+        """The same reads in the compact upload encodings of include/smc_b200.h (ABI v3): 8- or 16-bit nm / l_seq / store_lo /
         store_len when every value fits, and 2- or 4-bit quality codes when the batch shows at most 4 / 16 distinct
         qualities (sequencers that bin qualities; a batch with more keeps one byte per base), 2-bit bases with a side list for
         the non-ACGT ones (`seq_bits_wanted=4` keeps BAM's nibbles).  Needs a packed layout (repack() / trim_to_targets() /
@@ -193,10 +193,11 @@ class ReadsSoA:
         kw = {f: getattr(src, f) for f in ("ref_id", "pos", "flag", "mapq", "seq_off", "qual_off", "cigar_off", "n_cigar", "umi", "frag_id",
                                             "seq", "cigar", "chroms", "umi_names")}
         scal = {"nm": src.nm, "l_seq": src.l_seq, "store_lo": src.store_lo, "store_len": src.store_len}
-        fits = all(a is None or (len(a) == 0 or (int(a.min()) >= 0 and int(a.max()) < 65536)) for a in scal.values())
-        scalar_bits = 16 if fits else 32
-        if fits:
-            scal = {k: (None if a is None else a.astype(np.uint16)) for k, a in scal.items()}
+        top = max([0] + [int(a.max()) for a in scal.values() if a is not None and len(a)])
+        low = min([0] + [int(a.min()) for a in scal.values() if a is not None and len(a)])
+        scalar_bits = max(32 if (low < 0 or top >= 65536) else 16 if top >= 256 else 8, scalar_bits_min)
+        if scalar_bits != 32:
+            scal = {k: (None if a is None else a.astype(np.uint16 if scalar_bits == 16 else np.uint8)) for k, a in scal.items()}
         present = np.flatnonzero(np.bincount(src.qual, minlength=256)) if len(src.qual) else np.zeros(0, np.int64)
         bits = 2 if len(present) <= 4 else 4 if len(present) <= 16 else 8
         lens = src.stored_len()

@@ -394,7 +394,7 @@ def test_compact_upload_encodings_give_identical_bits(nq, seq_bits):
     seen = {}
 
     def enc(soa):
-        out = soa.trim_to_targets(PIPE_IVS).compact(seq_bits_wanted=seq_bits)
+        out = soa.trim_to_targets(PIPE_IVS).compact(seq_bits_wanted=seq_bits, scalar_bits_min=16 if nq == 7 else 8)
         seen.update(qual_bits=out.qual_bits, seq_bits=out.seq_bits, n_exc=0 if out.seq_exc is None else len(out.seq_exc[0]), scalar_bits=out.scalar_bits,
                     umi=str(out.umi.dtype), ref_id=str(out.ref_id.dtype))
         return out
@@ -409,7 +409,7 @@ def test_compact_upload_encodings_give_identical_bits(nq, seq_bits):
         print(stats, seen)
         assert not problems, "\n".join(problems)
         assert seen["umi"] == ("uint32" if short else "uint64") and seen["ref_id"] == "uint8"
-    assert seen["qual_bits"] == (2 if nq + 1 <= 4 else 4 if nq + 1 <= 16 else 8) and seen["scalar_bits"] == 16   # + quality 2 of the 'N's
+    assert seen["qual_bits"] == (2 if nq + 1 <= 4 else 4 if nq + 1 <= 16 else 8) and seen["scalar_bits"] == (16 if nq == 7 else 8)   # + quality 2 of the 'N's
     assert seen["seq_bits"] == seq_bits and (seq_bits == 4 or seen["n_exc"] > 0)
 
 

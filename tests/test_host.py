@@ -526,10 +526,12 @@ def test_native_batch_packer_equals_select_plus_compact():
     rng = np.random.default_rng(3)
     for plain in (soa.repack(), soa.trim_to_targets(ivs)):
         for idx in (None, np.flatnonzero(rng.random(plain.n) < 0.6), np.zeros(0, np.int64)):
-            want = (plain if idx is None else plain.select(idx)).compact()
-            for threads in (1, 5):
+            for threads, sbits in ((1, 8), (5, 8), (3, 16)):
+                want = (plain if idx is None else plain.select(idx)).compact(scalar_bits_min=sbits)
+                plain.__dict__.pop("_upload_codebook", None)
+                _bamio.upload_codebook(plain)["scalar_bits"] = sbits          # reads of 150 bases fit 8 bits; the 16-bit path is forced
                 got = _bamio.pack_upload(plain, idx, threads=threads)
-                assert (got.scalar_bits, got.qual_bits, got.seq_bits) == (want.scalar_bits, want.qual_bits, want.seq_bits) == (16, 2, 2)
+                assert (got.scalar_bits, got.qual_bits, got.seq_bits) == (want.scalar_bits, want.qual_bits, want.seq_bits) == (sbits, 2, 2)
                 for f in ("ref_id", "pos", "flag", "mapq", "nm", "l_seq", "n_cigar", "umi", "frag_id", "seq", "qual", "cigar", "qual_lut"):
                     a, b = getattr(got, f), getattr(want, f)
                     if got.n == 0 and f in ("qual_lut", "ref_id", "umi"):
