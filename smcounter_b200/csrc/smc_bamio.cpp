@@ -473,16 +473,46 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
             return memcmp(qa + A.bc_off, qb + B.bc_off, A.bc_len) == 0 && memcmp(qa, qb, A.rid_len) == 0;
         };
         const int P = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n / 65536 + 1));
+        auto part_of = [&](size_t i) { return (int)((info[i].h2 >> 40) % (uint64_t)P); };
+        // the kept records of every partition, in record order: counted and filled by ranges of records in parallel, so that a
+        // partition's thread walks its own records only (not the whole file once per thread)
+        std::vector<uint32_t> plist(n);
+        std::vector<size_t> pstart((size_t)P + 1, 0);
+        {
+            const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, nrec / 65536 + 1));
+            std::vector<size_t> cnt((size_t)T * (size_t)P, 0);
+            auto run = [&](auto&& f) {
+                std::vector<std::thread> ts;
+                for (int t = 1; t < T; ++t) ts.emplace_back(f, t);
+                f(0);
+                for (auto& th : ts) th.join();
+            };
+            run([&](int t) {
+                std::vector<size_t> c((size_t)P, 0);
+                for (size_t i = nrec * (size_t)t / T, e = nrec * (size_t)(t + 1) / T; i < e; ++i) if (info[i].keep) ++c[(size_t)part_of(i)];
+                for (int q = 0; q < P; ++q) cnt[(size_t)t * P + q] = c[(size_t)q];
+            });
+            size_t run_tot = 0;
+            for (int q = 0; q < P; ++q) {
+                pstart[(size_t)q] = run_tot;
+                for (int t = 0; t < T; ++t) { const size_t c = cnt[(size_t)t * P + q]; cnt[(size_t)t * P + q] = run_tot; run_tot += c; }
+            }
+            pstart[(size_t)P] = run_tot;
+            run([&](int t) {
+                std::vector<size_t> cur((size_t)P);
+                for (int q = 0; q < P; ++q) cur[(size_t)q] = cnt[(size_t)t * P + q];
+                for (size_t i = nrec * (size_t)t / T, e = nrec * (size_t)(t + 1) / T; i < e; ++i) if (info[i].keep) plist[cur[(size_t)part_of(i)]++] = (uint32_t)i;
+            });
+        }
         auto part = [&](int t) {
             struct Ent { uint64_t h1, h2; uint32_t rec; };
-            size_t mine = 0;
-            for (size_t i = 0; i < nrec; ++i) if (info[i].keep && (int)((info[i].h2 >> 40) % (uint64_t)P) == t) ++mine;
+            const size_t mine = pstart[(size_t)t + 1] - pstart[(size_t)t];
             size_t cap = 16;
             while (cap < 2 * mine + 2) cap <<= 1;
             std::vector<Ent> tab(cap, Ent{0, 0, UINT32_MAX});
-            for (size_t i = 0; i < nrec; ++i) {
+            for (size_t q = pstart[(size_t)t]; q < pstart[(size_t)t + 1]; ++q) {
+                const size_t i = plist[q];
                 const RecInfo& R = info[i];
-                if (!R.keep || (int)((R.h2 >> 40) % (uint64_t)P) != t) continue;
                 size_t k = (size_t)R.h1 & (cap - 1);
                 for (;;) {
                     Ent& E = tab[k];
