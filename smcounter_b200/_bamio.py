@@ -11,7 +11,7 @@ from .soa import ReadsSoA
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmc_bamio.so")
 EXPORTS = ("smc_bam_set_trim", "smc_bam_open", "smc_bam_close", "smc_bam_last_error", "smc_bam_n_refs", "smc_bam_ref_name", "smc_bam_ref_length",
-           "smc_bam_decode", "smc_bam_dict_umi", "smc_rows_emit", "smc_rows_free", "smc_soa_qual_hist", "smc_soa_ref_end", "smc_soa_pack_begin", "smc_soa_pack_fill",
+           "smc_bam_decode", "smc_bam_dict_umi", "smc_bam_inflate_raw", "smc_rows_emit", "smc_rows_free", "smc_soa_qual_hist", "smc_soa_ref_end", "smc_soa_pack_begin", "smc_soa_pack_fill",
            "smc_soa_pack_end")
 _vp = C.c_void_p
 
@@ -89,6 +89,8 @@ def load():
     lib.smc_bam_decode.restype = C.c_int
     lib.smc_bam_dict_umi.argtypes = [_vp, C.c_int64]
     lib.smc_bam_dict_umi.restype = C.c_char_p
+    lib.smc_bam_inflate_raw.argtypes = [_vp, C.c_int64, _vp, C.c_int64]
+    lib.smc_bam_inflate_raw.restype = C.c_int
     lib.smc_rows_emit.argtypes = [C.POINTER(smc_rows_in), C.POINTER(smc_rows_out)]
     lib.smc_rows_emit.restype = C.c_int
     lib.smc_rows_free.argtypes = [C.POINTER(smc_rows_out)]

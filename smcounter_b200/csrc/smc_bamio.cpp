@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/smc_bamio.h"
+#include "smc_inflate.h"
 
 namespace {
 thread_local std::string g_open_error;
@@ -116,6 +117,8 @@ static int inflate_all(const RawBuf& file, int threads, RawBuf& out, std::string
     if (!out.alloc(uoff)) { err = "out of memory for the inflated BAM"; return -1; }
     std::atomic<size_t> next(0);
     std::atomic<int> bad(0);
+    // the blocks go through the decoder of smc_inflate.h; a block it rejects is given to zlib (SMC_INFLATE=zlib: zlib for all)
+    static const bool own_inflate = [] { const char* ev = getenv("SMC_INFLATE"); return !(ev && strcmp(ev, "zlib") == 0); }();
     auto work = [&]() {
         z_stream zs;
         for (;;) {
@@ -123,6 +126,7 @@ static int inflate_all(const RawBuf& file, int threads, RawBuf& out, std::string
             if (i >= blocks.size() || bad.load()) break;
             const Block& b = blocks[i];
             if (b.isize == 0) continue;
+            if (own_inflate && smc_inflate_raw(&file[b.coff], b.clen, &out[b.uoff], b.isize) == 0) continue;
             memset(&zs, 0, sizeof(zs));
             if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; break; }
             zs.next_in = const_cast<Bytef*>(&file[b.coff]); zs.avail_in = (uInt)b.clen;
@@ -150,7 +154,10 @@ extern "C" int smc_bam_open(const char* path, int threads, smc_bam** out) {
     fseek(fh, 0, SEEK_END);
     const long sz = ftell(fh);
     fseek(fh, 0, SEEK_SET);
-    if (!file.alloc(sz > 0 ? (size_t)sz : 0)) { fclose(fh); g_open_error = "smc_bam_open: out of memory"; return -1; }
+    // 64 bytes of slack: the block decoder reads its input eight bytes at a time
+    if (!file.alloc((sz > 0 ? (size_t)sz : 0) + 64)) { fclose(fh); g_open_error = "smc_bam_open: out of memory"; return -1; }
+    memset(file.p + (sz > 0 ? (size_t)sz : 0), 0, 64);
+    file.n = sz > 0 ? (size_t)sz : 0;
     const size_t got = file.size() ? fread(file.p, 1, file.size(), fh) : 0;
     fclose(fh);
     if (got != file.size()) { g_open_error = "smc_bam_open: short read"; return -1; }
@@ -180,6 +187,10 @@ extern "C" int smc_bam_open(const char* path, int threads, smc_bam** out) {
 }
 
 extern "C" void smc_bam_close(smc_bam* h) { delete h; }
+extern "C" int smc_bam_inflate_raw(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_len) {
+    if (!in || !out || in_len < 0 || out_len < 0) return -2;
+    return smc_inflate_raw(in, (size_t)in_len, out, (size_t)out_len);
+}
 extern "C" void smc_bam_set_trim(smc_bam* h, int trim) { if (h) h->trim = trim ? 1 : 0; }
 extern "C" const char* smc_bam_last_error(smc_bam* h) { return h ? h->err.c_str() : g_open_error.c_str(); }
 extern "C" int smc_bam_n_refs(smc_bam* h) { return h ? (int)h->ref_names.size() : 0; }

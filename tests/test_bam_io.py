@@ -208,3 +208,85 @@ def test_bgzf_streams_as_other_writers_make_them(tmp_path, native):
     want_t = bam.read_bam(path, intervals=ivs, native=native)
     for f in FIELDS:
         assert np.array_equal(getattr(got_t, f), getattr(want_t, f)), f
+
+
+def _native_inflate(comp: bytes, out_len: int):
+    import ctypes as C
+    from smcounter_b200 import _bamio
+    lib = _bamio.load()
+    src = np.frombuffer(comp + b"\x00" * 32, dtype=np.uint8).copy()        # the routine may read 16 bytes past the stream
+    dst = np.full(out_len + 64, 0xAB, dtype=np.uint8)                        # canary behind the output
+    rc = lib.smc_bam_inflate_raw(src.ctypes.data, len(comp), dst.ctypes.data, out_len)
+    assert (dst[out_len:] == 0xAB).all(), "wrote past the output"
+    return rc, dst[:out_len].tobytes()
+
+
+@pytest.mark.skipif(len(_decoders()) < 2, reason="libsmc_bamio.so not built")
+def test_own_inflate_equals_zlib_on_every_kind_of_stream():
+    """csrc/smc_inflate.h (what the BAM decoder inflates BGZF blocks with) against zlib: random bytes of several entropies,
+    text, BAM-like records, long runs, empty input; compression levels 0-9, default / fixed-Huffman / Huffman-only / RLE /
+    filtered strategies, streams of several deflate blocks (Z_FULL_FLUSH); sizes around every boundary of the copy loops."""
+    import zlib
+    rng = np.random.default_rng(12)
+    def corpus():
+        yield b""
+        yield b"a"
+        yield b"ab" * 7
+        for n in (1, 2, 7, 8, 9, 15, 16, 17, 255, 256, 257, 258, 259, 4095, 65280):
+            yield bytes(rng.integers(0, 256, size=n, dtype=np.uint8))                       # incompressible
+            yield bytes(rng.integers(0, 4, size=n, dtype=np.uint8))                         # 2 bits of entropy
+            yield (b"ACGT" * (n // 4 + 1))[:n]                                               # period 4
+            yield b"\x00" * n                                                                # one long run (distance 1)
+            yield bytes(np.repeat(rng.integers(0, 256, size=n // 9 + 1, dtype=np.uint8), 9)[:n])
+        yield (b"the quick brown fox jumps over the lazy dog. " * 900)[:40000]
+        s, refs, _ = _panel(seed=3)
+        p = "/tmp/_smc_inflate_case.bam"
+        bam.write_bam(p, s, refs.lengths)
+        yield bam.bgzf_decompress(open(p, "rb").read())[:65280]
+        os.remove(p)
+        yield bytes(rng.integers(0, 256, size=20000, dtype=np.uint8)) + b"\x07" * 20000 + bytes(rng.integers(0, 16, size=20000, dtype=np.uint8))
+    n_streams = 0
+    for data in corpus():
+        for level in (0, 1, 4, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
+                co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+                comp = co.compress(data) + co.flush()
+                rc, got = _native_inflate(comp, len(data))
+                assert rc == 0 and got == data, (len(data), level, strategy)
+                n_streams += 1
+        # several deflate blocks in one stream, of different kinds
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        half = len(data) // 2
+        comp = co.compress(data[:half]) + co.flush(zlib.Z_FULL_FLUSH) + co.compress(data[half:]) + co.flush()
+        rc, got = _native_inflate(comp, len(data))
+        assert rc == 0 and got == data
+    assert n_streams > 1500
+
+
+@pytest.mark.skipif(len(_decoders()) < 2, reason="libsmc_bamio.so not built")
+def test_own_inflate_rejects_what_it_cannot_prove_right():
+    """Wrong output size, truncated input, flipped bits: the routine must never write outside the output it was given (canary
+    checked in _native_inflate) and must return an error or -- for a flipped bit that still decodes -- output of the stated size;
+    it never crashes.  (The BAM decoder hands rejected blocks to zlib.)"""
+    import zlib
+    rng = np.random.default_rng(5)
+    data = bytes(rng.integers(0, 8, size=30000, dtype=np.uint8)) + b"GATTACA" * 500
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = co.compress(data) + co.flush()
+    assert _native_inflate(comp, len(data))[0] == 0
+    assert _native_inflate(comp, len(data) - 1)[0] == -1
+    assert _native_inflate(comp, len(data) + 1)[0] == -1
+    for cut in (1, 2, 10, len(comp) // 2, len(comp) - 1):
+        assert _native_inflate(comp[:cut], len(data))[0] == -1
+    bad = 0
+    for k in range(400):
+        b = bytearray(comp)
+        pos = int(rng.integers(0, len(b)))
+        b[pos] ^= 1 << int(rng.integers(0, 8))
+        rc, got = _native_inflate(bytes(b), len(data))
+        assert rc in (0, -1)
+        bad += rc == -1 or got != data
+    assert bad > 300                     # nearly every flip is caught by the stream's own consistency (size, codes, distances)
+    for k in range(200):                 # garbage
+        junk = bytes(rng.integers(0, 256, size=int(rng.integers(1, 400)), dtype=np.uint8))
+        assert _native_inflate(junk, 1000)[0] in (0, -1)
