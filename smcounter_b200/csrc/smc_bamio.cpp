@@ -1,5 +1,6 @@
 // libsmc_bamio.so -- BAM (BGZF) -> flat SoA read buffers (include/smc_bamio.h).  Host-side input decoding only.
 // Container format restated from the SAM/BAM specification (SAMv1 sections 4.1-4.2); zlib does the inflating.
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -158,12 +159,30 @@ extern "C" int smc_bam_open(const char* path, int threads, smc_bam** out) {
     if (!file.alloc((sz > 0 ? (size_t)sz : 0) + 64)) { fclose(fh); g_open_error = "smc_bam_open: out of memory"; return -1; }
     memset(file.p + (sz > 0 ? (size_t)sz : 0), 0, 64);
     file.n = sz > 0 ? (size_t)sz : 0;
-    const size_t got = file.size() ? fread(file.p, 1, file.size(), fh) : 0;
-    fclose(fh);
-    if (got != file.size()) { g_open_error = "smc_bam_open: short read"; return -1; }
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    {   // the file (usually in the page cache) is read by all threads, each its own range (pread)
+        const int fd = fileno(fh);
+        const size_t total = file.size();
+        const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, total / (size_t(4) << 20) + 1));
+        std::atomic<int> short_read(0);
+        auto rd = [&](int t) {
+            size_t a = total * (size_t)t / (size_t)nt;
+            const size_t e = total * (size_t)(t + 1) / (size_t)nt;
+            while (a < e) {
+                const ssize_t k = pread(fd, file.p + a, e - a, (off_t)a);
+                if (k <= 0) { short_read = 1; return; }
+                a += (size_t)k;
+            }
+        };
+        std::vector<std::thread> ts;
+        for (int t = 1; t < nt; ++t) ts.emplace_back(rd, t);
+        rd(0);
+        for (auto& t : ts) t.join();
+        fclose(fh);
+        if (short_read.load()) { g_open_error = "smc_bam_open: short read"; return -1; }
+    }
     pt.lap("read file");
     smc_bam* h = new smc_bam();
-    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     h->threads = threads;
     if (inflate_all(file, threads, h->raw, g_open_error) != 0) { delete h; return -1; }
     pt.lap("inflate");
