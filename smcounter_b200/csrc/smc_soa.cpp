@@ -25,6 +25,13 @@ template <class F> void par_for(size_t n, int threads, F f) {      // f(begin, e
     for (auto& th : ts) th.join();
 }
 
+template <class F> void par_each(int tasks, F f) {                  // f(task) for every task, one thread each
+    std::vector<std::thread> ts;
+    for (int t = 1; t < tasks; ++t) ts.emplace_back([=] { f(t); });
+    if (tasks > 0) f(0);
+    for (auto& th : ts) th.join();
+}
+
 int n_threads(int want) { return want > 0 ? want : (int)std::max(1u, std::thread::hardware_concurrency()); }
 
 struct Exc { uint32_t read, pos; uint8_t nib; };
@@ -148,9 +155,29 @@ extern "C" int smc_soa_pack_begin(const smc_soa_view* v, const int64_t* idx, int
     });
     for (int t = 0; t < T; ++t) if (bad[(size_t)t]) { delete h; return SMC_SOA_E_RANGE; }
     pt.lap("begin: sizes pass");
-    // prefix sums (three short serial passes over n + 1 words: a few ms for millions of reads)
-    for (int64_t k = 0; k < n; ++k) {
-        h->seq_off[(size_t)k + 1] += h->seq_off[(size_t)k]; h->qual_off[(size_t)k + 1] += h->qual_off[(size_t)k]; h->cig_off[(size_t)k + 1] += h->cig_off[(size_t)k];
+    // prefix sums: every range scans its own slice, the range totals are scanned serially, every range adds its base
+    {
+        struct Tot { int64_t s, q, c; };
+        std::vector<Tot> tot((size_t)T + 1, Tot{0, 0, 0});
+        const size_t per = ((size_t)n + (size_t)T - 1) / (size_t)T;
+        const int tasks = (size_t)n < 65536 ? 1 : T;
+        par_each(tasks, [&](int ti) {
+            const size_t t = (size_t)ti, a = tasks == 1 ? 0 : std::min((size_t)n, per * t), e = tasks == 1 ? (size_t)n : std::min((size_t)n, a + per);
+            Tot run{0, 0, 0};
+            for (size_t k = a; k < e; ++k) {
+                run.s += h->seq_off[k + 1]; run.q += h->qual_off[k + 1]; run.c += h->cig_off[k + 1];
+                h->seq_off[k + 1] = run.s; h->qual_off[k + 1] = run.q; h->cig_off[k + 1] = run.c;
+            }
+            tot[t + 1] = run;
+        });
+        for (int t = 0; t < tasks; ++t) { tot[(size_t)t + 1].s += tot[(size_t)t].s; tot[(size_t)t + 1].q += tot[(size_t)t].q; tot[(size_t)t + 1].c += tot[(size_t)t].c; }
+        if (tasks > 1)
+            par_each(tasks, [&](int ti) {
+                if (ti == 0) return;
+                const size_t t = (size_t)ti, a = std::min((size_t)n, per * t), e = std::min((size_t)n, a + per);
+                const Tot b = tot[t];
+                for (size_t k = a; k < e; ++k) { h->seq_off[k + 1] += b.s; h->qual_off[k + 1] += b.q; h->cig_off[k + 1] += b.c; }
+            });
     }
     pt.lap("begin: prefix sums");
     // dense fragment ids in the old relative order: mark the ids of the batch, count them in order
