@@ -67,7 +67,7 @@ int         smc_bam_decode(smc_bam *h, int64_t n_intervals, const int32_t *iv_re
 const char *smc_bam_dict_umi(smc_bam *h, int64_t i);                      /* barcode string of dictionary id i */
 
 /* The decoder's own raw-DEFLATE routine (csrc/smc_inflate.h), exposed for tests: inflates one stream of exactly out_len bytes;
- * `in` must be readable up to in + in_len + 16.  0, or -1 when the stream is malformed / of another size (the BAM decoder then
+ * `in` must be readable up to in + in_len + 64.  0, or -1 when the stream is malformed / of another size (the BAM decoder then
  * hands the block to zlib). */
 int         smc_bam_inflate_raw(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len);
 

@@ -95,8 +95,8 @@ inline int build_table(const uint8_t* lens, int n, int root, int kind, uint32_t*
 
 }  // namespace smc_inflate_detail
 
-// Inflates one raw DEFLATE stream of exactly out_len bytes.  `in` must be readable up to in + in_len + 8 (the caller's buffer has
-// that much slack).  Returns 0, or -1 if the stream is malformed, does not end where it should, or does not produce out_len bytes.
+// Inflates one raw DEFLATE stream of exactly out_len bytes.  `in` must be readable up to in + in_len + 64 (the bit buffer is
+// refilled eight bytes at a time and may run a few refills past a truncated stream before the end checks stop it).  Returns 0, or -1 if the stream is malformed, does not end where it should, or does not produce out_len bytes.
 inline int smc_inflate_raw(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len) {
     using namespace smc_inflate_detail;
     const uint8_t* const in_end = in + in_len;

@@ -214,7 +214,7 @@ def _native_inflate(comp: bytes, out_len: int):
     import ctypes as C
     from smcounter_b200 import _bamio
     lib = _bamio.load()
-    src = np.frombuffer(comp + b"\x00" * 32, dtype=np.uint8).copy()        # the routine may read 16 bytes past the stream
+    src = np.frombuffer(comp + b"\x00" * 64, dtype=np.uint8).copy()        # the routine may read up to 64 bytes past the stream
     dst = np.full(out_len + 64, 0xAB, dtype=np.uint8)                        # canary behind the output
     rc = lib.smc_bam_inflate_raw(src.ctypes.data, len(comp), dst.ctypes.data, out_len)
     assert (dst[out_len:] == 0xAB).all(), "wrote past the output"
