@@ -48,6 +48,7 @@ typedef struct smc_bam_reads {
     int64_t         n_dict_umis; /* barcodes that needed the dictionary (see smc_bam_dict_umi) */
     const int32_t  *store_lo;   /* trim mode (smc_bam_set_trim): the stored window of smc_reads_soa, else NULL */
     const int32_t  *store_len;
+    const uint64_t *qual_hist;  /* 256 counts: how often every phred value occurs in qual[] (decides the upload codebook) */
 } smc_bam_reads;
 
 int         smc_bam_open(const char *path, int threads, smc_bam **out);   /* read + inflate + parse the header */

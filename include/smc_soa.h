@@ -104,6 +104,9 @@ int  smc_soa_qual_hist(const smc_soa_view *v, int threads, uint64_t hist[256]);
 /* 0-based exclusive reference end of every read (pos + the reference bases its CIGAR consumes: M D N = X); what the host
  * needs to find the reads of an interval. */
 int  smc_soa_ref_end(const smc_soa_view *v, int threads, int64_t *ref_end);
+/* The same pass, plus what an interval look-up over the reads needs to know: stats[0] = 1 when the reads are in BAM coordinate
+ * order ((ref_id, pos) never decreases), stats[1] = the longest reference span of a read. */
+int  smc_soa_order_stats(const smc_soa_view *v, int threads, int64_t *ref_end, int64_t stats[2]);
 /* idx: ascending read indices of the batch, or NULL = all reads of the view. */
 int  smc_soa_pack_begin(const smc_soa_view *v, const int64_t *idx, int64_t n_idx, const smc_soa_pack_opts *opts,
                         smc_soa_pack **out, smc_soa_pack_sizes *sizes);

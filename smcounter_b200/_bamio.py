@@ -11,7 +11,7 @@ from .soa import ReadsSoA
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmc_bamio.so")
 EXPORTS = ("smc_bam_set_trim", "smc_bam_open", "smc_bam_close", "smc_bam_last_error", "smc_bam_n_refs", "smc_bam_ref_name", "smc_bam_ref_length",
-           "smc_bam_decode", "smc_bam_dict_umi", "smc_bam_inflate_raw", "smc_rows_emit", "smc_rows_free", "smc_soa_qual_hist", "smc_soa_ref_end", "smc_soa_pack_begin", "smc_soa_pack_fill",
+           "smc_bam_decode", "smc_bam_dict_umi", "smc_bam_inflate_raw", "smc_rows_emit", "smc_rows_free", "smc_soa_qual_hist", "smc_soa_ref_end", "smc_soa_order_stats", "smc_soa_pack_begin", "smc_soa_pack_fill",
            "smc_soa_pack_end")
 _vp = C.c_void_p
 
@@ -20,7 +20,7 @@ class smc_bam_reads(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("ref_id", _vp), ("pos", _vp), ("flag", _vp), ("mapq", _vp), ("nm", _vp), ("l_seq", _vp),
                 ("seq_off", _vp), ("qual_off", _vp), ("cigar_off", _vp), ("n_cigar", _vp), ("umi", _vp), ("frag_id", _vp),
                 ("seq", _vp), ("seq_bytes", C.c_int64), ("qual", _vp), ("qual_bytes", C.c_int64), ("cigar", _vp),
-                ("n_cigar_words", C.c_int64), ("n_dict_umis", C.c_int64), ("store_lo", _vp), ("store_len", _vp)]
+                ("n_cigar_words", C.c_int64), ("n_dict_umis", C.c_int64), ("store_lo", _vp), ("store_len", _vp), ("qual_hist", _vp)]
 
 
 class smc_rows_in(C.Structure):               # include/smc_rows.h
@@ -99,6 +99,8 @@ def load():
     lib.smc_soa_qual_hist.restype = C.c_int
     lib.smc_soa_ref_end.argtypes = [C.POINTER(smc_soa_view), C.c_int, _vp]
     lib.smc_soa_ref_end.restype = C.c_int
+    lib.smc_soa_order_stats.argtypes = [C.POINTER(smc_soa_view), C.c_int, _vp, _vp]
+    lib.smc_soa_order_stats.restype = C.c_int
     lib.smc_soa_pack_begin.argtypes = [C.POINTER(smc_soa_view), _vp, C.c_int64, C.POINTER(smc_soa_pack_opts), C.POINTER(_vp), C.POINTER(smc_soa_pack_sizes)]
     lib.smc_soa_pack_begin.restype = C.c_int
     lib.smc_soa_pack_fill.argtypes = [_vp, C.POINTER(smc_soa_pack_bufs), C.POINTER(smc_soa_pack_exc)]
@@ -177,6 +179,8 @@ def read_bam_native(path: str, intervals=None, threads: int = 0, trim: bool = Fa
             cigar=A(out.cigar, out.n_cigar_words, np.uint32), chroms=chroms, umi_names=names, packed=True,
             store_lo=A(out.store_lo, n, np.int32) if out.store_lo else None,
             store_len=A(out.store_len, n, np.int32) if out.store_len else None)
+        if out.qual_hist:                   # counted during the decode: the upload codebook needs no pass of its own
+            soa.__dict__["_qual_hist"] = np.frombuffer((C.c_uint64 * 256).from_address(out.qual_hist), dtype=np.uint64).copy()
         ok = True
         return soa
     finally:
@@ -208,6 +212,17 @@ def ref_end_native(reads: ReadsSoA, threads: int = 0) -> np.ndarray:
     return out
 
 
+def order_stats_native(reads: ReadsSoA, threads: int = 0):
+    """(ref_end, in BAM coordinate order?, longest reference span) by one threaded native pass."""
+    out = np.empty(reads.n, np.int64)
+    st = np.zeros(2, np.int64)
+    v = _view(reads)
+    rc = load().smc_soa_order_stats(C.byref(v), threads, out.ctypes.data, st.ctypes.data)
+    if rc:
+        raise RuntimeError("smc_soa_order_stats failed (%d)" % rc)
+    return out, bool(st[0]), int(st[1])
+
+
 def upload_codebook(reads: ReadsSoA, threads: int = 0) -> dict:
     """What every batch of ``reads`` is packed with (memoised on the SoA): 16-bit scalars when every value fits, the
     quality codebook (2 / 4 bits when at most 4 / 16 distinct phred values occur in the whole file)."""
@@ -215,11 +230,13 @@ def upload_codebook(reads: ReadsSoA, threads: int = 0) -> dict:
     if memo is not None:
         return memo
     lib = load()
-    hist = np.zeros(256, np.uint64)
-    v = _view(reads)
-    rc = lib.smc_soa_qual_hist(C.byref(v), threads, hist.ctypes.data)
-    if rc:
-        raise RuntimeError("smc_soa_qual_hist failed (%d)" % rc)
+    hist = reads.__dict__.get("_qual_hist")
+    if hist is None:
+        hist = np.zeros(256, np.uint64)
+        v = _view(reads)
+        rc = lib.smc_soa_qual_hist(C.byref(v), threads, hist.ctypes.data)
+        if rc:
+            raise RuntimeError("smc_soa_qual_hist failed (%d)" % rc)
     present = np.flatnonzero(hist)
     bits = 2 if len(present) <= 4 else 4 if len(present) <= 16 else 8
     lut = code_of = None

@@ -85,6 +85,7 @@ struct smc_bam {
     PodBuf<uint32_t> frag_id, cigar;
     std::vector<std::string> dict_umis;
     PodBuf<int32_t> store_lo, store_len;        // stored window per read (trim mode)
+    uint64_t qual_hist[256] = {0};              // how often every phred value occurs among the stored qualities
     int trim = 0;
     bool decoded = false;
 };
@@ -625,8 +626,14 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
     pt.lap("pass 3 numbering + offsets");
     h->seq.resize(seq_tot); h->qual.resize(qual_tot); h->cigar.resize(cig_tot);
     pt.lap("alloc payload");
-    // ---- pass 4: scalars and payloads
-    parallel_for(nrec, threads, [&](size_t a, size_t e, int) {
+    // ---- pass 4: scalars and payloads; the stored qualities are counted on the way (the upload codebook needs to know which occur)
+    std::vector<std::vector<uint64_t>> qhist((size_t)std::max(1, threads), std::vector<uint64_t>(256, 0));
+    parallel_for(nrec, threads, [&](size_t a, size_t e, int th) {
+        uint32_t hq[4][256];
+        memset(hq, 0, sizeof(hq));
+        uint64_t since = 0;
+        uint64_t* hout = qhist[(size_t)th % qhist.size()].data();
+        auto flush = [&]() { for (int c = 0; c < 256; ++c) hout[c] += (uint64_t)hq[0][c] + hq[1][c] + hq[2][c] + hq[3][c]; memset(hq, 0, sizeof(hq)); since = 0; };
         for (size_t i = a; i < e; ++i) {
             if (!info[i].keep) continue;
             const size_t o = slot[i];
@@ -647,8 +654,18 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
             if (w_len) memcpy(&h->seq[(size_t)h->seq_off[o]], sq + w_lo / 2, (w_len + 1) / 2);
             if (w_len) memcpy(&h->qual[(size_t)h->qual_off[o]], ql + w_lo, w_len);
             if (n_cig) memcpy(&h->cigar[(size_t)h->cigar_off[o]], cig, 4 * (size_t)n_cig);
+            {
+                const uint8_t* q = ql + w_lo;
+                size_t k = 0;
+                for (; k + 4 <= w_len; k += 4) { ++hq[0][q[k]]; ++hq[1][q[k + 1]]; ++hq[2][q[k + 2]]; ++hq[3][q[k + 3]]; }
+                for (; k < w_len; ++k) ++hq[0][q[k]];
+                since += w_len;
+                if (since > (1u << 30)) flush();
+            }
         }
+        flush();
     });
+    for (int c = 0; c < 256; ++c) { h->qual_hist[c] = 0; for (auto& t : qhist) h->qual_hist[c] += t[(size_t)c]; }
     pt.lap("pass 4 copy");
     out->n_reads = (int64_t)n;
     out->ref_id = h->ref_id.data(); out->pos = h->pos.data(); out->flag = h->flag.data(); out->mapq = h->mapq.data();
@@ -657,6 +674,7 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
     out->seq = h->seq.data(); out->seq_bytes = (int64_t)h->seq.size(); out->qual = h->qual.data(); out->qual_bytes = (int64_t)h->qual.size();
     out->cigar = h->cigar.data(); out->n_cigar_words = (int64_t)h->cigar.size(); out->n_dict_umis = (int64_t)h->dict_umis.size();
     out->store_lo = trim ? h->store_lo.data() : nullptr; out->store_len = trim ? h->store_len.data() : nullptr;
+    out->qual_hist = h->qual_hist;
     h->raw.alloc(0);                               // the inflated stream is not needed any more (one decode per handle)
     h->decoded = true;
     return 0;

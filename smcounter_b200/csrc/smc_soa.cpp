@@ -110,6 +110,32 @@ extern "C" int smc_soa_ref_end(const smc_soa_view* v, int threads, int64_t* ref_
     return SMC_SOA_OK;
 }
 
+extern "C" int smc_soa_order_stats(const smc_soa_view* v, int threads, int64_t* ref_end, int64_t stats[2]) {
+    if (!v || !stats || v->n_reads < 0 || (v->n_reads > 0 && !ref_end)) return SMC_SOA_E_ARG;
+    const int T = n_threads(threads);
+    std::vector<int64_t> span((size_t)T, 0);
+    std::vector<int> unsorted((size_t)T, 0);
+    par_for((size_t)v->n_reads, T, [&](size_t a, size_t e, int t) {
+        int64_t longest = 0;
+        int bad = 0;
+        for (size_t r = a; r < e; ++r) {
+            const uint32_t* c = v->cigar + v->cigar_off[r];
+            int64_t sp = 0;
+            for (int k = 0, nc = v->n_cigar[r]; k < nc; ++k) {
+                const uint32_t op = c[k] & 15u;
+                if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) sp += (int64_t)(c[k] >> 4);
+            }
+            ref_end[r] = (int64_t)v->pos[r] + sp;
+            if (sp > longest) longest = sp;
+            if (r > 0 && (v->ref_id[r] < v->ref_id[r - 1] || (v->ref_id[r] == v->ref_id[r - 1] && v->pos[r] < v->pos[r - 1]))) bad = 1;
+        }
+        span[(size_t)t] = longest; unsorted[(size_t)t] = bad;
+    });
+    stats[0] = 1; stats[1] = 0;
+    for (int t = 0; t < T; ++t) { if (unsorted[(size_t)t]) stats[0] = 0; if (span[(size_t)t] > stats[1]) stats[1] = span[(size_t)t]; }
+    return SMC_SOA_OK;
+}
+
 extern "C" int smc_soa_pack_begin(const smc_soa_view* v, const int64_t* idx, int64_t n_idx, const smc_soa_pack_opts* opts,
                                   smc_soa_pack** out, smc_soa_pack_sizes* sizes) {
     if (!v || !opts || !out || !sizes || v->n_reads < 0 || (idx && n_idx < 0)) return SMC_SOA_E_ARG;

@@ -53,15 +53,26 @@ class ReadLocator:
     def __init__(self, reads: ReadsSoA, chroms):
         self.reads = reads
         self.cidx = {c: i for i, c in enumerate(chroms)}
-        self.starts = reads.pos.astype(np.int64)
+        stats = None
+        if reads.n > (1 << 16) and reads.qual_bits == 8 and reads.scalar_bits == 32 and reads.seq_bits == 4 and reads.__dict__.get("_ref_end") is None:
+            try:                                # big plain SoAs: reference ends, order check and longest span in one native pass
+                from ._bamio import order_stats_native
+                stats = order_stats_native(reads)
+                reads.__dict__["_ref_end"] = stats[0]
+            except ImportError:
+                stats = None
+        self.starts = reads.pos                 # int32 is fine for searchsorted and comparisons
         self.ends = reads.ref_end()
-        key = (reads.ref_id.astype(np.int64) << 32) | self.starts
-        self.sorted = bool(reads.n == 0 or np.all(key[1:] >= key[:-1]))
-        self.max_span = int((self.ends - self.starts).max()) if reads.n else 0
+        if stats is not None:
+            self.sorted, self.max_span = stats[1], stats[2]
+        else:
+            key = (reads.ref_id.astype(np.int64) << 32) | self.starts.astype(np.int64)
+            self.sorted = bool(reads.n == 0 or np.all(key[1:] >= key[:-1]))
+            self.max_span = int((self.ends - self.starts).max()) if reads.n else 0
         self.block = {}
         if self.sorted and reads.n:
             rid = reads.ref_id
-            cuts = np.flatnonzero(np.diff(rid) != 0) + 1
+            cuts = np.flatnonzero(rid[1:] != rid[:-1]) + 1
             for a, b in zip(np.concatenate(([0], cuts)), np.concatenate((cuts, [reads.n]))):
                 self.block[int(rid[a])] = (int(a), int(b))
 

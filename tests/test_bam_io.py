@@ -340,3 +340,22 @@ def test_own_inflate_under_address_sanitizer(tmp_path):
     r = subprocess.run([exe, str(tmp_path / "cases.bin")], capture_output=True, text=True)
     assert r.returncode == 0 and "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stdout[-500:] + r.stderr[-2000:]
     assert ("%d cases" % n) in r.stdout and " 0 wrong" in r.stdout
+
+
+@pytest.mark.skipif(len(_decoders()) < 2, reason="libsmc_bamio.so not built")
+def test_native_decoder_counts_the_stored_qualities(tmp_path):
+    """smc_bam_reads.qual_hist (counted during the copy pass) == a histogram of the decoded qual[] -- with and without trimming,
+    any thread count -- and the upload codebook built from it equals the one from smc_soa_qual_hist."""
+    from smcounter_b200 import _bamio
+    s, refs, ivs = _panel(seed=21)
+    path = str(tmp_path / "q.bam")
+    bam.write_bam(path, s, refs.lengths)
+    for trim in (False, True):
+        for threads in (1, 4):
+            r = bam.read_bam(path, intervals=ivs, native=True, threads=threads, trim=trim)
+            h = r.__dict__["_qual_hist"]
+            assert np.array_equal(h, np.bincount(r.qual, minlength=256).astype(np.uint64))
+            cb = dict(_bamio.upload_codebook(r))
+            r.__dict__.pop("_qual_hist"); r.__dict__.pop("_upload_codebook")
+            cb2 = _bamio.upload_codebook(r)
+            assert cb["qual_bits"] == cb2["qual_bits"] and np.array_equal(cb["qual_lut"], cb2["qual_lut"]) and np.array_equal(cb["code_of"], cb2["code_of"])

@@ -556,3 +556,28 @@ def test_native_batch_packer_equals_select_plus_compact():
     import pytest
     with pytest.raises(RuntimeError):
         _bamio.pack_upload(plain, np.array([3, 2], np.int64))
+
+
+def test_native_order_stats_equal_numpy():
+    """smc_soa_order_stats (include/smc_soa.h): reference ends, coordinate-order check and longest span of the interval locator."""
+    import numpy as np
+    from smcounter_b200 import _bamio
+    from smcounter_b200.shard import ReadLocator
+    from smcounter_b200.synth import SynthSpec, make_panel
+    ivs = [("chr1", 1000, 1300), ("chr2", 200, 420)]
+    soa, _, _ = make_panel(ivs, SynthSpec(umis_per_locus=20, rpb=2.0, indel_every=40, indel_vaf=0.3, softclip_frac=0.3), seed=2)
+    soa = soa.repack()
+    ends, is_sorted, span = _bamio.order_stats_native(soa, threads=3)
+    want = soa._ref_end_compute()
+    assert np.array_equal(ends, want) and is_sorted and span == int((want - soa.pos).max())
+    loc = ReadLocator(soa, soa.chroms)
+    assert loc.sorted and loc.max_span == span
+    # out of order: swap two reads
+    perm = np.arange(soa.n)
+    perm[[5, 50]] = perm[[50, 5]]
+    shuffled = soa.select(np.sort(perm))             # select() keeps order: build the disorder by hand on pos instead
+    shuffled.pos = shuffled.pos.copy()
+    shuffled.pos[7] = shuffled.pos[6] - 1 if shuffled.ref_id[7] == shuffled.ref_id[6] else shuffled.pos[7]
+    _, is_sorted2, _ = _bamio.order_stats_native(shuffled, threads=2)
+    key = (shuffled.ref_id.astype(np.int64) << 32) | shuffled.pos.astype(np.int64)
+    assert is_sorted2 == bool(np.all(key[1:] >= key[:-1]))
