@@ -359,3 +359,119 @@ def test_native_decoder_counts_the_stored_qualities(tmp_path):
             r.__dict__.pop("_qual_hist"); r.__dict__.pop("_upload_codebook")
             cb2 = _bamio.upload_codebook(r)
             assert cb["qual_bits"] == cb2["qual_bits"] and np.array_equal(cb["qual_lut"], cb2["qual_lut"]) and np.array_equal(cb["code_of"], cb2["code_of"])
+
+
+def _random_code_lengths(rng, n_symbols_used, alphabet, must_have=(), deep=False):
+    """Lengths (<= 15) of a COMPLETE prefix code over ``n_symbols_used`` random symbols of ``alphabet`` (others 0)."""
+    leaves = [0]
+    while len(leaves) < n_symbols_used:
+        cand = [i for i, d in enumerate(leaves) if d < 15]
+        i = (max(cand, key=lambda k: leaves[k]) if deep and rng.random() < 0.8 else int(rng.choice(cand)))
+        d = leaves.pop(i)
+        leaves += [d + 1, d + 1]
+    syms = list(must_have) + [int(x) for x in rng.permutation([s for s in range(alphabet) if s not in must_have])][:n_symbols_used - len(must_have)]
+    lens = [0] * alphabet
+    for s, d in zip(rng.permutation(syms), leaves):
+        lens[int(s)] = max(d, 1)
+    return lens
+
+
+def _canonical_codes(lens):
+    count = [0] * 16
+    for l in lens:
+        count[l] += 1
+    count[0] = 0
+    code, nxt = 0, [0] * 16
+    for l in range(1, 16):
+        code = (code + count[l - 1]) << 1
+        nxt[l] = code
+    out = {}
+    for s, l in enumerate(lens):
+        if l:
+            out[s] = (nxt[l], l)
+            nxt[l] += 1
+    return out
+
+
+class _BitWriter:
+    def __init__(self):
+        self.acc, self.n, self.out = 0, 0, bytearray()
+
+    def bits(self, value, nbits):                 # LSB first
+        self.acc |= value << self.n
+        self.n += nbits
+        while self.n >= 8:
+            self.out.append(self.acc & 255)
+            self.acc >>= 8
+            self.n -= 8
+
+    def code(self, cl):                           # Huffman codes go in MSB first
+        c, l = cl
+        self.bits(int(format(c, "0%db" % l)[::-1], 2), l)
+
+    def done(self):
+        if self.n:
+            self.out.append(self.acc & 255)
+        return bytes(self.out)
+
+
+@pytest.mark.skipif(len(_decoders()) < 2, reason="libsmc_bamio.so not built")
+def test_own_inflate_on_hand_made_dynamic_blocks():
+    """Dynamic-Huffman blocks written bit by bit with RANDOM complete codes -- code lengths up to 15 on both alphabets (the
+    secondary tables of the decoder), single-code distance alphabets, every length / distance symbol with its extra bits --
+    decoded by zlib (which validates the encoder) and by csrc/smc_inflate.h."""
+    import zlib
+    LEN_BASE = [3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258]
+    LEN_EXTRA = [0] * 8 + [1] * 4 + [2] * 4 + [3] * 4 + [4] * 4 + [5] * 4 + [0]
+    DIST_BASE = [1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577]
+    DIST_EXTRA = [0, 0, 0, 0] + [k for k in range(1, 14) for _ in (0, 1)]
+    ORDER = [16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15]
+    rng = np.random.default_rng(31)
+    deepest = 0
+    for case in range(120):
+        deep = case % 2 == 0
+        n_lit = int(rng.integers(2, 286))
+        lit_lens = _random_code_lengths(rng, n_lit, 286, must_have=(256,), deep=deep)
+        n_dist = int(rng.integers(1, 31))
+        dist_lens = _random_code_lengths(rng, n_dist, 30, deep=deep) if n_dist > 1 else [0] * 30
+        if n_dist == 1:
+            dist_lens[int(rng.integers(0, 30))] = 1                      # one distance code: the incomplete code RFC 1951 allows
+        deepest = max(deepest, max(lit_lens), max(dist_lens))
+        lit_codes, dist_codes = _canonical_codes(lit_lens), _canonical_codes(dist_lens)
+        pre_lens = [0] * 19
+        for k, s in enumerate(rng.permutation(19)):
+            pre_lens[int(s)] = 4 if k < 13 else 5                        # 13/16 + 6/32 = 1: complete
+        pre_codes = _canonical_codes(pre_lens)
+        w = _BitWriter()
+        w.bits(1, 1); w.bits(2, 2)
+        w.bits(286 - 257, 5); w.bits(30 - 1, 5); w.bits(19 - 4, 4)
+        for s in ORDER:
+            w.bits(pre_lens[s], 3)
+        for l in lit_lens + dist_lens:
+            w.code(pre_codes[l])
+        out = bytearray()
+        lits = [s for s in lit_codes if s < 256]
+        lens_syms = [s for s in lit_codes if s > 256]
+        dsyms = list(dist_codes)
+        for step in range(int(rng.integers(1, 400))):
+            can_match = lens_syms and len(out) > 0 and any(DIST_BASE[d] <= len(out) for d in dsyms)
+            if lits and (not can_match or rng.random() < 0.5):
+                s = int(rng.choice(lits))
+                w.code(lit_codes[s]); out.append(s)
+            elif can_match:
+                ls = int(rng.choice(lens_syms))
+                ds = int(rng.choice([d for d in dsyms if DIST_BASE[d] <= len(out)]))
+                le = int(rng.integers(0, 1 << LEN_EXTRA[ls - 257])) if LEN_EXTRA[ls - 257] else 0
+                dmax = min((1 << DIST_EXTRA[ds]) - 1, len(out) - DIST_BASE[ds])
+                de = int(rng.integers(0, dmax + 1))
+                length, dist = LEN_BASE[ls - 257] + le, DIST_BASE[ds] + de
+                w.code(lit_codes[ls]); w.bits(le, LEN_EXTRA[ls - 257])
+                w.code(dist_codes[ds]); w.bits(de, DIST_EXTRA[ds])
+                for _ in range(length):
+                    out.append(out[-dist])
+        w.code(lit_codes[256])
+        stream = w.done()
+        assert zlib.decompress(stream, -15) == bytes(out), "the test's encoder is wrong"
+        rc, got = _native_inflate(stream, len(out))
+        assert rc == 0 and got == bytes(out), case
+    assert deepest == 15
