@@ -405,9 +405,12 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
     const size_t nrec = offs.size();
     pt.lap("pass 1 boundaries");
     // ---- pass 2: fields, filter, identity hash
-    std::vector<RecInfo> info(nrec);
+    PodBuf<RecInfo> info; info.resize(nrec);          // not zero-filled: pass 2 writes keep for every record, the rest for kept ones
     std::atomic<size_t> bad_rec(SIZE_MAX);
+    std::atomic<size_t> n_kept(0);
     parallel_for(nrec, threads, [&](size_t a, size_t e, int) {
+        size_t kept_here = 0;
+        struct AddKept { std::atomic<size_t>& tot; size_t& k; ~AddKept() { tot += k; } } add_kept{n_kept, kept_here};
         for (size_t i = a; i < e; ++i) {
             RecInfo& R = info[i];
             R.keep = 0;
@@ -477,25 +480,25 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
             hash_bytes(reinterpret_cast<const uint8_t*>(qname), R.rid_len, h1, h2);
             R.h1 = h1; R.h2 = h2;
             R.keep = 1;
+            ++kept_here;
         }
     });
     pt.lap("pass 2 fields + hash");
     if (bad_rec.load() != SIZE_MAX) { h->err = "malformed BAM record (field lengths exceed block_size)"; return -1; }
     // ---- pass 3: output slots, payload offsets, fragment ids, barcode dictionary
-    std::vector<uint32_t> slot(nrec);
-    size_t n = 0, seq_tot = 0, qual_tot = 0, cig_tot = 0;
-    for (size_t i = 0; i < nrec; ++i) if (info[i].keep) ++n;
+    PodBuf<uint32_t> slot; slot.resize(nrec);         // written for every kept record before it is read
+    size_t n = n_kept.load(), seq_tot = 0, qual_tot = 0, cig_tot = 0;
     if (n >= (1ull << 31)) { h->err = "more than 2^31 reads"; return -1; }
     h->ref_id.resize(n); h->pos.resize(n); h->nm.resize(n); h->l_seq.resize(n); h->flag.resize(n); h->n_cigar.resize(n);
     h->mapq.resize(n); h->seq_off.resize(n); h->qual_off.resize(n); h->cigar_off.resize(n); h->umi.resize(n); h->frag_id.resize(n);
     h->dict_umis.clear();
-    h->store_lo.assign(trim ? n : 0, 0); h->store_len.assign(trim ? n : 0, 0);
+    h->store_lo.resize(trim ? n : 0); h->store_len.resize(trim ? n : 0);          // pass 4 writes every entry
     // fragment ids = first-appearance numbers of the (barcode, readid) identities.  Threads own disjoint hash partitions:
     // each walks the records in order, keeps its identities in its own open-addressing table and notes, per record, the
     // FIRST record of that identity (hits verified on the name bytes).  A prefix sum over "is a first record" then numbers
     // the identities in order of first appearance -- the same ids the sequential dictionary would hand out.
     pt.lap("alloc outputs");
-    std::vector<uint32_t> first_rec(nrec);
+    PodBuf<uint32_t> first_rec; first_rec.resize(nrec);
     {
         auto same_identity = [&](size_t i, size_t j) {
             const RecInfo& A = info[i]; const RecInfo& B = info[j];
@@ -588,7 +591,7 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
             base[t + 1].qual += base[t].qual; base[t + 1].cig += base[t].cig;
         }
         seq_tot = base[T].seq; qual_tot = base[T].qual; cig_tot = base[T].cig;
-        std::vector<uint32_t> id_of(nrec);                                       // id of the identity whose first record is i
+        PodBuf<uint32_t> id_of; id_of.resize(nrec);                              // id of the identity whose first record is i
         run([&](int t) {
             size_t a, e; range(t, a, e);
             Tot s = base[t];
@@ -603,7 +606,12 @@ extern "C" int smc_bam_decode(smc_bam* h, int64_t n_iv, const int32_t* iv_ref, c
         });
         // barcodes that do not pack into 64 bits get dictionary codes in order of first appearance (rare: sequential)
         std::unordered_map<std::string, uint64_t> umi_dict;
-        for (size_t i = 0; i < nrec; ++i) {
+        std::atomic<int> any_dict(0);
+        run([&](int t) {
+            size_t a, e; range(t, a, e);
+            for (size_t i = a; i < e; ++i) if (info[i].keep && info[i].code == 0) { any_dict = 1; break; }
+        });
+        for (size_t i = 0; any_dict.load() && i < nrec; ++i) {
             RecInfo& R = info[i];
             if (!R.keep || R.code != 0) continue;
             const std::string bc(reinterpret_cast<const char*>(&r[offs[i] + 4 + 32]) + R.bc_off, R.bc_len);
