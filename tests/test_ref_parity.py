@@ -154,9 +154,13 @@ def test_native_order_containers_differ_only_in_tie_breaks():
         xf, yf = x[1].split("\t"), y[1].split("\t")
         cols = {orc.headerAll[i] for i in range(45) if xf[i] != yf[i]}
         assert cols <= ALT_COLS, cols
-        if cols:
+        if cols and "ALT" not in cols:
+            # the plain containers iterate in the order of this process's string hashes (PYTHONHASHSEED): the reference's float
+            # sum over the barcodes can then land one ulp away and print another last digit of PI -- nothing else may move
+            assert cols <= {"PI"}, cols
+        elif cols:
             n_diff += 1
-            tied = [k for k, v in x[2]["PI"].items() if v == x[2]["altPI"]]
+            tied = [k for k, v in x[2]["PI"].items() if abs(v - x[2]["altPI"]) <= 1e-12 * max(abs(v), abs(x[2]["altPI"]), 1e-300)]
             assert len(tied) >= 2
     assert 0 < n_diff < len(a)
 
