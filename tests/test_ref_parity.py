@@ -162,7 +162,8 @@ def test_native_order_containers_differ_only_in_tie_breaks():
             n_diff += 1
             tied = [k for k, v in x[2]["PI"].items() if abs(v - x[2]["altPI"]) <= 1e-12 * max(abs(v), abs(x[2]["altPI"]), 1e-300)]
             assert len(tied) >= 2
-    assert 0 < n_diff < len(a)
+    print("rows whose ALT differs between the container flavours:", n_diff, "of", len(a))
+    assert n_diff < len(a)            # how many ties fall the other way depends on this process's string hashes (0 .. most)
 
 
 # ---------------------------------------------------------------------------------------------- calProb
