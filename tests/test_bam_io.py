@@ -475,3 +475,28 @@ def test_own_inflate_on_hand_made_dynamic_blocks():
         rc, got = _native_inflate(stream, len(out))
         assert rc == 0 and got == bytes(out), case
     assert deepest == 15
+
+
+@pytest.mark.skipif(len(_decoders()) < 2, reason="libsmc_bamio.so not built")
+def test_dictionary_coded_barcodes_native_equals_python(tmp_path):
+    """Barcodes that do not pack into 64 bits (an 'N', more than 31 nt) get dictionary codes in order of first appearance: the
+    C++ decoder (whose dictionary pass runs only when such a barcode exists) and the Python walker must agree, and a file
+    without any such barcode must come out without a dictionary."""
+    from smcounter_b200.soa import umi_string
+    s, refs, ivs = _panel(seed=17)
+    odd = {3: "ACGTNACGTACG", 11: "A" * 40, 12: "ACGTNACGTACG", 30: "TTTTGGGGNNNN"}
+
+    def qname(i, fid, bc):
+        return "M1:F%d:%s:%d" % (fid, odd.get(i % 40, bc), 1)
+    for fn, expect_dict in ((qname, True), (None, False)):
+        path = str(tmp_path / ("d%d.bam" % expect_dict))
+        bam.write_bam(path, s, refs.lengths, qname_fn=fn)
+        a = bam.read_bam(path, native=True, threads=3)
+        b = bam.read_bam(path, native=False)
+        assert a.n == b.n
+        for f in FIELDS:
+            assert np.array_equal(getattr(a, f), getattr(b, f)), f
+        da, db = ({k: v for k, v in x.umi_names.items() if k >> 63} for x in (a, b))      # the Python walker also names the packed codes
+        assert da == db and bool(da) == expect_dict
+        if expect_dict:
+            assert {umi_string(int(c), a.umi_names) for c in a.umi.tolist() if c >> 63} == {"ACGTNACGTACG", "A" * 40, "TTTTGGGGNNNN"}
