@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <thread>
 #include <vector>
@@ -55,7 +56,7 @@ struct smc_soa_pack {
     int64_t n;
     smc_soa_pack_opts o;
     int threads;
-    std::vector<int64_t> seq_off, qual_off, cig_off;       // n + 1 each: offsets inside the packed arrays
+    std::unique_ptr<int64_t[]> seq_off, qual_off, cig_off; // n + 1 each: offsets inside the packed arrays (not zero-filled)
     uint32_t frag_lo = 0;
     std::vector<uint32_t> frag_rank;                       // rank of parent id frag_lo + i among the ids of the batch
     std::vector<uint16_t> qpair;                           // quality pair (q0 | q1 << 8) -> its two codes (c0 | c1 << qual_bits), bit 15: no code
@@ -149,7 +150,8 @@ extern "C" int smc_soa_pack_begin(const smc_soa_view* v, const int64_t* idx, int
     const int64_t n = h->n;
     PhaseTimer pt;
     try {
-        h->seq_off.assign((size_t)n + 1, 0); h->qual_off.assign((size_t)n + 1, 0); h->cig_off.assign((size_t)n + 1, 0);
+        h->seq_off.reset(new int64_t[(size_t)n + 1]); h->qual_off.reset(new int64_t[(size_t)n + 1]); h->cig_off.reset(new int64_t[(size_t)n + 1]);
+        h->seq_off[0] = h->qual_off[0] = h->cig_off[0] = 0;      // the sizes pass writes every other entry
     } catch (...) { delete h; return SMC_SOA_E_MEM; }
     const int T = h->threads;
     const int qb = opts->qual_bits, sb = opts->seq_bits;
